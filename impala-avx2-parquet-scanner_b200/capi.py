@@ -1,0 +1,281 @@
+"""ctypes binding of the C ABI in include/fle_b200.h (libfle_b200.so).
+
+This is the Python-side twin of the cgo/JNI-style stub INTEGRATION.md shows for the
+reference's C++ tree: plain pointers and sizes only.  torch is used purely as a provider
+of device memory and streams (tensor.data_ptr(), torch.cuda.current_stream()).
+
+There is NO fallback: if the shared library is missing or no B200 is present, loading or
+context creation raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Iterable, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfle_b200.so")
+
+# opcodes (fle_b200.h)
+EQ, LT, LE, GT, GE, IN, AND, OR, ALL, NONE = range(10)
+OK, E_INVALID, E_NOMEM, E_CUDA, E_BUFFER, E_ALIGN, E_UNSUPPORTED, E_NODEVICE = 0, -1, -2, -3, -4, -5, -6, -7
+
+EXPORTS = [
+    "fle_ctx_create", "fle_ctx_destroy", "fle_ctx_set_stream", "fle_ctx_sync", "fle_ctx_set_option",
+    "fle_ctx_get_option", "fle_ctx_launch_count", "fle_last_error", "fle_strerror", "fle_version",
+    "fle_device_count", "fle_host_alloc", "fle_host_free", "fle_dev_alloc", "fle_dev_free", "fle_h2d",
+    "fle_d2h", "fle_encoded_bytes", "fle_pack_u32", "fle_pack_u32_dev", "fle_unpack_u32",
+    "fle_unpack_u32_dev", "fle_eval", "fle_eval_dev", "fle_bitmap_count_dev", "fle_intersect_bitset",
+    "fle_intersect_bitset_dev",
+]
+
+
+class FleError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"fle_b200 error {code}: {msg}")
+        self.code = code
+
+
+class ColDesc(C.Structure):
+    _fields_ = [("planes", C.c_void_p), ("bytes", C.c_uint64), ("bit_width", C.c_int32),
+                ("max_def_level", C.c_int32), ("def_planes", C.c_void_p), ("def_bytes", C.c_uint64)]
+
+
+class PredNode(C.Structure):
+    _fields_ = [("op", C.c_int32), ("col", C.c_int32), ("code", C.c_uint64),
+                ("codes", C.POINTER(C.c_uint64)), ("ncodes", C.c_int32), ("reserved", C.c_int32)]
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen libfle_b200.so and declare every prototype.  Raises if it was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "fle_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i64, u64p, i32 = C.c_void_p, C.c_int64, C.POINTER(C.c_uint64), C.c_int
+    L.fle_ctx_create.argtypes = [i32, vp, C.POINTER(vp)]
+    L.fle_ctx_destroy.argtypes = [vp]
+    L.fle_ctx_set_stream.argtypes = [vp, vp]
+    L.fle_ctx_sync.argtypes = [vp]
+    L.fle_ctx_set_option.argtypes = [vp, C.c_char_p, i64]
+    L.fle_ctx_get_option.argtypes = [vp, C.c_char_p]
+    L.fle_ctx_get_option.restype = i64
+    L.fle_ctx_launch_count.argtypes = [vp]
+    L.fle_ctx_launch_count.restype = i64
+    L.fle_last_error.argtypes = [vp]
+    L.fle_last_error.restype = C.c_char_p
+    L.fle_strerror.argtypes = [i32]
+    L.fle_strerror.restype = C.c_char_p
+    L.fle_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.fle_host_free.argtypes = [vp]
+    L.fle_dev_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    L.fle_dev_free.argtypes = [vp, vp]
+    L.fle_h2d.argtypes = [vp, vp, vp, C.c_size_t]
+    L.fle_d2h.argtypes = [vp, vp, vp, C.c_size_t]
+    L.fle_encoded_bytes.argtypes = [i64, i32]
+    L.fle_encoded_bytes.restype = C.c_size_t
+    for f in (L.fle_pack_u32, L.fle_pack_u32_dev):
+        f.argtypes = [vp, vp, i64, i32, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    for f in (L.fle_unpack_u32, L.fle_unpack_u32_dev):
+        f.argtypes = [vp, vp, C.c_size_t, i32, i64, i64, vp]
+    for f in (L.fle_eval, L.fle_eval_dev):
+        f.argtypes = [vp, C.POINTER(ColDesc), i32, C.POINTER(PredNode), i32, i64, i64, vp, vp]
+    L.fle_bitmap_count_dev.argtypes = [vp, vp, i64, vp]
+    for f in (L.fle_intersect_bitset, L.fle_intersect_bitset_dev):
+        f.argtypes = [vp, vp, i64, vp, i64]
+    _lib = L
+    return L
+
+
+def _build_program(program: Sequence[tuple]):
+    """program: postfix list of (op, col, literal_or_list).  Returns (PredNode array, keepalive)."""
+    nodes = (PredNode * len(program))()
+    keep = []
+    for i, item in enumerate(program):
+        op = int(item[0])
+        col = item[1] if len(item) > 1 and item[1] is not None else 0
+        lit = item[2] if len(item) > 2 else None
+        nodes[i].op = op
+        nodes[i].col = int(col)
+        if op == IN:
+            arr = np.ascontiguousarray(np.atleast_1d(np.asarray(lit if lit is not None else [], dtype=np.uint64)))
+            keep.append(arr)
+            nodes[i].codes = arr.ctypes.data_as(C.POINTER(C.c_uint64)) if len(arr) else None
+            nodes[i].ncodes = len(arr)
+        elif op <= GE:
+            nodes[i].code = int(np.atleast_1d(lit)[0]) if lit is not None else 0
+    return nodes, keep
+
+
+class FleContext:
+    """One scanner thread's handle: a CUDA stream plus the library's device scratch."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        """stream: a cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream); 0 means the
+        legacy default stream (passed to the library as cudaStreamLegacy); None lets the library
+        create its own non-blocking stream."""
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.fle_ctx_create(device, self._stream_arg(stream), C.byref(h))
+        if rc != OK:
+            raise FleError(rc, self.lib.fle_strerror(rc).decode())
+        self.h = h
+        self.device = device
+
+    @staticmethod
+    def _stream_arg(stream):
+        if stream is None:
+            return None
+        return C.c_void_p(stream if stream else 0x1)  # 0x1 == cudaStreamLegacy
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.fle_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != OK:
+            raise FleError(rc, f"{self.lib.fle_strerror(rc).decode()}: {self.lib.fle_last_error(self.h).decode()}")
+
+    # -- context ---------------------------------------------------------------------
+    def set_stream(self, stream: int | None):
+        self._check(self.lib.fle_ctx_set_stream(self.h, self._stream_arg(stream)))
+
+    def sync(self):
+        self._check(self.lib.fle_ctx_sync(self.h))
+
+    def set_option(self, name: str, value: int):
+        self._check(self.lib.fle_ctx_set_option(self.h, name.encode(), int(value)))
+
+    def get_option(self, name: str) -> int:
+        return int(self.lib.fle_ctx_get_option(self.h, name.encode()))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.fle_ctx_launch_count(self.h))
+
+    def encoded_bytes(self, n: int, bw: int) -> int:
+        return int(self.lib.fle_encoded_bytes(n, bw))
+
+    # -- host-buffer entry points (numpy) -------------------------------------------------
+    def pack(self, vals: np.ndarray, bw: int) -> np.ndarray:
+        vals = np.ascontiguousarray(vals, dtype=np.uint32)
+        out = np.empty(self.encoded_bytes(len(vals), bw) // 8, dtype=np.uint64)
+        ln = C.c_size_t(0)
+        self._check(self.lib.fle_pack_u32(self.h, vals.ctypes.data, len(vals), bw, out.ctypes.data, out.nbytes, C.byref(ln)))
+        assert ln.value == out.nbytes
+        return out
+
+    def unpack(self, words: np.ndarray, bw: int, first_row: int, n: int) -> np.ndarray:
+        words = np.ascontiguousarray(words)
+        out = np.empty(n, dtype=np.uint32)
+        self._check(self.lib.fle_unpack_u32(self.h, words.ctypes.data, words.nbytes, bw, first_row, n, out.ctypes.data))
+        return out
+
+    def eval(self, cols: Sequence, program: Sequence[tuple], n: int, first_row: int = 0):
+        """cols: list of (words ndarray, bw) or (words, bw, def_words) for nullable columns.
+        Returns (bitmap uint64 ndarray, match_count)."""
+        descs = (ColDesc * len(cols))()
+        keep = []
+        for i, c in enumerate(cols):
+            w = np.ascontiguousarray(c[0])
+            keep.append(w)
+            descs[i].planes = w.ctypes.data
+            descs[i].bytes = w.nbytes
+            descs[i].bit_width = int(c[1])
+            if len(c) > 2 and c[2] is not None:
+                d = np.ascontiguousarray(c[2])
+                keep.append(d)
+                descs[i].max_def_level = 1
+                descs[i].def_planes = d.ctypes.data
+                descs[i].def_bytes = d.nbytes
+        nodes, keep2 = _build_program(program)
+        bm = np.zeros((n + 63) // 64, dtype=np.uint64)
+        cnt = C.c_uint64(0)
+        self._check(self.lib.fle_eval(self.h, descs, len(cols), nodes, len(program), first_row, n,
+                                      bm.ctypes.data if len(bm) else None, C.byref(cnt)))
+        return bm, int(cnt.value)
+
+    def intersect_bitset(self, root: np.ndarray, n_root: int, sub: np.ndarray, n_sub: int) -> np.ndarray:
+        r = np.array(root, dtype=np.uint64, copy=True)
+        s = np.ascontiguousarray(sub, dtype=np.uint64)
+        self._check(self.lib.fle_intersect_bitset(self.h, r.ctypes.data, n_root, s.ctypes.data if len(s) else None, n_sub))
+        return r
+
+    # -- device entry points (torch tensors as memory) --------------------------------------
+    def pack_dev(self, vals, bw: int, out=None):
+        """vals: torch int32/uint32-compatible CUDA tensor (4-byte elements).  Returns an int64
+        CUDA tensor of plane words."""
+        import torch
+        n = vals.numel()
+        nbytes = self.encoded_bytes(n, bw)
+        if out is None:
+            out = torch.empty(nbytes // 8, dtype=torch.int64, device=vals.device)
+        ln = C.c_size_t(0)
+        self._check(self.lib.fle_pack_u32_dev(self.h, vals.data_ptr(), n, bw, out.data_ptr(), out.numel() * 8, C.byref(ln)))
+        return out
+
+    def unpack_dev(self, words, bw: int, first_row: int, n: int, out=None):
+        import torch
+        if out is None:
+            out = torch.empty(n, dtype=torch.int32, device=words.device)
+        self._check(self.lib.fle_unpack_u32_dev(self.h, words.data_ptr(), words.numel() * words.element_size(), bw,
+                                                first_row, n, out.data_ptr()))
+        return out
+
+    def make_col_descs(self, cols: Sequence):
+        descs = (ColDesc * len(cols))()
+        for i, c in enumerate(cols):
+            w = c[0]
+            descs[i].planes = w.data_ptr()
+            descs[i].bytes = w.numel() * w.element_size()
+            descs[i].bit_width = int(c[1])
+            if len(c) > 2 and c[2] is not None:
+                d = c[2]
+                descs[i].max_def_level = 1
+                descs[i].def_planes = d.data_ptr()
+                descs[i].def_bytes = d.numel() * d.element_size()
+        return descs
+
+    def eval_dev(self, cols: Sequence, program: Sequence[tuple], n: int, first_row: int = 0, bitmap=None, count=None,
+                 prepared=None):
+        """cols: list of (int64 CUDA tensor of plane words, bw[, def-level words]).  Enqueues on the
+        context's stream; returns (bitmap int64 tensor, count int64 tensor[1])."""
+        import torch
+        dev = cols[0][0].device
+        if bitmap is None:
+            bitmap = torch.empty(max(1, (n + 63) // 64), dtype=torch.int64, device=dev)
+        if count is None:
+            count = torch.zeros(1, dtype=torch.int64, device=dev)
+        if prepared is None:
+            prepared = (self.make_col_descs(cols),) + _build_program(program)
+        descs, nodes, _keep = prepared
+        self._check(self.lib.fle_eval_dev(self.h, descs, len(cols), nodes, len(nodes), first_row, n,
+                                          bitmap.data_ptr(), count.data_ptr()))
+        return bitmap, count
+
+    def bitmap_count_dev(self, bitmap, nbits: int, count=None):
+        import torch
+        if count is None:
+            count = torch.zeros(1, dtype=torch.int64, device=bitmap.device)
+        self._check(self.lib.fle_bitmap_count_dev(self.h, bitmap.data_ptr(), nbits, count.data_ptr()))
+        return count
+
+    def intersect_bitset_dev(self, root, n_root: int, sub, n_sub: int):
+        self._check(self.lib.fle_intersect_bitset_dev(self.h, root.data_ptr(), n_root, sub.data_ptr(), n_sub))
+        return root

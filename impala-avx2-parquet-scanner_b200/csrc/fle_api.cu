@@ -1,0 +1,661 @@
+// extern "C" surface of libfle_b200.so (see include/fle_b200.h): contexts, memory helpers,
+// the host-buffer entry points (H2D / D2H inside the call, chunked and overlapped with the
+// kernels) and the device-pointer entry points.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "fle_internal.h"
+
+namespace fle {
+
+int set_error(fle_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->last_error = msg;
+  return code;
+}
+
+int set_cuda_error(fle_ctx* ctx, cudaError_t e, const char* what) {
+  if (ctx) ctx->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return FLE_E_NODEVICE;
+  if (e == cudaErrorMemoryAllocation) return FLE_E_NOMEM;
+  return FLE_E_CUDA;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) {
+      switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
+int ensure_scratch(fle_ctx* ctx, int nblocks, int n_in_lits) {
+  if (nblocks > ctx->partial_cap) {
+    const int cap = std::max(nblocks, 4096);
+    uint64_t* p = nullptr;
+    FLE_CUDA_TRY(ctx, cudaMalloc(&p, (size_t)cap * 8));
+    if (ctx->d_partial) {
+      FLE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      cudaFree(ctx->d_partial);
+    }
+    ctx->d_partial = p;
+    ctx->partial_cap = cap;
+  }
+  if (n_in_lits > ctx->in_lits_cap) {
+    const int cap = std::max(n_in_lits, 4096);
+    uint32_t *d = nullptr, *h = nullptr;
+    FLE_CUDA_TRY(ctx, cudaMalloc(&d, (size_t)cap * 4));
+    FLE_CUDA_TRY(ctx, cudaMallocHost(&h, (size_t)cap * 4));
+    if (ctx->d_in_lits) {
+      FLE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      cudaFree(ctx->d_in_lits);
+      cudaFreeHost(ctx->h_in_lits);
+    }
+    ctx->d_in_lits = d;
+    ctx->h_in_lits = h;
+    ctx->in_lits_cap = cap;
+  }
+  return FLE_OK;
+}
+
+static int ensure_stage(fle_ctx* ctx, int idx, size_t bytes) {
+  if (bytes <= ctx->d_stage_cap[idx]) return FLE_OK;
+  if (ctx->d_stage[idx]) {
+    FLE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_stage[idx]);
+    ctx->d_stage[idx] = nullptr;
+    ctx->d_stage_cap[idx] = 0;
+  }
+  FLE_CUDA_TRY(ctx, cudaMalloc(&ctx->d_stage[idx], bytes));
+  ctx->d_stage_cap[idx] = bytes;
+  return FLE_OK;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------
+// nullable columns (hdfs-parquet-scanner.cc:333-445): per leaf
+//   notnull = def_levels.Eq(n, max_def_level)
+//   data    = dict.Op(popcount(notnull), literal)        (indexed by non-null ordinal)
+//   leaf    = IntersectBitset(notnull, data)
+// When no column actually contains a NULL the deposit is the identity and the columns are
+// evaluated by the fused kernel as if they were required.
+// ------------------------------------------------------------------------------------------
+static int eval_dev_nullable(fle_ctx* ctx, const fle_col_desc* cols, int ncols,
+                             const fle_pred_node* nodes, int nnodes, int64_t first_row, int64_t n,
+                             uint64_t* bitmap_dev, uint64_t* count_dev) {
+  if (first_row != 0)
+    return set_error(ctx, FLE_E_UNSUPPORTED, "nullable columns are evaluated from row 0 of the page");
+  const int64_t nwords = (n + 63) / 64;
+  if (nwords == 0) {
+    if (count_dev) FLE_CUDA_TRY(ctx, cudaMemsetAsync(count_dev, 0, 8, ctx->stream));
+    return FLE_OK;
+  }
+  // 1. not-null bitmaps + their popcounts
+  std::vector<uint64_t*> notnull(ncols, nullptr);
+  std::vector<uint64_t*> tmp;  // everything to free
+  uint64_t* d_counts = nullptr;
+  FLE_CUDA_TRY(ctx, cudaMallocAsync(&d_counts, (size_t)ncols * 8, ctx->stream));
+  tmp.push_back(d_counts);
+  auto cleanup = [&]() {
+    for (uint64_t* p : tmp) cudaFreeAsync(p, ctx->stream);
+  };
+  int rc = FLE_OK;
+  for (int c = 0; c < ncols && rc == FLE_OK; ++c) {
+    if (cols[c].max_def_level == 0) continue;
+    if (cols[c].max_def_level != 1) { rc = set_error(ctx, FLE_E_UNSUPPORTED, "max_def_level > 1 (nested types)"); break; }
+    if (!cols[c].def_planes) { rc = set_error(ctx, FLE_E_INVALID, "nullable column without def_planes"); break; }
+    cudaError_t e = cudaMallocAsync(&notnull[c], (size_t)nwords * 8, ctx->stream);
+    if (e != cudaSuccess) { rc = set_cuda_error(ctx, e, "cudaMallocAsync(notnull)"); break; }
+    tmp.push_back(notnull[c]);
+    fle_col_desc dc{cols[c].def_planes, cols[c].def_bytes, 1, 0, nullptr, 0};
+    fle_pred_node leaf{FLE_OP_EQ, 0, (uint64_t)cols[c].max_def_level, nullptr, 0, 0};
+    rc = launch_eval(ctx, &dc, 1, &leaf, 1, 0, n, notnull[c], d_counts + c);
+  }
+  if (rc != FLE_OK) { cleanup(); return rc; }
+  std::vector<uint64_t> h_counts(ncols, 0);
+  FLE_CUDA_TRY(ctx, cudaMemcpyAsync(h_counts.data(), d_counts, (size_t)ncols * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  FLE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  bool any_null = false;
+  for (int c = 0; c < ncols; ++c)
+    if (cols[c].max_def_level != 0 && (int64_t)h_counts[c] != n) any_null = true;
+
+  if (!any_null) {
+    // 2a. no NULL anywhere: data ordinal == row index
+    std::vector<fle_col_desc> req(cols, cols + ncols);
+    for (auto& d : req) { d.max_def_level = 0; d.def_planes = nullptr; d.def_bytes = 0; }
+    rc = launch_eval(ctx, req.data(), ncols, nodes, nnodes, 0, n, bitmap_dev, count_dev);
+    cleanup();
+    return rc;
+  }
+
+  // 2b. general case: one bitmap per leaf, deposited through its column's not-null bitmap
+  std::vector<const uint64_t*> leaf_bm;
+  std::vector<fle_pred_node> prog(nodes, nodes + nnodes);
+  for (int i = 0; i < nnodes && rc == FLE_OK; ++i) {
+    const fle_pred_node& nd = nodes[i];
+    if (nd.op == FLE_OP_AND || nd.op == FLE_OP_OR) continue;
+    const bool is_const = nd.op == FLE_OP_ALL || nd.op == FLE_OP_NONE;
+    const bool nullable = nd.col >= 0 && nd.col < ncols && cols[nd.col].max_def_level != 0;
+    if (is_const && !nullable) continue;  // stays a constant in the combine program
+    if (!is_const && (nd.col < 0 || nd.col >= ncols)) { rc = set_error(ctx, FLE_E_INVALID, "leaf column out of range"); break; }
+    uint64_t* lb = nullptr;
+    cudaError_t e = cudaMallocAsync(&lb, (size_t)nwords * 8, ctx->stream);
+    if (e != cudaSuccess) { rc = set_cuda_error(ctx, e, "cudaMallocAsync(leaf)"); break; }
+    tmp.push_back(lb);
+    if (!nullable) {
+      fle_col_desc dc = cols[nd.col];
+      fle_pred_node leaf = nd;
+      leaf.col = 0;
+      rc = launch_eval(ctx, &dc, 1, &leaf, 1, 0, n, lb, nullptr);
+    } else {
+      const fle_col_desc& col = cols[nd.col];
+      const int64_t m = (int64_t)h_counts[nd.col];  // non-null values = rows of the data stream
+      FLE_CUDA_TRY(ctx, cudaMemcpyAsync(lb, notnull[nd.col], (size_t)nwords * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+      if (nd.op == FLE_OP_NONE || m == 0) {
+        FLE_CUDA_TRY(ctx, cudaMemsetAsync(lb, 0, (size_t)nwords * 8, ctx->stream));
+      } else if (nd.op != FLE_OP_ALL) {
+        uint64_t* db = nullptr;
+        e = cudaMallocAsync(&db, (size_t)((m + 63) / 64) * 8, ctx->stream);
+        if (e != cudaSuccess) { rc = set_cuda_error(ctx, e, "cudaMallocAsync(data bitmap)"); break; }
+        tmp.push_back(db);
+        fle_col_desc dc{col.planes, col.bytes, col.bit_width, 0, nullptr, 0};
+        fle_pred_node leaf = nd;
+        leaf.col = 0;
+        rc = launch_eval(ctx, &dc, 1, &leaf, 1, 0, m, db, nullptr);
+        if (rc == FLE_OK) rc = launch_intersect(ctx, lb, n, db, m);
+      }
+    }
+    prog[i].op = FLE_OP_EQ;  // any leaf opcode: the combine kernel only looks at .col
+    prog[i].col = (int32_t)leaf_bm.size();
+    leaf_bm.push_back(lb);
+  }
+  if (rc == FLE_OK)
+    rc = launch_bitmap_combine(ctx, leaf_bm.data(), (int)leaf_bm.size(), prog.data(), nnodes, n, bitmap_dev, count_dev);
+  cleanup();
+  return rc;
+}
+
+static bool any_nullable(const fle_col_desc* cols, int ncols) {
+  for (int c = 0; c < ncols; ++c)
+    if (cols[c].max_def_level != 0) return true;
+  return false;
+}
+
+}  // namespace fle
+
+using namespace fle;
+
+#define FLE_CHECK_CTX(ctx) \
+  if (!(ctx)) return FLE_E_INVALID; \
+  fle::DeviceGuard _guard((ctx)->device)
+
+extern "C" {
+
+int fle_version(void) { return FLE_B200_VERSION; }
+
+int fle_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+const char* fle_strerror(int code) {
+  switch (code) {
+    case FLE_OK: return "ok";
+    case FLE_E_INVALID: return "invalid argument";
+    case FLE_E_NOMEM: return "out of memory";
+    case FLE_E_CUDA: return "CUDA error";
+    case FLE_E_BUFFER: return "buffer too small";
+    case FLE_E_ALIGN: return "misaligned pointer or row offset";
+    case FLE_E_UNSUPPORTED: return "unsupported request";
+    case FLE_E_NODEVICE: return "no CUDA device (this library has no CPU path)";
+  }
+  return "unknown error";
+}
+
+const char* fle_last_error(fle_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+int fle_ctx_create(int device, void* cuda_stream, fle_ctx** out) {
+  if (!out) return FLE_E_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return FLE_E_NODEVICE;
+  }
+  if (device < 0 || device >= ndev) return FLE_E_INVALID;
+  fle_ctx* ctx = new (std::nothrow) fle_ctx();
+  if (!ctx) return FLE_E_NOMEM;
+  ctx->device = device;
+  fle::DeviceGuard guard(device);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    delete ctx;
+    return FLE_E_CUDA;
+  }
+  if (prop.major < 10) {  // kernels are built for sm_100a only
+    delete ctx;
+    return FLE_E_NODEVICE;
+  }
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  if (cuda_stream) {
+    ctx->stream = (cudaStream_t)cuda_stream;
+  } else {
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      delete ctx;
+      return FLE_E_CUDA;
+    }
+    ctx->own_stream = true;
+  }
+  bool ok = cudaMalloc(&ctx->d_ticket, 4) == cudaSuccess &&
+            cudaMemset(ctx->d_ticket, 0, 4) == cudaSuccess &&
+            cudaMalloc(&ctx->d_count, 8) == cudaSuccess &&
+            cudaMallocHost(&ctx->h_count, 8) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < 2 && ok; ++i) {
+    ok = cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
+  }
+  if (!ok || ensure_scratch(ctx, 4096, 0) != FLE_OK) {
+    fle_ctx_destroy(ctx);
+    return FLE_E_CUDA;
+  }
+  *out = ctx;
+  return FLE_OK;
+}
+
+int fle_ctx_destroy(fle_ctx* ctx) {
+  if (!ctx) return FLE_OK;
+  fle::DeviceGuard guard(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+  }
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
+    if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+    if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
+  }
+  if (ctx->d_partial) cudaFree(ctx->d_partial);
+  if (ctx->d_ticket) cudaFree(ctx->d_ticket);
+  if (ctx->d_in_lits) cudaFree(ctx->d_in_lits);
+  if (ctx->h_in_lits) cudaFreeHost(ctx->h_in_lits);
+  if (ctx->d_count) cudaFree(ctx->d_count);
+  if (ctx->h_count) cudaFreeHost(ctx->h_count);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return FLE_OK;
+}
+
+int fle_ctx_set_stream(fle_ctx* ctx, void* cuda_stream) {
+  FLE_CHECK_CTX(ctx);
+  FLE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->own_stream) {
+    cudaStreamDestroy(ctx->stream);
+    ctx->own_stream = false;
+  }
+  if (cuda_stream) {
+    ctx->stream = (cudaStream_t)cuda_stream;
+  } else {
+    FLE_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+  }
+  return FLE_OK;
+}
+
+int fle_ctx_sync(fle_ctx* ctx) {
+  FLE_CHECK_CTX(ctx);
+  FLE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return FLE_OK;
+}
+
+int fle_ctx_set_option(fle_ctx* ctx, const char* name, int64_t value) {
+  if (!ctx || !name) return FLE_E_INVALID;
+  const std::string k(name);
+  if (k == "eval_variant") ctx->eval_variant = (int)value;
+  else if (k == "eval_stages") ctx->eval_stages = (int)value;
+  else if (k == "eval_block") ctx->eval_block = (int)value;
+  else if (k == "eval_ctas_per_sm") ctx->eval_ctas_per_sm = (int)value;
+  else if (k == "eval_gpt") ctx->eval_gpt = (int)value;
+  else if (k == "codec_variant") ctx->codec_variant = (int)value;
+  else if (k == "h2d_chunk_rows") ctx->h2d_chunk_rows = value;
+  else return set_error(ctx, FLE_E_INVALID, "unknown option " + k);
+  return FLE_OK;
+}
+
+int64_t fle_ctx_get_option(fle_ctx* ctx, const char* name) {
+  if (!ctx || !name) return -1;
+  const std::string k(name);
+  if (k == "eval_variant") return ctx->eval_variant;
+  if (k == "eval_stages") return ctx->eval_stages;
+  if (k == "eval_block") return ctx->eval_block;
+  if (k == "eval_ctas_per_sm") return ctx->eval_ctas_per_sm;
+  if (k == "eval_gpt") return ctx->eval_gpt;
+  if (k == "codec_variant") return ctx->codec_variant;
+  if (k == "h2d_chunk_rows") return ctx->h2d_chunk_rows;
+  if (k == "num_sms") return ctx->num_sms;
+  if (k == "max_smem_optin") return ctx->max_smem_optin;
+  return -1;
+}
+
+int64_t fle_ctx_launch_count(fle_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+// ---- memory helpers ----------------------------------------------------------------------
+int fle_host_alloc(size_t bytes, void** out) {
+  if (!out) return FLE_E_INVALID;
+  cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? FLE_E_NOMEM : FLE_E_CUDA;
+  }
+  return FLE_OK;
+}
+int fle_host_free(void* p) {
+  if (p && cudaFreeHost(p) != cudaSuccess) return FLE_E_CUDA;
+  return FLE_OK;
+}
+int fle_dev_alloc(fle_ctx* ctx, size_t bytes, void** out) {
+  FLE_CHECK_CTX(ctx);
+  if (!out) return FLE_E_INVALID;
+  FLE_CUDA_TRY(ctx, cudaMalloc(out, bytes ? bytes : 1));
+  return FLE_OK;
+}
+int fle_dev_free(fle_ctx* ctx, void* p) {
+  FLE_CHECK_CTX(ctx);
+  if (p) {
+    FLE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    FLE_CUDA_TRY(ctx, cudaFree(p));
+  }
+  return FLE_OK;
+}
+int fle_h2d(fle_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+  FLE_CHECK_CTX(ctx);
+  FLE_CUDA_TRY(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return FLE_OK;
+}
+int fle_d2h(fle_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+  FLE_CHECK_CTX(ctx);
+  FLE_CUDA_TRY(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return FLE_OK;
+}
+
+// ---- codec -------------------------------------------------------------------------------
+size_t fle_encoded_bytes(int64_t n, int bit_width) {
+  int64_t g = (n + 63) / 64;
+  if (g < 1) g = 1;
+  return (size_t)g * (size_t)bit_width * 8;
+}
+
+int fle_pack_u32_dev(fle_ctx* ctx, const uint32_t* vals_dev, int64_t n, int bw, uint8_t* enc_dev,
+                     size_t enc_cap, size_t* enc_len) {
+  FLE_CHECK_CTX(ctx);
+  if (n < 0 || !enc_dev || (n > 0 && !vals_dev)) return set_error(ctx, FLE_E_INVALID, "bad pack arguments");
+  if (bw < 1 || bw > 32) return set_error(ctx, FLE_E_INVALID, "bit width outside 1..32");
+  const size_t need = fle_encoded_bytes(n, bw);
+  if (enc_len) *enc_len = need;
+  if (enc_cap < need) return set_error(ctx, FLE_E_BUFFER, "encode buffer too small");
+  if ((reinterpret_cast<uintptr_t>(enc_dev) & 7) || (reinterpret_cast<uintptr_t>(vals_dev) & 15))
+    return set_error(ctx, FLE_E_ALIGN, "pack: enc_dev must be 8-byte and vals_dev 16-byte aligned");
+  return launch_pack_u32(ctx, vals_dev, n, bw, reinterpret_cast<uint64_t*>(enc_dev));
+}
+
+int fle_unpack_u32_dev(fle_ctx* ctx, const uint8_t* enc_dev, size_t enc_len, int bw,
+                       int64_t first_row, int64_t n, uint32_t* out_dev) {
+  FLE_CHECK_CTX(ctx);
+  if (n < 0 || first_row < 0 || !enc_dev || (n > 0 && !out_dev))
+    return set_error(ctx, FLE_E_INVALID, "bad unpack arguments");
+  if (bw < 1 || bw > 32) return set_error(ctx, FLE_E_INVALID, "bit width outside 1..32");
+  if (first_row & 63) return set_error(ctx, FLE_E_ALIGN, "unpack_dev: first_row must be a multiple of 64");
+  const int64_t g0 = first_row / 64, G = (n + 63) / 64;
+  if ((uint64_t)(g0 + G) * bw * 8u > enc_len) return set_error(ctx, FLE_E_BUFFER, "rows beyond the encoded buffer");
+  const uint8_t* p = enc_dev + (uint64_t)g0 * bw * 8u;
+  if ((reinterpret_cast<uintptr_t>(p) & 7) || (reinterpret_cast<uintptr_t>(out_dev) & 15))
+    return set_error(ctx, FLE_E_ALIGN, "unpack_dev: enc must be 8-byte and out 16-byte aligned");
+  return launch_unpack_u32(ctx, reinterpret_cast<const uint64_t*>(p), bw, n, out_dev);
+}
+
+// Host variants: values/planes cross PCIe in chunks through the context's two staging buffers.
+static const int64_t kCodecChunkValues = 32ll << 20;  // 32 Mi values (128 MiB of u32) per chunk
+
+int fle_pack_u32(fle_ctx* ctx, const uint32_t* vals, int64_t n, int bw, uint8_t* enc, size_t enc_cap,
+                 size_t* enc_len) {
+  FLE_CHECK_CTX(ctx);
+  if (n < 0 || !enc || (n > 0 && !vals)) return set_error(ctx, FLE_E_INVALID, "bad pack arguments");
+  if (bw < 1 || bw > 32) return set_error(ctx, FLE_E_INVALID, "bit width outside 1..32");
+  const size_t need = fle_encoded_bytes(n, bw);
+  if (enc_len) *enc_len = need;
+  if (enc_cap < need) return set_error(ctx, FLE_E_BUFFER, "encode buffer too small");
+  if (n == 0) {
+    std::memset(enc, 0, need);
+    return FLE_OK;
+  }
+  const int64_t chunk = std::min<int64_t>(n, kCodecChunkValues);
+  int rc = ensure_stage(ctx, 0, (size_t)chunk * 4);
+  if (rc != FLE_OK) return rc;
+  rc = ensure_stage(ctx, 1, fle_encoded_bytes(chunk, bw));
+  if (rc != FLE_OK) return rc;
+  for (int64_t off = 0; off < n; off += chunk) {
+    const int64_t m = std::min(chunk, n - off);
+    const size_t eb = fle_encoded_bytes(m, bw);
+    FLE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_stage[0], vals + off, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
+    rc = launch_pack_u32(ctx, (const uint32_t*)ctx->d_stage[0], m, bw, (uint64_t*)ctx->d_stage[1]);
+    if (rc != FLE_OK) return rc;
+    FLE_CUDA_TRY(ctx, cudaMemcpyAsync(enc + (size_t)(off / 64) * bw * 8, ctx->d_stage[1], eb, cudaMemcpyDeviceToHost, ctx->stream));
+    FLE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return FLE_OK;
+}
+
+int fle_unpack_u32(fle_ctx* ctx, const uint8_t* enc, size_t enc_len, int bw, int64_t first_row,
+                   int64_t n, uint32_t* out) {
+  FLE_CHECK_CTX(ctx);
+  if (n < 0 || first_row < 0 || !enc || (n > 0 && !out)) return set_error(ctx, FLE_E_INVALID, "bad unpack arguments");
+  if (bw < 1 || bw > 32) return set_error(ctx, FLE_E_INVALID, "bit width outside 1..32");
+  if (n == 0) return FLE_OK;
+  const int64_t g_first = first_row / 64;
+  const int64_t g_end = (first_row + n + 63) / 64;
+  if ((uint64_t)g_end * bw * 8u > enc_len) return set_error(ctx, FLE_E_BUFFER, "rows beyond the encoded buffer");
+  const int64_t chunk_groups = kCodecChunkValues / 64;
+  int rc = ensure_stage(ctx, 0, (size_t)std::min(chunk_groups, g_end - g_first) * bw * 8);
+  if (rc != FLE_OK) return rc;
+  rc = ensure_stage(ctx, 1, (size_t)std::min(chunk_groups, g_end - g_first) * 256);
+  if (rc != FLE_OK) return rc;
+  for (int64_t g = g_first; g < g_end; g += chunk_groups) {
+    const int64_t ng = std::min(chunk_groups, g_end - g);
+    FLE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_stage[0], enc + (size_t)g * bw * 8, (size_t)ng * bw * 8, cudaMemcpyHostToDevice, ctx->stream));
+    rc = launch_unpack_u32(ctx, (const uint64_t*)ctx->d_stage[0], bw, ng * 64, (uint32_t*)ctx->d_stage[1]);
+    if (rc != FLE_OK) return rc;
+    // rows of this chunk that the caller asked for
+    const int64_t r0 = std::max(first_row, g * 64), r1 = std::min(first_row + n, (g + ng) * 64);
+    FLE_CUDA_TRY(ctx, cudaMemcpyAsync(out + (r0 - first_row), (const uint32_t*)ctx->d_stage[1] + (r0 - g * 64),
+                                      (size_t)(r1 - r0) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FLE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return FLE_OK;
+}
+
+// ---- fused predicate evaluation ------------------------------------------------------------
+int fle_eval_dev(fle_ctx* ctx, const fle_col_desc* cols, int ncols, const fle_pred_node* nodes,
+                 int nnodes, int64_t first_row, int64_t n, uint64_t* bitmap_dev, uint64_t* count_dev) {
+  FLE_CHECK_CTX(ctx);
+  if (!cols || !nodes || ncols < 1 || nnodes < 1) return set_error(ctx, FLE_E_INVALID, "empty program");
+  if (ncols > FLE_MAX_COLS) return set_error(ctx, FLE_E_UNSUPPORTED, "too many columns");
+  if (any_nullable(cols, ncols))
+    return eval_dev_nullable(ctx, cols, ncols, nodes, nnodes, first_row, n, bitmap_dev, count_dev);
+  return launch_eval(ctx, cols, ncols, nodes, nnodes, first_row, n, bitmap_dev, count_dev);
+}
+
+int fle_eval(fle_ctx* ctx, const fle_col_desc* cols, int ncols, const fle_pred_node* nodes, int nnodes,
+             int64_t first_row, int64_t n, uint64_t* bitmap_out, uint64_t* match_count) {
+  FLE_CHECK_CTX(ctx);
+  if (!cols || !nodes || ncols < 1 || nnodes < 1 || n < 0 || first_row < 0 || (n > 0 && !bitmap_out))
+    return set_error(ctx, FLE_E_INVALID, "bad eval arguments");
+  if (ncols > FLE_MAX_COLS) return set_error(ctx, FLE_E_UNSUPPORTED, "too many columns");
+  if (first_row & 63) return set_error(ctx, FLE_E_ALIGN, "first_row must be a multiple of 64");
+  if (match_count) *match_count = 0;
+  if (n == 0) {
+    LoweredProgram lp;
+    std::string err;
+    int rc0 = lower_program(cols, ncols, nodes, nnodes, &lp, &err);  // still validate the program
+    return rc0 == FLE_OK ? FLE_OK : set_error(ctx, rc0, err);
+  }
+  const int64_t G = (n + 63) / 64, g0 = first_row / 64;
+  int rc;
+
+  if (any_nullable(cols, ncols)) {
+    // upload everything, then run the def-level path on the device copies
+    if (first_row != 0) return set_error(ctx, FLE_E_UNSUPPORTED, "nullable columns are evaluated from row 0 of the page");
+    size_t total = 0;
+    std::vector<size_t> off_p(ncols), off_d(ncols);
+    for (int c = 0; c < ncols; ++c) {
+      if (!cols[c].planes && cols[c].bytes) return set_error(ctx, FLE_E_INVALID, "null column pointer");
+      off_p[c] = total; total = align_up(total + cols[c].bytes, 256);
+      off_d[c] = total; total = align_up(total + (cols[c].max_def_level ? cols[c].def_bytes : 0), 256);
+    }
+    const size_t off_bm = total; total += (size_t)G * 8;
+    rc = ensure_stage(ctx, 0, total + 256);
+    if (rc != FLE_OK) return rc;
+    uint8_t* base = (uint8_t*)ctx->d_stage[0];
+    std::vector<fle_col_desc> dc(cols, cols + ncols);
+    for (int c = 0; c < ncols; ++c) {
+      if (cols[c].bytes)
+        FLE_CUDA_TRY(ctx, cudaMemcpyAsync(base + off_p[c], cols[c].planes, cols[c].bytes, cudaMemcpyHostToDevice, ctx->stream));
+      dc[c].planes = base + off_p[c];
+      if (cols[c].max_def_level) {
+        if (!cols[c].def_planes) return set_error(ctx, FLE_E_INVALID, "nullable column without def_planes");
+        FLE_CUDA_TRY(ctx, cudaMemcpyAsync(base + off_d[c], cols[c].def_planes, cols[c].def_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        dc[c].def_planes = base + off_d[c];
+      }
+    }
+    rc = eval_dev_nullable(ctx, dc.data(), ncols, nodes, nnodes, 0, n, (uint64_t*)(base + off_bm), ctx->d_count);
+    if (rc != FLE_OK) return rc;
+    FLE_CUDA_TRY(ctx, cudaMemcpyAsync(bitmap_out, base + off_bm, (size_t)G * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FLE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_count, ctx->d_count, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FLE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (match_count) *match_count = *ctx->h_count;
+    return FLE_OK;
+  }
+
+  // required columns: chunked, double-buffered H2D -> kernel -> D2H
+  int sum_bw = 0;
+  for (int c = 0; c < ncols; ++c) {
+    const int bw = cols[c].bit_width;
+    if (bw < 1 || bw > 32) return set_error(ctx, FLE_E_INVALID, "bit width outside 1..32");
+    if (!cols[c].planes) return set_error(ctx, FLE_E_INVALID, "null column pointer");
+    if (cols[c].bytes < (uint64_t)(g0 + G) * bw * 8u) return set_error(ctx, FLE_E_BUFFER, "column shorter than the rows requested");
+    sum_bw += bw;
+  }
+  LoweredProgram lp;
+  rc = prepare_eval(ctx, cols, ncols, nodes, nnodes, &lp);
+  if (rc != FLE_OK) return rc;
+
+  int64_t chunk_groups = ctx->h2d_chunk_rows > 0 ? ctx->h2d_chunk_rows / 64
+                                                 : (int64_t)(48ull << 20) / ((int64_t)sum_bw * 8);
+  chunk_groups = std::max<int64_t>(2048, chunk_groups / 2048 * 2048);
+  chunk_groups = std::min<int64_t>(chunk_groups, (G + 2047) / 2048 * 2048);
+  const int64_t nchunks = (G + chunk_groups - 1) / chunk_groups;
+  std::vector<size_t> coff(ncols);
+  size_t total = 0;
+  for (int c = 0; c < ncols; ++c) {
+    coff[c] = total;
+    total = align_up(total + (size_t)chunk_groups * cols[c].bit_width * 8, 256);
+  }
+  const size_t off_bm = total;
+  total = align_up(total + (size_t)chunk_groups * 8, 256);
+  for (int b = 0; b < 2; ++b) {
+    if (b == 1 && nchunks == 1) break;
+    rc = ensure_stage(ctx, b, total);
+    if (rc != FLE_OK) return rc;
+  }
+  uint64_t* d_counts = nullptr;
+  FLE_CUDA_TRY(ctx, cudaMalloc(&d_counts, (size_t)nchunks * 8));
+  std::vector<uint64_t> h_counts(nchunks, 0);
+  rc = FLE_OK;
+  cudaError_t e = cudaSuccess;
+  for (int64_t k = 0; k < nchunks && rc == FLE_OK && e == cudaSuccess; ++k) {
+    const int b = (int)(k & 1);
+    const int64_t cg0 = k * chunk_groups;
+    const int64_t cg = std::min(chunk_groups, G - cg0);
+    const int64_t rows = std::min<int64_t>(cg * 64, n - cg0 * 64);
+    uint8_t* base = (uint8_t*)ctx->d_stage[b];
+    if (k >= 2) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0);
+    std::vector<fle_col_desc> dc(cols, cols + ncols);
+    for (int c = 0; c < ncols && e == cudaSuccess; ++c) {
+      const int bw = cols[c].bit_width;
+      const uint8_t* src = (const uint8_t*)cols[c].planes + (size_t)(g0 + cg0) * bw * 8;
+      e = cudaMemcpyAsync(base + coff[c], src, (size_t)cg * bw * 8, cudaMemcpyHostToDevice, ctx->copy_stream);
+      dc[c].planes = base + coff[c];
+      dc[c].bytes = (uint64_t)cg * bw * 8;
+    }
+    if (e != cudaSuccess) break;
+    e = cudaEventRecord(ctx->ev_copy[b], ctx->copy_stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[b], 0);
+    if (e != cudaSuccess) break;
+    rc = launch_prepared(ctx, &lp, dc.data(), ncols, 0, rows, (uint64_t*)(base + off_bm), d_counts + k);
+    if (rc != FLE_OK) break;
+    e = cudaMemcpyAsync(bitmap_out + cg0, base + off_bm, (size_t)cg * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_done[b], ctx->stream);
+  }
+  if (rc == FLE_OK && e == cudaSuccess)
+    e = cudaMemcpyAsync(h_counts.data(), d_counts, (size_t)nchunks * 8, cudaMemcpyDeviceToHost, ctx->stream);
+  cudaError_t e2 = cudaStreamSynchronize(ctx->copy_stream);
+  cudaError_t e3 = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_counts);
+  if (rc != FLE_OK) return rc;
+  if (e != cudaSuccess) return set_cuda_error(ctx, e, "fle_eval pipeline");
+  if (e2 != cudaSuccess) return set_cuda_error(ctx, e2, "fle_eval copy stream");
+  if (e3 != cudaSuccess) return set_cuda_error(ctx, e3, "fle_eval stream");
+  if (match_count) {
+    uint64_t t = 0;
+    for (uint64_t c : h_counts) t += c;
+    *match_count = t;
+  }
+  return FLE_OK;
+}
+
+// ---- bitmap utilities ----------------------------------------------------------------------
+int fle_bitmap_count_dev(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nbits, uint64_t* count_dev) {
+  FLE_CHECK_CTX(ctx);
+  if (!bitmap_dev && nbits > 0) return set_error(ctx, FLE_E_INVALID, "null bitmap");
+  return launch_bitmap_count(ctx, bitmap_dev, nbits, count_dev);
+}
+
+int fle_intersect_bitset_dev(fle_ctx* ctx, uint64_t* root_dev, int64_t n_root, const uint64_t* sub_dev,
+                             int64_t n_sub) {
+  FLE_CHECK_CTX(ctx);
+  return launch_intersect(ctx, root_dev, n_root, sub_dev, n_sub);
+}
+
+int fle_intersect_bitset(fle_ctx* ctx, uint64_t* root, int64_t n_root, const uint64_t* sub, int64_t n_sub) {
+  FLE_CHECK_CTX(ctx);
+  if (n_root < 0 || n_sub < 0 || (n_root > 0 && !root) || (n_sub > 0 && !sub))
+    return set_error(ctx, FLE_E_INVALID, "bad intersect arguments");
+  if (n_root == 0) return FLE_OK;
+  const size_t rb = (size_t)((n_root + 63) / 64) * 8, sb = (size_t)((n_sub + 63) / 64) * 8;
+  int rc = ensure_stage(ctx, 0, rb);
+  if (rc != FLE_OK) return rc;
+  rc = ensure_stage(ctx, 1, std::max<size_t>(sb, 8));
+  if (rc != FLE_OK) return rc;
+  FLE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_stage[0], root, rb, cudaMemcpyHostToDevice, ctx->stream));
+  if (sb) FLE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_stage[1], sub, sb, cudaMemcpyHostToDevice, ctx->stream));
+  rc = launch_intersect(ctx, (uint64_t*)ctx->d_stage[0], n_root, (const uint64_t*)ctx->d_stage[1], n_sub);
+  if (rc != FLE_OK) return rc;
+  FLE_CUDA_TRY(ctx, cudaMemcpyAsync(root, ctx->d_stage[0], rb, cudaMemcpyDeviceToHost, ctx->stream));
+  FLE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return FLE_OK;
+}
+
+}  // extern "C"

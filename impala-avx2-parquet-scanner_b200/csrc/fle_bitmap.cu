@@ -1,0 +1,183 @@
+// Selection-bitmap utilities.
+//   bitmap_count     = boost::dynamic_bitset::count()
+//   intersect_bitset = ColumnReader<T>::IntersectBitset
+//                      /root/reference/hdfs-parquet-scanner.cc:326-331
+// IntersectBitset walks root bit by bit and hands the i-th SET bit the i-th bit of sub; on
+// the device that is a prefix popcount over root's words followed, per word, by a bit
+// gather from sub (64-bit funnel shift across two words) and a bit deposit into the set
+// positions of the root word.
+#include "fle_device.cuh"
+#include "fle_internal.h"
+
+namespace fle {
+
+constexpr int kBmThreads = 256;
+constexpr int kBmWordsPerThread = 8;
+constexpr int kBmWordsPerBlock = kBmThreads * kBmWordsPerThread;
+
+__device__ __forceinline__ uint64_t tail_mask_word(int64_t w, int64_t nbits) {
+  const int64_t left = nbits - w * 64;
+  if (left >= 64) return ~0ull;
+  if (left <= 0) return 0ull;
+  return (1ull << left) - 1ull;
+}
+
+template <int NT>
+__device__ __forceinline__ uint64_t block_sum(uint64_t v, uint64_t* warp_buf) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) warp_buf[threadIdx.x >> 5] = v;
+  __syncthreads();
+  uint64_t t = 0;
+#pragma unroll
+  for (int w = 0; w < NT / 32; ++w) t += warp_buf[w];
+  __syncthreads();
+  return t;
+}
+
+// per-block popcounts (block b covers words [b*kBmWordsPerBlock, ...))
+__global__ void __launch_bounds__(kBmThreads)
+bitmap_block_counts_kernel(const uint64_t* __restrict__ bm, int64_t nbits, int64_t nwords,
+                           uint64_t* __restrict__ block_sums) {
+  __shared__ uint64_t warp_buf[kBmThreads / 32];
+  const int64_t w0 = (int64_t)blockIdx.x * kBmWordsPerBlock;
+  uint64_t c = 0;
+#pragma unroll
+  for (int k = 0; k < kBmWordsPerThread; ++k) {
+    const int64_t w = w0 + k * kBmThreads + threadIdx.x;
+    if (w < nwords) c += __popcll(bm[w] & tail_mask_word(w, nbits));
+  }
+  const uint64_t t = block_sum<kBmThreads>(c, warp_buf);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(kBmThreads)
+sum_u64_kernel(const uint64_t* __restrict__ v, int n, uint64_t* __restrict__ out) {
+  __shared__ uint64_t warp_buf[kBmThreads / 32];
+  uint64_t c = 0;
+  for (int i = threadIdx.x; i < n; i += kBmThreads) c += v[i];
+  const uint64_t t = block_sum<kBmThreads>(c, warp_buf);
+  if (threadIdx.x == 0) *out = t;
+}
+
+// bit deposit: the i-th set bit of mask (from the LSB) receives bit i of src
+__device__ __forceinline__ uint64_t deposit_bits(uint64_t src, uint64_t mask) {
+  if (mask == ~0ull) return src;
+  const int ones = __popcll(mask);
+  if (ones >= 32) {
+    // few holes: open a zero gap at every clear position of mask, lowest first
+    uint64_t holes = ~mask;
+    uint64_t r = src;
+    while (holes) {
+      const int z = __ffsll((long long)holes) - 1;
+      const uint64_t low = (1ull << z) - 1ull;
+      r = (r & low) | ((r & ~low) << 1);
+      holes &= holes - 1;
+    }
+    return r & mask;
+  }
+  uint64_t r = 0, m = mask;
+  int i = 0;
+  while (m) {
+    const int p = __ffsll((long long)m) - 1;
+    r |= ((src >> i) & 1ull) << p;
+    m &= m - 1;
+    ++i;
+  }
+  return r;
+}
+
+// 64 bits of sub starting at bit offset `pos` (bits past n_sub read as 0)
+__device__ __forceinline__ uint64_t gather_bits(const uint64_t* __restrict__ sub, int64_t n_sub,
+                                                int64_t pos) {
+  const int64_t nw = (n_sub + 63) >> 6;
+  const int64_t w = pos >> 6;
+  const int sh = (int)(pos & 63);
+  uint64_t lo = w < nw ? (sub[w] & tail_mask_word(w, n_sub)) : 0ull;
+  if (sh == 0) return lo;
+  uint64_t hi = (w + 1) < nw ? (sub[w + 1] & tail_mask_word(w + 1, n_sub)) : 0ull;
+  return (lo >> sh) | (hi << (64 - sh));
+}
+
+__global__ void __launch_bounds__(kBmThreads)
+intersect_kernel(uint64_t* __restrict__ root, int64_t n_root, int64_t nwords,
+                 const uint64_t* __restrict__ sub, int64_t n_sub,
+                 const uint64_t* __restrict__ block_sums) {
+  __shared__ uint64_t warp_buf[kBmThreads / 32];
+  __shared__ uint32_t warp_scan[kBmThreads / 32];
+  // exclusive offset of this block = sum of the popcounts of all earlier blocks
+  uint64_t pre = 0;
+  for (int i = threadIdx.x; i < (int)blockIdx.x; i += kBmThreads) pre += block_sums[i];
+  const uint64_t block_off = block_sum<kBmThreads>(pre, warp_buf);
+
+  // thread owns kBmWordsPerThread CONSECUTIVE words so that its ranks are contiguous
+  const int64_t w0 = (int64_t)blockIdx.x * kBmWordsPerBlock + (int64_t)threadIdx.x * kBmWordsPerThread;
+  uint64_t m[kBmWordsPerThread];
+  uint32_t mine = 0;
+#pragma unroll
+  for (int k = 0; k < kBmWordsPerThread; ++k) {
+    const int64_t w = w0 + k;
+    m[k] = w < nwords ? (root[w] & tail_mask_word(w, n_root)) : 0ull;
+    mine += __popcll(m[k]);
+  }
+  // block-wide exclusive scan of `mine`
+  uint32_t incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((threadIdx.x & 31) >= o) incl += y;
+  }
+  if ((threadIdx.x & 31) == 31) warp_scan[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  uint32_t warp_off = 0;
+  for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) warp_off += warp_scan[w];
+  int64_t rank = (int64_t)block_off + warp_off + (incl - mine);
+#pragma unroll
+  for (int k = 0; k < kBmWordsPerThread; ++k) {
+    const int64_t w = w0 + k;
+    if (w < nwords) {
+      const uint64_t bits = gather_bits(sub, n_sub, rank);
+      root[w] = deposit_bits(bits, m[k]);
+      rank += __popcll(m[k]);
+    }
+  }
+}
+
+int launch_bitmap_count(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nbits, uint64_t* count_dev) {
+  if (nbits < 0 || !count_dev) return set_error(ctx, FLE_E_INVALID, "bad bitmap_count arguments");
+  if (nbits == 0) {
+    FLE_CUDA_TRY(ctx, cudaMemsetAsync(count_dev, 0, 8, ctx->stream));
+    return FLE_OK;
+  }
+  const int64_t nwords = (nbits + 63) / 64;
+  const int nblocks = (int)((nwords + kBmWordsPerBlock - 1) / kBmWordsPerBlock);
+  int rc = ensure_scratch(ctx, nblocks, 0);
+  if (rc != FLE_OK) return rc;
+  bitmap_block_counts_kernel<<<nblocks, kBmThreads, 0, ctx->stream>>>(bitmap_dev, nbits, nwords, ctx->d_partial);
+  sum_u64_kernel<<<1, kBmThreads, 0, ctx->stream>>>(ctx->d_partial, nblocks, count_dev);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(ctx, e, "bitmap_count launch");
+  ctx->launches += 2;
+  return FLE_OK;
+}
+
+int launch_intersect(fle_ctx* ctx, uint64_t* root_dev, int64_t n_root, const uint64_t* sub_dev,
+                     int64_t n_sub) {
+  if (n_root < 0 || n_sub < 0 || !root_dev || (n_sub > 0 && !sub_dev))
+    return set_error(ctx, FLE_E_INVALID, "bad intersect arguments");
+  if (n_root == 0) return FLE_OK;
+  const int64_t nwords = (n_root + 63) / 64;
+  const int nblocks = (int)((nwords + kBmWordsPerBlock - 1) / kBmWordsPerBlock);
+  int rc = ensure_scratch(ctx, nblocks, 0);
+  if (rc != FLE_OK) return rc;
+  // NB: block_counts assigns words to threads interleaved, intersect consecutively; both
+  // cover the same words per BLOCK, which is all the block sums need.
+  bitmap_block_counts_kernel<<<nblocks, kBmThreads, 0, ctx->stream>>>(root_dev, n_root, nwords, ctx->d_partial);
+  intersect_kernel<<<nblocks, kBmThreads, 0, ctx->stream>>>(root_dev, n_root, nwords, sub_dev, n_sub, ctx->d_partial);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(ctx, e, "intersect launch");
+  ctx->launches += 2;
+  return FLE_OK;
+}
+
+}  // namespace fle

@@ -1,0 +1,234 @@
+// FLE pack / unpack kernels, one specialisation per bit width 1..32.
+//
+// Replaces
+//   FleEncoder::Put / Pack_1..16 / Pack_16_32 / Flush   /root/reference/fle-encoding.h:8315-9812
+//   FleDecoder::Get / Unpack_1..32                       /root/reference/fle-encoding.h:404-7329
+//
+// In the reference's layout a group is a 64 x bw bit matrix stored plane-major, so decode
+// and encode are bit-matrix transposes.  One thread owns one group and transposes it in
+// registers with a fully unrolled 32x32 butterfly (fle_device.cuh); for bw <= 16 the two
+// 32-row halves of a group share ONE butterfly (planes of the upper half in the high 16
+// lanes), and planes >= bw are compile-time zeros that fold out of the network.
+// Values move between registers and global memory through a swizzled shared-memory tile so
+// that every global access is a fully coalesced 128-bit transaction.
+#include "fle_device.cuh"
+#include "fle_internal.h"
+
+namespace fle {
+
+constexpr int kCodecThreads = 128;               // groups per tile
+constexpr int kTileValueBytes = kCodecThreads * 256;  // 64 u32 values per group
+
+// value tile in shared memory: row = group (256 B), 16-byte chunks rotated by the row index
+__device__ __forceinline__ uint32_t tile_chunk_addr(uint32_t tile, int row, int chunk) {
+  return tile + row * 256 + (((chunk + row) & 15) << 4);
+}
+
+// ------------------------------------------------------------------------------------------
+// unpack
+// ------------------------------------------------------------------------------------------
+template <int BW>
+__device__ __forceinline__ void transpose_planes_to_values(const uint64_t (&w)[BW], uint32_t (&v)[64]) {
+  if constexpr (BW <= 16) {
+    uint32_t A[32];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      A[31 - i] = i < BW ? (uint32_t)(w[i < BW ? i : 0] >> 32) : 0u;  // rows 0..31  (bits 63..32)
+      A[15 - i] = i < BW ? (uint32_t)(w[i < BW ? i : 0]) : 0u;        // rows 32..63 (bits 31..0)
+    }
+    transpose32(A);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      v[k] = A[k] & 0xFFFFu;
+      v[32 + k] = A[k] >> 16;
+    }
+  } else {
+    uint32_t A[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) A[31 - i] = i < BW ? (uint32_t)(w[i < BW ? i : 0] >> 32) : 0u;
+    transpose32(A);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = A[k];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) A[31 - i] = i < BW ? (uint32_t)(w[i < BW ? i : 0]) : 0u;
+    transpose32(A);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[32 + k] = A[k];
+  }
+}
+
+template <int BW>
+__global__ void __launch_bounds__(kCodecThreads)
+unpack_kernel(const uint64_t* __restrict__ enc, int64_t ngroups, int64_t nvals, uint32_t* __restrict__ out) {
+  __shared__ __align__(128) uint8_t tile_mem[kTileValueBytes];
+  const uint32_t tile = smem_u32(tile_mem);
+  const int t = threadIdx.x;
+  const int64_t ntiles = (ngroups + kCodecThreads - 1) / kCodecThreads;
+  for (int64_t tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+    const int64_t g = tl * kCodecThreads + t;
+    if (g < ngroups) {
+      uint64_t w[BW];
+      const uint64_t* src = enc + g * BW;
+#pragma unroll
+      for (int i = 0; i < BW; ++i) w[i] = __ldg(src + i);
+      uint32_t v[64];
+      transpose_planes_to_values<BW>(w, v);
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        sts128u(tile_chunk_addr(tile, t, c), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    }
+    __syncthreads();
+    // coalesced copy-out: the tile is kTileValueBytes contiguous bytes of `out`
+    const int64_t v0 = tl * kCodecThreads * 64;  // first value index of the tile
+    uint32_t* dst = out + v0;
+#pragma unroll 4
+    for (int it = 0; it < 16; ++it) {
+      const int L = it * kCodecThreads + t;  // 16-byte chunk index inside the tile
+      const int64_t vi = v0 + (int64_t)L * 4;
+      if (vi >= nvals) continue;
+      uint32_t a, b, c, d;
+      lds128u(tile_chunk_addr(tile, L >> 4, L & 15), a, b, c, d);
+      if (vi + 4 <= nvals) {
+        stg_stream128(dst + L * 4, make_uint4(a, b, c, d));
+      } else {
+        dst[L * 4] = a;
+        if (vi + 1 < nvals) dst[L * 4 + 1] = b;
+        if (vi + 2 < nvals) dst[L * 4 + 2] = c;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// pack
+// ------------------------------------------------------------------------------------------
+template <int BW>
+__device__ __forceinline__ void transpose_values_to_planes(const uint32_t (&v)[64], uint64_t (&w)[BW]) {
+  constexpr uint32_t kMask = BW >= 32 ? 0xFFFFFFFFu : ((1u << BW) - 1u);
+  if constexpr (BW <= 16) {
+    uint32_t A[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) A[k] = (v[k] & kMask) | ((v[32 + k] & kMask) << 16);
+    transpose32(A);
+#pragma unroll
+    for (int i = 0; i < BW; ++i) w[i] = ((uint64_t)A[31 - i] << 32) | A[15 - i];
+  } else {
+    uint32_t A[32], B[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      A[k] = v[k] & kMask;
+      B[k] = v[32 + k] & kMask;
+    }
+    transpose32(A);
+    transpose32(B);
+#pragma unroll
+    for (int i = 0; i < BW; ++i) w[i] = ((uint64_t)A[31 - i] << 32) | B[31 - i];
+  }
+}
+
+template <int BW>
+__global__ void __launch_bounds__(kCodecThreads)
+pack_kernel(const uint32_t* __restrict__ vals, int64_t nvals, int64_t ngroups, uint64_t* __restrict__ enc) {
+  __shared__ __align__(128) uint8_t tile_mem[kTileValueBytes];
+  const uint32_t tile = smem_u32(tile_mem);
+  const int t = threadIdx.x;
+  const int64_t ntiles = (ngroups + kCodecThreads - 1) / kCodecThreads;
+  for (int64_t tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+    const int64_t v0 = tl * kCodecThreads * 64;
+    const uint32_t* src = vals + v0;
+    // coalesced copy-in; rows past the end are zero (the reference leaves stale data there)
+#pragma unroll 4
+    for (int it = 0; it < 16; ++it) {
+      const int L = it * kCodecThreads + t;
+      const int64_t vi = v0 + (int64_t)L * 4;
+      uint4 x = make_uint4(0, 0, 0, 0);
+      if (vi + 4 <= nvals) {
+        x = ldg_stream128(src + L * 4);
+      } else if (vi < nvals) {
+        x.x = src[L * 4];
+        if (vi + 1 < nvals) x.y = src[L * 4 + 1];
+        if (vi + 2 < nvals) x.z = src[L * 4 + 2];
+      }
+      sts128u(tile_chunk_addr(tile, L >> 4, L & 15), x.x, x.y, x.z, x.w);
+    }
+    __syncthreads();
+    const int64_t g = tl * kCodecThreads + t;
+    if (g < ngroups) {
+      uint32_t v[64];
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        lds128u(tile_chunk_addr(tile, t, c), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      uint64_t w[BW];
+      transpose_values_to_planes<BW>(v, w);
+      uint64_t* dst = enc + g * BW;
+#pragma unroll
+      for (int i = 0; i < BW; ++i) dst[i] = w[i];
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// dispatch
+// ------------------------------------------------------------------------------------------
+namespace {
+
+typedef void (*UnpackFn)(const uint64_t*, int64_t, int64_t, uint32_t*);
+typedef void (*PackFn)(const uint32_t*, int64_t, int64_t, uint64_t*);
+
+template <int... I>
+struct Seq {};
+template <int N, int... I>
+struct MakeSeq : MakeSeq<N - 1, N, I...> {};
+template <int... I>
+struct MakeSeq<0, I...> { typedef Seq<I...> type; };
+
+template <int... I>
+UnpackFn unpack_table_entry(int bw, Seq<I...>) {
+  static const UnpackFn tab[] = {unpack_kernel<I>...};
+  return tab[bw - 1];
+}
+template <int... I>
+PackFn pack_table_entry(int bw, Seq<I...>) {
+  static const PackFn tab[] = {pack_kernel<I>...};
+  return tab[bw - 1];
+}
+
+int codec_grid(fle_ctx* ctx, int64_t ngroups) {
+  const int64_t ntiles = (ngroups + kCodecThreads - 1) / kCodecThreads;
+  // 32 KB static shared memory per CTA -> up to 7 CTAs per SM
+  return (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)ctx->num_sms * 6));
+}
+
+}  // namespace
+
+int launch_unpack_u32(fle_ctx* ctx, const uint64_t* enc_dev, int bw, int64_t n, uint32_t* out_dev) {
+  if (bw < 1 || bw > 32) return set_error(ctx, FLE_E_INVALID, "bit width outside 1..32");
+  if (n == 0) return FLE_OK;
+  const int64_t G = (n + 63) / 64;
+  UnpackFn fn = unpack_table_entry(bw, MakeSeq<32>::type());
+  fn<<<codec_grid(ctx, G), kCodecThreads, 0, ctx->stream>>>(enc_dev, G, n, out_dev);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(ctx, e, "unpack_kernel launch");
+  ctx->launches += 1;
+  return FLE_OK;
+}
+
+int launch_pack_u32(fle_ctx* ctx, const uint32_t* vals_dev, int64_t n, int bw, uint64_t* enc_dev) {
+  if (bw < 1 || bw > 32) return set_error(ctx, FLE_E_INVALID, "bit width outside 1..32");
+  const int64_t G = (n + 63) / 64;
+  if (G == 0) {
+    // Flush() packs one group even when nothing was Put (fle-encoding.h:9806-9811)
+    FLE_CUDA_TRY(ctx, cudaMemsetAsync(enc_dev, 0, (size_t)bw * 8, ctx->stream));
+    return FLE_OK;
+  }
+  PackFn fn = pack_table_entry(bw, MakeSeq<32>::type());
+  fn<<<codec_grid(ctx, G), kCodecThreads, 0, ctx->stream>>>(vals_dev, n, G, enc_dev);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(ctx, e, "pack_kernel launch");
+  ctx->launches += 1;
+  return FLE_OK;
+}
+
+}  // namespace fle

@@ -1,0 +1,165 @@
+// Device-side building blocks shared by the FLE kernels (sm_100a).
+//   * mbarrier + TMA 1-D bulk copy wrappers (cp.async.bulk, SASS UBLKCP)
+//   * shared-memory plane loaders
+//   * the 32x32 bit-matrix transpose that turns bit planes into values and back
+#pragma once
+#include <cstdint>
+
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#define FLE_HD __host__ __device__ __forceinline__
+#else
+#define FLE_HD inline
+#endif
+
+namespace fle {
+
+// ------------------------------------------------------------------------------------------
+// 32 x 32 bit-matrix transpose, fully unrolled so that it lives in registers and so that
+// rows known to be zero at compile time (planes >= bit width) fold away.
+//
+// Convention (checked on the host in tests/test_host_math.py through fle_selftest):
+// after transpose32(A):   A'[k] bit i  ==  A[31 - i] bit (31 - k).
+// Unpack: load plane i's 32-bit half into A[31 - i]; A'[k] is then the value of row k of
+// that half (row k lives at bit 31-k of the half-word, fle-encoding.h:426-430).
+// Pack:   load the value of row k into A[k]; A'[31 - i] is plane i's half-word
+// (fle-encoding.h:8338-8340).  The network is its own inverse.
+// ------------------------------------------------------------------------------------------
+template <int J, uint32_t M>
+FLE_HD void transpose32_stage(uint32_t (&A)[32]) {
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    if ((k & J) == 0) {
+      uint32_t t = (A[k] ^ (A[k + J] >> J)) & M;
+      A[k] ^= t;
+      A[k + J] ^= (t << J);
+    }
+  }
+}
+
+FLE_HD void transpose32(uint32_t (&A)[32]) {
+  transpose32_stage<16, 0x0000FFFFu>(A);
+  transpose32_stage<8, 0x00FF00FFu>(A);
+  transpose32_stage<4, 0x0F0F0F0Fu>(A);
+  transpose32_stage<2, 0x33333333u>(A);
+  transpose32_stage<1, 0x55555555u>(A);
+}
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------
+// mbarrier / TMA bulk copy (PTX ISA: mbarrier, cp.async.bulk)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_fence_init() {
+  // make the inits visible to the async proxy (TMA) before the first bulk copy
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+// Bounded wait: a protocol bug must trap (and fail the launch) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+
+// global -> shared bulk copy, completion signalled on an mbarrier in this CTA.
+// dst, src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void* src, uint32_t bytes,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+
+// shared -> global bulk store (bulk async-group completion).
+__device__ __forceinline__ void tma_store_1d(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+               "r"(src_smem), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+// generic-proxy smem writes -> visible to the async proxy (before a bulk store reads them)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ uint64_t lds64(uint32_t addr) {
+  uint64_t v;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void lds128(uint32_t addr, uint64_t& a, uint64_t& b) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint64_t v) {
+  asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ void lds128u(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c,
+                                        uint32_t& d) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(a), "=r"(b), "=r"(c), "=r"(d)
+               : "r"(addr));
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
+                                        uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c),
+               "r"(d)
+               : "memory");
+}
+// streaming (read-once) global loads/stores: keep L1 clean
+__device__ __forceinline__ uint64_t ldg_stream64(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint4 ldg_stream128(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_stream128(void* p, uint4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+#endif  // __CUDACC__
+
+}  // namespace fle

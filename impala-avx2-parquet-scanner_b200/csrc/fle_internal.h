@@ -1,0 +1,163 @@
+// Internal declarations shared by the translation units of libfle_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/fle_b200.h"
+
+namespace fle {
+
+// ------------------------------------------------------------------------------------------
+// Lowered form of a predicate program (built on the host by lower_program, consumed by the
+// eval kernels as a __grid_constant__ parameter).
+//
+// Every comparison leaf becomes one "borrow chain" over the planes, LSB -> MSB:
+//     acc' = (~W & C) | (~(W ^ C) & acc)          (one LOP3 per 32 rows per plane)
+// which is the borrow-out of x - c (init 0 => x < c) or of x - c - 1 (init ~0 => x <= c).
+//     Lt = chain(init 0)   Le = chain(init 1)   Ge = ~Lt   Gt = ~Le
+// These are exact boolean functions of the row's bits, hence bit-identical to the
+// reference's MSB -> LSB Mlt/Mgt/Meq recurrences (fle-encoding.h:8039-8042, :8151-8154).
+// Eq / In use the reference's own XNOR-AND chain (fle-encoding.h:7986-7988, :8283-8290).
+//
+// Chains are grouped into passes of up to 4 chains on one column, so each plane word is
+// fetched from shared memory once per pass.  Results fold into "slots": slot 0 lives in a
+// register, slots >= 1 in shared memory; a short list of combine ops finishes the tree.
+// ------------------------------------------------------------------------------------------
+enum PassType : uint8_t { PASS_LT = 0, PASS_EQ = 1, PASS_IN = 2, PASS_CONST = 3 };
+enum FoldOp : uint8_t { FOLD_SET = 0, FOLD_AND = 1, FOLD_OR = 2 };
+
+constexpr int kMaxPasses = 40;
+constexpr int kMaxCombs = 64;
+constexpr int kMaxSlots = 32;
+
+struct PassDesc {
+  uint8_t type;     // PassType
+  uint8_t col;      // column index
+  uint8_t k;        // chains in this pass (1..4); PASS_IN / PASS_CONST: 1
+  uint8_t pad;
+  uint8_t slot[4];  // destination slot per chain
+  uint8_t fold[4];  // FoldOp per chain
+  uint8_t neg[4];   // 1: complement the chain result before folding
+  uint8_t init[4];  // PASS_LT: chain init (0 => '<', 1 => '<='); PASS_CONST: the constant
+  uint32_t lit[4];  // literal per chain (masked to bw bits); PASS_IN: lit[0]=offset, lit[1]=count
+};
+
+struct CombDesc {
+  uint8_t op;  // FOLD_AND / FOLD_OR
+  uint8_t dst; // slot written (== a)
+  uint8_t a;
+  uint8_t b;
+};
+
+struct EvalParams {
+  const uint64_t* planes[FLE_MAX_COLS];  // already offset to first_row's group
+  uint32_t bw[FLE_MAX_COLS];
+  uint32_t col_off[FLE_MAX_COLS];     // byte offset of the column's region inside a stage
+  uint32_t seg_stride[FLE_MAX_COLS];  // byte distance between the 8 skewed segments
+  int32_t ncols, npasses, ncombs, nslots;
+  int32_t gpt;      // groups per thread per tile
+  int32_t nstages;  // TMA pipeline depth
+  uint32_t stage_bytes;
+  uint32_t smem_bar_off, smem_lits_off, smem_slots_off, smem_stage_off;
+  int64_t ngroups;
+  int64_t nrows;
+  uint64_t slot0_init;
+  uint64_t* bitmap;
+  uint64_t* partial;    // per-CTA popcounts (gridDim entries)
+  unsigned int* ticket; // self-resetting completion counter
+  uint64_t* count_out;  // may be null
+  const uint32_t* in_lits;
+  int32_t n_in_lits;
+  int32_t pad;
+  PassDesc passes[kMaxPasses];
+  CombDesc combs[kMaxCombs];
+};
+
+struct LoweredProgram {
+  EvalParams p;                  // passes / combs / nslots / slot0_init filled in
+  std::vector<uint32_t> in_lits; // IN literal pool
+  bool lits_uploaded = false;    // pool already copied to ctx->d_in_lits
+};
+
+// Returns FLE_OK or FLE_E_*; err gets a human-readable reason.
+int lower_program(const fle_col_desc* cols, int ncols, const fle_pred_node* nodes, int nnodes,
+                  LoweredProgram* out, std::string* err);
+
+}  // namespace fle
+
+// ------------------------------------------------------------------------------------------
+// Context
+// ------------------------------------------------------------------------------------------
+struct fle_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int num_sms = 0;
+  int max_smem_optin = 0;
+  int64_t launches = 0;
+  std::string last_error;
+
+  // options
+  int eval_variant = 1;
+  int eval_stages = 0;       // 0 = auto
+  int eval_block = 256;
+  int eval_ctas_per_sm = 0;  // 0 = auto (occupancy)
+  int eval_gpt = 0;          // 0 = auto
+  int codec_variant = 1;
+  int64_t h2d_chunk_rows = 0;  // 0 = auto
+
+  // scratch owned by the context (device)
+  uint64_t* d_partial = nullptr;  // per-CTA counts
+  int partial_cap = 0;
+  unsigned int* d_ticket = nullptr;
+  uint32_t* d_in_lits = nullptr;
+  int in_lits_cap = 0;
+  uint32_t* h_in_lits = nullptr;  // pinned staging for IN literal pools
+  uint64_t* d_count = nullptr;    // 8-byte result slot for host-facing calls
+  uint64_t* h_count = nullptr;    // pinned
+
+  // host-facing pipelines: staging buffers
+  void* d_stage[2] = {nullptr, nullptr};
+  size_t d_stage_cap[2] = {0, 0};
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+  cudaEvent_t ev_done[2] = {nullptr, nullptr};
+};
+
+namespace fle {
+
+int set_cuda_error(fle_ctx* ctx, cudaError_t e, const char* what);
+int set_error(fle_ctx* ctx, int code, const std::string& msg);
+int ensure_scratch(fle_ctx* ctx, int nblocks, int n_in_lits);
+
+#define FLE_CUDA_TRY(ctx, expr)                                   \
+  do {                                                            \
+    cudaError_t _e = (expr);                                      \
+    if (_e != cudaSuccess) return fle::set_cuda_error(ctx, _e, #expr); \
+  } while (0)
+
+// kernels' host launchers (fle_eval.cu, fle_codec.cu, fle_bitmap.cu)
+// lower + upload the IN literal pool (once per program) ...
+int prepare_eval(fle_ctx* ctx, const fle_col_desc* cols, int ncols, const fle_pred_node* nodes,
+                 int nnodes, LoweredProgram* lp);
+// ... then launch it any number of times on device-resident columns
+int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols_dev, int ncols,
+                    int64_t first_row, int64_t n, uint64_t* bitmap_dev, uint64_t* count_dev);
+int launch_eval(fle_ctx* ctx, const fle_col_desc* cols_dev, int ncols, const fle_pred_node* nodes,
+                int nnodes, int64_t first_row, int64_t n, uint64_t* bitmap_dev,
+                uint64_t* count_dev);
+// out = postfix program over K device bitmaps (leaf.col = bitmap index), word by word
+int launch_bitmap_combine(fle_ctx* ctx, const uint64_t* const* leaf_bitmaps_dev, int nleaf,
+                          const fle_pred_node* nodes, int nnodes, int64_t nbits, uint64_t* out_dev,
+                          uint64_t* count_dev);
+int launch_pack_u32(fle_ctx* ctx, const uint32_t* vals_dev, int64_t n, int bw, uint64_t* enc_dev);
+int launch_unpack_u32(fle_ctx* ctx, const uint64_t* enc_dev, int bw, int64_t n, uint32_t* out_dev);
+int launch_bitmap_count(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nbits, uint64_t* count_dev);
+int launch_intersect(fle_ctx* ctx, uint64_t* root_dev, int64_t n_root, const uint64_t* sub_dev,
+                     int64_t n_sub);
+
+}  // namespace fle

@@ -1,0 +1,181 @@
+/* fle_b200.h -- C ABI of libfle_b200.so: the B200 (sm_100a) implementation of the
+ * fixed-length-encoding (FLE) hot path of zuowang/Impala-avx2-parquet-scanner.
+ *
+ * This is the drop-in boundary.  Everything above it (FleEncoder/FleDecoder,
+ * DictDecoder<T>, the SimplePredicate tree, the column-reader batch interface) stays host
+ * C++ (impala-avx2-parquet-scanner_b200/host/) and calls only these entry points.  Plain
+ * pointers and sizes; no C++/torch types.  Each function cites the reference interface it
+ * replaces (file:line in the reference tree).
+ *
+ * Data layout (identical to the reference, fle-encoding.h:8338-8340, :426-430):
+ *   64 values = 1 group = bit_width consecutive little-endian uint64 words; word i holds
+ *   bit i of all 64 values; value k of the group is bit (63 - k) of every word.
+ * Selection bitmaps follow boost::dynamic_bitset<unsigned long> as the reference fills it
+ *   (fle-encoding.h:7989-8008): row r -> bit (r & 63) of uint64 word (r >> 6); a set bit
+ *   means the row PASSES (hdfs-parquet-scanner.cc:1139-1140).  Bits past the last row are 0.
+ *
+ * Conventions: every function returns FLE_OK (0) or a negative FLE_E_* code and never
+ * throws or aborts (the reference's predicate functions return void / DCHECK; its setup
+ * paths return Status -- the host shims map codes to Status / false).  A context is
+ * single-threaded (one scanner thread, one CUDA stream), many contexts may be used
+ * concurrently; there is no hidden global state.  The caller owns every buffer it passes.
+ * "_dev" functions take DEVICE pointers and only enqueue work on the context's stream;
+ * the others take HOST pointers and return after the result is in host memory.
+ * There is no CPU fallback: without a usable CUDA device every call fails with
+ * FLE_E_NODEVICE / FLE_E_CUDA.
+ */
+#ifndef FLE_B200_H
+#define FLE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define FLE_B200_VERSION 100
+
+enum {
+  FLE_OK = 0,
+  FLE_E_INVALID = -1,     /* bad argument (NULL, bit width outside 1..32, malformed program) */
+  FLE_E_NOMEM = -2,       /* host or device allocation failed */
+  FLE_E_CUDA = -3,        /* CUDA runtime error; fle_last_error() has the text */
+  FLE_E_BUFFER = -4,      /* output buffer too small / input shorter than the rows asked for */
+  FLE_E_ALIGN = -5,       /* pointer or row offset not aligned as documented */
+  FLE_E_UNSUPPORTED = -6, /* valid request this build cannot run (e.g. > FLE_MAX_COLS columns) */
+  FLE_E_NODEVICE = -7     /* no CUDA device: the product has no CPU path */
+};
+
+/* Predicate opcodes.  EQ..IN are leaves = FleDecoder::Eq/Lt/Le/Gt/Ge/In
+ * (fle-encoding.h:7962-8313); AND/OR = AndOperate/OrOperate (simple-predicates.h:145-163);
+ * ALL/NONE = the DictDecoder short-circuits `resize(num_rows, true/false)`
+ * (dict-encoding.h:466,476-478,489-491,502-504,514-516,537). */
+enum {
+  FLE_OP_EQ = 0, FLE_OP_LT = 1, FLE_OP_LE = 2, FLE_OP_GT = 3, FLE_OP_GE = 4, FLE_OP_IN = 5,
+  FLE_OP_AND = 6, FLE_OP_OR = 7, FLE_OP_ALL = 8, FLE_OP_NONE = 9
+};
+
+#define FLE_MAX_COLS 8      /* columns per fused evaluation */
+#define FLE_MAX_NODES 64    /* postfix nodes per fused evaluation */
+#define FLE_MAX_IN_CODES 4096
+
+/* One encoded column (chunk / page payload).  `planes` points at the first FLE group, i.e.
+ * AFTER the 1-byte bit-width header DictDecoderBase::SetData strips (dict-encoding.h:185-192).
+ * Nullable columns (max_def_level > 0, hdfs-parquet-scanner.cc:342-345): def_planes is the
+ * 1-bit FLE definition-level stream covering the rows; `planes` then holds only the
+ * non-NULL values, indexed by non-null ordinal.  NULL rows fail every leaf. */
+typedef struct fle_col_desc {
+  const void* planes;
+  uint64_t bytes;         /* byte length readable at planes */
+  int32_t bit_width;      /* 1..32 */
+  int32_t max_def_level;  /* 0 = required column, 1 = nullable */
+  const void* def_planes; /* NULL when max_def_level == 0 */
+  uint64_t def_bytes;
+} fle_col_desc;
+
+/* One node of a postfix (reverse-Polish) predicate program.  Leaves name a column and carry
+ * dictionary CODES pre-encoded on the host (DictDecoder<T>::Eq..In, dict-encoding.h:461-541);
+ * only the low bit_width bits of a code are compared, as in the reference's plane algebra. */
+typedef struct fle_pred_node {
+  int32_t op;            /* FLE_OP_* */
+  int32_t col;           /* leaf: index into cols[] */
+  uint64_t code;         /* EQ/LT/LE/GT/GE literal */
+  const uint64_t* codes; /* IN: host array of ncodes literals (always a HOST pointer) */
+  int32_t ncodes;
+  int32_t reserved;
+} fle_pred_node;
+
+typedef struct fle_ctx fle_ctx;
+
+/* ---- context --------------------------------------------------------------------------- */
+/* cuda_stream: a cudaStream_t to enqueue on (e.g. torch's current stream), or NULL to let the
+ * context create its own non-blocking stream. */
+int fle_ctx_create(int device, void* cuda_stream, fle_ctx** out);
+int fle_ctx_destroy(fle_ctx* ctx);
+int fle_ctx_set_stream(fle_ctx* ctx, void* cuda_stream);
+int fle_ctx_sync(fle_ctx* ctx);
+/* Tuning knobs, all optional: "eval_variant" (0 = direct-load kernel, 1 = TMA-staged
+ * pipeline [default]), "eval_stages", "eval_block", "eval_ctas_per_sm", "eval_gpt",
+ * "codec_variant", "h2d_chunk_rows". */
+int fle_ctx_set_option(fle_ctx* ctx, const char* name, int64_t value);
+int64_t fle_ctx_get_option(fle_ctx* ctx, const char* name);
+/* Number of kernels of this library launched through ctx so far (bench `gpu_launches`). */
+int64_t fle_ctx_launch_count(fle_ctx* ctx);
+const char* fle_last_error(fle_ctx* ctx);
+const char* fle_strerror(int code);
+int fle_version(void);
+int fle_device_count(void);
+
+/* ---- memory helpers (so host C++ needs no CUDA headers) ---------------------------------- */
+int fle_host_alloc(size_t bytes, void** out);   /* pinned host memory */
+int fle_host_free(void* p);
+int fle_dev_alloc(fle_ctx* ctx, size_t bytes, void** out); /* 256-byte aligned device memory */
+int fle_dev_free(fle_ctx* ctx, void* p);
+int fle_h2d(fle_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes); /* async on ctx stream */
+int fle_d2h(fle_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes); /* async on ctx stream */
+
+/* ---- codec ----------------------------------------------------------------------------- */
+/* Byte length FleEncoder::Flush() reports for n values (fle-encoding.h:9806-9811):
+ * max(1, ceil(n / 64)) * bit_width * 8. */
+size_t fle_encoded_bytes(int64_t n, int bit_width);
+
+/* Replaces FleEncoder::Put x n + Flush (fle-encoding.h:8315-8365, :9806; Pack_1..16 and
+ * Pack_16_32 :8367-9803).  vals[i] must be < 2^bit_width (the reference DCHECKs it; here the
+ * high bits are ignored).  Unfilled rows of the last group are written as 0 (the reference
+ * leaves stale staging data there; those rows are never decoded).  FLE_E_BUFFER when
+ * enc_cap < fle_encoded_bytes(n, bw), mirroring Put() == false (fle-encoding.h:8318). */
+int fle_pack_u32(fle_ctx* ctx, const uint32_t* vals, int64_t n, int bit_width, uint8_t* enc,
+                 size_t enc_cap, size_t* enc_len);
+int fle_pack_u32_dev(fle_ctx* ctx, const uint32_t* vals_dev, int64_t n, int bit_width,
+                     uint8_t* enc_dev, size_t enc_cap, size_t* enc_len);
+
+/* Replaces FleDecoder::Get<T>(T*) x n after first_row values were consumed
+ * (fle-encoding.h:404-567; Unpack_1..32 :569-7329) and the whole-group jump of
+ * Get(T*, skip) / Skip (:344-402).  FLE_E_BUFFER when the rows are not inside enc_len,
+ * mirroring Get() == false at the buffer guard (:407).  The _dev variant requires
+ * first_row % 64 == 0 and 16-byte aligned enc_dev (FLE_E_ALIGN otherwise). */
+int fle_unpack_u32(fle_ctx* ctx, const uint8_t* enc, size_t enc_len, int bit_width,
+                   int64_t first_row, int64_t n, uint32_t* out);
+int fle_unpack_u32_dev(fle_ctx* ctx, const uint8_t* enc_dev, size_t enc_len, int bit_width,
+                       int64_t first_row, int64_t n, uint32_t* out_dev);
+
+/* ---- fused predicate evaluation --------------------------------------------------------- */
+/* Replaces, in ONE pass that reads every encoded byte once:
+ *   FleDecoder::Eq/Lt/Le/Gt/Ge/In            fle-encoding.h:7962-8313   (leaves)
+ *   ColumnReader<T>::Eq..In + IntersectBitset hdfs-parquet-scanner.cc:326-445 (nullable cols)
+ *   And/OrOperate::GetBitset                  simple-predicates.h:145-163 (inner nodes)
+ *   the conjunct `&=` loop                    hdfs-parquet-scanner.cc:1857-1862
+ * for rows [first_row, first_row + n) of every column (first_row % 64 == 0).
+ * bitmap_out: ceil(n / 64) uint64 words.  match_count (optional): popcount of the bitmap.
+ * fle_eval takes host column buffers (copied to the device inside the call, overlapped
+ * with evaluation in row chunks); fle_eval_dev takes device-resident columns, bitmap and
+ * count pointers and only enqueues work. */
+int fle_eval(fle_ctx* ctx, const fle_col_desc* cols, int ncols, const fle_pred_node* postfix,
+             int nnodes, int64_t first_row, int64_t n, uint64_t* bitmap_out,
+             uint64_t* match_count);
+int fle_eval_dev(fle_ctx* ctx, const fle_col_desc* cols_dev, int ncols,
+                 const fle_pred_node* postfix, int nnodes, int64_t first_row, int64_t n,
+                 uint64_t* bitmap_out_dev, uint64_t* match_count_dev);
+
+/* ---- bitmap utilities ------------------------------------------------------------------- */
+/* dynamic_bitset::count() over the first nbits bits. */
+int fle_bitmap_count_dev(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nbits,
+                         uint64_t* count_dev);
+/* Replaces ColumnReader<T>::IntersectBitset (hdfs-parquet-scanner.cc:326-331): the i-th set
+ * bit of root (n_root bits) takes bit i of sub; root is updated in place. */
+int fle_intersect_bitset(fle_ctx* ctx, uint64_t* root, int64_t n_root, const uint64_t* sub,
+                         int64_t n_sub);
+int fle_intersect_bitset_dev(fle_ctx* ctx, uint64_t* root_dev, int64_t n_root,
+                             const uint64_t* sub_dev, int64_t n_sub);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLE_B200_H */

@@ -1,0 +1,1 @@
+// Build shim: intentionally empty (fle-encoding.h includes it but uses nothing from it).

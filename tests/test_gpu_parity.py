@@ -1,0 +1,293 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (libfle_b200.so), against
+(1) the golden vectors the reference produced, (2) the CPU oracle on the same seeded inputs and
+(3) size-independent properties at BASELINE.json's full sizes.  Integer/bit work: bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import tail_mask_words, valid_row_mask_planes
+from oracle.oracle import ALL, AND, EQ, GE, GT, IN, LE, LT, NONE, OR
+
+pytestmark = pytest.mark.gpu
+
+OPS = (EQ, LT, LE, GT, GE)
+BWS = list(range(1, 33))
+Q6 = [(GE, 0, 730), (LE, 0, 1094), (AND, None, None), (GE, 1, 5), (LE, 1, 7), (AND, None, None),
+      (AND, None, None), (LT, 2, 23), (AND, None, None)]
+ORV = [(IN, 1, [2, 9]), (EQ, 2, 17), (OR, None, None), (LT, 0, 1200), (AND, None, None), (GT, 1, 8),
+       (OR, None, None)]
+
+
+def popcount(words):
+    return int(np.unpackbits(np.ascontiguousarray(words).view(np.uint8)).sum())
+
+
+# ------------------------------------------------------------------------------------------
+# golden vectors (outputs of the reference's own code)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bw", BWS)
+def test_codec_vs_golden(ctx, golden, bw):
+    n = int(golden["meta_n"][0])
+    vals, words = golden[f"vals_{bw}"], golden[f"words_{bw}"]
+    mine = ctx.pack(vals, bw)
+    assert mine.shape == words.shape
+    full = (n // 64) * bw
+    assert (mine[:full] == words[:full]).all()
+    m = valid_row_mask_planes(n % 64)
+    assert ((mine[full:] & m) == (words[full:] & m)).all()
+    assert (mine[full:] & ~m == 0).all()  # our padding rows are zero
+    assert (ctx.unpack(words, bw, 0, n) == vals).all()  # stale tail bits in `words` must not leak
+    for first, cnt in ((0, 1), (1, 1), (13, 100), (63, 2), (64, 64), (100, n - 100), (n - 1, 1)):
+        assert (ctx.unpack(words, bw, first, cnt) == vals[first:first + cnt]).all(), (first, cnt)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("bw", BWS)
+def test_predicates_vs_golden(ctx, golden, bw, variant):
+    ctx.set_option("eval_variant", variant)
+    try:
+        n = int(golden["meta_n"][0])
+        words, lits, G = golden[f"words_{bw}"], golden[f"pred_lits_{bw}"], golden[f"pred_{bw}"]
+        for oi, op in enumerate(OPS):
+            for li, lit in enumerate(lits):
+                for pi, pre in ((0, 0), (2, 64)):
+                    bm, cnt = ctx.eval([(words, bw)], [(op, 0, int(lit))], n - pre, first_row=pre)
+                    want = G[oi, li, pi, : len(bm)]
+                    assert (bm == want).all(), (bw, op, int(lit), pre)
+                    assert cnt == popcount(want)
+        for pi, pre in ((0, 0), (2, 64)):
+            bm, cnt = ctx.eval([(words, bw)], [(IN, 0, golden[f"in_lits_{bw}"])], n - pre, first_row=pre)
+            assert (bm == golden[f"in_{bw}"][pi, : len(bm)]).all()
+        bm, _ = ctx.eval([(words, bw)], [(GE, 0, int(golden[f"win_lit_{bw}"][0]))], n)
+        assert (bm == golden[f"win_ge_{bw}"]).all()
+    finally:
+        ctx.set_option("eval_variant", 1)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_trees_vs_golden(ctx, golden, variant):
+    ctx.set_option("eval_variant", variant)
+    try:
+        n = int(golden["tree_n"][0])
+        cols = [(golden[f"tree_words_{i}"], bw) for i, bw in enumerate((12, 4, 6))]
+        bm, cnt = ctx.eval(cols, Q6, n)
+        assert (bm == golden["tree_q6"]).all() and cnt == popcount(golden["tree_q6"])
+        bm, cnt = ctx.eval(cols, ORV, n)
+        assert (bm == golden["tree_or"]).all() and cnt == popcount(golden["tree_or"])
+    finally:
+        ctx.set_option("eval_variant", 1)
+
+
+# ------------------------------------------------------------------------------------------
+# seeded random inputs vs the oracle
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bw", BWS)
+def test_single_column_vs_oracle(ctx, oracle, bw):
+    rng = np.random.default_rng(0xF1E00000 + bw)
+    n = 64 * 4096 * 3 + 64 * 37 + 29  # several TMA tiles + ragged groups + ragged rows
+    vals = rng.integers(0, 1 << bw, size=n, dtype=np.uint64).astype(np.uint32)
+    words = oracle.pack(vals, bw)
+    assert (ctx.pack(vals, bw) == words).all()
+    assert (ctx.unpack(words, bw, 0, n) == vals).all()
+    D = 1 << bw
+    lo, hi = D // 4, max(D // 4, (3 * D) // 4 - 1)
+    progs = [
+        [(GE, 0, lo), (LE, 0, hi), (AND, None, None)],
+        [(LT, 0, lo), (GT, 0, hi), (OR, None, None)],
+        [(EQ, 0, int(vals[11]))],
+        [(IN, 0, rng.choice(vals, size=8).astype(np.uint64))],
+    ]
+    for variant in (1, 0):
+        ctx.set_option("eval_variant", variant)
+        for prog in progs:
+            bm, cnt = ctx.eval([(words, bw)], prog, n)
+            want, wcnt = oracle.eval_tree([(words, bw)], prog, n)
+            assert (bm == want).all() and cnt == wcnt, (bw, variant, prog[0][0])
+    ctx.set_option("eval_variant", 1)
+
+
+@pytest.mark.parametrize("opts", [dict(), dict(eval_block=128), dict(eval_stages=2, eval_gpt=2),
+                                  dict(eval_stages=4, eval_ctas_per_sm=1), dict(h2d_chunk_rows=64 * 4096)])
+def test_multi_column_programs_vs_oracle(ctx, oracle, opts):
+    rng = np.random.default_rng(2024)
+    n = 64 * 20000 + 17
+    bws = (12, 4, 6, 3, 16)
+    doms = (2526, 11, 50, 7, 40000)
+    vals = [rng.integers(0, d, size=n).astype(np.uint32) for d in doms]
+    cols = [(oracle.pack(v, bw), bw) for v, bw in zip(vals, bws)]
+    progs = {
+        "q6": (cols[:3], Q6),
+        "or": (cols[:3], ORV),
+        "q12": ([cols[3], cols[0]], [(IN, 0, [1, 4]), (GE, 1, 400), (AND, None, None), (LT, 1, 765), (AND, None, None)]),
+        "in64": ([cols[4]], [(IN, 0, rng.choice(vals[4], size=64).astype(np.uint64))]),
+        "in256_and": ([cols[0], cols[2]], [(IN, 0, rng.choice(vals[0], size=256).astype(np.uint64)), (LT, 1, 30),
+                                            (AND, None, None)]),
+        "consts": (cols[:2], [(ALL, None, None), (LT, 0, 1000), (AND, None, None), (NONE, None, None), (OR, None, None),
+                              (GE, 1, 3), (AND, None, None)]),
+        "deep": (cols[:3], [(LT, 0, 500), (GT, 0, 2000), (OR, None, None), (EQ, 1, 3), (EQ, 1, 4), (OR, None, None),
+                            (AND, None, None), (GE, 2, 10), (LE, 2, 40), (AND, None, None), (OR, None, None),
+                            (LT, 1, 9), (AND, None, None)]),
+        "five_on_one": ([cols[0]], [(GE, 0, 10), (LE, 0, 2500), (AND, None, None), (GT, 0, 11), (AND, None, None),
+                                     (LT, 0, 2499), (AND, None, None), (GE, 0, 12), (AND, None, None)]),
+    }
+    for k, v in opts.items():
+        ctx.set_option(k, v)
+    try:
+        for name, (pc, prog) in progs.items():
+            bm, cnt = ctx.eval(pc, prog, n)
+            want, wcnt = oracle.eval_tree(pc, prog, n)
+            assert (bm == want).all() and cnt == wcnt, name
+    finally:
+        for k in opts:
+            ctx.set_option(k, {"eval_block": 256}.get(k, 0))
+
+
+def test_edge_sizes_and_errors(ctx, oracle):
+    import fle_b200
+    from fle_b200 import capi
+    rng = np.random.default_rng(9)
+    for n in (0, 1, 63, 64, 65, 127, 128, 129, 4095, 4096, 4097):
+        vals = rng.integers(0, 1 << 9, size=n).astype(np.uint32)
+        words = oracle.pack(vals, 9)
+        assert (ctx.pack(vals, 9) == words).all()
+        if n:
+            assert (ctx.unpack(words, 9, 0, n) == vals).all()
+        bm, cnt = ctx.eval([(words, 9)], [(LT, 0, 200)], n)
+        want, wcnt = oracle.pred(LT, words, 9, 0, n, [200])
+        assert (bm == want).all() and cnt == wcnt
+    w = oracle.pack(np.arange(640, dtype=np.uint32) % 512, 9)
+    for bad_bw in (0, 33, -1):
+        with pytest.raises(fle_b200.FleError) as ei:
+            ctx.eval([(w, bad_bw)], [(LT, 0, 1)], 640)
+        assert ei.value.code == capi.E_INVALID
+    with pytest.raises(fle_b200.FleError) as ei:  # rows beyond the buffer == Get() false at the guard
+        ctx.unpack(w, 9, 0, 641)
+    assert ei.value.code == capi.E_BUFFER
+    with pytest.raises(fle_b200.FleError) as ei:
+        ctx.eval([(w, 9)], [(LT, 0, 1)], 100, first_row=7)
+    assert ei.value.code == capi.E_ALIGN
+    with pytest.raises(fle_b200.FleError) as ei:
+        ctx.eval([(w, 9)], [(LT, 0, 1), (AND, None, None)], 100)
+    assert ei.value.code == capi.E_INVALID
+    with pytest.raises(fle_b200.FleError) as ei:
+        ctx.eval([(w, 9)], [(LT, 1, 1)], 100)
+    assert ei.value.code == capi.E_INVALID
+    # literal wider than the column: only bw bits take part, as in the reference's plane algebra
+    bm, _ = ctx.eval([(w, 9)], [(EQ, 0, 512 + 5)], 640)
+    assert (bm == oracle.pred(EQ, w, 9, 0, 640, [5])[0]).all()
+
+
+def test_intersect_bitset_vs_oracle(ctx, oracle):
+    rng = np.random.default_rng(31)
+    for n, p_root in ((1, 1.0), (64, 0.5), (1000, 0.7), (64 * 5000 + 3, 0.97), (64 * 5000 + 3, 0.03), (70000, 1.0)):
+        root_bits = rng.random(n) < p_root
+        m = int(root_bits.sum())
+        sub_bits = rng.random(m) < 0.4
+        root = np.packbits(root_bits, bitorder="little")
+        root = np.pad(root, (0, (-len(root)) % 8)).view(np.uint64)
+        sub = np.packbits(sub_bits, bitorder="little")
+        sub = np.pad(sub, (0, (-len(sub)) % 8)).view(np.uint64)
+        want, _ = oracle.intersect_bitset(root, n, sub)
+        got = ctx.intersect_bitset(root, n, sub, m)
+        assert (got == want).all(), (n, p_root)
+
+
+@pytest.mark.parametrize("null_frac", [0.0, 0.02, 0.6])
+def test_nullable_columns_vs_oracle(ctx, oracle, null_frac):
+    """ColumnReader<T>::Eq..In for max_def_level > 0 (hdfs-parquet-scanner.cc:333-445)."""
+    rng = np.random.default_rng(55)
+    n = 64 * 3000 + 21
+    notnull = [rng.random(n) >= null_frac, rng.random(n) >= null_frac / 2]
+    bws, doms = (12, 5), (2526, 25)
+    cols, ocols = [], []
+    for nn, bw, d in zip(notnull, bws, doms):
+        data = rng.integers(0, d, size=int(nn.sum())).astype(np.uint32)
+        cols.append((oracle.pack(data, bw), bw, oracle.pack(nn.astype(np.uint32), 1)))
+        ocols.append((data, nn))
+    req = rng.integers(0, 50, size=n).astype(np.uint32)
+    cols.append((oracle.pack(req, 6), 6))
+    prog = [(GE, 0, 730), (LE, 0, 1094), (AND, None, None), (IN, 1, [3, 4, 20]), (OR, None, None), (LT, 2, 23),
+            (AND, None, None)]
+
+    def leaf(op, ci, lits):
+        if ci == 2:
+            return oracle.pred(op, cols[2][0], 6, 0, n, lits)[0]
+        data, nn = ocols[ci]
+        root = oracle.pred(EQ, cols[ci][2], 1, 0, n, [1])[0]           # fle_def_levels_->Eq(n, bits, max_def)
+        sub = oracle.pred(op, cols[ci][0], bws[ci], 0, len(data), lits)[0]  # dict_decoder_->Op(count, ...)
+        return oracle.intersect_bitset(root, n, sub)[0]                # IntersectBitset
+
+    st = []
+    for op, ci, lits in prog:
+        if op <= IN:
+            st.append(leaf(op, ci, lits))
+        else:
+            b = st.pop()
+            st[-1] = st[-1] & b if op == AND else st[-1] | b
+    bm, cnt = ctx.eval(cols, prog, n)
+    assert (bm == st[0]).all() and cnt == popcount(st[0])
+
+
+# ------------------------------------------------------------------------------------------
+# device-resident API at BASELINE.json sizes: size-independent properties
+# ------------------------------------------------------------------------------------------
+def _torch_bits_to_count(bitmap):
+    import torch
+    b = bitmap.view(torch.uint8)
+    lut = torch.tensor([bin(i).count("1") for i in range(256)], dtype=torch.int64, device=b.device)
+    return int(lut[b.long()].sum().item())
+
+
+@pytest.mark.parametrize("bw", [1, 4, 7, 8, 12, 13, 16, 17, 24, 32])
+def test_cfg0_roundtrip_16M(ctx, bw):
+    """config 0 (fle-benchmark shape): 16 Mi values, encode -> decode round trip on the device."""
+    import torch
+    n = 16 * 1024 * 1024
+    g = torch.Generator(device="cuda").manual_seed(0xF1E0 + bw)
+    vals = torch.randint(0, 2 ** bw, (n,), generator=g, device="cuda", dtype=torch.int64).to(torch.int32)
+    words = ctx.pack_dev(vals, bw)
+    out = ctx.unpack_dev(words, bw, 0, n)
+    assert torch.equal(out, vals)
+    # plane image check on a slice: plane i of group g, bit 63-k == bit i of value 64g+k
+    k = 64 * 1000
+    sl = (vals[:k].to(torch.int64) & 0xFFFFFFFF).view(-1, 64)
+    for i in (0, bw - 1):
+        bits = (sl >> i) & 1
+        weights = torch.tensor([1 << (63 - j) if j > 0 else -(1 << 63) for j in range(64)], device="cuda", dtype=torch.int64)
+        plane = (bits * weights).sum(dim=1)
+        assert torch.equal(words.view(-1, bw)[:1000, i], plane)
+    # unpack from an offset group
+    assert torch.equal(ctx.unpack_dev(words, bw, 64 * 777, 12345), vals[64 * 777: 64 * 777 + 12345])
+
+
+def test_cfg1_between_full_size(ctx):
+    """config 1: N = 600,037,902 (SF100 lineitem rows), bw 12 BETWEEN; the count must equal a
+    plain torch compare on the values, both kernels must agree bit for bit, and the bitmap's
+    popcount must equal the reported count (checksum of checksums)."""
+    import torch
+    n = 600_037_902
+    bw = 12
+    g = torch.Generator(device="cuda").manual_seed(0xF1E00100)
+    vals = torch.randint(0, 4096, (n,), generator=g, device="cuda", dtype=torch.int32)
+    words = ctx.pack_dev(vals, bw)
+    lo, hi = 1000, 1409  # ~10 %
+    want = int(((vals >= lo) & (vals <= hi)).sum().item())
+    prog = [(GE, 0, lo), (LE, 0, hi), (AND, None, None)]
+    bm1, c1 = ctx.eval_dev([(words, bw)], prog, n)
+    torch.cuda.synchronize()
+    assert int(c1.item()) == want
+    assert _torch_bits_to_count(bm1) == want
+    ctx.set_option("eval_variant", 0)
+    try:
+        bm0, c0 = ctx.eval_dev([(words, bw)], prog, n)
+        torch.cuda.synchronize()
+    finally:
+        ctx.set_option("eval_variant", 1)
+    assert int(c0.item()) == want and torch.equal(bm0, bm1)
+    # spot-check the bitmap against the values
+    idx = torch.randint(0, n, (100000,), device="cuda")
+    bit = (bm1[idx >> 6] >> (idx & 63)) & 1
+    assert torch.equal(bit.bool(), (vals[idx] >= lo) & (vals[idx] <= hi))
+    del vals
+    cnt = ctx.bitmap_count_dev(bm1, n)
+    torch.cuda.synchronize()
+    assert int(cnt.item()) == want
