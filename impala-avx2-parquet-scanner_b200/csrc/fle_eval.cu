@@ -434,13 +434,11 @@ int lower_program(const fle_col_desc* cols, int ncols, const fle_pred_node* node
   P.slot0_init = flat ? (flat_fold == FOLD_AND ? ~0ull : 0ull) : 0ull;
 
   std::vector<Chain> chains;
+  // General mode: every leaf owns a slot for the whole evaluation, because ALL passes run
+  // before ANY combine op (passes are regrouped by column, not kept in postfix order).
   std::vector<int> stack;       // slot ids (general mode)
-  std::vector<bool> used(kMaxSlots, false);
-  auto alloc_slot = [&]() {
-    for (int s = 0; s < kMaxSlots; ++s)
-      if (!used[s]) { used[s] = true; return s; }
-    return -1;
-  };
+  int next_slot = 0;
+  auto alloc_slot = [&]() { return next_slot < kMaxSlots ? next_slot++ : -1; };
   int max_slot = 0;
   for (int i = 0; i < nnodes; ++i) {
     const fle_pred_node& nd = nodes[i];
@@ -451,14 +449,13 @@ int lower_program(const fle_col_desc* cols, int ncols, const fle_pred_node* node
       if (P.ncombs >= kMaxCombs) return fail(FLE_E_UNSUPPORTED, "predicate tree too large");
       P.combs[P.ncombs++] = CombDesc{(uint8_t)(nd.op == FLE_OP_AND ? FOLD_AND : FOLD_OR),
                                      (uint8_t)a, (uint8_t)a, (uint8_t)b};
-      used[b] = false;
       continue;
     }
     int slot = 0;
     uint8_t fold = flat_fold;
     if (!flat) {
       slot = alloc_slot();
-      if (slot < 0) return fail(FLE_E_UNSUPPORTED, "predicate tree too deep");
+      if (slot < 0) return fail(FLE_E_UNSUPPORTED, "too many leaves in a mixed AND/OR tree");
       stack.push_back(slot);
       fold = FOLD_SET;
       max_slot = std::max(max_slot, slot);

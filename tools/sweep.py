@@ -1,0 +1,234 @@
+#!/usr/bin/env python
+"""Kernel sweeps on one B200 (device-resident inputs, CUDA events, min/median of `reps`).
+
+    python tools/sweep.py between|codec|programs|tune|all [--rows N] [--out gpurun_out/sweep.jsonl]
+
+Every record: {"what", "bw", ..., "ms_min", "ms_med", "alg_bytes", "GBps", "frac"} where
+alg_bytes is the algorithmic traffic of DESIGN.md (planes read once + bitmap / values written
+once) and frac is against MEASURED_PEAKS.json's HBM copy bandwidth."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import fle_b200  # noqa: E402
+from fle_b200 import AND, EQ, GE, GT, IN, LE, LT, OR  # noqa: E402
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+PEAK = peak()
+
+
+def timeit(fn, reps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return min(ts), statistics.median(ts)
+
+
+def rec(out, **kw):
+    if "alg_bytes" in kw and "ms_min" in kw:
+        kw["GBps"] = kw["alg_bytes"] / (kw["ms_min"] * 1e-3) / 1e9
+        kw["GBps_med"] = kw["alg_bytes"] / (kw["ms_med"] * 1e-3) / 1e9
+        kw["frac"] = kw["GBps"] / PEAK
+    line = json.dumps(kw)
+    print(line, flush=True)
+    out.write(line + "\n")
+    out.flush()
+
+
+def make_col(ctx, n, bw, dom=None, seed=1):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    hi = dom if dom else (1 << bw)
+    v = torch.randint(0, hi, (n,), generator=g, device="cuda", dtype=torch.int64).to(torch.int32)
+    w = ctx.pack_dev(v, bw)
+    torch.cuda.synchronize()
+    return v, w
+
+
+def sweep_between(ctx, out, n, variants=(1, 0), bws=range(1, 33)):
+    G = (n + 63) // 64
+    bm = torch.empty(G, dtype=torch.int64, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for bw in bws:
+        v, w = make_col(ctx, n, bw, seed=bw)
+        D = 1 << bw
+        lo = D // 4
+        hi = max(lo, lo + D // 10 - 1)
+        prog = [(GE, 0, lo), (LE, 0, hi), (AND, None, None)]
+        want = int(((v.to(torch.int64) & 0xFFFFFFFF >= lo) & ((v.to(torch.int64) & 0xFFFFFFFF) <= hi)).sum().item()) if False else None
+        del v
+        cols = [(w, bw)]
+        prep = (ctx.make_col_descs(cols),) + fle_b200.capi._build_program(prog)
+        for var in variants:
+            ctx.set_option("eval_variant", var)
+            mn, md = timeit(lambda: ctx.eval_dev(cols, prog, n, bitmap=bm, count=cnt, prepared=prep))
+            rec(out, what="between", variant=var, bw=bw, rows=n, ms_min=mn, ms_med=md, alg_bytes=G * bw * 8 + G * 8,
+                rows_per_s=n / (mn * 1e-3), count=int(cnt.item()))
+        ctx.set_option("eval_variant", 1)
+        del w
+        torch.cuda.empty_cache()
+
+
+def sweep_selectivity(ctx, out, n, bw=12):
+    G = (n + 63) // 64
+    bm = torch.empty(G, dtype=torch.int64, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    v, w = make_col(ctx, n, bw, seed=99)
+    del v
+    cols = [(w, bw)]
+    D = 1 << bw
+    for sel in (1, 10, 20, 30, 50, 80, 100):
+        width = max(1, round(sel * D / 100))
+        lo = (D - width) // 2
+        prog = [(GE, 0, lo), (LE, 0, lo + width - 1), (AND, None, None)]
+        prep = (ctx.make_col_descs(cols),) + fle_b200.capi._build_program(prog)
+        mn, md = timeit(lambda: ctx.eval_dev(cols, prog, n, bitmap=bm, count=cnt, prepared=prep))
+        rec(out, what="selectivity", sel_pct=sel, bw=bw, rows=n, ms_min=mn, ms_med=md, alg_bytes=G * bw * 8 + G * 8,
+            rows_per_s=n / (mn * 1e-3), observed_sel=int(cnt.item()) / n)
+
+
+def sweep_codec(ctx, out, n, bws=range(1, 33)):
+    G = (n + 63) // 64
+    for bw in bws:
+        v, w = make_col(ctx, n, bw, seed=100 + bw)
+        o = torch.empty(n, dtype=torch.int32, device="cuda")
+        mn, md = timeit(lambda: ctx.unpack_dev(w, bw, 0, n, out=o))
+        ok = bool(torch.equal(o, v))
+        rec(out, what="unpack", bw=bw, values=n, ms_min=mn, ms_med=md, alg_bytes=G * bw * 8 + n * 4,
+            values_per_s=n / (mn * 1e-3), ok=ok)
+        w2 = torch.empty_like(w)
+        mn, md = timeit(lambda: ctx.pack_dev(v, bw, out=w2))
+        ok = bool(torch.equal(w2, w))
+        rec(out, what="pack", bw=bw, values=n, ms_min=mn, ms_med=md, alg_bytes=G * bw * 8 + n * 4,
+            values_per_s=n / (mn * 1e-3), ok=ok)
+        del v, w, o, w2
+        torch.cuda.empty_cache()
+
+
+def sweep_programs(ctx, out, n):
+    G = (n + 63) // 64
+    bm = torch.empty(G, dtype=torch.int64, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    spec = {"shipdate": (2526, 12), "discount": (11, 4), "quantity": (50, 6), "shipmode": (7, 3), "instruct": (4, 2),
+            "receipt": (2526, 12), "wide16": (40000, 16)}
+    cols = {}
+    for i, (k, (d, bw)) in enumerate(spec.items()):
+        v, w = make_col(ctx, n, bw, dom=d, seed=200 + i)
+        del v
+        cols[k] = (w, bw)
+    g = torch.Generator().manual_seed(5)
+    programs = {
+        "q6": (["shipdate", "discount", "quantity"],
+               [(GE, 0, 730), (LE, 0, 1094), (AND,), (GE, 1, 5), (LE, 1, 7), (AND,), (AND,), (LT, 2, 23), (AND,)]),
+        "q12": (["shipmode", "receipt"], [(IN, 0, [1, 4]), (GE, 1, 730), (AND,), (LT, 1, 1095), (AND,)]),
+        "q14": (["shipdate"], [(GE, 0, 1339), (LT, 0, 1369), (AND,)]),
+        "or_variant": (["shipmode", "instruct", "quantity"], [(IN, 0, [1, 4]), (EQ, 1, 2), (OR,), (LT, 2, 23), (AND,)]),
+        "in8_bw12": (["shipdate"], [(IN, 0, torch.randint(0, 2526, (8,), generator=g).tolist())]),
+        "in64_bw12": (["shipdate"], [(IN, 0, torch.randint(0, 2526, (64,), generator=g).tolist())]),
+        "in256_bw12": (["shipdate"], [(IN, 0, torch.randint(0, 2526, (256,), generator=g).tolist())]),
+        "in8_bw16": (["wide16"], [(IN, 0, torch.randint(0, 40000, (8,), generator=g).tolist())]),
+        "in64_bw16": (["wide16"], [(IN, 0, torch.randint(0, 40000, (64,), generator=g).tolist())]),
+        "in256_bw16": (["wide16"], [(IN, 0, torch.randint(0, 40000, (256,), generator=g).tolist())]),
+    }
+    for name, (cn, prog) in programs.items():
+        pc = [cols[c] for c in cn]
+        prog = [tuple(p) + (None,) * (3 - len(p)) for p in prog]
+        prep = (ctx.make_col_descs(pc),) + fle_b200.capi._build_program(prog)
+        sum_bw = sum(bw for _, bw in pc)
+        for var in (1, 0):
+            ctx.set_option("eval_variant", var)
+            mn, md = timeit(lambda: ctx.eval_dev(pc, prog, n, bitmap=bm, count=cnt, prepared=prep), reps=5 if "in256" in name else 10)
+            rec(out, what="program", name=name, variant=var, rows=n, sum_bw=sum_bw, ms_min=mn, ms_med=md,
+                alg_bytes=G * sum_bw * 8 + G * 8, rows_per_s=n / (mn * 1e-3), count=int(cnt.item()))
+        ctx.set_option("eval_variant", 1)
+
+
+def sweep_tune(ctx, out, n):
+    G = (n + 63) // 64
+    bm = torch.empty(G, dtype=torch.int64, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    cases = {}
+    v, w12 = make_col(ctx, n, 12, seed=1)
+    del v
+    cases["between12"] = ([(w12, 12)], [(GE, 0, 1000), (LE, 0, 1409), (AND, None, None)], 12)
+    q6c = []
+    for i, (d, bw) in enumerate(((2526, 12), (11, 4), (50, 6))):
+        v, w = make_col(ctx, n, bw, dom=d, seed=300 + i)
+        del v
+        q6c.append((w, bw))
+    cases["q6"] = (q6c, [(GE, 0, 730), (LE, 0, 1094), (AND, None, None), (GE, 1, 5), (LE, 1, 7), (AND, None, None),
+                         (AND, None, None), (LT, 2, 23), (AND, None, None)], 22)
+    for bwx in (1, 4, 32):
+        v, w = make_col(ctx, n, bwx, seed=400 + bwx)
+        del v
+        cases[f"lt{bwx}"] = ([(w, bwx)], [(LT, 0, (1 << bwx) // 2)], bwx)
+    for cname, (pc, prog, sum_bw) in cases.items():
+        prep = (ctx.make_col_descs(pc),) + fle_b200.capi._build_program(prog)
+        for block in (256, 128):
+            for stages in (0, 2, 3, 4, 6):
+                for gpt in (0, 1, 2, 4):
+                    for cps in (0, 1, 2):
+                        ctx.set_option("eval_block", block)
+                        ctx.set_option("eval_stages", stages)
+                        ctx.set_option("eval_gpt", gpt)
+                        ctx.set_option("eval_ctas_per_sm", cps)
+                        try:
+                            mn, md = timeit(lambda: ctx.eval_dev(pc, prog, n, bitmap=bm, count=cnt, prepared=prep), reps=5, warm=2)
+                        except fle_b200.FleError as e:
+                            rec(out, what="tune", case=cname, block=block, stages=stages, gpt=gpt, ctas=cps, error=str(e))
+                            continue
+                        rec(out, what="tune", case=cname, block=block, stages=stages, gpt=gpt, ctas=cps, ms_min=mn,
+                            ms_med=md, alg_bytes=G * sum_bw * 8 + G * 8)
+    for k, d in (("eval_block", 256), ("eval_stages", 0), ("eval_gpt", 0), ("eval_ctas_per_sm", 0)):
+        ctx.set_option(k, d)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", nargs="+")
+    ap.add_argument("--rows", type=int, default=1 << 28)
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.jsonl"))
+    args = ap.parse_args()
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    torch.cuda.set_device(0)
+    ctx = fle_b200.FleContext(0, torch.cuda.current_stream().cuda_stream)
+    with open(args.out, "a") as out:
+        what = set(args.what)
+        if what & {"between", "all"}:
+            sweep_between(ctx, out, args.rows)
+        if what & {"selectivity", "all"}:
+            sweep_selectivity(ctx, out, args.rows)
+        if what & {"codec", "all"}:
+            sweep_codec(ctx, out, min(args.rows, 1 << 26))
+        if what & {"programs", "all"}:
+            sweep_programs(ctx, out, args.rows)
+        if what & {"tune"}:
+            sweep_tune(ctx, out, args.rows)
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
