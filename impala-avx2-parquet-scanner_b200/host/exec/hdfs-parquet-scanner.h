@@ -1,0 +1,606 @@
+// Host-side mirror of the column-reader batch interface of the reference's Parquet scanner
+// (exec/hdfs-parquet-scanner.{h,cc}) -- only the part that sits on the FLE hot path:
+//
+//   BaseColumnReader / ColumnReader<T>      hdfs-parquet-scanner.cc:142-302, :304-560
+//     ReadDataPage / InitDataPage           :730-924, :448-472   (page body framing only)
+//     Eq/Lt/Le/Gt/Ge/In + IntersectBitset   :326-445
+//     ReadValue(skip) / SkipValue / ReadSlot(skip) / SkipSlot   :1006-1035, :515-547
+//     (required columns: the reference's ReadDefinitionLevel returns 1 and then compares it
+//      with max_def_level() == 0, which would turn every value into NULL; here every row of
+//      a required column is defined.  Impala's own writer only produces nullable columns.)
+//   HdfsParquetScanner::Eq<T>..In<T>        hdfs-parquet-scanner.h:91-102, .cc:1867-1907
+//   EvalSimplePredicates                    .cc:1837-1865
+//   AssembleRows, simple-predicate branch   .cc:1101-1181
+//
+// Everything the reference gets from the rest of Impala (thrift page headers, DiskIoMgr
+// streams, MemPool, Tuple/RowBatch, RuntimeState) is out of scope: pages are handed in as
+// in-memory uncompressed page bodies and tuples are rows of a flat byte buffer.
+//
+// Page body layout (hdfs-parquet-table-writer.cc:567-575, hdfs-parquet-scanner.cc:882-919,
+// dict-encoding.h:185-192):
+//     nullable column:  [int32 num_def_bytes][def levels: FLE, bit width 1][u8 bw][FLE groups]
+//     required column:  [u8 bw][FLE groups]
+//
+// Two evaluation paths, same results:
+//   * per leaf (the reference's structure): every leaf call goes through ColumnReader<T> ->
+//     DictDecoder<T> -> FleDecoder, which evaluates the WHOLE page on the GPU on first use and
+//     then serves the <=1024-row windows from the cached bitmap;
+//   * fused (default): the whole SimplePredicate forest is lowered to one postfix program and
+//     ONE fle_eval call covers every column for the span of rows during which no reader
+//     changes page; windows are bit slices of that result.  Used whenever the span starts on
+//     a 64-row group boundary of every page involved (always true for page-aligned row
+//     groups); otherwise the per-leaf path takes over for that window.
+#ifndef IMPALA_EXEC_HDFS_PARQUET_SCANNER_H
+#define IMPALA_EXEC_HDFS_PARQUET_SCANNER_H
+
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include <boost/dynamic_bitset.hpp>
+
+#include "exprs/simple-predicates.h"
+#include "util/dict-encoding.h"
+#include "util/fle-encoding.h"
+
+namespace impala {
+
+class Status {
+ public:
+  Status() : ok_(true) {}
+  explicit Status(const std::string& msg) : ok_(false), msg_(msg) {}
+  bool ok() const { return ok_; }
+  const std::string& GetErrorMsg() const { return msg_; }
+  static Status OK() { return Status(); }
+ private:
+  bool ok_;
+  std::string msg_;
+};
+
+// parquet.thrift:206-224 (the reference adds the two non-standard FLE encodings)
+namespace parquet_encoding {
+enum type { PLAIN = 0, PLAIN_DICTIONARY = 2, RLE = 3, BIT_PACKED = 4, FLE = 9, FLE_DICTIONARY = 10 };
+}
+
+class HdfsParquetScanner {
+ public:
+  struct DataPage {
+    const uint8_t* data;  // uncompressed page body
+    int size;
+    int num_values;       // data_page_header.num_values (rows, NULLs included)
+    int encoding;         // parquet_encoding::FLE_DICTIONARY
+    DataPage() : data(NULL), size(0), num_values(0), encoding(parquet_encoding::FLE_DICTIONARY) {}
+    DataPage(const uint8_t* d, int s, int n) : data(d), size(s), num_values(n),
+        encoding(parquet_encoding::FLE_DICTIONARY) {}
+  };
+
+  class BaseColumnReader;
+  template<typename T> class ColumnReader;
+
+  HdfsParquetScanner() : tuple_size_(0), fused_enabled_(true), fused_pos_(0), fused_rows_(0),
+      fused_evals_(0), leaf_windows_(0) {}
+  ~HdfsParquetScanner();
+
+  // CreateColumnReaders/CreateReader (:1410-1451, :670-720) + InitColumns (:1453-1531) for
+  // one column chunk: its sorted PLAIN dictionary page and its data pages.  Returns the
+  // column-reader index used by the predicate leaves (slot_idx, scalar-fn-call.cc:940-942).
+  template<typename T>
+  int AddColumn(int max_def_level, const uint8_t* dict_page, int dict_len,
+                const std::vector<DataPage>& pages);
+
+  // CreateSimplePredicates (:1825-1835): one root per conjunct; the scanner ANDs them.
+  void AddSimplePredicate(SimplePredicate* root) { simple_predicates_.push_back(root); }
+
+  // typed trampolines (hdfs-parquet-scanner.h:91-102, .cc:1867-1907)
+  template<typename T> void Eq(int idx, int64_t num_rows, boost::dynamic_bitset<>& skip_bitset, T& val);
+  template<typename T> void Lt(int idx, int64_t num_rows, boost::dynamic_bitset<>& skip_bitset, T& val);
+  template<typename T> void Le(int idx, int64_t num_rows, boost::dynamic_bitset<>& skip_bitset, T& val);
+  template<typename T> void Gt(int idx, int64_t num_rows, boost::dynamic_bitset<>& skip_bitset, T& val);
+  template<typename T> void Ge(int idx, int64_t num_rows, boost::dynamic_bitset<>& skip_bitset, T& val);
+  template<typename T> void In(int idx, int64_t num_rows, boost::dynamic_bitset<>& skip_bitset, std::vector<T>& vals);
+
+  // :1837-1865.  Appends min(1024, rows left in every reader's page) bits to skip_bitset; a
+  // set bit means the row PASSES (:1139-1140).  false = no more data or parse_status_ not ok.
+  bool EvalSimplePredicates(boost::dynamic_bitset<>& skip_bitset);
+
+  // Simple-predicate branch of AssembleRows (:1101-1181): evaluates window after window and
+  // materialises the surviving rows, column by column, with ReadValue(skip).  Tuples are
+  // appended to `rows` (tuple_size() bytes each: one null-indicator byte per column, then the
+  // slots in AddColumn order).  Returns the number of rows that passed.
+  Status AssembleRows(int64_t expected_rows_in_group, std::vector<uint8_t>* rows, int64_t* num_passed);
+
+  int tuple_size() const { return tuple_size_; }
+  int slot_offset(int idx) const;
+  int null_offset(int idx) const { return idx; }
+  int num_columns() const { return static_cast<int>(column_readers_.size()); }
+  const Status& parse_status() const { return parse_status_; }
+
+  // false: force the reference's one-pass-per-leaf structure (still on the GPU).
+  void set_fused(bool on) { fused_enabled_ = on; }
+  int64_t fused_evals() const { return fused_evals_; }
+  int64_t leaf_windows() const { return leaf_windows_; }
+
+  BaseColumnReader* column_reader(int idx) { return column_readers_[idx]; }
+
+ private:
+  bool FusedWindow(int64_t limit_rows, const std::vector<int64_t>& page_pos,
+                   boost::dynamic_bitset<>& skip_bitset);
+  bool BuildFusedSpan(const std::vector<int64_t>& page_pos);
+
+  std::vector<BaseColumnReader*> column_readers_;
+  std::vector<SimplePredicate*> simple_predicates_;
+  Status parse_status_;
+  int tuple_size_;
+
+  bool fused_enabled_;
+  std::vector<uint64_t> fused_bitmap_;  // result of the last fused evaluation
+  std::vector<int64_t> fused_start_;    // every reader's row_position() when it was built
+  int64_t fused_pos_, fused_rows_;      // (unused) / rows covered
+  int64_t fused_evals_, leaf_windows_;
+};
+
+// ---------------------------------------------------------------------------------------
+class HdfsParquetScanner::BaseColumnReader {
+ public:
+  BaseColumnReader(HdfsParquetScanner* parent, int max_def_level, int slot_size)
+    : parent_(parent), max_def_level_(max_def_level), slot_size_(slot_size), tuple_offset_(0),
+      null_offset_(0), next_page_(0), num_buffered_values_(0), page_num_values_(0),
+      data_(NULL), data_size_(0), def_data_(NULL), def_bytes_(0), dict_decoder_base_(NULL) {}
+  virtual ~BaseColumnReader() {}
+
+  int max_def_level() const { return max_def_level_; }
+  int64_t num_buffered_values() const { return num_buffered_values_; }
+  void num_buffered_values(int64_t fetched_rows) { num_buffered_values_ -= fetched_rows; }  // :179-181
+  int64_t page_num_values() const { return page_num_values_; }
+  // Rows of the current page already consumed by ReadValue/SkipValue, i.e. the cursor the
+  // per-leaf predicates would start from (predicates never advance it).
+  int64_t row_position() const {
+    if (max_def_level() > 0) return fle_def_levels_.get() ? fle_def_levels_->position() : 0;
+    return (dict_decoder_base_ && dict_decoder_base_->data_decoder())
+        ? dict_decoder_base_->data_decoder()->position() : 0;
+  }
+
+  // :730-924 reduced to the page-body framing (see file comment).
+  Status ReadDataPage();
+
+  // :1006-1035
+  bool ReadValue(uint8_t* tuple, int skip_rows);
+  bool SkipValue(int skip_rows);
+
+  // fused-path accessors: the current page's encoded streams
+  const uint8_t* fle_data() const { return data_ + 1; }     // after the bit-width byte
+  int fle_data_len() const { return data_size_ - 1; }
+  int fle_bit_width() const { return data_size_ > 0 ? data_[0] : 0; }
+  const uint8_t* def_data() const { return def_data_; }
+  int def_bytes() const { return def_bytes_; }
+  bool page_is_dictionary() const { return page_encoding_ == parquet_encoding::FLE_DICTIONARY ||
+                                           page_encoding_ == parquet_encoding::PLAIN_DICTIONARY; }
+
+ protected:
+  friend class HdfsParquetScanner;
+  virtual Status InitDataPage(uint8_t* data, int size) = 0;
+  virtual bool ReadSlot(void* slot, int skip_rows) = 0;
+  virtual bool SkipSlot(int skip_rows) = 0;
+  int ReadDefinitionLevel();
+
+  HdfsParquetScanner* parent_;
+  int max_def_level_;
+  int slot_size_;
+  int tuple_offset_, null_offset_;
+  std::vector<DataPage> pages_;
+  size_t next_page_;
+  int64_t num_buffered_values_;
+  int64_t page_num_values_;
+  int page_encoding_;
+  uint8_t* data_;
+  int data_size_;
+  const uint8_t* def_data_;
+  int def_bytes_;
+  std::unique_ptr<FleDecoder> fle_def_levels_;
+  DictDecoderBase* dict_decoder_base_;
+};
+
+template<typename T>
+class HdfsParquetScanner::ColumnReader : public HdfsParquetScanner::BaseColumnReader {
+ public:
+  ColumnReader(HdfsParquetScanner* parent, int max_def_level)
+    : BaseColumnReader(parent, max_def_level, sizeof(T)) {}
+
+  void CreateDictionaryDecoder(uint8_t* values, int size) {  // :448-451
+    dict_decoder_.reset(new DictDecoder<T>(values, size, sizeof(T)));
+    dict_decoder_base_ = dict_decoder_.get();
+  }
+  DictDecoder<T>* dict_decoder() { return dict_decoder_.get(); }
+
+  // :326-331 -- on the device: prefix popcount + bit deposit (fle_intersect_bitset)
+  void IntersectBitset(boost::dynamic_bitset<>& root_bitset, boost::dynamic_bitset<>& sub_bitset) {
+    const size_t n_root = root_bitset.size(), n_sub = sub_bitset.size();
+    if (n_root == 0) return;
+    std::vector<uint64_t> root((n_root + 63) / 64), sub((n_sub + 63) / 64 + 1);
+    boost::to_block_range(root_bitset, root.begin());
+    boost::to_block_range(sub_bitset, sub.begin());
+    fle_ctx* ctx = FleGpu::ctx();
+    if (ctx == NULL) return;
+    if (FleGpu::Check(fle_intersect_bitset(ctx, &root[0], n_root, &sub[0], n_sub), "fle_intersect_bitset") != FLE_OK) return;
+    root_bitset.clear();
+    root_bitset.append(root.begin(), root.end());
+    root_bitset.resize(n_root);
+  }
+
+#define FLE_COLUMN_READER_OP(Name, ArgT)                                                   \
+  void Name(int64_t num_rows, boost::dynamic_bitset<>& skip_bitset, ArgT val) {            \
+    if (!page_is_dictionary()) { skip_bitset.resize(skip_bitset.size() + num_rows, false); return; } \
+    if (max_def_level() == 0) {                                                            \
+      dict_decoder_->Name(num_rows, skip_bitset, val);                                     \
+      return;                                                                              \
+    }                                                                                      \
+    fle_def_levels_->Eq(num_rows, skip_bitset, max_def_level());                           \
+    boost::dynamic_bitset<> data_bitset;                                                   \
+    dict_decoder_->Name(skip_bitset.count(), data_bitset, val);                            \
+    IntersectBitset(skip_bitset, data_bitset);                                             \
+  }
+  FLE_COLUMN_READER_OP(Eq, T&)   // :333-350
+  FLE_COLUMN_READER_OP(Lt, T&)   // :352-369
+  FLE_COLUMN_READER_OP(Le, T&)   // :371-388
+  FLE_COLUMN_READER_OP(Gt, T&)   // :390-407
+  FLE_COLUMN_READER_OP(Ge, T&)   // :409-426
+  FLE_COLUMN_READER_OP(In, std::vector<T>&)  // :428-445
+#undef FLE_COLUMN_READER_OP
+
+ protected:
+  virtual Status InitDataPage(uint8_t* data, int size) {  // :453-472
+    if (dict_decoder_.get() == NULL) return Status("File corrupt. Missing dictionary page.");
+    dict_decoder_->SetData(data, size);
+    return Status::OK();
+  }
+  virtual bool ReadSlot(void* slot, int skip_rows) {  // :515-531
+    T val;
+    bool result = dict_decoder_->GetValue(&val, skip_rows);
+    memcpy(slot, &val, sizeof(T));
+    return result;
+  }
+  virtual bool SkipSlot(int skip_rows) {  // :533-547
+    if (skip_rows <= 0) return true;
+    return dict_decoder_->SkipValue(skip_rows);
+  }
+
+ private:
+  std::unique_ptr<DictDecoder<T> > dict_decoder_;
+  std::vector<uint8_t> dict_copy_;
+  friend class HdfsParquetScanner;
+};
+
+// ---------------------------------------------------------------------------------------
+inline HdfsParquetScanner::~HdfsParquetScanner() {
+  for (size_t i = 0; i < column_readers_.size(); ++i) delete column_readers_[i];
+}
+
+inline int HdfsParquetScanner::slot_offset(int idx) const { return column_readers_[idx]->tuple_offset_; }
+
+template<typename T>
+inline int HdfsParquetScanner::AddColumn(int max_def_level, const uint8_t* dict_page, int dict_len,
+                                         const std::vector<DataPage>& pages) {
+  ColumnReader<T>* r = new ColumnReader<T>(this, max_def_level);
+  // the dictionary page is copied out of the I/O buffer as in :829-842
+  r->dict_copy_.assign(dict_page, dict_page + dict_len);
+  r->CreateDictionaryDecoder(r->dict_copy_.empty() ? NULL : &r->dict_copy_[0], dict_len);
+  r->pages_ = pages;
+  column_readers_.push_back(r);
+  // tuple layout: [null byte per column][slots]; recomputed as columns are added
+  int off = static_cast<int>(column_readers_.size());
+  for (size_t i = 0; i < column_readers_.size(); ++i) {
+    BaseColumnReader* c = column_readers_[i];
+    off = (off + c->slot_size_ - 1) / c->slot_size_ * c->slot_size_;
+    c->tuple_offset_ = off;
+    c->null_offset_ = static_cast<int>(i);
+    off += c->slot_size_;
+  }
+  tuple_size_ = (off + 7) / 8 * 8;
+  return static_cast<int>(column_readers_.size()) - 1;
+}
+
+inline Status HdfsParquetScanner::BaseColumnReader::ReadDataPage() {
+  num_buffered_values_ = 0;
+  if (next_page_ >= pages_.size()) return Status::OK();  // end of column chunk
+  const DataPage& pg = pages_[next_page_++];
+  data_ = const_cast<uint8_t*>(pg.data);
+  data_size_ = pg.size;
+  page_encoding_ = pg.encoding;
+  num_buffered_values_ = pg.num_values;
+  page_num_values_ = pg.num_values;
+  def_data_ = NULL;
+  def_bytes_ = 0;
+  if (max_def_level() > 0) {  // :882-919, definition_level_encoding == FLE
+    if (data_size_ < 4) return Status("page too small for definition levels");
+    int32_t num_definition_bytes = 0;
+    memcpy(&num_definition_bytes, data_, 4);
+    data_ += 4;
+    data_size_ -= 4;
+    if (num_definition_bytes <= 0 || num_definition_bytes > data_size_) return Status("bad definition level length");
+    const int bit_width = FleLog2Ceil(max_def_level() + 1);
+    fle_def_levels_.reset(new FleDecoder(data_, num_definition_bytes, bit_width));
+    def_data_ = data_;
+    def_bytes_ = num_definition_bytes;
+    data_ += num_definition_bytes;
+    data_size_ -= num_definition_bytes;
+  }
+  if (!page_is_dictionary()) return Status("only FLE_DICTIONARY data pages are on the hot path");
+  // Data can be empty if the column contains all NULLs (:921)
+  if (data_size_ != 0) return InitDataPage(data_, data_size_);
+  return Status::OK();
+}
+
+inline int HdfsParquetScanner::BaseColumnReader::ReadDefinitionLevel() {  // :924-951
+  if (max_def_level() == 0) return 1;
+  uint8_t definition_level;
+  if (!fle_def_levels_->Get(&definition_level)) return -1;
+  return definition_level;
+}
+
+inline bool HdfsParquetScanner::BaseColumnReader::ReadValue(uint8_t* tuple, int skip_rows) {  // :1006-1026
+  int tmp_skip_rows = 0;
+  for (int i = 0; i < skip_rows; ++i) {
+    int definition_level = ReadDefinitionLevel();
+    if (definition_level < 0) return false;
+    if (max_def_level() > 0 && definition_level != max_def_level()) continue;
+    ++tmp_skip_rows;
+  }
+  int definition_level = ReadDefinitionLevel();
+  if (definition_level < 0) return false;
+  if (max_def_level() > 0 && definition_level != max_def_level()) {
+    tuple[null_offset_] = 1;  // tuple->SetNull(...)
+    if (!SkipSlot(tmp_skip_rows)) return false;
+    return true;
+  }
+  return ReadSlot(tuple + tuple_offset_, tmp_skip_rows);
+}
+
+inline bool HdfsParquetScanner::BaseColumnReader::SkipValue(int skip_rows) {  // :1028-1037
+  int tmp_skip_rows = 0;
+  for (int i = 0; i < skip_rows; ++i) {
+    int definition_level = ReadDefinitionLevel();
+    if (definition_level < 0) return false;
+    if (max_def_level() > 0 && definition_level != max_def_level()) continue;
+    ++tmp_skip_rows;
+  }
+  return SkipSlot(tmp_skip_rows);
+}
+
+#define FLE_SCANNER_TRAMPOLINE(Name, ArgT)                                                        \
+  template<typename T>                                                                            \
+  inline void HdfsParquetScanner::Name(int idx, int64_t num_rows,                                 \
+      boost::dynamic_bitset<>& skip_bitset, ArgT val) {                                           \
+    reinterpret_cast<HdfsParquetScanner::ColumnReader<T>*>(column_readers_[idx])->Name(           \
+        num_rows, skip_bitset, val);                                                              \
+  }
+FLE_SCANNER_TRAMPOLINE(Eq, T&)
+FLE_SCANNER_TRAMPOLINE(Lt, T&)
+FLE_SCANNER_TRAMPOLINE(Le, T&)
+FLE_SCANNER_TRAMPOLINE(Gt, T&)
+FLE_SCANNER_TRAMPOLINE(Ge, T&)
+FLE_SCANNER_TRAMPOLINE(In, std::vector<T>&)
+#undef FLE_SCANNER_TRAMPOLINE
+
+inline bool HdfsParquetScanner::EvalSimplePredicates(boost::dynamic_bitset<>& skip_bitset) {
+  int64_t limit_rows = 1024;
+  for (size_t c = 0; c < column_readers_.size(); ++c) {
+    if (column_readers_[c]->num_buffered_values() == 0) {
+      parse_status_ = column_readers_[c]->ReadDataPage();
+      fused_rows_ = 0;  // a reader moved to a new page: the fused span ends here
+      if (column_readers_[c]->num_buffered_values() == 0 || !parse_status_.ok()) return false;
+    }
+    if (column_readers_[c]->num_buffered_values() < limit_rows) {
+      limit_rows = column_readers_[c]->num_buffered_values();
+    }
+  }
+  std::vector<int64_t> page_pos(column_readers_.size());
+  for (size_t c = 0; c < column_readers_.size(); ++c) {
+    page_pos[c] = column_readers_[c]->row_position();
+    column_readers_[c]->num_buffered_values(limit_rows);
+  }
+  if (simple_predicates_.empty()) return false;
+
+  if (fused_enabled_ && FusedWindow(limit_rows, page_pos, skip_bitset)) return FleGpu::ok();
+
+  ++leaf_windows_;
+  simple_predicates_[0]->GetBitset(this, limit_rows, skip_bitset);
+  for (size_t i = 1; i < simple_predicates_.size(); ++i) {
+    boost::dynamic_bitset<> tmp_bitset;
+    simple_predicates_[i]->GetBitset(this, limit_rows, tmp_bitset);
+    skip_bitset &= tmp_bitset;
+  }
+  if (!FleGpu::ok()) {
+    parse_status_ = Status(FleGpu::message());
+    return false;
+  }
+  return true;
+}
+
+inline bool HdfsParquetScanner::BuildFusedSpan(const std::vector<int64_t>& page_pos) {
+  const int ncols = static_cast<int>(column_readers_.size());
+  if (ncols > FLE_MAX_COLS) return false;
+  int64_t span = -1;
+  std::vector<fle_col_desc> cols(ncols);
+  for (int c = 0; c < ncols; ++c) {
+    BaseColumnReader* r = column_readers_[c];
+    if (!r->page_is_dictionary()) return false;
+    const int64_t left = r->page_num_values() - page_pos[c];
+    span = span < 0 ? left : std::min(span, left);
+    memset(&cols[c], 0, sizeof(fle_col_desc));
+    const int bw = r->fle_bit_width();
+    if (r->max_def_level() == 0) {
+      if (page_pos[c] & 63) return false;  // FLE groups hold 64 rows
+      if (bw < 1 || bw > 32) return false;
+      const int64_t off = (page_pos[c] / 64) * bw * 8;
+      cols[c].planes = r->fle_data() + off;
+      cols[c].bytes = r->fle_data_len() - off;
+      cols[c].bit_width = bw;
+    } else {
+      if (page_pos[c] != 0) return false;  // data values are indexed by non-null ordinal
+      if (r->max_def_level() != 1) return false;
+      cols[c].planes = r->fle_data_len() > 0 ? r->fle_data() : NULL;
+      cols[c].bytes = std::max(0, r->fle_data_len());
+      cols[c].bit_width = (bw >= 1 && bw <= 32) ? bw : 1;
+      cols[c].max_def_level = 1;
+      cols[c].def_planes = r->def_data();
+      cols[c].def_bytes = r->def_bytes();
+    }
+  }
+  if (span <= 0) return false;
+  FusedProgram prog;
+  for (size_t i = 0; i < simple_predicates_.size(); ++i) {
+    if (!simple_predicates_[i]->Lower(this, &prog)) return false;
+    if (i > 0) prog.Push(FLE_OP_AND);  // the conjunct `&=` loop, :1857-1862
+  }
+  if (prog.nodes.size() > FLE_MAX_NODES) return false;
+  fle_ctx* ctx = FleGpu::ctx();
+  if (ctx == NULL) return false;
+  fused_bitmap_.assign((span + 63) / 64, 0);
+  int rc = fle_eval(ctx, &cols[0], ncols, &prog.nodes[0], static_cast<int>(prog.nodes.size()), 0, span,
+                    &fused_bitmap_[0], NULL);
+  if (rc == FLE_E_UNSUPPORTED) return false;  // e.g. too many leaves: per-leaf path instead
+  if (FleGpu::Check(rc, "fle_eval(fused)") != FLE_OK) return false;
+  ++fused_evals_;
+  fused_start_ = page_pos;
+  fused_rows_ = span;
+  return true;
+}
+
+inline bool HdfsParquetScanner::FusedWindow(int64_t limit_rows, const std::vector<int64_t>& page_pos,
+                                            boost::dynamic_bitset<>& skip_bitset) {
+  // the cached span is usable if every reader sits at the same offset inside it
+  bool usable = fused_rows_ > 0 && fused_start_.size() == page_pos.size();
+  int64_t offset = usable ? page_pos[0] - fused_start_[0] : 0;
+  for (size_t c = 0; usable && c < page_pos.size(); ++c) {
+    if (page_pos[c] - fused_start_[c] != offset) usable = false;
+  }
+  if (!usable || offset < 0 || offset + limit_rows > fused_rows_) {
+    if (!BuildFusedSpan(page_pos)) return false;
+    offset = 0;
+    if (limit_rows > fused_rows_) return false;
+  }
+  fused_pos_ = offset;
+  // bit slice [fused_pos_, fused_pos_ + limit_rows) of the cached result
+  int64_t pos = fused_pos_;
+  int64_t left = limit_rows;
+  while (left > 0) {
+    const int sh = static_cast<int>(pos & 63);
+    uint64_t w = fused_bitmap_[pos >> 6] >> sh;
+    if (sh != 0 && static_cast<size_t>((pos >> 6) + 1) < fused_bitmap_.size()) {
+      w |= fused_bitmap_[(pos >> 6) + 1] << (64 - sh);
+    }
+    if (left >= 64) {
+      skip_bitset.append(w);
+      pos += 64;
+      left -= 64;
+    } else {
+      for (int i = 0; i < left; ++i) skip_bitset.push_back((w >> i) & 1);
+      pos += left;
+      left = 0;
+    }
+  }
+  fused_pos_ = pos;
+  return true;
+}
+
+inline Status HdfsParquetScanner::AssembleRows(int64_t expected_rows_in_group, std::vector<uint8_t>* rows,
+                                               int64_t* num_passed) {
+  int64_t rows_read = 0;
+  const int num_column_readers = static_cast<int>(column_readers_.size());
+  boost::dynamic_bitset<> skip_bitset;
+  std::vector<int> skip_rows;
+  *num_passed = 0;
+  while (rows_read < expected_rows_in_group) {
+    skip_bitset.clear();
+    if (!EvalSimplePredicates(skip_bitset)) return parse_status_;
+    if (skip_bitset.size() == 0) break;
+    const int bitset_size = static_cast<int>(skip_bitset.size());
+    if (skip_bitset.count() == 0) {  // :1125-1131
+      for (int c = 0; c < num_column_readers; ++c) {
+        if (!column_readers_[c]->SkipValue(bitset_size)) return Status("SkipValue failed");
+      }
+      rows_read += bitset_size;
+      continue;
+    }
+    skip_rows.clear();  // :1134-1148
+    int start = 0;
+    for (int i = 0; i < bitset_size; ++i) {
+      if (skip_bitset[i]) {
+        skip_rows.push_back(i - start);
+        start = i + 1;
+      }
+    }
+    const int last_skip_rows = bitset_size - start;
+    const size_t base = rows->size();
+    rows->resize(base + skip_rows.size() * tuple_size_, 0);
+    for (int c = 0; c < num_column_readers; ++c) {  // :1151-1168, column by column
+      uint8_t* tuple = &(*rows)[base];
+      for (size_t i = 0; i < skip_rows.size(); ++i) {
+        if (!column_readers_[c]->ReadValue(tuple, skip_rows[i])) return Status("ReadValue failed");
+        tuple += tuple_size_;
+      }
+    }
+    if (last_skip_rows != 0) {  // :1107-1113
+      for (int c = 0; c < num_column_readers; ++c) {
+        if (!column_readers_[c]->SkipValue(last_skip_rows)) return Status("SkipValue failed");
+      }
+    }
+    *num_passed += static_cast<int64_t>(skip_rows.size());
+    rows_read += bitset_size;
+  }
+  return FleGpu::ok() ? Status::OK() : Status(FleGpu::message());
+}
+
+// ---------------------------------------------------------------------------------------
+// predicate leaves (simple-predicates.h:165-205) + their lowering to dictionary codes
+// ---------------------------------------------------------------------------------------
+namespace detail {
+inline bool PushTranslated(FusedProgram* prog, int idx, const DictCode& c) {
+  switch (c.op) {
+    case FLE_OP_IN: prog->PushIn(idx, c.codes); return true;
+    case FLE_OP_ALL: case FLE_OP_NONE: prog->Push(c.op, idx); return true;  // idx: NULL rows still fail
+    default: prog->Push(c.op, idx, c.code); return true;
+  }
+}
+}  // namespace detail
+
+#define FLE_DEFINE_LEAF(Name)                                                                       \
+  template <typename T>                                                                             \
+  inline void Name##Operate<T>::GetBitset(HdfsParquetScanner* scanner, int64_t num_rows,            \
+      boost::dynamic_bitset<>& skip_bitset) {                                                       \
+    scanner->Name(idx_, num_rows, skip_bitset, val_);                                               \
+  }                                                                                                 \
+  template <typename T>                                                                             \
+  inline bool Name##Operate<T>::Lower(HdfsParquetScanner* scanner, FusedProgram* prog) {            \
+    HdfsParquetScanner::ColumnReader<T>* r =                                                        \
+        reinterpret_cast<HdfsParquetScanner::ColumnReader<T>*>(scanner->column_reader(idx_));       \
+    if (r->dict_decoder() == NULL) return false;                                                    \
+    return detail::PushTranslated(prog, idx_, r->dict_decoder()->Translate##Name(val_));            \
+  }
+FLE_DEFINE_LEAF(Eq)
+FLE_DEFINE_LEAF(Lt)
+FLE_DEFINE_LEAF(Le)
+FLE_DEFINE_LEAF(Gt)
+FLE_DEFINE_LEAF(Ge)
+#undef FLE_DEFINE_LEAF
+
+template <typename T>
+inline void InOperate<T>::GetBitset(HdfsParquetScanner* scanner, int64_t num_rows,
+    boost::dynamic_bitset<>& skip_bitset) {
+  scanner->In(idx_, num_rows, skip_bitset, vals_);
+}
+template <typename T>
+inline bool InOperate<T>::Lower(HdfsParquetScanner* scanner, FusedProgram* prog) {
+  HdfsParquetScanner::ColumnReader<T>* r =
+      reinterpret_cast<HdfsParquetScanner::ColumnReader<T>*>(scanner->column_reader(idx_));
+  if (r->dict_decoder() == NULL) return false;
+  return detail::PushTranslated(prog, idx_, r->dict_decoder()->TranslateIn(vals_));
+}
+
+}  // namespace impala
+
+#endif

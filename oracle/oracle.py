@@ -209,11 +209,12 @@ def ref_available() -> bool:
 class Ref:
     """The compiled reference.  enc arguments are uint64 word arrays (as Oracle.pack makes)."""
 
-    def __init__(self):
-        path = os.path.join(_HERE, "_ref", "libfle_ref.so")
+    def __init__(self, lib_path: str | None = None):
+        """lib_path: another build of oracle/ref_driver.cc -- tests compile the same driver against
+        the product's drop-in fle-encoding.h to run identical call sequences on both."""
+        path = lib_path or os.path.join(_HERE, "_ref", "libfle_ref.so")
         if not os.path.exists(path):
-            raise RuntimeError("oracle/_ref/libfle_ref.so missing: run `make -C oracle` where "
-                               "/root/reference is mounted")
+            raise RuntimeError(f"{path} missing: run `make -C oracle` where /root/reference is mounted")
         L = self.lib = C.CDLL(path)
         if not L.ref_has_avx2():
             raise RuntimeError("host CPU lacks AVX2; the reference cannot run here")

@@ -58,7 +58,7 @@ void RunPred(FleDecoder& d, int op, int64_t num_rows, Bitset& bs, const uint64_t
 }
 
 void CopyBits(const Bitset& bs, uint64_t* out_words) {
-  memcpy(out_words, bs.blocks(), bs.num_blocks() * 8);
+  boost::to_block_range(bs, out_words);  // real boost API, also provided by both stand-ins
 }
 
 }  // namespace

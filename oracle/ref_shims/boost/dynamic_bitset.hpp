@@ -67,8 +67,9 @@ class dynamic_bitset {
     for (std::size_t i = 0; i < w_.size(); ++i) w_[i] |= o.w_[i];
     return *this;
   }
-  const Block* blocks() const { return w_.data(); }
   std::size_t num_blocks() const { return w_.size(); }
+  template <class B, class It>
+  friend void to_block_range(const dynamic_bitset<B>& b, It result);
  private:
   void trim() {
     if (n_ & 63) w_.back() &= ~(~Block(0) << (n_ & 63));
@@ -76,4 +77,8 @@ class dynamic_bitset {
   std::vector<Block> w_;
   std::size_t n_;
 };
+template <class B, class It>
+inline void to_block_range(const dynamic_bitset<B>& b, It result) {
+  for (std::size_t i = 0; i < b.w_.size(); ++i) *result++ = b.w_[i];
+}
 }  // namespace boost
