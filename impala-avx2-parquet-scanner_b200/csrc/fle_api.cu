@@ -250,6 +250,7 @@ int fle_ctx_create(int device, void* cuda_stream, fle_ctx** out) {
   }
   ctx->num_sms = prop.multiProcessorCount;
   ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  ctx->max_smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
   if (cuda_stream) {
     ctx->stream = (cudaStream_t)cuda_stream;
   } else {

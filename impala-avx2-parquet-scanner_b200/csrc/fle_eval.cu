@@ -19,9 +19,13 @@
 // used for unaligned inputs, the ragged last tile's groups and as an on-device cross-check.
 #include <algorithm>
 #include <cstring>
+#include <mutex>
+#include <set>
+#include <utility>
 
 #include "fle_device.cuh"
 #include "fle_internal.h"
+#include "fle_eval_common.cuh"
 
 namespace fle {
 
@@ -196,59 +200,6 @@ __device__ __forceinline__ uint64_t eval_group(const EvalParams& P, const uint32
   return sl.s0;
 }
 
-// plane order -> row order (fle-encoding.h:7989-7998 does this with six swap steps), then
-// clear the bits of rows past the end (the reference pushes only num_rows bits, :8000-8006).
-__device__ __forceinline__ uint64_t finish_word(uint64_t planes_order, int64_t g, int64_t nrows) {
-  uint64_t r = __brevll(planes_order);
-  const int64_t rows_left = nrows - g * 64;
-  if (rows_left < 64) r &= (rows_left <= 0) ? 0ull : ((1ull << rows_left) - 1ull);
-  return r;
-}
-
-// block-wide popcount reduction + "last block sums" so the launch needs no memset/atomics
-// on the result slot.
-template <int NT>
-__device__ __forceinline__ void publish_count(const EvalParams& P, uint64_t cnt) {
-  __shared__ uint64_t warp_cnt[NT / 32];
-  __shared__ bool is_last;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = cnt;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint64_t t = 0;
-#pragma unroll
-    for (int w = 0; w < NT / 32; ++w) t += warp_cnt[w];
-    P.partial[blockIdx.x] = t;
-    __threadfence();
-    const unsigned int prev = atomicAdd(P.ticket, 1u);
-    is_last = (prev == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (is_last) {
-    __threadfence();
-    uint64_t t = 0;
-    for (unsigned int i = threadIdx.x; i < gridDim.x; i += NT)
-      t += *((volatile uint64_t*)&P.partial[i]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = t;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      uint64_t tot = 0;
-#pragma unroll
-      for (int w = 0; w < NT / 32; ++w) tot += warp_cnt[w];
-      if (P.count_out) *P.count_out = tot;
-      *P.ticket = 0;  // self-reset for the next launch on this stream
-    }
-  }
-}
-
-__device__ __forceinline__ void load_in_lits(const EvalParams& P, uint32_t* lits_smem) {
-  for (int i = threadIdx.x; i < P.n_in_lits; i += blockDim.x) lits_smem[i] = P.in_lits[i];
-}
-
 // ------------------------------------------------------------------------------------------
 // Kernel 0: direct global loads
 // ------------------------------------------------------------------------------------------
@@ -276,14 +227,221 @@ __global__ void __launch_bounds__(NT) eval_direct_kernel(const __grid_constant__
 
 // ------------------------------------------------------------------------------------------
 // Kernel 1: TMA-staged persistent pipeline
+//
+// The staged path does not interpret the program per group.  For every tile it walks the pass
+// list ONCE (warp-uniform), and each pass runs a body specialised at compile time on
+// <kind, K chains, bit width>: planes come from shared memory with 64/128-bit loads, the
+// per-plane literal masks sit in registers (loaded once per tile and pass), the plane loop is
+// fully unrolled, and the body loops over the thread's `gpt` groups.  Per group that leaves
+// BW/2 LDS + 2*K*BW LOP3 + a slot update, close to the minimum the plane algebra needs.
+// Pass results are folded into per-thread slots in shared memory ([slot][q][thread]); a short
+// epilogue per group applies the combine ops, reverses the word into row order, stores it and
+// counts it.
 // ------------------------------------------------------------------------------------------
+#ifndef FLE_PASS_FN
+#define FLE_PASS_FN __device__ __forceinline__
+#endif
+
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
 template <int NT>
-__global__ void __launch_bounds__(NT) eval_tma_kernel(const __grid_constant__ EvalParams P) {
+__device__ __forceinline__ uint32_t slot_addr(uint32_t slot_base, int gpt, int slot, int q) {
+  return slot_base + (uint32_t)((slot * gpt + q) * NT) * 8u;
+}
+
+__device__ __forceinline__ void fold_smem(uint32_t addr, int op, uint64_t v) {
+  if (op != FOLD_SET) {
+    const uint64_t cur = lds64(addr);
+    v = (op == FOLD_AND) ? (cur & v) : (cur | v);
+  }
+  sts64(addr, v);
+}
+
+// One pass over one column for all of this thread's groups in the tile.
+//   mask_addr : shared address of this pass's mask table [4][32] u32 (all-ones where the
+//               literal has a 1 at that plane)
+//   col_addr  : shared address of plane 0 of the thread's first group (q = 0) in this column
+//   slots4/folds4/negs4/inits4 : PassDesc::slot/fold/neg/init packed one byte per chain
+template <int NT, bool IS_LT, int K, int BW>
+FLE_PASS_FN void pass_tile(uint32_t mask_addr, uint32_t col_addr, uint32_t slot_base, int gpt,
+                           uint32_t slots4, uint32_t folds4, uint32_t negs4, uint32_t inits4,
+                           uint32_t merge) {
+  constexpr bool kRegMasks = (K * BW <= 40);  // keep every body under ~80 registers (3 CTAs/SM)
+  uint32_t m[kRegMasks ? K * BW : 1];
+  if constexpr (kRegMasks) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+      for (int i = 0; i < BW; ++i) m[k * BW + i] = lds32(mask_addr + (uint32_t)(k * 32 + i) * 4u);
+    }
+  }
+  uint32_t nm[K], ini[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    nm[k] = ((negs4 >> (8 * k)) & 1u) ? ~0u : 0u;
+    ini[k] = IS_LT ? (((inits4 >> (8 * k)) & 1u) ? ~0u : 0u) : ~0u;
+  }
+  constexpr uint32_t kGroupStride = (uint32_t)(NT / 8) * BW * 8u;  // q -> q+1 inside a segment
+  for (int q = 0; q < gpt; ++q) {
+    const uint32_t a = col_addr + (uint32_t)q * kGroupStride;
+    uint32_t al[K], ah[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) al[k] = ah[k] = ini[k];
+#pragma unroll
+    for (int i = 0; i < BW; i += 2) {
+      uint64_t w0, w1 = 0;
+      if constexpr (BW % 2 == 0) {
+        lds128(a + i * 8, w0, w1);
+      } else {
+        w0 = lds64(a + i * 8);
+        if (i + 1 < BW) w1 = lds64(a + (i + 1) * 8);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (i + h < BW) {
+          const uint64_t w = h ? w1 : w0;
+          const uint32_t wl = (uint32_t)w, wh = (uint32_t)(w >> 32);
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            uint32_t mk;
+            if constexpr (kRegMasks) mk = m[k * BW + i + h];
+            else mk = lds32(mask_addr + (uint32_t)(k * 32 + i + h) * 4u);
+            if (IS_LT) {
+              al[k] = (~wl & mk) | (~(wl ^ mk) & al[k]);
+              ah[k] = (~wh & mk) | (~(wh ^ mk) & ah[k]);
+            } else {
+              al[k] = al[k] & ~(wl ^ mk);
+              ah[k] = ah[k] & ~(wh ^ mk);
+            }
+          }
+        }
+      }
+    }
+    if (merge) {
+      const int mop = (int)((folds4 >> (8 * (K - 1))) & 0xffu);
+      uint32_t rl = al[0] ^ nm[0], rh = ah[0] ^ nm[0];
+#pragma unroll
+      for (int k = 1; k < K; ++k) {
+        const uint32_t xl = al[k] ^ nm[k], xh = ah[k] ^ nm[k];
+        if (mop == FOLD_AND) { rl &= xl; rh &= xh; } else { rl |= xl; rh |= xh; }
+      }
+      fold_smem(slot_addr<NT>(slot_base, gpt, (int)(slots4 & 0xffu), q), (int)(folds4 & 0xffu),
+                ((uint64_t)rh << 32) | rl);
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const uint64_t r = ((uint64_t)(ah[k] ^ nm[k]) << 32) | (al[k] ^ nm[k]);
+        fold_smem(slot_addr<NT>(slot_base, gpt, (int)((slots4 >> (8 * k)) & 0xffu), q),
+                  (int)((folds4 >> (8 * k)) & 0xffu), r);
+      }
+    }
+  }
+}
+
+// IN list: OR over literals of an XNOR-AND chain (fle-encoding.h:8282-8290), four literals per
+// sweep over the planes; partial results accumulate in the scratch slot, then fold once.
+template <int NT, int BW>
+FLE_PASS_FN void in_tile(const uint32_t* lits, int cnt, uint32_t col_addr, uint32_t slot_base, int gpt,
+                         int tmp_slot, int dst_slot, int fold, uint32_t negmask) {
+  constexpr bool kRegMasks = (4 * BW <= 40);
+  constexpr uint32_t kGroupStride = (uint32_t)(NT / 8) * BW * 8u;
+  for (int j = 0; j < cnt; j += 4) {
+    uint32_t lit[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) lit[k] = lits[min(j + k, cnt - 1)];  // pad by repetition
+    uint32_t m[kRegMasks ? 4 * BW : 1];
+    if constexpr (kRegMasks) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int i = 0; i < BW; ++i) m[k * BW + i] = 0u - ((lit[k] >> i) & 1u);
+      }
+    }
+    for (int q = 0; q < gpt; ++q) {
+      const uint32_t a = col_addr + (uint32_t)q * kGroupStride;
+      uint32_t al[4], ah[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) al[k] = ah[k] = ~0u;
+#pragma unroll
+      for (int i = 0; i < BW; i += 2) {
+        uint64_t w0, w1 = 0;
+        if constexpr (BW % 2 == 0) {
+          lds128(a + i * 8, w0, w1);
+        } else {
+          w0 = lds64(a + i * 8);
+          if (i + 1 < BW) w1 = lds64(a + (i + 1) * 8);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (i + h < BW) {
+            const uint64_t w = h ? w1 : w0;
+            const uint32_t wl = (uint32_t)w, wh = (uint32_t)(w >> 32);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              uint32_t mk;
+              if constexpr (kRegMasks) mk = m[k * BW + i + h];
+              else mk = 0u - ((lit[k] >> (i + h)) & 1u);
+              al[k] = al[k] & ~(wl ^ mk);
+              ah[k] = ah[k] & ~(wh ^ mk);
+            }
+          }
+        }
+      }
+      const uint64_t any = ((uint64_t)((ah[0] | ah[1]) | (ah[2] | ah[3])) << 32) | ((al[0] | al[1]) | (al[2] | al[3]));
+      fold_smem(slot_addr<NT>(slot_base, gpt, tmp_slot, q), j == 0 ? FOLD_SET : FOLD_OR, any);
+    }
+  }
+  const uint64_t nm64 = ((uint64_t)negmask << 32) | negmask;
+  for (int q = 0; q < gpt; ++q) {
+    const uint64_t v = lds64(slot_addr<NT>(slot_base, gpt, tmp_slot, q)) ^ nm64;
+    fold_smem(slot_addr<NT>(slot_base, gpt, dst_slot, q), fold, v);
+  }
+}
+
+#define FLE_BW_CASES(X) \
+  X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) \
+  X(17) X(18) X(19) X(20) X(21) X(22) X(23) X(24) X(25) X(26) X(27) X(28) X(29) X(30) X(31) X(32)
+
+template <int NT, bool IS_LT, int K>
+__device__ __forceinline__ void dispatch_pass(int bw, uint32_t mask_addr, uint32_t col_addr, uint32_t slot_base,
+                                              int gpt, uint32_t slots4, uint32_t folds4, uint32_t negs4,
+                                              uint32_t inits4, uint32_t merge) {
+  switch (bw) {
+#define X(B) case B: pass_tile<NT, IS_LT, K, B>(mask_addr, col_addr, slot_base, gpt, slots4, folds4, negs4, inits4, merge); break;
+    FLE_BW_CASES(X)
+#undef X
+  }
+}
+
+template <int NT>
+__device__ __forceinline__ void dispatch_in(int bw, const uint32_t* lits, int cnt, uint32_t col_addr,
+                                            uint32_t slot_base, int gpt, int tmp_slot, int dst_slot, int fold,
+                                            uint32_t negmask) {
+  switch (bw) {
+#define X(B) case B: in_tile<NT, B>(lits, cnt, col_addr, slot_base, gpt, tmp_slot, dst_slot, fold, negmask); break;
+    FLE_BW_CASES(X)
+#undef X
+  }
+}
+
+__device__ __forceinline__ uint32_t pack4(const uint8_t (&b)[4]) {
+  return (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 768 / NT) eval_tma_kernel(const __grid_constant__ EvalParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint32_t* lits_smem = reinterpret_cast<uint32_t*>(smem + P.smem_lits_off);
+  uint32_t* masks_smem = reinterpret_cast<uint32_t*>(smem + P.smem_masks_off);
   const uint32_t bar0 = smem_u32(smem + P.smem_bar_off);
   const uint32_t stage0 = smem_u32(smem + P.smem_stage_off);
-  const int T = NT * P.gpt;          // groups per tile
+  const uint32_t masks0 = smem_u32(masks_smem);
+  const int gpt = P.gpt;
+  const int T = NT * gpt;            // groups per tile
   const int seg_groups = T >> 3;     // groups per skewed segment
   const int64_t ntiles = P.ngroups / T;  // full tiles; the ragged rest goes the direct way
   const int nst = P.nstages;
@@ -293,24 +451,15 @@ __global__ void __launch_bounds__(NT) eval_tma_kernel(const __grid_constant__ Ev
     mbar_fence_init();
   }
   load_in_lits(P, lits_smem);
+  // literal masks: entry [p][k][i] = all-ones iff bit i of chain k's literal of pass p is set
+  for (int e = threadIdx.x; e < P.npasses * 128; e += NT) {
+    const int p = e >> 7, k = (e >> 5) & 3, i = e & 31;
+    masks_smem[e] = 0u - ((P.passes[p].lit[k] >> i) & 1u);
+  }
   __syncthreads();
 
   // producer side (thread 0): stage `stage` <- tile `tile`
-  auto issue = [&](int stage, int64_t tile) {
-    const uint32_t bar = bar0 + stage * 8;
-    uint32_t total = 0;
-    for (int c = 0; c < P.ncols; ++c) total += (uint32_t)T * P.bw[c] * 8u;
-    mbar_arrive_expect_tx(bar, total);
-    for (int c = 0; c < P.ncols; ++c) {
-      const uint32_t seg_bytes = (uint32_t)seg_groups * P.bw[c] * 8u;
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(P.planes[c]) +
-                           (uint64_t)tile * T * P.bw[c] * 8u;
-      const uint32_t dst = stage0 + stage * P.stage_bytes + P.col_off[c];
-#pragma unroll
-      for (int s = 0; s < 8; ++s)
-        tma_load_1d(dst + s * P.seg_stride[c], src + (uint64_t)s * seg_bytes, seg_bytes, bar);
-    }
-  };
+  auto issue = [&](int stage, int64_t tile) { issue_tile(P, bar0, stage0, stage, tile, T); };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < nst - 1; ++s) {
@@ -319,9 +468,8 @@ __global__ void __launch_bounds__(NT) eval_tma_kernel(const __grid_constant__ Ev
     }
   }
 
-  Slots sl;
-  sl.smem = smem_u32(smem + P.smem_slots_off) + threadIdx.x * 8;
-  sl.stride = NT * 8;
+  const uint32_t seg = threadIdx.x & 7, jrow = threadIdx.x >> 3;
+  const uint32_t slot_base = smem_u32(smem + P.smem_slots_off) + threadIdx.x * 8u;
   uint64_t cnt = 0;
 
   int stage = 0;
@@ -339,15 +487,47 @@ __global__ void __launch_bounds__(NT) eval_tma_kernel(const __grid_constant__ Ev
     }
     mbar_wait(bar0 + stage * 8, parity);
     const uint32_t sbase = stage0 + stage * P.stage_bytes;
-    for (int q = 0; q < P.gpt; ++q) {
-      const int idx = q * NT + threadIdx.x;
-      const int seg = idx & 7, j = idx >> 3;
-      const int64_t g = tile * T + (int64_t)seg * seg_groups + j;
-      auto loader_of = [&](int col) {
-        return SmemPlanes{sbase + P.col_off[col] + seg * P.seg_stride[col] +
-                          (uint32_t)j * P.bw[col] * 8u};
-      };
-      const uint64_t r = finish_word(eval_group<SmemPlanes>(P, lits_smem, sl, loader_of), g, P.nrows);
+
+    // 1. passes (warp-uniform control flow, specialised bodies)
+    for (int p = 0; p < P.npasses; ++p) {
+      const PassDesc& pd = P.passes[p];
+      const int type = pd.type;
+      if (type == PASS_CONST) {
+        const uint64_t v = pd.init[0] ? ~0ull : 0ull;
+        for (int q = 0; q < gpt; ++q) fold_smem(slot_addr<NT>(slot_base, gpt, pd.slot[0], q), pd.fold[0], v);
+        continue;
+      }
+      const int col = pd.col;
+      const int bw = (int)P.bw[col];
+      const uint32_t col_addr = sbase + P.col_off[col] + seg * P.seg_stride[col] + jrow * (uint32_t)bw * 8u;
+      if (type == PASS_IN) {
+        dispatch_in<NT>(bw, lits_smem + pd.lit[0], (int)pd.lit[1], col_addr, slot_base, gpt, P.in_tmp_slot,
+                        pd.slot[0], pd.fold[0], pd.neg[0] ? ~0u : 0u);
+        continue;
+      }
+      const uint32_t mask_addr = masks0 + (uint32_t)p * 512u;
+      const uint32_t slots4 = pack4(pd.slot), folds4 = pack4(pd.fold), negs4 = pack4(pd.neg), inits4 = pack4(pd.init);
+      const uint32_t merge = pd.merge;
+      if (type == PASS_LT) {
+        if (pd.k == 1) dispatch_pass<NT, true, 1>(bw, mask_addr, col_addr, slot_base, gpt, slots4, folds4, negs4, inits4, merge);
+        else if (pd.k == 2) dispatch_pass<NT, true, 2>(bw, mask_addr, col_addr, slot_base, gpt, slots4, folds4, negs4, inits4, merge);
+        else dispatch_pass<NT, true, 4>(bw, mask_addr, col_addr, slot_base, gpt, slots4, folds4, negs4, inits4, merge);
+      } else {
+        if (pd.k == 1) dispatch_pass<NT, false, 1>(bw, mask_addr, col_addr, slot_base, gpt, slots4, folds4, negs4, inits4, merge);
+        else dispatch_pass<NT, false, 4>(bw, mask_addr, col_addr, slot_base, gpt, slots4, folds4, negs4, inits4, merge);
+      }
+    }
+
+    // 2. per-group epilogue: combine ops, row order, store, count
+    for (int q = 0; q < gpt; ++q) {
+      for (int c = 0; c < P.ncombs; ++c) {
+        const CombDesc cd = P.combs[c];
+        const uint64_t a = lds64(slot_addr<NT>(slot_base, gpt, cd.a, q));
+        const uint64_t b = lds64(slot_addr<NT>(slot_base, gpt, cd.b, q));
+        sts64(slot_addr<NT>(slot_base, gpt, cd.dst, q), cd.op == FOLD_AND ? (a & b) : (a | b));
+      }
+      const int64_t g = tile * T + (int64_t)seg * seg_groups + q * (NT / 8) + jrow;
+      const uint64_t r = finish_word(lds64(slot_addr<NT>(slot_base, gpt, 0, q)), g, P.nrows);
       P.bitmap[g] = r;
       cnt += __popcll(r);
     }
@@ -357,8 +537,12 @@ __global__ void __launch_bounds__(NT) eval_tma_kernel(const __grid_constant__ Ev
     }
   }
 
-  // ragged remainder (< T groups): spread over all CTAs, planes straight from global memory
+  // ragged remainder (< T groups): spread over all CTAs, planes straight from global memory,
+  // generic interpreter (slots: slot 0 in a register, the rest reuse the slot area)
   {
+    Slots sl;
+    sl.smem = slot_base;
+    sl.stride = NT * 8;
     const int64_t g0 = ntiles * T;
     for (int64_t g = g0 + (int64_t)blockIdx.x * NT + threadIdx.x; g < P.ngroups;
          g += (int64_t)gridDim.x * NT) {
@@ -498,6 +682,9 @@ int lower_program(const fle_col_desc* cols, int ncols, const fle_pred_node* node
     if (a.col != b.col) return a.col < b.col;
     return a.type < b.type;
   });
+  // flat programs: the first chain executed initialises slot 0 (SET), the rest fold into it
+  if (flat && !chains.empty()) chains[0].fold = FOLD_SET;
+  bool any_in = false;
   size_t i = 0;
   while (i < chains.size()) {
     if (P.npasses >= kMaxPasses) return fail(FLE_E_UNSUPPORTED, "too many predicate leaves");
@@ -509,6 +696,7 @@ int lower_program(const fle_col_desc* cols, int ncols, const fle_pred_node* node
       pd.k = 1;
       pd.slot[0] = c0.slot; pd.fold[0] = c0.fold; pd.neg[0] = c0.neg; pd.init[0] = c0.init;
       pd.lit[0] = c0.in_off; pd.lit[1] = c0.in_cnt;
+      any_in = any_in || c0.type == PASS_IN;
       ++i;
       continue;
     }
@@ -519,7 +707,27 @@ int lower_program(const fle_col_desc* cols, int ncols, const fle_pred_node* node
       pd.lit[k] = c.lit;
       ++k; ++i;
     }
-    pd.k = (uint8_t)k;
+    // merge: every chain lands in the same slot, chains 1.. with one and the same op
+    bool merge = k > 1;
+    for (int j = 1; j < k && merge; ++j)
+      merge = pd.slot[j] == pd.slot[0] && pd.fold[j] == pd.fold[1] && pd.fold[j] != FOLD_SET;
+    pd.merge = merge ? 1 : 0;
+    // only K = 1, 2, 4 (LT) and 1, 4 (EQ) bodies exist: pad by repeating the last chain, which
+    // changes nothing because SET/AND/OR with the same value are idempotent
+    const int want = (k == 3 || (c0.type == PASS_EQ && k == 2)) ? 4 : k;
+    for (int j = k; j < want; ++j) {
+      pd.slot[j] = pd.slot[k - 1]; pd.fold[j] = pd.fold[k - 1]; pd.neg[j] = pd.neg[k - 1];
+      pd.init[j] = pd.init[k - 1]; pd.lit[j] = pd.lit[k - 1];
+    }
+    // (a repeated SET cannot clobber later folds: in flat mode the only SET is chain 0 of the
+    //  first pass and padding repeats the LAST chain of a pass with k >= 2; in mixed trees every
+    //  chain SETs its own slot)
+    pd.k = (uint8_t)want;
+  }
+  P.in_tmp_slot = -1;
+  if (any_in) {
+    if (P.nslots >= kMaxSlots) return fail(FLE_E_UNSUPPORTED, "too many leaves in a mixed AND/OR tree");
+    P.in_tmp_slot = P.nslots++;
   }
   return FLE_OK;
 }
@@ -531,29 +739,83 @@ namespace {
 
 inline uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
-template <int NT>
-int launch_with_block(fle_ctx* ctx, EvalParams& P, bool use_tma, int sum_bw) {
-  // shared memory carve-up: [mbarriers][IN literals][slots][stages]
+constexpr int kNT = 256;
+enum LaunchMode { MODE_DIRECT = 0, MODE_STAGED = 1, MODE_SINGLE_PASS = 2 };
+
+// cudaOccupancyMaxActiveBlocksPerMultiprocessor / cudaFuncSetAttribute are not free; remember
+// the answers per (kernel, dynamic smem)
+int blocks_per_sm(fle_ctx* ctx, const void* kern, size_t smem_bytes, int* out) {
+  for (const auto& e : ctx->occ_cache) {
+    if (e.kern == kern && e.smem == smem_bytes) {
+      *out = e.blocks;
+      return FLE_OK;
+    }
+  }
+  // MaxDynamicSharedMemorySize is a property of the KERNEL (per device, process-wide), not of a
+  // context or a launch: raise it once to the device limit, under a lock, and never lower it
+  cudaError_t e = cudaSuccess;
+  {
+    static std::mutex mu;
+    static std::set<std::pair<int, const void*> > raised;
+    std::lock_guard<std::mutex> lock(mu);
+    const std::pair<int, const void*> key(ctx->device, kern);
+    if (raised.find(key) == raised.end()) {
+      cudaFuncAttributes fa;
+      e = cudaFuncGetAttributes(&fa, kern);
+      if (e != cudaSuccess) return set_cuda_error(ctx, e, "cudaFuncGetAttributes");
+      // static + dynamic shared memory together are bounded by the opt-in limit
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               ctx->max_smem_optin - (int)fa.sharedSizeBytes);
+      if (e != cudaSuccess) return set_cuda_error(ctx, e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+      raised.insert(key);
+    }
+  }
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kNT, smem_bytes);
+  if (e != cudaSuccess) return set_cuda_error(ctx, e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+  ctx->occ_cache.push_back({kern, smem_bytes, per_sm});
+  *out = per_sm;
+  return FLE_OK;
+}
+
+int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw) {
+  const int64_t G = P.ngroups;
+  const void* kern = nullptr;
+  if (mode == MODE_SINGLE_PASS) {
+    kern = eval1_kernel_for(P.passes[0].type, P.passes[0].k, (int)P.bw[0]);
+    if (!kern) return FLE_E_UNSUPPORTED;
+  } else {
+    kern = mode == MODE_STAGED ? (const void*)eval_tma_kernel<kNT> : (const void*)eval_direct_kernel<kNT>;
+  }
+  const bool staged = mode != MODE_DIRECT;
+
+  // tile sizing: groups per thread per tile so that a stage is a few tens of KB
+  int gpt = 1;
+  if (staged) {
+    gpt = ctx->eval_gpt;
+    const uint32_t bytes_per_gpt = (uint32_t)kNT * sum_bw * 8u;
+    const uint32_t target = mode == MODE_SINGLE_PASS ? 40u * 1024u : 32u * 1024u;
+    if (gpt <= 0) gpt = (int)std::max<uint32_t>(1, std::min<uint32_t>(8, (target + bytes_per_gpt / 2) / bytes_per_gpt));
+    gpt = std::min(gpt, 8);
+  }
+  // shared memory carve-up: [mbarriers][IN literals][literal masks][slots][stages]
   uint32_t off = 0;
   P.smem_bar_off = off;
   off += 8 * 8;  // up to 8 stages
   P.smem_lits_off = off;
-  off = round_up(off + (uint32_t)P.n_in_lits * 4u, 16);
+  if (mode != MODE_SINGLE_PASS) off = round_up(off + (uint32_t)P.n_in_lits * 4u, 16);
+  P.smem_masks_off = off;
+  if (mode == MODE_STAGED) off += (uint32_t)P.npasses * 512u;
   P.smem_slots_off = off;
-  off += (uint32_t)std::max(0, P.nslots - 1) * NT * 8u;
+  if (mode != MODE_SINGLE_PASS) off += (uint32_t)P.nslots * gpt * kNT * 8u;
   off = round_up(off, 128);
   P.smem_stage_off = off;
 
-  const int64_t G = P.ngroups;
   int grid = 0;
   size_t smem_bytes = off;
-  const void* kern = nullptr;
-  if (use_tma) {
-    // tile sizing: aim at ~32 KB per stage; narrow programs take several groups per thread
-    int gpt = ctx->eval_gpt;
-    const uint32_t bytes_per_gpt = (uint32_t)NT * sum_bw * 8u;
-    if (gpt <= 0) gpt = (int)std::max<uint32_t>(1, std::min<uint32_t>(8, (32u * 1024u) / bytes_per_gpt));
-    const int T = NT * gpt;
+  int rc;
+  if (staged) {
+    const int T = kNT * gpt;
     uint32_t coff = 0;
     for (int c = 0; c < P.ncols; ++c) {
       P.col_off[c] = coff;
@@ -561,52 +823,56 @@ int launch_with_block(fle_ctx* ctx, EvalParams& P, bool use_tma, int sum_bw) {
       coff += 8u * P.seg_stride[c];
     }
     P.stage_bytes = round_up(coff, 128);
-    const uint32_t avail = (uint32_t)ctx->max_smem_optin - off - 1024u;
-    int nst = ctx->eval_stages;
+    // stages x resident CTAs: as many bytes in flight per SM as shared memory allows, with at
+    // least 2 stages per CTA and preferably 3 CTAs (24 warps) per SM
+    const uint32_t sm_budget = (uint32_t)ctx->max_smem_per_sm;
+    int nst = ctx->eval_stages, want_ctas = ctx->eval_ctas_per_sm;
     if (nst <= 0) {
-      // ~100 KB per CTA keeps two CTAs per SM resident with >= 2 tiles each in flight
-      nst = (int)std::min<uint32_t>(4, std::max<uint32_t>(2, (96u * 1024u) / P.stage_bytes));
-    }
-    nst = std::min(nst, 8);
-    if (nst < 2 || (uint64_t)nst * P.stage_bytes > avail) {
-      nst = (int)std::min<uint32_t>(8, avail / P.stage_bytes);
+      nst = 0;
+      for (int ctas = (want_ctas > 0 ? want_ctas : 3); ctas >= 1 && nst < 2; --ctas) {
+        const uint32_t per_cta = sm_budget / ctas;
+        if (per_cta < off + 1024u + 2u * P.stage_bytes) continue;
+        nst = (int)std::min<uint32_t>(4, (per_cta - off - 1024u) / P.stage_bytes);
+      }
       if (nst < 2) return FLE_E_UNSUPPORTED;  // caller falls back to the direct kernel
     }
+    nst = std::min(nst, 8);
+    if ((uint64_t)off + (uint64_t)nst * P.stage_bytes > (uint64_t)ctx->max_smem_optin) return FLE_E_UNSUPPORTED;
     P.gpt = gpt;
     P.nstages = nst;
     smem_bytes = off + (size_t)nst * P.stage_bytes;
-    kern = (const void*)eval_tma_kernel<NT>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e != cudaSuccess) return set_cuda_error(ctx, e, "cudaFuncSetAttribute(eval_tma)");
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem_bytes);
-    if (e != cudaSuccess) return set_cuda_error(ctx, e, "occupancy(eval_tma)");
+    rc = blocks_per_sm(ctx, kern, smem_bytes, &per_sm);
+    if (rc != FLE_OK) return rc;
     if (per_sm < 1) return FLE_E_UNSUPPORTED;
-    if (ctx->eval_ctas_per_sm > 0) per_sm = std::min(per_sm, ctx->eval_ctas_per_sm);
+    if (want_ctas > 0) per_sm = std::min(per_sm, want_ctas);
     const int64_t ntiles = G / T;
-    const int64_t rest_blocks = ((G - ntiles * T) + NT - 1) / NT;
+    const int64_t rest_blocks = ((G - ntiles * T) + kNT - 1) / kNT;
     grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * per_sm,
                                                         std::max<int64_t>(ntiles, rest_blocks)));
   } else {
     P.gpt = 1;
     P.nstages = 0;
-    kern = (const void*)eval_direct_kernel<NT>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e != cudaSuccess) return set_cuda_error(ctx, e, "cudaFuncSetAttribute(eval_direct)");
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem_bytes);
-    if (e != cudaSuccess) return set_cuda_error(ctx, e, "occupancy(eval_direct)");
+    rc = blocks_per_sm(ctx, kern, smem_bytes, &per_sm);
+    if (rc != FLE_OK) return rc;
     per_sm = std::max(per_sm, 1);
-    grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * per_sm, (G + NT - 1) / NT));
+    grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * per_sm, (G + kNT - 1) / kNT));
   }
-  int rc = ensure_scratch(ctx, grid, P.n_in_lits);
+  rc = ensure_scratch(ctx, grid, P.n_in_lits);
   if (rc != FLE_OK) return rc;
   P.partial = ctx->d_partial;
   P.ticket = ctx->d_ticket;
   P.in_lits = ctx->d_in_lits;
   void* args[] = {(void*)&P};
-  cudaError_t e = cudaLaunchKernel(kern, dim3(grid), dim3(NT), args, smem_bytes, ctx->stream);
-  if (e != cudaSuccess) return set_cuda_error(ctx, e, "cudaLaunchKernel(eval)");
+  cudaError_t e = cudaLaunchKernel(kern, dim3(grid), dim3(kNT), args, smem_bytes, ctx->stream);
+  if (e != cudaSuccess) {
+    cudaGetLastError();  // clear the non-sticky error
+    char what[160];
+    snprintf(what, sizeof(what), "cudaLaunchKernel(eval mode=%d grid=%d smem=%zu gpt=%d stages=%d bw0=%u k=%d type=%d)",
+             mode, grid, smem_bytes, P.gpt, P.nstages, P.bw[0], (int)P.passes[0].k, (int)P.passes[0].type);
+    return set_cuda_error(ctx, e, what);
+  }
   ctx->launches += 1;
   return FLE_OK;
 }
@@ -666,15 +932,26 @@ int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, 
     if (count_dev) FLE_CUDA_TRY(ctx, cudaMemsetAsync(count_dev, 0, 8, ctx->stream));
     return FLE_OK;
   }
-  const bool use_tma = ctx->eval_variant != 0 && aligned;
-  const int NT = ctx->eval_block == 128 ? 128 : 256;
-  int rc;
-  if (use_tma) {
-    rc = NT == 128 ? launch_with_block<128>(ctx, P, true, sum_bw) : launch_with_block<256>(ctx, P, true, sum_bw);
-    if (rc == FLE_E_UNSUPPORTED && NT == 256) rc = launch_with_block<128>(ctx, P, true, sum_bw);
+  const bool staged_ok = ctx->eval_variant != 0 && aligned;
+  // one pass of compare chains folding into one word: the per-bit-width kernels of fle_eval1.cu
+  const PassDesc& p0 = P.passes[0];
+  const bool single_pass = P.npasses == 1 && P.ncombs == 0 && (p0.type == PASS_LT || p0.type == PASS_EQ) &&
+                           (p0.k == 1 || p0.merge) && p0.slot[0] == 0;
+  if (staged_ok && single_pass && ctx->eval_variant != 2) {
+    EvalParams P1 = P;  // only the pass's column is staged
+    const int c = p0.col;
+    P1.ncols = 1;
+    P1.planes[0] = P.planes[c];
+    P1.bw[0] = P.bw[c];
+    P1.passes[0].col = 0;
+    const int rc = launch_program(ctx, P1, MODE_SINGLE_PASS, (int)P.bw[c]);
     if (rc != FLE_E_UNSUPPORTED) return rc;
   }
-  return NT == 128 ? launch_with_block<128>(ctx, P, false, sum_bw) : launch_with_block<256>(ctx, P, false, sum_bw);
+  if (staged_ok) {
+    const int rc = launch_program(ctx, P, MODE_STAGED, sum_bw);
+    if (rc != FLE_E_UNSUPPORTED) return rc;  // tile does not fit in shared memory: direct kernel
+  }
+  return launch_program(ctx, P, MODE_DIRECT, sum_bw);
 }
 
 int launch_eval(fle_ctx* ctx, const fle_col_desc* cols, int ncols, const fle_pred_node* nodes,

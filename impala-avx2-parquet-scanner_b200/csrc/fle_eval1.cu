@@ -1,0 +1,205 @@
+// Single-pass fused-eval kernels, one specialisation per <kind, chains, bit width>.
+//
+// Programs whose leaves all sit on ONE column and fold with ONE operator -- a single compare,
+// BETWEEN (= And(Ge, Le)), NOT BETWEEN, a short conjunction or disjunction of
+// compares, Eq -- lower to exactly one pass (fle_internal.h).  For those the whole program is
+// known at compile time except the literals, so the kernel is the bare plane algebra:
+// per 64-row group  BW/2 x LDS.128  +  2*K*BW x LOP3  +  ~20 instructions of epilogue
+// (merge, BREV, tail mask, store, POPC).  The literal masks live in registers for the whole
+// kernel.  Same TMA/mbarrier tile pipeline and same skewed shared-memory layout as the generic
+// kernel in fle_eval.cu; replaces FleDecoder::Eq/Lt/Le/Gt/Ge (fle-encoding.h:7962-8234) and
+// the And/OrOperate `&=`/`|=` on top of them (simple-predicates.h:145-163).
+#include <algorithm>
+
+#include "fle_eval_common.cuh"
+
+namespace fle {
+
+struct SmemGroup {
+  uint32_t base;
+  template <int BW>
+  __device__ __forceinline__ void load_pair(int i, uint64_t& w0, uint64_t& w1) const {
+    if constexpr (BW % 2 == 0) {
+      lds128(base + i * 8, w0, w1);
+    } else {
+      w0 = lds64(base + i * 8);
+      w1 = (i + 1 < BW) ? lds64(base + (i + 1) * 8) : 0ull;
+    }
+  }
+};
+
+struct GlobalGroup {
+  const uint64_t* base;
+  template <int BW>
+  __device__ __forceinline__ void load_pair(int i, uint64_t& w0, uint64_t& w1) const {
+    w0 = __ldg(base + i);
+    w1 = (i + 1 < BW) ? __ldg(base + i + 1) : 0ull;
+  }
+};
+
+template <bool IS_LT, int K, int BW>
+struct PassRegs {
+  static constexpr bool kRegMasks = (K * BW <= 64);
+  uint32_t m[kRegMasks ? K * BW : 1];
+  uint32_t lit[K], nm[K], ini[K];
+  int mop;
+
+  __device__ __forceinline__ void init(const PassDesc& pd) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      lit[k] = pd.lit[k];
+      nm[k] = pd.neg[k] ? ~0u : 0u;
+      ini[k] = IS_LT ? (pd.init[k] ? ~0u : 0u) : ~0u;
+      if constexpr (kRegMasks) {
+#pragma unroll
+        for (int i = 0; i < BW; ++i) m[k * BW + i] = 0u - ((lit[k] >> i) & 1u);
+      }
+    }
+    mop = pd.fold[K - 1];
+  }
+
+  // plane-order result word of one group (bit 63-r = row r)
+  template <class L>
+  __device__ __forceinline__ uint64_t run(const L& ld) const {
+    uint32_t al[K], ah[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) al[k] = ah[k] = ini[k];
+#pragma unroll
+    for (int i = 0; i < BW; i += 2) {
+      uint64_t w0, w1;
+      ld.template load_pair<BW>(i, w0, w1);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (i + h < BW) {
+          const uint64_t w = h ? w1 : w0;
+          const uint32_t wl = (uint32_t)w, wh = (uint32_t)(w >> 32);
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            uint32_t mk;
+            if constexpr (kRegMasks) mk = m[k * BW + i + h];
+            else mk = 0u - ((lit[k] >> (i + h)) & 1u);
+            if (IS_LT) {
+              al[k] = (~wl & mk) | (~(wl ^ mk) & al[k]);
+              ah[k] = (~wh & mk) | (~(wh ^ mk) & ah[k]);
+            } else {
+              al[k] = al[k] & ~(wl ^ mk);
+              ah[k] = ah[k] & ~(wh ^ mk);
+            }
+          }
+        }
+      }
+    }
+    uint32_t rl = al[0] ^ nm[0], rh = ah[0] ^ nm[0];
+#pragma unroll
+    for (int k = 1; k < K; ++k) {
+      const uint32_t xl = al[k] ^ nm[k], xh = ah[k] ^ nm[k];
+      if (mop == FOLD_AND) { rl &= xl; rh &= xh; } else { rl |= xl; rh |= xh; }
+    }
+    return ((uint64_t)rh << 32) | rl;
+  }
+};
+
+template <bool IS_LT, int K, int BW>
+__global__ void __launch_bounds__(256) eval1_kernel(const __grid_constant__ EvalParams P) {
+  constexpr int NT = 256;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t bar0 = smem_u32(smem + P.smem_bar_off);
+  const uint32_t stage0 = smem_u32(smem + P.smem_stage_off);
+  const int gpt = P.gpt;
+  const int T = NT * gpt;
+  const int seg_groups = T >> 3;
+  const int64_t ntiles = P.ngroups / T;
+  const int nst = P.nstages;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nst; ++s) mbar_init(bar0 + s * 8, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nst - 1; ++s) {
+      const int64_t tile = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
+      if (tile < ntiles) issue_tile(P, bar0, stage0, s, tile, T);
+    }
+  }
+
+  PassRegs<IS_LT, K, BW> pr;
+  pr.init(P.passes[0]);
+
+  const uint32_t seg = threadIdx.x & 7, jrow = threadIdx.x >> 3;
+  // shared address of the thread's first group inside a stage, and the step to its next one
+  const uint32_t thread_off = P.col_off[0] + seg * P.seg_stride[0] + jrow * (uint32_t)(BW * 8);
+  constexpr uint32_t kGroupStride = (uint32_t)(NT / 8) * BW * 8u;
+  // bitmap word of the thread's first group inside a tile
+  const int64_t thread_g = (int64_t)seg * seg_groups + jrow;
+  uint64_t cnt = 0;
+
+  int stage = 0;
+  uint32_t parity = 0;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    __syncthreads();  // everyone is done with the stage consumed in the previous iteration
+    if (threadIdx.x == 0) {
+      const int64_t nxt = tile + (int64_t)(nst - 1) * gridDim.x;
+      int st2 = stage + nst - 1;
+      if (st2 >= nst) st2 -= nst;
+      if (nxt < ntiles) issue_tile(P, bar0, stage0, st2, nxt, T);
+    }
+    mbar_wait(bar0 + stage * 8, parity);
+    uint32_t a = stage0 + stage * P.stage_bytes + thread_off;
+    int64_t g = tile * T + thread_g;
+    for (int q = 0; q < gpt; ++q) {
+      const uint64_t r = finish_word(pr.run(SmemGroup{a}), g, P.nrows);
+      P.bitmap[g] = r;
+      cnt += __popcll(r);
+      a += kGroupStride;
+      g += NT / 8;
+    }
+    if (++stage == nst) {
+      stage = 0;
+      parity ^= 1u;
+    }
+  }
+  // ragged remainder (< T groups), planes straight from global memory
+  for (int64_t g = ntiles * T + (int64_t)blockIdx.x * NT + threadIdx.x; g < P.ngroups;
+       g += (int64_t)gridDim.x * NT) {
+    const uint64_t r = finish_word(pr.run(GlobalGroup{P.planes[0] + g * BW}), g, P.nrows);
+    P.bitmap[g] = r;
+    cnt += __popcll(r);
+  }
+  publish_count<NT>(P, cnt);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: kernel table
+// ------------------------------------------------------------------------------------------
+namespace {
+
+#define FLE_BW_CASES(X) \
+  X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) \
+  X(17) X(18) X(19) X(20) X(21) X(22) X(23) X(24) X(25) X(26) X(27) X(28) X(29) X(30) X(31) X(32)
+
+template <bool IS_LT, int K>
+const void* eval1_for_bw(int bw) {
+  switch (bw) {
+#define X(B) case B: return (const void*)eval1_kernel<IS_LT, K, B>;
+    FLE_BW_CASES(X)
+#undef X
+  }
+  return nullptr;
+}
+
+}  // namespace
+
+const void* eval1_kernel_for(int type, int k, int bw) {
+  if (type == PASS_LT) {
+    if (k == 1) return eval1_for_bw<true, 1>(bw);
+    if (k == 2) return eval1_for_bw<true, 2>(bw);
+    if (k == 4) return eval1_for_bw<true, 4>(bw);
+  } else if (type == PASS_EQ) {
+    if (k == 1) return eval1_for_bw<false, 1>(bw);
+    if (k == 4) return eval1_for_bw<false, 4>(bw);
+  }
+  return nullptr;
+}
+
+}  // namespace fle

@@ -37,8 +37,10 @@ constexpr int kMaxSlots = 32;
 struct PassDesc {
   uint8_t type;     // PassType
   uint8_t col;      // column index
-  uint8_t k;        // chains in this pass (1..4); PASS_IN / PASS_CONST: 1
-  uint8_t pad;
+  uint8_t k;        // chains in this pass: 1, 2 or 4 (3 is padded by repeating the last chain,
+                    // which is harmless because SET/AND/OR of the same value are idempotent);
+                    // PASS_IN / PASS_CONST: 1
+  uint8_t merge;    // 1: all chains fold into slot[0] with the same op -> combine in registers
   uint8_t slot[4];  // destination slot per chain
   uint8_t fold[4];  // FoldOp per chain
   uint8_t neg[4];   // 1: complement the chain result before folding
@@ -58,7 +60,9 @@ struct EvalParams {
   uint32_t bw[FLE_MAX_COLS];
   uint32_t col_off[FLE_MAX_COLS];     // byte offset of the column's region inside a stage
   uint32_t seg_stride[FLE_MAX_COLS];  // byte distance between the 8 skewed segments
-  int32_t ncols, npasses, ncombs, nslots;
+  int32_t ncols, npasses, ncombs, nslots;  // nslots includes in_tmp_slot when present
+  int32_t in_tmp_slot;                     // scratch slot for IN passes (-1: none)
+  uint32_t smem_masks_off;                 // per-pass literal masks [npasses][4][32] u32
   int32_t gpt;      // groups per thread per tile
   int32_t nstages;  // TMA pipeline depth
   uint32_t stage_bytes;
@@ -97,12 +101,15 @@ struct fle_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int num_sms = 0;
-  int max_smem_optin = 0;
+  int max_smem_optin = 0;   // per block
+  int max_smem_per_sm = 0;
+  struct OccEntry { const void* kern; size_t smem; int blocks; };
+  std::vector<OccEntry> occ_cache;
   int64_t launches = 0;
   std::string last_error;
 
   // options
-  int eval_variant = 1;
+  int eval_variant = 1;      // 0 direct loads, 1 staged (single-pass kernels when possible), 2 staged generic only
   int eval_stages = 0;       // 0 = auto
   int eval_block = 256;
   int eval_ctas_per_sm = 0;  // 0 = auto (occupancy)
@@ -150,6 +157,8 @@ int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols_d
 int launch_eval(fle_ctx* ctx, const fle_col_desc* cols_dev, int ncols, const fle_pred_node* nodes,
                 int nnodes, int64_t first_row, int64_t n, uint64_t* bitmap_dev,
                 uint64_t* count_dev);
+// fle_eval1.cu: the single-pass kernel for (PassType, chains, bit width), or nullptr
+const void* eval1_kernel_for(int type, int k, int bw);
 // out = postfix program over K device bitmaps (leaf.col = bitmap index), word by word
 int launch_bitmap_combine(fle_ctx* ctx, const uint64_t* const* leaf_bitmaps_dev, int nleaf,
                           const fle_pred_node* nodes, int nnodes, int64_t nbits, uint64_t* out_dev,

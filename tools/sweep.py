@@ -33,7 +33,9 @@ def peak():
 PEAK = peak()
 
 
-def timeit(fn, reps=10, warm=3):
+def timeit(fn, reps=10, warm=3, inner=8):
+    """Per-launch time with `inner` launches queued back to back between two events, so that the
+    host-side launch path overlaps the previous kernel (as in a real scan loop)."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -41,10 +43,11 @@ def timeit(fn, reps=10, warm=3):
     for _ in range(reps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        fn()
+        for _ in range(inner):
+            fn()
         b.record()
         torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b))
+        ts.append(a.elapsed_time(b) / inner)
     return min(ts), statistics.median(ts)
 
 
