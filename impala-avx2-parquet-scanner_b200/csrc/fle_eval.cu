@@ -947,7 +947,11 @@ int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, 
     const int rc = launch_program(ctx, P1, MODE_SINGLE_PASS, (int)P.bw[c]);
     if (rc != FLE_E_UNSUPPORTED) return rc;
   }
-  if (staged_ok) {
+  // Multi-pass programs: measured on B200 (tools/sweep.py programs, profiles/), the direct-load
+  // kernel currently beats the generic staged kernel (Q6: 0.85 vs 0.63 of the HBM roofline)
+  // because the staged one pays its per-tile pass dispatch once per group at gpt = 1; the
+  // staged generic kernel stays selectable with eval_variant = 2.
+  if (staged_ok && ctx->eval_variant == 2) {
     const int rc = launch_program(ctx, P, MODE_STAGED, sum_bw);
     if (rc != FLE_E_UNSUPPORTED) return rc;  // tile does not fit in shared memory: direct kernel
   }

@@ -98,9 +98,11 @@ int fle_ctx_create(int device, void* cuda_stream, fle_ctx** out);
 int fle_ctx_destroy(fle_ctx* ctx);
 int fle_ctx_set_stream(fle_ctx* ctx, void* cuda_stream);
 int fle_ctx_sync(fle_ctx* ctx);
-/* Tuning knobs, all optional: "eval_variant" (0 = direct-load kernel, 1 = TMA-staged
- * pipeline [default]), "eval_stages", "eval_block", "eval_ctas_per_sm", "eval_gpt",
- * "codec_variant", "h2d_chunk_rows". */
+/* Tuning knobs, all optional: "eval_variant" (0 = direct-load generic kernel for everything;
+ * 1 [default] = TMA-staged single-pass kernels specialised per bit width where the program
+ * is one pass, direct-load generic kernel otherwise; 2 = TMA-staged kernels for everything),
+ * "eval_stages", "eval_ctas_per_sm", "eval_gpt" (0 = auto), "codec_variant",
+ * "h2d_chunk_rows". */
 int fle_ctx_set_option(fle_ctx* ctx, const char* name, int64_t value);
 int64_t fle_ctx_get_option(fle_ctx* ctx, const char* name);
 /* Number of kernels of this library launched through ctx so far (bench `gpu_launches`). */

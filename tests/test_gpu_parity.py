@@ -40,7 +40,7 @@ def test_codec_vs_golden(ctx, golden, bw):
         assert (ctx.unpack(words, bw, first, cnt) == vals[first:first + cnt]).all(), (first, cnt)
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("bw", BWS)
 def test_predicates_vs_golden(ctx, golden, bw, variant):
     ctx.set_option("eval_variant", variant)
@@ -63,7 +63,7 @@ def test_predicates_vs_golden(ctx, golden, bw, variant):
         ctx.set_option("eval_variant", 1)
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_trees_vs_golden(ctx, golden, variant):
     ctx.set_option("eval_variant", variant)
     try:
@@ -96,7 +96,7 @@ def test_single_column_vs_oracle(ctx, oracle, bw):
         [(EQ, 0, int(vals[11]))],
         [(IN, 0, rng.choice(vals, size=8).astype(np.uint64))],
     ]
-    for variant in (1, 0):
+    for variant in (1, 2, 0):
         ctx.set_option("eval_variant", variant)
         for prog in progs:
             bm, cnt = ctx.eval([(words, bw)], prog, n)
@@ -105,8 +105,9 @@ def test_single_column_vs_oracle(ctx, oracle, bw):
     ctx.set_option("eval_variant", 1)
 
 
-@pytest.mark.parametrize("opts", [dict(), dict(eval_block=128), dict(eval_stages=2, eval_gpt=2),
-                                  dict(eval_stages=4, eval_ctas_per_sm=1), dict(h2d_chunk_rows=64 * 4096)])
+@pytest.mark.parametrize("opts", [dict(), dict(eval_variant=2), dict(eval_variant=2, eval_stages=2, eval_gpt=2),
+                                  dict(eval_variant=2, eval_stages=4, eval_ctas_per_sm=1), dict(eval_variant=0),
+                                  dict(h2d_chunk_rows=64 * 4096)])
 def test_multi_column_programs_vs_oracle(ctx, oracle, opts):
     rng = np.random.default_rng(2024)
     n = 64 * 20000 + 17
@@ -138,7 +139,7 @@ def test_multi_column_programs_vs_oracle(ctx, oracle, opts):
             assert (bm == want).all() and cnt == wcnt, name
     finally:
         for k in opts:
-            ctx.set_option(k, {"eval_block": 256}.get(k, 0))
+            ctx.set_option(k, {"eval_variant": 1}.get(k, 0))
 
 
 def test_edge_sizes_and_errors(ctx, oracle):

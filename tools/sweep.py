@@ -188,23 +188,26 @@ def sweep_tune(ctx, out, n):
         v, w = make_col(ctx, n, bwx, seed=400 + bwx)
         del v
         cases[f"lt{bwx}"] = ([(w, bwx)], [(LT, 0, (1 << bwx) // 2)], bwx)
+    v, w3 = make_col(ctx, n, 3, dom=7, seed=500)
+    del v
+    cases["q12"] = ([(w3, 3), q6c[0]], [(IN, 0, [1, 4]), (GE, 1, 730), (AND, None, None), (LT, 1, 1095), (AND, None, None)], 15)
     for cname, (pc, prog, sum_bw) in cases.items():
         prep = (ctx.make_col_descs(pc),) + fle_b200.capi._build_program(prog)
-        for block in (256, 128):
-            for stages in (0, 2, 3, 4, 6):
-                for gpt in (0, 1, 2, 4):
-                    for cps in (0, 1, 2):
-                        ctx.set_option("eval_block", block)
+        for variant in (1, 2):
+            for stages in (0, 2, 3, 4):
+                for gpt in (0, 1, 2, 3, 4, 8):
+                    for cps in (0, 1, 2, 3, 4):
+                        ctx.set_option("eval_variant", variant)
                         ctx.set_option("eval_stages", stages)
                         ctx.set_option("eval_gpt", gpt)
                         ctx.set_option("eval_ctas_per_sm", cps)
                         try:
-                            mn, md = timeit(lambda: ctx.eval_dev(pc, prog, n, bitmap=bm, count=cnt, prepared=prep), reps=5, warm=2)
+                            mn, md = timeit(lambda: ctx.eval_dev(pc, prog, n, bitmap=bm, count=cnt, prepared=prep), reps=4, warm=2)
                         except fle_b200.FleError as e:
-                            rec(out, what="tune", case=cname, block=block, stages=stages, gpt=gpt, ctas=cps, error=str(e))
                             continue
-                        rec(out, what="tune", case=cname, block=block, stages=stages, gpt=gpt, ctas=cps, ms_min=mn,
+                        rec(out, what="tune", case=cname, block=variant, stages=stages, gpt=gpt, ctas=cps, ms_min=mn,
                             ms_med=md, alg_bytes=G * sum_bw * 8 + G * 8)
+    ctx.set_option("eval_variant", 1)
     for k, d in (("eval_block", 256), ("eval_stages", 0), ("eval_gpt", 0), ("eval_ctas_per_sm", 0)):
         ctx.set_option(k, d)
 
