@@ -397,7 +397,7 @@ def main():
             },
             "encoded_GBps": alg_bytes * world / (ms_per_step * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "fle::eval_tma_kernel<256>",
+                         "traffic": None, "peak_source": peak_src, "kernel": "fle::eval1_kernel<IS_LT=true, K=2, BW=12> (TMA-staged single-pass BETWEEN)",
                          "algorithmic_bytes_per_launch": alg_bytes, "mean_launch_ms": mean_kern_ms,
                          "min_launch_ms": min(kern_ms), "frac_of_nominal_8TBps": achieved / 8000.0},
             "q6": {"ms": q6_ms, "rows_per_s": n * world / (q6_ms * 1e-3), "survivors_rank0": q6_count,
