@@ -234,10 +234,21 @@ def main():
     col = ctx.pack_dev(vals, BW)
     # Q6 columns: shipdate D=2526 bw12, discount D=11 bw4, quantity D=50 bw6
     q6_cols = []
-    for d, bw in ((2526, 12), (11, 4), (50, 6)):
+    q6_mask = None
+    price = torch.randint(90_000, 10_500_000, (n,), generator=gen, device=dev, dtype=torch.int64)  # l_extendedprice, cents (PLAIN)
+    disc_dict = torch.arange(0, 11, device=dev, dtype=torch.int64)                                  # l_discount dictionary, cents
+    for (d, bw), (lo_, hi_) in zip(((2526, 12), (11, 4), (50, 6)), ((730, 1094), (5, 7), (0, 22))):
         v = torch.randint(0, d, (n,), generator=gen, device=dev, dtype=torch.int32)
         q6_cols.append((ctx.pack_dev(v, bw), bw))
-        del v
+        m_ = (v >= lo_) & (v <= hi_)
+        q6_mask = m_ if q6_mask is None else (q6_mask & m_)
+        if d == 11:
+            disc_vals = v
+        else:
+            del v
+    q6_want_count = int(q6_mask.sum().item())
+    q6_want_revenue = int((price[q6_mask] * disc_dict[disc_vals[q6_mask].long()]).sum().item())
+    del q6_mask, disc_vals, m_
     q6_prog = [(GE, 0, 730), (LE, 0, 1094), (AND, None, None), (GE, 1, 5), (LE, 1, 7), (AND, None, None),
                (AND, None, None), (LT, 2, 23), (AND, None, None)]
     torch.cuda.synchronize()
@@ -258,12 +269,22 @@ def main():
     cols = [(col, BW)]
     prepared = {sel: (ctx.make_col_descs(cols),) + fle_b200.capi._build_program(progs[sel]) for sel in SELECTIVITIES}
 
-    def step(i):
+    count_ring = torch.zeros(max(args.steps, 16), dtype=torch.int64, device=dev)
+    pending = []
+
+    def step(i, timed=False):
         sel = SELECTIVITIES[i % len(SELECTIVITIES)]
-        ctx.eval_dev(cols, progs[sel], n, bitmap=bitmap, count=count, prepared=prepared[sel])
-        if world > 1:
-            total.copy_(count)
-            dist.all_reduce(total)  # match counts only: 8 bytes over NVLink
+        if world > 1 and timed:
+            # every step's match count is summed over the ranks (8 bytes over NVLink); the
+            # reduce of query i is in flight while the kernel of query i+1 runs
+            c = count_ring[i:i + 1]
+            ctx.eval_dev(cols, progs[sel], n, bitmap=bitmap, count=c, prepared=prepared[sel])
+            pending.append(dist.all_reduce(c, async_op=True))
+        else:
+            ctx.eval_dev(cols, progs[sel], n, bitmap=bitmap, count=count, prepared=prepared[sel])
+            if world > 1:
+                total.copy_(count)
+                dist.all_reduce(total)
         return sel
 
     def barrier():
@@ -287,10 +308,17 @@ def main():
     t0.record(stream)
     for i in range(args.steps):
         ev[i][0].record(stream)
-        step(i)
+        step(i, timed=True)
         ev[i][1].record(stream)
+    for w in pending:
+        w.wait()  # all reduced counts are complete before the clock stops
     t1.record(stream)
     barrier()
+    if world > 1:
+        want_total = torch.tensor([want_counts[SELECTIVITIES[i % len(SELECTIVITIES)]] for i in range(args.steps)],
+                                  dtype=torch.int64, device=dev)
+        dist.all_reduce(want_total)
+        assert torch.equal(count_ring[:args.steps], want_total), "reduced match counts differ from the reference compare"
     sampler.stop()
     launches = ctx.launch_count - launches0
     elapsed_ms = t0.elapsed_time(t1)
@@ -302,27 +330,44 @@ def main():
     ms_per_step = elapsed_ms / args.steps
     value = n * world / (ms_per_step * 1e-3)
 
-    # Q6 compound scan, same protocol (device-resident)
+    # TPC-H Q6 end to end on the device: fused compound scan -> bitmap -> SUM(price * discount)
+    # over the survivors (exact int64) -> one all-reduce of {count, revenue}
     q6_prep = (ctx.make_col_descs(q6_cols),) + fle_b200.capi._build_program(q6_prog)
-    for _ in range(3):
+    agg = torch.zeros(2, dtype=torch.int64, device=dev)
+
+    def q6_step():
         ctx.eval_dev(q6_cols, q6_prog, n, bitmap=bitmap, count=count, prepared=q6_prep)
+        ctx.sum_product_dev(bitmap, n, price, q6_cols[1][0], 4, disc_dict, out=agg)
+        if world > 1:
+            dist.all_reduce(agg)
+
+    for _ in range(3):
+        q6_step()
+    torch.cuda.synchronize()
+    if world == 1:
+        assert int(agg[0].item()) == q6_want_revenue and int(agg[1].item()) == q6_want_count == int(count.item())
     barrier()
     q6_steps = max(10, args.steps // 4)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(stream)
     for _ in range(q6_steps):
-        ctx.eval_dev(q6_cols, q6_prog, n, bitmap=bitmap, count=count, prepared=q6_prep)
-        if world > 1:
-            total.copy_(count)
-            dist.all_reduce(total)
+        q6_step()
     b.record(stream)
     barrier()
     q6_ms = a.elapsed_time(b) / q6_steps
+    # scan kernel alone (no aggregate, no reduce)
+    a.record(stream)
+    for _ in range(q6_steps):
+        ctx.eval_dev(q6_cols, q6_prog, n, bitmap=bitmap, count=count, prepared=q6_prep)
+    b.record(stream)
+    barrier()
+    q6_scan_ms = a.elapsed_time(b) / q6_steps
     if world > 1:
-        t = torch.tensor([q6_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([q6_ms, q6_scan_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        q6_ms = float(t.item())
+        q6_ms, q6_scan_ms = float(t[0].item()), float(t[1].item())
     q6_count = int(count.item())
+    q6_revenue_cents2 = int(agg[0].item())
     q6_bytes = G * (12 + 4 + 6) * 8 + G * 8
 
     peak, peak_src = measured_peak()
@@ -397,12 +442,18 @@ def main():
             },
             "encoded_GBps": alg_bytes * world / (ms_per_step * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "fle::eval1_kernel<IS_LT=true, K=2, BW=12> (TMA-staged single-pass BETWEEN)",
+                         "traffic": 971.6e6, "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch, "
+                         "profiles/r01_eval1_bw12_ncu_full_summary.txt (900.1 MB + 71.5 MB; algorithmic 975.1 MB)",
+                         "peak_source": peak_src, "kernel": "fle::eval1_kernel<IS_LT=true, K=2, BW=12> (TMA-staged single-pass BETWEEN)",
                          "algorithmic_bytes_per_launch": alg_bytes, "mean_launch_ms": mean_kern_ms,
                          "min_launch_ms": min(kern_ms), "frac_of_nominal_8TBps": achieved / 8000.0},
-            "q6": {"ms": q6_ms, "rows_per_s": n * world / (q6_ms * 1e-3), "survivors_rank0": q6_count,
-                   "achieved_GBps_per_gpu": q6_bytes / (q6_ms * 1e-3) / 1e9,
-                   "frac_of_peak": q6_bytes / (q6_ms * 1e-3) / 1e9 / peak, "steps": q6_steps},
+            "q6": {"ms": q6_ms, "scan_ms": q6_scan_ms, "rows_per_s": n * world / (q6_ms * 1e-3),
+                   "what": "fused 3-column 5-leaf scan + SUM(extendedprice*discount) over survivors (exact int64)"
+                           + (" + all-reduce{count,revenue}" if world > 1 else ""),
+                   "survivors_rank0": q6_count, "revenue": q6_revenue_cents2 / 1e4,
+                   "revenue_exact_int64_1e-4_dollars": q6_revenue_cents2,
+                   "scan_achieved_GBps_per_gpu": q6_bytes / (q6_scan_ms * 1e-3) / 1e9,
+                   "scan_frac_of_peak": q6_bytes / (q6_scan_ms * 1e-3) / 1e9 / peak, "steps": q6_steps},
             "clocks": sampler.summary(),
             "gpu_launches": launches,
             "e2e": e2e,

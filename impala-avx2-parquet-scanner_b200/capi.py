@@ -28,7 +28,7 @@ EXPORTS = [
     "fle_device_count", "fle_host_alloc", "fle_host_free", "fle_dev_alloc", "fle_dev_free", "fle_h2d",
     "fle_d2h", "fle_encoded_bytes", "fle_pack_u32", "fle_pack_u32_dev", "fle_unpack_u32",
     "fle_unpack_u32_dev", "fle_eval", "fle_eval_dev", "fle_bitmap_count_dev", "fle_intersect_bitset",
-    "fle_intersect_bitset_dev",
+    "fle_intersect_bitset_dev", "fle_bitmap_select_dev", "fle_gather_dev", "fle_sum_product_dev",
 ]
 
 
@@ -92,6 +92,9 @@ def load_library() -> C.CDLL:
     L.fle_bitmap_count_dev.argtypes = [vp, vp, i64, vp]
     for f in (L.fle_intersect_bitset, L.fle_intersect_bitset_dev):
         f.argtypes = [vp, vp, i64, vp, i64]
+    L.fle_bitmap_select_dev.argtypes = [vp, vp, i64, vp, i64, vp]
+    L.fle_gather_dev.argtypes = [vp, vp, C.c_size_t, i32, vp, vp, i64, vp, i32, i32, vp]
+    L.fle_sum_product_dev.argtypes = [vp, vp, i64, vp, vp, C.c_size_t, i32, vp, i32, vp, vp]
     _lib = L
     return L
 
@@ -275,6 +278,42 @@ class FleContext:
             count = torch.zeros(1, dtype=torch.int64, device=bitmap.device)
         self._check(self.lib.fle_bitmap_count_dev(self.h, bitmap.data_ptr(), nbits, count.data_ptr()))
         return count
+
+    def bitmap_select_dev(self, bitmap, nbits: int, cap: int | None = None, ids=None, count=None):
+        """Ascending row ids of the set bits.  Returns (ids int32 tensor[cap], count int64 tensor[1])."""
+        import torch
+        cap = nbits if cap is None else cap
+        if ids is None:
+            ids = torch.empty(max(1, cap), dtype=torch.int32, device=bitmap.device)
+        if count is None:
+            count = torch.zeros(1, dtype=torch.int64, device=bitmap.device)
+        self._check(self.lib.fle_bitmap_select_dev(self.h, bitmap.data_ptr(), nbits, ids.data_ptr(), cap, count.data_ptr()))
+        return ids, count
+
+    def gather_dev(self, words, bw: int, ids, count, cap: int, dict_values=None, out=None):
+        """Codes (or dictionary values when dict_values is given) of the selected rows."""
+        import torch
+        if dict_values is None:
+            if out is None:
+                out = torch.empty(max(1, cap), dtype=torch.int32, device=words.device)
+            dptr, nd, es = None, 0, 0
+        else:
+            if out is None:
+                out = torch.empty(max(1, cap), dtype=dict_values.dtype, device=words.device)
+            dptr, nd, es = dict_values.data_ptr(), dict_values.numel(), dict_values.element_size()
+        self._check(self.lib.fle_gather_dev(self.h, words.data_ptr(), words.numel() * words.element_size(), bw,
+                                            ids.data_ptr(), count.data_ptr(), cap, dptr, nd, es, out.data_ptr()))
+        return out
+
+    def sum_product_dev(self, bitmap, nrows: int, plain_i64, words, bw: int, dict_i64, out=None):
+        """(sum, count) int64 tensors: SUM over selected rows of plain_i64[r] * dict_i64[code(r)]."""
+        import torch
+        if out is None:
+            out = torch.zeros(2, dtype=torch.int64, device=bitmap.device)
+        self._check(self.lib.fle_sum_product_dev(self.h, bitmap.data_ptr(), nrows, plain_i64.data_ptr(), words.data_ptr(),
+                                                 words.numel() * words.element_size(), bw, dict_i64.data_ptr(),
+                                                 dict_i64.numel(), out.data_ptr(), out.data_ptr() + 8))
+        return out
 
     def intersect_bitset_dev(self, root, n_root: int, sub, n_sub: int):
         self._check(self.lib.fle_intersect_bitset_dev(self.h, root.data_ptr(), n_root, sub.data_ptr(), n_sub))

@@ -659,4 +659,32 @@ int fle_intersect_bitset(fle_ctx* ctx, uint64_t* root, int64_t n_root, const uin
   return FLE_OK;
 }
 
+// ---- survivor materialisation --------------------------------------------------------------
+int fle_bitmap_select_dev(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nbits, uint32_t* row_ids_dev,
+                          int64_t cap, uint64_t* count_dev) {
+  FLE_CHECK_CTX(ctx);
+  return launch_select(ctx, bitmap_dev, nbits, row_ids_dev, cap, count_dev);
+}
+
+int fle_gather_dev(fle_ctx* ctx, const uint8_t* enc_dev, size_t enc_len, int bit_width,
+                   const uint32_t* row_ids_dev, const uint64_t* count_dev, int64_t cap, const void* dict_dev,
+                   int ndict, int elem_size, void* out_dev) {
+  FLE_CHECK_CTX(ctx);
+  (void)enc_len;
+  if (reinterpret_cast<uintptr_t>(enc_dev) & 7) return set_error(ctx, FLE_E_ALIGN, "enc_dev must be 8-byte aligned");
+  return launch_gather(ctx, reinterpret_cast<const uint64_t*>(enc_dev), bit_width, row_ids_dev, count_dev, cap,
+                       dict_dev, ndict, elem_size, out_dev);
+}
+
+int fle_sum_product_dev(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nrows, const int64_t* plain_i64_dev,
+                        const uint8_t* enc_dev, size_t enc_len, int bit_width, const int64_t* dict_i64_dev,
+                        int ndict, int64_t* sum_dev, uint64_t* count_dev) {
+  FLE_CHECK_CTX(ctx);
+  if (bit_width < 1 || bit_width > 32) return set_error(ctx, FLE_E_INVALID, "bit width outside 1..32");
+  if ((uint64_t)((nrows + 63) / 64) * bit_width * 8u > enc_len) return set_error(ctx, FLE_E_BUFFER, "rows beyond the encoded buffer");
+  if (reinterpret_cast<uintptr_t>(enc_dev) & 7) return set_error(ctx, FLE_E_ALIGN, "enc_dev must be 8-byte aligned");
+  return launch_sum_product(ctx, bitmap_dev, nrows, plain_i64_dev, reinterpret_cast<const uint64_t*>(enc_dev),
+                            bit_width, dict_i64_dev, ndict, sum_dev, count_dev);
+}
+
 }  // extern "C"

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -168,5 +169,14 @@ int launch_unpack_u32(fle_ctx* ctx, const uint64_t* enc_dev, int bw, int64_t n, 
 int launch_bitmap_count(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nbits, uint64_t* count_dev);
 int launch_intersect(fle_ctx* ctx, uint64_t* root_dev, int64_t n_root, const uint64_t* sub_dev,
                      int64_t n_sub);
+// fle_scan.cu
+int launch_select(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nbits, uint32_t* ids_dev, int64_t cap,
+                  uint64_t* count_dev);
+int launch_gather(fle_ctx* ctx, const uint64_t* planes_dev, int bw, const uint32_t* ids_dev,
+                  const uint64_t* count_dev, int64_t cap, const void* dict_dev, int ndict, int elem_size,
+                  void* out_dev);
+int launch_sum_product(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nrows, const int64_t* plain_dev,
+                       const uint64_t* planes_dev, int bw, const int64_t* dict_dev, int ndict, int64_t* sum_dev,
+                       uint64_t* count_dev);
 
 }  // namespace fle

@@ -1,0 +1,250 @@
+// Survivor materialisation: what AssembleRows does AFTER the selection bitmap
+// exists -- /root/reference/hdfs-parquet-scanner.cc:1134-1168 turns the bitmap into skip
+// distances and then calls ReadValue(skip) -> DictDecoder::GetValue(T*, skip) ->
+// FleDecoder::Get(T*, skip) (fle-encoding.h:344-379) once per survivor and column.
+// On the device that is
+//   select   : bitmap -> ascending row ids            (ordered stream compaction)
+//   gather   : row id -> code = bit (63 - r%64) of the bw plane words of group r/64
+//   lookup   : code -> dictionary value               (dense output column)
+// plus the fused aggregate a TPC-H Q6 scan needs downstream of the bitmap:
+//   sum_product : SUM over survivors of plain_i64[r] * dict[code(r)]   (exact int64)
+#include "fle_device.cuh"
+#include "fle_internal.h"
+
+namespace fle {
+
+constexpr int kSelThreads = 256;
+constexpr int kSelWordsPerThread = 4;
+constexpr int kSelWordsPerBlock = kSelThreads * kSelWordsPerThread;
+
+__device__ __forceinline__ uint64_t sel_tail_mask(int64_t w, int64_t nbits) {
+  const int64_t left = nbits - w * 64;
+  if (left >= 64) return ~0ull;
+  if (left <= 0) return 0ull;
+  return (1ull << left) - 1ull;
+}
+
+// pass 1: popcount per block of kSelWordsPerBlock words (thread t owns consecutive words)
+__global__ void __launch_bounds__(kSelThreads)
+select_count_kernel(const uint64_t* __restrict__ bm, int64_t nbits, int64_t nwords, uint64_t* __restrict__ block_sums) {
+  __shared__ uint32_t warp_sum[kSelThreads / 32];
+  const int64_t w0 = (int64_t)blockIdx.x * kSelWordsPerBlock + (int64_t)threadIdx.x * kSelWordsPerThread;
+  uint32_t c = 0;
+#pragma unroll
+  for (int k = 0; k < kSelWordsPerThread; ++k) {
+    const int64_t w = w0 + k;
+    if (w < nwords) c += __popcll(bm[w] & sel_tail_mask(w, nbits));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint64_t t = 0;
+    for (int i = 0; i < kSelThreads / 32; ++i) t += warp_sum[i];
+    block_sums[blockIdx.x] = t;
+  }
+}
+
+// pass 2 (one block): exclusive scan of the block sums in place; total -> *count_out
+__global__ void __launch_bounds__(1024) select_scan_kernel(uint64_t* __restrict__ block_sums, int nblocks,
+                                                           uint64_t* __restrict__ count_out) {
+  __shared__ uint64_t warp_tot[32];
+  __shared__ uint64_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < nblocks; base += 1024) {
+    const int i = base + threadIdx.x;
+    const uint64_t v = i < nblocks ? block_sums[i] : 0;
+    uint64_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint64_t y = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((threadIdx.x & 31) >= o) incl += y;
+    }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint64_t woff = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += warp_tot[w];
+    const uint64_t carry = carry_s;
+    if (i < nblocks) block_sums[i] = carry + woff + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + woff + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && count_out) *count_out = carry_s;
+}
+
+// pass 3: every block writes its survivors' row ids at its scanned offset, in row order
+__global__ void __launch_bounds__(kSelThreads)
+select_write_kernel(const uint64_t* __restrict__ bm, int64_t nbits, int64_t nwords,
+                    const uint64_t* __restrict__ block_offs, uint32_t* __restrict__ ids, int64_t cap) {
+  __shared__ uint32_t warp_scan[kSelThreads / 32];
+  const int64_t w0 = (int64_t)blockIdx.x * kSelWordsPerBlock + (int64_t)threadIdx.x * kSelWordsPerThread;
+  uint64_t m[kSelWordsPerThread];
+  uint32_t mine = 0;
+#pragma unroll
+  for (int k = 0; k < kSelWordsPerThread; ++k) {
+    const int64_t w = w0 + k;
+    m[k] = w < nwords ? (bm[w] & sel_tail_mask(w, nbits)) : 0ull;
+    mine += __popcll(m[k]);
+  }
+  uint32_t incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((threadIdx.x & 31) >= o) incl += y;
+  }
+  if ((threadIdx.x & 31) == 31) warp_scan[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  uint32_t woff = 0;
+  for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += warp_scan[w];
+  int64_t pos = (int64_t)block_offs[blockIdx.x] + woff + (incl - mine);
+#pragma unroll
+  for (int k = 0; k < kSelWordsPerThread; ++k) {
+    uint64_t x = m[k];
+    const uint32_t base = (uint32_t)((w0 + k) * 64);
+    while (x) {
+      const int b = __ffsll((long long)x) - 1;
+      if (pos < cap) ids[pos] = base + (uint32_t)b;
+      ++pos;
+      x &= x - 1;
+    }
+  }
+}
+
+// code of row r: bit (63 - r%64) of each of the bw plane words of group r/64
+__device__ __forceinline__ uint32_t code_at(const uint64_t* __restrict__ planes, int bw, uint32_t r) {
+  const uint64_t* g = planes + (uint64_t)(r >> 6) * bw;
+  const int sh = 63 - (int)(r & 63);
+  uint32_t v = 0;
+  for (int i = 0; i < bw; ++i) v |= (uint32_t)((__ldg(g + i) >> sh) & 1ull) << i;
+  return v;
+}
+
+// out[j] = code(ids[j])            (dict == nullptr)
+// out[j] = dict[code(ids[j])]      (elem_size 4 or 8; codes >= ndict give 0, as GetValue()==false)
+__global__ void __launch_bounds__(256)
+gather_kernel(const uint64_t* __restrict__ planes, int bw, const uint32_t* __restrict__ ids,
+              const uint64_t* __restrict__ count_dev, int64_t cap, const void* __restrict__ dict, int ndict,
+              int elem_size, void* __restrict__ out) {
+  const int64_t n = min((int64_t)*count_dev, cap);
+  for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < n; j += (int64_t)gridDim.x * 256) {
+    const uint32_t c = code_at(planes, bw, ids[j]);
+    if (dict == nullptr) {
+      reinterpret_cast<uint32_t*>(out)[j] = c;
+    } else if (elem_size == 4) {
+      reinterpret_cast<uint32_t*>(out)[j] = c < (uint32_t)ndict ? reinterpret_cast<const uint32_t*>(dict)[c] : 0u;
+    } else {
+      reinterpret_cast<uint64_t*>(out)[j] = c < (uint32_t)ndict ? reinterpret_cast<const uint64_t*>(dict)[c] : 0ull;
+    }
+  }
+}
+
+// Fused Q6-style aggregate: one thread per 64-row group; groups without survivors cost one
+// bitmap word.  Exact int64 arithmetic; per-block partials are added with 64-bit atomics.
+__global__ void __launch_bounds__(256)
+sum_product_kernel(const uint64_t* __restrict__ bm, int64_t nrows, const int64_t* __restrict__ plain,
+                   const uint64_t* __restrict__ planes, int bw, const int64_t* __restrict__ dict, int ndict,
+                   unsigned long long* __restrict__ sum_out, unsigned long long* __restrict__ count_out) {
+  __shared__ long long warp_sum[8];
+  __shared__ unsigned long long warp_cnt[8];
+  const int64_t nwords = (nrows + 63) >> 6;
+  long long s = 0;
+  unsigned long long c = 0;
+  for (int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x; g < nwords; g += (int64_t)gridDim.x * 256) {
+    uint64_t x = bm[g] & sel_tail_mask(g, nrows);
+    if (x == 0) continue;
+    uint64_t w[32];
+    const uint64_t* gp = planes + (uint64_t)g * bw;
+    for (int i = 0; i < bw; ++i) w[i] = __ldg(gp + i);
+    c += __popcll(x);
+    while (x) {
+      const int b = __ffsll((long long)x) - 1;  // row b of the group sits at plane bit 63-b
+      uint32_t code = 0;
+      for (int i = 0; i < bw; ++i) code |= (uint32_t)((w[i] >> (63 - b)) & 1ull) << i;
+      const long long d = code < (uint32_t)ndict ? dict[code] : 0;
+      s += plain[g * 64 + b] * d;
+      x &= x - 1;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    warp_sum[threadIdx.x >> 5] = s;
+    warp_cnt[threadIdx.x >> 5] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long ts = 0;
+    unsigned long long tc = 0;
+    for (int i = 0; i < 8; ++i) { ts += warp_sum[i]; tc += warp_cnt[i]; }
+    if (tc) {
+      atomicAdd(sum_out, (unsigned long long)ts);  // two's complement: exact for signed sums too
+      if (count_out) atomicAdd(count_out, tc);
+    }
+  }
+}
+
+int launch_select(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nbits, uint32_t* ids_dev, int64_t cap,
+                  uint64_t* count_dev) {
+  if (nbits < 0 || cap < 0 || !count_dev || (nbits > 0 && !bitmap_dev) || (cap > 0 && !ids_dev))
+    return set_error(ctx, FLE_E_INVALID, "bad select arguments");
+  if (nbits > (int64_t)0xFFFFFFFFll) return set_error(ctx, FLE_E_UNSUPPORTED, "row ids are 32-bit: at most 2^32-1 rows per call");
+  if (nbits == 0) {
+    FLE_CUDA_TRY(ctx, cudaMemsetAsync(count_dev, 0, 8, ctx->stream));
+    return FLE_OK;
+  }
+  const int64_t nwords = (nbits + 63) / 64;
+  const int nblocks = (int)((nwords + kSelWordsPerBlock - 1) / kSelWordsPerBlock);
+  int rc = ensure_scratch(ctx, nblocks, 0);
+  if (rc != FLE_OK) return rc;
+  select_count_kernel<<<nblocks, kSelThreads, 0, ctx->stream>>>(bitmap_dev, nbits, nwords, ctx->d_partial);
+  select_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_partial, nblocks, count_dev);
+  select_write_kernel<<<nblocks, kSelThreads, 0, ctx->stream>>>(bitmap_dev, nbits, nwords, ctx->d_partial, ids_dev, cap);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(ctx, e, "select launch");
+  ctx->launches += 3;
+  return FLE_OK;
+}
+
+int launch_gather(fle_ctx* ctx, const uint64_t* planes_dev, int bw, const uint32_t* ids_dev,
+                  const uint64_t* count_dev, int64_t cap, const void* dict_dev, int ndict, int elem_size,
+                  void* out_dev) {
+  if (bw < 1 || bw > 32) return set_error(ctx, FLE_E_INVALID, "bit width outside 1..32");
+  if (!planes_dev || !ids_dev || !count_dev || !out_dev || cap < 0)
+    return set_error(ctx, FLE_E_INVALID, "bad gather arguments");
+  if (dict_dev && elem_size != 4 && elem_size != 8) return set_error(ctx, FLE_E_INVALID, "dictionary elements must be 4 or 8 bytes");
+  if (cap == 0) return FLE_OK;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 8, (cap + 255) / 256));
+  gather_kernel<<<grid, 256, 0, ctx->stream>>>(planes_dev, bw, ids_dev, count_dev, cap, dict_dev, ndict, elem_size, out_dev);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(ctx, e, "gather launch");
+  ctx->launches += 1;
+  return FLE_OK;
+}
+
+int launch_sum_product(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nrows, const int64_t* plain_dev,
+                       const uint64_t* planes_dev, int bw, const int64_t* dict_dev, int ndict, int64_t* sum_dev,
+                       uint64_t* count_dev) {
+  if (bw < 1 || bw > 32) return set_error(ctx, FLE_E_INVALID, "bit width outside 1..32");
+  if (nrows < 0 || !sum_dev || (nrows > 0 && (!bitmap_dev || !plain_dev || !planes_dev || !dict_dev)))
+    return set_error(ctx, FLE_E_INVALID, "bad sum_product arguments");
+  FLE_CUDA_TRY(ctx, cudaMemsetAsync(sum_dev, 0, 8, ctx->stream));
+  if (count_dev) FLE_CUDA_TRY(ctx, cudaMemsetAsync(count_dev, 0, 8, ctx->stream));
+  if (nrows == 0) return FLE_OK;
+  const int64_t nwords = (nrows + 63) / 64;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 8, (nwords + 255) / 256));
+  sum_product_kernel<<<grid, 256, 0, ctx->stream>>>(bitmap_dev, nrows, plain_dev, planes_dev, bw, dict_dev, ndict,
+                                                   reinterpret_cast<unsigned long long*>(sum_dev),
+                                                   reinterpret_cast<unsigned long long*>(count_dev));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(ctx, e, "sum_product launch");
+  ctx->launches += 1;
+  return FLE_OK;
+}
+
+}  // namespace fle

@@ -174,6 +174,29 @@ int fle_intersect_bitset(fle_ctx* ctx, uint64_t* root, int64_t n_root, const uin
 int fle_intersect_bitset_dev(fle_ctx* ctx, uint64_t* root_dev, int64_t n_root,
                              const uint64_t* sub_dev, int64_t n_sub);
 
+/* ---- survivor materialisation (device-resident) ----------------------------------------- */
+/* Replaces the bitmap -> skip-distance list of AssembleRows (hdfs-parquet-scanner.cc:1134-1148):
+ * writes the row indices of the set bits, ascending, to row_ids_dev[0..min(count, cap)) and the
+ * number of set bits to *count_dev.  nbits < 2^32. */
+int fle_bitmap_select_dev(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nbits,
+                          uint32_t* row_ids_dev, int64_t cap, uint64_t* count_dev);
+/* Replaces ReadValue(skip) -> DictDecoder<T>::GetValue(T*, skip) -> FleDecoder::Get(T*, skip)
+ * per survivor (hdfs-parquet-scanner.cc:1151-1168, dict-encoding.h:321-330,
+ * fle-encoding.h:344-379): out[j] = code of row row_ids_dev[j] for j < min(*count_dev, cap).
+ * With dict_dev != NULL (elem_size 4 or 8 bytes, ndict entries) the dictionary value is written
+ * instead of the code (a code >= ndict yields 0, where GetValue returns false). */
+int fle_gather_dev(fle_ctx* ctx, const uint8_t* enc_dev, size_t enc_len, int bit_width,
+                   const uint32_t* row_ids_dev, const uint64_t* count_dev, int64_t cap,
+                   const void* dict_dev, int ndict, int elem_size, void* out_dev);
+/* Downstream aggregate of a TPC-H Q6-shaped scan, fused with the materialisation:
+ * *sum_dev = SUM over rows r with bitmap bit r set of plain_i64_dev[r] * dict_i64_dev[code(r)],
+ * exact in int64 (e.g. l_extendedprice in cents (PLAIN) x l_discount (dictionary, cents));
+ * *count_dev = number of such rows.  bitmap row r <-> plain_i64_dev[r] <-> row r of enc_dev. */
+int fle_sum_product_dev(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nrows,
+                        const int64_t* plain_i64_dev, const uint8_t* enc_dev, size_t enc_len,
+                        int bit_width, const int64_t* dict_i64_dev, int ndict, int64_t* sum_dev,
+                        uint64_t* count_dev);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

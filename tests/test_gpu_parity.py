@@ -292,3 +292,41 @@ def test_cfg1_between_full_size(ctx):
     cnt = ctx.bitmap_count_dev(bm1, n)
     torch.cuda.synchronize()
     assert int(cnt.item()) == want
+
+
+# ------------------------------------------------------------------------------------------
+# survivor materialisation + the Q6 aggregate
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("sel", [0.0, 0.019, 0.5, 1.0])
+def test_select_gather_sum_product(ctx, sel):
+    import torch
+    n = 64 * 50000 + 41
+    g = torch.Generator(device="cuda").manual_seed(77)
+    ship = torch.randint(0, 2526, (n,), generator=g, device="cuda", dtype=torch.int32)
+    disc = torch.randint(0, 11, (n,), generator=g, device="cuda", dtype=torch.int32)
+    price = torch.randint(90_000, 10_500_000, (n,), generator=g, device="cuda", dtype=torch.int64)
+    w_ship, w_disc = ctx.pack_dev(ship, 12), ctx.pack_dev(disc, 4)
+    hi = int(round(sel * 2526)) - 1
+    prog = [(LE, 0, hi)] if hi >= 0 else [(NONE, None, None)]
+    bm, cnt = ctx.eval_dev([(w_ship, 12)], prog, n)
+    mask = ship <= hi
+    want_ids = torch.nonzero(mask).flatten().to(torch.int32)
+    ids, c2 = ctx.bitmap_select_dev(bm, n)
+    torch.cuda.synchronize()
+    k = int(c2.item())
+    assert k == int(cnt.item()) == want_ids.numel()
+    assert torch.equal(ids[:k], want_ids)                       # ascending row ids == skip distances
+    codes = ctx.gather_dev(w_disc, 4, ids, c2, n)
+    assert torch.equal(codes[:k], disc[mask])                   # Get(val, skip) per survivor
+    dict_disc = torch.arange(0, 11, device="cuda", dtype=torch.int64) * 100 + 7   # any sorted dictionary
+    vals = ctx.gather_dev(w_disc, 4, ids, c2, n, dict_values=dict_disc)
+    assert torch.equal(vals[:k], dict_disc[disc[mask].long()])  # dictionary lookup -> dense column
+    out = ctx.sum_product_dev(bm, n, price, w_disc, 4, dict_disc)
+    torch.cuda.synchronize()
+    want = int((price[mask] * dict_disc[disc[mask].long()]).sum().item())  # exact int64
+    assert int(out[0].item()) == want and int(out[1].item()) == k
+    # capacity smaller than the number of survivors: count is still exact, ids truncated
+    if k > 10:
+        ids2, c3 = ctx.bitmap_select_dev(bm, n, cap=10)
+        torch.cuda.synchronize()
+        assert int(c3.item()) == k and torch.equal(ids2[:10], want_ids[:10])
