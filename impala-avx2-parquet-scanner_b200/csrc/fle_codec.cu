@@ -11,6 +11,10 @@
 // lanes), and planes >= bw are compile-time zeros that fold out of the network.
 // Values move between registers and global memory through a swizzled shared-memory tile so
 // that every global access is a fully coalesced 128-bit transaction.
+#include <mutex>
+#include <set>
+#include <utility>
+
 #include "fle_device.cuh"
 #include "fle_internal.h"
 
@@ -19,9 +23,11 @@ namespace fle {
 constexpr int kCodecThreads = 128;               // groups per tile
 constexpr int kTileValueBytes = kCodecThreads * 256;  // 64 u32 values per group
 
-// value tile in shared memory: row = group (256 B), 16-byte chunks rotated by the row index
+// value tile in shared memory: row = group (256 B), 16-byte chunks rotated by row + row/16, so
+// that 8 lanes are conflict-free both when they own consecutive rows (direct kernels) and when
+// they own rows 16 apart (staged kernels: lane t works on row 16*(t&7) + (t>>3))
 __device__ __forceinline__ uint32_t tile_chunk_addr(uint32_t tile, int row, int chunk) {
-  return tile + row * 256 + (((chunk + row) & 15) << 4);
+  return tile + row * 256 + (((chunk + row + (row >> 4)) & 15) << 4);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -170,6 +176,189 @@ pack_kernel(const uint32_t* __restrict__ vals, int64_t nvals, int64_t ngroups, u
 }
 
 // ------------------------------------------------------------------------------------------
+// TMA-staged variants (codec_variant = 1, default).
+//
+// The direct variants above fetch / store each thread's bw plane words with 64-bit accesses that
+// are bw*8 bytes apart between neighbouring lanes: one warp instruction touches 32 different
+// 128-byte lines, and for wide columns the L1 wavefront rate, not HBM, bounds the kernel
+// (profiles/: bw 16/24/32 at 0.47-0.58 of roofline).  Here the plane side of a 128-group tile
+// moves as 8 TMA bulk copies (cp.async.bulk) between global memory and a shared-memory image
+// whose 8 segments are skewed by 16 bytes, so that the per-thread 64/128-bit shared accesses are
+// bank-conflict free for every bit width (same layout as the eval kernels).
+// ------------------------------------------------------------------------------------------
+template <int BW>
+struct PlaneTile {
+  static constexpr int kGroups = kCodecThreads;             // 128 groups per tile
+  static constexpr int kSegGroups = kGroups / 8;            // 16
+  static constexpr uint32_t kSegBytes = kSegGroups * BW * 8;
+  static constexpr uint32_t kSegStride = kSegBytes + 16;
+  static constexpr uint32_t kBytes = 8 * kSegStride;        // shared-memory image of one tile
+  // thread t works on segment t & 7, group (t >> 3) of that segment
+  __device__ static __forceinline__ uint32_t thread_off(int t) {
+    return (uint32_t)(t & 7) * kSegStride + (uint32_t)(t >> 3) * (BW * 8);
+  }
+  __device__ static __forceinline__ int thread_group(int t) { return (t & 7) * kSegGroups + (t >> 3); }
+};
+
+template <int BW>
+__global__ void __launch_bounds__(kCodecThreads)
+unpack_tma_kernel(const uint64_t* __restrict__ enc, int64_t ngroups, int64_t nvals, uint32_t* __restrict__ out) {
+  using PT = PlaneTile<BW>;
+  constexpr int kStages = 2;
+  extern __shared__ __align__(128) uint8_t smem[];
+  // [value tile 32 KB][stage 0][stage 1][2 mbarriers]
+  const uint32_t tile = smem_u32(smem);
+  const uint32_t stage0 = tile + kTileValueBytes;
+  const uint32_t bar0 = stage0 + kStages * ((PT::kBytes + 127) / 128 * 128);
+  constexpr uint32_t kStageStride = (PT::kBytes + 127) / 128 * 128;
+  const int t = threadIdx.x;
+  const int64_t ntiles_full = ngroups / PT::kGroups;  // full tiles go through TMA
+
+  if (t == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(bar0 + s * 8, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue = [&](int stage, int64_t tl) {
+    const uint32_t bar = bar0 + stage * 8;
+    mbar_arrive_expect_tx(bar, 8 * PT::kSegBytes);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(enc) + (uint64_t)tl * PT::kGroups * BW * 8;
+#pragma unroll
+    for (int s = 0; s < 8; ++s)
+      tma_load_1d(stage0 + stage * kStageStride + s * PT::kSegStride, src + (uint64_t)s * PT::kSegBytes, PT::kSegBytes, bar);
+  };
+  if (t == 0 && (int64_t)blockIdx.x < ntiles_full) issue(0, blockIdx.x);
+
+  const int64_t ntiles = (ngroups + PT::kGroups - 1) / PT::kGroups;
+  int stage = 0;
+  uint32_t parity = 0;
+  for (int64_t tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+    const bool full = tl < ntiles_full;
+    const int row = full ? PT::thread_group(t) : t;  // tile row (group inside the tile) of this thread
+    const int64_t g = tl * PT::kGroups + row;
+    uint64_t w[BW];
+    if (full) {
+      // prefetch the next tile into the other stage (its previous contents were consumed in
+      // the previous iteration, which ended with __syncthreads)
+      if (t == 0) {
+        const int64_t nxt = tl + gridDim.x;
+        if (nxt < ntiles_full) issue(stage ^ 1, nxt);
+      }
+      mbar_wait(bar0 + stage * 8, parity);
+      const uint32_t a = stage0 + stage * kStageStride + PT::thread_off(t);
+      if constexpr (BW % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < BW; i += 2) lds128(a + i * 8, w[i], w[i + 1 < BW ? i + 1 : i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < BW; ++i) w[i] = lds64(a + i * 8);
+      }
+      stage ^= 1;
+      if (stage == 0) parity ^= 1u;
+    } else if (g < ngroups) {
+      const uint64_t* src = enc + g * BW;
+#pragma unroll
+      for (int i = 0; i < BW; ++i) w[i] = __ldg(src + i);
+    }
+    if (g < ngroups) {
+      uint32_t v[64];
+      transpose_planes_to_values<BW>(w, v);
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        sts128u(tile_chunk_addr(tile, row, c), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    }
+    __syncthreads();
+    const int64_t v0 = tl * PT::kGroups * 64;
+    uint32_t* dst = out + v0;
+#pragma unroll 4
+    for (int it = 0; it < 16; ++it) {
+      const int L = it * kCodecThreads + t;
+      const int64_t vi = v0 + (int64_t)L * 4;
+      if (vi >= nvals) continue;
+      uint32_t a, b, c, d;
+      lds128u(tile_chunk_addr(tile, L >> 4, L & 15), a, b, c, d);
+      if (vi + 4 <= nvals) {
+        stg_stream128(dst + L * 4, make_uint4(a, b, c, d));
+      } else {
+        dst[L * 4] = a;
+        if (vi + 1 < nvals) dst[L * 4 + 1] = b;
+        if (vi + 2 < nvals) dst[L * 4 + 2] = c;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int BW>
+__global__ void __launch_bounds__(kCodecThreads)
+pack_tma_kernel(const uint32_t* __restrict__ vals, int64_t nvals, int64_t ngroups, uint64_t* __restrict__ enc) {
+  using PT = PlaneTile<BW>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  // [value tile 32 KB][plane image of the tile]
+  const uint32_t tile = smem_u32(smem);
+  const uint32_t planes = tile + kTileValueBytes;
+  const int t = threadIdx.x;
+  const int64_t ntiles = (ngroups + PT::kGroups - 1) / PT::kGroups;
+  const int64_t ntiles_full = ngroups / PT::kGroups;
+  for (int64_t tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+    const int64_t v0 = tl * PT::kGroups * 64;
+    const uint32_t* src = vals + v0;
+#pragma unroll 4
+    for (int it = 0; it < 16; ++it) {
+      const int L = it * kCodecThreads + t;
+      const int64_t vi = v0 + (int64_t)L * 4;
+      uint4 x = make_uint4(0, 0, 0, 0);
+      if (vi + 4 <= nvals) {
+        x = ldg_stream128(src + L * 4);
+      } else if (vi < nvals) {
+        x.x = src[L * 4];
+        if (vi + 1 < nvals) x.y = src[L * 4 + 1];
+        if (vi + 2 < nvals) x.z = src[L * 4 + 2];
+      }
+      sts128u(tile_chunk_addr(tile, L >> 4, L & 15), x.x, x.y, x.z, x.w);
+    }
+    // the previous tile's bulk stores must have finished READING the plane image before it is
+    // overwritten (only thread 0 issued them, so only it can wait on the bulk group)
+    if (t == 0) tma_store_wait_read<0>();
+    __syncthreads();
+    const bool full = tl < ntiles_full;
+    const int row = full ? PT::thread_group(t) : t;
+    const int64_t g = tl * PT::kGroups + row;
+    if (g < ngroups) {
+      uint32_t v[64];
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        lds128u(tile_chunk_addr(tile, row, c), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      uint64_t w[BW];
+      transpose_values_to_planes<BW>(v, w);
+      if (full) {
+        const uint32_t a = planes + PT::thread_off(t);
+#pragma unroll
+        for (int i = 0; i < BW; ++i) sts64(a + i * 8, w[i]);
+      } else {
+        uint64_t* dst = enc + g * BW;
+#pragma unroll
+        for (int i = 0; i < BW; ++i) dst[i] = w[i];
+      }
+    }
+    if (full) {
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the bulk-copy engine
+      __syncthreads();
+      if (t == 0) {
+        uint8_t* dst = reinterpret_cast<uint8_t*>(enc) + (uint64_t)tl * PT::kGroups * BW * 8;
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+          tma_store_1d(dst + (uint64_t)s * PT::kSegBytes, planes + s * PT::kSegStride, PT::kSegBytes);
+        tma_store_commit();
+      }
+    } else {
+      __syncthreads();
+    }
+  }
+  if (t == 0) tma_store_wait<0>();  // all bulk stores complete before the CTA exits
+}
+
+// ------------------------------------------------------------------------------------------
 // dispatch
 // ------------------------------------------------------------------------------------------
 namespace {
@@ -194,6 +383,38 @@ PackFn pack_table_entry(int bw, Seq<I...>) {
   static const PackFn tab[] = {pack_kernel<I>...};
   return tab[bw - 1];
 }
+template <int... I>
+UnpackFn unpack_tma_table_entry(int bw, Seq<I...>) {
+  static const UnpackFn tab[] = {unpack_tma_kernel<I>...};
+  return tab[bw - 1];
+}
+template <int... I>
+PackFn pack_tma_table_entry(int bw, Seq<I...>) {
+  static const PackFn tab[] = {pack_tma_kernel<I>...};
+  return tab[bw - 1];
+}
+template <int... I>
+uint32_t plane_tile_bytes(int bw, Seq<I...>) {
+  static const uint32_t tab[] = {PlaneTile<I>::kBytes...};
+  return tab[bw - 1];
+}
+
+// opt in to > 48 KB of dynamic shared memory once per kernel and device (process-wide)
+int raise_smem_limit(fle_ctx* ctx, const void* kern, size_t smem_bytes) {
+  if (smem_bytes <= 48 * 1024) return FLE_OK;
+  static std::mutex mu;
+  static std::set<std::pair<int, const void*> > raised;
+  std::lock_guard<std::mutex> lock(mu);
+  const std::pair<int, const void*> key(ctx->device, kern);
+  if (raised.find(key) != raised.end()) return FLE_OK;
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+  if (e != cudaSuccess) return set_cuda_error(ctx, e, "cudaFuncGetAttributes");
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin - (int)fa.sharedSizeBytes);
+  if (e != cudaSuccess) return set_cuda_error(ctx, e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+  raised.insert(key);
+  return FLE_OK;
+}
 
 int codec_grid(fle_ctx* ctx, int64_t ngroups) {
   const int64_t ntiles = (ngroups + kCodecThreads - 1) / kCodecThreads;
@@ -207,6 +428,21 @@ int launch_unpack_u32(fle_ctx* ctx, const uint64_t* enc_dev, int bw, int64_t n, 
   if (bw < 1 || bw > 32) return set_error(ctx, FLE_E_INVALID, "bit width outside 1..32");
   if (n == 0) return FLE_OK;
   const int64_t G = (n + 63) / 64;
+  if (ctx->codec_variant != 0 && (reinterpret_cast<uintptr_t>(enc_dev) & 15) == 0) {
+    UnpackFn fn = unpack_tma_table_entry(bw, MakeSeq<32>::type());
+    const size_t stage = (plane_tile_bytes(bw, MakeSeq<32>::type()) + 127) / 128 * 128;
+    const size_t smem = kTileValueBytes + 2 * stage + 64;
+    int rc = raise_smem_limit(ctx, (const void*)fn, smem);
+    if (rc != FLE_OK) return rc;
+    const int per_sm = std::max<int>(1, std::min<int>(8, (int)((size_t)ctx->max_smem_per_sm / (smem + 1024))));
+    const int64_t ntiles = (G + kCodecThreads - 1) / kCodecThreads;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)ctx->num_sms * per_sm));
+    fn<<<grid, kCodecThreads, smem, ctx->stream>>>(enc_dev, G, n, out_dev);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(ctx, e, "unpack_tma_kernel launch");
+    ctx->launches += 1;
+    return FLE_OK;
+  }
   UnpackFn fn = unpack_table_entry(bw, MakeSeq<32>::type());
   fn<<<codec_grid(ctx, G), kCodecThreads, 0, ctx->stream>>>(enc_dev, G, n, out_dev);
   cudaError_t e = cudaGetLastError();
@@ -221,6 +457,20 @@ int launch_pack_u32(fle_ctx* ctx, const uint32_t* vals_dev, int64_t n, int bw, u
   if (G == 0) {
     // Flush() packs one group even when nothing was Put (fle-encoding.h:9806-9811)
     FLE_CUDA_TRY(ctx, cudaMemsetAsync(enc_dev, 0, (size_t)bw * 8, ctx->stream));
+    return FLE_OK;
+  }
+  if (ctx->codec_variant != 0 && (reinterpret_cast<uintptr_t>(enc_dev) & 15) == 0) {
+    PackFn fn = pack_tma_table_entry(bw, MakeSeq<32>::type());
+    const size_t smem = kTileValueBytes + (plane_tile_bytes(bw, MakeSeq<32>::type()) + 127) / 128 * 128;
+    int rc = raise_smem_limit(ctx, (const void*)fn, smem);
+    if (rc != FLE_OK) return rc;
+    const int per_sm = std::max<int>(1, std::min<int>(8, (int)((size_t)ctx->max_smem_per_sm / (smem + 1024))));
+    const int64_t ntiles = (G + kCodecThreads - 1) / kCodecThreads;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)ctx->num_sms * per_sm));
+    fn<<<grid, kCodecThreads, smem, ctx->stream>>>(vals_dev, n, G, enc_dev);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(ctx, e, "pack_tma_kernel launch");
+    ctx->launches += 1;
     return FLE_OK;
   }
   PackFn fn = pack_table_entry(bw, MakeSeq<32>::type());

@@ -155,16 +155,18 @@ sum_product_kernel(const uint64_t* __restrict__ bm, int64_t nrows, const int64_t
   for (int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x; g < nwords; g += (int64_t)gridDim.x * 256) {
     uint64_t x = bm[g] & sel_tail_mask(g, nrows);
     if (x == 0) continue;
-    uint64_t w[32];
     const uint64_t* gp = planes + (uint64_t)g * bw;
-    for (int i = 0; i < bw; ++i) w[i] = __ldg(gp + i);
     c += __popcll(x);
+    const int64_t* pg = plain + g * 64;
     while (x) {
       const int b = __ffsll((long long)x) - 1;  // row b of the group sits at plane bit 63-b
+      const long long pv = __ldg(pg + b);       // issue the random price load first
+      const int sh = 63 - b;
       uint32_t code = 0;
-      for (int i = 0; i < bw; ++i) code |= (uint32_t)((w[i] >> (63 - b)) & 1ull) << i;
-      const long long d = code < (uint32_t)ndict ? dict[code] : 0;
-      s += plain[g * 64 + b] * d;
+#pragma unroll 4
+      for (int i = 0; i < bw; ++i) code |= (uint32_t)((__ldg(gp + i) >> sh) & 1ull) << i;  // L1 hits after the first survivor
+      const long long d = code < (uint32_t)ndict ? __ldg(dict + code) : 0;
+      s += pv * d;
       x &= x - 1;
     }
   }

@@ -24,8 +24,10 @@ def popcount(words):
 # ------------------------------------------------------------------------------------------
 # golden vectors (outputs of the reference's own code)
 # ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("codec_variant", [1, 0])
 @pytest.mark.parametrize("bw", BWS)
-def test_codec_vs_golden(ctx, golden, bw):
+def test_codec_vs_golden(ctx, golden, bw, codec_variant):
+    ctx.set_option("codec_variant", codec_variant)
     n = int(golden["meta_n"][0])
     vals, words = golden[f"vals_{bw}"], golden[f"words_{bw}"]
     mine = ctx.pack(vals, bw)
@@ -38,6 +40,7 @@ def test_codec_vs_golden(ctx, golden, bw):
     assert (ctx.unpack(words, bw, 0, n) == vals).all()  # stale tail bits in `words` must not leak
     for first, cnt in ((0, 1), (1, 1), (13, 100), (63, 2), (64, 64), (100, n - 100), (n - 1, 1)):
         assert (ctx.unpack(words, bw, first, cnt) == vals[first:first + cnt]).all(), (first, cnt)
+    ctx.set_option("codec_variant", 1)
 
 
 @pytest.mark.parametrize("variant", [0, 1, 2])
@@ -248,6 +251,12 @@ def test_cfg0_roundtrip_16M(ctx, bw):
     words = ctx.pack_dev(vals, bw)
     out = ctx.unpack_dev(words, bw, 0, n)
     assert torch.equal(out, vals)
+    ctx.set_option("codec_variant", 0)  # the direct-load/store kernels must produce the same bytes
+    try:
+        assert torch.equal(ctx.pack_dev(vals, bw), words)
+        assert torch.equal(ctx.unpack_dev(words, bw, 0, n), vals)
+    finally:
+        ctx.set_option("codec_variant", 1)
     # plane image check on a slice: plane i of group g, bit 63-k == bit i of value 64g+k
     k = 64 * 1000
     sl = (vals[:k].to(torch.int64) & 0xFFFFFFFF).view(-1, 64)
