@@ -10,31 +10,47 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfle_b200.so")
-SOURCES = ["fle_api.cu", "fle_eval.cu", "fle_eval1.cu", "fle_codec.cu", "fle_bitmap.cu", "fle_scan.cu"]
+SOURCES = ["fle_api.cu", "fle_eval.cu", "fle_eval1.cu", "fle_eval_in.cu", "fle_codec.cu", "fle_bitmap.cu", "fle_scan.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--threads", "0",
               "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 
 
+OBJ_DIR = os.path.join(CSRC, "_obj")
+HEADERS = ["fle_device.cuh", "fle_internal.h", "fle_eval_common.cuh"]
+
+
 def _sources():
-    return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    return [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
 
-def _stale() -> bool:
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
-        os.path.join(HERE, "..", "include", "fle_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+def _mtime(p):
+    return os.path.getmtime(p) if os.path.exists(p) else 0.0
 
 
 def build_lib(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
-        return LIB
+    """Incremental: one object per .cu (rebuilt when it or a shared header changed), then link."""
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + _sources()
-    print("[fle_b200] " + " ".join(cmd), file=sys.stderr)
-    subprocess.check_call(cmd)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    hdr_time = max([_mtime(os.path.join(CSRC, h)) for h in HEADERS] +
+                   [_mtime(os.path.join(HERE, "..", "include", "fle_b200.h")), _mtime(__file__)])
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+    jobs, objs = [], []
+    for src in _sources():
+        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        objs.append(obj)
+        if force or _mtime(obj) < max(_mtime(os.path.join(CSRC, src)), hdr_time):
+            jobs.append([nvcc] + compile_flags + ["-c", "-o", obj, os.path.join(CSRC, src)])
+
+    def run(cmd):
+        print("[fle_b200] " + " ".join(cmd), file=sys.stderr)
+        subprocess.check_call(cmd)
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 2)) as ex:
+            list(ex.map(run, jobs))
+    if jobs or not os.path.exists(LIB) or any(_mtime(o) > _mtime(LIB) for o in objs):
+        run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", LIB] + objs)
     return LIB
 
 

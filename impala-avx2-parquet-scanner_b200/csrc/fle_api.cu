@@ -331,6 +331,7 @@ int fle_ctx_set_option(fle_ctx* ctx, const char* name, int64_t value) {
   else if (k == "eval_block") ctx->eval_block = (int)value;
   else if (k == "eval_ctas_per_sm") ctx->eval_ctas_per_sm = (int)value;
   else if (k == "eval_gpt") ctx->eval_gpt = (int)value;
+  else if (k == "in_lookup_min") ctx->in_lookup_min = (int)value;
   else if (k == "codec_variant") ctx->codec_variant = (int)value;
   else if (k == "h2d_chunk_rows") ctx->h2d_chunk_rows = value;
   else return set_error(ctx, FLE_E_INVALID, "unknown option " + k);
@@ -345,6 +346,7 @@ int64_t fle_ctx_get_option(fle_ctx* ctx, const char* name) {
   if (k == "eval_block") return ctx->eval_block;
   if (k == "eval_ctas_per_sm") return ctx->eval_ctas_per_sm;
   if (k == "eval_gpt") return ctx->eval_gpt;
+  if (k == "in_lookup_min") return ctx->in_lookup_min;
   if (k == "codec_variant") return ctx->codec_variant;
   if (k == "h2d_chunk_rows") return ctx->h2d_chunk_rows;
   if (k == "num_sms") return ctx->num_sms;

@@ -119,6 +119,11 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ uint64_t lds64(uint32_t addr) {
   uint64_t v;
   asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));

@@ -242,12 +242,6 @@ __global__ void __launch_bounds__(NT) eval_direct_kernel(const __grid_constant__
 #define FLE_PASS_FN __device__ __forceinline__
 #endif
 
-__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
-  return v;
-}
-
 template <int NT>
 __device__ __forceinline__ uint32_t slot_addr(uint32_t slot_base, int gpt, int slot, int q) {
   return slot_base + (uint32_t)((slot * gpt + q) * NT) * 8u;
@@ -740,7 +734,7 @@ namespace {
 inline uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 constexpr int kNT = 256;
-enum LaunchMode { MODE_DIRECT = 0, MODE_STAGED = 1, MODE_SINGLE_PASS = 2 };
+enum LaunchMode { MODE_DIRECT = 0, MODE_STAGED = 1, MODE_SINGLE_PASS = 2, MODE_IN_LOOKUP = 3 };
 
 // cudaOccupancyMaxActiveBlocksPerMultiprocessor / cudaFuncSetAttribute are not free; remember
 // the answers per (kernel, dynamic smem)
@@ -784,6 +778,9 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw) {
   if (mode == MODE_SINGLE_PASS) {
     kern = eval1_kernel_for(P.passes[0].type, P.passes[0].k, (int)P.bw[0]);
     if (!kern) return FLE_E_UNSUPPORTED;
+  } else if (mode == MODE_IN_LOOKUP) {
+    kern = eval_in_kernel_for((int)P.bw[0]);
+    if (!kern) return FLE_E_UNSUPPORTED;
   } else {
     kern = mode == MODE_STAGED ? (const void*)eval_tma_kernel<kNT> : (const void*)eval_direct_kernel<kNT>;
   }
@@ -794,7 +791,7 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw) {
   if (staged) {
     gpt = ctx->eval_gpt;
     const uint32_t bytes_per_gpt = (uint32_t)kNT * sum_bw * 8u;
-    const uint32_t target = mode == MODE_SINGLE_PASS ? 40u * 1024u : 32u * 1024u;
+    const uint32_t target = mode == MODE_STAGED ? 32u * 1024u : 40u * 1024u;
     if (gpt <= 0) gpt = (int)std::max<uint32_t>(1, std::min<uint32_t>(8, (target + bytes_per_gpt / 2) / bytes_per_gpt));
     gpt = std::min(gpt, 8);
   }
@@ -803,11 +800,12 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw) {
   P.smem_bar_off = off;
   off += 8 * 8;  // up to 8 stages
   P.smem_lits_off = off;
-  if (mode != MODE_SINGLE_PASS) off = round_up(off + (uint32_t)P.n_in_lits * 4u, 16);
+  if (mode == MODE_DIRECT || mode == MODE_STAGED) off = round_up(off + (uint32_t)P.n_in_lits * 4u, 16);
   P.smem_masks_off = off;
   if (mode == MODE_STAGED) off += (uint32_t)P.npasses * 512u;
+  if (mode == MODE_IN_LOOKUP) off += std::max(4u, (1u << P.bw[0]) / 8u);  // membership table, 2^bw bits
   P.smem_slots_off = off;
-  if (mode != MODE_SINGLE_PASS) off += (uint32_t)P.nslots * gpt * kNT * 8u;
+  if (mode == MODE_DIRECT || mode == MODE_STAGED) off += (uint32_t)P.nslots * gpt * kNT * 8u;
   off = round_up(off, 128);
   P.smem_stage_off = off;
 
@@ -937,6 +935,19 @@ int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, 
   const PassDesc& p0 = P.passes[0];
   const bool single_pass = P.npasses == 1 && P.ncombs == 0 && (p0.type == PASS_LT || p0.type == PASS_EQ) &&
                            (p0.k == 1 || p0.merge) && p0.slot[0] == 0;
+  // one IN list on one dictionary-coded column: decode + membership lookup (fle_eval_in.cu)
+  const bool in_lookup = P.npasses == 1 && P.ncombs == 0 && p0.type == PASS_IN && p0.slot[0] == 0 &&
+                         P.bw[p0.col] <= 16 && (int)p0.lit[1] >= ctx->in_lookup_min;
+  if (staged_ok && in_lookup) {
+    EvalParams P1 = P;
+    const int c = p0.col;
+    P1.ncols = 1;
+    P1.planes[0] = P.planes[c];
+    P1.bw[0] = P.bw[c];
+    P1.passes[0].col = 0;
+    const int rc = launch_program(ctx, P1, MODE_IN_LOOKUP, (int)P.bw[c]);
+    if (rc != FLE_E_UNSUPPORTED) return rc;
+  }
   if (staged_ok && single_pass && ctx->eval_variant != 2) {
     EvalParams P1 = P;  // only the pass's column is staged
     const int c = p0.col;

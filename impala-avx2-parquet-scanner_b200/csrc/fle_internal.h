@@ -115,6 +115,7 @@ struct fle_ctx {
   int eval_block = 256;
   int eval_ctas_per_sm = 0;  // 0 = auto (occupancy)
   int eval_gpt = 0;          // 0 = auto
+  int in_lookup_min = 12;    // IN lists at least this long use the decode+lookup kernel (bw <= 16)
   int codec_variant = 1;
   int64_t h2d_chunk_rows = 0;  // 0 = auto
 
@@ -160,6 +161,8 @@ int launch_eval(fle_ctx* ctx, const fle_col_desc* cols_dev, int ncols, const fle
                 uint64_t* count_dev);
 // fle_eval1.cu: the single-pass kernel for (PassType, chains, bit width), or nullptr
 const void* eval1_kernel_for(int type, int k, int bw);
+// fle_eval_in.cu: IN list by decode + membership-table lookup (bw <= 16), or nullptr
+const void* eval_in_kernel_for(int bw);
 // out = postfix program over K device bitmaps (leaf.col = bitmap index), word by word
 int launch_bitmap_combine(fle_ctx* ctx, const uint64_t* const* leaf_bitmaps_dev, int nleaf,
                           const fle_pred_node* nodes, int nnodes, int64_t nbits, uint64_t* out_dev,

@@ -339,3 +339,23 @@ def test_select_gather_sum_product(ctx, sel):
         ids2, c3 = ctx.bitmap_select_dev(bm, n, cap=10)
         torch.cuda.synchronize()
         assert int(c3.item()) == k and torch.equal(ids2[:10], want_ids[:10])
+
+
+@pytest.mark.parametrize("bw", list(range(1, 17)) + [20])
+def test_in_list_lookup_kernel_vs_oracle(ctx, oracle, bw):
+    """IN by decode + membership lookup (bw <= 16) must equal the OR-of-equalities of the
+    reference (fle-encoding.h:8236-8313) and the flat plane-algebra kernels, for any list length."""
+    rng = np.random.default_rng(900 + bw)
+    n = 64 * 4096 * 2 + 64 * 11 + 5
+    vals = rng.integers(0, 1 << bw, size=n, dtype=np.uint64).astype(np.uint32)
+    words = oracle.pack(vals, bw)
+    for L in (1, 8, 64, 256, 1000):
+        lits = rng.integers(0, 1 << bw, size=L, dtype=np.uint64)  # duplicates and absent codes included
+        want, wcnt = oracle.pred(IN, words, bw, 0, n, lits)
+        for lookup_min in (1, 1 << 30):
+            ctx.set_option("in_lookup_min", lookup_min)
+            try:
+                bm, cnt = ctx.eval([(words, bw)], [(IN, 0, lits)], n)
+            finally:
+                ctx.set_option("in_lookup_min", 12)
+            assert (bm == want).all() and cnt == wcnt, (bw, L, lookup_min)
