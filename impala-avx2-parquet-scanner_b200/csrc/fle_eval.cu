@@ -962,7 +962,12 @@ int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, 
   // kernel currently beats the generic staged kernel (Q6: 0.85 vs 0.63 of the HBM roofline)
   // because the staged one pays its per-tile pass dispatch once per group at gpt = 1; the
   // staged generic kernel stays selectable with eval_variant = 2.
-  if (staged_ok && ctx->eval_variant == 2) {
+  // Exception: columns whose group size is a multiple of 128 bytes (bw 16, 32) or 64 bytes (24)
+  // make the direct kernel's per-thread strided loads collide in L1 (0.35-0.47 of roofline
+  // measured), so programs touching such a column go the staged way.
+  bool strided_l1_hazard = false;
+  for (int c = 0; c < ncols; ++c) strided_l1_hazard = strided_l1_hazard || (P.bw[c] >= 16 && P.bw[c] % 8 == 0);
+  if (staged_ok && (ctx->eval_variant == 2 || (ctx->eval_variant == 1 && strided_l1_hazard))) {
     const int rc = launch_program(ctx, P, MODE_STAGED, sum_bw);
     if (rc != FLE_E_UNSUPPORTED) return rc;  // tile does not fit in shared memory: direct kernel
   }

@@ -115,7 +115,7 @@ struct fle_ctx {
   int eval_block = 256;
   int eval_ctas_per_sm = 0;  // 0 = auto (occupancy)
   int eval_gpt = 0;          // 0 = auto
-  int in_lookup_min = 12;    // IN lists at least this long use the decode+lookup kernel (bw <= 16)
+  int in_lookup_min = 6;     // IN lists at least this long use the decode+lookup kernel (bw <= 16)
   int codec_variant = 1;
   int64_t h2d_chunk_rows = 0;  // 0 = auto
 
