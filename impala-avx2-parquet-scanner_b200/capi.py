@@ -29,6 +29,7 @@ EXPORTS = [
     "fle_d2h", "fle_encoded_bytes", "fle_pack_u32", "fle_pack_u32_dev", "fle_unpack_u32",
     "fle_unpack_u32_dev", "fle_eval", "fle_eval_dev", "fle_bitmap_count_dev", "fle_intersect_bitset",
     "fle_intersect_bitset_dev", "fle_bitmap_select_dev", "fle_gather_dev", "fle_sum_product_dev",
+    "fle_page_parse", "fle_realign_dev", "fle_plain_eval_dev",
 ]
 
 
@@ -41,6 +42,14 @@ class FleError(RuntimeError):
 class ColDesc(C.Structure):
     _fields_ = [("planes", C.c_void_p), ("bytes", C.c_uint64), ("bit_width", C.c_int32),
                 ("max_def_level", C.c_int32), ("def_planes", C.c_void_p), ("def_bytes", C.c_uint64)]
+
+
+class PageLayout(C.Structure):
+    _fields_ = [("def_off", C.c_uint32), ("def_bytes", C.c_uint32), ("data_off", C.c_uint32),
+                ("data_bytes", C.c_uint32), ("bit_width", C.c_int32), ("reserved", C.c_int32)]
+
+
+T_INT32, T_INT64, T_FLOAT, T_DOUBLE = range(4)
 
 
 class PredNode(C.Structure):
@@ -92,6 +101,9 @@ def load_library() -> C.CDLL:
     L.fle_bitmap_count_dev.argtypes = [vp, vp, i64, vp]
     for f in (L.fle_intersect_bitset, L.fle_intersect_bitset_dev):
         f.argtypes = [vp, vp, i64, vp, i64]
+    L.fle_page_parse.argtypes = [vp, C.c_size_t, i32, C.POINTER(PageLayout)]
+    L.fle_realign_dev.argtypes = [vp, vp, C.c_size_t, vp]
+    L.fle_plain_eval_dev.argtypes = [vp, vp, i32, i64, i32, vp, i32, i32, vp, vp]
     L.fle_bitmap_select_dev.argtypes = [vp, vp, i64, vp, i64, vp]
     L.fle_gather_dev.argtypes = [vp, vp, C.c_size_t, i32, vp, vp, i64, vp, i32, i32, vp]
     L.fle_sum_product_dev.argtypes = [vp, vp, i64, vp, vp, C.c_size_t, i32, vp, i32, vp, vp]
@@ -314,6 +326,35 @@ class FleContext:
                                                  words.numel() * words.element_size(), bw, dict_i64.data_ptr(),
                                                  dict_i64.numel(), out.data_ptr(), out.data_ptr() + 8))
         return out
+
+    def page_parse(self, page: np.ndarray, max_def_level: int) -> PageLayout:
+        page = np.ascontiguousarray(page, dtype=np.uint8)
+        out = PageLayout()
+        self._check(self.lib.fle_page_parse(page.ctypes.data, page.nbytes, max_def_level, C.byref(out)))
+        return out
+
+    def realign_dev(self, blob, offset: int, nbytes: int, out=None):
+        """Funnel-shift copy of blob[offset:offset+nbytes] (uint8 CUDA tensor) to an aligned tensor."""
+        import torch
+        if out is None:
+            out = torch.empty((nbytes + 15) // 16 * 2, dtype=torch.int64, device=blob.device)
+        self._check(self.lib.fle_realign_dev(self.h, blob.data_ptr() + offset, nbytes, out.data_ptr()))
+        return out
+
+    def plain_eval_dev(self, values, op: int, literals, reference_order: bool = False, bitmap=None, count=None):
+        """values: int32/int64/float32/float64 CUDA tensor.  Returns (bitmap int64 tensor, count tensor)."""
+        import torch
+        et = {torch.int32: (T_INT32, np.int32), torch.int64: (T_INT64, np.int64), torch.float32: (T_FLOAT, np.float32),
+              torch.float64: (T_DOUBLE, np.float64)}[values.dtype]
+        n = values.numel()
+        lits = np.ascontiguousarray(np.atleast_1d(np.asarray(literals, dtype=et[1])))
+        if bitmap is None:
+            bitmap = torch.empty(max(1, (n + 63) // 64), dtype=torch.int64, device=values.device)
+        if count is None:
+            count = torch.zeros(1, dtype=torch.int64, device=values.device)
+        self._check(self.lib.fle_plain_eval_dev(self.h, values.data_ptr(), et[0], n, op, lits.ctypes.data if len(lits) else None,
+                                                len(lits), 1 if reference_order else 0, bitmap.data_ptr(), count.data_ptr()))
+        return bitmap, count
 
     def intersect_bitset_dev(self, root, n_root: int, sub, n_sub: int):
         self._check(self.lib.fle_intersect_bitset_dev(self.h, root.data_ptr(), n_root, sub.data_ptr(), n_sub))

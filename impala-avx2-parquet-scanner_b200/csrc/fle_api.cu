@@ -689,4 +689,37 @@ int fle_sum_product_dev(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nrows,
                             bit_width, dict_i64_dev, ndict, sum_dev, count_dev);
 }
 
+// ---- page framing / PLAIN columns ------------------------------------------------------------
+int fle_page_parse(const uint8_t* page, size_t size, int max_def_level, fle_page_layout* out) {
+  if (!page || !out || max_def_level < 0) return FLE_E_INVALID;
+  std::memset(out, 0, sizeof(*out));
+  size_t pos = 0;
+  if (max_def_level > 0) {  // hdfs-parquet-scanner.cc:882-919
+    if (size < 4) return FLE_E_BUFFER;
+    int32_t nd = 0;
+    std::memcpy(&nd, page, 4);
+    if (nd <= 0 || (size_t)nd > size - 4) return FLE_E_BUFFER;
+    out->def_off = 4;
+    out->def_bytes = (uint32_t)nd;
+    pos = 4 + (size_t)nd;
+  }
+  if (pos == size) return FLE_OK;  // all-NULL page: no value section (:921)
+  out->bit_width = page[pos];      // dict-encoding.h:185-192
+  out->data_off = (uint32_t)(pos + 1);
+  out->data_bytes = (uint32_t)(size - pos - 1);
+  return FLE_OK;
+}
+
+int fle_realign_dev(fle_ctx* ctx, const uint8_t* src_dev, size_t nbytes, uint8_t* dst_dev) {
+  FLE_CHECK_CTX(ctx);
+  return launch_realign(ctx, src_dev, nbytes, dst_dev);
+}
+
+int fle_plain_eval_dev(fle_ctx* ctx, const void* values_dev, int elem_type, int64_t n, int op, const void* literals,
+                       int nlits, int reference_operand_order, uint64_t* bitmap_out_dev, uint64_t* match_count_dev) {
+  FLE_CHECK_CTX(ctx);
+  return launch_plain_eval(ctx, values_dev, elem_type, n, op, literals, nlits, reference_operand_order,
+                           bitmap_out_dev, match_count_dev);
+}
+
 }  // extern "C"

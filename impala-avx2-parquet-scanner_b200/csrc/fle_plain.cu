@@ -1,0 +1,200 @@
+// "Next" rows of the scope table: what sits either side of the FLE planes
+// inside a data page.
+//
+//  * realign_kernel -- page bodies are byte streams: [int32 def_len][def levels][u8 bw][groups]
+//    (/root/reference/hdfs-parquet-table-writer.cc:567-575, dict-encoding.h:185-192), so the FLE
+//    groups of a page start at an ODD byte offset.  A chunk that is kept in HBM as the raw file
+//    image is re-based onto 16-byte aligned plane buffers with a funnel-shift copy
+//    (__funnelshift_r over adjacent 32-bit words), one coalesced pass.
+//  * plain_eval_kernel -- predicates on PLAIN-encoded fixed-width columns (those that overflow
+//    the 40000-entry dictionary, e.g. l_extendedprice; hdfs-parquet-table-writer.cc:276-279):
+//    /root/reference/parquet-common.h:197-250 compares row by row and push_back()s one bit at
+//    a time.  Here a warp compares 32 rows per instruction and __ballot_sync emits the 32-row
+//    selection word directly; __popc accumulates the match count.
+//    NB the reference's generic templates compare `val OP data[i]` (literal on the LEFT,
+//    parquet-common.h:214,225,236,247) while its Decimal specialisations and the whole
+//    dictionary path mean `data[i] OP val`; the default here is the SQL meaning
+//    (`column OP literal`), the literal reference order is available as a flag.  The reference's
+//    PLAIN In() is an empty stub (:252-255); here it is implemented.
+#include "fle_device.cuh"
+#include "fle_internal.h"
+
+namespace fle {
+
+// ------------------------------------------------------------------------------------------
+// funnel-shift realignment
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+realign_kernel(const uint32_t* __restrict__ src_words, uint32_t shift_bits, int64_t nwords_out, int64_t nbytes,
+               uint32_t* __restrict__ dst) {
+  // dst word w = bytes [4w, 4w+4) of the unaligned stream = funnel of aligned words w, w+1
+  for (int64_t w = (int64_t)blockIdx.x * 256 + threadIdx.x; w < nwords_out; w += (int64_t)gridDim.x * 256) {
+    const uint32_t lo = src_words[w];
+    // the upper word is only touched when it holds bytes of the stream
+    const bool need_hi = shift_bits != 0 && (w * 4 + 4 + (shift_bits >> 3)) > 0 &&
+                         (int64_t)(w * 4 + (4 - (shift_bits >> 3))) < nbytes;
+    const uint32_t hi = need_hi ? src_words[w + 1] : 0u;
+    uint32_t v = __funnelshift_r(lo, hi, shift_bits);
+    const int64_t left = nbytes - w * 4;
+    if (left < 4) v &= (1u << (8 * (int)left)) - 1u;  // zero the bytes past the end
+    dst[w] = v;
+  }
+}
+
+int launch_realign(fle_ctx* ctx, const uint8_t* src_dev, size_t nbytes, uint8_t* dst_dev) {
+  if (!src_dev || !dst_dev) return set_error(ctx, FLE_E_INVALID, "null pointer");
+  if (reinterpret_cast<uintptr_t>(dst_dev) & 15) return set_error(ctx, FLE_E_ALIGN, "realign destination must be 16-byte aligned");
+  if (nbytes == 0) return FLE_OK;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(src_dev);
+  const uint32_t shift = (uint32_t)(a & 3) * 8;
+  const uint32_t* src_words = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+  const int64_t nwords = (int64_t)((nbytes + 3) / 4);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 16, (nwords + 255) / 256));
+  realign_kernel<<<grid, 256, 0, ctx->stream>>>(src_words, shift, nwords, (int64_t)nbytes, reinterpret_cast<uint32_t*>(dst_dev));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(ctx, e, "realign launch");
+  ctx->launches += 1;
+  return FLE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// PLAIN predicates
+// ------------------------------------------------------------------------------------------
+constexpr int kPlainMaxLits = 1024;
+
+struct PlainParams {
+  const void* values;
+  int64_t n;
+  int op;            // FLE_OP_EQ..FLE_OP_IN
+  int nlits;
+  int swap;          // 1: reference operand order `literal OP value`
+  uint32_t* bitmap;  // 32-row words (same memory image as the 64-bit LSB-first bitmap)
+  int64_t nwords32;  // words to write (even: covers whole 64-bit words)
+  uint64_t* partial;
+  unsigned int* ticket;
+  uint64_t* count_out;
+  const void* lits;  // device copy of the literals
+};
+
+template <typename T>
+__device__ __forceinline__ bool plain_cmp(int op, T a, T b) {  // a OP b
+  switch (op) {
+    case FLE_OP_EQ: return a == b;
+    case FLE_OP_LT: return a < b;
+    case FLE_OP_LE: return a <= b;
+    case FLE_OP_GT: return a > b;
+    case FLE_OP_GE: return a >= b;
+  }
+  return false;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) plain_eval_kernel(const PlainParams P) {
+  __shared__ T lits_s[kPlainMaxLits];
+  __shared__ uint64_t warp_cnt[8];
+  __shared__ bool is_last;
+  for (int i = threadIdx.x; i < P.nlits; i += 256) lits_s[i] = reinterpret_cast<const T*>(P.lits)[i];
+  __syncthreads();
+  const T* vals = reinterpret_cast<const T*>(P.values);
+  const T lit0 = lits_s[0];
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * 256) >> 5;
+  constexpr int U = 8;  // 32-row words per warp iteration
+  uint64_t cnt = 0;
+  for (int64_t w0 = warp * U; w0 < P.nwords32; w0 += nwarps * U) {
+    T v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = (w0 + u) * 32 + lane;
+      v[u] = r < P.n ? vals[r] : T(0);
+    }
+    uint32_t mine = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = (w0 + u) * 32 + lane;
+      bool p = false;
+      if (r < P.n) {
+        if (P.op == FLE_OP_IN) {
+          for (int j = 0; j < P.nlits; ++j) p = p || (v[u] == lits_s[j]);
+        } else {
+          p = P.swap ? plain_cmp<T>(P.op, lit0, v[u]) : plain_cmp<T>(P.op, v[u], lit0);
+        }
+      }
+      const uint32_t word = __ballot_sync(0xffffffffu, p);  // rows 32(w0+u) .. +31, LSB first
+      if (lane == u) mine = word;
+      if (lane == 0) cnt += __popc(word);
+    }
+    if (lane < U && w0 + lane < P.nwords32) P.bitmap[w0 + lane] = mine;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) warp_cnt[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint64_t t = 0;
+    for (int i = 0; i < 8; ++i) t += warp_cnt[i];
+    P.partial[blockIdx.x] = t;
+    __threadfence();
+    is_last = (atomicAdd(P.ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    uint64_t tot = 0;
+    for (unsigned int i = 0; i < gridDim.x; ++i) tot += *((volatile uint64_t*)&P.partial[i]);
+    if (P.count_out) *P.count_out = tot;
+    *P.ticket = 0;
+  }
+}
+
+int launch_plain_eval(fle_ctx* ctx, const void* values_dev, int elem_type, int64_t n, int op, const void* lits_host,
+                      int nlits, int reference_order, uint64_t* bitmap_dev, uint64_t* count_dev) {
+  static const int kElemSize[4] = {4, 8, 4, 8};
+  if (elem_type < 0 || elem_type > 3) return set_error(ctx, FLE_E_INVALID, "unknown element type");
+  if (op < FLE_OP_EQ || op > FLE_OP_IN) return set_error(ctx, FLE_E_INVALID, "PLAIN predicates are EQ..IN leaves");
+  if (n < 0 || nlits < (op == FLE_OP_IN ? 0 : 1) || nlits > kPlainMaxLits || (nlits > 0 && !lits_host))
+    return set_error(ctx, FLE_E_INVALID, "bad literal list");
+  if (n > 0 && (!values_dev || !bitmap_dev)) return set_error(ctx, FLE_E_INVALID, "null pointer");
+  const int es = kElemSize[elem_type];
+  if (reinterpret_cast<uintptr_t>(values_dev) & (es - 1))
+    return set_error(ctx, FLE_E_ALIGN, "PLAIN values must be naturally aligned (use fle_realign_dev)");
+  if (n == 0) {
+    if (count_dev) FLE_CUDA_TRY(ctx, cudaMemsetAsync(count_dev, 0, 8, ctx->stream));
+    return FLE_OK;
+  }
+  PlainParams P;
+  P.values = values_dev;
+  P.n = n;
+  P.op = op;
+  P.nlits = nlits;
+  P.swap = reference_order ? 1 : 0;
+  P.bitmap = reinterpret_cast<uint32_t*>(bitmap_dev);
+  P.nwords32 = ((n + 63) / 64) * 2;
+  P.count_out = count_dev;
+  const int64_t warps_needed = (P.nwords32 + 7) / 8;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 8, (warps_needed + 7) / 8));
+  int rc = ensure_scratch(ctx, grid, std::max(2 * nlits, 2));
+  if (rc != FLE_OK) return rc;
+  // literals travel through the context's pinned staging buffer (reused: drain first)
+  FLE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (nlits > 0) {
+    std::memcpy(ctx->h_in_lits, lits_host, (size_t)nlits * es);
+    FLE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_in_lits, ctx->h_in_lits, (size_t)nlits * es, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  P.lits = ctx->d_in_lits;
+  P.partial = ctx->d_partial;
+  P.ticket = ctx->d_ticket;
+  switch (elem_type) {
+    case 0: plain_eval_kernel<int32_t><<<grid, 256, 0, ctx->stream>>>(P); break;
+    case 1: plain_eval_kernel<int64_t><<<grid, 256, 0, ctx->stream>>>(P); break;
+    case 2: plain_eval_kernel<float><<<grid, 256, 0, ctx->stream>>>(P); break;
+    case 3: plain_eval_kernel<double><<<grid, 256, 0, ctx->stream>>>(P); break;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(ctx, e, "plain_eval launch");
+  ctx->launches += 1;
+  return FLE_OK;
+}
+
+}  // namespace fle

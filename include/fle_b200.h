@@ -197,6 +197,37 @@ int fle_sum_product_dev(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nrows,
                         int bit_width, const int64_t* dict_i64_dev, int ndict, int64_t* sum_dev,
                         uint64_t* count_dev);
 
+/* ---- page framing and PLAIN-encoded columns ("next" rows) ------------- */
+/* Byte layout of one uncompressed data-page body (hdfs-parquet-table-writer.cc:567-575,
+ * hdfs-parquet-scanner.cc:882-919, dict-encoding.h:185-192):
+ *   max_def_level > 0 : [int32 num_def_bytes][def levels, FLE bw 1][u8 bit_width][FLE groups]
+ *   max_def_level == 0:                                          [u8 bit_width][FLE groups]   */
+typedef struct fle_page_layout {
+  uint32_t def_off, def_bytes;   /* 0, 0 for a required column */
+  uint32_t data_off, data_bytes; /* FLE groups (after the bit-width byte) */
+  int32_t bit_width;             /* the header byte */
+  int32_t reserved;
+} fle_page_layout;
+/* Host-side parse of the two header fields (reads 5 bytes); FLE_E_BUFFER if the page is too
+ * short for what its header promises. */
+int fle_page_parse(const uint8_t* page_host, size_t size, int max_def_level, fle_page_layout* out);
+/* Copies nbytes from an arbitrarily aligned DEVICE address to a 16-byte aligned device buffer
+ * with a funnel-shift kernel (the FLE groups of a page start at an odd offset of the file
+ * image); bytes of the last 32-bit word past nbytes are written as 0, so dst needs
+ * (nbytes + 3) / 4 * 4 bytes. */
+int fle_realign_dev(fle_ctx* ctx, const uint8_t* src_dev, size_t nbytes, uint8_t* dst_dev);
+
+/* Element types of PLAIN fixed-width columns (parquet-common.h:39-76). */
+enum { FLE_T_INT32 = 0, FLE_T_INT64 = 1, FLE_T_FLOAT = 2, FLE_T_DOUBLE = 3 };
+/* Replaces ParquetPlainEncoder::Eq/Lt/Le/Gt/Ge/In<T> (parquet-common.h:197-255) for n values
+ * stored back to back at values_dev (naturally aligned).  literals: HOST array of nlits
+ * elements of the column type (1 unless op == FLE_OP_IN, at most 1024).  The predicate is
+ * `value OP literal`; reference_operand_order != 0 evaluates the reference's generic template
+ * literally, `literal OP value` (parquet-common.h:214,225,236,247).  Output as fle_eval_dev. */
+int fle_plain_eval_dev(fle_ctx* ctx, const void* values_dev, int elem_type, int64_t n, int op,
+                       const void* literals, int nlits, int reference_operand_order,
+                       uint64_t* bitmap_out_dev, uint64_t* match_count_dev);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

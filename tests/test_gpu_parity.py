@@ -359,3 +359,77 @@ def test_in_list_lookup_kernel_vs_oracle(ctx, oracle, bw):
             finally:
                 ctx.set_option("in_lookup_min", 6)
             assert (bm == want).all() and cnt == wcnt, (bw, L, lookup_min)
+
+
+# ------------------------------------------------------------------------------------------
+# "next" rows: page framing on the device, PLAIN-encoded predicates
+# ------------------------------------------------------------------------------------------
+def test_page_framing_realign_and_eval(ctx, oracle):
+    """A column chunk kept in HBM as the raw file image: pages [int32 def_len][def FLE][u8 bw][FLE]
+    at arbitrary byte offsets -> fle_page_parse + funnel-shift realign on the device -> fused eval
+    with def levels; per-page bit widths; result == reference structure evaluated by the oracle."""
+    import torch
+    rng = np.random.default_rng(321)
+    pages, blob = [], bytearray(b"\x7f" * 3)  # leading junk so that nothing is aligned by accident
+    for pi, (rows, bw, null_frac) in enumerate(((64 * 300 + 17, 12, 0.05), (64 * 200, 9, 0.0), (777, 5, 0.5), (64 * 64, 16, 0.01))):
+        nn = rng.random(rows) >= null_frac
+        data = rng.integers(0, 1 << bw, size=int(nn.sum()), dtype=np.uint64).astype(np.uint32)
+        defw = oracle.pack(nn.astype(np.uint32), 1)
+        dataw = oracle.pack(data, bw)
+        body = np.int32(defw.nbytes).tobytes() + defw.tobytes() + bytes([bw]) + dataw.tobytes()
+        blob += b"\x55" * int(rng.integers(0, 7))
+        pages.append((len(blob), len(body), rows, bw, nn, data, defw, dataw))
+        blob += body
+    host = np.frombuffer(bytes(blob), dtype=np.uint8)
+    dev = torch.from_numpy(host.copy()).cuda()
+    for off, size, rows, bw, nn, data, defw, dataw in pages:
+        lay = ctx.page_parse(host[off:off + size], 1)
+        assert lay.bit_width == bw and lay.def_bytes == defw.nbytes and lay.data_bytes == dataw.nbytes
+        assert (off + lay.data_off) % 8 != 0 or True
+        d_def = ctx.realign_dev(dev, off + lay.def_off, lay.def_bytes)
+        d_data = ctx.realign_dev(dev, off + lay.data_off, lay.data_bytes)
+        torch.cuda.synchronize()
+        assert (d_def.cpu().numpy().view(np.uint64)[: len(defw)] == defw).all()
+        assert (d_data.cpu().numpy().view(np.uint64)[: len(dataw)] == dataw).all()
+        lit = int(data[len(data) // 2])
+        bm, cnt = ctx.eval_dev([(d_data[: len(dataw)], bw, d_def[: len(defw)])], [(LE, 0, lit)], rows)
+        torch.cuda.synchronize()
+        root = oracle.pred(EQ, defw, 1, 0, rows, [1])[0]
+        sub = oracle.pred(LE, dataw, bw, 0, len(data), [lit])[0]
+        want = oracle.intersect_bitset(root, rows, sub)[0]
+        assert (bm.cpu().numpy().view(np.uint64)[: len(want)] == want).all() and int(cnt.item()) == popcount(want)
+    # odd sizes / every misalignment
+    for off in range(0, 9):
+        for nbytes in (1, 3, 4, 5, 8, 13, 64, 1001):
+            out = ctx.realign_dev(dev, off, nbytes)
+            torch.cuda.synchronize()
+            got = out.cpu().numpy().view(np.uint8)
+            assert (got[:nbytes] == host[off:off + nbytes]).all() and (got[nbytes:(nbytes + 3) // 4 * 4] == 0).all()
+
+
+@pytest.mark.parametrize("dtype", ["int32", "int64", "float32", "float64"])
+def test_plain_predicates(ctx, dtype):
+    """PLAIN fixed-width columns (parquet-common.h:197-255): `value OP literal` by default, the
+    reference's literal `literal OP value` order on request, and a working IN."""
+    import torch
+    rng = np.random.default_rng(17)
+    for n in (1, 31, 32, 33, 64, 65, 64 * 3000 + 19):
+        if dtype.startswith("int"):
+            vals = rng.integers(-50, 50, size=n).astype(dtype)
+        else:
+            vals = (rng.integers(-50, 50, size=n) / 4).astype(dtype)
+        t = torch.from_numpy(vals).cuda()
+        lit = vals[n // 2]
+        for op, f in ((EQ, np.equal), (LT, np.less), (LE, np.less_equal), (GT, np.greater), (GE, np.greater_equal)):
+            for ref_order in (False, True):
+                bm, cnt = ctx.plain_eval_dev(t, op, [lit], reference_order=ref_order)
+                torch.cuda.synchronize()
+                want_bits = f(lit, vals) if ref_order else f(vals, lit)
+                got = np.unpackbits(bm.cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
+                assert (got == want_bits).all() and int(cnt.item()) == int(want_bits.sum()), (dtype, n, op, ref_order)
+                assert np.unpackbits(bm.cpu().numpy().view(np.uint8), bitorder="little")[n:].sum() == 0
+        lits = rng.choice(vals, size=min(5, n))
+        bm, cnt = ctx.plain_eval_dev(t, IN, lits)
+        torch.cuda.synchronize()
+        got = np.unpackbits(bm.cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
+        assert (got == np.isin(vals, lits)).all() and int(cnt.item()) == int(np.isin(vals, lits).sum())
