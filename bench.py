@@ -31,6 +31,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; stdout carries exactly one JSON line
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 import numpy as np  # noqa: E402
 
