@@ -400,17 +400,6 @@ FLE_PASS_FN void in_tile(const uint32_t* lits, int cnt, uint32_t col_addr, uint3
   X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) \
   X(17) X(18) X(19) X(20) X(21) X(22) X(23) X(24) X(25) X(26) X(27) X(28) X(29) X(30) X(31) X(32)
 
-template <int NT, bool IS_LT, int K>
-__device__ __forceinline__ void dispatch_pass(int bw, uint32_t mask_addr, uint32_t col_addr, uint32_t slot_base,
-                                              int gpt, uint32_t slots4, uint32_t folds4, uint32_t negs4,
-                                              uint32_t inits4, uint32_t merge) {
-  switch (bw) {
-#define X(B) case B: pass_tile<NT, IS_LT, K, B>(mask_addr, col_addr, slot_base, gpt, slots4, folds4, negs4, inits4, merge); break;
-    FLE_BW_CASES(X)
-#undef X
-  }
-}
-
 template <int NT>
 __device__ __forceinline__ void dispatch_in(int bw, const uint32_t* lits, int cnt, uint32_t col_addr,
                                             uint32_t slot_base, int gpt, int tmp_slot, int dst_slot, int fold,
@@ -420,10 +409,6 @@ __device__ __forceinline__ void dispatch_in(int bw, const uint32_t* lits, int cn
     FLE_BW_CASES(X)
 #undef X
   }
-}
-
-__device__ __forceinline__ uint32_t pack4(const uint8_t (&b)[4]) {
-  return (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
 }
 
 template <int NT>
@@ -482,33 +467,31 @@ __global__ void __launch_bounds__(NT, 768 / NT) eval_tma_kernel(const __grid_con
     mbar_wait(bar0 + stage * 8, parity);
     const uint32_t sbase = stage0 + stage * P.stage_bytes;
 
-    // 1. passes (warp-uniform control flow, specialised bodies)
+    // 1. passes (warp-uniform control flow): one jump through a flat table of specialised bodies;
+    //    the pass record is read as nine 32-bit words straight from the constant bank
     for (int p = 0; p < P.npasses; ++p) {
-      const PassDesc& pd = P.passes[p];
-      const int type = pd.type;
-      if (type == PASS_CONST) {
-        const uint64_t v = pd.init[0] ? ~0ull : 0ull;
-        for (int q = 0; q < gpt; ++q) fold_smem(slot_addr<NT>(slot_base, gpt, pd.slot[0], q), pd.fold[0], v);
-        continue;
-      }
-      const int col = pd.col;
-      const int bw = (int)P.bw[col];
-      const uint32_t col_addr = sbase + P.col_off[col] + seg * P.seg_stride[col] + jrow * (uint32_t)bw * 8u;
-      if (type == PASS_IN) {
-        dispatch_in<NT>(bw, lits_smem + pd.lit[0], (int)pd.lit[1], col_addr, slot_base, gpt, P.in_tmp_slot,
-                        pd.slot[0], pd.fold[0], pd.neg[0] ? ~0u : 0u);
-        continue;
-      }
+      const uint32_t* pw = reinterpret_cast<const uint32_t*>(&P.passes[p]);
+      const uint32_t w0 = pw[0], slots4 = pw[1], folds4 = pw[2], negs4 = pw[3], inits4 = pw[4];
+      const uint32_t dispatch = pw[9];
+      const uint32_t col = (w0 >> 8) & 0xffu, merge = w0 >> 24;
+      const uint32_t col_addr = sbase + P.col_off[col] + seg * P.seg_stride[col] + jrow * (P.bw[col] * 8u);
       const uint32_t mask_addr = masks0 + (uint32_t)p * 512u;
-      const uint32_t slots4 = pack4(pd.slot), folds4 = pack4(pd.fold), negs4 = pack4(pd.neg), inits4 = pack4(pd.init);
-      const uint32_t merge = pd.merge;
-      if (type == PASS_LT) {
-        if (pd.k == 1) dispatch_pass<NT, true, 1>(bw, mask_addr, col_addr, slot_base, gpt, slots4, folds4, negs4, inits4, merge);
-        else if (pd.k == 2) dispatch_pass<NT, true, 2>(bw, mask_addr, col_addr, slot_base, gpt, slots4, folds4, negs4, inits4, merge);
-        else dispatch_pass<NT, true, 4>(bw, mask_addr, col_addr, slot_base, gpt, slots4, folds4, negs4, inits4, merge);
-      } else {
-        if (pd.k == 1) dispatch_pass<NT, false, 1>(bw, mask_addr, col_addr, slot_base, gpt, slots4, folds4, negs4, inits4, merge);
-        else dispatch_pass<NT, false, 4>(bw, mask_addr, col_addr, slot_base, gpt, slots4, folds4, negs4, inits4, merge);
+      switch (dispatch) {
+#define FLE_BODY(IDX, IS_LT, K, B) \
+        case (IDX) * 32 + (B) - 1: pass_tile<NT, IS_LT, K, B>(mask_addr, col_addr, slot_base, gpt, slots4, folds4, negs4, inits4, merge); break;
+#define X(B) FLE_BODY(0, true, 1, B) FLE_BODY(1, true, 2, B) FLE_BODY(2, true, 4, B) FLE_BODY(3, false, 1, B) FLE_BODY(4, false, 4, B)
+        FLE_BW_CASES(X)
+#undef X
+#undef FLE_BODY
+        case kDispatchIn:
+          dispatch_in<NT>((int)P.bw[col], lits_smem + pw[5], (int)pw[6], col_addr, slot_base, gpt, P.in_tmp_slot,
+                          (int)(slots4 & 0xffu), (int)(folds4 & 0xffu), (negs4 & 1u) ? ~0u : 0u);
+          break;
+        default: {  // kDispatchConst
+          const uint64_t v = (inits4 & 1u) ? ~0ull : 0ull;
+          for (int q = 0; q < gpt; ++q) fold_smem(slot_addr<NT>(slot_base, gpt, (int)(slots4 & 0xffu), q), (int)(folds4 & 0xffu), v);
+          break;
+        }
       }
     }
 
@@ -717,6 +700,12 @@ int lower_program(const fle_col_desc* cols, int ncols, const fle_pred_node* node
     //  first pass and padding repeats the LAST chain of a pass with k >= 2; in mixed trees every
     //  chain SETs its own slot)
     pd.k = (uint8_t)want;
+    const int kind_k = c0.type == PASS_LT ? (want == 1 ? 0 : want == 2 ? 1 : 2) : (want == 1 ? 3 : 4);
+    pd.dispatch = (uint32_t)(kind_k * 32 + cols[c0.col].bit_width - 1);
+  }
+  for (int q = 0; q < P.npasses; ++q) {
+    if (P.passes[q].type == PASS_IN) P.passes[q].dispatch = kDispatchIn;
+    if (P.passes[q].type == PASS_CONST) P.passes[q].dispatch = kDispatchConst;
   }
   P.in_tmp_slot = -1;
   if (any_in) {

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstddef>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -48,7 +49,12 @@ struct PassDesc {
   uint8_t neg[4];   // 1: complement the chain result before folding
   uint8_t init[4];  // PASS_LT: chain init (0 => '<', 1 => '<='); PASS_CONST: the constant
   uint32_t lit[4];  // literal per chain (masked to bw bits); PASS_IN: lit[0]=offset, lit[1]=count
+  uint32_t dispatch;  // staged kernel: body index = kindK * 32 + (bw - 1), kindK: LT K1/K2/K4 = 0/1/2,
+                      // EQ K1/K4 = 3/4; kDispatchIn / kDispatchConst for the other pass types
 };
+constexpr uint32_t kDispatchIn = 200, kDispatchConst = 201;
+static_assert(sizeof(PassDesc) == 40 && offsetof(PassDesc, lit) == 20 && offsetof(PassDesc, dispatch) == 36,
+              "the staged kernel reads PassDesc as 32-bit words");
 
 struct CombDesc {
   uint8_t op;  // FOLD_AND / FOLD_OR

@@ -161,7 +161,7 @@ def sweep_programs(ctx, out, n):
         prog = [tuple(p) + (None,) * (3 - len(p)) for p in prog]
         prep = (ctx.make_col_descs(pc),) + fle_b200.capi._build_program(prog)
         sum_bw = sum(bw for _, bw in pc)
-        for var in (1, 0):
+        for var in (1, 2, 0):
             ctx.set_option("eval_variant", var)
             mn, md = timeit(lambda: ctx.eval_dev(pc, prog, n, bitmap=bm, count=cnt, prepared=prep), reps=5 if "in256" in name else 10)
             rec(out, what="program", name=name, variant=var, rows=n, sum_bw=sum_bw, ms_min=mn, ms_med=md,
