@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfle_b200.so")
-SOURCES = ["fle_api.cu", "fle_eval.cu", "fle_eval1.cu", "fle_eval_in.cu", "fle_codec.cu", "fle_bitmap.cu", "fle_scan.cu", "fle_plain.cu"]
+SOURCES = ["fle_api.cu", "fle_eval.cu", "fle_eval1.cu", "fle_eval_in.cu", "fle_codec.cu", "fle_bitmap.cu", "fle_scan.cu", "fle_plain.cu", "fle_dict.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--threads", "0",
               "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

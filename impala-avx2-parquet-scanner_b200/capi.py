@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(_HERE, "libfle_b200.so")
 
 # opcodes (fle_b200.h)
 EQ, LT, LE, GT, GE, IN, AND, OR, ALL, NONE = range(10)
-OK, E_INVALID, E_NOMEM, E_CUDA, E_BUFFER, E_ALIGN, E_UNSUPPORTED, E_NODEVICE = 0, -1, -2, -3, -4, -5, -6, -7
+OK, E_INVALID, E_NOMEM, E_CUDA, E_BUFFER, E_ALIGN, E_UNSUPPORTED, E_NODEVICE, E_DICT_FULL = 0, -1, -2, -3, -4, -5, -6, -7, -8
 
 EXPORTS = [
     "fle_ctx_create", "fle_ctx_destroy", "fle_ctx_set_stream", "fle_ctx_sync", "fle_ctx_set_option",
@@ -29,7 +29,7 @@ EXPORTS = [
     "fle_d2h", "fle_encoded_bytes", "fle_pack_u32", "fle_pack_u32_dev", "fle_unpack_u32",
     "fle_unpack_u32_dev", "fle_eval", "fle_eval_dev", "fle_bitmap_count_dev", "fle_intersect_bitset",
     "fle_intersect_bitset_dev", "fle_bitmap_select_dev", "fle_gather_dev", "fle_sum_product_dev",
-    "fle_page_parse", "fle_realign_dev", "fle_plain_eval_dev",
+    "fle_page_parse", "fle_realign_dev", "fle_plain_eval_dev", "fle_dict_encode_dev",
 ]
 
 
@@ -101,6 +101,8 @@ def load_library() -> C.CDLL:
     L.fle_bitmap_count_dev.argtypes = [vp, vp, i64, vp]
     for f in (L.fle_intersect_bitset, L.fle_intersect_bitset_dev):
         f.argtypes = [vp, vp, i64, vp, i64]
+    L.fle_dict_encode_dev.argtypes = [vp, vp, i32, i64, i32, vp, C.POINTER(C.c_int), C.POINTER(C.c_int), vp, C.c_size_t,
+                                      C.POINTER(C.c_size_t)]
     L.fle_page_parse.argtypes = [vp, C.c_size_t, i32, C.POINTER(PageLayout)]
     L.fle_realign_dev.argtypes = [vp, vp, C.c_size_t, vp]
     L.fle_plain_eval_dev.argtypes = [vp, vp, i32, i64, i32, vp, i32, i32, vp, vp]
@@ -355,6 +357,19 @@ class FleContext:
         self._check(self.lib.fle_plain_eval_dev(self.h, values.data_ptr(), et[0], n, op, lits.ctypes.data if len(lits) else None,
                                                 len(lits), 1 if reference_order else 0, bitmap.data_ptr(), count.data_ptr()))
         return bitmap, count
+
+    def dict_encode_dev(self, values, max_entries: int = 40000):
+        """values: int32/int64 CUDA tensor.  Returns (sorted dictionary int64 tensor[nd], bit_width,
+        plane words int64 tensor).  Raises FleError(E_DICT_FULL) like DictEncoder::Put() == -1."""
+        import torch
+        et = T_INT32 if values.dtype == torch.int32 else T_INT64
+        n = values.numel()
+        d = torch.empty(max_entries, dtype=torch.int64, device=values.device)
+        enc = torch.empty(max(1, self.encoded_bytes(n, 16) // 8), dtype=torch.int64, device=values.device)
+        nd, bw, ln = C.c_int(0), C.c_int(0), C.c_size_t(0)
+        self._check(self.lib.fle_dict_encode_dev(self.h, values.data_ptr(), et, n, max_entries, d.data_ptr(), C.byref(nd),
+                                                 C.byref(bw), enc.data_ptr(), enc.numel() * 8, C.byref(ln)))
+        return d[: nd.value], bw.value, enc[: ln.value // 8]
 
     def intersect_bitset_dev(self, root, n_root: int, sub, n_sub: int):
         self._check(self.lib.fle_intersect_bitset_dev(self.h, root.data_ptr(), n_root, sub.data_ptr(), n_sub))

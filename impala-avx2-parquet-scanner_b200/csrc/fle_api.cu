@@ -219,6 +219,7 @@ const char* fle_strerror(int code) {
     case FLE_E_ALIGN: return "misaligned pointer or row offset";
     case FLE_E_UNSUPPORTED: return "unsupported request";
     case FLE_E_NODEVICE: return "no CUDA device (this library has no CPU path)";
+    case FLE_E_DICT_FULL: return "dictionary full";
   }
   return "unknown error";
 }
@@ -720,6 +721,14 @@ int fle_plain_eval_dev(fle_ctx* ctx, const void* values_dev, int elem_type, int6
   FLE_CHECK_CTX(ctx);
   return launch_plain_eval(ctx, values_dev, elem_type, n, op, literals, nlits, reference_operand_order,
                            bitmap_out_dev, match_count_dev);
+}
+
+int fle_dict_encode_dev(fle_ctx* ctx, const void* values_dev, int elem_type, int64_t n, int max_entries,
+                        int64_t* dict_out_dev, int* num_entries, int* bit_width, uint8_t* enc_dev, size_t enc_cap,
+                        size_t* enc_len) {
+  FLE_CHECK_CTX(ctx);
+  return launch_dict_encode(ctx, values_dev, elem_type, n, max_entries, dict_out_dev, num_entries, bit_width, enc_dev,
+                            enc_cap, enc_len);
 }
 
 }  // extern "C"

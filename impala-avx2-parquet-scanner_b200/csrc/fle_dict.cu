@@ -1,0 +1,195 @@
+// Dictionary build + encode of a whole column chunk on the device.
+//
+// Replaces, for fixed-width integer columns already resident in HBM,
+//   DictEncoder<T>::Put x n          /root/reference/dict-encoding.h:234-274  (hash table, <= 40000 entries)
+//   DictEncoder<T>::WriteDict        :393-406  (SORTS the dictionary, builds to_sorted_indice_)
+//   DictEncoderBase::WriteData       :408-447  (remap indices, [bit width] + FLE groups)
+// so that dictionary codes are order-preserving, which is what lets the scanner translate
+// `col < literal` into `code < lower_bound(literal)` (dict-encoding.h:485-496).
+//   1. insert   : open-addressing hash table (2^17 slots, linear probing, 64-bit atomicCAS);
+//                 more than max_entries distinct values => FLE_E_DICT_FULL, the caller keeps the
+//                 column PLAIN exactly like the writer does when Put() returns -1
+//                 (hdfs-parquet-table-writer.cc:276-279)
+//   2. compact  : occupied slots -> (key, slot) list
+//   3. rank     : rank_i = #{j : key_j < key_i} by tiled all-pairs counting (<= 40000^2 compares,
+//                 exact because the keys are distinct) -> sorted dictionary + slot -> code map
+//   4. encode   : value -> slot (probe) -> code (u32)
+//   5. pack     : pack_kernel<bw> with bw = DictEncoderBase::bit_width() (dict-encoding.h:76-80)
+#include "fle_device.cuh"
+#include "fle_internal.h"
+
+namespace fle {
+
+constexpr int kDictSlots = 1 << 17;
+constexpr unsigned long long kEmptyKey = 0x8000000000000000ull;  // INT64_MIN is handled out of band
+
+__device__ __forceinline__ uint32_t dict_hash(unsigned long long k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return (uint32_t)k & (kDictSlots - 1);
+}
+
+template <typename T>
+__device__ __forceinline__ unsigned long long widen(T v) { return (unsigned long long)(long long)v; }
+
+struct DictState {
+  unsigned int count;     // distinct keys inserted (without INT64_MIN)
+  unsigned int overflow;  // set when count would exceed max_entries
+  unsigned int has_min;   // INT64_MIN occurs in the column
+  unsigned int nlist;     // compaction cursor
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+dict_insert_kernel(const T* __restrict__ vals, int64_t n, unsigned long long* __restrict__ keys, DictState* st,
+                   unsigned int max_entries) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    if (*((volatile unsigned int*)&st->overflow)) return;
+    const unsigned long long k = widen(vals[i]);
+    if (k == kEmptyKey) { st->has_min = 1; continue; }
+    uint32_t h = dict_hash(k);
+    for (int probe = 0; probe < kDictSlots; ++probe) {
+      const unsigned long long cur = keys[h];
+      if (cur == k) break;
+      if (cur == kEmptyKey) {
+        const unsigned long long old = atomicCAS(&keys[h], kEmptyKey, k);
+        if (old == kEmptyKey) {
+          if (atomicAdd(&st->count, 1u) + 1u > max_entries) st->overflow = 1;
+          break;
+        }
+        if (old == k) break;
+      }
+      h = (h + 1) & (kDictSlots - 1);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+dict_compact_kernel(const unsigned long long* __restrict__ keys, DictState* st, long long* __restrict__ list_keys,
+                    uint32_t* __restrict__ list_slots) {
+  const int s = blockIdx.x * 256 + threadIdx.x;
+  if (s == 0 && st->has_min) {  // INT64_MIN: pseudo slot kDictSlots
+    const unsigned int p = atomicAdd(&st->nlist, 1u);
+    list_keys[p] = (long long)kEmptyKey;
+    list_slots[p] = kDictSlots;
+  }
+  if (s < kDictSlots && keys[s] != kEmptyKey) {
+    const unsigned int p = atomicAdd(&st->nlist, 1u);
+    list_keys[p] = (long long)keys[s];
+    list_slots[p] = (uint32_t)s;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+dict_rank_kernel(const long long* __restrict__ list_keys, const uint32_t* __restrict__ list_slots, int nd,
+                 long long* __restrict__ dict_sorted, uint32_t* __restrict__ slot_to_code) {
+  __shared__ long long tile[1024];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const long long mine = i < nd ? list_keys[i] : 0;
+  uint32_t rank = 0;
+  for (int base = 0; base < nd; base += 1024) {
+    __syncthreads();
+    for (int j = threadIdx.x; j < 1024; j += 256) tile[j] = base + j < nd ? list_keys[base + j] : 0x7fffffffffffffffll;
+    __syncthreads();
+    const int m = min(1024, nd - base);
+#pragma unroll 8
+    for (int j = 0; j < m; ++j) rank += tile[j] < mine;
+  }
+  if (i < nd) {
+    dict_sorted[rank] = mine;
+    slot_to_code[list_slots[i]] = rank;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+dict_encode_kernel(const T* __restrict__ vals, int64_t n, const unsigned long long* __restrict__ keys,
+                   const uint32_t* __restrict__ slot_to_code, uint32_t* __restrict__ codes) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const unsigned long long k = widen(vals[i]);
+    uint32_t h = kDictSlots;
+    if (k != kEmptyKey) {
+      h = dict_hash(k);
+      while (keys[h] != k) h = (h + 1) & (kDictSlots - 1);
+    }
+    codes[i] = slot_to_code[h];
+  }
+}
+
+int launch_dict_encode(fle_ctx* ctx, const void* values_dev, int elem_type, int64_t n, int max_entries,
+                       int64_t* dict_out_dev, int* num_entries, int* bit_width, uint8_t* enc_dev, size_t enc_cap,
+                       size_t* enc_len) {
+  if (elem_type != FLE_T_INT32 && elem_type != FLE_T_INT64) return set_error(ctx, FLE_E_UNSUPPORTED, "dictionary build handles INT32/INT64 columns");
+  if (n < 0 || (n > 0 && !values_dev) || !dict_out_dev || !num_entries || !bit_width || !enc_dev || max_entries < 1 ||
+      max_entries > 40000)
+    return set_error(ctx, FLE_E_INVALID, "bad dict_encode arguments");
+  const int es = elem_type == FLE_T_INT32 ? 4 : 8;
+  if ((reinterpret_cast<uintptr_t>(values_dev) & (es - 1)) || (reinterpret_cast<uintptr_t>(enc_dev) & 15))
+    return set_error(ctx, FLE_E_ALIGN, "values must be naturally aligned, enc_dev 16-byte aligned");
+  cudaStream_t st = ctx->stream;
+  unsigned long long* keys = nullptr;
+  DictState* state = nullptr;
+  long long* list_keys = nullptr;
+  uint32_t *list_slots = nullptr, *slot_to_code = nullptr, *codes = nullptr;
+  auto cleanup = [&]() {
+    cudaFreeAsync(keys, st); cudaFreeAsync(state, st); cudaFreeAsync(list_keys, st);
+    cudaFreeAsync(list_slots, st); cudaFreeAsync(slot_to_code, st); cudaFreeAsync(codes, st);
+  };
+#define DICT_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return set_cuda_error(ctx, _e, #expr); } } while (0)
+  DICT_TRY(cudaMallocAsync(&keys, (size_t)kDictSlots * 8, st));
+  DICT_TRY(cudaMallocAsync(&state, sizeof(DictState), st));
+  DICT_TRY(cudaMallocAsync(&list_keys, (size_t)(max_entries + 2) * 8, st));
+  DICT_TRY(cudaMallocAsync(&list_slots, (size_t)(max_entries + 2) * 4, st));
+  DICT_TRY(cudaMallocAsync(&slot_to_code, (size_t)(kDictSlots + 1) * 4, st));
+  DICT_TRY(cudaMallocAsync(&codes, (size_t)std::max<int64_t>(n, 1) * 4, st));
+  // every byte 0x80 would not be kEmptyKey: fill the table with a tiny kernel-free pattern copy
+  {
+    std::vector<unsigned long long> init(4096, kEmptyKey);
+    for (int off = 0; off < kDictSlots; off += 4096)
+      DICT_TRY(cudaMemcpyAsync(keys + off, init.data(), 4096 * 8, cudaMemcpyHostToDevice, st));
+    DICT_TRY(cudaStreamSynchronize(st));  // `init` is pageable stack-lifetime memory
+  }
+  DICT_TRY(cudaMemsetAsync(state, 0, sizeof(DictState), st));
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 8, (n + 255) / 256));
+  if (n > 0) {
+    if (es == 4) dict_insert_kernel<int32_t><<<grid, 256, 0, st>>>((const int32_t*)values_dev, n, keys, state, (unsigned)max_entries);
+    else dict_insert_kernel<int64_t><<<grid, 256, 0, st>>>((const int64_t*)values_dev, n, keys, state, (unsigned)max_entries);
+  }
+  DictState h;
+  DICT_TRY(cudaMemcpyAsync(&h, state, sizeof(h), cudaMemcpyDeviceToHost, st));
+  DICT_TRY(cudaStreamSynchronize(st));
+  ctx->launches += n > 0 ? 1 : 0;
+  const int nd = (int)h.count + (h.has_min ? 1 : 0);
+  if (h.overflow || nd > max_entries) {
+    cleanup();
+    *num_entries = nd;
+    return set_error(ctx, FLE_E_DICT_FULL, "more distinct values than dictionary entries: keep the column PLAIN");
+  }
+  *num_entries = nd;
+  int bw = 0;  // DictEncoderBase::bit_width(), dict-encoding.h:76-80
+  if (nd == 1) bw = 1;
+  else if (nd > 1) { bw = 1; unsigned x = (unsigned)nd - 1; while (x >>= 1) ++bw; }
+  *bit_width = bw;
+  const size_t need = bw == 0 ? 0 : fle_encoded_bytes(n, bw);
+  if (enc_len) *enc_len = need;
+  if (enc_cap < need) { cleanup(); return set_error(ctx, FLE_E_BUFFER, "encode buffer too small"); }
+  if (nd > 0) {
+    dict_compact_kernel<<<kDictSlots / 256, 256, 0, st>>>(keys, state, list_keys, list_slots);
+    dict_rank_kernel<<<(nd + 255) / 256, 256, 0, st>>>(list_keys, list_slots, nd, (long long*)dict_out_dev, slot_to_code);
+    if (es == 4) dict_encode_kernel<int32_t><<<grid, 256, 0, st>>>((const int32_t*)values_dev, n, keys, slot_to_code, codes);
+    else dict_encode_kernel<int64_t><<<grid, 256, 0, st>>>((const int64_t*)values_dev, n, keys, slot_to_code, codes);
+    ctx->launches += 3;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { cleanup(); return set_cuda_error(ctx, e, "dict kernels"); }
+    const int rc = launch_pack_u32(ctx, codes, n, bw, reinterpret_cast<uint64_t*>(enc_dev));
+    if (rc != FLE_OK) { cleanup(); return rc; }
+  }
+  cleanup();
+#undef DICT_TRY
+  return FLE_OK;
+}
+
+}  // namespace fle

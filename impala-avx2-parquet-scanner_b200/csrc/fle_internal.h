@@ -183,6 +183,10 @@ int launch_intersect(fle_ctx* ctx, uint64_t* root_dev, int64_t n_root, const uin
 int launch_realign(fle_ctx* ctx, const uint8_t* src_dev, size_t nbytes, uint8_t* dst_dev);
 int launch_plain_eval(fle_ctx* ctx, const void* values_dev, int elem_type, int64_t n, int op, const void* lits_host,
                       int nlits, int reference_order, uint64_t* bitmap_dev, uint64_t* count_dev);
+// fle_dict.cu
+int launch_dict_encode(fle_ctx* ctx, const void* values_dev, int elem_type, int64_t n, int max_entries,
+                       int64_t* dict_out_dev, int* num_entries, int* bit_width, uint8_t* enc_dev, size_t enc_cap,
+                       size_t* enc_len);
 // fle_scan.cu
 int launch_select(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nbits, uint32_t* ids_dev, int64_t cap,
                   uint64_t* count_dev);

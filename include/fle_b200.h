@@ -47,7 +47,8 @@ enum {
   FLE_E_BUFFER = -4,      /* output buffer too small / input shorter than the rows asked for */
   FLE_E_ALIGN = -5,       /* pointer or row offset not aligned as documented */
   FLE_E_UNSUPPORTED = -6, /* valid request this build cannot run (e.g. > FLE_MAX_COLS columns) */
-  FLE_E_NODEVICE = -7     /* no CUDA device: the product has no CPU path */
+  FLE_E_NODEVICE = -7,    /* no CUDA device: the product has no CPU path */
+  FLE_E_DICT_FULL = -8    /* more distinct values than dictionary entries (DictEncoder::Put == -1) */
 };
 
 /* Predicate opcodes.  EQ..IN are leaves = FleDecoder::Eq/Lt/Le/Gt/Ge/In
@@ -227,6 +228,19 @@ enum { FLE_T_INT32 = 0, FLE_T_INT64 = 1, FLE_T_FLOAT = 2, FLE_T_DOUBLE = 3 };
 int fle_plain_eval_dev(fle_ctx* ctx, const void* values_dev, int elem_type, int64_t n, int op,
                        const void* literals, int nlits, int reference_operand_order,
                        uint64_t* bitmap_out_dev, uint64_t* match_count_dev);
+
+/* ---- dictionary build on the device ("next" row) ----------------------------- */
+/* Replaces DictEncoder<T>::Put x n + WriteDict + WriteData (dict-encoding.h:234-274, 393-447)
+ * for a whole INT32/INT64 column chunk resident on the device: deduplicates the values, SORTS
+ * the dictionary (order-preserving codes), remaps and FLE-packs the codes with
+ * bit_width = DictEncoderBase::bit_width() (dict-encoding.h:76-80).
+ * dict_out_dev: room for max_entries int64 values (INT32 columns are widened);
+ * *num_entries / *bit_width / *enc_len are HOST outputs (the call synchronises).
+ * FLE_E_DICT_FULL when the column has more than max_entries (<= 40000, dict-encoding.h:157)
+ * distinct values -- the writer then falls back to PLAIN (hdfs-parquet-table-writer.cc:276-279). */
+int fle_dict_encode_dev(fle_ctx* ctx, const void* values_dev, int elem_type, int64_t n,
+                        int max_entries, int64_t* dict_out_dev, int* num_entries, int* bit_width,
+                        uint8_t* enc_dev, size_t enc_cap, size_t* enc_len);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -433,3 +433,31 @@ def test_plain_predicates(ctx, dtype):
         torch.cuda.synchronize()
         got = np.unpackbits(bm.cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
         assert (got == np.isin(vals, lits)).all() and int(cnt.item()) == int(np.isin(vals, lits).sum())
+
+
+def test_dict_build_on_device(ctx, oracle):
+    """DictEncoder::Put + WriteDict (sorted) + WriteData on the device (SURVEY 8f-4): the dictionary
+    is the sorted set of values, codes are order-preserving, the planes equal the oracle's packing
+    of those codes; an over-full dictionary reports FLE_E_DICT_FULL (Put() == -1)."""
+    import torch
+    import fle_b200
+    rng = np.random.default_rng(8)
+    for dtype, nd, n in ((np.int64, 2526, 64 * 4000 + 7), (np.int32, 11, 1000), (np.int64, 1, 130), (np.int64, 40000, 400000),
+                         (np.int32, 3, 64)):
+        domain = np.unique(rng.integers(-10**9, 10**9, size=nd * 2).astype(dtype))[:nd]
+        if dtype == np.int64 and nd > 5:
+            domain[0] = np.iinfo(np.int64).min  # the hash table's sentinel value must work as data
+            domain.sort()
+        vals = rng.choice(domain, size=n)
+        vals[: len(domain)] = domain  # every entry occurs
+        d, bw, enc = ctx.dict_encode_dev(torch.from_numpy(vals).cuda())
+        torch.cuda.synchronize()
+        want_dict = np.unique(vals)
+        assert (d.cpu().numpy() == want_dict.astype(np.int64)).all()
+        assert bw == oracle.dict_bit_width(len(want_dict))
+        codes = np.searchsorted(want_dict, vals).astype(np.uint32)
+        assert (enc.cpu().numpy().view(np.uint64) == oracle.pack(codes, bw)).all()
+    big = torch.arange(0, 50000, device="cuda", dtype=torch.int64)
+    with pytest.raises(fle_b200.FleError) as ei:
+        ctx.dict_encode_dev(big)
+    assert ei.value.code == fle_b200.capi.E_DICT_FULL
