@@ -226,188 +226,98 @@ __global__ void __launch_bounds__(NT) eval_direct_kernel(const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------
-// Kernel 1: TMA-staged persistent pipeline
+// Kernel 1: TMA-staged persistent pipeline for generic programs
 //
-// The staged path does not interpret the program per group.  For every tile it walks the pass
-// list ONCE (warp-uniform), and each pass runs a body specialised at compile time on
-// <kind, K chains, bit width>: planes come from shared memory with 64/128-bit loads, the
-// per-plane literal masks sit in registers (loaded once per tile and pass), the plane loop is
-// fully unrolled, and the body loops over the thread's `gpt` groups.  Per group that leaves
-// BW/2 LDS + 2*K*BW LOP3 + a slot update, close to the minimum the plane algebra needs.
-// Pass results are folded into per-thread slots in shared memory ([slot][q][thread]); a short
-// epilogue per group applies the combine ops, reverses the word into row order, stores it and
-// counts it.
+// Tiles of T = 256 * gpt groups are staged by TMA exactly as in fle_eval1.cu.  A thread then
+// evaluates its group pass by pass with small bodies templated on <kind, K chains> only: the
+// bit width is a run-time loop over plane QUADS -- two LDS.128 fetch four planes, one LDS.128
+// per chain fetches the four literal masks (precomputed once per CTA into shared memory),
+// 8*K LOP3 do the work -- plus a remainder loop for bw % 4 planes.  Slot 0 (the only slot of
+// flat AND / OR programs) lives in a register, further slots of mixed trees in per-thread shared
+// words.  Keeping the bodies small (no per-bit-width unrolling here; the single-pass kernels of
+// fle_eval1.cu have that) keeps the kernel's register allocation and instruction cache tight.
 // ------------------------------------------------------------------------------------------
-#ifndef FLE_PASS_FN
-#define FLE_PASS_FN __device__ __forceinline__
-#endif
-
-template <int NT>
-__device__ __forceinline__ uint32_t slot_addr(uint32_t slot_base, int gpt, int slot, int q) {
-  return slot_base + (uint32_t)((slot * gpt + q) * NT) * 8u;
-}
-
-__device__ __forceinline__ void fold_smem(uint32_t addr, int op, uint64_t v) {
-  if (op != FOLD_SET) {
-    const uint64_t cur = lds64(addr);
-    v = (op == FOLD_AND) ? (cur & v) : (cur | v);
-  }
-  sts64(addr, v);
-}
-
-// One pass over one column for all of this thread's groups in the tile.
-//   mask_addr : shared address of this pass's mask table [4][32] u32 (all-ones where the
-//               literal has a 1 at that plane)
-//   col_addr  : shared address of plane 0 of the thread's first group (q = 0) in this column
-//   slots4/folds4/negs4/inits4 : PassDesc::slot/fold/neg/init packed one byte per chain
-template <int NT, bool IS_LT, int K, int BW>
-FLE_PASS_FN void pass_tile(uint32_t mask_addr, uint32_t col_addr, uint32_t slot_base, int gpt,
-                           uint32_t slots4, uint32_t folds4, uint32_t negs4, uint32_t inits4,
-                           uint32_t merge) {
-  constexpr bool kRegMasks = (K * BW <= 40);  // keep every body under ~80 registers (3 CTAs/SM)
-  uint32_t m[kRegMasks ? K * BW : 1];
-  if constexpr (kRegMasks) {
+template <bool IS_LT, int K>
+__device__ __forceinline__ void quad_step(const uint64_t (&w)[4], const uint32_t (&m)[K][4], uint32_t (&al)[K],
+                                          uint32_t (&ah)[K]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t wl = (uint32_t)w[j], wh = (uint32_t)(w[j] >> 32);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-#pragma unroll
-      for (int i = 0; i < BW; ++i) m[k * BW + i] = lds32(mask_addr + (uint32_t)(k * 32 + i) * 4u);
+      const uint32_t mk = m[k][j];
+      if (IS_LT) {
+        al[k] = (~wl & mk) | (~(wl ^ mk) & al[k]);
+        ah[k] = (~wh & mk) | (~(wh ^ mk) & ah[k]);
+      } else {
+        al[k] = al[k] & ~(wl ^ mk);
+        ah[k] = ah[k] & ~(wh ^ mk);
+      }
     }
   }
-  uint32_t nm[K], ini[K];
+}
+
+// One pass on one group: planes at shared address `a` (8-byte aligned; 16-byte aligned when bw is
+// even), masks at mask_addr ([4 chains][32 planes] u32).  r[k] = plane-order result of chain k.
+template <bool IS_LT, int K>
+__device__ __forceinline__ void staged_pass(uint32_t a, int bw, uint32_t mask_addr, uint32_t inits4, uint32_t negs4,
+                                            uint64_t (&r)[K]) {
+  uint32_t al[K], ah[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) al[k] = ah[k] = IS_LT ? (0u - ((inits4 >> (8 * k)) & 1u)) : ~0u;
+  int i = 0;
+  const bool even = (bw & 1) == 0;
+  for (; i + 4 <= bw; i += 4) {
+    uint64_t w[4];
+    if (even) {
+      lds128(a + i * 8, w[0], w[1]);
+      lds128(a + i * 8 + 16, w[2], w[3]);
+    } else {
+      w[0] = lds64(a + i * 8);
+      w[1] = lds64(a + i * 8 + 8);
+      w[2] = lds64(a + i * 8 + 16);
+      w[3] = lds64(a + i * 8 + 24);
+    }
+    uint32_t m[K][4];
+#pragma unroll
+    for (int k = 0; k < K; ++k) lds128u(mask_addr + k * 128 + i * 4, m[k][0], m[k][1], m[k][2], m[k][3]);
+    quad_step<IS_LT, K>(w, m, al, ah);
+  }
+  for (; i < bw; ++i) {
+    const uint64_t w = lds64(a + i * 8);
+    const uint32_t wl = (uint32_t)w, wh = (uint32_t)(w >> 32);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const uint32_t mk = lds32(mask_addr + k * 128 + i * 4);
+      if (IS_LT) {
+        al[k] = (~wl & mk) | (~(wl ^ mk) & al[k]);
+        ah[k] = (~wh & mk) | (~(wh ^ mk) & ah[k]);
+      } else {
+        al[k] = al[k] & ~(wl ^ mk);
+        ah[k] = ah[k] & ~(wh ^ mk);
+      }
+    }
+  }
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    nm[k] = ((negs4 >> (8 * k)) & 1u) ? ~0u : 0u;
-    ini[k] = IS_LT ? (((inits4 >> (8 * k)) & 1u) ? ~0u : 0u) : ~0u;
-  }
-  constexpr uint32_t kGroupStride = (uint32_t)(NT / 8) * BW * 8u;  // q -> q+1 inside a segment
-  for (int q = 0; q < gpt; ++q) {
-    const uint32_t a = col_addr + (uint32_t)q * kGroupStride;
-    uint32_t al[K], ah[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) al[k] = ah[k] = ini[k];
-#pragma unroll
-    for (int i = 0; i < BW; i += 2) {
-      uint64_t w0, w1 = 0;
-      if constexpr (BW % 2 == 0) {
-        lds128(a + i * 8, w0, w1);
-      } else {
-        w0 = lds64(a + i * 8);
-        if (i + 1 < BW) w1 = lds64(a + (i + 1) * 8);
-      }
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (i + h < BW) {
-          const uint64_t w = h ? w1 : w0;
-          const uint32_t wl = (uint32_t)w, wh = (uint32_t)(w >> 32);
-#pragma unroll
-          for (int k = 0; k < K; ++k) {
-            uint32_t mk;
-            if constexpr (kRegMasks) mk = m[k * BW + i + h];
-            else mk = lds32(mask_addr + (uint32_t)(k * 32 + i + h) * 4u);
-            if (IS_LT) {
-              al[k] = (~wl & mk) | (~(wl ^ mk) & al[k]);
-              ah[k] = (~wh & mk) | (~(wh ^ mk) & ah[k]);
-            } else {
-              al[k] = al[k] & ~(wl ^ mk);
-              ah[k] = ah[k] & ~(wh ^ mk);
-            }
-          }
-        }
-      }
-    }
-    if (merge) {
-      const int mop = (int)((folds4 >> (8 * (K - 1))) & 0xffu);
-      uint32_t rl = al[0] ^ nm[0], rh = ah[0] ^ nm[0];
-#pragma unroll
-      for (int k = 1; k < K; ++k) {
-        const uint32_t xl = al[k] ^ nm[k], xh = ah[k] ^ nm[k];
-        if (mop == FOLD_AND) { rl &= xl; rh &= xh; } else { rl |= xl; rh |= xh; }
-      }
-      fold_smem(slot_addr<NT>(slot_base, gpt, (int)(slots4 & 0xffu), q), (int)(folds4 & 0xffu),
-                ((uint64_t)rh << 32) | rl);
-    } else {
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        const uint64_t r = ((uint64_t)(ah[k] ^ nm[k]) << 32) | (al[k] ^ nm[k]);
-        fold_smem(slot_addr<NT>(slot_base, gpt, (int)((slots4 >> (8 * k)) & 0xffu), q),
-                  (int)((folds4 >> (8 * k)) & 0xffu), r);
-      }
-    }
+    const uint32_t nm = 0u - ((negs4 >> (8 * k)) & 1u);
+    r[k] = ((uint64_t)(ah[k] ^ nm) << 32) | (al[k] ^ nm);
   }
 }
 
-// IN list: OR over literals of an XNOR-AND chain (fle-encoding.h:8282-8290), four literals per
-// sweep over the planes; partial results accumulate in the scratch slot, then fold once.
-template <int NT, int BW>
-FLE_PASS_FN void in_tile(const uint32_t* lits, int cnt, uint32_t col_addr, uint32_t slot_base, int gpt,
-                         int tmp_slot, int dst_slot, int fold, uint32_t negmask) {
-  constexpr bool kRegMasks = (4 * BW <= 40);
-  constexpr uint32_t kGroupStride = (uint32_t)(NT / 8) * BW * 8u;
-  for (int j = 0; j < cnt; j += 4) {
-    uint32_t lit[4];
+// fold K chain results into their slots (slot 0 = register s0, others = per-thread shared words)
+template <int K>
+__device__ __forceinline__ void staged_fold(const uint64_t (&r)[K], uint32_t slots4, uint32_t folds4, uint32_t merge,
+                                            Slots& sl) {
+  if (K > 1 && merge) {
+    const int mop = (int)((folds4 >> (8 * (K - 1))) & 0xffu);
+    uint64_t v = r[0];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) lit[k] = lits[min(j + k, cnt - 1)];  // pad by repetition
-    uint32_t m[kRegMasks ? 4 * BW : 1];
-    if constexpr (kRegMasks) {
+    for (int k = 1; k < K; ++k) v = (mop == FOLD_AND) ? (v & r[k]) : (v | r[k]);
+    sl.fold((int)(slots4 & 0xffu), (int)(folds4 & 0xffu), v);
+  } else {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-#pragma unroll
-        for (int i = 0; i < BW; ++i) m[k * BW + i] = 0u - ((lit[k] >> i) & 1u);
-      }
-    }
-    for (int q = 0; q < gpt; ++q) {
-      const uint32_t a = col_addr + (uint32_t)q * kGroupStride;
-      uint32_t al[4], ah[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) al[k] = ah[k] = ~0u;
-#pragma unroll
-      for (int i = 0; i < BW; i += 2) {
-        uint64_t w0, w1 = 0;
-        if constexpr (BW % 2 == 0) {
-          lds128(a + i * 8, w0, w1);
-        } else {
-          w0 = lds64(a + i * 8);
-          if (i + 1 < BW) w1 = lds64(a + (i + 1) * 8);
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (i + h < BW) {
-            const uint64_t w = h ? w1 : w0;
-            const uint32_t wl = (uint32_t)w, wh = (uint32_t)(w >> 32);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              uint32_t mk;
-              if constexpr (kRegMasks) mk = m[k * BW + i + h];
-              else mk = 0u - ((lit[k] >> (i + h)) & 1u);
-              al[k] = al[k] & ~(wl ^ mk);
-              ah[k] = ah[k] & ~(wh ^ mk);
-            }
-          }
-        }
-      }
-      const uint64_t any = ((uint64_t)((ah[0] | ah[1]) | (ah[2] | ah[3])) << 32) | ((al[0] | al[1]) | (al[2] | al[3]));
-      fold_smem(slot_addr<NT>(slot_base, gpt, tmp_slot, q), j == 0 ? FOLD_SET : FOLD_OR, any);
-    }
-  }
-  const uint64_t nm64 = ((uint64_t)negmask << 32) | negmask;
-  for (int q = 0; q < gpt; ++q) {
-    const uint64_t v = lds64(slot_addr<NT>(slot_base, gpt, tmp_slot, q)) ^ nm64;
-    fold_smem(slot_addr<NT>(slot_base, gpt, dst_slot, q), fold, v);
-  }
-}
-
-#define FLE_BW_CASES(X) \
-  X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) \
-  X(17) X(18) X(19) X(20) X(21) X(22) X(23) X(24) X(25) X(26) X(27) X(28) X(29) X(30) X(31) X(32)
-
-template <int NT>
-__device__ __forceinline__ void dispatch_in(int bw, const uint32_t* lits, int cnt, uint32_t col_addr,
-                                            uint32_t slot_base, int gpt, int tmp_slot, int dst_slot, int fold,
-                                            uint32_t negmask) {
-  switch (bw) {
-#define X(B) case B: in_tile<NT, B>(lits, cnt, col_addr, slot_base, gpt, tmp_slot, dst_slot, fold, negmask); break;
-    FLE_BW_CASES(X)
-#undef X
+    for (int k = 0; k < K; ++k) sl.fold((int)((slots4 >> (8 * k)) & 0xffu), (int)((folds4 >> (8 * k)) & 0xffu), r[k]);
   }
 }
 
@@ -448,7 +358,9 @@ __global__ void __launch_bounds__(NT, 768 / NT) eval_tma_kernel(const __grid_con
   }
 
   const uint32_t seg = threadIdx.x & 7, jrow = threadIdx.x >> 3;
-  const uint32_t slot_base = smem_u32(smem + P.smem_slots_off) + threadIdx.x * 8u;
+  Slots sl;
+  sl.smem = smem_u32(smem + P.smem_slots_off) + threadIdx.x * 8u;
+  sl.stride = NT * 8;
   uint64_t cnt = 0;
 
   int stage = 0;
@@ -467,44 +379,61 @@ __global__ void __launch_bounds__(NT, 768 / NT) eval_tma_kernel(const __grid_con
     mbar_wait(bar0 + stage * 8, parity);
     const uint32_t sbase = stage0 + stage * P.stage_bytes;
 
-    // 1. passes (warp-uniform control flow): one jump through a flat table of specialised bodies;
-    //    the pass record is read as nine 32-bit words straight from the constant bank
-    for (int p = 0; p < P.npasses; ++p) {
-      const uint32_t* pw = reinterpret_cast<const uint32_t*>(&P.passes[p]);
-      const uint32_t w0 = pw[0], slots4 = pw[1], folds4 = pw[2], negs4 = pw[3], inits4 = pw[4];
-      const uint32_t dispatch = pw[9];
-      const uint32_t col = (w0 >> 8) & 0xffu, merge = w0 >> 24;
-      const uint32_t col_addr = sbase + P.col_off[col] + seg * P.seg_stride[col] + jrow * (P.bw[col] * 8u);
-      const uint32_t mask_addr = masks0 + (uint32_t)p * 512u;
-      switch (dispatch) {
-#define FLE_BODY(IDX, IS_LT, K, B) \
-        case (IDX) * 32 + (B) - 1: pass_tile<NT, IS_LT, K, B>(mask_addr, col_addr, slot_base, gpt, slots4, folds4, negs4, inits4, merge); break;
-#define X(B) FLE_BODY(0, true, 1, B) FLE_BODY(1, true, 2, B) FLE_BODY(2, true, 4, B) FLE_BODY(3, false, 1, B) FLE_BODY(4, false, 4, B)
-        FLE_BW_CASES(X)
-#undef X
-#undef FLE_BODY
-        case kDispatchIn:
-          dispatch_in<NT>((int)P.bw[col], lits_smem + pw[5], (int)pw[6], col_addr, slot_base, gpt, P.in_tmp_slot,
-                          (int)(slots4 & 0xffu), (int)(folds4 & 0xffu), (negs4 & 1u) ? ~0u : 0u);
-          break;
-        default: {  // kDispatchConst
-          const uint64_t v = (inits4 & 1u) ? ~0ull : 0ull;
-          for (int q = 0; q < gpt; ++q) fold_smem(slot_addr<NT>(slot_base, gpt, (int)(slots4 & 0xffu), q), (int)(folds4 & 0xffu), v);
-          break;
+    for (int q = 0; q < gpt; ++q) {
+      const uint32_t jq = (uint32_t)q * (NT / 8) + jrow;  // group index inside the thread's segment
+      sl.s0 = P.slot0_init;
+      // passes: warp-uniform control flow; the pass record is read as 32-bit constant-bank words
+      for (int p = 0; p < P.npasses; ++p) {
+        const uint32_t* pw = reinterpret_cast<const uint32_t*>(&P.passes[p]);
+        const uint32_t w0 = pw[0], slots4 = pw[1], folds4 = pw[2], negs4 = pw[3], inits4 = pw[4];
+        const uint32_t type = w0 & 0xffu, col = (w0 >> 8) & 0xffu, k = (w0 >> 16) & 0xffu, merge = w0 >> 24;
+        if (type == PASS_CONST) {
+          sl.fold((int)(slots4 & 0xffu), (int)(folds4 & 0xffu), (inits4 & 1u) ? ~0ull : 0ull);
+          continue;
+        }
+        const int bw = (int)P.bw[col];
+        const uint32_t a = sbase + P.col_off[col] + seg * P.seg_stride[col] + jq * (uint32_t)(bw * 8);
+        const uint32_t mask_addr = masks0 + (uint32_t)p * 512u;
+        if (type == PASS_LT) {
+          if (k == 1) { uint64_t r[1]; staged_pass<true, 1>(a, bw, mask_addr, inits4, negs4, r); staged_fold<1>(r, slots4, folds4, merge, sl); }
+          else if (k == 2) { uint64_t r[2]; staged_pass<true, 2>(a, bw, mask_addr, inits4, negs4, r); staged_fold<2>(r, slots4, folds4, merge, sl); }
+          else { uint64_t r[4]; staged_pass<true, 4>(a, bw, mask_addr, inits4, negs4, r); staged_fold<4>(r, slots4, folds4, merge, sl); }
+        } else if (type == PASS_EQ) {
+          if (k == 1) { uint64_t r[1]; staged_pass<false, 1>(a, bw, mask_addr, inits4, negs4, r); staged_fold<1>(r, slots4, folds4, merge, sl); }
+          else { uint64_t r[4]; staged_pass<false, 4>(a, bw, mask_addr, inits4, negs4, r); staged_fold<4>(r, slots4, folds4, merge, sl); }
+        } else {  // PASS_IN: OR of equality chains, four literals per sweep (fle-encoding.h:8282-8290)
+          const uint32_t* lits = lits_smem + pw[5];
+          const int lcnt = (int)pw[6];
+          uint64_t any = 0;
+          for (int j = 0; j < lcnt; j += 4) {
+            uint32_t lit[4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) lit[kk] = lits[min(j + kk, lcnt - 1)];
+            uint32_t al[4], ah[4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) al[kk] = ah[kk] = ~0u;
+            for (int i = 0; i < bw; ++i) {
+              const uint64_t w = lds64(a + i * 8);
+              const uint32_t wl = (uint32_t)w, wh = (uint32_t)(w >> 32);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint32_t mk = 0u - ((lit[kk] >> i) & 1u);
+                al[kk] = al[kk] & ~(wl ^ mk);
+                ah[kk] = ah[kk] & ~(wh ^ mk);
+              }
+            }
+            any |= ((uint64_t)((ah[0] | ah[1]) | (ah[2] | ah[3])) << 32) | ((al[0] | al[1]) | (al[2] | al[3]));
+          }
+          sl.fold((int)(slots4 & 0xffu), (int)(folds4 & 0xffu), (negs4 & 1u) ? ~any : any);
         }
       }
-    }
-
-    // 2. per-group epilogue: combine ops, row order, store, count
-    for (int q = 0; q < gpt; ++q) {
       for (int c = 0; c < P.ncombs; ++c) {
         const CombDesc cd = P.combs[c];
-        const uint64_t a = lds64(slot_addr<NT>(slot_base, gpt, cd.a, q));
-        const uint64_t b = lds64(slot_addr<NT>(slot_base, gpt, cd.b, q));
-        sts64(slot_addr<NT>(slot_base, gpt, cd.dst, q), cd.op == FOLD_AND ? (a & b) : (a | b));
+        const uint64_t x = sl.get(cd.a), y = sl.get(cd.b);
+        sl.put(cd.dst, cd.op == FOLD_AND ? (x & y) : (x | y));
       }
-      const int64_t g = tile * T + (int64_t)seg * seg_groups + q * (NT / 8) + jrow;
-      const uint64_t r = finish_word(lds64(slot_addr<NT>(slot_base, gpt, 0, q)), g, P.nrows);
+      const int64_t g = tile * T + (int64_t)seg * seg_groups + jq;
+      const uint64_t r = finish_word(sl.s0, g, P.nrows);
       P.bitmap[g] = r;
       cnt += __popcll(r);
     }
@@ -514,12 +443,8 @@ __global__ void __launch_bounds__(NT, 768 / NT) eval_tma_kernel(const __grid_con
     }
   }
 
-  // ragged remainder (< T groups): spread over all CTAs, planes straight from global memory,
-  // generic interpreter (slots: slot 0 in a register, the rest reuse the slot area)
+  // ragged remainder (< T groups): spread over all CTAs, planes straight from global memory
   {
-    Slots sl;
-    sl.smem = slot_base;
-    sl.stride = NT * 8;
     const int64_t g0 = ntiles * T;
     for (int64_t g = g0 + (int64_t)blockIdx.x * NT + threadIdx.x; g < P.ngroups;
          g += (int64_t)gridDim.x * NT) {
@@ -794,7 +719,7 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw) {
   if (mode == MODE_STAGED) off += (uint32_t)P.npasses * 512u;
   if (mode == MODE_IN_LOOKUP) off += std::max(4u, (1u << P.bw[0]) / 8u);  // membership table, 2^bw bits
   P.smem_slots_off = off;
-  if (mode == MODE_DIRECT || mode == MODE_STAGED) off += (uint32_t)P.nslots * gpt * kNT * 8u;
+  if (mode == MODE_DIRECT || mode == MODE_STAGED) off += (uint32_t)P.nslots * kNT * 8u;
   off = round_up(off, 128);
   P.smem_stage_off = off;
 
@@ -947,18 +872,12 @@ int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, 
     const int rc = launch_program(ctx, P1, MODE_SINGLE_PASS, (int)P.bw[c]);
     if (rc != FLE_E_UNSUPPORTED) return rc;
   }
-  // Multi-pass programs: measured on B200 (tools/sweep.py programs, profiles/), the direct-load
-  // kernel currently beats the generic staged kernel (Q6: 0.85 vs 0.63 of the HBM roofline)
-  // because the staged one pays its per-tile pass dispatch once per group at gpt = 1; the
-  // staged generic kernel stays selectable with eval_variant = 2.
-  // Exception: columns whose group size is a multiple of 128 bytes (bw 16, 32) or 64 bytes (24)
-  // make the direct kernel's per-thread strided loads collide in L1 (0.35-0.47 of roofline
-  // measured), so programs touching such a column go the staged way.
-  bool strided_l1_hazard = false;
-  for (int c = 0; c < ncols; ++c) strided_l1_hazard = strided_l1_hazard || (P.bw[c] >= 16 && P.bw[c] % 8 == 0);
-  if (staged_ok && (ctx->eval_variant == 2 || (ctx->eval_variant == 1 && strided_l1_hazard))) {
+  // Everything else (several passes, mixed AND/OR trees, IN lists inside larger programs): the
+  // TMA-staged generic kernel; the direct-load kernel remains for unaligned inputs, tiles that do
+  // not fit in shared memory, and as eval_variant = 0.
+  if (staged_ok) {
     const int rc = launch_program(ctx, P, MODE_STAGED, sum_bw);
-    if (rc != FLE_E_UNSUPPORTED) return rc;  // tile does not fit in shared memory: direct kernel
+    if (rc != FLE_E_UNSUPPORTED) return rc;
   }
   return launch_program(ctx, P, MODE_DIRECT, sum_bw);
 }

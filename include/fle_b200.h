@@ -100,8 +100,9 @@ int fle_ctx_destroy(fle_ctx* ctx);
 int fle_ctx_set_stream(fle_ctx* ctx, void* cuda_stream);
 int fle_ctx_sync(fle_ctx* ctx);
 /* Tuning knobs, all optional: "eval_variant" (0 = direct-load generic kernel for everything;
- * 1 [default] = TMA-staged single-pass kernels specialised per bit width where the program
- * is one pass, direct-load generic kernel otherwise; 2 = TMA-staged kernels for everything),
+ * 1 [default] = TMA-staged kernels: single-pass kernels specialised per bit width where the
+ * program is one pass, the staged generic kernel otherwise; 2 = staged generic kernel for
+ * everything),
  * "eval_stages", "eval_ctas_per_sm", "eval_gpt" (0 = auto), "codec_variant",
  * "h2d_chunk_rows". */
 int fle_ctx_set_option(fle_ctx* ctx, const char* name, int64_t value);

@@ -16,6 +16,8 @@ if b:
         line = f"bw{bw:2d}"
         if t:
             line += f" tma {t['ms_min']:.4f}ms {t['GBps']:6.0f} {t['frac']:.3f}"
+        if b[bw].get(2):
+            line += f" | generic-staged {b[bw][2]['GBps']:6.0f} {b[bw][2]['frac']:.3f}"
         if d:
             line += f" | direct {d['GBps']:6.0f} {d['frac']:.3f}"
         if t:

@@ -71,7 +71,7 @@ def make_col(ctx, n, bw, dom=None, seed=1):
     return v, w
 
 
-def sweep_between(ctx, out, n, variants=(1, 0), bws=range(1, 33)):
+def sweep_between(ctx, out, n, variants=(1, 2, 0), bws=range(1, 33)):
     G = (n + 63) // 64
     bm = torch.empty(G, dtype=torch.int64, device="cuda")
     cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
@@ -191,12 +191,15 @@ def sweep_tune(ctx, out, n):
     v, w3 = make_col(ctx, n, 3, dom=7, seed=500)
     del v
     cases["q12"] = ([(w3, 3), q6c[0]], [(IN, 0, [1, 4]), (GE, 1, 730), (AND, None, None), (LT, 1, 1095), (AND, None, None)], 15)
+    v, w2 = make_col(ctx, n, 2, dom=4, seed=501)
+    del v
+    cases["or_variant"] = ([(w3, 3), (w2, 2), q6c[2]], [(IN, 0, [1, 4]), (EQ, 1, 2), (OR, None, None), (LT, 2, 23), (AND, None, None)], 11)
     for cname, (pc, prog, sum_bw) in cases.items():
         prep = (ctx.make_col_descs(pc),) + fle_b200.capi._build_program(prog)
-        for variant in (1, 2):
+        for variant in (2,):
             for stages in (0, 2, 3, 4):
-                for gpt in (0, 1, 2, 3, 4, 8):
-                    for cps in (0, 1, 2, 3, 4):
+                for gpt in (0, 1, 2, 4):
+                    for cps in (0, 2, 3):
                         ctx.set_option("eval_variant", variant)
                         ctx.set_option("eval_stages", stages)
                         ctx.set_option("eval_gpt", gpt)
