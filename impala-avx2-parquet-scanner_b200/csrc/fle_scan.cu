@@ -141,33 +141,66 @@ gather_kernel(const uint64_t* __restrict__ planes, int bw, const uint32_t* __res
   }
 }
 
-// Fused Q6-style aggregate: one thread per 64-row group; groups without survivors cost one
-// bitmap word.  Exact int64 arithmetic; per-block partials are added with 64-bit atomics.
+// Fused Q6-style aggregate.  A warp takes 32 consecutive groups (one bitmap word per lane), then
+// walks the survivors of those 2048 rows in a FLATTENED order -- survivor t of the warp goes to
+// lane t % 32 -- so that every lane has one independent random load of plain[] in flight per
+// step no matter how the survivors are distributed over the groups (a thread-per-group loop is
+// latency-bound on that load and diverges with the popcount).  Exact int64 arithmetic;
+// per-block partials are added with 64-bit atomics.
+__device__ __forceinline__ int nth_set_bit64(uint64_t x, int n) {  // position of the n-th (0-based) set bit
+  const uint32_t lo = (uint32_t)x;
+  const int clo = __popc(lo);
+  if (n < clo) return (int)__fns(lo, 0, n + 1);
+  return 32 + (int)__fns((uint32_t)(x >> 32), 0, n - clo + 1);
+}
+
 __global__ void __launch_bounds__(256)
 sum_product_kernel(const uint64_t* __restrict__ bm, int64_t nrows, const int64_t* __restrict__ plain,
                    const uint64_t* __restrict__ planes, int bw, const int64_t* __restrict__ dict, int ndict,
                    unsigned long long* __restrict__ sum_out, unsigned long long* __restrict__ count_out) {
   __shared__ long long warp_sum[8];
   __shared__ unsigned long long warp_cnt[8];
+  __shared__ uint32_t prefix_s[8][33];
+  __shared__ uint64_t word_s[8][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t nwords = (nrows + 63) >> 6;
+  const int64_t nwarps = ((int64_t)gridDim.x * 256) >> 5;
   long long s = 0;
   unsigned long long c = 0;
-  for (int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x; g < nwords; g += (int64_t)gridDim.x * 256) {
-    uint64_t x = bm[g] & sel_tail_mask(g, nrows);
-    if (x == 0) continue;
-    const uint64_t* gp = planes + (uint64_t)g * bw;
-    c += __popcll(x);
-    const int64_t* pg = plain + g * 64;
-    while (x) {
-      const int b = __ffsll((long long)x) - 1;  // row b of the group sits at plane bit 63-b
-      const long long pv = __ldg(pg + b);       // issue the random price load first
+  for (int64_t g0 = ((((int64_t)blockIdx.x * 256) >> 5) + wid) * 32; g0 < nwords; g0 += nwarps * 32) {
+    const int64_t g = g0 + lane;
+    const uint64_t x = g < nwords ? (bm[g] & sel_tail_mask(g, nrows)) : 0ull;
+    const uint32_t mine = __popcll(x);
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) continue;
+    __syncwarp();
+    prefix_s[wid][lane] = incl - mine;  // exclusive
+    if (lane == 31) prefix_s[wid][32] = total;
+    word_s[wid][lane] = x;
+    __syncwarp();
+    c += mine;
+    for (uint32_t t = lane; t < total; t += 32) {
+      // owner lane j: prefix[j] <= t < prefix[j+1]
+      int j = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1)
+        if (prefix_s[wid][j + step] <= t) j += step;
+      const int b = nth_set_bit64(word_s[wid][j], (int)(t - prefix_s[wid][j]));  // row b of group g0+j
+      const int64_t gg = g0 + j;
+      const long long pv = __ldg(plain + gg * 64 + b);
+      const uint64_t* gp = planes + (uint64_t)gg * bw;
       const int sh = 63 - b;
       uint32_t code = 0;
 #pragma unroll 4
-      for (int i = 0; i < bw; ++i) code |= (uint32_t)((__ldg(gp + i) >> sh) & 1ull) << i;  // L1 hits after the first survivor
+      for (int i = 0; i < bw; ++i) code |= (uint32_t)((__ldg(gp + i) >> sh) & 1ull) << i;
       const long long d = code < (uint32_t)ndict ? __ldg(dict + code) : 0;
       s += pv * d;
-      x &= x - 1;
     }
   }
 #pragma unroll
@@ -175,9 +208,9 @@ sum_product_kernel(const uint64_t* __restrict__ bm, int64_t nrows, const int64_t
     s += __shfl_xor_sync(0xffffffffu, s, o);
     c += __shfl_xor_sync(0xffffffffu, c, o);
   }
-  if ((threadIdx.x & 31) == 0) {
-    warp_sum[threadIdx.x >> 5] = s;
-    warp_cnt[threadIdx.x >> 5] = c;
+  if (lane == 0) {
+    warp_sum[wid] = s;
+    warp_cnt[wid] = c;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
