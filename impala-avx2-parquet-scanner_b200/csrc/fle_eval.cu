@@ -9,14 +9,16 @@
 // One thread owns one group at a time and walks its planes LSB -> MSB with 64-bit boolean
 // algebra (2 x LOP3 per plane per comparison), so no value is ever decoded.
 //
-// Kernel 1 (eval_tma_kernel, default): persistent CTAs; every tile of T = blockDim*gpt groups
-// is staged global -> shared by TMA bulk copies (cp.async.bulk, one per column per segment)
-// into an nstages-deep mbarrier ring, so ~50-150 KB per SM are in flight with no register
-// cost.  The tile of each column is split into 8 segments skewed by 16 B so that the
-// per-thread (strided by bw*8 bytes) 64/128-bit shared loads are bank-conflict free for
-// every bit width.
-// Kernel 0 (eval_direct_kernel): same algebra, planes read straight from global memory;
-// used for unaligned inputs, the ragged last tile's groups and as an on-device cross-check.
+// eval_tma_kernel (default for programs with several passes): persistent CTAs; every tile of
+// T = 256*gpt groups is staged global -> shared by TMA bulk copies (cp.async.bulk, one per column
+// per segment) into an nstages-deep mbarrier ring, so ~50-150 KB per SM are in flight with no
+// register cost.  The tile of each column is split into 8 segments skewed by 16 B so that the
+// per-thread (strided by bw*8 bytes) 64/128-bit shared loads are bank-conflict free for every
+// bit width.
+// eval_direct_kernel: same algebra, planes read straight from global memory; used for
+// unaligned inputs, tiles that do not fit in shared memory, the ragged last tile's groups, and
+// as an on-device cross-check (eval_variant = 0).
+// Single-pass programs and single IN lists have their own kernels (fle_eval1.cu, fle_eval_in.cu).
 #include <algorithm>
 #include <cstring>
 #include <mutex>
@@ -586,7 +588,6 @@ int lower_program(const fle_col_desc* cols, int ncols, const fle_pred_node* node
   });
   // flat programs: the first chain executed initialises slot 0 (SET), the rest fold into it
   if (flat && !chains.empty()) chains[0].fold = FOLD_SET;
-  bool any_in = false;
   size_t i = 0;
   while (i < chains.size()) {
     if (P.npasses >= kMaxPasses) return fail(FLE_E_UNSUPPORTED, "too many predicate leaves");
@@ -598,7 +599,6 @@ int lower_program(const fle_col_desc* cols, int ncols, const fle_pred_node* node
       pd.k = 1;
       pd.slot[0] = c0.slot; pd.fold[0] = c0.fold; pd.neg[0] = c0.neg; pd.init[0] = c0.init;
       pd.lit[0] = c0.in_off; pd.lit[1] = c0.in_cnt;
-      any_in = any_in || c0.type == PASS_IN;
       ++i;
       continue;
     }
@@ -625,17 +625,6 @@ int lower_program(const fle_col_desc* cols, int ncols, const fle_pred_node* node
     //  first pass and padding repeats the LAST chain of a pass with k >= 2; in mixed trees every
     //  chain SETs its own slot)
     pd.k = (uint8_t)want;
-    const int kind_k = c0.type == PASS_LT ? (want == 1 ? 0 : want == 2 ? 1 : 2) : (want == 1 ? 3 : 4);
-    pd.dispatch = (uint32_t)(kind_k * 32 + cols[c0.col].bit_width - 1);
-  }
-  for (int q = 0; q < P.npasses; ++q) {
-    if (P.passes[q].type == PASS_IN) P.passes[q].dispatch = kDispatchIn;
-    if (P.passes[q].type == PASS_CONST) P.passes[q].dispatch = kDispatchConst;
-  }
-  P.in_tmp_slot = -1;
-  if (any_in) {
-    if (P.nslots >= kMaxSlots) return fail(FLE_E_UNSUPPORTED, "too many leaves in a mixed AND/OR tree");
-    P.in_tmp_slot = P.nslots++;
   }
   return FLE_OK;
 }

@@ -28,7 +28,11 @@ namespace fle {
 //
 // Chains are grouped into passes of up to 4 chains on one column, so each plane word is
 // fetched from shared memory once per pass.  Results fold into "slots": slot 0 lives in a
-// register, slots >= 1 in shared memory; a short list of combine ops finishes the tree.
+// register, slots >= 1 in per-thread shared-memory words; a short list of combine ops finishes
+// the tree.  A program that is ONE pass (single compare, BETWEEN, Eq, <= 4 compares on one
+// column) runs on the per-bit-width kernels of fle_eval1.cu, a single IN list on a column of
+// <= 16 bits on the decode + lookup kernel of fle_eval_in.cu, everything else on the generic
+// kernels of fle_eval.cu.
 // ------------------------------------------------------------------------------------------
 enum PassType : uint8_t { PASS_LT = 0, PASS_EQ = 1, PASS_IN = 2, PASS_CONST = 3 };
 enum FoldOp : uint8_t { FOLD_SET = 0, FOLD_AND = 1, FOLD_OR = 2 };
@@ -49,11 +53,9 @@ struct PassDesc {
   uint8_t neg[4];   // 1: complement the chain result before folding
   uint8_t init[4];  // PASS_LT: chain init (0 => '<', 1 => '<='); PASS_CONST: the constant
   uint32_t lit[4];  // literal per chain (masked to bw bits); PASS_IN: lit[0]=offset, lit[1]=count
-  uint32_t dispatch;  // staged kernel: body index = kindK * 32 + (bw - 1), kindK: LT K1/K2/K4 = 0/1/2,
-                      // EQ K1/K4 = 3/4; kDispatchIn / kDispatchConst for the other pass types
+  uint32_t reserved;
 };
-constexpr uint32_t kDispatchIn = 200, kDispatchConst = 201;
-static_assert(sizeof(PassDesc) == 40 && offsetof(PassDesc, lit) == 20 && offsetof(PassDesc, dispatch) == 36,
+static_assert(sizeof(PassDesc) == 40 && offsetof(PassDesc, slot) == 4 && offsetof(PassDesc, lit) == 20,
               "the staged kernel reads PassDesc as 32-bit words");
 
 struct CombDesc {
@@ -68,9 +70,10 @@ struct EvalParams {
   uint32_t bw[FLE_MAX_COLS];
   uint32_t col_off[FLE_MAX_COLS];     // byte offset of the column's region inside a stage
   uint32_t seg_stride[FLE_MAX_COLS];  // byte distance between the 8 skewed segments
-  int32_t ncols, npasses, ncombs, nslots;  // nslots includes in_tmp_slot when present
-  int32_t in_tmp_slot;                     // scratch slot for IN passes (-1: none)
-  uint32_t smem_masks_off;                 // per-pass literal masks [npasses][4][32] u32
+  int32_t ncols, npasses, ncombs, nslots;
+  int32_t pad0;
+  uint32_t smem_masks_off;                 // per-pass literal masks [npasses][4][32] u32 (staged generic kernel);
+                                           // membership table (IN lookup kernel)
   int32_t gpt;      // groups per thread per tile
   int32_t nstages;  // TMA pipeline depth
   uint32_t stage_bytes;
