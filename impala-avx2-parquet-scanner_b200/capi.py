@@ -29,7 +29,7 @@ EXPORTS = [
     "fle_d2h", "fle_encoded_bytes", "fle_pack_u32", "fle_pack_u32_dev", "fle_unpack_u32",
     "fle_unpack_u32_dev", "fle_eval", "fle_eval_dev", "fle_bitmap_count_dev", "fle_intersect_bitset",
     "fle_intersect_bitset_dev", "fle_bitmap_select_dev", "fle_gather_dev", "fle_sum_product_dev",
-    "fle_page_parse", "fle_realign_dev", "fle_plain_eval_dev", "fle_dict_encode_dev",
+    "fle_page_parse", "fle_realign_dev", "fle_plain_eval_dev", "fle_dict_encode_dev", "fle_eval_codegen",
 ]
 
 
@@ -109,6 +109,8 @@ def load_library() -> C.CDLL:
     L.fle_bitmap_select_dev.argtypes = [vp, vp, i64, vp, i64, vp]
     L.fle_gather_dev.argtypes = [vp, vp, C.c_size_t, i32, vp, vp, i64, vp, i32, i32, vp]
     L.fle_sum_product_dev.argtypes = [vp, vp, i64, vp, vp, C.c_size_t, i32, vp, i32, vp, vp]
+    L.fle_eval_codegen.argtypes = [C.POINTER(ColDesc), i32, C.POINTER(PredNode), i32, i32, C.c_char_p, C.c_size_t,
+                                   C.POINTER(C.c_size_t)]
     _lib = L
     return L
 
@@ -131,6 +133,24 @@ def _build_program(program: Sequence[tuple]):
         elif op <= GE:
             nodes[i].code = int(np.atleast_1d(lit)[0]) if lit is not None else 0
     return nodes, keep
+
+
+def eval_codegen(bit_widths: Sequence[int], program: Sequence[tuple], compile=False):
+    """The run-time specialisation of a program's shape, no device needed (fle_eval_codegen).
+    Returns (rc, text): the generated CUDA C++ (compile=False), the NVRTC log, '' on success
+    (compile=True), or the cubin as bytes (compile=2)."""
+    lib = load_library()
+    cols = (ColDesc * len(bit_widths))()
+    for i, bw in enumerate(bit_widths):
+        cols[i].bit_width = int(bw)
+    nodes, _keep = _build_program(program)
+    cap = 1 << 20
+    buf = C.create_string_buffer(cap)
+    n = C.c_size_t(0)
+    rc = lib.fle_eval_codegen(cols, len(bit_widths), nodes, len(nodes), int(compile), buf, cap, C.byref(n))
+    if int(compile) == 2 and rc == OK:
+        return rc, buf.raw[:n.value]
+    return rc, buf.value.decode(errors="replace")
 
 
 class FleContext:

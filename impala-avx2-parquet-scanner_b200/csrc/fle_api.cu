@@ -334,6 +334,8 @@ int fle_ctx_set_option(fle_ctx* ctx, const char* name, int64_t value) {
   else if (k == "eval_gpt") ctx->eval_gpt = (int)value;
   else if (k == "in_lookup_min") ctx->in_lookup_min = (int)value;
   else if (k == "codec_variant") ctx->codec_variant = (int)value;
+  else if (k == "eval_jit") ctx->eval_jit = (int)value;
+  else if (k == "eval_jit_min_rows") ctx->eval_jit_min_rows = value;
   else if (k == "h2d_chunk_rows") ctx->h2d_chunk_rows = value;
   else return set_error(ctx, FLE_E_INVALID, "unknown option " + k);
   return FLE_OK;
@@ -349,7 +351,10 @@ int64_t fle_ctx_get_option(fle_ctx* ctx, const char* name) {
   if (k == "eval_gpt") return ctx->eval_gpt;
   if (k == "in_lookup_min") return ctx->in_lookup_min;
   if (k == "codec_variant") return ctx->codec_variant;
+  if (k == "eval_jit") return ctx->eval_jit;
+  if (k == "eval_jit_min_rows") return ctx->eval_jit_min_rows;
   if (k == "h2d_chunk_rows") return ctx->h2d_chunk_rows;
+  if (k == "jit_launches") return ctx->jit_launches;
   if (k == "num_sms") return ctx->num_sms;
   if (k == "max_smem_optin") return ctx->max_smem_optin;
   return -1;
@@ -500,6 +505,37 @@ int fle_eval_dev(fle_ctx* ctx, const fle_col_desc* cols, int ncols, const fle_pr
   if (any_nullable(cols, ncols))
     return eval_dev_nullable(ctx, cols, ncols, nodes, nnodes, first_row, n, bitmap_dev, count_dev);
   return launch_eval(ctx, cols, ncols, nodes, nnodes, first_row, n, bitmap_dev, count_dev);
+}
+
+int fle_eval_codegen(const fle_col_desc* cols, int ncols, const fle_pred_node* nodes, int nnodes, int compile,
+                     char* out, size_t cap, size_t* len) {
+  if (len) *len = 0;
+  if (out && cap) out[0] = '\0';
+  LoweredProgram lp;
+  std::string text;
+  int rc = lower_program(cols, ncols, nodes, nnodes, &lp, &text);
+  if (rc == FLE_OK) {
+    lp.p.ncols = ncols;
+    for (int c = 0; c < ncols; ++c) lp.p.bw[c] = (uint32_t)cols[c].bit_width;
+    text.clear();
+    if (!jit_plan(lp.p, lp.in_lits, &lp.jit_plan)) {
+      rc = FLE_E_UNSUPPORTED;
+      text = "program too large for a specialised kernel";
+    } else if (compile) {
+      std::vector<char> cubin;
+      rc = jit_compile_text(lp.jit_plan.text, &cubin, &text);
+      if (rc == FLE_OK && compile == 2) text.assign(cubin.begin(), cubin.end());
+    } else {
+      text = lp.jit_plan.text;
+    }
+  }
+  if (len) *len = text.size();
+  if (out && cap) {
+    const size_t m = std::min(cap - 1, text.size());
+    std::memcpy(out, text.data(), m);
+    out[m] = '\0';
+  }
+  return rc;
 }
 
 int fle_eval(fle_ctx* ctx, const fle_col_desc* cols, int ncols, const fle_pred_node* nodes, int nnodes,

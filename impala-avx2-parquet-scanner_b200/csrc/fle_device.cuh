@@ -3,10 +3,24 @@
 //   * shared-memory plane loaders
 //   * the 32x32 bit-matrix transpose that turns bit planes into values and back
 #pragma once
+#ifdef __CUDACC_RTC__
+#ifndef FLE_RTC_TYPES
+#define FLE_RTC_TYPES
+typedef unsigned char uint8_t;
+typedef unsigned short uint16_t;
+typedef unsigned int uint32_t;
+typedef int int32_t;
+typedef unsigned long long uint64_t;
+typedef long long int64_t;
+#endif
+#else
 #include <cstdint>
+#endif
 
 #ifdef __CUDACC__
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
+#endif
 #define FLE_HD __host__ __device__ __forceinline__
 #else
 #define FLE_HD inline

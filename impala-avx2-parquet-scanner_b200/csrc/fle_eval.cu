@@ -599,6 +599,7 @@ int lower_program(const fle_col_desc* cols, int ncols, const fle_pred_node* node
       pd.k = 1;
       pd.slot[0] = c0.slot; pd.fold[0] = c0.fold; pd.neg[0] = c0.neg; pd.init[0] = c0.init;
       pd.lit[0] = c0.in_off; pd.lit[1] = c0.in_cnt;
+      pd.k_real = 1;
       ++i;
       continue;
     }
@@ -625,6 +626,7 @@ int lower_program(const fle_col_desc* cols, int ncols, const fle_pred_node* node
     //  first pass and padding repeats the LAST chain of a pass with k >= 2; in mixed trees every
     //  chain SETs its own slot)
     pd.k = (uint8_t)want;
+    pd.k_real = (uint32_t)k;
   }
   return FLE_OK;
 }
@@ -637,7 +639,7 @@ namespace {
 inline uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 constexpr int kNT = 256;
-enum LaunchMode { MODE_DIRECT = 0, MODE_STAGED = 1, MODE_SINGLE_PASS = 2, MODE_IN_LOOKUP = 3 };
+enum LaunchMode { MODE_DIRECT = 0, MODE_STAGED = 1, MODE_SINGLE_PASS = 2, MODE_IN_LOOKUP = 3, MODE_JIT = 4 };
 
 // cudaOccupancyMaxActiveBlocksPerMultiprocessor / cudaFuncSetAttribute are not free; remember
 // the answers per (kernel, dynamic smem)
@@ -669,16 +671,29 @@ int blocks_per_sm(fle_ctx* ctx, const void* kern, size_t smem_bytes, int* out) {
   }
   int per_sm = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kNT, smem_bytes);
-  if (e != cudaSuccess) return set_cuda_error(ctx, e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+  if (e != cudaSuccess) {
+    // (kernels loaded at run time: older runtimes answer only for statically linked functions)
+    cudaGetLastError();
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return set_cuda_error(ctx, e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    const int regs_per_cta = ((std::max(fa.numRegs, 16) + 7) / 8 * 8) * kNT;
+    const size_t smem_per_cta = smem_bytes + fa.sharedSizeBytes + 1024;
+    per_sm = (int)std::min<size_t>(std::min<size_t>(65536 / regs_per_cta, 2048 / kNT),
+                                   (size_t)ctx->max_smem_per_sm / smem_per_cta);
+  }
   ctx->occ_cache.push_back({kern, smem_bytes, per_sm});
   *out = per_sm;
   return FLE_OK;
 }
 
-int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw) {
+int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void* jit_kern = nullptr,
+                   void* jit_args = nullptr, bool jit_staged = true) {
   const int64_t G = P.ngroups;
   const void* kern = nullptr;
-  if (mode == MODE_SINGLE_PASS) {
+  if (mode == MODE_JIT) {
+    kern = jit_kern;
+  } else if (mode == MODE_SINGLE_PASS) {
     kern = eval1_kernel_for(P.passes[0].type, P.passes[0].k, (int)P.bw[0]);
     if (!kern) return FLE_E_UNSUPPORTED;
   } else if (mode == MODE_IN_LOOKUP) {
@@ -687,14 +702,18 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw) {
   } else {
     kern = mode == MODE_STAGED ? (const void*)eval_tma_kernel<kNT> : (const void*)eval_direct_kernel<kNT>;
   }
-  const bool staged = mode != MODE_DIRECT;
+  // (a specialised kernel also runs unstaged -- planes straight from global memory -- for
+  //  unaligned columns and for programs whose 256-group tile does not fit shared memory twice)
+  const bool staged = mode != MODE_DIRECT && !(mode == MODE_JIT && !jit_staged);
 
   // tile sizing: groups per thread per tile so that a stage is a few tens of KB
   int gpt = 1;
   if (staged) {
     gpt = ctx->eval_gpt;
     const uint32_t bytes_per_gpt = (uint32_t)kNT * sum_bw * 8u;
-    const uint32_t target = mode == MODE_STAGED ? 32u * 1024u : 40u * 1024u;
+    // (measured, tools/sweep.py tune: the interpreting kernel likes ~32 KB stages and 3 CTAs/SM, the
+    //  single-pass kernels ~40 KB, the multi-column specialised kernels ~90 KB with 1-2 CTAs/SM)
+    const uint32_t target = mode == MODE_STAGED ? 32u * 1024u : (mode == MODE_JIT ? 88u * 1024u : 40u * 1024u);
     if (gpt <= 0) gpt = (int)std::max<uint32_t>(1, std::min<uint32_t>(8, (target + bytes_per_gpt / 2) / bytes_per_gpt));
     gpt = std::min(gpt, 8);
   }
@@ -703,7 +722,7 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw) {
   P.smem_bar_off = off;
   off += 8 * 8;  // up to 8 stages
   P.smem_lits_off = off;
-  if (mode == MODE_DIRECT || mode == MODE_STAGED) off = round_up(off + (uint32_t)P.n_in_lits * 4u, 16);
+  if (mode == MODE_DIRECT || mode == MODE_STAGED || mode == MODE_JIT) off = round_up(off + (uint32_t)P.n_in_lits * 4u, 16);
   P.smem_masks_off = off;
   if (mode == MODE_STAGED) off += (uint32_t)P.npasses * 512u;
   if (mode == MODE_IN_LOOKUP) off += std::max(4u, (1u << P.bw[0]) / 8u);  // membership table, 2^bw bits
@@ -765,7 +784,7 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw) {
   P.partial = ctx->d_partial;
   P.ticket = ctx->d_ticket;
   P.in_lits = ctx->d_in_lits;
-  void* args[] = {(void*)&P};
+  void* args[] = {(void*)&P, jit_args};
   cudaError_t e = cudaLaunchKernel(kern, dim3(grid), dim3(kNT), args, smem_bytes, ctx->stream);
   if (e != cudaSuccess) {
     cudaGetLastError();  // clear the non-sticky error
@@ -775,6 +794,7 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw) {
     return set_cuda_error(ctx, e, what);
   }
   ctx->launches += 1;
+  if (mode == MODE_JIT) ctx->jit_launches += 1;
   return FLE_OK;
 }
 
@@ -861,8 +881,35 @@ int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, 
     const int rc = launch_program(ctx, P1, MODE_SINGLE_PASS, (int)P.bw[c]);
     if (rc != FLE_E_UNSUPPORTED) return rc;
   }
-  // Everything else (several passes, mixed AND/OR trees, IN lists inside larger programs): the
-  // TMA-staged generic kernel; the direct-load kernel remains for unaligned inputs, tiles that do
+  // Several passes, mixed AND/OR trees, IN lists inside larger programs: a kernel specialised
+  // for the program's shape at run time (fle_jit.cu) when the call is large enough to pay for
+  // one compilation, or the shape has been compiled before
+  if (ctx->eval_variant == 1 && ctx->eval_jit != 0) {
+    bool same_bw = lp->jit_state != 0;
+    for (int c = 0; c < ncols && same_bw; ++c) same_bw = lp->jit_bw[c] == P.bw[c];
+    if (!same_bw) {
+      lp->jit_state = jit_plan(P, lp->in_lits, &lp->jit_plan) ? 1 : -1;
+      for (int c = 0; c < ncols; ++c) lp->jit_bw[c] = P.bw[c];
+      lp->jit_entry.reset();
+    }
+    if (lp->jit_state == 1) {
+      if (!lp->jit_entry)
+        lp->jit_entry = jit_lookup(lp->jit_plan.text, ctx->eval_jit == 2 || n >= ctx->eval_jit_min_rows);
+      if (lp->jit_entry && lp->jit_entry->rc == FLE_OK) {
+        jit_fill_args(lp->jit_plan, P, lp->in_lits, &lp->jit_args);
+        int rc = FLE_E_UNSUPPORTED;
+        if (staged_ok) rc = launch_program(ctx, P, MODE_JIT, sum_bw, lp->jit_entry->kern, lp->jit_args.data(), true);
+        if (rc == FLE_E_UNSUPPORTED)
+          rc = launch_program(ctx, P, MODE_JIT, sum_bw, lp->jit_entry->kern, lp->jit_args.data(), false);
+        if (rc != FLE_E_UNSUPPORTED) return rc;
+      } else if (lp->jit_entry && ctx->eval_jit == 2) {
+        return set_error(ctx, FLE_E_UNSUPPORTED, "eval_jit = 2: " + lp->jit_entry->log);
+      }
+    } else if (ctx->eval_jit == 2) {
+      return set_error(ctx, FLE_E_UNSUPPORTED, "eval_jit = 2: program too large for a specialised kernel");
+    }
+  }
+  // Everything else: the TMA-staged generic kernel; the direct-load kernel remains for unaligned inputs, tiles that do
   // not fit in shared memory, and as eval_variant = 0.
   if (staged_ok) {
     const int rc = launch_program(ctx, P, MODE_STAGED, sum_bw);

@@ -2,7 +2,7 @@
 // fle_eval1.cu: single-pass kernels specialised per bit width).
 #pragma once
 #include "fle_device.cuh"
-#include "fle_internal.h"
+#include "fle_params.h"
 
 namespace fle {
 

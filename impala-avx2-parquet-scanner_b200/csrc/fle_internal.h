@@ -11,91 +11,21 @@
 #include <vector>
 
 #include "../../include/fle_b200.h"
+#include "fle_params.h"
+#include "fle_jit.h"
 
 namespace fle {
-
-// ------------------------------------------------------------------------------------------
-// Lowered form of a predicate program (built on the host by lower_program, consumed by the
-// eval kernels as a __grid_constant__ parameter).
-//
-// Every comparison leaf becomes one "borrow chain" over the planes, LSB -> MSB:
-//     acc' = (~W & C) | (~(W ^ C) & acc)          (one LOP3 per 32 rows per plane)
-// which is the borrow-out of x - c (init 0 => x < c) or of x - c - 1 (init ~0 => x <= c).
-//     Lt = chain(init 0)   Le = chain(init 1)   Ge = ~Lt   Gt = ~Le
-// These are exact boolean functions of the row's bits, hence bit-identical to the
-// reference's MSB -> LSB Mlt/Mgt/Meq recurrences (fle-encoding.h:8039-8042, :8151-8154).
-// Eq / In use the reference's own XNOR-AND chain (fle-encoding.h:7986-7988, :8283-8290).
-//
-// Chains are grouped into passes of up to 4 chains on one column, so each plane word is
-// fetched from shared memory once per pass.  Results fold into "slots": slot 0 lives in a
-// register, slots >= 1 in per-thread shared-memory words; a short list of combine ops finishes
-// the tree.  A program that is ONE pass (single compare, BETWEEN, Eq, <= 4 compares on one
-// column) runs on the per-bit-width kernels of fle_eval1.cu, a single IN list on a column of
-// <= 16 bits on the decode + lookup kernel of fle_eval_in.cu, everything else on the generic
-// kernels of fle_eval.cu.
-// ------------------------------------------------------------------------------------------
-enum PassType : uint8_t { PASS_LT = 0, PASS_EQ = 1, PASS_IN = 2, PASS_CONST = 3 };
-enum FoldOp : uint8_t { FOLD_SET = 0, FOLD_AND = 1, FOLD_OR = 2 };
-
-constexpr int kMaxPasses = 40;
-constexpr int kMaxCombs = 64;
-constexpr int kMaxSlots = 32;
-
-struct PassDesc {
-  uint8_t type;     // PassType
-  uint8_t col;      // column index
-  uint8_t k;        // chains in this pass: 1, 2 or 4 (3 is padded by repeating the last chain,
-                    // which is harmless because SET/AND/OR of the same value are idempotent);
-                    // PASS_IN / PASS_CONST: 1
-  uint8_t merge;    // 1: all chains fold into slot[0] with the same op -> combine in registers
-  uint8_t slot[4];  // destination slot per chain
-  uint8_t fold[4];  // FoldOp per chain
-  uint8_t neg[4];   // 1: complement the chain result before folding
-  uint8_t init[4];  // PASS_LT: chain init (0 => '<', 1 => '<='); PASS_CONST: the constant
-  uint32_t lit[4];  // literal per chain (masked to bw bits); PASS_IN: lit[0]=offset, lit[1]=count
-  uint32_t reserved;
-};
-static_assert(sizeof(PassDesc) == 40 && offsetof(PassDesc, slot) == 4 && offsetof(PassDesc, lit) == 20,
-              "the staged kernel reads PassDesc as 32-bit words");
-
-struct CombDesc {
-  uint8_t op;  // FOLD_AND / FOLD_OR
-  uint8_t dst; // slot written (== a)
-  uint8_t a;
-  uint8_t b;
-};
-
-struct EvalParams {
-  const uint64_t* planes[FLE_MAX_COLS];  // already offset to first_row's group
-  uint32_t bw[FLE_MAX_COLS];
-  uint32_t col_off[FLE_MAX_COLS];     // byte offset of the column's region inside a stage
-  uint32_t seg_stride[FLE_MAX_COLS];  // byte distance between the 8 skewed segments
-  int32_t ncols, npasses, ncombs, nslots;
-  int32_t pad0;
-  uint32_t smem_masks_off;                 // per-pass literal masks [npasses][4][32] u32 (staged generic kernel);
-                                           // membership table (IN lookup kernel)
-  int32_t gpt;      // groups per thread per tile
-  int32_t nstages;  // TMA pipeline depth
-  uint32_t stage_bytes;
-  uint32_t smem_bar_off, smem_lits_off, smem_slots_off, smem_stage_off;
-  int64_t ngroups;
-  int64_t nrows;
-  uint64_t slot0_init;
-  uint64_t* bitmap;
-  uint64_t* partial;    // per-CTA popcounts (gridDim entries)
-  unsigned int* ticket; // self-resetting completion counter
-  uint64_t* count_out;  // may be null
-  const uint32_t* in_lits;
-  int32_t n_in_lits;
-  int32_t pad;
-  PassDesc passes[kMaxPasses];
-  CombDesc combs[kMaxCombs];
-};
 
 struct LoweredProgram {
   EvalParams p;                  // passes / combs / nslots / slot0_init filled in
   std::vector<uint32_t> in_lits; // IN literal pool
   bool lits_uploaded = false;    // pool already copied to ctx->d_in_lits
+  // run-time specialisation (fle_jit.cu), filled in lazily by launch_prepared
+  JitPlan jit_plan;
+  uint32_t jit_bw[FLE_MAX_COLS] = {0};  // bit widths jit_plan was made for
+  int jit_state = 0;                     // 0 not planned, 1 planned, -1 shape not supported
+  std::shared_ptr<JitEntry> jit_entry;
+  std::vector<uint32_t> jit_args;
 };
 
 // Returns FLE_OK or FLE_E_*; err gets a human-readable reason.
@@ -117,6 +47,7 @@ struct fle_ctx {
   struct OccEntry { const void* kern; size_t smem; int blocks; };
   std::vector<OccEntry> occ_cache;
   int64_t launches = 0;
+  int64_t jit_launches = 0;  // ... of which kernels specialised at run time
   std::string last_error;
 
   // options
@@ -127,6 +58,8 @@ struct fle_ctx {
   int eval_gpt = 0;          // 0 = auto
   int in_lookup_min = 6;     // IN lists at least this long use the decode+lookup kernel (bw <= 16)
   int codec_variant = 1;
+  int eval_jit = 1;                      // 0 never, 1 when n >= eval_jit_min_rows or already compiled, 2 always
+  int64_t eval_jit_min_rows = 1ll << 24;
   int64_t h2d_chunk_rows = 0;  // 0 = auto
 
   // scratch owned by the context (device)

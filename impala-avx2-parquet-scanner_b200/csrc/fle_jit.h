@@ -1,0 +1,42 @@
+// Run-time program specialisation (fle_jit.cu): plan, generated text, kernel cache.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "fle_params.h"
+
+namespace fle {
+
+struct JitChain {
+  bool lt;       // borrow chain ('<' family) or equality chain
+  int bw;
+  int pass, k;   // literal / init / negate come from P.passes[pass] chain k ...
+  int in_idx;    // ... or (>= 0) the literal is in_lits[in_idx] of an unrolled IN list
+  int mask_off;  // first of bw mask words in JitArgs::mask
+};
+
+struct JitPlan {
+  std::string text;  // "fle_jit_program.h" -- also the cache key
+  std::vector<JitChain> chains;
+  int nmask = 0;
+};
+
+struct JitEntry {
+  int rc = 0;                  // FLE_OK or why there is no kernel
+  std::string log;
+  void* lib = nullptr;         // cudaLibrary_t
+  const void* kern = nullptr;  // cudaKernel_t, usable with cudaLaunchKernel / cudaFuncSetAttribute
+};
+
+// P: lowered program with ncols / bw[] filled in.  false: shape not supported (too large)
+bool jit_plan(const EvalParams& P, const std::vector<uint32_t>& in_lits, JitPlan* plan);
+// the JitArgs parameter block for the current literals
+void jit_fill_args(const JitPlan& plan, const EvalParams& P, const std::vector<uint32_t>& in_lits,
+                   std::vector<uint32_t>* args);
+// NVRTC only (no device needed): FLE_OK and the cubin, or an error and the compiler log
+int jit_compile_text(const std::string& program_text, std::vector<char>* cubin, std::string* log);
+// process-wide kernel cache; compiles and loads on a miss when asked to
+std::shared_ptr<JitEntry> jit_lookup(const std::string& program_text, bool compile_if_missing);
+
+}  // namespace fle

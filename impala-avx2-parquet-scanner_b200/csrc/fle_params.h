@@ -1,0 +1,106 @@
+// Plain-data description of a lowered predicate program: the kernel parameter block of every
+// fused-eval kernel.  Pure C-style structs so that the SAME text compiles under nvcc (library
+// build) and under NVRTC (programs specialised at run time, fle_jit.cu embeds this file).
+#pragma once
+#ifdef __CUDACC_RTC__
+#ifndef FLE_RTC_TYPES
+#define FLE_RTC_TYPES
+typedef unsigned char uint8_t;
+typedef unsigned short uint16_t;
+typedef unsigned int uint32_t;
+typedef int int32_t;
+typedef unsigned long long uint64_t;
+typedef long long int64_t;
+#endif
+#else
+#include <cstddef>
+#include <cstdint>
+#endif
+
+#ifndef FLE_MAX_COLS
+#define FLE_MAX_COLS 8 /* == include/fle_b200.h */
+#endif
+
+namespace fle {
+
+// ------------------------------------------------------------------------------------------
+// Lowered form of a predicate program (built on the host by lower_program, consumed by the
+// eval kernels as a __grid_constant__ parameter).
+//
+// Every comparison leaf becomes one "borrow chain" over the planes, LSB -> MSB:
+//     acc' = (~W & C) | (~(W ^ C) & acc)          (one LOP3 per 32 rows per plane)
+// which is the borrow-out of x - c (init 0 => x < c) or of x - c - 1 (init ~0 => x <= c).
+//     Lt = chain(init 0)   Le = chain(init 1)   Ge = ~Lt   Gt = ~Le
+// These are exact boolean functions of the row's bits, hence bit-identical to the
+// reference's MSB -> LSB Mlt/Mgt/Meq recurrences (fle-encoding.h:8039-8042, :8151-8154).
+// Eq / In use the reference's own XNOR-AND chain (fle-encoding.h:7986-7988, :8283-8290).
+//
+// Chains are grouped into passes of up to 4 chains on one column, so each plane word is
+// fetched from shared memory once per pass.  Results fold into "slots": slot 0 lives in a
+// register, slots >= 1 in per-thread shared-memory words; a short list of combine ops finishes
+// the tree.  A program that is ONE pass (single compare, BETWEEN, Eq, <= 4 compares on one
+// column) runs on the per-bit-width kernels of fle_eval1.cu, a single IN list on a column of
+// <= 16 bits on the decode + lookup kernel of fle_eval_in.cu, everything else on the generic
+// kernels of fle_eval.cu.
+// ------------------------------------------------------------------------------------------
+enum PassType : uint8_t { PASS_LT = 0, PASS_EQ = 1, PASS_IN = 2, PASS_CONST = 3 };
+enum FoldOp : uint8_t { FOLD_SET = 0, FOLD_AND = 1, FOLD_OR = 2 };
+
+constexpr int kMaxPasses = 40;
+constexpr int kMaxCombs = 64;
+constexpr int kMaxSlots = 32;
+
+struct PassDesc {
+  uint8_t type;     // PassType
+  uint8_t col;      // column index
+  uint8_t k;        // chains in this pass: 1, 2 or 4 (3 is padded by repeating the last chain,
+                    // which is harmless because SET/AND/OR of the same value are idempotent);
+                    // PASS_IN / PASS_CONST: 1
+  uint8_t merge;    // 1: all chains fold into slot[0] with the same op -> combine in registers
+  uint8_t slot[4];  // destination slot per chain
+  uint8_t fold[4];  // FoldOp per chain
+  uint8_t neg[4];   // 1: complement the chain result before folding
+  uint8_t init[4];  // PASS_LT: chain init (0 => '<', 1 => '<='); PASS_CONST: the constant
+  uint32_t lit[4];  // literal per chain (masked to bw bits); PASS_IN: lit[0]=offset, lit[1]=count
+  uint32_t k_real;  // chains before padding (what a program specialised at run time unrolls)
+};
+#ifndef __CUDACC_RTC__
+static_assert(sizeof(PassDesc) == 40 && offsetof(PassDesc, slot) == 4 && offsetof(PassDesc, lit) == 20,
+              "the staged kernel reads PassDesc as 32-bit words");
+#endif
+
+struct CombDesc {
+  uint8_t op;  // FOLD_AND / FOLD_OR
+  uint8_t dst; // slot written (== a)
+  uint8_t a;
+  uint8_t b;
+};
+
+struct EvalParams {
+  const uint64_t* planes[FLE_MAX_COLS];  // already offset to first_row's group
+  uint32_t bw[FLE_MAX_COLS];
+  uint32_t col_off[FLE_MAX_COLS];     // byte offset of the column's region inside a stage
+  uint32_t seg_stride[FLE_MAX_COLS];  // byte distance between the 8 skewed segments
+  int32_t ncols, npasses, ncombs, nslots;
+  int32_t pad0;
+  uint32_t smem_masks_off;                 // per-pass literal masks [npasses][4][32] u32 (staged generic kernel);
+                                           // membership table (IN lookup kernel)
+  int32_t gpt;      // groups per thread per tile
+  int32_t nstages;  // TMA pipeline depth
+  uint32_t stage_bytes;
+  uint32_t smem_bar_off, smem_lits_off, smem_slots_off, smem_stage_off;
+  int64_t ngroups;
+  int64_t nrows;
+  uint64_t slot0_init;
+  uint64_t* bitmap;
+  uint64_t* partial;    // per-CTA popcounts (gridDim entries)
+  unsigned int* ticket; // self-resetting completion counter
+  uint64_t* count_out;  // may be null
+  const uint32_t* in_lits;
+  int32_t n_in_lits;
+  int32_t pad;
+  PassDesc passes[kMaxPasses];
+  CombDesc combs[kMaxCombs];
+};
+
+}  // namespace fle

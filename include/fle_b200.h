@@ -103,6 +103,12 @@ int fle_ctx_sync(fle_ctx* ctx);
  * 1 [default] = TMA-staged kernels: single-pass kernels specialised per bit width where the
  * program is one pass, the staged generic kernel otherwise; 2 = staged generic kernel for
  * everything),
+ * "eval_jit" (programs that are not one pass -- several columns, mixed AND/OR trees -- can run
+ * on a kernel specialised for the program's SHAPE at run time, compiled once per shape with
+ * NVRTC and cached process-wide; literals are not part of the shape.  0 = never, 1 [default] =
+ * when the call covers at least "eval_jit_min_rows" rows (default 2^24) or the shape's kernel
+ * already exists, 2 = always; without a usable libnvrtc.so.12 modes 0/1 use the interpreting
+ * kernels and mode 2 fails with FLE_E_UNSUPPORTED),
  * "eval_stages", "eval_ctas_per_sm", "eval_gpt" (0 = auto), "codec_variant",
  * "h2d_chunk_rows". */
 int fle_ctx_set_option(fle_ctx* ctx, const char* name, int64_t value);
@@ -164,6 +170,17 @@ int fle_eval(fle_ctx* ctx, const fle_col_desc* cols, int ncols, const fle_pred_n
 int fle_eval_dev(fle_ctx* ctx, const fle_col_desc* cols_dev, int ncols,
                  const fle_pred_node* postfix, int nnodes, int64_t first_row, int64_t n,
                  uint64_t* bitmap_out_dev, uint64_t* match_count_dev);
+
+/* The run-time specialisation behind "eval_jit", without a device: writes the CUDA C++ generated
+ * for the program's shape (compile == 0) or compiles it for sm_100a with NVRTC and writes the
+ * compiler log, empty on success (compile == 1), NUL-terminated, into out[0..cap); *len (optional)
+ * receives the untruncated length.  compile == 2 writes the sm_100a cubin instead (binary; for
+ * cuobjdump -sass).  Only cols[i].bit_width is read.  FLE_E_UNSUPPORTED: the
+ * program has no specialised form (it is a single pass, or too large) or NVRTC is missing.
+ * This is the step Impala's LLVM codegen performs for the expression trees the reference
+ * interprets (simple-predicates.h:113-163). */
+int fle_eval_codegen(const fle_col_desc* cols, int ncols, const fle_pred_node* postfix, int nnodes,
+                     int compile, char* out, size_t cap, size_t* len);
 
 /* ---- bitmap utilities ------------------------------------------------------------------- */
 /* dynamic_bitset::count() over the first nbits bits. */

@@ -66,9 +66,10 @@ def test_predicates_vs_golden(ctx, golden, bw, variant):
         ctx.set_option("eval_variant", 1)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, "jit"])
 def test_trees_vs_golden(ctx, golden, variant):
-    ctx.set_option("eval_variant", variant)
+    ctx.set_option("eval_variant", 1 if variant == "jit" else variant)
+    ctx.set_option("eval_jit", 2 if variant == "jit" else 0)
     try:
         n = int(golden["tree_n"][0])
         cols = [(golden[f"tree_words_{i}"], bw) for i, bw in enumerate((12, 4, 6))]
@@ -78,6 +79,7 @@ def test_trees_vs_golden(ctx, golden, variant):
         assert (bm == golden["tree_or"]).all() and cnt == popcount(golden["tree_or"])
     finally:
         ctx.set_option("eval_variant", 1)
+        ctx.set_option("eval_jit", 1)
 
 
 # ------------------------------------------------------------------------------------------
@@ -110,7 +112,8 @@ def test_single_column_vs_oracle(ctx, oracle, bw):
 
 @pytest.mark.parametrize("opts", [dict(), dict(eval_variant=2), dict(eval_variant=2, eval_stages=2, eval_gpt=2),
                                   dict(eval_variant=2, eval_stages=4, eval_ctas_per_sm=1), dict(eval_variant=0),
-                                  dict(h2d_chunk_rows=64 * 4096)])
+                                  dict(h2d_chunk_rows=64 * 4096), dict(eval_jit=2), dict(eval_jit=2, eval_gpt=1, eval_stages=2),
+                                  dict(eval_jit=0)])
 def test_multi_column_programs_vs_oracle(ctx, oracle, opts):
     rng = np.random.default_rng(2024)
     n = 64 * 20000 + 17
@@ -142,7 +145,7 @@ def test_multi_column_programs_vs_oracle(ctx, oracle, opts):
             assert (bm == want).all() and cnt == wcnt, name
     finally:
         for k in opts:
-            ctx.set_option(k, {"eval_variant": 1}.get(k, 0))
+            ctx.set_option(k, {"eval_variant": 1, "eval_jit": 1}.get(k, 0))
 
 
 def test_edge_sizes_and_errors(ctx, oracle):

@@ -8,7 +8,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 import fle_b200  # noqa: E402
-from fle_b200 import AND, GE, IN, LE, LT  # noqa: E402
+from fle_b200 import AND, EQ, GE, IN, LE, LT, OR  # noqa: E402
 
 case = sys.argv[1] if len(sys.argv) > 1 else "between12"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 600_037_902
@@ -34,6 +34,16 @@ if case == "q6":
     cols = [(col(2526, 12)[1], 12), (col(11, 4)[1], 4), (col(50, 6)[1], 6)]
     prog = [(GE, 0, 730), (LE, 0, 1094), (AND, None, None), (GE, 1, 5), (LE, 1, 7), (AND, None, None),
             (AND, None, None), (LT, 2, 23), (AND, None, None)]
+    for _ in range(reps):
+        ctx.eval_dev(cols, prog, n, bitmap=bm, count=cnt)
+elif case == "or_variant":
+    cols = [(col(7, 3)[1], 3), (col(4, 2)[1], 2), (col(50, 6)[1], 6)]
+    prog = [(IN, 0, [1, 4]), (EQ, 1, 2), (OR, None, None), (LT, 2, 23), (AND, None, None)]
+    for _ in range(reps):
+        ctx.eval_dev(cols, prog, n, bitmap=bm, count=cnt)
+elif case == "q12":
+    cols = [(col(7, 3)[1], 3), (col(2526, 12)[1], 12)]
+    prog = [(IN, 0, [1, 4]), (GE, 1, 730), (AND, None, None), (LT, 1, 1095), (AND, None, None)]
     for _ in range(reps):
         ctx.eval_dev(cols, prog, n, bitmap=bm, count=cnt)
 elif case.startswith("between"):

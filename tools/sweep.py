@@ -149,6 +149,11 @@ def sweep_programs(ctx, out, n):
         "q12": (["shipmode", "receipt"], [(IN, 0, [1, 4]), (GE, 1, 730), (AND,), (LT, 1, 1095), (AND,)]),
         "q14": (["shipdate"], [(GE, 0, 1339), (LT, 0, 1369), (AND,)]),
         "or_variant": (["shipmode", "instruct", "quantity"], [(IN, 0, [1, 4]), (EQ, 1, 2), (OR,), (LT, 2, 23), (AND,)]),
+        "q19ish": (["shipmode", "instruct", "quantity", "discount", "shipdate"],
+                   [(IN, 0, [0, 2]), (EQ, 1, 1), (AND,), (GE, 2, 1), (LE, 2, 11), (AND,), (AND,),
+                    (IN, 0, [1, 3]), (EQ, 1, 1), (AND,), (GE, 2, 10), (LE, 2, 20), (AND,), (AND,), (OR,),
+                    (LT, 3, 9), (AND,), (GE, 4, 100), (AND,)]),
+        "in20_and_lt": (["shipdate", "quantity"], [(IN, 0, torch.randint(0, 2526, (20,), generator=g).tolist()), (LT, 1, 30), (OR,)]),
         "in8_bw12": (["shipdate"], [(IN, 0, torch.randint(0, 2526, (8,), generator=g).tolist())]),
         "in64_bw12": (["shipdate"], [(IN, 0, torch.randint(0, 2526, (64,), generator=g).tolist())]),
         "in256_bw12": (["shipdate"], [(IN, 0, torch.randint(0, 2526, (256,), generator=g).tolist())]),
@@ -161,12 +166,15 @@ def sweep_programs(ctx, out, n):
         prog = [tuple(p) + (None,) * (3 - len(p)) for p in prog]
         prep = (ctx.make_col_descs(pc),) + fle_b200.capi._build_program(prog)
         sum_bw = sum(bw for _, bw in pc)
-        for var in (1, 2, 0):
+        # "1j": default path with run-time specialised kernels forced on; 1 / 2 / 0: interpreting kernels
+        for label, var, jit in (("1j", 1, 2), (1, 1, 0), (2, 2, 0), (0, 0, 0)):
             ctx.set_option("eval_variant", var)
+            ctx.set_option("eval_jit", jit)
             mn, md = timeit(lambda: ctx.eval_dev(pc, prog, n, bitmap=bm, count=cnt, prepared=prep), reps=5 if "in256" in name else 10)
-            rec(out, what="program", name=name, variant=var, rows=n, sum_bw=sum_bw, ms_min=mn, ms_med=md,
+            rec(out, what="program", name=name, variant=label, rows=n, sum_bw=sum_bw, ms_min=mn, ms_med=md,
                 alg_bytes=G * sum_bw * 8 + G * 8, rows_per_s=n / (mn * 1e-3), count=int(cnt.item()))
         ctx.set_option("eval_variant", 1)
+        ctx.set_option("eval_jit", 1)
 
 
 def sweep_tune(ctx, out, n):
@@ -196,11 +204,14 @@ def sweep_tune(ctx, out, n):
     cases["or_variant"] = ([(w3, 3), (w2, 2), q6c[2]], [(IN, 0, [1, 4]), (EQ, 1, 2), (OR, None, None), (LT, 2, 23), (AND, None, None)], 11)
     for cname, (pc, prog, sum_bw) in cases.items():
         prep = (ctx.make_col_descs(pc),) + fle_b200.capi._build_program(prog)
-        for variant in (2,):
+        for variant in (2, "jit"):
+            if variant == "jit" and len(pc) == 1:
+                continue
             for stages in (0, 2, 3, 4):
-                for gpt in (0, 1, 2, 4):
-                    for cps in (0, 2, 3):
-                        ctx.set_option("eval_variant", variant)
+                for gpt in (0, 1, 2, 4, 8):
+                    for cps in (0, 1, 2, 3):
+                        ctx.set_option("eval_variant", 1 if variant == "jit" else variant)
+                        ctx.set_option("eval_jit", 2 if variant == "jit" else 0)
                         ctx.set_option("eval_stages", stages)
                         ctx.set_option("eval_gpt", gpt)
                         ctx.set_option("eval_ctas_per_sm", cps)
@@ -211,6 +222,7 @@ def sweep_tune(ctx, out, n):
                         rec(out, what="tune", case=cname, block=variant, stages=stages, gpt=gpt, ctas=cps, ms_min=mn,
                             ms_med=md, alg_bytes=G * sum_bw * 8 + G * 8)
     ctx.set_option("eval_variant", 1)
+    ctx.set_option("eval_jit", 1)
     for k, d in (("eval_block", 256), ("eval_stages", 0), ("eval_gpt", 0), ("eval_ctas_per_sm", 0)):
         ctx.set_option(k, d)
 
