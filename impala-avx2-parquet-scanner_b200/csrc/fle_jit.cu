@@ -29,10 +29,8 @@ namespace {
 constexpr int kShortIn = 8;  // IN lists up to this long are unrolled into equality chains
 
 void emit_fold(std::string& t, int slot, int fold, const std::string& v) {
-  char b[160];
   const char* op = fold == FOLD_SET ? "=" : (fold == FOLD_AND ? "&=" : "|=");
-  snprintf(b, sizeof(b), "    s%d %s %s;\n", slot, op, v.c_str());
-  t += b;
+  t += "    s" + std::to_string(slot) + " " + op + " " + v + ";\n";
 }
 
 }  // namespace

@@ -147,3 +147,48 @@ def test_device_resident_q6_matches_interpreting_kernel(ctx):
     ctx.set_option("eval_jit", 1)
     torch.cuda.synchronize()
     assert torch.equal(a, b) and int(ca.item()) == int(cb.item()) > 0
+
+
+def random_program(rng, bws, max_leaves=8):
+    """A random postfix tree over the columns: compare / IN / constant leaves, AND / OR nodes."""
+    nleaves = int(rng.integers(1, max_leaves + 1))
+    prog, depth = [], 0
+    for i in range(nleaves):
+        c = int(rng.integers(0, len(bws)))
+        dom = 1 << bws[c]
+        kind = rng.choice(["cmp", "cmp", "cmp", "in", "const"], p=[0.3, 0.3, 0.2, 0.15, 0.05])
+        if kind == "cmp":
+            prog.append((int(rng.choice([EQ, LT, LE, GT, GE])), c, int(rng.integers(0, dom))))
+        elif kind == "in":
+            k = int(rng.choice([0, 1, 2, 3, 8, 9, 12]))
+            prog.append((IN, c, rng.integers(0, dom, size=k).astype(np.uint64)))
+        else:
+            prog.append((int(rng.choice([ALL, NONE])),) + N_)
+        depth += 1
+        while depth > 1 and (i == nleaves - 1 or rng.random() < 0.5):
+            prog.append((int(rng.choice([AND, OR])),) + N_)
+            depth -= 1
+    return prog
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_programs_all_paths_vs_oracle(ctx, oracle, seed):
+    """Fuzz: the specialised kernel, the staged interpreter and the direct interpreter against the
+    oracle on the same random program (random shapes, widths 1..32, ragged row counts)."""
+    rng = np.random.default_rng(1000 + seed)
+    ncols = int(rng.integers(1, 5))
+    bws = [int(rng.choice([1, 2, 3, 5, 8, 12, 13, 16, 17, 24, 32])) for _ in range(ncols)]
+    n = int(rng.choice([64 * 700 + 13, 64 * 4096 + 1, 64 * 5000]))
+    _, cols = make_cols(oracle, rng, n, bws, [min(1 << b, 50) if rng.random() < 0.5 else 1 << b for b in bws])
+    try:
+        for _ in range(3):
+            prog = random_program(rng, bws)
+            want, wcnt = oracle.eval_tree(cols, prog, n)
+            for variant, jit in ((1, 2), (2, 0), (0, 0)):
+                ctx.set_option("eval_variant", variant)
+                ctx.set_option("eval_jit", jit)
+                bm, cnt = ctx.eval(cols, prog, n)
+                assert (bm == want).all() and cnt == wcnt, (seed, variant, jit, prog)
+    finally:
+        ctx.set_option("eval_variant", 1)
+        ctx.set_option("eval_jit", 1)

@@ -15,6 +15,7 @@ SHAPES = {
     "q6": ([12, 4, 6], Q6),
     "or_tree": ([3, 2, 6], [(IN, 0, [1, 4]), (EQ, 1, 2), (OR,), (LT, 2, 23), (AND,)]),
     "odd_widths": ([1, 31, 17], [(EQ, 0, 1), (GT, 1, 5), (AND,), (LE, 2, 99), (AND,)]),
+    "in8_in_tree": ([13, 5], [(IN, 0, list(range(8))), (GE, 1, 3), (AND,), (IN, 0, [9, 10, 11, 12, 13, 14, 15, 16]), (OR,)]),
     "long_in": ([12, 32], [(IN, 0, list(range(20))), (LT, 1, 5), (OR,)]),
     "consts": ([12, 4], [(ALL,), (LT, 0, 1000), (AND,), (NONE,), (OR,), (GE, 1, 3), (AND,)]),
     "eight_columns": ([5] * 8, [(LT, 0, 3)] + sum([[(GE, c, 2), (AND,)] for c in range(1, 8)], [])),
