@@ -44,6 +44,22 @@ FLE_HD void transpose32_stage(uint32_t (&A)[32]) {
 #pragma unroll
   for (int k = 0; k < 32; ++k) {
     if ((k & J) == 0) {
+#ifdef __CUDA_ARCH__
+      // the 16- and 8-bit stages move whole bytes: one PRMT per output word instead of
+      // shift/xor/and/xor/shift/xor
+      if (J == 16) {
+        const uint32_t x = A[k], y = A[k + J];
+        A[k] = __byte_perm(x, y, 0x3276);      // (x & 0xFFFF0000) | (y >> 16)
+        A[k + J] = __byte_perm(x, y, 0x1054);  // (y & 0x0000FFFF) | (x << 16)
+        continue;
+      }
+      if (J == 8) {
+        const uint32_t x = A[k], y = A[k + J];
+        A[k] = __byte_perm(x, y, 0x3715);      // (x & 0xFF00FF00) | ((y >> 8) & 0x00FF00FF)
+        A[k + J] = __byte_perm(x, y, 0x2604);  // (y & 0x00FF00FF) | ((x & 0x00FF00FF) << 8)
+        continue;
+      }
+#endif
       uint32_t t = (A[k] ^ (A[k + J] >> J)) & M;
       A[k] ^= t;
       A[k + J] ^= (t << J);
@@ -131,6 +147,18 @@ __device__ __forceinline__ void tma_store_wait() {
 // generic-proxy smem writes -> visible to the async proxy (before a bulk store reads them)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// Ampere-style asynchronous 16-byte copies global -> shared (LDGSTS): arbitrary (swizzled)
+// destinations, no staging registers; bytes past src_bytes are written as zero.
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
