@@ -293,15 +293,18 @@ unpack_tma_kernel(const uint64_t* __restrict__ enc, int64_t ngroups, int64_t nva
 // asynchronous 16-byte copies (cp.async, SASS LDGSTS) straight into the swizzled tile, double
 // buffered: the next tile is in flight while this one is transposed, with no staging registers.
 // (The first version loaded through registers, 4 x 16 bytes per thread at a time: ncu showed
-// 70 % of the stall samples on those loads and 0.60-0.77 of roofline.)
+// 70 % of the stall samples on those loads and 0.60-0.77 of roofline.)  The plane image of a
+// tile is written over the value buffer it was transposed from -- every thread holds its row in
+// registers by then -- so a CTA needs 2 x 32 KB for any bit width and three CTAs fit an SM.
+constexpr uint32_t kPackBufBytes = kTileValueBytes + 128;  // >= PlaneTile<32>::kBytes
+
 template <int BW>
 __global__ void __launch_bounds__(kCodecThreads)
 pack_tma_kernel(const uint32_t* __restrict__ vals, int64_t nvals, int64_t ngroups, uint64_t* __restrict__ enc) {
   using PT = PlaneTile<BW>;
+  static_assert(PT::kBytes <= kPackBufBytes, "plane image must fit the value buffer it replaces");
   extern __shared__ __align__(128) uint8_t smem[];
-  // [value tile 0][value tile 1][plane image of the tile]
-  const uint32_t tile0 = smem_u32(smem);
-  const uint32_t planes = tile0 + 2 * kTileValueBytes;
+  const uint32_t tile0 = smem_u32(smem);  // two buffers: value tile, then the plane image of the same tile
   const int t = threadIdx.x;
   const int64_t ntiles = (ngroups + PT::kGroups - 1) / PT::kGroups;
   const int64_t ntiles_full = ngroups / PT::kGroups;
@@ -309,7 +312,7 @@ pack_tma_kernel(const uint32_t* __restrict__ vals, int64_t nvals, int64_t ngroup
   // coalesced copy-in; rows past the end are zero (the reference leaves stale data there)
   auto fetch = [&](int buf, int64_t tl) {
     const int64_t v0 = tl * PT::kGroups * 64;
-    const uint32_t dst = tile0 + buf * kTileValueBytes;
+    const uint32_t dst = tile0 + buf * kPackBufBytes;
     if (v0 + PT::kGroups * 64 <= nvals) {  // whole tile inside the input (CTA-uniform)
       const uint32_t* src = vals + v0 + t * 4;
 #pragma unroll
@@ -332,51 +335,41 @@ pack_tma_kernel(const uint32_t* __restrict__ vals, int64_t nvals, int64_t ngroup
   int buf = 0;
   if ((int64_t)blockIdx.x < ntiles) fetch(0, blockIdx.x);
   for (int64_t tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
-    // the other buffer was last read in the previous iteration, which ended with __syncthreads
-    const int64_t nxt = tl + gridDim.x;
-    if (nxt < ntiles) {
-      fetch(buf ^ 1, nxt);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    // the previous tile's bulk stores must have finished READING the plane image before it is
-    // overwritten (only thread 0 issued them, so only it can wait on the bulk group)
+    cp_async_wait<0>();  // this tile's values have landed (this thread's copies; the barrier covers the rest)
+    // the other buffer holds the previous tile's plane image: its bulk stores must have finished
+    // READING it before the next tile's values overwrite it (only thread 0 issued them)
     if (t == 0) tma_store_wait_read<0>();
     __syncthreads();
-    const uint32_t tile = tile0 + buf * kTileValueBytes;
+    const int64_t nxt = tl + gridDim.x;
+    if (nxt < ntiles) fetch(buf ^ 1, nxt);
+    const uint32_t tile = tile0 + buf * kPackBufBytes;
     const bool full = tl < ntiles_full;
     const int row = full ? PT::thread_group(t) : t;
     const int64_t g = tl * PT::kGroups + row;
-    if (g < ngroups) {
-      uint32_t v[64];
+    uint32_t v[64];
 #pragma unroll
-      for (int c = 0; c < 16; ++c)
-        lds128u(tile_chunk_addr(tile, row, c), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-      uint64_t w[BW];
-      transpose_values_to_planes<BW>(v, w);
-      if (full) {
-        const uint32_t a = planes + PT::thread_off(t);
-#pragma unroll
-        for (int i = 0; i < BW; ++i) sts64(a + i * 8, w[i]);
-      } else {
-        uint64_t* dst = enc + g * BW;
-#pragma unroll
-        for (int i = 0; i < BW; ++i) dst[i] = w[i];
-      }
-    }
+    for (int c = 0; c < 16; ++c)
+      lds128u(tile_chunk_addr(tile, row, c), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    __syncthreads();  // every row is in registers: the buffer may now take the plane image
+    uint64_t w[BW];
+    transpose_values_to_planes<BW>(v, w);
     if (full) {
+      const uint32_t a = tile + PT::thread_off(t);
+#pragma unroll
+      for (int i = 0; i < BW; ++i) sts64(a + i * 8, w[i]);
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the bulk-copy engine
       __syncthreads();
       if (t == 0) {
         uint8_t* dst = reinterpret_cast<uint8_t*>(enc) + (uint64_t)tl * PT::kGroups * BW * 8;
 #pragma unroll
         for (int s = 0; s < 8; ++s)
-          tma_store_1d(dst + (uint64_t)s * PT::kSegBytes, planes + s * PT::kSegStride, PT::kSegBytes);
+          tma_store_1d(dst + (uint64_t)s * PT::kSegBytes, tile + s * PT::kSegStride, PT::kSegBytes);
         tma_store_commit();
       }
-    } else {
-      __syncthreads();
+    } else if (g < ngroups) {
+      uint64_t* dst = enc + g * BW;
+#pragma unroll
+      for (int i = 0; i < BW; ++i) dst[i] = w[i];
     }
     buf ^= 1;
   }
@@ -486,7 +479,7 @@ int launch_pack_u32(fle_ctx* ctx, const uint32_t* vals_dev, int64_t n, int bw, u
   }
   if (ctx->codec_variant != 0 && ((reinterpret_cast<uintptr_t>(enc_dev) | reinterpret_cast<uintptr_t>(vals_dev)) & 15) == 0) {
     PackFn fn = pack_tma_table_entry(bw, MakeSeq<32>::type());
-    const size_t smem = 2 * kTileValueBytes + (plane_tile_bytes(bw, MakeSeq<32>::type()) + 127) / 128 * 128;
+    const size_t smem = 2 * kPackBufBytes;
     int rc = raise_smem_limit(ctx, (const void*)fn, smem);
     if (rc != FLE_OK) return rc;
     const int per_sm = std::max<int>(1, std::min<int>(8, (int)((size_t)ctx->max_smem_per_sm / (smem + 1024))));
