@@ -725,7 +725,10 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
   if (mode == MODE_DIRECT || mode == MODE_STAGED || mode == MODE_JIT) off = round_up(off + (uint32_t)P.n_in_lits * 4u, 16);
   P.smem_masks_off = off;
   if (mode == MODE_STAGED) off += (uint32_t)P.npasses * 512u;
-  if (mode == MODE_IN_LOOKUP) off += std::max(4u, (1u << P.bw[0]) / 8u);  // membership table, 2^bw bits
+  if (mode == MODE_IN_LOOKUP) {  // membership table, 2^bw bits (+ 32 lane-private copies for bw <= 13)
+    const uint32_t tbytes = std::max(4u, (1u << P.bw[0]) / 8u);
+    off += P.bw[0] <= 13 ? tbytes * 33u : tbytes;
+  }
   P.smem_slots_off = off;
   if (mode == MODE_DIRECT || mode == MODE_STAGED) off += (uint32_t)P.nslots * kNT * 8u;
   off = round_up(off, 128);

@@ -6,7 +6,10 @@
 // dozen literals (profiles/: L = 256 at 2 % of the HBM roofline).  For bw <= 16 -- every column
 // the scanner can reach, since a dictionary holds at most 40000 entries (dict-encoding.h:157) --
 // this kernel instead
-//   1. builds a 2^bw-bit membership table of the literals in shared memory (<= 8 KB),
+//   1. builds a 2^bw-bit membership table of the literals in shared memory (<= 8 KB); for
+//      bw <= 13 the table is replicated per lane (word w of lane l at w * 128 + l * 4 bytes, <= 32 KB)
+//      so that the 64 data-dependent lookups of a group never conflict on a bank -- with one shared
+//      copy 32 random words hit ~3.5 words per bank and the LSU pipe, not HBM, bounded the kernel,
 //   2. transposes each group's planes into its 64 codes in registers (one 32x32 butterfly, both
 //      32-row halves at once, as in the unpack kernel),
 //   3. looks every code up in the table and assembles the 64-bit selection word directly in
@@ -19,6 +22,14 @@
 #include "fle_eval_common.cuh"
 
 namespace fle {
+
+// lane-private table copies (bank = lane) while they fit: 2^13 bits x 32 lanes = 32 KB
+template <int BW>
+struct InTable {
+  static constexpr bool kPerLane = BW <= 13;
+  static constexpr int kWords = BW <= 5 ? 1 : (1 << (BW - 5));
+  static constexpr int kShift = kPerLane ? 7 : 2;  // byte stride between consecutive table words
+};
 
 template <int BW, class L>
 __device__ __forceinline__ uint64_t in_lookup_group(const L& ld, uint32_t table) {
@@ -42,8 +53,8 @@ __device__ __forceinline__ uint64_t in_lookup_group(const L& ld, uint32_t table)
 #pragma unroll
   for (int k = 31; k >= 0; --k) {
     const uint32_t c0 = A[k] & 0xFFFFu, c1 = A[k] >> 16;
-    const uint32_t t0 = lds32(table + ((c0 >> 5) << 2));
-    const uint32_t t1 = lds32(table + ((c1 >> 5) << 2));
+    const uint32_t t0 = lds32(table + ((c0 >> 5) << InTable<BW>::kShift));
+    const uint32_t t1 = lds32(table + ((c1 >> 5) << InTable<BW>::kShift));
     lo = (lo << 1) | (__funnelshift_r(t0, 0u, c0) & 1u);  // funnel shift uses c & 31
     hi = (hi << 1) | (__funnelshift_r(t1, 0u, c1) & 1u);
   }
@@ -85,8 +96,11 @@ __global__ void __launch_bounds__(256) eval_in_kernel(const __grid_constant__ Ev
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t bar0 = smem_u32(smem + P.smem_bar_off);
   const uint32_t stage0 = smem_u32(smem + P.smem_stage_off);
-  uint32_t* table_ptr = reinterpret_cast<uint32_t*>(smem + P.smem_masks_off);  // 2^BW bits
-  const uint32_t table = smem_u32(table_ptr);
+  // [lane-private copies: kWords x 32 words (bw <= 13 only)][one shared copy: kWords words]
+  using IT = InTable<BW>;
+  uint32_t* rep_ptr = reinterpret_cast<uint32_t*>(smem + P.smem_masks_off);
+  uint32_t* table_ptr = rep_ptr + (IT::kPerLane ? IT::kWords * 32 : 0);
+  const uint32_t table = IT::kPerLane ? smem_u32(rep_ptr) + (threadIdx.x & 31u) * 4u : smem_u32(table_ptr);
   const int gpt = P.gpt;
   const int T = NT * gpt;
   const int seg_groups = T >> 3;
@@ -97,8 +111,7 @@ __global__ void __launch_bounds__(256) eval_in_kernel(const __grid_constant__ Ev
     for (int s = 0; s < nst; ++s) mbar_init(bar0 + s * 8, 1);
     mbar_fence_init();
   }
-  constexpr int kTableWords = BW <= 5 ? 1 : (1 << (BW - 5));
-  for (int i = threadIdx.x; i < kTableWords; i += NT) table_ptr[i] = 0;
+  for (int i = threadIdx.x; i < IT::kWords; i += NT) table_ptr[i] = 0;
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int s = 0; s < nst - 1; ++s) {
@@ -113,6 +126,10 @@ __global__ void __launch_bounds__(256) eval_in_kernel(const __grid_constant__ Ev
     atomicOr(&table_ptr[c >> 5], 1u << (c & 31));
   }
   __syncthreads();
+  if (IT::kPerLane) {
+    for (int i = threadIdx.x; i < IT::kWords * 32; i += NT) rep_ptr[i] = table_ptr[i >> 5];
+    __syncthreads();
+  }
   const uint64_t negmask = pd.neg[0] ? ~0ull : 0ull;
 
   const uint32_t seg = threadIdx.x & 7, jrow = threadIdx.x >> 3;
