@@ -897,7 +897,7 @@ int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, 
     }
     if (lp->jit_state == 1) {
       if (!lp->jit_entry)
-        lp->jit_entry = jit_lookup(lp->jit_plan.text, ctx->eval_jit == 2 || n >= ctx->eval_jit_min_rows);
+        lp->jit_entry = jit_lookup(lp->jit_plan.text, n, ctx->eval_jit_min_rows, ctx->eval_jit == 2);
       if (lp->jit_entry && lp->jit_entry->rc == FLE_OK) {
         jit_fill_args(lp->jit_plan, P, lp->in_lits, &lp->jit_args);
         int rc = FLE_E_UNSUPPORTED;

@@ -264,6 +264,7 @@ Nvrtc* nvrtc() {
 
 std::mutex g_mu;
 std::map<std::string, std::shared_ptr<JitEntry> > g_cache;
+std::map<std::string, int64_t> g_pending_rows;
 
 }  // namespace
 
@@ -310,11 +311,17 @@ int jit_compile_text(const std::string& program_text, std::vector<char>* cubin, 
   return FLE_OK;
 }
 
-std::shared_ptr<JitEntry> jit_lookup(const std::string& program_text, bool compile_if_missing) {
+std::shared_ptr<JitEntry> jit_lookup(const std::string& program_text, int64_t rows, int64_t min_rows, bool force) {
   std::lock_guard<std::mutex> lock(g_mu);
   auto it = g_cache.find(program_text);
   if (it != g_cache.end()) return it->second;
-  if (!compile_if_missing) return nullptr;
+  // not compiled yet: the shape pays for its compilation once the rows evaluated with it (this
+  // call included, all contexts of the process together) reach min_rows
+  if (g_pending_rows.size() > 1024) g_pending_rows.clear();  // bounded bookkeeping for one-off shapes
+  int64_t& seen = g_pending_rows[program_text];
+  seen += rows;
+  if (!force && seen < min_rows) return nullptr;
+  g_pending_rows.erase(program_text);
   std::shared_ptr<JitEntry> e = std::make_shared<JitEntry>();
   std::vector<char> cubin;
   int rc = jit_compile_text(program_text, &cubin, &e->log);

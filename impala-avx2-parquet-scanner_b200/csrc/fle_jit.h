@@ -36,7 +36,9 @@ void jit_fill_args(const JitPlan& plan, const EvalParams& P, const std::vector<u
                    std::vector<uint32_t>* args);
 // NVRTC only (no device needed): FLE_OK and the cubin, or an error and the compiler log
 int jit_compile_text(const std::string& program_text, std::vector<char>* cubin, std::string* log);
-// process-wide kernel cache; compiles and loads on a miss when asked to
-std::shared_ptr<JitEntry> jit_lookup(const std::string& program_text, bool compile_if_missing);
+// process-wide kernel cache.  A shape that has no kernel yet is compiled (synchronously) once
+// `force` is set or the rows evaluated with it so far, `rows` included, reach min_rows; until then
+// the answer is null and the caller interprets.
+std::shared_ptr<JitEntry> jit_lookup(const std::string& program_text, int64_t rows, int64_t min_rows, bool force);
 
 }  // namespace fle

@@ -106,8 +106,8 @@ int fle_ctx_sync(fle_ctx* ctx);
  * "eval_jit" (programs that are not one pass -- several columns, mixed AND/OR trees -- can run
  * on a kernel specialised for the program's SHAPE at run time, compiled once per shape with
  * NVRTC and cached process-wide; literals are not part of the shape.  0 = never, 1 [default] =
- * when the call covers at least "eval_jit_min_rows" rows (default 2^24) or the shape's kernel
- * already exists, 2 = always; without a usable libnvrtc.so.12 modes 0/1 use the interpreting
+ * once the rows evaluated with the shape in this process (this call included) reach
+ * "eval_jit_min_rows" (default 2^24; the compilation happens inside that call), 2 = always; without a usable libnvrtc.so.12 modes 0/1 use the interpreting
  * kernels and mode 2 fails with FLE_E_UNSUPPORTED),
  * "eval_stages", "eval_ctas_per_sm", "eval_gpt" (0 = auto), "codec_variant",
  * "h2d_chunk_rows". */

@@ -92,8 +92,8 @@ def test_trees_consts_in_lists(jit_ctx, oracle):
 
 
 def test_auto_mode_policy(ctx, oracle):
-    """eval_jit = 1: small calls of a shape nobody compiled keep to the interpreting kernels; a call
-    of at least eval_jit_min_rows rows compiles, after which small calls use the kernel too."""
+    """eval_jit = 1: a shape keeps to the interpreting kernels until the rows evaluated with it
+    reach eval_jit_min_rows; then it is compiled and every later call uses the kernel."""
     rng = np.random.default_rng(13)
     n = 64 * 3000
     _, cols = make_cols(oracle, rng, n, (9, 7), (500, 100))  # a shape no other test uses
@@ -105,7 +105,9 @@ def test_auto_mode_policy(ctx, oracle):
         j0 = ctx.get_option("jit_launches")
         bm, cnt = ctx.eval(cols, prog, n)
         assert (bm == want).all() and cnt == wcnt and ctx.get_option("jit_launches") == j0
-        ctx.set_option("eval_jit_min_rows", n)
+        ctx.set_option("eval_jit_min_rows", 3 * n)  # cumulative: this is the shape's third call
+        bm, cnt = ctx.eval(cols, prog, n)
+        assert (bm == want).all() and cnt == wcnt and ctx.get_option("jit_launches") == j0
         bm, cnt = ctx.eval(cols, prog, n)
         assert (bm == want).all() and cnt == wcnt and ctx.get_option("jit_launches") > j0
         ctx.set_option("eval_jit_min_rows", 1 << 24)
