@@ -30,6 +30,7 @@ EXPORTS = [
     "fle_unpack_u32_dev", "fle_eval", "fle_eval_dev", "fle_bitmap_count_dev", "fle_intersect_bitset",
     "fle_intersect_bitset_dev", "fle_bitmap_select_dev", "fle_gather_dev", "fle_sum_product_dev",
     "fle_page_parse", "fle_realign_dev", "fle_plain_eval_dev", "fle_dict_encode_dev", "fle_eval_codegen",
+    "fle_eval_sum_product_dev",
 ]
 
 
@@ -109,6 +110,8 @@ def load_library() -> C.CDLL:
     L.fle_bitmap_select_dev.argtypes = [vp, vp, i64, vp, i64, vp]
     L.fle_gather_dev.argtypes = [vp, vp, C.c_size_t, i32, vp, vp, i64, vp, i32, i32, vp]
     L.fle_sum_product_dev.argtypes = [vp, vp, i64, vp, vp, C.c_size_t, i32, vp, i32, vp, vp]
+    L.fle_eval_sum_product_dev.argtypes = [vp, C.POINTER(ColDesc), i32, C.POINTER(PredNode), i32, i64, i64, vp, i32, vp, i32,
+                                           vp, vp, vp]
     L.fle_eval_codegen.argtypes = [C.POINTER(ColDesc), i32, C.POINTER(PredNode), i32, i32, C.c_char_p, C.c_size_t,
                                    C.POINTER(C.c_size_t)]
     _lib = L
@@ -135,7 +138,7 @@ def _build_program(program: Sequence[tuple]):
     return nodes, keep
 
 
-def eval_codegen(bit_widths: Sequence[int], program: Sequence[tuple], compile=False):
+def eval_codegen(bit_widths: Sequence[int], program: Sequence[tuple], compile=False, agg_col: int = -1):
     """The run-time specialisation of a program's shape, no device needed (fle_eval_codegen).
     Returns (rc, text): the generated CUDA C++ (compile=False), the NVRTC log, '' on success
     (compile=True), or the cubin as bytes (compile=2)."""
@@ -147,7 +150,8 @@ def eval_codegen(bit_widths: Sequence[int], program: Sequence[tuple], compile=Fa
     cap = 1 << 20
     buf = C.create_string_buffer(cap)
     n = C.c_size_t(0)
-    rc = lib.fle_eval_codegen(cols, len(bit_widths), nodes, len(nodes), int(compile), buf, cap, C.byref(n))
+    rc = lib.fle_eval_codegen(cols, len(bit_widths), nodes, len(nodes), int(compile) | ((agg_col + 1) << 8), buf, cap,
+                              C.byref(n))
     if int(compile) == 2 and rc == OK:
         return rc, buf.raw[:n.value]
     return rc, buf.value.decode(errors="replace")
@@ -347,6 +351,21 @@ class FleContext:
         self._check(self.lib.fle_sum_product_dev(self.h, bitmap.data_ptr(), nrows, plain_i64.data_ptr(), words.data_ptr(),
                                                  words.numel() * words.element_size(), bw, dict_i64.data_ptr(),
                                                  dict_i64.numel(), out.data_ptr(), out.data_ptr() + 8))
+        return out
+
+    def eval_sum_product_dev(self, cols: Sequence, program: Sequence[tuple], n: int, plain_i64, code_col: int, dict_i64,
+                             first_row: int = 0, bitmap=None, out=None, prepared=None):
+        """Predicate program + SUM(plain_i64[r] * dict_i64[code of row r in cols[code_col]]) over the selected
+        rows in one pass.  out: int64[2] CUDA tensor = (sum, count); bitmap: optional int64 tensor."""
+        import torch
+        if prepared is None:
+            prepared = (self.make_col_descs(cols),) + _build_program(program)
+        descs, nodes, _keep = prepared
+        if out is None:
+            out = torch.zeros(2, dtype=torch.int64, device=plain_i64.device)
+        self._check(self.lib.fle_eval_sum_product_dev(
+            self.h, descs, len(cols), nodes, len(nodes), first_row, n, plain_i64.data_ptr(), code_col, dict_i64.data_ptr(),
+            dict_i64.numel(), bitmap.data_ptr() if bitmap is not None else None, out.data_ptr(), out.data_ptr() + 8))
         return out
 
     def page_parse(self, page: np.ndarray, max_def_level: int) -> PageLayout:

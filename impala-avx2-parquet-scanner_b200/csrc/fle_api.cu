@@ -518,7 +518,9 @@ int fle_eval_codegen(const fle_col_desc* cols, int ncols, const fle_pred_node* n
     lp.p.ncols = ncols;
     for (int c = 0; c < ncols; ++c) lp.p.bw[c] = (uint32_t)cols[c].bit_width;
     text.clear();
-    if (!jit_plan(lp.p, lp.in_lits, &lp.jit_plan)) {
+    const int agg_col = ((compile >> 8) & 0xff) - 1;
+    compile &= 0xff;
+    if (!jit_plan(lp.p, lp.in_lits, &lp.jit_plan, agg_col)) {
       rc = FLE_E_UNSUPPORTED;
       text = "program too large for a specialised kernel";
     } else if (compile) {
@@ -724,6 +726,37 @@ int fle_sum_product_dev(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nrows,
   if (reinterpret_cast<uintptr_t>(enc_dev) & 7) return set_error(ctx, FLE_E_ALIGN, "enc_dev must be 8-byte aligned");
   return launch_sum_product(ctx, bitmap_dev, nrows, plain_i64_dev, reinterpret_cast<const uint64_t*>(enc_dev),
                             bit_width, dict_i64_dev, ndict, sum_dev, count_dev);
+}
+
+int fle_eval_sum_product_dev(fle_ctx* ctx, const fle_col_desc* cols, int ncols, const fle_pred_node* nodes, int nnodes,
+                             int64_t first_row, int64_t n, const int64_t* plain_i64_dev, int code_col,
+                             const int64_t* dict_i64_dev, int ndict, uint64_t* bitmap_dev, int64_t* sum_dev,
+                             uint64_t* count_dev) {
+  FLE_CHECK_CTX(ctx);
+  if (!cols || !nodes || ncols < 1 || nnodes < 1) return set_error(ctx, FLE_E_INVALID, "empty program");
+  if (ncols > FLE_MAX_COLS) return set_error(ctx, FLE_E_UNSUPPORTED, "too many columns");
+  if (code_col < 0 || code_col >= ncols || !plain_i64_dev || !dict_i64_dev || !sum_dev || ndict < 0)
+    return set_error(ctx, FLE_E_INVALID, "bad aggregate arguments");
+  if (any_nullable(cols, ncols)) return set_error(ctx, FLE_E_UNSUPPORTED, "fused aggregate over nullable columns");
+  LoweredProgram lp;
+  int rc = prepare_eval(ctx, cols, ncols, nodes, nnodes, &lp);
+  if (rc != FLE_OK) return rc;
+  const AggSpec agg{plain_i64_dev, code_col, dict_i64_dev, ndict, sum_dev};
+  rc = launch_prepared(ctx, &lp, cols, ncols, first_row, n, bitmap_dev, count_dev, &agg);
+  if (rc != FLE_E_UNSUPPORTED || ctx->eval_jit == 2) return rc;
+  // no specialised kernel to be had: predicate pass, then the aggregate over its bitmap
+  const int64_t G = (n + 63) / 64;
+  if (!bitmap_dev) {
+    rc = ensure_stage(ctx, 0, (size_t)std::max<int64_t>(G, 1) * 8);
+    if (rc != FLE_OK) return rc;
+    bitmap_dev = static_cast<uint64_t*>(ctx->d_stage[0]);
+  }
+  rc = launch_prepared(ctx, &lp, cols, ncols, first_row, n, bitmap_dev, nullptr);
+  if (rc != FLE_OK) return rc;
+  const int bw = cols[code_col].bit_width;
+  const uint8_t* planes = reinterpret_cast<const uint8_t*>(cols[code_col].planes) + (uint64_t)(first_row / 64) * bw * 8u;
+  return launch_sum_product(ctx, bitmap_dev, n, plain_i64_dev, reinterpret_cast<const uint64_t*>(planes), bw,
+                            dict_i64_dev, ndict, sum_dev, count_dev);
 }
 
 // ---- page framing / PLAIN columns ------------------------------------------------------------

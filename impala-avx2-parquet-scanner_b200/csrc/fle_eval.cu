@@ -782,7 +782,7 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
     per_sm = std::max(per_sm, 1);
     grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * per_sm, (G + kNT - 1) / kNT));
   }
-  rc = ensure_scratch(ctx, grid, P.n_in_lits);
+  rc = ensure_scratch(ctx, P.agg_plain ? 2 * grid : grid, P.n_in_lits);
   if (rc != FLE_OK) return rc;
   P.partial = ctx->d_partial;
   P.ticket = ctx->d_ticket;
@@ -824,8 +824,10 @@ int prepare_eval(fle_ctx* ctx, const fle_col_desc* cols, int ncols, const fle_pr
 }
 
 int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, int ncols,
-                    int64_t first_row, int64_t n, uint64_t* bitmap_dev, uint64_t* count_dev) {
-  if (n < 0 || first_row < 0 || !bitmap_dev) return set_error(ctx, FLE_E_INVALID, "bad row range or null bitmap");
+                    int64_t first_row, int64_t n, uint64_t* bitmap_dev, uint64_t* count_dev, const AggSpec* agg) {
+  if (n < 0 || first_row < 0 || (!bitmap_dev && !agg)) return set_error(ctx, FLE_E_INVALID, "bad row range or null bitmap");
+  if (agg && (agg->col < 0 || agg->col >= ncols || !agg->plain || !agg->dict || !agg->sum_out))
+    return set_error(ctx, FLE_E_INVALID, "bad aggregate arguments");
   if (first_row & 63) return set_error(ctx, FLE_E_ALIGN, "first_row must be a multiple of 64");
   EvalParams P = lp->p;  // per-launch copy
   const int64_t G = (n + 63) / 64;
@@ -852,8 +854,15 @@ int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, 
   P.bitmap = bitmap_dev;
   P.count_out = count_dev;
   P.n_in_lits = (int)lp->in_lits.size();
+  if (agg) {
+    P.agg_plain = agg->plain;
+    P.agg_dict = agg->dict;
+    P.agg_ndict = agg->ndict;
+    P.agg_sum_out = agg->sum_out;
+  }
   if (G == 0) {
     if (count_dev) FLE_CUDA_TRY(ctx, cudaMemsetAsync(count_dev, 0, 8, ctx->stream));
+    if (agg) FLE_CUDA_TRY(ctx, cudaMemsetAsync(agg->sum_out, 0, 8, ctx->stream));
     return FLE_OK;
   }
   const bool staged_ok = ctx->eval_variant != 0 && aligned;
@@ -864,7 +873,7 @@ int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, 
   // one IN list on one dictionary-coded column: decode + membership lookup (fle_eval_in.cu)
   const bool in_lookup = P.npasses == 1 && P.ncombs == 0 && p0.type == PASS_IN && p0.slot[0] == 0 &&
                          P.bw[p0.col] <= 16 && (int)p0.lit[1] >= ctx->in_lookup_min;
-  if (staged_ok && in_lookup) {
+  if (staged_ok && in_lookup && !agg) {
     EvalParams P1 = P;
     const int c = p0.col;
     P1.ncols = 1;
@@ -874,7 +883,7 @@ int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, 
     const int rc = launch_program(ctx, P1, MODE_IN_LOOKUP, (int)P.bw[c]);
     if (rc != FLE_E_UNSUPPORTED) return rc;
   }
-  if (staged_ok && single_pass && ctx->eval_variant != 2) {
+  if (staged_ok && single_pass && ctx->eval_variant != 2 && !agg) {
     EvalParams P1 = P;  // only the pass's column is staged
     const int c = p0.col;
     P1.ncols = 1;
@@ -887,21 +896,27 @@ int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, 
   // Several passes, mixed AND/OR trees, IN lists inside larger programs: a kernel specialised
   // for the program's shape at run time (fle_jit.cu) when the call is large enough to pay for
   // one compilation, or the shape has been compiled before
-  if (ctx->eval_variant == 1 && ctx->eval_jit != 0) {
-    bool same_bw = lp->jit_state != 0;
+  if ((ctx->eval_variant == 1 || agg) && ctx->eval_jit != 0) {
+    const int agg_col = agg ? agg->col : -1;
+    bool same_bw = lp->jit_state != 0 && lp->jit_agg_col == agg_col;
     for (int c = 0; c < ncols && same_bw; ++c) same_bw = lp->jit_bw[c] == P.bw[c];
     if (!same_bw) {
-      lp->jit_state = jit_plan(P, lp->in_lits, &lp->jit_plan) ? 1 : -1;
+      lp->jit_state = jit_plan(P, lp->in_lits, &lp->jit_plan, agg_col) ? 1 : -1;
+      lp->jit_agg_col = agg_col;
       for (int c = 0; c < ncols; ++c) lp->jit_bw[c] = P.bw[c];
       lp->jit_entry.reset();
     }
     if (lp->jit_state == 1) {
       if (!lp->jit_entry)
-        lp->jit_entry = jit_lookup(lp->jit_plan.text, n, ctx->eval_jit_min_rows, ctx->eval_jit == 2);
+        lp->jit_entry = jit_lookup(lp->jit_plan.text, n, ctx->eval_jit_min_rows, ctx->eval_jit == 2 || agg);
       if (lp->jit_entry && lp->jit_entry->rc == FLE_OK) {
         jit_fill_args(lp->jit_plan, P, lp->in_lits, &lp->jit_args);
         int rc = FLE_E_UNSUPPORTED;
-        if (staged_ok) rc = launch_program(ctx, P, MODE_JIT, sum_bw, lp->jit_entry->kern, lp->jit_args.data(), true);
+        // With a fused aggregate the kernel is bound by the latency of the survivors' random loads,
+        // which only many resident warps hide: 64 warps/SM on global loads beat 8-16 warps/SM behind the
+        // TMA stages (Q6, 600 M rows: 0.43 vs 0.56 ms), unless the caller forces a stage count.
+        const bool want_staged = staged_ok && (!agg || ctx->eval_stages > 0);
+        if (want_staged) rc = launch_program(ctx, P, MODE_JIT, sum_bw, lp->jit_entry->kern, lp->jit_args.data(), true);
         if (rc == FLE_E_UNSUPPORTED)
           rc = launch_program(ctx, P, MODE_JIT, sum_bw, lp->jit_entry->kern, lp->jit_args.data(), false);
         if (rc != FLE_E_UNSUPPORTED) return rc;
@@ -912,6 +927,7 @@ int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, 
       return set_error(ctx, FLE_E_UNSUPPORTED, "eval_jit = 2: program too large for a specialised kernel");
     }
   }
+  if (agg) return FLE_E_UNSUPPORTED;  // only specialised kernels fuse the aggregate
   // Everything else: the TMA-staged generic kernel; the direct-load kernel remains for unaligned inputs, tiles that do
   // not fit in shared memory, and as eval_variant = 0.
   if (staged_ok) {

@@ -15,21 +15,33 @@ __device__ __forceinline__ uint64_t finish_word(uint64_t planes_order, int64_t g
   return r;
 }
 
-// block-wide popcount reduction + "last block sums" so the launch needs no memset/atomics
-// on the result slot.
-template <int NT>
-__device__ __forceinline__ void publish_count(const EvalParams& P, uint64_t cnt) {
+// block-wide reduction of the popcounts (and, for fused aggregates, of a second 64-bit sum kept in
+// partial[gridDim.x ...]) + "last block sums", so the launch needs no memset/atomics on the
+// result slots.
+template <int NT, bool WITH_SUM>
+__device__ __forceinline__ void publish_totals(const EvalParams& P, uint64_t cnt, uint64_t sum) {
   __shared__ uint64_t warp_cnt[NT / 32];
+  __shared__ uint64_t warp_sum[WITH_SUM ? NT / 32 : 1];
   __shared__ bool is_last;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = cnt;
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (WITH_SUM) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    warp_cnt[threadIdx.x >> 5] = cnt;
+    if (WITH_SUM) warp_sum[threadIdx.x >> 5] = sum;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
-    uint64_t t = 0;
+    uint64_t t = 0, u = 0;
 #pragma unroll
-    for (int w = 0; w < NT / 32; ++w) t += warp_cnt[w];
+    for (int w = 0; w < NT / 32; ++w) {
+      t += warp_cnt[w];
+      if (WITH_SUM) u += warp_sum[w];
+    }
     P.partial[blockIdx.x] = t;
+    if (WITH_SUM) P.partial[gridDim.x + blockIdx.x] = u;
     __threadfence();
     const unsigned int prev = atomicAdd(P.ticket, 1u);
     is_last = (prev == gridDim.x - 1);
@@ -37,22 +49,39 @@ __device__ __forceinline__ void publish_count(const EvalParams& P, uint64_t cnt)
   __syncthreads();
   if (is_last) {
     __threadfence();
-    uint64_t t = 0;
-    for (unsigned int i = threadIdx.x; i < gridDim.x; i += NT)
+    uint64_t t = 0, u = 0;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += NT) {
       t += *((volatile uint64_t*)&P.partial[i]);
+      if (WITH_SUM) u += *((volatile uint64_t*)&P.partial[gridDim.x + i]);
+    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    for (int o = 16; o > 0; o >>= 1) {
+      t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (WITH_SUM) u += __shfl_xor_sync(0xffffffffu, u, o);
+    }
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = t;
+    if ((threadIdx.x & 31) == 0) {
+      warp_cnt[threadIdx.x >> 5] = t;
+      if (WITH_SUM) warp_sum[threadIdx.x >> 5] = u;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-      uint64_t tot = 0;
+      uint64_t tot = 0, tot2 = 0;
 #pragma unroll
-      for (int w = 0; w < NT / 32; ++w) tot += warp_cnt[w];
+      for (int w = 0; w < NT / 32; ++w) {
+        tot += warp_cnt[w];
+        if (WITH_SUM) tot2 += warp_sum[w];
+      }
       if (P.count_out) *P.count_out = tot;
+      if (WITH_SUM && P.agg_sum_out) *P.agg_sum_out = (int64_t)tot2;
       *P.ticket = 0;  // self-reset for the next launch on this stream
     }
   }
+}
+
+template <int NT>
+__device__ __forceinline__ void publish_count(const EvalParams& P, uint64_t cnt) {
+  publish_totals<NT, false>(P, cnt, 0);
 }
 
 __device__ __forceinline__ void load_in_lits(const EvalParams& P, uint32_t* lits_smem) {

@@ -88,7 +88,115 @@ __device__ __forceinline__ uint64_t jit_in_list(const uint64_t (&w)[BW], const u
 //   jit_advance(a[])                          ... to its next group (NT/8 groups further)
 //   jit_global_addr(P, g, p[])                plane pointers of group g
 //   jit_eval_group(P, A, ld, lits_smem)       plane-order result word of one group
+//   [FLE_JIT_AGG]  kJitAggCol, kJitAggBw, jit_agg_code_smem(addr, sh), jit_agg_code_global(ptr, sh):
+//                  code of the row at plane bit sh of a group of the aggregate's column
 #include "fle_jit_program.h"
+
+#ifdef FLE_JIT_AGG
+namespace fle {
+// Fused aggregate: acc += plain[row] * dict[code of the row in the aggregate's dictionary column]
+// for every selected row.  A warp holds 32 groups' selection words; their survivors are walked in
+// FLATTENED order -- survivor t goes to lane t % 32 -- so that every lane keeps an independent
+// random load of plain[] in flight however the survivors are spread over the groups (one thread
+// looping over its own group's survivors serialises dependent loads and made the fused kernel
+// slower than two separate ones).  Each lane lists its own survivors as (owner lane, row) entries
+// at its exclusive prefix position in a per-warp shared array; lane t then simply reads entry t.
+// The code is picked out of the column's planes, which are still in the stage the predicate has
+// just read.  The load of plain[] is DEFERRED: the first two rounds park the price (still in
+// flight) and the dictionary value in registers and multiply them at the next call -- after another
+// group's predicate work -- so the load latency overlaps the scan instead of stalling the warp
+// (all warps of a CTA reach this point together, tile after tile).  Must be called by all 32 lanes.
+constexpr uint32_t kJitAggSlots = 128;  // survivors per 32 groups on the fast path (selectivity <~ 6 %)
+
+struct JitAggScratch {  // per warp, in shared memory
+  uint32_t prefix[33];
+  uint32_t addr[32];
+  uint64_t word[32];
+  int64_t group[32];
+  uint16_t slot[kJitAggSlots];
+};
+
+struct JitAggPending {
+  int64_t price[2], d[2];
+};
+
+__device__ __forceinline__ int jit_nth_set_bit64(uint64_t x, int n) {  // position of the n-th (0-based) set bit
+  const uint32_t lo = (uint32_t)x;
+  const int clo = __popc(lo);
+  if (n < clo) return (int)__fns(lo, 0, n + 1);
+  return 32 + (int)__fns((uint32_t)(x >> 32), 0, n - clo + 1);
+}
+
+template <bool STAGED>
+__device__ __forceinline__ uint32_t jit_agg_code_of(const EvalParams& P, const JitAggScratch& sc, int j, int64_t gg, int k) {
+  return STAGED ? jit_agg_code_smem(sc.addr[j], 63 - k)
+                : jit_agg_code_global(P.planes[kJitAggCol] + gg * kJitAggBw, 63 - k);
+}
+
+template <bool STAGED>
+__device__ __forceinline__ void jit_agg_warp(const EvalParams& P, JitAggScratch& sc, uint64_t r, int64_t g, uint32_t a,
+                                             int64_t& acc, JitAggPending& pend) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t mine = __popcll(r);
+  uint32_t incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (uint32_t)o) incl += y;
+  }
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total == 0) return;
+  __syncwarp();
+  sc.group[lane] = g;
+  if (STAGED) sc.addr[lane] = a;
+  if (total <= kJitAggSlots) {
+    uint32_t pos = incl - mine;
+    for (uint64_t m = r; m; m &= m - 1) sc.slot[pos++] = (uint16_t)((lane << 8) | (uint32_t)(__ffsll((long long)m) - 1));
+    __syncwarp();
+    acc += pend.price[0] * pend.d[0] + pend.price[1] * pend.d[1];  // parked by the previous call
+    pend.price[0] = pend.price[1] = 0;
+    pend.d[0] = pend.d[1] = 0;
+#pragma unroll
+    for (int round = 0; round < 2; ++round) {  // loads land straight in the parked registers
+      const uint32_t t = lane + 32u * round;
+      if (t < total) {
+        const uint32_t e = sc.slot[t];
+        const int j = (int)(e >> 8), k = (int)(e & 63u);
+        const int64_t gg = sc.group[j];
+        pend.price[round] = __ldg(P.agg_plain + gg * 64 + k);
+        const uint32_t code = jit_agg_code_of<STAGED>(P, sc, j, gg, k);
+        pend.d[round] = code < (uint32_t)P.agg_ndict ? __ldg(P.agg_dict + code) : 0;
+      }
+    }
+    for (uint32_t t = lane + 64; t < total; t += 32) {  // further rounds: consumed at once
+      const uint32_t e = sc.slot[t];
+      const int j = (int)(e >> 8), k = (int)(e & 63u);
+      const int64_t gg = sc.group[j];
+      const int64_t price = __ldg(P.agg_plain + gg * 64 + k);
+      const uint32_t code = jit_agg_code_of<STAGED>(P, sc, j, gg, k);
+      acc += price * (code < (uint32_t)P.agg_ndict ? __ldg(P.agg_dict + code) : 0);
+    }
+    return;
+  }
+  // dense selections: owner lane by binary search over the prefix sums, row by n-th set bit
+  sc.prefix[lane] = incl - mine;  // exclusive
+  if (lane == 31) sc.prefix[32] = total;
+  sc.word[lane] = r;
+  __syncwarp();
+  for (uint32_t t = lane; t < total; t += 32) {
+    int j = 0;  // prefix[j] <= t < prefix[j + 1]
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1)
+      if (sc.prefix[j + step] <= t) j += step;
+    const int k = jit_nth_set_bit64(sc.word[j], (int)(t - sc.prefix[j]));
+    const int64_t gg = sc.group[j];
+    const int64_t price = __ldg(P.agg_plain + gg * 64 + k);
+    const uint32_t code = jit_agg_code_of<STAGED>(P, sc, j, gg, k);
+    acc += price * (code < (uint32_t)P.agg_ndict ? __ldg(P.agg_dict + code) : 0);
+  }
+}
+}  // namespace fle
+#endif
 
 extern "C" __global__ void __launch_bounds__(256)
 fle_jit_kernel(const __grid_constant__ fle::EvalParams P, const __grid_constant__ fle::JitArgs A) {
@@ -120,6 +228,12 @@ fle_jit_kernel(const __grid_constant__ fle::EvalParams P, const __grid_constant_
   const uint32_t seg = threadIdx.x & 7, jrow = threadIdx.x >> 3;
   const int64_t thread_g = (int64_t)seg * seg_groups + jrow;
   uint64_t cnt = 0;
+#ifdef FLE_JIT_AGG
+  int64_t acc = 0;
+  __shared__ JitAggScratch agg_scratch[NT / 32];
+  JitAggScratch& sc = agg_scratch[threadIdx.x >> 5];
+  JitAggPending pend{{0, 0}, {0, 0}};
+#endif
   int stage = 0;
   uint32_t parity = 0;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -136,8 +250,11 @@ fle_jit_kernel(const __grid_constant__ fle::EvalParams P, const __grid_constant_
     int64_t g = tile * T + thread_g;
     for (int q = 0; q < gpt; ++q) {
       const uint64_t r = finish_word(jit_eval_group(P, A, ld, lits_smem), g, P.nrows);
-      P.bitmap[g] = r;
+      if (P.bitmap) P.bitmap[g] = r;
       cnt += __popcll(r);
+#ifdef FLE_JIT_AGG
+      jit_agg_warp<true>(P, sc, r, g, ld.a[kJitAggCol], acc, pend);
+#endif
       jit_advance(ld.a);
       g += NT / 8;
     }
@@ -147,6 +264,21 @@ fle_jit_kernel(const __grid_constant__ fle::EvalParams P, const __grid_constant_
     }
   }
   // ragged remainder (< T groups), planes straight from global memory
+#ifdef FLE_JIT_AGG
+  // (warp-uniform trip count: the aggregate's warp-wide walk needs all 32 lanes)
+  for (int64_t g = ntiles * T + (int64_t)blockIdx.x * NT + threadIdx.x; g - (threadIdx.x & 31) < P.ngroups;
+       g += (int64_t)gridDim.x * NT) {
+    uint64_t r = 0;
+    if (g < P.ngroups) {
+      JitGlobalGroup<kJitNCols> ld;
+      jit_global_addr(P, g, ld.p);
+      r = finish_word(jit_eval_group(P, A, ld, lits_smem), g, P.nrows);
+      if (P.bitmap) P.bitmap[g] = r;
+      cnt += __popcll(r);
+    }
+    jit_agg_warp<false>(P, sc, r, g, 0u, acc, pend);
+  }
+#else
   for (int64_t g = ntiles * T + (int64_t)blockIdx.x * NT + threadIdx.x; g < P.ngroups;
        g += (int64_t)gridDim.x * NT) {
     JitGlobalGroup<kJitNCols> ld;
@@ -155,5 +287,11 @@ fle_jit_kernel(const __grid_constant__ fle::EvalParams P, const __grid_constant_
     P.bitmap[g] = r;
     cnt += __popcll(r);
   }
+#endif
+#ifdef FLE_JIT_AGG
+  acc += pend.price[0] * pend.d[0] + pend.price[1] * pend.d[1];
+  publish_totals<NT, true>(P, cnt, (uint64_t)acc);
+#else
   publish_count<NT>(P, cnt);
+#endif
 }

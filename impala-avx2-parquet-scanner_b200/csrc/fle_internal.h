@@ -24,6 +24,7 @@ struct LoweredProgram {
   JitPlan jit_plan;
   uint32_t jit_bw[FLE_MAX_COLS] = {0};  // bit widths jit_plan was made for
   int jit_state = 0;                     // 0 not planned, 1 planned, -1 shape not supported
+  int jit_agg_col = -1;                  // aggregate column jit_plan was made for (-1: none)
   std::shared_ptr<JitEntry> jit_entry;
   std::vector<uint32_t> jit_args;
 };
@@ -97,8 +98,19 @@ int ensure_scratch(fle_ctx* ctx, int nblocks, int n_in_lits);
 int prepare_eval(fle_ctx* ctx, const fle_col_desc* cols, int ncols, const fle_pred_node* nodes,
                  int nnodes, LoweredProgram* lp);
 // ... then launch it any number of times on device-resident columns
+// agg (optional): SUM(plain[r] * dict[code of row r in column col]) over the selected rows, fused into
+// a specialised kernel; FLE_E_UNSUPPORTED when no such kernel can be had (the caller then runs
+// eval + launch_sum_product).  bitmap_dev may be null only with agg.
+struct AggSpec {
+  const int64_t* plain;
+  int col;
+  const int64_t* dict;
+  int ndict;
+  int64_t* sum_out;
+};
 int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols_dev, int ncols,
-                    int64_t first_row, int64_t n, uint64_t* bitmap_dev, uint64_t* count_dev);
+                    int64_t first_row, int64_t n, uint64_t* bitmap_dev, uint64_t* count_dev,
+                    const AggSpec* agg = nullptr);
 int launch_eval(fle_ctx* ctx, const fle_col_desc* cols_dev, int ncols, const fle_pred_node* nodes,
                 int nnodes, int64_t first_row, int64_t n, uint64_t* bitmap_dev,
                 uint64_t* count_dev);

@@ -35,7 +35,7 @@ void emit_fold(std::string& t, int slot, int fold, const std::string& v) {
 
 }  // namespace
 
-bool jit_plan(const EvalParams& P, const std::vector<uint32_t>& in_lits, JitPlan* plan) {
+bool jit_plan(const EvalParams& P, const std::vector<uint32_t>& in_lits, JitPlan* plan, int agg_col) {
   JitPlan& J = *plan;
   J.text.clear();
   J.chains.clear();
@@ -189,7 +189,37 @@ bool jit_plan(const EvalParams& P, const std::vector<uint32_t>& in_lits, JitPlan
     snprintf(b, sizeof(b), "  s%d = s%d %s s%d;\n", cd.dst, cd.a, cd.op == FOLD_AND ? "&" : "|", cd.b);
     t += b;
   }
-  t += "  return s0;\n}\n}  // namespace fle\n";
+  t += "  return s0;\n}\n";
+  if (agg_col >= 0) {
+    if (agg_col >= P.ncols) return false;
+    const int bw = (int)P.bw[agg_col];
+    snprintf(b, sizeof(b), "#define FLE_JIT_AGG 1\nconstexpr int kJitAggCol = %d;\nconstexpr int kJitAggBw = %d;\n", agg_col, bw);
+    t += b;
+    // code of the row at plane bit `sh` of one group of the aggregate's column, planes in shared / global memory
+    t += "__device__ __forceinline__ uint32_t jit_agg_code_smem(uint32_t a, int sh) {\n  uint32_t code = 0;\n";
+    if (bw % 2 == 0) {
+      t += "  uint64_t w0, w1;\n";
+      for (int i = 0; i < bw; i += 2) {
+        snprintf(b, sizeof(b),
+                 "  lds128(a + %d, w0, w1);\n  code |= (uint32_t)((w0 >> sh) & 1ull) << %d;\n"
+                 "  code |= (uint32_t)((w1 >> sh) & 1ull) << %d;\n", i * 8, i, i + 1);
+        t += b;
+      }
+    } else {
+      for (int i = 0; i < bw; ++i) {
+        snprintf(b, sizeof(b), "  code |= (uint32_t)((lds64(a + %d) >> sh) & 1ull) << %d;\n", i * 8, i);
+        t += b;
+      }
+    }
+    t += "  return code;\n}\n"
+         "__device__ __forceinline__ uint32_t jit_agg_code_global(const uint64_t* p, int sh) {\n  uint32_t code = 0;\n";
+    for (int i = 0; i < bw; ++i) {
+      snprintf(b, sizeof(b), "  code |= (uint32_t)((__ldg(p + %d) >> sh) & 1ull) << %d;\n", i, i);
+      t += b;
+    }
+    t += "  return code;\n}\n";
+  }
+  t += "}  // namespace fle\n";
   return true;
 }
 

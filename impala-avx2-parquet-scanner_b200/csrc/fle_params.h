@@ -98,7 +98,12 @@ struct EvalParams {
   uint64_t* count_out;  // may be null
   const uint32_t* in_lits;
   int32_t n_in_lits;
-  int32_t pad;
+  int32_t agg_ndict;
+  // optional aggregate fused into a specialised kernel (fle_eval_sum_product_dev):
+  // *agg_sum_out = SUM over selected rows r of agg_plain[r] * agg_dict[code of row r in column agg_col]
+  const int64_t* agg_plain;
+  const int64_t* agg_dict;
+  int64_t* agg_sum_out;
   PassDesc passes[kMaxPasses];
   CombDesc combs[kMaxCombs];
 };

@@ -175,7 +175,8 @@ int fle_eval_dev(fle_ctx* ctx, const fle_col_desc* cols_dev, int ncols,
  * for the program's shape (compile == 0) or compiles it for sm_100a with NVRTC and writes the
  * compiler log, empty on success (compile == 1), NUL-terminated, into out[0..cap); *len (optional)
  * receives the untruncated length.  compile == 2 writes the sm_100a cubin instead (binary; for
- * cuobjdump -sass).  Only cols[i].bit_width is read.  FLE_E_UNSUPPORTED: the
+ * cuobjdump -sass).  Bits 8..15 of `compile`: 1 + code_col to generate the fused aggregate of
+ * fle_eval_sum_product_dev as well, 0 for none.  Only cols[i].bit_width is read.  FLE_E_UNSUPPORTED: the
  * program has no specialised form (it is a single pass, or too large) or NVRTC is missing.
  * This is the step Impala's LLVM codegen performs for the expression trees the reference
  * interprets (simple-predicates.h:113-163). */
@@ -215,6 +216,22 @@ int fle_sum_product_dev(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nrows,
                         const int64_t* plain_i64_dev, const uint8_t* enc_dev, size_t enc_len,
                         int bit_width, const int64_t* dict_i64_dev, int ndict, int64_t* sum_dev,
                         uint64_t* count_dev);
+
+/* fle_eval_dev + fle_sum_product_dev in ONE pass (the whole of TPC-H Q6 below the final
+ * all-reduce): evaluates the program over rows [first_row, first_row + n) and accumulates
+ *   *sum_dev = SUM over selected rows r of plain_i64_dev[r - first_row] * dict_i64_dev[code(r)]
+ * where code(r) is the row's code in cols_dev[code_col] (exact int64; a code >= ndict counts 0),
+ * *count_dev (optional) = number of selected rows, bitmap_out_dev (optional, may be NULL) as
+ * fle_eval_dev.  Runs on a kernel specialised for the program shape ("eval_jit"): the survivors'
+ * codes are picked out of the planes the predicate has just read from shared memory, so the
+ * aggregate costs one 8-byte load per survivor instead of a second pass.  Without a usable NVRTC
+ * (or with eval_jit = 0) the same result comes from the two separate kernels.  Columns must be
+ * non-nullable. */
+int fle_eval_sum_product_dev(fle_ctx* ctx, const fle_col_desc* cols_dev, int ncols,
+                             const fle_pred_node* postfix, int nnodes, int64_t first_row, int64_t n,
+                             const int64_t* plain_i64_dev, int code_col, const int64_t* dict_i64_dev,
+                             int ndict, uint64_t* bitmap_out_dev, int64_t* sum_dev,
+                             uint64_t* count_dev);
 
 /* ---- page framing and PLAIN-encoded columns ("next" rows) ------------- */
 /* Byte layout of one uncompressed data-page body (hdfs-parquet-table-writer.cc:567-575,

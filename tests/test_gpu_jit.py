@@ -194,3 +194,47 @@ def test_random_programs_all_paths_vs_oracle(ctx, oracle, seed):
     finally:
         ctx.set_option("eval_variant", 1)
         ctx.set_option("eval_jit", 1)
+
+
+@pytest.mark.parametrize("jit", [1, 0])
+@pytest.mark.parametrize("n", [64 * 50000 + 41, 64 * 256 * 2, 37])
+def test_fused_scan_and_aggregate(ctx, jit, n):
+    """fle_eval_sum_product_dev (predicate + SUM(price * dict[discount]) in one specialised kernel)
+    against torch on the decoded columns -- exact int64 -- and against the two-kernel path (jit=0)."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(n)
+    ship = torch.randint(0, 2526, (n,), generator=g, device="cuda", dtype=torch.int32)
+    disc = torch.randint(0, 11, (n,), generator=g, device="cuda", dtype=torch.int32)
+    qty = torch.randint(0, 50, (n,), generator=g, device="cuda", dtype=torch.int32)
+    price = torch.randint(90_000, 10_500_000, (n,), generator=g, device="cuda", dtype=torch.int64)
+    cols = [(ctx.pack_dev(ship, 12), 12), (ctx.pack_dev(disc, 4), 4), (ctx.pack_dev(qty, 6), 6)]
+    dict_disc = torch.arange(0, 11, device="cuda", dtype=torch.int64) * 100 + 7
+    ctx.set_option("eval_jit", jit)
+    try:
+        for lo, hi in ((730, 1094), (0, 2525), (2000, 10)):
+            prog = q6(lo, hi)
+            mask = (ship >= lo) & (ship <= hi) & (disc >= 5) & (disc <= 7) & (qty < 23)
+            want = int((price[mask] * dict_disc[disc[mask].long()]).sum().item())
+            j0 = ctx.get_option("jit_launches")
+            bm = torch.zeros((n + 63) // 64, dtype=torch.int64, device="cuda")
+            out = ctx.eval_sum_product_dev(cols, prog, n, price, 1, dict_disc, bitmap=bm)
+            torch.cuda.synchronize()
+            assert int(out[0].item()) == want and int(out[1].item()) == int(mask.sum().item()), (lo, hi)
+            assert (ctx.get_option("jit_launches") > j0) == (jit != 0)
+            bm2, cnt2 = ctx.eval_dev(cols, prog, n)
+            assert torch.equal(bm, bm2)
+            out2 = ctx.eval_sum_product_dev(cols, prog, n, price, 1, dict_disc)  # no bitmap wanted
+            torch.cuda.synchronize()
+            assert torch.equal(out, out2)
+        # rows [128, n) of the same columns; a dictionary shorter than the codes (code >= ndict counts 0)
+        if n > 128:
+            mask = (ship >= 730) & (ship <= 1094) & (disc >= 5) & (disc <= 7) & (qty < 23)
+            mask[:128] = False
+            short = dict_disc[:7]
+            dd = torch.where(disc < 7, short[disc.clamp(max=6).long()], torch.zeros_like(price))
+            want = int((price[mask] * dd[mask]).sum().item())
+            out = ctx.eval_sum_product_dev(cols, q6(), n - 128, price[128:], 1, short, first_row=128)
+            torch.cuda.synchronize()
+            assert int(out[0].item()) == want and int(out[1].item()) == int(mask.sum().item())
+    finally:
+        ctx.set_option("eval_jit", 1)

@@ -85,3 +85,18 @@ def test_specialised_sass_is_register_resident():
         os.unlink(f.name)
     assert "fle_jit_kernel" in res and "STACK:0" in res and "LOCAL:0" in res  # no spills
     assert "UBLKCP" in sass and "SYNCS" in sass  # TMA bulk copies + mbarrier waits
+
+
+def test_fused_aggregate_shape_compiles():
+    ok, why = nvrtc_available()
+    if not ok:
+        pytest.skip("NVRTC unavailable here: " + why[:200])
+    rc, text = eval_codegen([12, 4, 6], Q6, agg_col=1)
+    assert rc == OK and "#define FLE_JIT_AGG 1" in text and "jit_agg_code_smem" in text
+    assert "kJitAggCol = 1" in text and "kJitAggBw = 4" in text
+    rc, log = eval_codegen([12, 4, 6], Q6, compile=True, agg_col=1)
+    assert rc == OK, log[:4000]
+    rc, log = eval_codegen([12, 5, 7], Q6, compile=True, agg_col=2)  # odd width
+    assert rc == OK, log[:4000]
+    rc, _ = eval_codegen([12, 4, 6], Q6, agg_col=5)
+    assert rc != OK
