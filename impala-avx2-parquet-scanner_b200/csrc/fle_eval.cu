@@ -716,6 +716,7 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
     const uint32_t target = mode == MODE_STAGED ? 32u * 1024u : (mode == MODE_JIT ? 88u * 1024u : 40u * 1024u);
     if (gpt <= 0) gpt = (int)std::max<uint32_t>(1, std::min<uint32_t>(8, (target + bytes_per_gpt / 2) / bytes_per_gpt));
     gpt = std::min(gpt, 8);
+    if (mode == MODE_JIT && P.agg_plain) gpt = kJitAggGpt;  // compiled into the kernel (fle_eval_jit.cuh)
   }
   // shared memory carve-up: [mbarriers][IN literals][literal masks][slots][stages]
   uint32_t off = 0;
@@ -912,9 +913,9 @@ int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, 
       if (lp->jit_entry && lp->jit_entry->rc == FLE_OK) {
         jit_fill_args(lp->jit_plan, P, lp->in_lits, &lp->jit_args);
         int rc = FLE_E_UNSUPPORTED;
-        // With a fused aggregate the kernel is bound by the latency of the survivors' random loads,
-        // which only many resident warps hide: 64 warps/SM on global loads beat 8-16 warps/SM behind the
-        // TMA stages (Q6, 600 M rows: 0.43 vs 0.56 ms), unless the caller forces a stage count.
+        // With a fused aggregate the survivors' random loads and the warp-wide survivor walk want many
+        // resident warps: 64 warps/SM on global loads beat 8 warps/SM behind the TMA stages (Q6, 600 M
+        // rows: 0.41 vs 0.48 ms; DRAM traffic bound 0.37 ms), unless the caller forces a stage count.
         const bool want_staged = staged_ok && (!agg || ctx->eval_stages > 0);
         if (want_staged) rc = launch_program(ctx, P, MODE_JIT, sum_bw, lp->jit_entry->kern, lp->jit_args.data(), true);
         if (rc == FLE_E_UNSUPPORTED)

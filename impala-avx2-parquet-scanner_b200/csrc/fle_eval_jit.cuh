@@ -163,7 +163,7 @@ __device__ __forceinline__ void jit_agg_warp(const EvalParams& P, JitAggScratch&
         const uint32_t e = sc.slot[t];
         const int j = (int)(e >> 8), k = (int)(e & 63u);
         const int64_t gg = sc.group[j];
-        pend.price[round] = __ldg(P.agg_plain + gg * 64 + k);
+        pend.price[round] = (int64_t)ldg_gather64(P.agg_plain + gg * 64 + k);
         const uint32_t code = jit_agg_code_of<STAGED>(P, sc, j, gg, k);
         pend.d[round] = code < (uint32_t)P.agg_ndict ? __ldg(P.agg_dict + code) : 0;
       }
@@ -172,7 +172,7 @@ __device__ __forceinline__ void jit_agg_warp(const EvalParams& P, JitAggScratch&
       const uint32_t e = sc.slot[t];
       const int j = (int)(e >> 8), k = (int)(e & 63u);
       const int64_t gg = sc.group[j];
-      const int64_t price = __ldg(P.agg_plain + gg * 64 + k);
+      const int64_t price = (int64_t)ldg_gather64(P.agg_plain + gg * 64 + k);
       const uint32_t code = jit_agg_code_of<STAGED>(P, sc, j, gg, k);
       acc += price * (code < (uint32_t)P.agg_ndict ? __ldg(P.agg_dict + code) : 0);
     }
@@ -190,7 +190,7 @@ __device__ __forceinline__ void jit_agg_warp(const EvalParams& P, JitAggScratch&
       if (sc.prefix[j + step] <= t) j += step;
     const int k = jit_nth_set_bit64(sc.word[j], (int)(t - sc.prefix[j]));
     const int64_t gg = sc.group[j];
-    const int64_t price = __ldg(P.agg_plain + gg * 64 + k);
+    const int64_t price = (int64_t)ldg_gather64(P.agg_plain + gg * 64 + k);
     const uint32_t code = jit_agg_code_of<STAGED>(P, sc, j, gg, k);
     acc += price * (code < (uint32_t)P.agg_ndict ? __ldg(P.agg_dict + code) : 0);
   }
@@ -232,7 +232,7 @@ fle_jit_kernel(const __grid_constant__ fle::EvalParams P, const __grid_constant_
   int64_t acc = 0;
   __shared__ JitAggScratch agg_scratch[NT / 32];
   JitAggScratch& sc = agg_scratch[threadIdx.x >> 5];
-  JitAggPending pend{{0, 0}, {0, 0}};
+  JitAggPending pend[FLE_JIT_GPT] = {};
 #endif
   int stage = 0;
   uint32_t parity = 0;
@@ -248,16 +248,28 @@ fle_jit_kernel(const __grid_constant__ fle::EvalParams P, const __grid_constant_
     JitSmemGroup<kJitNCols> ld;
     jit_stage_addr(P, stage0 + stage * P.stage_bytes, seg, jrow, ld.a);
     int64_t g = tile * T + thread_g;
-    for (int q = 0; q < gpt; ++q) {
+#ifdef FLE_JIT_AGG
+    // fixed trip count (the host launches aggregate kernels with gpt == FLE_JIT_GPT): the survivors
+    // parked by group q of this tile are consumed by group q of the NEXT tile, a whole tile period
+    // (~2 us) later, which covers the latency of their random loads
+#pragma unroll
+    for (int q = 0; q < FLE_JIT_GPT; ++q) {
       const uint64_t r = finish_word(jit_eval_group(P, A, ld, lits_smem), g, P.nrows);
       if (P.bitmap) P.bitmap[g] = r;
       cnt += __popcll(r);
-#ifdef FLE_JIT_AGG
-      jit_agg_warp<true>(P, sc, r, g, ld.a[kJitAggCol], acc, pend);
-#endif
+      jit_agg_warp<true>(P, sc, r, g, ld.a[kJitAggCol], acc, pend[q]);
       jit_advance(ld.a);
       g += NT / 8;
     }
+#else
+    for (int q = 0; q < gpt; ++q) {
+      const uint64_t r = finish_word(jit_eval_group(P, A, ld, lits_smem), g, P.nrows);
+      P.bitmap[g] = r;
+      cnt += __popcll(r);
+      jit_advance(ld.a);
+      g += NT / 8;
+    }
+#endif
     if (++stage == nst) {
       stage = 0;
       parity ^= 1u;
@@ -276,7 +288,7 @@ fle_jit_kernel(const __grid_constant__ fle::EvalParams P, const __grid_constant_
       if (P.bitmap) P.bitmap[g] = r;
       cnt += __popcll(r);
     }
-    jit_agg_warp<false>(P, sc, r, g, 0u, acc, pend);
+    jit_agg_warp<false>(P, sc, r, g, 0u, acc, pend[0]);
   }
 #else
   for (int64_t g = ntiles * T + (int64_t)blockIdx.x * NT + threadIdx.x; g < P.ngroups;
@@ -289,7 +301,8 @@ fle_jit_kernel(const __grid_constant__ fle::EvalParams P, const __grid_constant_
   }
 #endif
 #ifdef FLE_JIT_AGG
-  acc += pend.price[0] * pend.d[0] + pend.price[1] * pend.d[1];
+#pragma unroll
+  for (int q = 0; q < FLE_JIT_GPT; ++q) acc += pend[q].price[0] * pend[q].d[0] + pend[q].price[1] * pend[q].d[1];
   publish_totals<NT, true>(P, cnt, (uint64_t)acc);
 #else
   publish_count<NT>(P, cnt);

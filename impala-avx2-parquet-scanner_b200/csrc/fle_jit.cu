@@ -193,7 +193,9 @@ bool jit_plan(const EvalParams& P, const std::vector<uint32_t>& in_lits, JitPlan
   if (agg_col >= 0) {
     if (agg_col >= P.ncols) return false;
     const int bw = (int)P.bw[agg_col];
-    snprintf(b, sizeof(b), "#define FLE_JIT_AGG 1\nconstexpr int kJitAggCol = %d;\nconstexpr int kJitAggBw = %d;\n", agg_col, bw);
+    snprintf(b, sizeof(b),
+             "#define FLE_JIT_AGG 1\n#define FLE_JIT_GPT %d\nconstexpr int kJitAggCol = %d;\nconstexpr int kJitAggBw = %d;\n",
+             kJitAggGpt, agg_col, bw);
     t += b;
     // code of the row at plane bit `sh` of one group of the aggregate's column, planes in shared / global memory
     t += "__device__ __forceinline__ uint32_t jit_agg_code_smem(uint32_t a, int sh) {\n  uint32_t code = 0;\n";
@@ -214,7 +216,7 @@ bool jit_plan(const EvalParams& P, const std::vector<uint32_t>& in_lits, JitPlan
     t += "  return code;\n}\n"
          "__device__ __forceinline__ uint32_t jit_agg_code_global(const uint64_t* p, int sh) {\n  uint32_t code = 0;\n";
     for (int i = 0; i < bw; ++i) {
-      snprintf(b, sizeof(b), "  code |= (uint32_t)((__ldg(p + %d) >> sh) & 1ull) << %d;\n", i, i);
+      snprintf(b, sizeof(b), "  code |= (uint32_t)((ldg_gather64(p + %d) >> sh) & 1ull) << %d;\n", i, i);
       t += b;
     }
     t += "  return code;\n}\n";

@@ -8,6 +8,9 @@
 
 namespace fle {
 
+// groups per thread per tile that kernels with a fused aggregate are generated (and launched) with
+constexpr int kJitAggGpt = 2;
+
 struct JitChain {
   bool lt;       // borrow chain ('<' family) or equality chain
   int bw;

@@ -118,7 +118,7 @@ __device__ __forceinline__ uint32_t code_at(const uint64_t* __restrict__ planes,
   const uint64_t* g = planes + (uint64_t)(r >> 6) * bw;
   const int sh = 63 - (int)(r & 63);
   uint32_t v = 0;
-  for (int i = 0; i < bw; ++i) v |= (uint32_t)((__ldg(g + i) >> sh) & 1ull) << i;
+  for (int i = 0; i < bw; ++i) v |= (uint32_t)((ldg_gather64(g + i) >> sh) & 1ull) << i;
   return v;
 }
 
@@ -193,12 +193,12 @@ sum_product_kernel(const uint64_t* __restrict__ bm, int64_t nrows, const int64_t
         if (prefix_s[wid][j + step] <= t) j += step;
       const int b = nth_set_bit64(word_s[wid][j], (int)(t - prefix_s[wid][j]));  // row b of group g0+j
       const int64_t gg = g0 + j;
-      const long long pv = __ldg(plain + gg * 64 + b);
+      const long long pv = (long long)ldg_gather64(plain + gg * 64 + b);
       const uint64_t* gp = planes + (uint64_t)gg * bw;
       const int sh = 63 - b;
       uint32_t code = 0;
 #pragma unroll 4
-      for (int i = 0; i < bw; ++i) code |= (uint32_t)((__ldg(gp + i) >> sh) & 1ull) << i;
+      for (int i = 0; i < bw; ++i) code |= (uint32_t)((ldg_gather64(gp + i) >> sh) & 1ull) << i;
       const long long d = code < (uint32_t)ndict ? __ldg(dict + code) : 0;
       s += pv * d;
     }

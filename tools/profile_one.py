@@ -36,6 +36,15 @@ if case == "q6":
             (AND, None, None), (LT, 2, 23), (AND, None, None)]
     for _ in range(reps):
         ctx.eval_dev(cols, prog, n, bitmap=bm, count=cnt)
+elif case == "q6agg":
+    cols = [(col(2526, 12)[1], 12), (col(11, 4)[1], 4), (col(50, 6)[1], 6)]
+    prog = [(GE, 0, 730), (LE, 0, 1094), (AND, None, None), (GE, 1, 5), (LE, 1, 7), (AND, None, None),
+            (AND, None, None), (LT, 2, 23), (AND, None, None)]
+    price = torch.randint(90_000, 10_500_000, (n,), generator=g, device="cuda", dtype=torch.int64)
+    dd = torch.arange(0, 11, device="cuda", dtype=torch.int64)
+    for _ in range(reps):
+        out = ctx.eval_sum_product_dev(cols, prog, n, price, 1, dd, bitmap=bm)
+    cnt = out[1:2]
 elif case == "or_variant":
     cols = [(col(7, 3)[1], 3), (col(4, 2)[1], 2), (col(50, 6)[1], 6)]
     prog = [(IN, 0, [1, 4]), (EQ, 1, 2), (OR, None, None), (LT, 2, 23), (AND, None, None)]
