@@ -73,59 +73,68 @@ struct PlainParams {
   uint64_t* partial;
   unsigned int* ticket;
   uint64_t* count_out;
-  const void* lits;  // device copy of the literals
+  const void* lits;  // device copy of the literals (lists longer than kPlainInlineLits)
+  uint64_t lit_inline[8];  // ... shorter lists travel in the parameter block: no staging copy, no host sync
 };
+constexpr int kPlainInlineLits = 8;
 
-template <typename T>
-__device__ __forceinline__ bool plain_cmp(int op, T a, T b) {  // a OP b
-  switch (op) {
-    case FLE_OP_EQ: return a == b;
-    case FLE_OP_LT: return a < b;
-    case FLE_OP_LE: return a <= b;
-    case FLE_OP_GT: return a > b;
-    case FLE_OP_GE: return a >= b;
-  }
-  return false;
+// value OP literal, OP fixed at compile time (the reference's operand order `literal OP value` is
+// the mirrored operator, chosen on the host)
+template <int OP, typename T>
+__device__ __forceinline__ bool plain_test(T v, T lit0, const T* lits_s, int nlits) {
+  if (OP == FLE_OP_EQ) return v == lit0;
+  if (OP == FLE_OP_LT) return v < lit0;
+  if (OP == FLE_OP_LE) return v <= lit0;
+  if (OP == FLE_OP_GT) return v > lit0;
+  if (OP == FLE_OP_GE) return v >= lit0;
+  bool p = false;  // FLE_OP_IN
+  for (int j = 0; j < nlits; ++j) p = p || (v == lits_s[j]);
+  return p;
 }
 
-template <typename T>
+template <typename T, int OP>
 __global__ void __launch_bounds__(256) plain_eval_kernel(const PlainParams P) {
-  __shared__ T lits_s[kPlainMaxLits];
+  __shared__ T lits_s[OP == FLE_OP_IN ? kPlainMaxLits : 1];
   __shared__ uint64_t warp_cnt[8];
   __shared__ bool is_last;
-  for (int i = threadIdx.x; i < P.nlits; i += 256) lits_s[i] = reinterpret_cast<const T*>(P.lits)[i];
-  __syncthreads();
+  if (OP == FLE_OP_IN) {
+    for (int i = threadIdx.x; i < P.nlits; i += 256)
+      lits_s[i] = P.nlits <= kPlainInlineLits ? reinterpret_cast<const T*>(P.lit_inline)[i]
+                                              : reinterpret_cast<const T*>(P.lits)[i];
+    __syncthreads();
+  }
   const T* vals = reinterpret_cast<const T*>(P.values);
-  const T lit0 = lits_s[0];
+  const T lit0 = reinterpret_cast<const T*>(P.lit_inline)[0];
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * 256) >> 5;
-  constexpr int U = 8;  // 32-row words per warp iteration
+  constexpr int U = 8;  // 32-row words per warp iteration: 8 coalesced loads in flight per lane
   uint64_t cnt = 0;
   for (int64_t w0 = warp * U; w0 < P.nwords32; w0 += nwarps * U) {
-    T v[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t r = (w0 + u) * 32 + lane;
-      v[u] = r < P.n ? vals[r] : T(0);
-    }
     uint32_t mine = 0;
+    if ((w0 + U) * 32 <= P.n) {  // whole iteration inside the column: no bounds checks
+      const T* p = vals + w0 * 32 + lane;
+      T v[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t r = (w0 + u) * 32 + lane;
-      bool p = false;
-      if (r < P.n) {
-        if (P.op == FLE_OP_IN) {
-          for (int j = 0; j < P.nlits; ++j) p = p || (v[u] == lits_s[j]);
-        } else {
-          p = P.swap ? plain_cmp<T>(P.op, lit0, v[u]) : plain_cmp<T>(P.op, v[u], lit0);
-        }
+      for (int u = 0; u < U; ++u) v[u] = p[u * 32];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t word = __ballot_sync(0xffffffffu, plain_test<OP, T>(v[u], lit0, lits_s, P.nlits));
+        if (lane == u) mine = word;  // rows 32(w0+u) .. +31, LSB first
       }
-      const uint32_t word = __ballot_sync(0xffffffffu, p);  // rows 32(w0+u) .. +31, LSB first
-      if (lane == u) mine = word;
-      if (lane == 0) cnt += __popc(word);
+    } else {
+#pragma unroll 1
+      for (int u = 0; u < U; ++u) {
+        const int64_t r = (w0 + u) * 32 + lane;
+        const bool pr = r < P.n && plain_test<OP, T>(vals[r < P.n ? r : 0], lit0, lits_s, P.nlits);
+        const uint32_t word = __ballot_sync(0xffffffffu, pr);
+        if (lane == u) mine = word;
+      }
     }
-    if (lane < U && w0 + lane < P.nwords32) P.bitmap[w0 + lane] = mine;
+    if (lane < U && w0 + lane < P.nwords32) {
+      P.bitmap[w0 + lane] = mine;
+      cnt += __popc(mine);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
@@ -145,6 +154,18 @@ __global__ void __launch_bounds__(256) plain_eval_kernel(const PlainParams P) {
     for (unsigned int i = 0; i < gridDim.x; ++i) tot += *((volatile uint64_t*)&P.partial[i]);
     if (P.count_out) *P.count_out = tot;
     *P.ticket = 0;
+  }
+}
+
+template <typename T>
+void launch_plain_typed(const PlainParams& P, int op, int grid, cudaStream_t st) {
+  switch (op) {
+    case FLE_OP_EQ: plain_eval_kernel<T, FLE_OP_EQ><<<grid, 256, 0, st>>>(P); break;
+    case FLE_OP_LT: plain_eval_kernel<T, FLE_OP_LT><<<grid, 256, 0, st>>>(P); break;
+    case FLE_OP_LE: plain_eval_kernel<T, FLE_OP_LE><<<grid, 256, 0, st>>>(P); break;
+    case FLE_OP_GT: plain_eval_kernel<T, FLE_OP_GT><<<grid, 256, 0, st>>>(P); break;
+    case FLE_OP_GE: plain_eval_kernel<T, FLE_OP_GE><<<grid, 256, 0, st>>>(P); break;
+    default: plain_eval_kernel<T, FLE_OP_IN><<<grid, 256, 0, st>>>(P); break;
   }
 }
 
@@ -176,20 +197,30 @@ int launch_plain_eval(fle_ctx* ctx, const void* values_dev, int elem_type, int64
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 8, (warps_needed + 7) / 8));
   int rc = ensure_scratch(ctx, grid, std::max(2 * nlits, 2));
   if (rc != FLE_OK) return rc;
-  // literals travel through the context's pinned staging buffer (reused: drain first)
-  FLE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  if (nlits > 0) {
+  if (nlits <= kPlainInlineLits) {
+    if (nlits > 0) std::memcpy(P.lit_inline, lits_host, (size_t)nlits * es);
+  } else {
+    // longer lists travel through the context's pinned staging buffer (reused: drain first)
+    FLE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     std::memcpy(ctx->h_in_lits, lits_host, (size_t)nlits * es);
     FLE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_in_lits, ctx->h_in_lits, (size_t)nlits * es, cudaMemcpyHostToDevice, ctx->stream));
   }
   P.lits = ctx->d_in_lits;
   P.partial = ctx->d_partial;
   P.ticket = ctx->d_ticket;
+  // `literal OP value` (the reference's generic template) is `value OP' literal` with OP' mirrored
+  int kop = op;
+  if (reference_order) {
+    if (op == FLE_OP_LT) kop = FLE_OP_GT;
+    else if (op == FLE_OP_GT) kop = FLE_OP_LT;
+    else if (op == FLE_OP_LE) kop = FLE_OP_GE;
+    else if (op == FLE_OP_GE) kop = FLE_OP_LE;
+  }
   switch (elem_type) {
-    case 0: plain_eval_kernel<int32_t><<<grid, 256, 0, ctx->stream>>>(P); break;
-    case 1: plain_eval_kernel<int64_t><<<grid, 256, 0, ctx->stream>>>(P); break;
-    case 2: plain_eval_kernel<float><<<grid, 256, 0, ctx->stream>>>(P); break;
-    case 3: plain_eval_kernel<double><<<grid, 256, 0, ctx->stream>>>(P); break;
+    case 0: launch_plain_typed<int32_t>(P, kop, grid, ctx->stream); break;
+    case 1: launch_plain_typed<int64_t>(P, kop, grid, ctx->stream); break;
+    case 2: launch_plain_typed<float>(P, kop, grid, ctx->stream); break;
+    case 3: launch_plain_typed<double>(P, kop, grid, ctx->stream); break;
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(ctx, e, "plain_eval launch");

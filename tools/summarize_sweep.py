@@ -41,3 +41,6 @@ for case in sorted(set(r["case"] for r in t)):
     best = sorted([r for r in t if r["case"] == case], key=lambda r: r["ms_min"])[:6]
     for r in best:
         print(f"tune {case:10s} block {r['block']} stages {r['stages']} gpt {r['gpt']} ctas {r['ctas']}: {r['ms_min']:.4f}ms {r['GBps']:.0f}GB/s {r['frac']:.3f}")
+for r in rows:
+    if r["what"] == "aux":
+        print(f"aux {r['name']:70s} {r['ms_min']:.4f}ms {r['GBps']:7.0f}GB/s frac {r['frac']:.3f}")

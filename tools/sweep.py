@@ -227,6 +227,52 @@ def sweep_tune(ctx, out, n):
         ctx.set_option(k, d)
 
 
+def sweep_aux(ctx, out, n):
+    """The kernels either side of the fused eval: bitmap count / select / gather / intersect,
+    PLAIN predicates, realign, dictionary build."""
+    from fle_b200 import GE
+    G = (n + 63) // 64
+    g = torch.Generator(device="cuda").manual_seed(9)
+    v, w = make_col(ctx, n, 12, dom=2526, seed=900)
+    bm, cnt = ctx.eval_dev([(w, 12)], [(GE, 0, 2480)], n)  # ~1.8 % survivors
+    torch.cuda.synchronize()
+    k = int(cnt.item())
+    mn, md = timeit(lambda: ctx.bitmap_count_dev(bm, n, count=cnt))
+    rec(out, what="aux", name="bitmap_count", rows=n, ms_min=mn, ms_med=md, alg_bytes=G * 8)
+    ids = torch.empty(k + 64, dtype=torch.int32, device="cuda")
+    mn, md = timeit(lambda: ctx.bitmap_select_dev(bm, n, cap=k + 64, ids=ids, count=cnt))
+    rec(out, what="aux", name=f"bitmap_select ({k} survivors, 3 launches)", rows=n, ms_min=mn, ms_med=md,
+        alg_bytes=2 * G * 8 + k * 4)
+    o = torch.empty(k + 64, dtype=torch.int32, device="cuda")
+    mn, md = timeit(lambda: ctx.gather_dev(w, 12, ids, cnt, k + 64, out=o))
+    rec(out, what="aux", name="gather codes of survivors (64 B fetched per survivor group)", rows=n, ms_min=mn, ms_med=md,
+        alg_bytes=k * (64 + 4 + 4))
+    full = torch.full((G,), -1, dtype=torch.int64, device="cuda")
+    sub = bm.clone()  # n_sub = popcount(root) = n bits
+    root = full.clone()
+    mn, md = timeit(lambda: ctx.intersect_bitset_dev(root, n, sub, n))
+    rec(out, what="aux", name="intersect_bitset (all-ones root)", rows=n, ms_min=mn, ms_med=md, alg_bytes=3 * G * 8)
+    del root, full, sub, ids, o, v, w
+    for dt, nb in ((torch.int32, 4), (torch.int64, 8), (torch.float64, 8)):
+        m = min(n, 1 << 28)
+        x = torch.randint(0, 1 << 20, (m,), generator=g, device="cuda", dtype=torch.int64).to(dt)
+        pb = torch.empty((m + 63) // 64, dtype=torch.int64, device="cuda")
+        mn, md = timeit(lambda: ctx.plain_eval_dev(x, GE, [1 << 19], bitmap=pb, count=cnt))
+        rec(out, what="aux", name=f"plain_eval {str(dt).split('.')[-1]}", rows=m, ms_min=mn, ms_med=md,
+            alg_bytes=m * nb + (m + 63) // 64 * 8)
+        del x, pb
+    blob = torch.randint(0, 255, ((1 << 28) + 64,), generator=g, device="cuda", dtype=torch.int64).to(torch.uint8)
+    dst = torch.empty((1 << 28) // 8 + 2, dtype=torch.int64, device="cuda")
+    mn, md = timeit(lambda: ctx.realign_dev(blob, 5, 1 << 28, out=dst))
+    rec(out, what="aux", name="realign (funnel-shift copy, 256 MiB)", rows=1 << 28, ms_min=mn, ms_med=md, alg_bytes=2 << 28)
+    del blob, dst
+    m = 1 << 24
+    x = torch.randint(0, 2526, (m,), generator=g, device="cuda", dtype=torch.int64)
+    mn, md = timeit(lambda: ctx.dict_encode_dev(x), reps=3, warm=1)
+    rec(out, what="aux", name="dict_encode int64 (2526 distinct, 16 Mi values; includes its host sync)", rows=m, ms_min=mn,
+        ms_med=md, alg_bytes=m * 8 + m * 12 // 8)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("what", nargs="+")
@@ -248,6 +294,8 @@ def main():
             sweep_programs(ctx, out, args.rows)
         if what & {"tune"}:
             sweep_tune(ctx, out, args.rows)
+        if what & {"aux", "all"}:
+            sweep_aux(ctx, out, args.rows)
     ctx.close()
 
 
