@@ -24,20 +24,34 @@ namespace fle {
 // ------------------------------------------------------------------------------------------
 // funnel-shift realignment
 // ------------------------------------------------------------------------------------------
+// One thread writes 16 output bytes from the two 16-byte aligned source chunks that hold them
+// (the second chunk is the neighbour's first: an L1 hit), so both sides move as 128-bit accesses.
+// `src16` = source address rounded down to 16 bytes, `skew` = bytes dropped from its front (0..15).
 __global__ void __launch_bounds__(256)
-realign_kernel(const uint32_t* __restrict__ src_words, uint32_t shift_bits, int64_t nwords_out, int64_t nbytes,
-               uint32_t* __restrict__ dst) {
-  // dst word w = bytes [4w, 4w+4) of the unaligned stream = funnel of aligned words w, w+1
-  for (int64_t w = (int64_t)blockIdx.x * 256 + threadIdx.x; w < nwords_out; w += (int64_t)gridDim.x * 256) {
-    const uint32_t lo = src_words[w];
-    // the upper word is only touched when it holds bytes of the stream
-    const bool need_hi = shift_bits != 0 && (w * 4 + 4 + (shift_bits >> 3)) > 0 &&
-                         (int64_t)(w * 4 + (4 - (shift_bits >> 3))) < nbytes;
-    const uint32_t hi = need_hi ? src_words[w + 1] : 0u;
-    uint32_t v = __funnelshift_r(lo, hi, shift_bits);
-    const int64_t left = nbytes - w * 4;
-    if (left < 4) v &= (1u << (8 * (int)left)) - 1u;  // zero the bytes past the end
-    dst[w] = v;
+realign_kernel(const uint4* __restrict__ src16, uint32_t skew, int64_t nchunks_out, int64_t nbytes,
+               int64_t src_chunks, uint4* __restrict__ dst) {
+  const uint32_t wsel = skew >> 2, sh = (skew & 3u) * 8u;
+  for (int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x; c < nchunks_out; c += (int64_t)gridDim.x * 256) {
+    const uint4 a = __ldg(src16 + c);
+    // the upper chunk is only touched when it holds bytes of the stream
+    const uint4 b = (skew != 0 && c + 1 < src_chunks) ? __ldg(src16 + c + 1) : make_uint4(0, 0, 0, 0);
+    const uint32_t w[9] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, 0u};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t lo = 0, hi = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {  // wsel is uniform: a 4-way select, not a local-memory index
+        if (wsel == (uint32_t)k) {
+          lo = w[j + k];
+          hi = w[j + k + 1];
+        }
+      }
+      o[j] = __funnelshift_r(lo, hi, sh);
+      const int64_t left = nbytes - (c * 16 + j * 4);
+      if (left < 4) o[j] = left <= 0 ? 0u : (o[j] & ((1u << (8 * (int)left)) - 1u));  // zero the bytes past the end
+    }
+    dst[c] = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -46,11 +60,13 @@ int launch_realign(fle_ctx* ctx, const uint8_t* src_dev, size_t nbytes, uint8_t*
   if (reinterpret_cast<uintptr_t>(dst_dev) & 15) return set_error(ctx, FLE_E_ALIGN, "realign destination must be 16-byte aligned");
   if (nbytes == 0) return FLE_OK;
   const uintptr_t a = reinterpret_cast<uintptr_t>(src_dev);
-  const uint32_t shift = (uint32_t)(a & 3) * 8;
-  const uint32_t* src_words = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-  const int64_t nwords = (int64_t)((nbytes + 3) / 4);
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 16, (nwords + 255) / 256));
-  realign_kernel<<<grid, 256, 0, ctx->stream>>>(src_words, shift, nwords, (int64_t)nbytes, reinterpret_cast<uint32_t*>(dst_dev));
+  const uint32_t skew = (uint32_t)(a & 15);
+  const uint4* src16 = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
+  // whole 16-byte chunks are written: the destination holds (nbytes + 15) / 16 * 16 bytes
+  const int64_t nchunks = (int64_t)((nbytes + 15) / 16);
+  const int64_t src_chunks = (int64_t)((skew + nbytes + 15) / 16);  // aligned chunks that hold stream bytes
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 16, (nchunks + 255) / 256));
+  realign_kernel<<<grid, 256, 0, ctx->stream>>>(src16, skew, nchunks, (int64_t)nbytes, src_chunks, reinterpret_cast<uint4*>(dst_dev));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(ctx, e, "realign launch");
   ctx->launches += 1;

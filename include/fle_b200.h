@@ -249,8 +249,9 @@ typedef struct fle_page_layout {
 int fle_page_parse(const uint8_t* page_host, size_t size, int max_def_level, fle_page_layout* out);
 /* Copies nbytes from an arbitrarily aligned DEVICE address to a 16-byte aligned device buffer
  * with a funnel-shift kernel (the FLE groups of a page start at an odd offset of the file
- * image); bytes of the last 32-bit word past nbytes are written as 0, so dst needs
- * (nbytes + 3) / 4 * 4 bytes. */
+ * image); whole 16-byte chunks are written, bytes past nbytes as 0, so dst needs
+ * (nbytes + 15) / 16 * 16 bytes.  The source is read in aligned 16-byte chunks: up to 15 bytes
+ * before src_dev and after src_dev + nbytes are touched (inside any cudaMalloc'ed buffer). */
 int fle_realign_dev(fle_ctx* ctx, const uint8_t* src_dev, size_t nbytes, uint8_t* dst_dev);
 
 /* Element types of PLAIN fixed-width columns (parquet-common.h:39-76). */

@@ -402,12 +402,12 @@ def test_page_framing_realign_and_eval(ctx, oracle):
         want = oracle.intersect_bitset(root, rows, sub)[0]
         assert (bm.cpu().numpy().view(np.uint64)[: len(want)] == want).all() and int(cnt.item()) == popcount(want)
     # odd sizes / every misalignment
-    for off in range(0, 9):
-        for nbytes in (1, 3, 4, 5, 8, 13, 64, 1001):
+    for off in list(range(0, 18)) + [31, 33, 255]:
+        for nbytes in (1, 3, 4, 5, 8, 13, 15, 16, 17, 64, 1001, 4099):
             out = ctx.realign_dev(dev, off, nbytes)
             torch.cuda.synchronize()
             got = out.cpu().numpy().view(np.uint8)
-            assert (got[:nbytes] == host[off:off + nbytes]).all() and (got[nbytes:(nbytes + 3) // 4 * 4] == 0).all()
+            assert (got[:nbytes] == host[off:off + nbytes]).all() and (got[nbytes:(nbytes + 15) // 16 * 16] == 0).all()
 
 
 @pytest.mark.parametrize("dtype", ["int32", "int64", "float32", "float64"])
