@@ -59,6 +59,14 @@ FLE_HD void transpose32_stage(uint32_t (&A)[32]) {
         A[k + J] = __byte_perm(x, y, 0x2604);  // (y & 0x00FF00FF) | ((x & 0x00FF00FF) << 8)
         continue;
       }
+      if (true) {
+        // (a & ~M) | (b & M) as ONE LOP3 per output word: written in C the compiler spends a
+        // LOP3 per constant (M and ~M), and the xor form below needs three
+        const uint32_t x = A[k], y = A[k + J];
+        asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(A[k]) : "r"(x), "r"(y >> J), "n"(M));
+        asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(A[k + J]) : "r"(x << J), "r"(y), "n"(M));
+        continue;
+      }
 #endif
       uint32_t t = (A[k] ^ (A[k + J] >> J)) & M;
       A[k] ^= t;

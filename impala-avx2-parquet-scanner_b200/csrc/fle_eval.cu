@@ -639,7 +639,7 @@ namespace {
 inline uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 constexpr int kNT = 256;
-enum LaunchMode { MODE_DIRECT = 0, MODE_STAGED = 1, MODE_SINGLE_PASS = 2, MODE_IN_LOOKUP = 3, MODE_JIT = 4 };
+enum LaunchMode { MODE_DIRECT = 0, MODE_STAGED = 1, MODE_SINGLE_PASS = 2, MODE_IN_LOOKUP = 3, MODE_JIT = 4, MODE_NARROW = 5 };
 
 // cudaOccupancyMaxActiveBlocksPerMultiprocessor / cudaFuncSetAttribute are not free; remember
 // the answers per (kernel, dynamic smem)
@@ -699,12 +699,15 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
   } else if (mode == MODE_IN_LOOKUP) {
     kern = eval_in_kernel_for((int)P.bw[0]);
     if (!kern) return FLE_E_UNSUPPORTED;
+  } else if (mode == MODE_NARROW) {
+    kern = eval1_narrow_kernel_for(P.passes[0].type, P.passes[0].k, (int)P.bw[0]);
+    if (!kern) return FLE_E_UNSUPPORTED;
   } else {
     kern = mode == MODE_STAGED ? (const void*)eval_tma_kernel<kNT> : (const void*)eval_direct_kernel<kNT>;
   }
   // (a specialised kernel also runs unstaged -- planes straight from global memory -- for
   //  unaligned columns and for programs whose 256-group tile does not fit shared memory twice)
-  const bool staged = mode != MODE_DIRECT && !(mode == MODE_JIT && !jit_staged);
+  const bool staged = mode != MODE_DIRECT && mode != MODE_NARROW && !(mode == MODE_JIT && !jit_staged);
 
   // tile sizing: groups per thread per tile so that a stage is a few tens of KB
   int gpt = 1;
@@ -781,7 +784,12 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
     rc = blocks_per_sm(ctx, kern, smem_bytes, &per_sm);
     if (rc != FLE_OK) return rc;
     per_sm = std::max(per_sm, 1);
-    grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * per_sm, (G + kNT - 1) / kNT));
+    int64_t blocks = (G + kNT - 1) / kNT;
+    if (mode == MODE_NARROW) {  // tiles of kNT * kNarrowUnits units (fle_eval1.cu), then one group per thread for the rest
+      const int64_t per_tile = (int64_t)kNT * kNarrowUnits * (P.bw[0] == 1 ? 2 : 1);
+      blocks = std::max<int64_t>(G / per_tile, (G % per_tile + kNT - 1) / kNT);
+    }
+    grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * per_sm, blocks));
   }
   rc = ensure_scratch(ctx, P.agg_plain ? 2 * grid : grid, P.n_in_lits);
   if (rc != FLE_OK) return rc;
@@ -871,17 +879,37 @@ int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, 
   const PassDesc& p0 = P.passes[0];
   const bool single_pass = P.npasses == 1 && P.ncombs == 0 && (p0.type == PASS_LT || p0.type == PASS_EQ) &&
                            (p0.k == 1 || p0.merge) && p0.slot[0] == 0;
-  // one IN list on one dictionary-coded column: decode + membership lookup (fle_eval_in.cu)
-  const bool in_lookup = P.npasses == 1 && P.ncombs == 0 && p0.type == PASS_IN && p0.slot[0] == 0 &&
-                         P.bw[p0.col] <= 16 && (int)p0.lit[1] >= ctx->in_lookup_min;
-  if (staged_ok && in_lookup && !agg) {
+  // one IN list on one dictionary-coded column: decode + membership lookup (fle_eval_in.cu), whose
+  // cost does not depend on the list length.  Lists shorter than in_lookup_min are cheaper as
+  // unrolled equality chains on the planes (specialised kernel below: 0.79-0.89 of the HBM roofline
+  // up to 8 literals against 0.56 for the lookup); if that kernel is not available (not compiled
+  // yet, no NVRTC) lists of at least kInLookupFloor literals come back to the lookup kernel.
+  constexpr int kInLookupFloor = 6;
+  const bool in_single = P.npasses == 1 && P.ncombs == 0 && p0.type == PASS_IN && p0.slot[0] == 0 &&
+                         P.bw[p0.col] <= 16 && staged_ok && !agg;
+  const auto launch_in_lookup = [&]() {
     EvalParams P1 = P;
     const int c = p0.col;
     P1.ncols = 1;
     P1.planes[0] = P.planes[c];
     P1.bw[0] = P.bw[c];
     P1.passes[0].col = 0;
-    const int rc = launch_program(ctx, P1, MODE_IN_LOOKUP, (int)P.bw[c]);
+    return launch_program(ctx, P1, MODE_IN_LOOKUP, (int)P.bw[c]);
+  };
+  if (in_single && (int)p0.lit[1] >= ctx->in_lookup_min) {
+    const int rc = launch_in_lookup();
+    if (rc != FLE_E_UNSUPPORTED) return rc;
+  }
+  // narrow columns: consecutive groups are already 128-bit coalesced in global memory
+  if (staged_ok && single_pass && ctx->eval_variant == 1 && !agg && (int)P.bw[p0.col] <= ctx->eval_narrow_bw &&
+      (reinterpret_cast<uintptr_t>(bitmap_dev) & 15) == 0) {
+    EvalParams P1 = P;
+    const int c = p0.col;
+    P1.ncols = 1;
+    P1.planes[0] = P.planes[c];
+    P1.bw[0] = P.bw[c];
+    P1.passes[0].col = 0;
+    const int rc = launch_program(ctx, P1, MODE_NARROW, (int)P.bw[c]);
     if (rc != FLE_E_UNSUPPORTED) return rc;
   }
   if (staged_ok && single_pass && ctx->eval_variant != 2 && !agg) {
@@ -929,6 +957,11 @@ int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, 
     }
   }
   if (agg) return FLE_E_UNSUPPORTED;  // only specialised kernels fuse the aggregate
+  if (in_single && ctx->in_lookup_min < (1 << 30) /* 2^30 and up: lookup kernel disabled */ &&
+      (int)p0.lit[1] >= std::min(kInLookupFloor, ctx->in_lookup_min)) {
+    const int rc = launch_in_lookup();
+    if (rc != FLE_E_UNSUPPORTED) return rc;
+  }
   // Everything else: the TMA-staged generic kernel; the direct-load kernel remains for unaligned inputs, tiles that do
   // not fit in shared memory, and as eval_variant = 0.
   if (staged_ok) {

@@ -10,8 +10,8 @@
 //      bw <= 13 the table is replicated per lane (word w of lane l at w * 128 + l * 4 bytes, <= 32 KB)
 //      so that the 64 data-dependent lookups of a group never conflict on a bank -- with one shared
 //      copy 32 random words hit ~3.5 words per bank and the LSU pipe, not HBM, bounded the kernel,
-//   2. transposes each group's planes into its 64 codes in registers (one 32x32 butterfly, both
-//      32-row halves at once, as in the unpack kernel),
+//   2. transposes each group's planes into its 64 codes in registers (16 x 16-block butterflies,
+//      two codes per 32-bit word),
 //   3. looks every code up in the table and assembles the 64-bit selection word directly in
 //      row order,
 // which costs the same for any L.  Same TMA/mbarrier tile pipeline and skewed shared layout as
@@ -23,43 +23,111 @@
 
 namespace fle {
 
-// lane-private table copies (bank = lane) while they fit: 2^13 bits x 32 lanes = 32 KB
+// The kernel is bound by the ALU pipe (LOP3 / SHF / PRMT: 64 lanes per clock per SM), not by HBM:
+// ncu on the first version showed 88 % ALU-pipe utilisation (574 ALU instructions per group) with
+// the FMA pipe (IMAD) at 20 %.  The group function is therefore written for few ALU instructions
+// (407 now, 600 instructions in all against 903):
+//   * the two 32-row halves are transposed as 16 x 16 blocks (stages 8, 4, 2, 1 only: a
+//     transposed word then holds the codes of rows k and 16 + k instead of k and 32 + k, which
+//     the result assembly absorbs) -- the 16-bit stage (32 PRMT) disappears;
+//   * a butterfly stage is two selects,  a' = (a & ~M) | ((b >> J) & M),  b' = (b & M) | ((a << J) & ~M),
+//     each ONE LOP3 (inline PTX: written in C the compiler spends a LOP3 per constant), the left
+//     shift an IMAD.SHL on the FMA pipe;
+//   * plane i is fed to the butterfly at the bit position the lookup wants it: code bits 0..4
+//     stay at 0..4 (SHF uses them as the shift amount without masking), bits 5.. land at 7..
+//     for the lane-private table, whose word w sits at byte w * 128 + lane * 4, so the word
+//     address is one LOP3 (half & mask) plus an IMAD add of the lane's base;
+//   * table words are stored bit-reversed: `word << (code & 31)` brings the wanted bit to bit 31
+//     and the funnel shift  acc = (acc : x) << 1  appends it.
+// Tried and dropped (profiles/r01_in_lookup_tuning.txt): right shifts as IMAD.HI (x >> J ==
+// umulhi(x, 2^(32-J))) to unload the ALU pipe -- IMAD.HI issues at a quarter of the LOP3 rate
+// (tools/micro/int_pipes.cu) and shows up as dispatch stalls, every mix was slower; 2 stages /
+// 3-4 CTAs per SM instead of 4 stages / 2 CTAs -- no change, the pipe is the limit.
 template <int BW>
 struct InTable {
-  static constexpr bool kPerLane = BW <= 13;
+  static constexpr bool kPerLane = BW <= 13;  // 2^13 bits x 32 lanes = 32 KB
   static constexpr int kWords = BW <= 5 ? 1 : (1 << (BW - 5));
-  static constexpr int kShift = kPerLane ? 7 : 2;  // byte stride between consecutive table words
+  static constexpr int kShift = kPerLane ? 7 : 2;  // log2 of the byte stride between consecutive table words
+  static constexpr uint32_t kAddrMask = (uint32_t)(kWords - 1) << kShift;
+  // bit position of code bit i inside its 16-bit half of a transposed word
+  FLE_HD static constexpr int pos(int i) { return (kPerLane && i >= 5) ? i + 2 : i; }
 };
 
-template <int BW, class L>
-__device__ __forceinline__ uint64_t in_lookup_group(const L& ld, uint32_t table) {
-  uint64_t w[BW];
-#pragma unroll
-  for (int i = 0; i < BW; i += 2) {
-    uint64_t a, b;
-    ld.template load_pair<BW>(i, a, b);
-    w[i] = a;
-    if (i + 1 < BW) w[i + 1] = b;
-  }
-  // A'[k] = code(row k) | code(row 32 + k) << 16   (see fle_device.cuh / fle_codec.cu)
-  uint32_t A[32];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    A[31 - i] = i < BW ? (uint32_t)(w[i < BW ? i : 0] >> 32) : 0u;
-    A[15 - i] = i < BW ? (uint32_t)(w[i < BW ? i : 0]) : 0u;
-  }
-  transpose32(A);
-  uint32_t lo = 0, hi = 0;  // rows 0..31 / 32..63, row order (bit r%32)
-#pragma unroll
-  for (int k = 31; k >= 0; --k) {
-    const uint32_t c0 = A[k] & 0xFFFFu, c1 = A[k] >> 16;
-    const uint32_t t0 = lds32(table + ((c0 >> 5) << InTable<BW>::kShift));
-    const uint32_t t1 = lds32(table + ((c1 >> 5) << InTable<BW>::kShift));
-    lo = (lo << 1) | (__funnelshift_r(t0, 0u, c0) & 1u);  // funnel shift uses c & 31
-    hi = (hi << 1) | (__funnelshift_r(t1, 0u, c1) & 1u);
-  }
-  return ((uint64_t)hi << 32) | lo;
+// (a & ~M) | (b & M) as ONE LOP3 (written in C the compiler spends a LOP3 per constant, M and ~M)
+template <uint32_t M>
+__device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(r) : "r"(a), "r"(b), "n"(M));
+  return r;
 }
+
+template <int BW>
+struct InDecode {
+  using IT = InTable<BW>;
+  uint32_t table;  // shared address of this lane's table (of the shared one for bw > 13)
+
+  template <int J, uint32_t M>
+  __device__ __forceinline__ void stage(uint32_t (&S)[16]) const {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      if ((k & J) == 0) {
+        const uint32_t a = S[k], b = S[k + J];
+        if (J == 8) {
+          S[k] = __byte_perm(a, b, 0x3715);      // (a & 0xFF00FF00) | ((b >> 8) & 0x00FF00FF)
+          S[k + J] = __byte_perm(a, b, 0x2604);  // (b & 0x00FF00FF) | ((a & 0x00FF00FF) << 8)
+        } else {
+          S[k] = bitsel<M>(a, b >> J);
+          S[k + J] = bitsel<M>(a << J, b);
+        }
+      }
+    }
+  }
+
+  // 16 x 16 bit transposes of the low and of the high halves of S[0..15] at once:
+  // S'[k] bit i == S[15 - i] bit (15 - k),   S'[k] bit 16 + i == S[15 - i] bit (31 - k)
+  __device__ __forceinline__ void transpose(uint32_t (&S)[16]) const {
+    stage<8, 0x00FF00FFu>(S);
+    stage<4, 0x0F0F0F0Fu>(S);
+    stage<2, 0x33333333u>(S);
+    stage<1, 0x55555555u>(S);
+  }
+
+  // membership of the code in bits 0..15 of h (higher bits ignored) -> bit 31 of the result
+  __device__ __forceinline__ uint32_t probe(uint32_t h) const {
+    const uint32_t off = IT::kPerLane ? (h & IT::kAddrMask) : ((h >> 3) & IT::kAddrMask);
+    return lds32(table + off) << (h & 31u);
+  }
+
+  template <class L>
+  __device__ __forceinline__ uint64_t run(const L& ld) const {
+    uint32_t S0[16], S1[16];  // bit planes of rows 0..31 / 32..63, plane i at word 15 - pos(i)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) S0[j] = S1[j] = 0u;
+#pragma unroll
+    for (int i = 0; i < BW; i += 2) {
+      uint64_t a, b;
+      ld.template load_pair<BW>(i, a, b);
+      S0[15 - IT::pos(i)] = (uint32_t)(a >> 32);
+      S1[15 - IT::pos(i)] = (uint32_t)a;
+      if (i + 1 < BW) {
+        S0[15 - IT::pos(i + 1 < BW ? i + 1 : i)] = (uint32_t)(b >> 32);
+        S1[15 - IT::pos(i + 1 < BW ? i + 1 : i)] = (uint32_t)b;
+      }
+    }
+    transpose(S0);  // S0[k] = half(row k) << 16 | half(row 16 + k)
+    transpose(S1);  // S1[k] = half(row 32 + k) << 16 | half(row 48 + k)
+    uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;  // rows 0..15, 16..31, 32..47, 48..63 (bit k = row base + k)
+#pragma unroll
+    for (int k = 15; k >= 0; --k) {
+      const uint32_t a = S0[k], b = S1[k];
+      r1 = __funnelshift_l(probe(a), r1, 1);
+      r0 = __funnelshift_l(probe(a >> 16), r0, 1);
+      r3 = __funnelshift_l(probe(b), r3, 1);
+      r2 = __funnelshift_l(probe(b >> 16), r2, 1);
+    }
+    return ((uint64_t)(r2 | (r3 << 16)) << 32) | (uint64_t)(r0 | (r1 << 16));
+  }
+};
 
 struct InSmemGroup {
   uint32_t base;
@@ -100,7 +168,8 @@ __global__ void __launch_bounds__(256) eval_in_kernel(const __grid_constant__ Ev
   using IT = InTable<BW>;
   uint32_t* rep_ptr = reinterpret_cast<uint32_t*>(smem + P.smem_masks_off);
   uint32_t* table_ptr = rep_ptr + (IT::kPerLane ? IT::kWords * 32 : 0);
-  const uint32_t table = IT::kPerLane ? smem_u32(rep_ptr) + (threadIdx.x & 31u) * 4u : smem_u32(table_ptr);
+  InDecode<BW> dec;
+  dec.table = IT::kPerLane ? smem_u32(rep_ptr) + (threadIdx.x & 31u) * 4u : smem_u32(table_ptr);
   const int gpt = P.gpt;
   const int T = NT * gpt;
   const int seg_groups = T >> 3;
@@ -123,7 +192,7 @@ __global__ void __launch_bounds__(256) eval_in_kernel(const __grid_constant__ Ev
   const int off = (int)pd.lit[0], cnt = (int)pd.lit[1];
   for (int i = threadIdx.x; i < cnt; i += NT) {
     const uint32_t c = P.in_lits[off + i];  // already masked to BW bits by the host
-    atomicOr(&table_ptr[c >> 5], 1u << (c & 31));
+    atomicOr(&table_ptr[c >> 5], 0x80000000u >> (c & 31));  // bit-reversed words, see probe()
   }
   __syncthreads();
   if (IT::kPerLane) {
@@ -152,7 +221,7 @@ __global__ void __launch_bounds__(256) eval_in_kernel(const __grid_constant__ Ev
     uint32_t a = stage0 + stage * P.stage_bytes + thread_off;
     int64_t g = tile * T + thread_g;
     for (int q = 0; q < gpt; ++q) {
-      const uint64_t r = finish_row_order(in_lookup_group<BW>(InSmemGroup{a}, table), negmask, g, P.nrows);
+      const uint64_t r = finish_row_order(dec.run(InSmemGroup{a}), negmask, g, P.nrows);
       P.bitmap[g] = r;
       cnt_bits += __popcll(r);
       a += kGroupStride;
@@ -165,7 +234,7 @@ __global__ void __launch_bounds__(256) eval_in_kernel(const __grid_constant__ Ev
   }
   for (int64_t g = ntiles * T + (int64_t)blockIdx.x * NT + threadIdx.x; g < P.ngroups;
        g += (int64_t)gridDim.x * NT) {
-    const uint64_t r = finish_row_order(in_lookup_group<BW>(InGlobalGroup{P.planes[0] + g * BW}, table), negmask, g, P.nrows);
+    const uint64_t r = finish_row_order(dec.run(InGlobalGroup{P.planes[0] + g * BW}), negmask, g, P.nrows);
     P.bitmap[g] = r;
     cnt_bits += __popcll(r);
   }

@@ -57,7 +57,8 @@ struct fle_ctx {
   int eval_block = 256;
   int eval_ctas_per_sm = 0;  // 0 = auto (occupancy)
   int eval_gpt = 0;          // 0 = auto
-  int in_lookup_min = 6;     // IN lists at least this long use the decode+lookup kernel (bw <= 16)
+  int eval_narrow_bw = 2;    // single-pass programs on columns up to this width skip shared-memory staging (bw 1, 2, 4)
+  int in_lookup_min = 9;     // IN lists at least this long use the decode+lookup kernel (bw <= 16); shorter ones the plane form
   int codec_variant = 1;
   int eval_jit = 1;                      // 0 never, 1 when n >= eval_jit_min_rows or already compiled, 2 always
   int64_t eval_jit_min_rows = 1ll << 24;
@@ -116,6 +117,9 @@ int launch_eval(fle_ctx* ctx, const fle_col_desc* cols_dev, int ncols, const fle
                 uint64_t* count_dev);
 // fle_eval1.cu: the single-pass kernel for (PassType, chains, bit width), or nullptr
 const void* eval1_kernel_for(int type, int k, int bw);
+// fle_eval1.cu: unstaged kernels for bw 1, 2, 4 (coalesced 128-bit global loads), or nullptr
+const void* eval1_narrow_kernel_for(int type, int k, int bw);
+constexpr int kNarrowUnits = 8;  // 16/32-byte units per thread per tile of the narrow kernels
 // fle_eval_in.cu: IN list by decode + membership-table lookup (bw <= 16), or nullptr
 const void* eval_in_kernel_for(int bw);
 // out = postfix program over K device bitmaps (leaf.col = bitmap index), word by word

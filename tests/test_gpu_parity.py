@@ -360,7 +360,7 @@ def test_in_list_lookup_kernel_vs_oracle(ctx, oracle, bw):
             try:
                 bm, cnt = ctx.eval([(words, bw)], [(IN, 0, lits)], n)
             finally:
-                ctx.set_option("in_lookup_min", 6)
+                ctx.set_option("in_lookup_min", 9)
             assert (bm == want).all() and cnt == wcnt, (bw, L, lookup_min)
 
 
