@@ -335,6 +335,7 @@ int fle_ctx_set_option(fle_ctx* ctx, const char* name, int64_t value) {
   else if (k == "in_lookup_min") ctx->in_lookup_min = (int)value;
   else if (k == "eval_narrow_bw") ctx->eval_narrow_bw = (int)value;
   else if (k == "codec_variant") ctx->codec_variant = (int)value;
+  else if (k == "codec_ctas_per_sm") ctx->codec_ctas_per_sm = (int)value;
   else if (k == "eval_jit") ctx->eval_jit = (int)value;
   else if (k == "eval_jit_min_rows") ctx->eval_jit_min_rows = value;
   else if (k == "h2d_chunk_rows") ctx->h2d_chunk_rows = value;
@@ -353,6 +354,7 @@ int64_t fle_ctx_get_option(fle_ctx* ctx, const char* name) {
   if (k == "in_lookup_min") return ctx->in_lookup_min;
   if (k == "eval_narrow_bw") return ctx->eval_narrow_bw;
   if (k == "codec_variant") return ctx->codec_variant;
+  if (k == "codec_ctas_per_sm") return ctx->codec_ctas_per_sm;
   if (k == "eval_jit") return ctx->eval_jit;
   if (k == "eval_jit_min_rows") return ctx->eval_jit_min_rows;
   if (k == "h2d_chunk_rows") return ctx->h2d_chunk_rows;

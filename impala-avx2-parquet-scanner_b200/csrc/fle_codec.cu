@@ -176,7 +176,7 @@ pack_kernel(const uint32_t* __restrict__ vals, int64_t nvals, int64_t ngroups, u
 }
 
 // ------------------------------------------------------------------------------------------
-// TMA-staged variants (codec_variant = 1, default).
+// TMA-staged variants (codec_variant = 4; 1 = auto picks per bit width, see unpack_choice).
 //
 // The direct variants above fetch / store each thread's bw plane words with 64-bit accesses that
 // are bw*8 bytes apart between neighbouring lanes: one warp instruction touches 32 different
@@ -287,6 +287,224 @@ unpack_tma_kernel(const uint64_t* __restrict__ enc, int64_t ngroups, int64_t nva
     }
     __syncthreads();
   }
+}
+
+// Unpack with warp-private copy-out (codec_variant = 3): same data path as unpack_tma_kernel, but a
+// warp copies out the 32 rows its own lanes wrote (two adjacent rows = 512 contiguous bytes per
+// store instruction), so the two CTA barriers around the copy-out become __syncwarp, and the plane
+// stages are handed back to the producer through per-stage "empty" mbarriers (one arrival per warp)
+// instead of a CTA barrier: the four warps of a CTA drift apart and one warp's stores overlap
+// another's transposes.
+template <int BW>
+__global__ void __launch_bounds__(kCodecThreads)
+unpack_warp_kernel(const uint64_t* __restrict__ enc, int64_t ngroups, int64_t nvals, uint32_t* __restrict__ out) {
+  using PT = PlaneTile<BW>;
+  constexpr int kStages = 3;
+  constexpr uint32_t kStageStride = (PT::kBytes + 127) / 128 * 128;
+  extern __shared__ __align__(128) uint8_t smem[];
+  // [value tile 32 KB][stages][full mbarriers][empty mbarriers]
+  const uint32_t tile = smem_u32(smem);
+  const uint32_t stage0 = tile + kTileValueBytes;
+  const uint32_t full0 = stage0 + kStages * kStageStride;
+  const uint32_t empty0 = full0 + kStages * 8;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int64_t ntiles_full = nvals / (PT::kGroups * 64);
+
+  if (t == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full0 + s * 8, 1);
+      mbar_init(empty0 + s * 8, kCodecThreads / 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue = [&](int stage, int64_t tl) {
+    const uint32_t bar = full0 + stage * 8;
+    mbar_arrive_expect_tx(bar, 8 * PT::kSegBytes);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(enc) + (uint64_t)tl * PT::kGroups * BW * 8;
+#pragma unroll
+    for (int s = 0; s < 8; ++s)
+      tma_load_1d(stage0 + stage * kStageStride + s * PT::kSegStride, src + (uint64_t)s * PT::kSegBytes, PT::kSegBytes, bar);
+  };
+  if (t == 0) {
+    for (int s = 0; s < kStages - 1; ++s) {
+      const int64_t tl = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
+      if (tl < ntiles_full) issue(s, tl);
+    }
+  }
+  const int row = PT::thread_group(t);  // (t & 7) * 16 + (t >> 3)
+  int stage = 0;
+  uint32_t use = 0;
+  for (int64_t tl = blockIdx.x; tl < ntiles_full; tl += gridDim.x) {
+    if (t == 0) {
+      // refill the stage consumed in the previous iteration, two tiles ahead, once every warp has
+      // read it: iteration i of this CTA uses stage i % 3 for the (i / 3)-th time (== use); the tile
+      // of iteration i + 2 is fill number use2 of stage st2 and must wait for consumption use2 - 1
+      const int64_t nxt = tl + (int64_t)(kStages - 1) * gridDim.x;
+      int st2 = stage + kStages - 1;
+      uint32_t use2 = use;
+      if (st2 >= kStages) { st2 -= kStages; use2 += 1; }
+      if (nxt < ntiles_full) {
+        if (use2 >= 1) mbar_wait(empty0 + st2 * 8, (use2 - 1) & 1u);
+        issue(st2, nxt);
+      }
+    }
+    mbar_wait(full0 + stage * 8, use & 1u);
+    uint64_t w[BW];
+    const uint32_t a = stage0 + stage * kStageStride + PT::thread_off(t);
+    if constexpr (BW % 2 == 0) {
+#pragma unroll
+      for (int i = 0; i < BW; i += 2) lds128(a + i * 8, w[i], w[i + 1 < BW ? i + 1 : i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < BW; ++i) w[i] = lds64(a + i * 8);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty0 + stage * 8);
+    uint32_t v[64];
+    transpose_planes_to_values<BW>(w, v);
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+      sts128u(tile_chunk_addr(tile, row, c), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    __syncwarp();
+    uint32_t* dst = out + tl * PT::kGroups * 64;
+#pragma unroll 4
+    for (int it = 0; it < 16; ++it) {
+      const int q = it * 32 + lane;     // 16-byte chunk among this warp's 32 rows
+      const int rr = q >> 4;            // this warp's rr-th row: segment rr >> 2, row (rr & 3) of the warp's four
+      const int r = (rr >> 2) * 16 + warp * 4 + (rr & 3);
+      uint32_t x, y, z, u;
+      lds128u(tile_chunk_addr(tile, r, q & 15), x, y, z, u);
+      stg_stream128(dst + r * 64 + (q & 15) * 4, make_uint4(x, y, z, u));
+    }
+    __syncwarp();
+    if (++stage == kStages) {
+      stage = 0;
+      use += 1;
+    }
+  }
+  // ragged remainder (< 128 * 64 values): plain loads and guarded stores
+  for (int64_t g = ntiles_full * PT::kGroups + (int64_t)blockIdx.x * kCodecThreads + t; g < ngroups;
+       g += (int64_t)gridDim.x * kCodecThreads) {
+    uint64_t w[BW];
+    const uint64_t* src = enc + g * BW;
+#pragma unroll
+    for (int i = 0; i < BW; ++i) w[i] = __ldg(src + i);
+    uint32_t v[64];
+    transpose_planes_to_values<BW>(w, v);
+    const int64_t left = nvals - g * 64;
+    uint32_t* dst = out + g * 64;
+    if (left >= 64) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) stg_stream128(dst + 4 * c, make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 64; ++k)
+        if (k < left) dst[k] = v[k];
+    }
+  }
+}
+
+// Unpack with bulk stores (codec_variant = 2): the copy-out phase of the kernel above (16 x LDS.128
+// + 16 x STG.128 per thread between two CTA barriers) is replaced by ONE 256-byte bulk store per
+// thread.  A thread writes the 64 values of its group to its own shared-memory row (row stride
+// 272 bytes: the 16-byte STS of neighbouring lanes land in different banks), fences the async
+// proxy and hands the row to the copy engine; the next iteration only waits until the engine has
+// READ the row (cp.async.bulk.wait_group.read) before overwriting it.  One CTA barrier per tile
+// remains, after the plane words are in registers, so that the stage can be refilled two tiles ahead.
+constexpr uint32_t kRowStride = 256 + 16;
+__host__ __device__ constexpr int unpack_bulk_stages(int bw) { return bw <= 16 ? 3 : 2; }  // 3 CTAs per SM up to bw 16, 2 beyond
+
+template <int BW>
+__global__ void __launch_bounds__(kCodecThreads)
+unpack_bulk_kernel(const uint64_t* __restrict__ enc, int64_t ngroups, int64_t nvals, uint32_t* __restrict__ out) {
+  using PT = PlaneTile<BW>;
+  constexpr int kStages = unpack_bulk_stages(BW);
+  constexpr uint32_t kStageStride = (PT::kBytes + 127) / 128 * 128;
+  extern __shared__ __align__(128) uint8_t smem[];
+  // [value rows 128 x 272 B][stages][mbarriers]
+  const uint32_t rows = smem_u32(smem);
+  const uint32_t stage0 = rows + kCodecThreads * kRowStride;
+  const uint32_t bar0 = stage0 + kStages * kStageStride;
+  const int t = threadIdx.x;
+  const uint32_t my_row = rows + t * kRowStride;
+  // tiles whose 128 groups are complete rows of 64 values go through TMA both ways
+  const int64_t ntiles_full = nvals / (PT::kGroups * 64);
+
+  if (t == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(bar0 + s * 8, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue = [&](int stage, int64_t tl) {
+    const uint32_t bar = bar0 + stage * 8;
+    mbar_arrive_expect_tx(bar, 8 * PT::kSegBytes);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(enc) + (uint64_t)tl * PT::kGroups * BW * 8;
+#pragma unroll
+    for (int s = 0; s < 8; ++s)
+      tma_load_1d(stage0 + stage * kStageStride + s * PT::kSegStride, src + (uint64_t)s * PT::kSegBytes, PT::kSegBytes, bar);
+  };
+  if (t == 0) {
+    for (int s = 0; s < kStages - 1; ++s) {
+      const int64_t tl = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
+      if (tl < ntiles_full) issue(s, tl);
+    }
+  }
+  int stage = 0;
+  uint32_t parity = 0;
+  const int row = PT::thread_group(t);
+  for (int64_t tl = blockIdx.x; tl < ntiles_full; tl += gridDim.x) {
+    uint64_t w[BW];
+    mbar_wait(bar0 + stage * 8, parity);
+    const uint32_t a = stage0 + stage * kStageStride + PT::thread_off(t);
+    if constexpr (BW % 2 == 0) {
+#pragma unroll
+      for (int i = 0; i < BW; i += 2) lds128(a + i * 8, w[i], w[i + 1 < BW ? i + 1 : i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < BW; ++i) w[i] = lds64(a + i * 8);
+    }
+    __syncthreads();  // every thread holds its planes: this stage and the one before it are free
+    if (t == 0) {
+      const int64_t nxt = tl + (int64_t)(kStages - 1) * gridDim.x;
+      int st2 = stage + kStages - 1;
+      if (st2 >= kStages) st2 -= kStages;
+      if (nxt < ntiles_full) issue(st2, nxt);
+    }
+    uint32_t v[64];
+    transpose_planes_to_values<BW>(w, v);
+    tma_store_wait_read<0>();  // the copy engine is done reading this thread's previous row
+#pragma unroll
+    for (int c = 0; c < 16; ++c) sts128u(my_row + c * 16, v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    fence_proxy_async_smem();
+    tma_store_1d(out + (tl * PT::kGroups + row) * 64, my_row, 256);
+    tma_store_commit();
+    if (++stage == kStages) {
+      stage = 0;
+      parity ^= 1u;
+    }
+  }
+  // ragged remainder (< 128 * 64 values): plain loads and guarded stores
+  for (int64_t g = ntiles_full * PT::kGroups + (int64_t)blockIdx.x * kCodecThreads + t; g < ngroups;
+       g += (int64_t)gridDim.x * kCodecThreads) {
+    uint64_t w[BW];
+    const uint64_t* src = enc + g * BW;
+#pragma unroll
+    for (int i = 0; i < BW; ++i) w[i] = __ldg(src + i);
+    uint32_t v[64];
+    transpose_planes_to_values<BW>(w, v);
+    const int64_t left = nvals - g * 64;
+    uint32_t* dst = out + g * 64;
+    if (left >= 64) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) stg_stream128(dst + 4 * c, make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 64; ++k)
+        if (k < left) dst[k] = v[k];
+    }
+  }
+  tma_store_wait<0>();  // bulk stores complete before the CTA (and its shared memory) goes away
 }
 
 // Pack: the value side of a tile (32 KB, contiguous in global memory) is fetched with
@@ -407,6 +625,16 @@ UnpackFn unpack_tma_table_entry(int bw, Seq<I...>) {
   return tab[bw - 1];
 }
 template <int... I>
+UnpackFn unpack_warp_table_entry(int bw, Seq<I...>) {
+  static const UnpackFn tab[] = {unpack_warp_kernel<I>...};
+  return tab[bw - 1];
+}
+template <int... I>
+UnpackFn unpack_bulk_table_entry(int bw, Seq<I...>) {
+  static const UnpackFn tab[] = {unpack_bulk_kernel<I>...};
+  return tab[bw - 1];
+}
+template <int... I>
 PackFn pack_tma_table_entry(int bw, Seq<I...>) {
   static const PackFn tab[] = {pack_tma_kernel<I>...};
   return tab[bw - 1];
@@ -434,6 +662,11 @@ int raise_smem_limit(fle_ctx* ctx, const void* kern, size_t smem_bytes) {
   return FLE_OK;
 }
 
+int codec_ctas(fle_ctx* ctx, size_t smem) {
+  const int fit = std::max<int>(1, std::min<int>(8, (int)((size_t)ctx->max_smem_per_sm / (smem + 1024))));
+  return ctx->codec_ctas_per_sm > 0 ? std::min(fit, ctx->codec_ctas_per_sm) : fit;
+}
+
 int codec_grid(fle_ctx* ctx, int64_t ngroups) {
   const int64_t ntiles = (ngroups + kCodecThreads - 1) / kCodecThreads;
   // 32 KB static shared memory per CTA -> up to 7 CTAs per SM
@@ -442,22 +675,55 @@ int codec_grid(fle_ctx* ctx, int64_t ngroups) {
 
 }  // namespace
 
+// Which unpack kernel and how many CTAs per SM (codec_variant = 1, "auto"): measured per bit
+// width at 2^26 values (profiles/r01_codec_variants.txt).  More resident CTAs are NOT better here:
+// with three or more CTAs per SM the staged kernels lose 5-8 % against two -- more concurrent read
+// and write streams for the memory system, nothing left to hide -- except for the narrowest
+// widths, whose tiles are nearly all output.
+enum UnpackKind { UNPACK_STAGED = 4, UNPACK_BULK = 2, UNPACK_WARP = 3 };
+static void unpack_choice(int bw, int* kind, int* ctas) {
+  if (bw <= 3) { *kind = UNPACK_WARP; *ctas = 2; }
+  else if (bw <= 5) { *kind = UNPACK_STAGED; *ctas = 3; }
+  else if (bw <= 8) { *kind = UNPACK_BULK; *ctas = 2; }
+  else if (bw <= 21) { *kind = UNPACK_STAGED; *ctas = 2; }
+  else if (bw <= 28) { *kind = UNPACK_BULK; *ctas = 2; }
+  else { *kind = UNPACK_WARP; *ctas = 3; }
+}
+
 int launch_unpack_u32(fle_ctx* ctx, const uint64_t* enc_dev, int bw, int64_t n, uint32_t* out_dev) {
   if (bw < 1 || bw > 32) return set_error(ctx, FLE_E_INVALID, "bit width outside 1..32");
   if (n == 0) return FLE_OK;
   const int64_t G = (n + 63) / 64;
-  if (ctx->codec_variant != 0 && (reinterpret_cast<uintptr_t>(enc_dev) & 15) == 0) {
-    UnpackFn fn = unpack_tma_table_entry(bw, MakeSeq<32>::type());
+  const bool enc_ok = (reinterpret_cast<uintptr_t>(enc_dev) & 15) == 0;
+  const bool out_ok = (reinterpret_cast<uintptr_t>(out_dev) & 15) == 0;
+  if (ctx->codec_variant != 0 && enc_ok) {
+    // codec_variant: 1 auto, 2 bulk stores, 3 warp-private copy-out, 4 staged copy-out (0: direct loads)
+    int kind = ctx->codec_variant, ctas = 0;
+    if (kind == 1) unpack_choice(bw, &kind, &ctas);
+    if (!out_ok || (kind != UNPACK_BULK && kind != UNPACK_WARP)) kind = UNPACK_STAGED;
+    if (ctx->codec_ctas_per_sm > 0) ctas = ctx->codec_ctas_per_sm;
     const size_t stage = (plane_tile_bytes(bw, MakeSeq<32>::type()) + 127) / 128 * 128;
-    const size_t smem = kTileValueBytes + 2 * stage + 64;
+    UnpackFn fn;
+    size_t smem;
+    if (kind == UNPACK_BULK) {
+      fn = unpack_bulk_table_entry(bw, MakeSeq<32>::type());
+      smem = kCodecThreads * kRowStride + unpack_bulk_stages(bw) * stage + 64;
+    } else if (kind == UNPACK_WARP) {
+      fn = unpack_warp_table_entry(bw, MakeSeq<32>::type());
+      smem = kTileValueBytes + 3 * stage + 64;
+    } else {
+      fn = unpack_tma_table_entry(bw, MakeSeq<32>::type());
+      smem = kTileValueBytes + 2 * stage + 64;
+    }
     int rc = raise_smem_limit(ctx, (const void*)fn, smem);
     if (rc != FLE_OK) return rc;
-    const int per_sm = std::max<int>(1, std::min<int>(8, (int)((size_t)ctx->max_smem_per_sm / (smem + 1024))));
+    int per_sm = std::max<int>(1, std::min<int>(8, (int)((size_t)ctx->max_smem_per_sm / (smem + 1024))));
+    if (ctas > 0) per_sm = std::min(per_sm, ctas);
     const int64_t ntiles = (G + kCodecThreads - 1) / kCodecThreads;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)ctx->num_sms * per_sm));
     fn<<<grid, kCodecThreads, smem, ctx->stream>>>(enc_dev, G, n, out_dev);
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return set_cuda_error(ctx, e, "unpack_tma_kernel launch");
+    if (e != cudaSuccess) return set_cuda_error(ctx, e, "unpack kernel launch");
     ctx->launches += 1;
     return FLE_OK;
   }
@@ -482,7 +748,8 @@ int launch_pack_u32(fle_ctx* ctx, const uint32_t* vals_dev, int64_t n, int bw, u
     const size_t smem = 2 * kPackBufBytes;
     int rc = raise_smem_limit(ctx, (const void*)fn, smem);
     if (rc != FLE_OK) return rc;
-    const int per_sm = std::max<int>(1, std::min<int>(8, (int)((size_t)ctx->max_smem_per_sm / (smem + 1024))));
+    // three CTAs fit, two are faster at every bit width (0.88-0.95 against 0.83-0.89 of roofline)
+    const int per_sm = ctx->codec_ctas_per_sm > 0 ? codec_ctas(ctx, smem) : std::min(2, codec_ctas(ctx, smem));
     const int64_t ntiles = (G + kCodecThreads - 1) / kCodecThreads;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)ctx->num_sms * per_sm));
     fn<<<grid, kCodecThreads, smem, ctx->stream>>>(vals_dev, n, G, enc_dev);

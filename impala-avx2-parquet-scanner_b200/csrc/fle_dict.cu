@@ -42,6 +42,10 @@ struct DictState {
   unsigned int nlist;     // compaction cursor
 };
 
+__global__ void __launch_bounds__(256) dict_clear_kernel(unsigned long long* __restrict__ keys) {
+  keys[blockIdx.x * 256 + threadIdx.x] = kEmptyKey;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 dict_insert_kernel(const T* __restrict__ vals, int64_t n, unsigned long long* __restrict__ keys, DictState* st,
@@ -145,13 +149,8 @@ int launch_dict_encode(fle_ctx* ctx, const void* values_dev, int elem_type, int6
   DICT_TRY(cudaMallocAsync(&list_slots, (size_t)(max_entries + 2) * 4, st));
   DICT_TRY(cudaMallocAsync(&slot_to_code, (size_t)(kDictSlots + 1) * 4, st));
   DICT_TRY(cudaMallocAsync(&codes, (size_t)std::max<int64_t>(n, 1) * 4, st));
-  // every byte 0x80 would not be kEmptyKey: fill the table with a tiny kernel-free pattern copy
-  {
-    std::vector<unsigned long long> init(4096, kEmptyKey);
-    for (int off = 0; off < kDictSlots; off += 4096)
-      DICT_TRY(cudaMemcpyAsync(keys + off, init.data(), 4096 * 8, cudaMemcpyHostToDevice, st));
-    DICT_TRY(cudaStreamSynchronize(st));  // `init` is pageable stack-lifetime memory
-  }
+  // (no byte pattern gives kEmptyKey, so cudaMemset cannot fill the table)
+  dict_clear_kernel<<<kDictSlots / 256, 256, 0, st>>>(keys);
   DICT_TRY(cudaMemsetAsync(state, 0, sizeof(DictState), st));
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 8, (n + 255) / 256));
   if (n > 0) {

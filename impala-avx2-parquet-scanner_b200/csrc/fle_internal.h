@@ -60,6 +60,7 @@ struct fle_ctx {
   int eval_narrow_bw = 2;    // single-pass programs on columns up to this width skip shared-memory staging (bw 1, 2, 4)
   int in_lookup_min = 9;     // IN lists at least this long use the decode+lookup kernel (bw <= 16); shorter ones the plane form
   int codec_variant = 1;
+  int codec_ctas_per_sm = 0;  // 0 = as many as fit
   int eval_jit = 1;                      // 0 never, 1 when n >= eval_jit_min_rows or already compiled, 2 always
   int64_t eval_jit_min_rows = 1ll << 24;
   int64_t h2d_chunk_rows = 0;  // 0 = auto

@@ -24,7 +24,7 @@ def popcount(words):
 # ------------------------------------------------------------------------------------------
 # golden vectors (outputs of the reference's own code)
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("codec_variant", [1, 0])
+@pytest.mark.parametrize("codec_variant", [1, 0, 2, 3, 4])
 @pytest.mark.parametrize("bw", BWS)
 def test_codec_vs_golden(ctx, golden, bw, codec_variant):
     ctx.set_option("codec_variant", codec_variant)
@@ -254,10 +254,15 @@ def test_cfg0_roundtrip_16M(ctx, bw):
     words = ctx.pack_dev(vals, bw)
     out = ctx.unpack_dev(words, bw, 0, n)
     assert torch.equal(out, vals)
-    ctx.set_option("codec_variant", 0)  # the direct-load/store kernels must produce the same bytes
+    # every kernel family must produce the same bytes: 0 direct loads/stores, 2 per-row bulk stores,
+    # 3 warp-private copy-out, 4 staged copy-out (1 = the per-width choice among them, used above)
     try:
-        assert torch.equal(ctx.pack_dev(vals, bw), words)
-        assert torch.equal(ctx.unpack_dev(words, bw, 0, n), vals)
+        for variant in (0, 2, 3, 4):
+            ctx.set_option("codec_variant", variant)
+            assert torch.equal(ctx.pack_dev(vals, bw), words), variant
+            assert torch.equal(ctx.unpack_dev(words, bw, 0, n), vals), variant
+            m = n - 64 * 129 - 37  # ragged: partial last tile and partial last group
+            assert torch.equal(ctx.unpack_dev(words, bw, 0, m), vals[:m]), variant
     finally:
         ctx.set_option("codec_variant", 1)
     # plane image check on a slice: plane i of group g, bit 63-k == bit i of value 64g+k

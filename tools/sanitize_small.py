@@ -23,7 +23,7 @@ n = 64 * 2048 * 2 + 64 * 3 + 7
 for bw in (1, 5, 12, 16, 17, 32):
     vals = rng.integers(0, 1 << bw, size=n, dtype=np.uint64).astype(np.uint32)
     w = orc.pack(vals, bw)
-    for cv in (1, 0):
+    for cv in (1, 0, 2, 3, 4):
         ctx.set_option("codec_variant", cv)
         assert (ctx.pack(vals, bw) == w).all()
         assert (ctx.unpack(w, bw, 0, n) == vals).all()
