@@ -311,6 +311,145 @@ def test_cfg1_between_full_size(ctx):
     assert int(cnt.item()) == want
 
 
+def test_cfg2_q6_full_size(ctx):
+    """config 2: TPC-H Q6 over 600,037,902 rows (shipdate bw 12, discount bw 4, quantity bw 6, compound
+    AND of 5 leaves) + SUM(extendedprice * discount) over the survivors.  Count and the exact int64
+    revenue must equal a torch compare of the values; the fused kernel, the two-kernel path and
+    the interpreting kernel must agree bit for bit; popcount(bitmap) == count."""
+    import torch
+    n = 600_037_902
+    g = torch.Generator(device="cuda").manual_seed(0xF1E00200)
+    price = torch.randint(90_000, 10_500_000, (n,), generator=g, device="cuda", dtype=torch.int64)
+    dd = torch.arange(0, 11, device="cuda", dtype=torch.int64)
+    cols, mask, disc = [], None, None
+    for (d, bw), (lo, hi) in zip(((2526, 12), (11, 4), (50, 6)), ((730, 1094), (5, 7), (0, 22))):
+        v = torch.randint(0, d, (n,), generator=g, device="cuda", dtype=torch.int32)
+        cols.append((ctx.pack_dev(v, bw), bw))
+        m = (v >= lo) & (v <= hi)
+        mask = m if mask is None else (mask & m)
+        if bw == 4:
+            disc = v
+    want_cnt = int(mask.sum().item())
+    want_rev = int((price[mask] * dd[disc[mask].long()]).sum().item())
+    del mask, disc, v, m
+    prog = [(GE, 0, 730), (LE, 0, 1094), (AND, None, None), (GE, 1, 5), (LE, 1, 7), (AND, None, None),
+            (AND, None, None), (LT, 2, 23), (AND, None, None)]
+    bm = torch.empty((n + 63) // 64, dtype=torch.int64, device="cuda")
+    out = ctx.eval_sum_product_dev(cols, prog, n, price, 1, dd, bitmap=bm)
+    torch.cuda.synchronize()
+    assert int(out[0].item()) == want_rev and int(out[1].item()) == want_cnt
+    assert _torch_bits_to_count(bm) == want_cnt
+    bm1, c1 = ctx.eval_dev(cols, prog, n)
+    two = ctx.sum_product_dev(bm1, n, price, cols[1][0], 4, dd)
+    torch.cuda.synchronize()
+    assert torch.equal(bm1, bm) and int(c1.item()) == want_cnt
+    assert int(two[0].item()) == want_rev and int(two[1].item()) == want_cnt
+    for variant in (0, 2):
+        ctx.set_option("eval_variant", variant)
+        try:
+            bmv, cv = ctx.eval_dev(cols, prog, n)
+            torch.cuda.synchronize()
+        finally:
+            ctx.set_option("eval_variant", 1)
+        assert torch.equal(bmv, bm) and int(cv.item()) == want_cnt, variant
+
+
+def test_cfg3_in_lists_and_trees_full_size(ctx):
+    """config 3: IN lists of 8 / 64 / 256 literals on bw 12 and bw 16 columns and Q12- / Q14- / OR-style
+    trees over 600,037,902 rows: counts equal torch.isin / torch compares, popcount(bitmap) == count,
+    lookup kernel and plane form agree bit for bit."""
+    import torch
+    n = 600_037_902
+    g = torch.Generator(device="cuda").manual_seed(0xF1E00300)
+    cpu = torch.Generator().manual_seed(3)
+    for d, bw in ((2526, 12), (40000, 16)):
+        v = torch.randint(0, d, (n,), generator=g, device="cuda", dtype=torch.int32)
+        w = ctx.pack_dev(v, bw)
+        for L in (8, 64, 256):
+            lits = torch.randint(0, d, (L,), generator=cpu)
+            want = int(torch.isin(v, lits.to("cuda", torch.int32)).sum().item())
+            bm, c = ctx.eval_dev([(w, bw)], [(IN, 0, lits.tolist())], n)
+            torch.cuda.synchronize()
+            assert int(c.item()) == want and _torch_bits_to_count(bm) == want, (bw, L)
+            if L == 8:  # the other IN implementation (lookup kernel <-> unrolled equality chains)
+                ctx.set_option("in_lookup_min", 1)
+                try:
+                    bm2, c2 = ctx.eval_dev([(w, bw)], [(IN, 0, lits.tolist())], n)
+                    torch.cuda.synchronize()
+                finally:
+                    ctx.set_option("in_lookup_min", 9)
+                assert torch.equal(bm2, bm) and int(c2.item()) == want
+        del v, w
+    mode = torch.randint(0, 7, (n,), generator=g, device="cuda", dtype=torch.int32)
+    rcpt = torch.randint(0, 2526, (n,), generator=g, device="cuda", dtype=torch.int32)
+    instr = torch.randint(0, 4, (n,), generator=g, device="cuda", dtype=torch.int32)
+    qty = torch.randint(0, 50, (n,), generator=g, device="cuda", dtype=torch.int32)
+    w_mode, w_rcpt, w_instr, w_qty = ctx.pack_dev(mode, 3), ctx.pack_dev(rcpt, 12), ctx.pack_dev(instr, 2), ctx.pack_dev(qty, 6)
+    in_mode = (mode == 1) | (mode == 4)
+    cases = {
+        "q12": ([(w_mode, 3), (w_rcpt, 12)], [(IN, 0, [1, 4]), (GE, 1, 730), (AND, None, None), (LT, 1, 1095), (AND, None, None)],
+                in_mode & (rcpt >= 730) & (rcpt < 1095)),
+        "q14": ([(w_rcpt, 12)], [(GE, 0, 1000), (LT, 0, 1030), (AND, None, None)], (rcpt >= 1000) & (rcpt < 1030)),
+        "or": ([(w_mode, 3), (w_instr, 2), (w_qty, 6)], [(IN, 0, [1, 4]), (EQ, 1, 2), (OR, None, None), (LT, 2, 23), (AND, None, None)],
+               (in_mode | (instr == 2)) & (qty < 23)),
+    }
+    for name, (cols, prog, mask) in cases.items():
+        want = int(mask.sum().item())
+        bm, c = ctx.eval_dev(cols, prog, n)
+        torch.cuda.synchronize()
+        assert int(c.item()) == want and _torch_bits_to_count(bm) == want, name
+        idx = torch.randint(0, n, (100000,), device="cuda")
+        assert torch.equal(((bm[idx >> 6] >> (idx & 63)) & 1).bool(), mask[idx]), name
+
+
+def test_two_contexts_two_threads(ctx, oracle):
+    """The library is re-entrant: one context per scanner thread, each with its own stream
+    (SURVEY 8b threading).  Two threads evaluate different programs at the same time; each result
+    must equal the oracle's."""
+    import threading
+
+    import torch
+
+    import fle_b200
+    rng = np.random.default_rng(4242)
+    n = 64 * 30000 + 17
+    jobs = []
+    for bw, prog_of in ((12, lambda D: [(GE, 0, D // 4), (LE, 0, D // 2), (AND, None, None)]), (7, lambda D: [(IN, 0, list(range(3, 90, 7)))])):
+        vals = rng.integers(0, 1 << bw, size=n, dtype=np.uint64).astype(np.uint32)
+        words = oracle.pack(vals, bw)
+        prog = prog_of(1 << bw)
+        if prog[0][0] == IN:
+            want, wcnt = oracle.pred(IN, words, bw, 0, n, np.array(prog[0][2], dtype=np.uint64))
+        else:
+            a, _ = oracle.pred(GE, words, bw, 0, n, prog[0][2])
+            b, _ = oracle.pred(LE, words, bw, 0, n, prog[1][2])
+            want = a & b
+            wcnt = popcount(want)
+        jobs.append((words, bw, prog, want, wcnt))
+    errors = []
+
+    def worker(job):
+        words, bw, prog, want, wcnt = job
+        try:
+            stream = torch.cuda.Stream()
+            c = fle_b200.FleContext(0, stream.cuda_stream)
+            for _ in range(50):
+                bm, cnt = c.eval([(words, bw)], prog, n)
+                if not ((bm == want).all() and cnt == wcnt):
+                    errors.append((bw, "mismatch"))
+                    break
+            c.close()
+        except Exception as e:  # pragma: no cover
+            errors.append((bw, repr(e)))
+
+    ts = [threading.Thread(target=worker, args=(j,)) for j in jobs]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
+
+
 # ------------------------------------------------------------------------------------------
 # survivor materialisation + the Q6 aggregate (SURVEY 8f-2)
 # ------------------------------------------------------------------------------------------
