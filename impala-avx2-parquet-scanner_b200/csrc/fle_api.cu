@@ -359,6 +359,7 @@ int64_t fle_ctx_get_option(fle_ctx* ctx, const char* name) {
   if (k == "eval_jit_min_rows") return ctx->eval_jit_min_rows;
   if (k == "h2d_chunk_rows") return ctx->h2d_chunk_rows;
   if (k == "jit_launches") return ctx->jit_launches;
+  if (k == "last_mode") return ctx->last_mode;
   if (k == "num_sms") return ctx->num_sms;
   if (k == "max_smem_optin") return ctx->max_smem_optin;
   return -1;

@@ -711,15 +711,30 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
 
   // tile sizing: groups per thread per tile so that a stage is a few tens of KB
   int gpt = 1;
+  // single-pass kernels (tools/eval1_tune.py, profiles/r01_eval1_tune.txt): ONE CTA per SM with 2-3
+  // stages of 40-64 KB beats 2-3 CTAs with the same bytes in flight by 2-8 % (fewer concurrent
+  // streams for the memory system); narrow columns, whose stages stay small, take two CTAs
+  int sp_ctas = 0, sp_stages = 0;
   if (staged) {
     gpt = ctx->eval_gpt;
     const uint32_t bytes_per_gpt = (uint32_t)kNT * sum_bw * 8u;
-    // (measured, tools/sweep.py tune: the interpreting kernel likes ~32 KB stages and 3 CTAs/SM, the
-    //  single-pass kernels ~40 KB, the multi-column specialised kernels ~90 KB with 1-2 CTAs/SM)
-    const uint32_t target = mode == MODE_STAGED ? 32u * 1024u : (mode == MODE_JIT ? 88u * 1024u : 40u * 1024u);
+    // (measured, tools/sweep.py tune: the interpreting kernel likes ~32 KB stages and 3 CTAs/SM,
+    //  the multi-column specialised kernels ~90 KB with 1-2 CTAs/SM)
+    const bool sp_narrow = mode == MODE_SINGLE_PASS && sum_bw <= 5;
+    const uint32_t target = mode == MODE_STAGED ? 32u * 1024u : (mode == MODE_JIT ? 88u * 1024u : (sp_narrow ? 24u * 1024u : 48u * 1024u));
     if (gpt <= 0) gpt = (int)std::max<uint32_t>(1, std::min<uint32_t>(8, (target + bytes_per_gpt / 2) / bytes_per_gpt));
     gpt = std::min(gpt, 8);
     if (mode == MODE_JIT && P.agg_plain) gpt = kJitAggGpt;  // compiled into the kernel (fle_eval_jit.cuh)
+    if (mode == MODE_SINGLE_PASS) {
+      const uint32_t stage = (uint32_t)gpt * bytes_per_gpt;
+      if (sp_narrow) {
+        sp_ctas = stage < 20u * 1024u ? 3 : 2;
+        sp_stages = 3;
+      } else {
+        sp_ctas = 1;
+        sp_stages = (int)std::max<uint32_t>(2, std::min<uint32_t>(4, 150u * 1024u / stage));
+      }
+    }
   }
   // shared memory carve-up: [mbarriers][IN literals][literal masks][slots][stages]
   uint32_t off = 0;
@@ -754,6 +769,11 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
     // least 2 stages per CTA and preferably 3 CTAs (24 warps) per SM
     const uint32_t sm_budget = (uint32_t)ctx->max_smem_per_sm;
     int nst = ctx->eval_stages, want_ctas = ctx->eval_ctas_per_sm;
+    if (nst <= 0 && want_ctas <= 0 && sp_stages > 0 &&
+        (uint64_t)off + 1024u + (uint64_t)sp_stages * P.stage_bytes <= sm_budget / (uint32_t)sp_ctas) {
+      nst = sp_stages;
+      want_ctas = sp_ctas;
+    }
     if (nst <= 0) {
       nst = 0;
       for (int ctas = (want_ctas > 0 ? want_ctas : 3); ctas >= 1 && nst < 2; --ctas) {
@@ -806,6 +826,7 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
     return set_cuda_error(ctx, e, what);
   }
   ctx->launches += 1;
+  ctx->last_mode = mode;
   if (mode == MODE_JIT) ctx->jit_launches += 1;
   return FLE_OK;
 }

@@ -48,6 +48,7 @@ struct fle_ctx {
   struct OccEntry { const void* kern; size_t smem; int blocks; };
   std::vector<OccEntry> occ_cache;
   int64_t launches = 0;
+  int last_mode = -1;        // launch mode of the last fused-eval kernel (tuning scripts)
   int64_t jit_launches = 0;  // ... of which kernels specialised at run time
   std::string last_error;
 
