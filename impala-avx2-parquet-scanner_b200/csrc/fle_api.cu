@@ -97,43 +97,55 @@ static int eval_dev_nullable(fle_ctx* ctx, const fle_col_desc* cols, int ncols,
     if (count_dev) FLE_CUDA_TRY(ctx, cudaMemsetAsync(count_dev, 0, 8, ctx->stream));
     return FLE_OK;
   }
-  // 1. not-null bitmaps + their popcounts
+  // 1. non-null rows per column (one launch, nothing written) ...
   std::vector<uint64_t*> notnull(ncols, nullptr);
   std::vector<uint64_t*> tmp;  // everything to free
   uint64_t* d_counts = nullptr;
-  FLE_CUDA_TRY(ctx, cudaMallocAsync(&d_counts, (size_t)ncols * 8, ctx->stream));
+  FLE_CUDA_TRY(ctx, cudaMallocAsync(&d_counts, (size_t)FLE_MAX_COLS * 8, ctx->stream));
   tmp.push_back(d_counts);
   auto cleanup = [&]() {
     for (uint64_t* p : tmp) cudaFreeAsync(p, ctx->stream);
   };
   int rc = FLE_OK;
-  for (int c = 0; c < ncols && rc == FLE_OK; ++c) {
-    if (cols[c].max_def_level == 0) continue;
-    if (cols[c].max_def_level != 1) { rc = set_error(ctx, FLE_E_UNSUPPORTED, "max_def_level > 1 (nested types)"); break; }
-    if (!cols[c].def_planes) { rc = set_error(ctx, FLE_E_INVALID, "nullable column without def_planes"); break; }
-    cudaError_t e = cudaMallocAsync(&notnull[c], (size_t)nwords * 8, ctx->stream);
-    if (e != cudaSuccess) { rc = set_cuda_error(ctx, e, "cudaMallocAsync(notnull)"); break; }
-    tmp.push_back(notnull[c]);
-    fle_col_desc dc{cols[c].def_planes, cols[c].def_bytes, 1, 0, nullptr, 0};
-    fle_pred_node leaf{FLE_OP_EQ, 0, (uint64_t)cols[c].max_def_level, nullptr, 0, 0};
-    rc = launch_eval(ctx, &dc, 1, &leaf, 1, 0, n, notnull[c], d_counts + c);
-  }
+  for (int c = 0; c < ncols && rc == FLE_OK; ++c)
+    if (cols[c].max_def_level > 1) rc = set_error(ctx, FLE_E_UNSUPPORTED, "max_def_level > 1 (nested types)");
+  if (rc == FLE_OK) rc = launch_def_counts(ctx, cols, ncols, n, d_counts);
   if (rc != FLE_OK) { cleanup(); return rc; }
+  // 2a. ... and, without waiting for them, the fused kernel over the columns as if they were
+  // required: with no NULL anywhere (TPC-H; Impala's writer marks every column OPTIONAL) the data
+  // ordinal IS the row index and this is the answer.  (Skipped when a data stream is too short to
+  // hold n values -- then there are NULLs for sure.)
+  std::vector<fle_col_desc> req(cols, cols + ncols);
+  for (auto& d : req) { d.max_def_level = 0; d.def_planes = nullptr; d.def_bytes = 0; }
+  bool optimistic = true;
+  for (int c = 0; c < ncols; ++c)
+    if (cols[c].bytes < (uint64_t)nwords * (uint64_t)cols[c].bit_width * 8u) optimistic = false;
+  if (optimistic) {
+    rc = launch_eval(ctx, req.data(), ncols, nodes, nnodes, 0, n, bitmap_dev, count_dev);
+    if (rc != FLE_OK) { cleanup(); return rc; }
+  }
   std::vector<uint64_t> h_counts(ncols, 0);
   FLE_CUDA_TRY(ctx, cudaMemcpyAsync(h_counts.data(), d_counts, (size_t)ncols * 8, cudaMemcpyDeviceToHost, ctx->stream));
   FLE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   bool any_null = false;
   for (int c = 0; c < ncols; ++c)
     if (cols[c].max_def_level != 0 && (int64_t)h_counts[c] != n) any_null = true;
-
   if (!any_null) {
-    // 2a. no NULL anywhere: data ordinal == row index
-    std::vector<fle_col_desc> req(cols, cols + ncols);
-    for (auto& d : req) { d.max_def_level = 0; d.def_planes = nullptr; d.def_bytes = 0; }
-    rc = launch_eval(ctx, req.data(), ncols, nodes, nnodes, 0, n, bitmap_dev, count_dev);
+    if (!optimistic) rc = set_error(ctx, FLE_E_BUFFER, "column shorter than the rows requested");
     cleanup();
     return rc;
   }
+  // NULLs present: not-null bitmaps of the nullable columns (def level == max_def_level)
+  for (int c = 0; c < ncols && rc == FLE_OK; ++c) {
+    if (cols[c].max_def_level == 0) continue;
+    cudaError_t e = cudaMallocAsync(&notnull[c], (size_t)nwords * 8, ctx->stream);
+    if (e != cudaSuccess) { rc = set_cuda_error(ctx, e, "cudaMallocAsync(notnull)"); break; }
+    tmp.push_back(notnull[c]);
+    fle_col_desc dc{cols[c].def_planes, cols[c].def_bytes, 1, 0, nullptr, 0};
+    fle_pred_node leaf{FLE_OP_EQ, 0, (uint64_t)cols[c].max_def_level, nullptr, 0, 0};
+    rc = launch_eval(ctx, &dc, 1, &leaf, 1, 0, n, notnull[c], nullptr);
+  }
+  if (rc != FLE_OK) { cleanup(); return rc; }
 
   // 2b. general case: one bitmap per leaf, deposited through its column's not-null bitmap
   std::vector<const uint64_t*> leaf_bm;

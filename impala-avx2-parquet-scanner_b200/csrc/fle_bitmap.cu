@@ -35,6 +35,55 @@ __device__ __forceinline__ uint64_t block_sum(uint64_t v, uint64_t* warp_buf) {
   return t;
 }
 
+// Non-null rows per nullable column = set bits of its def-level stream (1-bit FLE planes: row k of a
+// group at bit 63 - k; def level 1 == present, hdfs-parquet-scanner.cc:890-899), all columns in one
+// launch (blockIdx.y = column).  Impala's writer marks every column OPTIONAL, so this runs on every
+// real scan and usually finds no NULL at all: it only counts, nothing is written.
+struct DefCountParams {
+  const uint64_t* planes[FLE_MAX_COLS];
+  int64_t ngroups, nrows;
+  unsigned long long* counts;
+};
+
+__global__ void __launch_bounds__(kBmThreads) def_count_kernel(const __grid_constant__ DefCountParams P) {
+  __shared__ uint64_t warp_buf[kBmThreads / 32];
+  const uint64_t* pl = P.planes[blockIdx.y];
+  if (!pl) return;
+  uint64_t c = 0;
+  for (int64_t g = (int64_t)blockIdx.x * kBmThreads + threadIdx.x; g < P.ngroups; g += (int64_t)gridDim.x * kBmThreads) {
+    uint64_t w = ldg_stream64(pl + g);
+    const int64_t left = P.nrows - g * 64;
+    if (left < 64) w &= ~0ull << (64 - left);  // (left >= 1 for every g < ngroups)
+    c += __popcll(w);
+  }
+  const uint64_t t = block_sum<kBmThreads>(c, warp_buf);
+  if (threadIdx.x == 0 && t) atomicAdd(&P.counts[blockIdx.y], (unsigned long long)t);
+}
+
+int launch_def_counts(fle_ctx* ctx, const fle_col_desc* cols, int ncols, int64_t n, uint64_t* counts_dev) {
+  if (ncols < 1 || ncols > FLE_MAX_COLS) return set_error(ctx, FLE_E_INVALID, "bad column count");
+  DefCountParams P;
+  P.ngroups = (n + 63) / 64;
+  P.nrows = n;
+  P.counts = reinterpret_cast<unsigned long long*>(counts_dev);
+  for (int c = 0; c < FLE_MAX_COLS; ++c) P.planes[c] = nullptr;
+  for (int c = 0; c < ncols; ++c) {
+    if (cols[c].max_def_level == 0) continue;
+    if (!cols[c].def_planes) return set_error(ctx, FLE_E_INVALID, "nullable column without def_planes");
+    if (reinterpret_cast<uintptr_t>(cols[c].def_planes) & 7) return set_error(ctx, FLE_E_ALIGN, "def_planes must be 8-byte aligned");
+    if (cols[c].def_bytes < (uint64_t)P.ngroups * 8u) return set_error(ctx, FLE_E_BUFFER, "def-level stream shorter than the rows requested");
+    P.planes[c] = reinterpret_cast<const uint64_t*>(cols[c].def_planes);
+  }
+  FLE_CUDA_TRY(ctx, cudaMemsetAsync(counts_dev, 0, (size_t)ncols * 8, ctx->stream));
+  if (P.ngroups == 0) return FLE_OK;
+  const int gx = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 4, (P.ngroups + kBmThreads - 1) / kBmThreads));
+  def_count_kernel<<<dim3(gx, ncols), kBmThreads, 0, ctx->stream>>>(P);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(ctx, e, "def_count launch");
+  ctx->launches += 1;
+  return FLE_OK;
+}
+
 // per-block popcounts (block b covers words [b*kBmWordsPerBlock, ...))
 __global__ void __launch_bounds__(kBmThreads)
 bitmap_block_counts_kernel(const uint64_t* __restrict__ bm, int64_t nbits, int64_t nwords,

@@ -175,6 +175,16 @@ def sweep_programs(ctx, out, n):
                 alg_bytes=G * sum_bw * 8 + G * 8, rows_per_s=n / (mn * 1e-3), count=int(cnt.item()))
         ctx.set_option("eval_variant", 1)
         ctx.set_option("eval_jit", 1)
+    # Q6 the way an Impala-written file presents it: every column OPTIONAL with a def-level stream
+    # (1-bit FLE, hdfs-parquet-table-writer.cc:103-105) that holds no NULL at all.  The call includes
+    # the def-level count kernel and the host sync that decides between the fused and the NULL path.
+    ones = torch.full((G,), -1, dtype=torch.int64, device="cuda")
+    pc = [cols[c] + (ones,) for c in ("shipdate", "discount", "quantity")]
+    prog = [tuple(p) + (None,) * (3 - len(p)) for p in programs["q6"][1]]
+    prep = (ctx.make_col_descs(pc),) + fle_b200.capi._build_program(prog)
+    mn, md = timeit(lambda: ctx.eval_dev(pc, prog, n, bitmap=bm, count=cnt, prepared=prep))
+    rec(out, what="program", name="q6_optional_cols_no_nulls", variant="1j", rows=n, sum_bw=25, ms_min=mn, ms_med=md,
+        alg_bytes=G * 25 * 8 + G * 8, rows_per_s=n / (mn * 1e-3), count=int(cnt.item()))
 
 
 def sweep_tune(ctx, out, n):
