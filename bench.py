@@ -462,9 +462,9 @@ def main():
             },
             "encoded_GBps": alg_bytes * world / (ms_per_step * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": 971.6e6, "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch, "
-                         "profiles/r01_eval1_bw12_ncu_full_summary.txt (900.1 MB + 71.5 MB; algorithmic 975.1 MB)",
-                         "peak_source": peak_src, "kernel": "fle::eval1_kernel<IS_LT=true, K=2, BW=12> (TMA-staged single-pass BETWEEN)",
+                         "traffic": 971.3e6, "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch, "
+                         "profiles/r01_eval1_bw12_ncu_full_summary.txt (900.1 MB + 71.2 MB; algorithmic 975.1 MB)",
+                         "peak_source": peak_src, "kernel": "fle::eval1_kernel<IS_LT=true, K=2, BW=12> (TMA-staged single-pass BETWEEN, 1 CTA per SM x 3 stages of 48 KB)",
                          "algorithmic_bytes_per_launch": alg_bytes, "mean_launch_ms": mean_kern_ms,
                          "min_launch_ms": min(kern_ms), "frac_of_nominal_8TBps": achieved / 8000.0},
             "q6": {"ms": q6_ms, "scan_ms": q6_scan_ms, "two_kernel_ms": q6_two_ms, "rows_per_s": n * world / (q6_ms * 1e-3),
