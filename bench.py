@@ -204,6 +204,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value")
+    ap.add_argument("--no-reduce", action="store_true", help="diagnostic: skip the per-step count all-reduce (N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -279,7 +280,7 @@ def main():
 
     def step(i, timed=False):
         sel = SELECTIVITIES[i % len(SELECTIVITIES)]
-        if world > 1 and timed:
+        if world > 1 and timed and not args.no_reduce:
             # every step's match count is summed over the ranks (8 bytes over NVLink); the
             # reduce of query i is in flight while the kernel of query i+1 runs
             c = count_ring[i:i + 1]
@@ -287,7 +288,7 @@ def main():
             pending.append(dist.all_reduce(c, async_op=True))
         else:
             ctx.eval_dev(cols, progs[sel], n, bitmap=bitmap, count=count, prepared=prepared[sel])
-            if world > 1:
+            if world > 1 and not (timed and args.no_reduce):
                 total.copy_(count)
                 dist.all_reduce(total)
         return sel
@@ -319,7 +320,7 @@ def main():
         w.wait()  # all reduced counts are complete before the clock stops
     t1.record(stream)
     barrier()
-    if world > 1:
+    if world > 1 and not args.no_reduce:
         want_total = torch.tensor([want_counts[SELECTIVITIES[i % len(SELECTIVITIES)]] for i in range(args.steps)],
                                   dtype=torch.int64, device=dev)
         dist.all_reduce(want_total)

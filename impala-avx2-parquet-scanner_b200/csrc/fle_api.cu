@@ -273,8 +273,9 @@ int fle_ctx_create(int device, void* cuda_stream, fle_ctx** out) {
     }
     ctx->own_stream = true;
   }
-  bool ok = cudaMalloc(&ctx->d_ticket, 4) == cudaSuccess &&
-            cudaMemset(ctx->d_ticket, 0, 4) == cudaSuccess &&
+  bool ok = cudaMalloc(&ctx->d_ticket, 8) == cudaSuccess &&  // [0] completion ticket, [1] tile counter
+           
+            cudaMemset(ctx->d_ticket, 0, 8) == cudaSuccess &&
             cudaMalloc(&ctx->d_count, 8) == cudaSuccess &&
             cudaMallocHost(&ctx->h_count, 8) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;

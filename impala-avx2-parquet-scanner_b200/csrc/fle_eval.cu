@@ -815,6 +815,7 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
   if (rc != FLE_OK) return rc;
   P.partial = ctx->d_partial;
   P.ticket = ctx->d_ticket;
+  P.tile_counter = ctx->d_ticket + 1;
   P.in_lits = ctx->d_in_lits;
   void* args[] = {(void*)&P, jit_args};
   cudaError_t e = cudaLaunchKernel(kern, dim3(grid), dim3(kNT), args, smem_bytes, ctx->stream);

@@ -100,10 +100,16 @@ struct PassRegs {
   }
 };
 
+// Tiles are handed out dynamically: the producer thread claims the next tile from a global counter
+// when it arms a stage and passes the tile id to the consumers through shared memory.  With a
+// static split a CTA that starts late or shares its SM (an NCCL reduction of the previous query's
+// count running beside the scan) delays the whole kernel by its full share: 8.5 us per 150 us
+// step on two GPUs; claimed tiles cost such a CTA only the tiles it did not get.
 template <bool IS_LT, int K, int BW>
 __global__ void __launch_bounds__(256) eval1_kernel(const __grid_constant__ EvalParams P) {
   constexpr int NT = 256;
   extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ int64_t stage_tile[8];  // tile held by each stage, -1 = no more tiles
   const uint32_t bar0 = smem_u32(smem + P.smem_bar_off);
   const uint32_t stage0 = smem_u32(smem + P.smem_stage_off);
   const int gpt = P.gpt;
@@ -117,11 +123,22 @@ __global__ void __launch_bounds__(256) eval1_kernel(const __grid_constant__ Eval
     mbar_fence_init();
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < nst - 1; ++s) {
-      const int64_t tile = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
-      if (tile < ntiles) issue_tile(P, bar0, stage0, s, tile, T);
+  // (the claim for the NEXT iteration is issued one iteration early, so the round trip of the
+  //  atomic to L2 -- about one tile's worth of time -- is never waited for)
+  unsigned int next_claim = 0;
+  auto arm = [&](int s, unsigned int claimed) {  // producer thread only
+    const int64_t tile = (int64_t)claimed;
+    if (tile < ntiles) {
+      stage_tile[s] = tile;
+      issue_tile(P, bar0, stage0, s, tile, T);
+    } else {
+      stage_tile[s] = -1;
+      mbar_arrive(bar0 + s * 8);  // completes the phase without data
     }
+  };
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nst - 1; ++s) arm(s, atomicAdd(P.tile_counter, 1u));
+    next_claim = atomicAdd(P.tile_counter, 1u);
   }
 
   PassRegs<IS_LT, K, BW> pr;
@@ -137,15 +154,17 @@ __global__ void __launch_bounds__(256) eval1_kernel(const __grid_constant__ Eval
 
   int stage = 0;
   uint32_t parity = 0;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  while (true) {
     __syncthreads();  // everyone is done with the stage consumed in the previous iteration
     if (threadIdx.x == 0) {
-      const int64_t nxt = tile + (int64_t)(nst - 1) * gridDim.x;
       int st2 = stage + nst - 1;
       if (st2 >= nst) st2 -= nst;
-      if (nxt < ntiles) issue_tile(P, bar0, stage0, st2, nxt, T);
+      arm(st2, next_claim);
+      next_claim = atomicAdd(P.tile_counter, 1u);
     }
     mbar_wait(bar0 + stage * 8, parity);
+    const int64_t tile = stage_tile[stage];
+    if (tile < 0) break;  // (every later stage holds -1 as well: nothing is in flight)
     uint32_t a = stage0 + stage * P.stage_bytes + thread_off;
     int64_t g = tile * T + thread_g;
     for (int q = 0; q < gpt; ++q) {

@@ -75,6 +75,7 @@ __device__ __forceinline__ void publish_totals(const EvalParams& P, uint64_t cnt
       if (P.count_out) *P.count_out = tot;
       if (WITH_SUM && P.agg_sum_out) *P.agg_sum_out = (int64_t)tot2;
       *P.ticket = 0;  // self-reset for the next launch on this stream
+      if (P.tile_counter) *P.tile_counter = 0;
     }
   }
 }

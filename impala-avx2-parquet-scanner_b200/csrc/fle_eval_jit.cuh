@@ -218,11 +218,23 @@ fle_jit_kernel(const __grid_constant__ fle::EvalParams P, const __grid_constant_
   }
   load_in_lits(P, lits_smem);
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < nst - 1; ++s) {
-      const int64_t tile = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
-      if (tile < ntiles) issue_tile(P, bar0, stage0, s, tile, T);
+  // dynamic tile scheduler, as in eval1_kernel (fle_eval1.cu): the producer thread claims tiles from a
+  // global counter one iteration ahead and hands the tile id to the consumers through shared memory
+  __shared__ int64_t stage_tile[8];  // tile held by each stage, -1 = no more tiles
+  unsigned int next_claim = 0;
+  auto arm = [&](int s, unsigned int claimed) {  // producer thread only
+    const int64_t tile = (int64_t)claimed;
+    if (tile < ntiles) {
+      stage_tile[s] = tile;
+      issue_tile(P, bar0, stage0, s, tile, T);
+    } else {
+      stage_tile[s] = -1;
+      mbar_arrive(bar0 + s * 8);  // completes the phase without data
     }
+  };
+  if (threadIdx.x == 0 && nst > 0) {
+    for (int s = 0; s < nst - 1; ++s) arm(s, atomicAdd(P.tile_counter, 1u));
+    next_claim = atomicAdd(P.tile_counter, 1u);
   }
 
   const uint32_t seg = threadIdx.x & 7, jrow = threadIdx.x >> 3;
@@ -236,15 +248,17 @@ fle_jit_kernel(const __grid_constant__ fle::EvalParams P, const __grid_constant_
 #endif
   int stage = 0;
   uint32_t parity = 0;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  while (nst > 0) {
     __syncthreads();  // everyone is done with the stage consumed in the previous iteration
     if (threadIdx.x == 0) {
-      const int64_t nxt = tile + (int64_t)(nst - 1) * gridDim.x;
       int st2 = stage + nst - 1;
       if (st2 >= nst) st2 -= nst;
-      if (nxt < ntiles) issue_tile(P, bar0, stage0, st2, nxt, T);
+      arm(st2, next_claim);
+      next_claim = atomicAdd(P.tile_counter, 1u);
     }
     mbar_wait(bar0 + stage * 8, parity);
+    const int64_t tile = stage_tile[stage];
+    if (tile < 0) break;  // (every later stage holds -1 as well: nothing is in flight)
     JitSmemGroup<kJitNCols> ld;
     jit_stage_addr(P, stage0 + stage * P.stage_bytes, seg, jrow, ld.a);
     int64_t g = tile * T + thread_g;

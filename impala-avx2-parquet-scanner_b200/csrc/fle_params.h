@@ -95,6 +95,7 @@ struct EvalParams {
   uint64_t* bitmap;
   uint64_t* partial;    // per-CTA popcounts (gridDim entries)
   unsigned int* ticket; // self-resetting completion counter
+  unsigned int* tile_counter;  // self-resetting dynamic tile scheduler (single-pass kernels), may be null
   uint64_t* count_out;  // may be null
   const uint32_t* in_lits;
   int32_t n_in_lits;
