@@ -722,7 +722,12 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
     //  the multi-column specialised kernels ~90 KB with 1-2 CTAs/SM)
     const bool sp_narrow = mode == MODE_SINGLE_PASS && sum_bw <= 5;
     const uint32_t target = mode == MODE_STAGED ? 32u * 1024u : (mode == MODE_JIT ? 88u * 1024u : (sp_narrow ? 24u * 1024u : 48u * 1024u));
-    if (gpt <= 0) gpt = (int)std::max<uint32_t>(1, std::min<uint32_t>(8, (target + bytes_per_gpt / 2) / bytes_per_gpt));
+    if (gpt <= 0) {
+      gpt = (int)std::max<uint32_t>(1, std::min<uint32_t>(8, (target + bytes_per_gpt / 2) / bytes_per_gpt));
+      // single-pass tiles of 33-44 KB (bw 17-21 at one group per thread) are too short for the
+      // dynamic tile scheduler (0.86-0.98 of roofline against 1.05 with two groups per thread)
+      if (mode == MODE_SINGLE_PASS && gpt == 1 && bytes_per_gpt > 33u * 1024u && bytes_per_gpt < 44u * 1024u) gpt = 2;
+    }
     gpt = std::min(gpt, 8);
     if (mode == MODE_JIT && P.agg_plain) gpt = kJitAggGpt;  // compiled into the kernel (fle_eval_jit.cuh)
     if (mode == MODE_SINGLE_PASS) {

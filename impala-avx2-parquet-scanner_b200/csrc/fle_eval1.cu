@@ -101,10 +101,13 @@ struct PassRegs {
 };
 
 // Tiles are handed out dynamically: the producer thread claims the next tile from a global counter
-// when it arms a stage and passes the tile id to the consumers through shared memory.  With a
-// static split a CTA that starts late or shares its SM (an NCCL reduction of the previous query's
-// count running beside the scan) delays the whole kernel by its full share: 8.5 us per 150 us
-// step on two GPUs; claimed tiles cost such a CTA only the tiles it did not get.
+// (one iteration before it is used, so the atomic's round trip to L2 is not waited for) and passes
+// the tile id to the consumers through shared memory.  With a static split a CTA that starts late
+// or shares its SM (an NCCL reduction of the previous query's count running beside the scan)
+// delays the whole kernel by its full share: 8.5 us per 150 us step on two GPUs; with claimed tiles
+// such a CTA only costs the tiles it did not get.  Claiming in batches of consecutive tiles was
+// slower (bw 12: 1.04 -> 1.00 of roofline): neighbouring CTAs on neighbouring tiles is what the
+// memory system likes.
 template <bool IS_LT, int K, int BW>
 __global__ void __launch_bounds__(256) eval1_kernel(const __grid_constant__ EvalParams P) {
   constexpr int NT = 256;
@@ -167,6 +170,9 @@ __global__ void __launch_bounds__(256) eval1_kernel(const __grid_constant__ Eval
     if (tile < 0) break;  // (every later stage holds -1 as well: nothing is in flight)
     uint32_t a = stage0 + stage * P.stage_bytes + thread_off;
     int64_t g = tile * T + thread_g;
+    // two groups interleaved (their dependency chains are short of bandwidth-bound on their own:
+    // bw 4 0.91 -> 0.95, bw 12 1.02 -> 1.04)
+#pragma unroll 2
     for (int q = 0; q < gpt; ++q) {
       const uint64_t r = finish_word(pr.run(SmemGroup{a}), g, P.nrows);
       P.bitmap[g] = r;

@@ -276,6 +276,7 @@ fle_jit_kernel(const __grid_constant__ fle::EvalParams P, const __grid_constant_
       g += NT / 8;
     }
 #else
+#pragma unroll FLE_JIT_UNROLL
     for (int q = 0; q < gpt; ++q) {
       const uint64_t r = finish_word(jit_eval_group(P, A, ld, lits_smem), g, P.nrows);
       P.bitmap[g] = r;

@@ -190,6 +190,14 @@ bool jit_plan(const EvalParams& P, const std::vector<uint32_t>& in_lits, JitPlan
     t += b;
   }
   t += "  return s0;\n}\n";
+  {
+    // two groups of a tile interleaved when a group is short (narrow columns: the per-group
+    // dependency chains, not bandwidth, bound such programs); longer groups are better left alone
+    int sum_bw = 0;
+    for (int c = 0; c < P.ncols; ++c) sum_bw += (int)P.bw[c];
+    snprintf(b, sizeof(b), "#define FLE_JIT_UNROLL %d\n", sum_bw <= 16 ? 2 : 1);
+    t += b;
+  }
   if (agg_col >= 0) {
     if (agg_col >= P.ncols) return false;
     const int bw = (int)P.bw[agg_col];
