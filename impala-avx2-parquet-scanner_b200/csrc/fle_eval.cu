@@ -1059,12 +1059,21 @@ __global__ void __launch_bounds__(256) bitmap_combine_kernel(const __grid_consta
     is_last = (atomicAdd(C.ticket, 1u) == gridDim.x - 1);
   }
   __syncthreads();
-  if (is_last && threadIdx.x == 0) {
+  if (is_last) {  // all threads of the last CTA (a serial loop over ~1200 partials costs 20-30 us)
     __threadfence();
-    uint64_t tot = 0;
-    for (unsigned int i = 0; i < gridDim.x; ++i) tot += *((volatile uint64_t*)&C.partial[i]);
-    if (C.count_out) *C.count_out = tot;
-    *C.ticket = 0;
+    uint64_t t = 0;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += 256) t += *((volatile uint64_t*)&C.partial[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint64_t tot = 0;
+      for (int w = 0; w < 8; ++w) tot += warp_cnt[w];
+      if (C.count_out) *C.count_out = tot;
+      *C.ticket = 0;
+    }
   }
 }
 

@@ -108,7 +108,20 @@ __device__ __forceinline__ bool plain_test(T v, T lit0, const T* lits_s, int nli
   return p;
 }
 
-template <typename T, int OP>
+// bits i of x (i < 8) -> bit 4 i
+__device__ __forceinline__ uint32_t spread8_by4(uint32_t x) {
+  x = (x | (x << 12)) & 0x000F000Fu;
+  x = (x | (x << 6)) & 0x03030303u;
+  x = (x | (x << 3)) & 0x11111111u;
+  return x;
+}
+
+// VEC = 4 (4-byte types on 16-byte aligned columns): a lane loads 4 consecutive values with one
+// 128-bit load, 4 x 16 bytes in flight per lane (one 4-byte load per lane and 8 in flight left the
+// kernel latency-bound at 0.83 of roofline; 8-byte types reach 0.93-0.96 that way).  Ballot j then
+// holds rows 4 l + j of a 128-row block, and the four 32-row words of the block are byte k of the
+// four ballots interleaved bit by bit.
+template <typename T, int OP, int VEC>
 __global__ void __launch_bounds__(256) plain_eval_kernel(const PlainParams P) {
   __shared__ T lits_s[OP == FLE_OP_IN ? kPlainMaxLits : 1];
   __shared__ uint64_t warp_cnt[8];
@@ -124,11 +137,32 @@ __global__ void __launch_bounds__(256) plain_eval_kernel(const PlainParams P) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * 256) >> 5;
-  constexpr int U = 8;  // 32-row words per warp iteration: 8 coalesced loads in flight per lane
+  constexpr int U = VEC == 4 ? 16 : 8;  // 32-row words per warp iteration (VEC = 1: 8 coalesced loads in flight per lane)
   uint64_t cnt = 0;
   for (int64_t w0 = warp * U; w0 < P.nwords32; w0 += nwarps * U) {
     uint32_t mine = 0;
-    if ((w0 + U) * 32 <= P.n) {  // whole iteration inside the column: no bounds checks
+    if (VEC == 4 && sizeof(T) == 4 && (w0 + U) * 32 <= P.n) {
+      const uint4* p4 = reinterpret_cast<const uint4*>(vals + w0 * 32) + lane;
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = ldg_stream128(p4 + u * 32);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t raw[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        uint32_t b[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          T x;
+          memcpy(&x, &raw[j], 4);
+          b[j] = __ballot_sync(0xffffffffu, plain_test<OP, T>(x, lit0, lits_s, P.nlits));
+        }
+        if ((lane >> 2) == u) {  // lane 4 u + k assembles word k of block u
+          const int sh = (lane & 3) * 8;
+          mine = spread8_by4((b[0] >> sh) & 0xFFu) | (spread8_by4((b[1] >> sh) & 0xFFu) << 1) |
+                 (spread8_by4((b[2] >> sh) & 0xFFu) << 2) | (spread8_by4((b[3] >> sh) & 0xFFu) << 3);
+        }
+      }
+    } else if (VEC != 4 && (w0 + U) * 32 <= P.n) {  // whole iteration inside the column: no bounds checks
       const T* p = vals + w0 * 32 + lane;
       T v[U];
 #pragma unroll
@@ -164,24 +198,33 @@ __global__ void __launch_bounds__(256) plain_eval_kernel(const PlainParams P) {
     is_last = (atomicAdd(P.ticket, 1u) == gridDim.x - 1);
   }
   __syncthreads();
-  if (is_last && threadIdx.x == 0) {
+  if (is_last) {  // the last CTA sums the per-CTA counts, all threads (a serial loop over ~1200 partials cost 20-30 us)
     __threadfence();
-    uint64_t tot = 0;
-    for (unsigned int i = 0; i < gridDim.x; ++i) tot += *((volatile uint64_t*)&P.partial[i]);
-    if (P.count_out) *P.count_out = tot;
-    *P.ticket = 0;
+    uint64_t t = 0;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += 256) t += *((volatile uint64_t*)&P.partial[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    __syncthreads();
+    if (lane == 0) warp_cnt[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint64_t tot = 0;
+      for (int i = 0; i < 8; ++i) tot += warp_cnt[i];
+      if (P.count_out) *P.count_out = tot;
+      *P.ticket = 0;
+    }
   }
 }
 
-template <typename T>
+template <typename T, int VEC>
 void launch_plain_typed(const PlainParams& P, int op, int grid, cudaStream_t st) {
   switch (op) {
-    case FLE_OP_EQ: plain_eval_kernel<T, FLE_OP_EQ><<<grid, 256, 0, st>>>(P); break;
-    case FLE_OP_LT: plain_eval_kernel<T, FLE_OP_LT><<<grid, 256, 0, st>>>(P); break;
-    case FLE_OP_LE: plain_eval_kernel<T, FLE_OP_LE><<<grid, 256, 0, st>>>(P); break;
-    case FLE_OP_GT: plain_eval_kernel<T, FLE_OP_GT><<<grid, 256, 0, st>>>(P); break;
-    case FLE_OP_GE: plain_eval_kernel<T, FLE_OP_GE><<<grid, 256, 0, st>>>(P); break;
-    default: plain_eval_kernel<T, FLE_OP_IN><<<grid, 256, 0, st>>>(P); break;
+    case FLE_OP_EQ: plain_eval_kernel<T, FLE_OP_EQ, VEC><<<grid, 256, 0, st>>>(P); break;
+    case FLE_OP_LT: plain_eval_kernel<T, FLE_OP_LT, VEC><<<grid, 256, 0, st>>>(P); break;
+    case FLE_OP_LE: plain_eval_kernel<T, FLE_OP_LE, VEC><<<grid, 256, 0, st>>>(P); break;
+    case FLE_OP_GT: plain_eval_kernel<T, FLE_OP_GT, VEC><<<grid, 256, 0, st>>>(P); break;
+    case FLE_OP_GE: plain_eval_kernel<T, FLE_OP_GE, VEC><<<grid, 256, 0, st>>>(P); break;
+    default: plain_eval_kernel<T, FLE_OP_IN, VEC><<<grid, 256, 0, st>>>(P); break;
   }
 }
 
@@ -209,8 +252,9 @@ int launch_plain_eval(fle_ctx* ctx, const void* values_dev, int elem_type, int64
   P.bitmap = reinterpret_cast<uint32_t*>(bitmap_dev);
   P.nwords32 = ((n + 63) / 64) * 2;
   P.count_out = count_dev;
-  const int64_t warps_needed = (P.nwords32 + 7) / 8;
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 8, (warps_needed + 7) / 8));
+  const bool vec4 = es == 4 && (reinterpret_cast<uintptr_t>(values_dev) & 15) == 0;
+  const int64_t warps_needed = (P.nwords32 + (vec4 ? 15 : 7)) / (vec4 ? 16 : 8);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * (es == 8 ? 6 : 8), (warps_needed + 7) / 8));
   int rc = ensure_scratch(ctx, grid, std::max(2 * nlits, 2));
   if (rc != FLE_OK) return rc;
   if (nlits <= kPlainInlineLits) {
@@ -233,10 +277,10 @@ int launch_plain_eval(fle_ctx* ctx, const void* values_dev, int elem_type, int64
     else if (op == FLE_OP_GE) kop = FLE_OP_LE;
   }
   switch (elem_type) {
-    case 0: launch_plain_typed<int32_t>(P, kop, grid, ctx->stream); break;
-    case 1: launch_plain_typed<int64_t>(P, kop, grid, ctx->stream); break;
-    case 2: launch_plain_typed<float>(P, kop, grid, ctx->stream); break;
-    case 3: launch_plain_typed<double>(P, kop, grid, ctx->stream); break;
+    case 0: vec4 ? launch_plain_typed<int32_t, 4>(P, kop, grid, ctx->stream) : launch_plain_typed<int32_t, 1>(P, kop, grid, ctx->stream); break;
+    case 1: launch_plain_typed<int64_t, 1>(P, kop, grid, ctx->stream); break;
+    case 2: vec4 ? launch_plain_typed<float, 4>(P, kop, grid, ctx->stream) : launch_plain_typed<float, 1>(P, kop, grid, ctx->stream); break;
+    case 3: launch_plain_typed<double, 1>(P, kop, grid, ctx->stream); break;
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(ctx, e, "plain_eval launch");
