@@ -109,8 +109,15 @@ int fle_ctx_sync(fle_ctx* ctx);
  * once the rows evaluated with the shape in this process (this call included) reach
  * "eval_jit_min_rows" (default 2^24; the compilation happens inside that call), 2 = always; without a usable libnvrtc.so.12 modes 0/1 use the interpreting
  * kernels and mode 2 fails with FLE_E_UNSUPPORTED),
- * "eval_stages", "eval_ctas_per_sm", "eval_gpt" (0 = auto), "codec_variant",
- * "h2d_chunk_rows". */
+ * "eval_stages", "eval_ctas_per_sm", "eval_gpt" (0 = auto: launch shape of the staged kernels),
+ * "eval_narrow_bw" (single-pass programs on columns up to this width -- default 2; 1, 2 or 4
+ * exist -- read the planes with coalesced 128-bit loads instead of staging them),
+ * "in_lookup_min" (IN lists of at least this many literals on columns of <= 16 bits use the
+ * decode + membership-lookup kernel, shorter ones equality chains on the planes; default 9,
+ * 2^30 disables the lookup kernel),
+ * "codec_variant" (0 = direct loads/stores; 1 [default] = per-bit-width choice among the staged
+ * unpack kernels; 2 = per-row bulk stores, 3 = warp-private copy-out, 4 = CTA-wide copy-out),
+ * "codec_ctas_per_sm" (0 = auto), "h2d_chunk_rows". */
 int fle_ctx_set_option(fle_ctx* ctx, const char* name, int64_t value);
 int64_t fle_ctx_get_option(fle_ctx* ctx, const char* name);
 /* Number of kernels of this library launched through ctx so far (bench `gpu_launches`). */
