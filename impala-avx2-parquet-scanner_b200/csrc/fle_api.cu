@@ -147,49 +147,107 @@ static int eval_dev_nullable(fle_ctx* ctx, const fle_col_desc* cols, int ncols,
   }
   if (rc != FLE_OK) { cleanup(); return rc; }
 
-  // 2b. general case: one bitmap per leaf, deposited through its column's not-null bitmap
-  std::vector<const uint64_t*> leaf_bm;
-  std::vector<fle_pred_node> prog(nodes, nodes + nnodes);
-  for (int i = 0; i < nnodes && rc == FLE_OK; ++i) {
-    const fle_pred_node& nd = nodes[i];
-    if (nd.op == FLE_OP_AND || nd.op == FLE_OP_OR) continue;
-    const bool is_const = nd.op == FLE_OP_ALL || nd.op == FLE_OP_NONE;
-    const bool nullable = nd.col >= 0 && nd.col < ncols && cols[nd.col].max_def_level != 0;
-    if (is_const && !nullable) continue;  // stays a constant in the combine program
-    if (!is_const && (nd.col < 0 || nd.col >= ncols)) { rc = set_error(ctx, FLE_E_INVALID, "leaf column out of range"); break; }
-    uint64_t* lb = nullptr;
-    cudaError_t e = cudaMallocAsync(&lb, (size_t)nwords * 8, ctx->stream);
-    if (e != cudaSuccess) { rc = set_cuda_error(ctx, e, "cudaMallocAsync(leaf)"); break; }
-    tmp.push_back(lb);
-    if (!nullable) {
-      fle_col_desc dc = cols[nd.col];
-      fle_pred_node leaf = nd;
-      leaf.col = 0;
-      rc = launch_eval(ctx, &dc, 1, &leaf, 1, 0, n, lb, nullptr);
+  // 2b. general case.  A NULL row yields 0 in every leaf, and the deposit through the not-null
+  // bitmap (IntersectBitset) is a bit-wise injection, so it distributes over AND and OR:
+  // deposit(a) op deposit(b) == deposit(a op b).  Every maximal subtree whose leaves sit on ONE
+  // nullable column is therefore evaluated as one fused program in the data-ordinal domain and
+  // deposited once; every maximal subtree over required columns only is one fused program over
+  // the rows; the remaining (mixed) operators combine those bitmaps word by word.
+  constexpr int kReq = -1, kMixed = -2;
+  std::vector<int> node_start(nnodes, 0), node_cls(nnodes, kMixed);
+  {
+    std::vector<int> stack;  // node index of the subtree roots
+    for (int i = 0; i < nnodes && rc == FLE_OK; ++i) {
+      const fle_pred_node& nd = nodes[i];
+      if (nd.op == FLE_OP_AND || nd.op == FLE_OP_OR) {
+        if (stack.size() < 2) { rc = set_error(ctx, FLE_E_INVALID, "malformed postfix program"); break; }
+        const int rb = stack.back(); stack.pop_back();
+        const int ra = stack.back(); stack.pop_back();
+        node_start[i] = node_start[ra];
+        node_cls[i] = (node_cls[ra] == node_cls[rb] && node_cls[ra] != kMixed) ? node_cls[ra] : kMixed;
+      } else {
+        const bool is_const = nd.op == FLE_OP_ALL || nd.op == FLE_OP_NONE;
+        const bool in_range = nd.col >= 0 && nd.col < ncols;
+        if (!is_const && !in_range) { rc = set_error(ctx, FLE_E_INVALID, "leaf column out of range"); break; }
+        const bool nullable = in_range && cols[nd.col].max_def_level != 0;
+        node_start[i] = i;
+        node_cls[i] = nullable ? nd.col : (is_const ? kMixed : kReq);  // a constant without a nullable column stays a constant
+      }
+      stack.push_back(i);
+    }
+    if (rc == FLE_OK && stack.size() != 1) rc = set_error(ctx, FLE_E_INVALID, "malformed postfix program");
+  }
+  if (rc != FLE_OK) { cleanup(); return rc; }
+  // maximal single-class subtrees, found from the root downwards ([node_start, i] is contiguous in postfix)
+  std::vector<std::pair<int, int> > subs;  // [start, end]
+  for (int i = nnodes - 1; i >= 0;) {
+    if (node_cls[i] != kMixed) {
+      subs.push_back(std::make_pair(node_start[i], i));
+      i = node_start[i] - 1;
     } else {
-      const fle_col_desc& col = cols[nd.col];
-      const int64_t m = (int64_t)h_counts[nd.col];  // non-null values = rows of the data stream
-      FLE_CUDA_TRY(ctx, cudaMemcpyAsync(lb, notnull[nd.col], (size_t)nwords * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-      if (nd.op == FLE_OP_NONE || m == 0) {
-        FLE_CUDA_TRY(ctx, cudaMemsetAsync(lb, 0, (size_t)nwords * 8, ctx->stream));
-      } else if (nd.op != FLE_OP_ALL) {
-        uint64_t* db = nullptr;
-        e = cudaMallocAsync(&db, (size_t)((m + 63) / 64) * 8, ctx->stream);
-        if (e != cudaSuccess) { rc = set_cuda_error(ctx, e, "cudaMallocAsync(data bitmap)"); break; }
-        tmp.push_back(db);
-        fle_col_desc dc{col.planes, col.bytes, col.bit_width, 0, nullptr, 0};
-        fle_pred_node leaf = nd;
-        leaf.col = 0;
-        rc = launch_eval(ctx, &dc, 1, &leaf, 1, 0, m, db, nullptr);
-        if (rc == FLE_OK) rc = launch_intersect(ctx, lb, n, db, m);
+      --i;
+    }
+  }
+  std::sort(subs.begin(), subs.end());
+  std::vector<const uint64_t*> leaf_bm;
+  std::vector<fle_pred_node> prog;  // the combine program: mixed nodes + one leaf per subtree
+  size_t si = 0;
+  auto alloc_words = [&](uint64_t** p, int64_t words) {
+    cudaError_t e = cudaMallocAsync(p, (size_t)std::max<int64_t>(words, 1) * 8, ctx->stream);
+    if (e != cudaSuccess) return set_cuda_error(ctx, e, "cudaMallocAsync(nullable path)");
+    tmp.push_back(*p);
+    return (int)FLE_OK;
+  };
+  for (int i = 0; i < nnodes && rc == FLE_OK; ++i) {
+    if (si >= subs.size() || i < subs[si].first) {  // mixed operator or plain constant: copied
+      prog.push_back(nodes[i]);
+      continue;
+    }
+    const int s0 = subs[si].first, s1 = subs[si].second, cls = node_cls[s1];
+    ++si;
+    i = s1;
+    uint64_t* lb = nullptr;
+    rc = alloc_words(&lb, nwords);
+    if (rc != FLE_OK) break;
+    std::vector<fle_pred_node> sub(nodes + s0, nodes + s1 + 1);
+    if (cls == kReq) {
+      // required columns only: remap the columns the subtree uses to 0..k-1
+      std::vector<int> map(ncols, -1);
+      std::vector<fle_col_desc> dc;
+      for (auto& nd : sub) {
+        if (nd.op == FLE_OP_AND || nd.op == FLE_OP_OR) continue;
+        if (map[nd.col] < 0) { map[nd.col] = (int)dc.size(); dc.push_back(cols[nd.col]); }
+        nd.col = map[nd.col];
+      }
+      rc = launch_eval(ctx, dc.data(), (int)dc.size(), sub.data(), (int)sub.size(), 0, n, lb, nullptr);
+    } else {
+      const fle_col_desc& col = cols[cls];
+      const int64_t m = (int64_t)h_counts[cls];  // non-null values = rows of the data stream
+      const bool single = sub.size() == 1;
+      if (m == 0 || (single && sub[0].op == FLE_OP_NONE)) {
+        cudaError_t e = cudaMemsetAsync(lb, 0, (size_t)nwords * 8, ctx->stream);
+        if (e != cudaSuccess) rc = set_cuda_error(ctx, e, "cudaMemsetAsync(leaf)");
+      } else {
+        cudaError_t e = cudaMemcpyAsync(lb, notnull[cls], (size_t)nwords * 8, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e != cudaSuccess) rc = set_cuda_error(ctx, e, "cudaMemcpyAsync(notnull)");
+        if (rc == FLE_OK && !(single && sub[0].op == FLE_OP_ALL)) {
+          uint64_t* db = nullptr;
+          rc = alloc_words(&db, (m + 63) / 64);
+          if (rc != FLE_OK) break;
+          fle_col_desc dc{col.planes, col.bytes, col.bit_width, 0, nullptr, 0};
+          for (auto& nd : sub)
+            if (nd.op != FLE_OP_AND && nd.op != FLE_OP_OR) nd.col = 0;
+          rc = launch_eval(ctx, &dc, 1, sub.data(), (int)sub.size(), 0, m, db, nullptr);
+          if (rc == FLE_OK) rc = launch_intersect(ctx, lb, n, db, m);
+        }
       }
     }
-    prog[i].op = FLE_OP_EQ;  // any leaf opcode: the combine kernel only looks at .col
-    prog[i].col = (int32_t)leaf_bm.size();
+    fle_pred_node ref{FLE_OP_EQ, (int32_t)leaf_bm.size(), 0, nullptr, 0, 0};  // any leaf opcode: the combine kernel only looks at .col
+    prog.push_back(ref);
     leaf_bm.push_back(lb);
   }
   if (rc == FLE_OK)
-    rc = launch_bitmap_combine(ctx, leaf_bm.data(), (int)leaf_bm.size(), prog.data(), nnodes, n, bitmap_dev, count_dev);
+    rc = launch_bitmap_combine(ctx, leaf_bm.data(), (int)leaf_bm.size(), prog.data(), (int)prog.size(), n, bitmap_dev, count_dev);
   cleanup();
   return rc;
 }

@@ -223,15 +223,21 @@ def test_nullable_columns_vs_oracle(ctx, oracle, null_frac):
         sub = oracle.pred(op, cols[ci][0], bws[ci], 0, len(data), lits)[0]  # dict_decoder_->Op(count, ...)
         return oracle.intersect_bitset(root, n, sub)[0]                # IntersectBitset
 
-    st = []
-    for op, ci, lits in prog:
-        if op <= IN:
-            st.append(leaf(op, ci, lits))
-        else:
-            b = st.pop()
-            st[-1] = st[-1] & b if op == AND else st[-1] | b
-    bm, cnt = ctx.eval(cols, prog, n)
-    assert (bm == st[0]).all() and cnt == popcount(st[0])
+    # a second tree with larger single-column subtrees (fused per column in the data-ordinal domain),
+    # a two-leaf subtree on the required column and a whole-program-on-one-column case
+    prog2 = [(GE, 0, 730), (LE, 0, 1094), (AND, None, None), (EQ, 0, 5), (OR, None, None),
+             (LT, 2, 10), (GT, 2, 40), (OR, None, None), (IN, 1, [3, 4, 20]), (AND, None, None), (AND, None, None)]
+    prog3 = [(GE, 1, 3), (LE, 1, 9), (AND, None, None), (EQ, 1, 20), (OR, None, None)]
+    for pr in (prog, prog2, prog3):
+        st = []
+        for op, ci, lits in pr:
+            if op <= IN:
+                st.append(leaf(op, ci, lits))
+            else:
+                b = st.pop()
+                st[-1] = st[-1] & b if op == AND else st[-1] | b
+        bm, cnt = ctx.eval(cols, pr, n)
+        assert (bm == st[0]).all() and cnt == popcount(st[0]), pr
 
 
 # ------------------------------------------------------------------------------------------
