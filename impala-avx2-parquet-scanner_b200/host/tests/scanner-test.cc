@@ -98,7 +98,8 @@ static bool RowPasses(const Table& t, int r) {
 }
 
 static void RunScan(const Table& t, bool nullable, int pp0, int pp1, int pp2, bool fused, vector<uint8_t>* rows,
-                    int64_t* passed, int64_t* fused_evals, int64_t* leaf_windows, int* tuple_size, int offs[3]) {
+                    int64_t* passed, int64_t* fused_evals, int64_t* leaf_windows, int* tuple_size, int offs[3],
+                    bool device = true, int64_t* device_spans = NULL) {
   ColumnChunk c0 = WriteColumn(t.shipdate, t.nn_shipdate, pp0, nullable);
   ColumnChunk c1 = WriteColumn(t.discount, t.nn_discount, pp1, nullable);
   ColumnChunk c2 = WriteColumn(t.quantity, t.nn_quantity, pp2, nullable);
@@ -120,8 +121,10 @@ static void RunScan(const Table& t, bool nullable, int pp0, int pp1, int pp2, bo
   scanner.AddSimplePredicate(&le1);
   scanner.AddSimplePredicate(&lt2);
   scanner.set_fused(fused);
+  scanner.set_device_materialise(device);
   Status st = scanner.AssembleRows(t.n, rows, passed);
   EXPECT_TRUE(st.ok());
+  if (device_spans) *device_spans = scanner.device_spans();
   *fused_evals = scanner.fused_evals();
   *leaf_windows = scanner.leaf_windows();
   *tuple_size = scanner.tuple_size();
@@ -136,9 +139,20 @@ static void CheckScan(const Table& t, bool nullable, int pp0, int pp1, int pp2, 
   vector<uint8_t> rows_f, rows_l;
   int64_t passed_f = 0, passed_l = 0, fe = 0, lw = 0, fe2 = 0, lw2 = 0;
   int ts = 0, ts2 = 0, offs[3], offs2[3];
-  RunScan(tt, nullable, pp0, pp1, pp2, true, &rows_f, &passed_f, &fe, &lw, &ts, offs);
+  int64_t spans = 0;
+  RunScan(tt, nullable, pp0, pp1, pp2, true, &rows_f, &passed_f, &fe, &lw, &ts, offs, true, &spans);
   RunScan(tt, nullable, pp0, pp1, pp2, false, &rows_l, &passed_l, &fe2, &lw2, &ts2, offs2);
   EXPECT_EQ(fe2, 0);
+  {  // fused evaluation with the survivors materialised on the host (ReadValue(skip) per survivor):
+     // must give the same bytes as the device-resident page-span path
+    vector<uint8_t> rows_h;
+    int64_t passed_h = 0, fe3 = 0, lw3 = 0, spans_h = 0;
+    int ts3 = 0, offs3[3];
+    RunScan(tt, nullable, pp0, pp1, pp2, true, &rows_h, &passed_h, &fe3, &lw3, &ts3, offs3, false, &spans_h);
+    EXPECT_EQ(spans_h, 0);
+    EXPECT_EQ(passed_h, passed_f);
+    EXPECT_TRUE(rows_h == rows_f);
+  }
   if (expect_fused) { EXPECT_TRUE(fe > 0); EXPECT_EQ(lw, 0); }
   EXPECT_EQ(passed_f, passed_l);
   EXPECT_TRUE(rows_f == rows_l);  // fused and per-leaf paths agree byte for byte
@@ -156,10 +170,14 @@ static void CheckScan(const Table& t, bool nullable, int pp0, int pp1, int pp2, 
   }
   EXPECT_EQ(passed_f, want);
   EXPECT_EQ(bad, 0);
-  std::printf("    rows=%d nullable=%d pages=%d/%d/%d survivors=%lld fused_evals=%lld leaf_windows=%lld\n", tt.n,
-              (int)nullable, pp0, pp1, pp2, (long long)passed_f, (long long)fe, (long long)lw);
+  std::printf("    rows=%d nullable=%d pages=%d/%d/%d survivors=%lld fused_evals=%lld leaf_windows=%lld device_spans=%lld\n", tt.n,
+              (int)nullable, pp0, pp1, pp2, (long long)passed_f, (long long)fe, (long long)lw, (long long)spans);
 }
 
+TEST(Scanner, EqualPagesDeviceSpans) {  // several whole-page spans, the last one ragged
+  CheckScan(MakeTable(64 * 3000 + 17, 0, 11), false, 64 * 700, 64 * 700, 64 * 700, true);
+  CheckScan(MakeTable(64 * 3000 + 17, 0, 12), true, 50001, 50001, 50001, true);
+}
 TEST(Scanner, RequiredColumnsOnePage) { CheckScan(MakeTable(64 * 3000 + 17, 0, 1), false, 1 << 30, 1 << 30, 1 << 30, true); }
 TEST(Scanner, RequiredColumnsAlignedPages) { CheckScan(MakeTable(64 * 3000 + 17, 0, 2), false, 64 * 500, 64 * 1000, 64 * 250, true); }
 TEST(Scanner, RequiredColumnsRaggedPages) { CheckScan(MakeTable(64 * 1000 + 5, 0, 3), false, 10007, 64 * 300, 33333, false); }
