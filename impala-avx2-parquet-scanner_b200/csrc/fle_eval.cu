@@ -639,11 +639,11 @@ namespace {
 inline uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 constexpr int kNT = 256;
-enum LaunchMode { MODE_DIRECT = 0, MODE_STAGED = 1, MODE_SINGLE_PASS = 2, MODE_IN_LOOKUP = 3, MODE_JIT = 4, MODE_NARROW = 5 };
+enum LaunchMode { MODE_DIRECT = 0, MODE_STAGED = 1, MODE_SINGLE_PASS = 2, MODE_IN_LOOKUP = 3, MODE_JIT = 4, MODE_NARROW = 5, MODE_IN_WIDE = 6 };
 
 // cudaOccupancyMaxActiveBlocksPerMultiprocessor / cudaFuncSetAttribute are not free; remember
 // the answers per (kernel, dynamic smem)
-int blocks_per_sm(fle_ctx* ctx, const void* kern, size_t smem_bytes, int* out) {
+int blocks_per_sm(fle_ctx* ctx, const void* kern, size_t smem_bytes, int* out, int nt = kNT) {
   for (const auto& e : ctx->occ_cache) {
     if (e.kern == kern && e.smem == smem_bytes) {
       *out = e.blocks;
@@ -670,16 +670,16 @@ int blocks_per_sm(fle_ctx* ctx, const void* kern, size_t smem_bytes, int* out) {
     }
   }
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kNT, smem_bytes);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nt, smem_bytes);
   if (e != cudaSuccess) {
     // (kernels loaded at run time: older runtimes answer only for statically linked functions)
     cudaGetLastError();
     cudaFuncAttributes fa;
     e = cudaFuncGetAttributes(&fa, kern);
     if (e != cudaSuccess) return set_cuda_error(ctx, e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-    const int regs_per_cta = ((std::max(fa.numRegs, 16) + 7) / 8 * 8) * kNT;
+    const int regs_per_cta = ((std::max(fa.numRegs, 16) + 7) / 8 * 8) * nt;
     const size_t smem_per_cta = smem_bytes + fa.sharedSizeBytes + 1024;
-    per_sm = (int)std::min<size_t>(std::min<size_t>(65536 / regs_per_cta, 2048 / kNT),
+    per_sm = (int)std::min<size_t>(std::min<size_t>(65536 / regs_per_cta, 2048 / nt),
                                    (size_t)ctx->max_smem_per_sm / smem_per_cta);
   }
   ctx->occ_cache.push_back({kern, smem_bytes, per_sm});
@@ -691,6 +691,8 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
                    void* jit_args = nullptr, bool jit_staged = true) {
   const int64_t G = P.ngroups;
   const void* kern = nullptr;
+  int nt = kNT;       // threads per CTA
+  int tile_nt = kNT;  // threads that share a tile (entry-table IN kernel: a consumer group of the CTA)
   if (mode == MODE_JIT) {
     kern = jit_kern;
   } else if (mode == MODE_SINGLE_PASS) {
@@ -698,6 +700,11 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
     if (!kern) return FLE_E_UNSUPPORTED;
   } else if (mode == MODE_IN_LOOKUP) {
     kern = eval_in_kernel_for((int)P.bw[0]);
+    if (!kern) return FLE_E_UNSUPPORTED;
+  } else if (mode == MODE_IN_WIDE) {
+    nt = kInWideThreadsPerCta;
+    tile_nt = ctx->in_wide_group;
+    kern = eval_in_wide_kernel_for((int)P.bw[0], tile_nt);
     if (!kern) return FLE_E_UNSUPPORTED;
   } else if (mode == MODE_NARROW) {
     kern = eval1_narrow_kernel_for(P.passes[0].type, P.passes[0].k, (int)P.bw[0]);
@@ -717,7 +724,7 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
   int sp_ctas = 0, sp_stages = 0;
   if (staged) {
     gpt = ctx->eval_gpt;
-    const uint32_t bytes_per_gpt = (uint32_t)kNT * sum_bw * 8u;
+    const uint32_t bytes_per_gpt = (uint32_t)tile_nt * sum_bw * 8u;
     // (measured, tools/sweep.py tune: the interpreting kernel likes ~32 KB stages and 3 CTAs/SM,
     //  the multi-column specialised kernels ~90 KB with 1-2 CTAs/SM)
     const bool sp_narrow = mode == MODE_SINGLE_PASS && sum_bw <= 5;
@@ -729,6 +736,7 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
       if (mode == MODE_SINGLE_PASS && gpt == 1 && bytes_per_gpt > 33u * 1024u && bytes_per_gpt < 44u * 1024u) gpt = 2;
     }
     gpt = std::min(gpt, 8);
+    if (mode == MODE_IN_WIDE && ctx->eval_gpt <= 0) gpt = 1;  // the table leaves room for 24-48 KB stages only
     if (mode == MODE_JIT && P.agg_plain) gpt = kJitAggGpt;  // compiled into the kernel (fle_eval_jit.cuh)
     if (mode == MODE_SINGLE_PASS) {
       const uint32_t stage = (uint32_t)gpt * bytes_per_gpt;
@@ -753,6 +761,7 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
     const uint32_t tbytes = std::max(4u, (1u << P.bw[0]) / 8u);
     off += P.bw[0] <= 13 ? tbytes * 33u : tbytes;
   }
+  if (mode == MODE_IN_WIDE) off += eval_in_wide_table_bytes((int)P.bw[0]);  // 16-bit entries x 32 lanes
   P.smem_slots_off = off;
   if (mode == MODE_DIRECT || mode == MODE_STAGED) off += (uint32_t)P.nslots * kNT * 8u;
   off = round_up(off, 128);
@@ -762,7 +771,8 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
   size_t smem_bytes = off;
   int rc;
   if (staged) {
-    const int T = kNT * gpt;
+    const int T = tile_nt * gpt;
+    const int ngrp = nt / tile_nt;  // stage rings per CTA
     uint32_t coff = 0;
     for (int c = 0; c < P.ncols; ++c) {
       P.col_off[c] = coff;
@@ -779,6 +789,13 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
       nst = sp_stages;
       want_ctas = sp_ctas;
     }
+    if (mode == MODE_IN_WIDE) {  // one CTA per SM; as many stages per consumer group as fit (8 mbarriers in all)
+      const uint32_t room = (uint32_t)ctx->max_smem_optin - 512u /* static */ - off;
+      const int fit = (int)(room / ((uint32_t)ngrp * P.stage_bytes));
+      nst = std::min(nst > 0 ? nst : 4, std::min(fit, 8 / ngrp));
+      if (nst < 2) return FLE_E_UNSUPPORTED;
+      want_ctas = 1;
+    }
     if (nst <= 0) {
       nst = 0;
       for (int ctas = (want_ctas > 0 ? want_ctas : 3); ctas >= 1 && nst < 2; --ctas) {
@@ -789,19 +806,19 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
       if (nst < 2) return FLE_E_UNSUPPORTED;  // caller falls back to the direct kernel
     }
     nst = std::min(nst, 8);
-    if ((uint64_t)off + (uint64_t)nst * P.stage_bytes > (uint64_t)ctx->max_smem_optin) return FLE_E_UNSUPPORTED;
+    if ((uint64_t)off + (uint64_t)nst * ngrp * P.stage_bytes > (uint64_t)ctx->max_smem_optin) return FLE_E_UNSUPPORTED;
     P.gpt = gpt;
     P.nstages = nst;
-    smem_bytes = off + (size_t)nst * P.stage_bytes;
+    smem_bytes = off + (size_t)nst * ngrp * P.stage_bytes;
     int per_sm = 0;
-    rc = blocks_per_sm(ctx, kern, smem_bytes, &per_sm);
+    rc = blocks_per_sm(ctx, kern, smem_bytes, &per_sm, nt);
     if (rc != FLE_OK) return rc;
     if (per_sm < 1) return FLE_E_UNSUPPORTED;
     if (want_ctas > 0) per_sm = std::min(per_sm, want_ctas);
     const int64_t ntiles = G / T;
-    const int64_t rest_blocks = ((G - ntiles * T) + kNT - 1) / kNT;
+    const int64_t rest_blocks = ((G - ntiles * T) + nt - 1) / nt;
     grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * per_sm,
-                                                        std::max<int64_t>(ntiles, rest_blocks)));
+                                                        std::max<int64_t>((ntiles + ngrp - 1) / ngrp, rest_blocks)));
   } else {
     P.gpt = 1;
     P.nstages = 0;
@@ -823,7 +840,7 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
   P.tile_counter = ctx->d_ticket + 1;
   P.in_lits = ctx->d_in_lits;
   void* args[] = {(void*)&P, jit_args};
-  cudaError_t e = cudaLaunchKernel(kern, dim3(grid), dim3(kNT), args, smem_bytes, ctx->stream);
+  cudaError_t e = cudaLaunchKernel(kern, dim3(grid), dim3(nt), args, smem_bytes, ctx->stream);
   if (e != cudaSuccess) {
     cudaGetLastError();  // clear the non-sticky error
     char what[160];
@@ -921,6 +938,11 @@ int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, 
     P1.planes[0] = P.planes[c];
     P1.bw[0] = P.bw[c];
     P1.passes[0].col = 0;
+    // bw <= 12: 16-bit table entries, one ALU instruction per lookup (fle_eval_in.cu)
+    if (ctx->in_wide != 0 && P.bw[c] <= 12) {
+      const int rc = launch_program(ctx, P1, MODE_IN_WIDE, (int)P.bw[c]);
+      if (rc != FLE_E_UNSUPPORTED) return rc;
+    }
     return launch_program(ctx, P1, MODE_IN_LOOKUP, (int)P.bw[c]);
   };
   if (in_single && (int)p0.lit[1] >= ctx->in_lookup_min) {

@@ -61,36 +61,36 @@ __device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b) {
   return r;
 }
 
+template <int J, uint32_t M>
+__device__ __forceinline__ void in_stage(uint32_t (&S)[16]) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    if ((k & J) == 0) {
+      const uint32_t a = S[k], b = S[k + J];
+      if (J == 8) {
+        S[k] = __byte_perm(a, b, 0x3715);      // (a & 0xFF00FF00) | ((b >> 8) & 0x00FF00FF)
+        S[k + J] = __byte_perm(a, b, 0x2604);  // (b & 0x00FF00FF) | ((a & 0x00FF00FF) << 8)
+      } else {
+        S[k] = bitsel<M>(a, b >> J);
+        S[k + J] = bitsel<M>(a << J, b);
+      }
+    }
+  }
+}
+
+// 16 x 16 bit transposes of the low and of the high halves of S[0..15] at once:
+// S'[k] bit i == S[15 - i] bit (15 - k),   S'[k] bit 16 + i == S[15 - i] bit (31 - k)
+__device__ __forceinline__ void in_transpose(uint32_t (&S)[16]) {
+  in_stage<8, 0x00FF00FFu>(S);
+  in_stage<4, 0x0F0F0F0Fu>(S);
+  in_stage<2, 0x33333333u>(S);
+  in_stage<1, 0x55555555u>(S);
+}
+
 template <int BW>
 struct InDecode {
   using IT = InTable<BW>;
   uint32_t table;  // shared address of this lane's table (of the shared one for bw > 13)
-
-  template <int J, uint32_t M>
-  __device__ __forceinline__ void stage(uint32_t (&S)[16]) const {
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      if ((k & J) == 0) {
-        const uint32_t a = S[k], b = S[k + J];
-        if (J == 8) {
-          S[k] = __byte_perm(a, b, 0x3715);      // (a & 0xFF00FF00) | ((b >> 8) & 0x00FF00FF)
-          S[k + J] = __byte_perm(a, b, 0x2604);  // (b & 0x00FF00FF) | ((a & 0x00FF00FF) << 8)
-        } else {
-          S[k] = bitsel<M>(a, b >> J);
-          S[k + J] = bitsel<M>(a << J, b);
-        }
-      }
-    }
-  }
-
-  // 16 x 16 bit transposes of the low and of the high halves of S[0..15] at once:
-  // S'[k] bit i == S[15 - i] bit (15 - k),   S'[k] bit 16 + i == S[15 - i] bit (31 - k)
-  __device__ __forceinline__ void transpose(uint32_t (&S)[16]) const {
-    stage<8, 0x00FF00FFu>(S);
-    stage<4, 0x0F0F0F0Fu>(S);
-    stage<2, 0x33333333u>(S);
-    stage<1, 0x55555555u>(S);
-  }
 
   // membership of the code in bits 0..15 of h (higher bits ignored) -> bit 31 of the result
   __device__ __forceinline__ uint32_t probe(uint32_t h) const {
@@ -114,8 +114,8 @@ struct InDecode {
         S1[15 - IT::pos(i + 1 < BW ? i + 1 : i)] = (uint32_t)b;
       }
     }
-    transpose(S0);  // S0[k] = half(row k) << 16 | half(row 16 + k)
-    transpose(S1);  // S1[k] = half(row 32 + k) << 16 | half(row 48 + k)
+    in_transpose(S0);  // S0[k] = half(row k) << 16 | half(row 16 + k)
+    in_transpose(S1);  // S1[k] = half(row 32 + k) << 16 | half(row 48 + k)
     uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;  // rows 0..15, 16..31, 32..47, 48..63 (bit k = row base + k)
 #pragma unroll
     for (int k = 15; k >= 0; --k) {
@@ -239,6 +239,259 @@ __global__ void __launch_bounds__(256) eval_in_kernel(const __grid_constant__ Ev
     cnt_bits += __popcll(r);
   }
   publish_count<NT>(P, cnt_bits);
+}
+
+// ------------------------------------------------------------------------------------------
+// Entry-table kernel (bw <= 12): one ALU instruction per lookup instead of 3.5.
+//
+// The bit table above costs, per row, a mask for the word address, a variable shift to bring the
+// row's bit to bit 31 and a funnel shift to append it -- all on the ALU pipe that already carries
+// the transposes, and that pipe is what bounds the kernel.  Here every code owns a 16-bit table
+// ENTRY (lane-private: entry e of lane l at byte (e >> 1) * 128 + l * 4 + (e & 1) * 2, 2^11 entries
+// = 128 KB), so a lookup is
+//     ALU: h = word >> 16  or  word & mask      (the half IS the entry address / 2)
+//     FMA: addr = h * 2 + lane_base             (IMAD)
+//     LSU: e = ld.shared.u16 [addr]
+//     FMA: acc = acc * 2 + e                    (IMAD appends the row's bit)
+// A 16-bit half holds 11 address bits (bit 0, then bits 6..15: the five in between are the lane),
+// so at most 11 code bits are transposed.  For bw 12 the top plane is NOT transposed: the entry of
+// the low 11 bits carries both answers, bit 0 = member(code) and bit 8 = member(code + 2^11); an
+// accumulator takes 8 rows (answers in bytes 0 and 1), two PRMTs gather the bytes of four
+// accumulators into two 32-row words M0 / M1 and the untouched plane selects between them
+// bitwise:  r = (M0 & ~X) | (M1 & X)  -- one LOP3 per 32 rows.
+// One CTA per SM (the table leaves 99 KB for the stages); set membership of the same codes, so
+// bit-identical to the OR of equalities by construction.
+template <int BW>
+struct InWide {
+  static constexpr int kTB = BW < 11 ? BW : 11;  // transposed code bits
+  static constexpr int kNX = BW - kTB;           // planes kept bit-sliced (0 or 1)
+  static constexpr int kEntries = 1 << kTB;
+  static constexpr uint32_t kTableBytes = (uint32_t)(kEntries < 2 ? 2 : kEntries) * 64u;
+  FLE_HD static constexpr int pos(int i) { return i == 0 ? 0 : i + 5; }
+  static constexpr uint32_t kHalfMask = 1u | ((((1u << (kTB - 1)) - 1u) << 6) & 0xFFFFu);
+};
+
+__device__ __forceinline__ uint32_t lds16(uint32_t addr) {
+  uint32_t v;
+  asm volatile("{ .reg .u16 t; ld.shared.u16 t, [%1]; cvt.u32.u16 %0, t; }" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+template <int BW>
+struct InWideDecode {
+  using IW = InWide<BW>;
+  uint32_t table;  // shared address of this lane's column of the table
+
+  // (inline PTX: from C the compiler folds the * 2 into the half's extraction -- shift by 15, then
+  //  a mask to clear bit 0 -- and spends a second ALU instruction per lookup)
+  __device__ __forceinline__ uint32_t entry(uint32_t h) const {
+    uint32_t addr;
+    asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(addr) : "r"(h), "r"(table));
+    return lds16(addr);
+  }
+
+  // the group's planes, in registers: bit planes of rows 0..31 / 32..63 (plane i at word
+  // 15 - pos(i)) and the plane that stays bit-sliced (bw 12)
+  struct Planes {
+    uint32_t S0[16], S1[16];
+    uint64_t X;
+  };
+
+  template <class L>
+  __device__ __forceinline__ uint64_t run(const L& ld) const {
+    Planes pl;
+    load(ld, pl);
+    return compute(pl);
+  }
+
+  template <class L>
+  __device__ __forceinline__ void load(const L& ld, Planes& pl) const {
+    uint32_t (&S0)[16] = pl.S0;
+    uint32_t (&S1)[16] = pl.S1;
+    uint64_t& X = pl.X;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) S0[j] = S1[j] = 0u;
+    X = 0;
+#pragma unroll
+    for (int i = 0; i < BW; i += 2) {
+      uint64_t a, b;
+      ld.template load_pair<BW>(i, a, b);
+      if (i < IW::kTB) {
+        S0[15 - IW::pos(i < IW::kTB ? i : 0)] = (uint32_t)(a >> 32);
+        S1[15 - IW::pos(i < IW::kTB ? i : 0)] = (uint32_t)a;
+      } else {
+        X = a;
+      }
+      if (i + 1 < BW) {
+        if (i + 1 < IW::kTB) {
+          S0[15 - IW::pos(i + 1 < IW::kTB ? i + 1 : 0)] = (uint32_t)(b >> 32);
+          S1[15 - IW::pos(i + 1 < IW::kTB ? i + 1 : 0)] = (uint32_t)b;
+        } else {
+          X = b;
+        }
+      }
+    }
+  }
+
+  __device__ __forceinline__ uint64_t compute(Planes& pl) const {
+    uint32_t (&S0)[16] = pl.S0;
+    uint32_t (&S1)[16] = pl.S1;
+    const uint64_t X = pl.X;
+    in_transpose(S0);  // S0[k] = half(row k) << 16 | half(row 16 + k)
+    in_transpose(S1);  // S1[k] = half(row 32 + k) << 16 | half(row 48 + k)
+    uint32_t lo, hi;
+    if constexpr (IW::kNX == 0) {
+      uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;  // rows 0..15, 16..31, 32..47, 48..63
+#pragma unroll
+      for (int k = 15; k >= 0; --k) {
+        const uint32_t a = S0[k], b = S1[k];
+        r0 = r0 * 2u + entry(a >> 16);
+        r1 = r1 * 2u + entry(a & IW::kHalfMask);
+        r2 = r2 * 2u + entry(b >> 16);
+        r3 = r3 * 2u + entry(b & IW::kHalfMask);
+      }
+      lo = r1 * 65536u + r0;
+      hi = r3 * 65536u + r2;
+    } else {
+      // eight rows per accumulator: byte 0 = answers for X = 0, byte 1 = answers for X = 1
+      uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+#pragma unroll
+      for (int k = 7; k >= 0; --k) {
+        const uint32_t u = S0[k], v = S0[k + 8], w = S1[k], z = S1[k + 8];
+        a0 = a0 * 2u + entry(u >> 16);            // rows 0..7
+        a1 = a1 * 2u + entry(v >> 16);            // rows 8..15
+        a2 = a2 * 2u + entry(u & IW::kHalfMask);  // rows 16..23
+        a3 = a3 * 2u + entry(v & IW::kHalfMask);  // rows 24..31
+        b0 = b0 * 2u + entry(w >> 16);            // rows 32..39
+        b1 = b1 * 2u + entry(z >> 16);
+        b2 = b2 * 2u + entry(w & IW::kHalfMask);
+        b3 = b3 * 2u + entry(z & IW::kHalfMask);
+      }
+      const uint32_t ca = a1 * 65536u + a0, cb = a3 * 65536u + a2;  // [M1 r8-15][M0 r8-15][M1 r0-7][M0 r0-7], ...
+      const uint32_t cc = b1 * 65536u + b0, cd = b3 * 65536u + b2;
+      const uint64_t xr = __brevll(X);  // plane order (row k at bit 63 - k) -> row order
+      const uint32_t xlo = (uint32_t)xr, xhi = (uint32_t)(xr >> 32);
+      lo = (__byte_perm(ca, cb, 0x6420) & ~xlo) | (__byte_perm(ca, cb, 0x7531) & xlo);
+      hi = (__byte_perm(cc, cd, 0x6420) & ~xhi) | (__byte_perm(cc, cd, 0x7531) & xhi);
+    }
+    return ((uint64_t)hi << 32) | (uint64_t)lo;
+  }
+};
+
+// The CTA's 512 threads form 512 / GS consumer groups of GS threads, each with its own ring of
+// stages, its own mbarriers and a named barrier, all sharing the one table: every group walks its
+// own sequence of GS-group tiles and the groups drift apart freely.  That matters because a group
+// body has an ALU-only phase (the transposes) and an FMA/LSU-heavy phase (the lookups): warps
+// marching in step behind one CTA-wide barrier leave one pipe idle in each phase (measured
+// 600 M rows bw 12: one group of 512 threads 230 us, 256 threads per CTA 296 us).
+constexpr int kInWideThreads = 512;
+
+template <int BW, int GS>
+__global__ void __launch_bounds__(kInWideThreads, 1) eval_in_wide_kernel(const __grid_constant__ EvalParams P) {
+  constexpr int NT = kInWideThreads;
+  constexpr int NGRP = NT / GS;
+  extern __shared__ __align__(128) uint8_t smem[];
+  using IW = InWide<BW>;
+  uint32_t* table_ptr = reinterpret_cast<uint32_t*>(smem + P.smem_masks_off);  // [entry pair][lane]
+  InWideDecode<BW> dec;
+  dec.table = smem_u32(table_ptr) + (threadIdx.x & 31u) * 4u;
+  const int gpt = P.gpt;
+  const int T = GS * gpt;
+  const int seg_groups = T >> 3;
+  const int64_t ntiles = P.ngroups / T;
+  const int nst = P.nstages;  // per consumer group
+  const uint32_t grp = threadIdx.x / GS, tg = threadIdx.x % GS;
+  const uint32_t bar0 = smem_u32(smem + P.smem_bar_off) + grp * (uint32_t)nst * 8u;
+  const uint32_t stage0 = smem_u32(smem + P.smem_stage_off) + grp * (uint32_t)nst * P.stage_bytes;
+  const int64_t tile0 = (int64_t)blockIdx.x * NGRP + grp, tile_step = (int64_t)gridDim.x * NGRP;
+
+  if (threadIdx.x == 0) {
+    const uint32_t b = smem_u32(smem + P.smem_bar_off);
+    for (int s = 0; s < nst * NGRP; ++s) mbar_init(b + s * 8, 1);
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < (int)(IW::kTableBytes / 4u); i += NT) table_ptr[i] = 0;
+  __syncthreads();
+  if (tg == 0) {
+    for (int s = 0; s < nst; ++s) {
+      const int64_t tile = tile0 + (int64_t)s * tile_step;
+      if (tile < ntiles) issue_tile(P, bar0, stage0, s, tile, T);
+    }
+  }
+  const PassDesc& pd = P.passes[0];
+  const int off = (int)pd.lit[0], cnt = (int)pd.lit[1];
+  for (int i = threadIdx.x; i < cnt * 32; i += NT) {
+    const uint32_t c = P.in_lits[off + (i >> 5)];  // already masked to BW bits by the host
+    const uint32_t e = c & (uint32_t)(IW::kEntries - 1), x = c >> IW::kTB;
+    atomicOr(&table_ptr[(e >> 1) * 32u + (uint32_t)(i & 31)], 1u << ((e & 1u) * 16u + x * 8u));
+  }
+  __syncthreads();
+  const uint64_t negmask = pd.neg[0] ? ~0ull : 0ull;
+
+  const uint32_t seg = tg & 7, jrow = tg >> 3;
+  const uint32_t thread_off = P.col_off[0] + seg * P.seg_stride[0] + jrow * (uint32_t)(BW * 8);
+  constexpr uint32_t kGroupStride = (uint32_t)(GS / 8) * BW * 8u;
+  const int64_t thread_g = (int64_t)seg * seg_groups + jrow;
+  uint64_t cnt_bits = 0;
+
+  int stage = 0;
+  uint32_t parity = 0;
+  // One group per thread per tile (gpt == 1, the launcher's choice): a thread's share of the stage is
+  // in its registers after six 128-bit loads, so the stage is handed back to the TMA producer BEFORE
+  // the group is evaluated -- every stage is in flight during the ~1.7 us a tile takes, which
+  // doubles the bytes in flight the 99 KB beside the table can buy.
+  for (int64_t tile = tile0; tile < ntiles; tile += tile_step) {
+    mbar_wait(bar0 + stage * 8, parity);
+    uint32_t a = stage0 + stage * P.stage_bytes + thread_off;
+    int64_t g = tile * T + thread_g;
+    for (int q = 0; q < gpt; ++q) {
+      typename InWideDecode<BW>::Planes pl;
+      dec.load(InSmemGroup{a}, pl);
+      if (q == gpt - 1) {
+        // every thread of the group has read the stage: refill it
+        if (NGRP == 1) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1u), "n"(GS) : "memory");
+        if (tg == 0) {
+          const int64_t nxt = tile + (int64_t)nst * tile_step;
+          if (nxt < ntiles) issue_tile(P, bar0, stage0, stage, nxt, T);
+        }
+      }
+      const uint64_t r = finish_row_order(dec.compute(pl), negmask, g, P.nrows);
+      P.bitmap[g] = r;
+      cnt_bits += __popcll(r);
+      a += kGroupStride;
+      g += GS / 8;
+    }
+    if (++stage == nst) {
+      stage = 0;
+      parity ^= 1u;
+    }
+  }
+  for (int64_t g = ntiles * T + (int64_t)blockIdx.x * NT + threadIdx.x; g < P.ngroups;
+       g += (int64_t)gridDim.x * NT) {
+    const uint64_t r = finish_row_order(dec.run(InGlobalGroup{P.planes[0] + g * BW}), negmask, g, P.nrows);
+    P.bitmap[g] = r;
+    cnt_bits += __popcll(r);
+  }
+  publish_count<NT>(P, cnt_bits);
+}
+
+const void* eval_in_wide_kernel_for(int bw, int gs) {
+  switch (bw) {
+#define X(B)                                                                                        \
+  case B:                                                                                           \
+    return gs == 128 ? (const void*)eval_in_wide_kernel<B, 128>                                     \
+                     : (gs == 256 ? (const void*)eval_in_wide_kernel<B, 256>                        \
+                                  : (gs == 512 ? (const void*)eval_in_wide_kernel<B, 512> : nullptr));
+    X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12)
+#undef X
+  }
+  return nullptr;
+}
+
+uint32_t eval_in_wide_table_bytes(int bw) {
+  const int tb = bw < 11 ? bw : 11;
+  return (uint32_t)std::max(2, 1 << tb) * 64u;
 }
 
 const void* eval_in_kernel_for(int bw) {
