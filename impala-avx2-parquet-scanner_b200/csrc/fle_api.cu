@@ -405,7 +405,6 @@ int fle_ctx_set_option(fle_ctx* ctx, const char* name, int64_t value) {
   else if (k == "eval_gpt") ctx->eval_gpt = (int)value;
   else if (k == "in_lookup_min") ctx->in_lookup_min = (int)value;
   else if (k == "in_wide") ctx->in_wide = (int)value;
-  else if (k == "in_wide_group") ctx->in_wide_group = (int)value;
   else if (k == "eval_narrow_bw") ctx->eval_narrow_bw = (int)value;
   else if (k == "codec_variant") ctx->codec_variant = (int)value;
   else if (k == "codec_ctas_per_sm") ctx->codec_ctas_per_sm = (int)value;
@@ -426,7 +425,6 @@ int64_t fle_ctx_get_option(fle_ctx* ctx, const char* name) {
   if (k == "eval_gpt") return ctx->eval_gpt;
   if (k == "in_lookup_min") return ctx->in_lookup_min;
   if (k == "in_wide") return ctx->in_wide;
-  if (k == "in_wide_group") return ctx->in_wide_group;
   if (k == "eval_narrow_bw") return ctx->eval_narrow_bw;
   if (k == "codec_variant") return ctx->codec_variant;
   if (k == "codec_ctas_per_sm") return ctx->codec_ctas_per_sm;

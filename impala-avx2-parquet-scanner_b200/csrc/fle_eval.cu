@@ -692,7 +692,6 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
   const int64_t G = P.ngroups;
   const void* kern = nullptr;
   int nt = kNT;       // threads per CTA
-  int tile_nt = kNT;  // threads that share a tile (entry-table IN kernel: a consumer group of the CTA)
   if (mode == MODE_JIT) {
     kern = jit_kern;
   } else if (mode == MODE_SINGLE_PASS) {
@@ -703,8 +702,7 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
     if (!kern) return FLE_E_UNSUPPORTED;
   } else if (mode == MODE_IN_WIDE) {
     nt = kInWideThreadsPerCta;
-    tile_nt = ctx->in_wide_group;
-    kern = eval_in_wide_kernel_for((int)P.bw[0], tile_nt);
+    kern = eval_in_wide_kernel_for((int)P.bw[0]);
     if (!kern) return FLE_E_UNSUPPORTED;
   } else if (mode == MODE_NARROW) {
     kern = eval1_narrow_kernel_for(P.passes[0].type, P.passes[0].k, (int)P.bw[0]);
@@ -724,7 +722,7 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
   int sp_ctas = 0, sp_stages = 0;
   if (staged) {
     gpt = ctx->eval_gpt;
-    const uint32_t bytes_per_gpt = (uint32_t)tile_nt * sum_bw * 8u;
+    const uint32_t bytes_per_gpt = (uint32_t)nt * sum_bw * 8u;
     // (measured, tools/sweep.py tune: the interpreting kernel likes ~32 KB stages and 3 CTAs/SM,
     //  the multi-column specialised kernels ~90 KB with 1-2 CTAs/SM)
     const bool sp_narrow = mode == MODE_SINGLE_PASS && sum_bw <= 5;
@@ -771,8 +769,7 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
   size_t smem_bytes = off;
   int rc;
   if (staged) {
-    const int T = tile_nt * gpt;
-    const int ngrp = nt / tile_nt;  // stage rings per CTA
+    const int T = nt * gpt;
     uint32_t coff = 0;
     for (int c = 0; c < P.ncols; ++c) {
       P.col_off[c] = coff;
@@ -789,10 +786,9 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
       nst = sp_stages;
       want_ctas = sp_ctas;
     }
-    if (mode == MODE_IN_WIDE) {  // one CTA per SM; as many stages per consumer group as fit (8 mbarriers in all)
+    if (mode == MODE_IN_WIDE) {  // one CTA per SM with as many stages as fit beside the table
       const uint32_t room = (uint32_t)ctx->max_smem_optin - 512u /* static */ - off;
-      const int fit = (int)(room / ((uint32_t)ngrp * P.stage_bytes));
-      nst = std::min(nst > 0 ? nst : 4, std::min(fit, 8 / ngrp));
+      nst = std::min(nst > 0 ? nst : 4, (int)(room / P.stage_bytes));
       if (nst < 2) return FLE_E_UNSUPPORTED;
       want_ctas = 1;
     }
@@ -806,10 +802,10 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
       if (nst < 2) return FLE_E_UNSUPPORTED;  // caller falls back to the direct kernel
     }
     nst = std::min(nst, 8);
-    if ((uint64_t)off + (uint64_t)nst * ngrp * P.stage_bytes > (uint64_t)ctx->max_smem_optin) return FLE_E_UNSUPPORTED;
+    if ((uint64_t)off + (uint64_t)nst * P.stage_bytes > (uint64_t)ctx->max_smem_optin) return FLE_E_UNSUPPORTED;
     P.gpt = gpt;
     P.nstages = nst;
-    smem_bytes = off + (size_t)nst * ngrp * P.stage_bytes;
+    smem_bytes = off + (size_t)nst * P.stage_bytes;
     int per_sm = 0;
     rc = blocks_per_sm(ctx, kern, smem_bytes, &per_sm, nt);
     if (rc != FLE_OK) return rc;
@@ -818,7 +814,7 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
     const int64_t ntiles = G / T;
     const int64_t rest_blocks = ((G - ntiles * T) + nt - 1) / nt;
     grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * per_sm,
-                                                        std::max<int64_t>((ntiles + ngrp - 1) / ngrp, rest_blocks)));
+                                                        std::max<int64_t>(ntiles, rest_blocks)));
   } else {
     P.gpt = 1;
     P.nstages = 0;

@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(256) eval_in_kernel(const __grid_constant__ Ev
 // accumulator takes 8 rows (answers in bytes 0 and 1), two PRMTs gather the bytes of four
 // accumulators into two 32-row words M0 / M1 and the untouched plane selects between them
 // bitwise:  r = (M0 & ~X) | (M1 & X)  -- one LOP3 per 32 rows.
-// One CTA per SM (the table leaves 99 KB for the stages); set membership of the same codes, so
+// One CTA per SM (the table leaves 99 KB for two 48 KB stages); set membership of the same codes, so
 // bit-identical to the OR of equalities by construction.
 template <int BW>
 struct InWide {
@@ -378,43 +378,39 @@ struct InWideDecode {
   }
 };
 
-// The CTA's 512 threads form 512 / GS consumer groups of GS threads, each with its own ring of
-// stages, its own mbarriers and a named barrier, all sharing the one table: every group walks its
-// own sequence of GS-group tiles and the groups drift apart freely.  That matters because a group
-// body has an ALU-only phase (the transposes) and an FMA/LSU-heavy phase (the lookups): warps
-// marching in step behind one CTA-wide barrier leave one pipe idle in each phase (measured
-// 600 M rows bw 12: one group of 512 threads 230 us, 256 threads per CTA 296 us).
+// One CTA of 512 threads per SM.  Tried and dropped (tools/in_wide_probe.py, 600 M rows, bw 12):
+// consumer groups of 128 / 256 threads with their own stage rings and named barriers, so that warps
+// drift apart (264 / 245 us against 228 us for one ring); half a group per thread in CTAs of 1024
+// threads at 64 registers (285 us).  ncu: issue slots 71 % busy, ALU pipe 64 %; a group costs 592
+// issued instructions (268 ALU, 195 FMA, 70 LSU), so the kernel is bound by instruction issue as
+// much as by the ALU pipe.
 constexpr int kInWideThreads = 512;
 
-template <int BW, int GS>
+template <int BW>
 __global__ void __launch_bounds__(kInWideThreads, 1) eval_in_wide_kernel(const __grid_constant__ EvalParams P) {
   constexpr int NT = kInWideThreads;
-  constexpr int NGRP = NT / GS;
   extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t bar0 = smem_u32(smem + P.smem_bar_off);
+  const uint32_t stage0 = smem_u32(smem + P.smem_stage_off);
   using IW = InWide<BW>;
   uint32_t* table_ptr = reinterpret_cast<uint32_t*>(smem + P.smem_masks_off);  // [entry pair][lane]
   InWideDecode<BW> dec;
   dec.table = smem_u32(table_ptr) + (threadIdx.x & 31u) * 4u;
   const int gpt = P.gpt;
-  const int T = GS * gpt;
+  const int T = NT * gpt;
   const int seg_groups = T >> 3;
   const int64_t ntiles = P.ngroups / T;
-  const int nst = P.nstages;  // per consumer group
-  const uint32_t grp = threadIdx.x / GS, tg = threadIdx.x % GS;
-  const uint32_t bar0 = smem_u32(smem + P.smem_bar_off) + grp * (uint32_t)nst * 8u;
-  const uint32_t stage0 = smem_u32(smem + P.smem_stage_off) + grp * (uint32_t)nst * P.stage_bytes;
-  const int64_t tile0 = (int64_t)blockIdx.x * NGRP + grp, tile_step = (int64_t)gridDim.x * NGRP;
+  const int nst = P.nstages;
 
   if (threadIdx.x == 0) {
-    const uint32_t b = smem_u32(smem + P.smem_bar_off);
-    for (int s = 0; s < nst * NGRP; ++s) mbar_init(b + s * 8, 1);
+    for (int s = 0; s < nst; ++s) mbar_init(bar0 + s * 8, 1);
     mbar_fence_init();
   }
   for (int i = threadIdx.x; i < (int)(IW::kTableBytes / 4u); i += NT) table_ptr[i] = 0;
   __syncthreads();
-  if (tg == 0) {
-    for (int s = 0; s < nst; ++s) {
-      const int64_t tile = tile0 + (int64_t)s * tile_step;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nst - 1; ++s) {
+      const int64_t tile = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
       if (tile < ntiles) issue_tile(P, bar0, stage0, s, tile, T);
     }
   }
@@ -428,39 +424,31 @@ __global__ void __launch_bounds__(kInWideThreads, 1) eval_in_wide_kernel(const _
   __syncthreads();
   const uint64_t negmask = pd.neg[0] ? ~0ull : 0ull;
 
-  const uint32_t seg = tg & 7, jrow = tg >> 3;
+  const uint32_t seg = threadIdx.x & 7, jrow = threadIdx.x >> 3;
   const uint32_t thread_off = P.col_off[0] + seg * P.seg_stride[0] + jrow * (uint32_t)(BW * 8);
-  constexpr uint32_t kGroupStride = (uint32_t)(GS / 8) * BW * 8u;
+  constexpr uint32_t kGroupStride = (uint32_t)(NT / 8) * BW * 8u;
   const int64_t thread_g = (int64_t)seg * seg_groups + jrow;
   uint64_t cnt_bits = 0;
 
   int stage = 0;
   uint32_t parity = 0;
-  // One group per thread per tile (gpt == 1, the launcher's choice): a thread's share of the stage is
-  // in its registers after six 128-bit loads, so the stage is handed back to the TMA producer BEFORE
-  // the group is evaluated -- every stage is in flight during the ~1.7 us a tile takes, which
-  // doubles the bytes in flight the 99 KB beside the table can buy.
-  for (int64_t tile = tile0; tile < ntiles; tile += tile_step) {
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int64_t nxt = tile + (int64_t)(nst - 1) * gridDim.x;
+      int st2 = stage + nst - 1;
+      if (st2 >= nst) st2 -= nst;
+      if (nxt < ntiles) issue_tile(P, bar0, stage0, st2, nxt, T);
+    }
     mbar_wait(bar0 + stage * 8, parity);
     uint32_t a = stage0 + stage * P.stage_bytes + thread_off;
     int64_t g = tile * T + thread_g;
     for (int q = 0; q < gpt; ++q) {
-      typename InWideDecode<BW>::Planes pl;
-      dec.load(InSmemGroup{a}, pl);
-      if (q == gpt - 1) {
-        // every thread of the group has read the stage: refill it
-        if (NGRP == 1) __syncthreads();
-        else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1u), "n"(GS) : "memory");
-        if (tg == 0) {
-          const int64_t nxt = tile + (int64_t)nst * tile_step;
-          if (nxt < ntiles) issue_tile(P, bar0, stage0, stage, nxt, T);
-        }
-      }
-      const uint64_t r = finish_row_order(dec.compute(pl), negmask, g, P.nrows);
+      const uint64_t r = finish_row_order(dec.run(InSmemGroup{a}), negmask, g, P.nrows);
       P.bitmap[g] = r;
       cnt_bits += __popcll(r);
       a += kGroupStride;
-      g += GS / 8;
+      g += NT / 8;
     }
     if (++stage == nst) {
       stage = 0;
@@ -476,13 +464,9 @@ __global__ void __launch_bounds__(kInWideThreads, 1) eval_in_wide_kernel(const _
   publish_count<NT>(P, cnt_bits);
 }
 
-const void* eval_in_wide_kernel_for(int bw, int gs) {
+const void* eval_in_wide_kernel_for(int bw) {
   switch (bw) {
-#define X(B)                                                                                        \
-  case B:                                                                                           \
-    return gs == 128 ? (const void*)eval_in_wide_kernel<B, 128>                                     \
-                     : (gs == 256 ? (const void*)eval_in_wide_kernel<B, 256>                        \
-                                  : (gs == 512 ? (const void*)eval_in_wide_kernel<B, 512> : nullptr));
+#define X(B) case B: return (const void*)eval_in_wide_kernel<B>;
     X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12)
 #undef X
   }

@@ -61,7 +61,6 @@ struct fle_ctx {
   int eval_narrow_bw = 2;    // single-pass programs on columns up to this width skip shared-memory staging (bw 1, 2, 4)
   int in_lookup_min = 9;     // IN lists at least this long use the decode+lookup kernel (bw <= 16); shorter ones the plane form
   int in_wide = 1;           // IN lookup on bw <= 12: 16-bit entry table (1) or the bit table (0)
-  int in_wide_group = 512;   // threads per consumer group of the entry-table kernel's 512-thread CTA (128, 256, 512)
   int codec_variant = 1;
   int codec_ctas_per_sm = 0;  // 0 = as many as fit
   int eval_jit = 1;                      // 0 never, 1 when n >= eval_jit_min_rows or already compiled, 2 always
@@ -126,8 +125,8 @@ const void* eval1_narrow_kernel_for(int type, int k, int bw);
 constexpr int kNarrowUnits = 8;  // 16/32-byte units per thread per tile of the narrow kernels
 // fle_eval_in.cu: IN list by decode + membership-table lookup (bw <= 16), or nullptr
 const void* eval_in_kernel_for(int bw);
-// fle_eval_in.cu: IN list by decode + 16-bit entry table (bw <= 12; 512 threads in consumer groups of gs), or nullptr
-const void* eval_in_wide_kernel_for(int bw, int gs);
+// fle_eval_in.cu: IN list by decode + 16-bit entry table (bw <= 12, CTAs of 512 threads), or nullptr
+const void* eval_in_wide_kernel_for(int bw);
 constexpr int kInWideThreadsPerCta = 512;
 uint32_t eval_in_wide_table_bytes(int bw);
 // out = postfix program over K device bitmaps (leaf.col = bitmap index), word by word

@@ -505,20 +505,17 @@ def test_in_list_lookup_kernel_vs_oracle(ctx, oracle, bw):
     for L in (1, 8, 64, 256, 1000):
         lits = rng.integers(0, 1 << bw, size=L, dtype=np.uint64)  # duplicates and absent codes included
         want, wcnt = oracle.pred(IN, words, bw, 0, n, lits)
-        # (lookup_min, in_wide, in_wide_group): entry-table kernel with consumer groups of 128 / 256 / 512
-        # threads (bw <= 12), bit-table kernel, plane form
-        for lookup_min, wide, nt in ((1, 1, 128), (1, 1, 256), (1, 1, 512), (1, 0, 128), (1 << 30, 1, 128)):
+        # (lookup_min, in_wide): entry-table kernel (bw <= 12), bit-table kernel, plane form
+        for lookup_min, wide in ((1, 1), (1, 0), (1 << 30, 1)):
             ctx.set_option("in_lookup_min", lookup_min)
             ctx.set_option("in_wide", wide)
-            ctx.set_option("in_wide_group", nt)
             try:
                 bm, cnt = ctx.eval([(words, bw)], [(IN, 0, lits)], n)
                 mode = ctx.get_option("last_mode")
             finally:
                 ctx.set_option("in_lookup_min", 9)
                 ctx.set_option("in_wide", 1)
-                ctx.set_option("in_wide_group", 512)
-            assert (bm == want).all() and cnt == wcnt, (bw, L, lookup_min, wide, nt)
+            assert (bm == want).all() and cnt == wcnt, (bw, L, lookup_min, wide)
             if lookup_min == 1 and bw <= 16:
                 assert mode == (6 if wide and bw <= 12 else 3), (bw, mode)
 

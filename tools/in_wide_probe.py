@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""IN lists on bw <= 12 columns: entry-table kernel (in_wide = 1; consumer groups of 128 / 256 / 512 threads) against
+"""IN lists on bw <= 12 columns: entry-table kernel (in_wide = 1) against
 the bit-table kernel (in_wide = 0), 600 M rows, bitmaps compared bit for bit.
 python tools/in_wide_probe.py [rows]"""
 import os
@@ -20,7 +20,7 @@ G = (n + 63) // 64
 cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
 gen = torch.Generator().manual_seed(7)
 ctx.set_option("in_lookup_min", 1)
-for bw, dom in ((12, 2526), (11, 2048), (10, 1000), (8, 256), (6, 50), (3, 7)):
+for bw, dom in ((12, 2526), (11, 2048), (10, 1000), (8, 256), (6, 50), (3, 7))[:int(os.environ.get("NBW", "6"))]:
     v, w = make_col(ctx, n, bw, dom=dom, seed=bw)
     del v
     by = G * bw * 8 + G * 8
@@ -28,9 +28,8 @@ for bw, dom in ((12, 2526), (11, 2048), (10, 1000), (8, 256), (6, 50), (3, 7)):
         lits = torch.randint(0, dom, (L,), generator=gen).tolist()
         prog = [(IN, 0, lits)]
         res = {}
-        for name, wide, nt, stages in (("bit", 0, 128, 0), ("g128", 1, 128, 0), ("g256", 1, 256, 0), ("g512", 1, 512, 0)):
+        for name, wide, nt, stages in (("bit", 0, 0, 0), ("wide", 1, 0, 0), ("bit2", 0, 0, 0), ("wide2", 1, 0, 0)):
             ctx.set_option("in_wide", wide)
-            ctx.set_option("in_wide_group", nt)
             ctx.set_option("eval_stages", stages)
             bm = torch.empty(G, dtype=torch.int64, device="cuda")
             try:
