@@ -734,7 +734,7 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
       if (mode == MODE_SINGLE_PASS && gpt == 1 && bytes_per_gpt > 33u * 1024u && bytes_per_gpt < 44u * 1024u) gpt = 2;
     }
     gpt = std::min(gpt, 8);
-    if (mode == MODE_IN_WIDE && ctx->eval_gpt <= 0) gpt = 1;  // the table leaves room for 24-48 KB stages only
+    if (mode == MODE_IN_WIDE) gpt = 1;  // the table leaves room for 24-48 KB stages only
     if (mode == MODE_JIT && P.agg_plain) gpt = kJitAggGpt;  // compiled into the kernel (fle_eval_jit.cuh)
     if (mode == MODE_SINGLE_PASS) {
       const uint32_t stage = (uint32_t)gpt * bytes_per_gpt;
@@ -769,7 +769,7 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
   size_t smem_bytes = off;
   int rc;
   if (staged) {
-    const int T = nt * gpt;
+    const int T = (mode == MODE_IN_WIDE ? kInWideGroupsPerTile : nt) * gpt;
     uint32_t coff = 0;
     for (int c = 0; c < P.ncols; ++c) {
       P.col_off[c] = coff;
@@ -788,7 +788,7 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
     }
     if (mode == MODE_IN_WIDE) {  // one CTA per SM with as many stages as fit beside the table
       const uint32_t room = (uint32_t)ctx->max_smem_optin - 512u /* static */ - off;
-      nst = std::min(nst > 0 ? nst : 4, (int)(room / P.stage_bytes));
+      nst = std::min(std::min(nst > 0 ? nst : 4, 4), (int)(room / P.stage_bytes));  // (full + empty mbarriers: at most 4 stages)
       if (nst < 2) return FLE_E_UNSUPPORTED;
       want_ctas = 1;
     }

@@ -384,36 +384,39 @@ struct InWideDecode {
 // threads at 64 registers (285 us).  ncu: issue slots 71 % busy, ALU pipe 64 %; a group costs 592
 // issued instructions (268 ALU, 195 FMA, 70 LSU), so the kernel is bound by instruction issue as
 // much as by the ALU pipe.
-constexpr int kInWideThreads = 512;
+// 16 consumer warps + one producer warp.  There is no CTA-wide barrier in the tile loop: a consumer
+// warp waits for the stage's "full" mbarrier, copies its groups' planes into registers, arrives on
+// the stage's "empty" mbarrier and only then evaluates; the producer refills a stage as soon as all
+// 16 warps have released it.  Warps therefore drift apart by up to a tile, which keeps some of them
+// in the ALU-only transposes while others are in the FMA / LSU-heavy lookups.
+constexpr int kInWideConsumers = 512;
+constexpr int kInWideThreads = kInWideConsumers + 32;
 
 template <int BW>
 __global__ void __launch_bounds__(kInWideThreads, 1) eval_in_wide_kernel(const __grid_constant__ EvalParams P) {
-  constexpr int NT = kInWideThreads;
+  constexpr int NT = kInWideThreads, NC = kInWideConsumers;
   extern __shared__ __align__(128) uint8_t smem[];
-  const uint32_t bar0 = smem_u32(smem + P.smem_bar_off);
+  const uint32_t full0 = smem_u32(smem + P.smem_bar_off);  // full[s] at + 8 s, empty[s] at + 32 + 8 s (nstages <= 4)
+  const uint32_t empty0 = full0 + 32u;
   const uint32_t stage0 = smem_u32(smem + P.smem_stage_off);
   using IW = InWide<BW>;
   uint32_t* table_ptr = reinterpret_cast<uint32_t*>(smem + P.smem_masks_off);  // [entry pair][lane]
   InWideDecode<BW> dec;
   dec.table = smem_u32(table_ptr) + (threadIdx.x & 31u) * 4u;
-  const int gpt = P.gpt;
-  const int T = NT * gpt;
+  const int T = NC;  // one group per consumer thread per tile
   const int seg_groups = T >> 3;
   const int64_t ntiles = P.ngroups / T;
   const int nst = P.nstages;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < nst; ++s) mbar_init(bar0 + s * 8, 1);
+    for (int s = 0; s < nst; ++s) {
+      mbar_init(full0 + s * 8, 1);
+      mbar_init(empty0 + s * 8, NC / 32);
+    }
     mbar_fence_init();
   }
   for (int i = threadIdx.x; i < (int)(IW::kTableBytes / 4u); i += NT) table_ptr[i] = 0;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < nst - 1; ++s) {
-      const int64_t tile = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
-      if (tile < ntiles) issue_tile(P, bar0, stage0, s, tile, T);
-    }
-  }
   const PassDesc& pd = P.passes[0];
   const int off = (int)pd.lit[0], cnt = (int)pd.lit[1];
   for (int i = threadIdx.x; i < cnt * 32; i += NT) {
@@ -422,44 +425,51 @@ __global__ void __launch_bounds__(kInWideThreads, 1) eval_in_wide_kernel(const _
     atomicOr(&table_ptr[(e >> 1) * 32u + (uint32_t)(i & 31)], 1u << ((e & 1u) * 16u + x * 8u));
   }
   __syncthreads();
-  const uint64_t negmask = pd.neg[0] ? ~0ull : 0ull;
-
-  const uint32_t seg = threadIdx.x & 7, jrow = threadIdx.x >> 3;
-  const uint32_t thread_off = P.col_off[0] + seg * P.seg_stride[0] + jrow * (uint32_t)(BW * 8);
-  constexpr uint32_t kGroupStride = (uint32_t)(NT / 8) * BW * 8u;
-  const int64_t thread_g = (int64_t)seg * seg_groups + jrow;
   uint64_t cnt_bits = 0;
 
-  int stage = 0;
-  uint32_t parity = 0;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const int64_t nxt = tile + (int64_t)(nst - 1) * gridDim.x;
-      int st2 = stage + nst - 1;
-      if (st2 >= nst) st2 -= nst;
-      if (nxt < ntiles) issue_tile(P, bar0, stage0, st2, nxt, T);
+  if (threadIdx.x >= NC) {
+    // ---- producer warp: one lane feeds the ring
+    if (threadIdx.x == NC) {
+      int stage = 0;
+      uint32_t parity = 1;  // (a fresh mbarrier passes a wait on the phase before its first)
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        mbar_wait(empty0 + stage * 8, parity);
+        issue_tile(P, full0, stage0, stage, tile, T);
+        if (++stage == nst) {
+          stage = 0;
+          parity ^= 1u;
+        }
+      }
     }
-    mbar_wait(bar0 + stage * 8, parity);
-    uint32_t a = stage0 + stage * P.stage_bytes + thread_off;
-    int64_t g = tile * T + thread_g;
-    for (int q = 0; q < gpt; ++q) {
-      const uint64_t r = finish_row_order(dec.run(InSmemGroup{a}), negmask, g, P.nrows);
+  } else {
+    // ---- consumer warps
+    const uint64_t negmask = pd.neg[0] ? ~0ull : 0ull;
+    const uint32_t seg = threadIdx.x & 7, jrow = threadIdx.x >> 3;
+    const uint32_t thread_off = P.col_off[0] + seg * P.seg_stride[0] + jrow * (uint32_t)(BW * 8);
+    const int64_t thread_g = (int64_t)seg * seg_groups + jrow;
+    int stage = 0;
+    uint32_t parity = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      mbar_wait(full0 + stage * 8, parity);
+      typename InWideDecode<BW>::Planes pl;
+      dec.load(InSmemGroup{stage0 + stage * P.stage_bytes + thread_off}, pl);
+      __syncwarp();
+      if ((threadIdx.x & 31u) == 0) mbar_arrive(empty0 + stage * 8);  // this warp is done with the stage
+      const int64_t g = tile * T + thread_g;
+      const uint64_t r = finish_row_order(dec.compute(pl), negmask, g, P.nrows);
       P.bitmap[g] = r;
       cnt_bits += __popcll(r);
-      a += kGroupStride;
-      g += NT / 8;
+      if (++stage == nst) {
+        stage = 0;
+        parity ^= 1u;
+      }
     }
-    if (++stage == nst) {
-      stage = 0;
-      parity ^= 1u;
+    for (int64_t g = ntiles * T + (int64_t)blockIdx.x * NC + threadIdx.x; g < P.ngroups;
+         g += (int64_t)gridDim.x * NC) {
+      const uint64_t r = finish_row_order(dec.run(InGlobalGroup{P.planes[0] + g * BW}), negmask, g, P.nrows);
+      P.bitmap[g] = r;
+      cnt_bits += __popcll(r);
     }
-  }
-  for (int64_t g = ntiles * T + (int64_t)blockIdx.x * NT + threadIdx.x; g < P.ngroups;
-       g += (int64_t)gridDim.x * NT) {
-    const uint64_t r = finish_row_order(dec.run(InGlobalGroup{P.planes[0] + g * BW}), negmask, g, P.nrows);
-    P.bitmap[g] = r;
-    cnt_bits += __popcll(r);
   }
   publish_count<NT>(P, cnt_bits);
 }

@@ -127,7 +127,8 @@ constexpr int kNarrowUnits = 8;  // 16/32-byte units per thread per tile of the 
 const void* eval_in_kernel_for(int bw);
 // fle_eval_in.cu: IN list by decode + 16-bit entry table (bw <= 12, CTAs of 512 threads), or nullptr
 const void* eval_in_wide_kernel_for(int bw);
-constexpr int kInWideThreadsPerCta = 512;
+constexpr int kInWideThreadsPerCta = 512 + 32;  // 16 consumer warps + the producer warp
+constexpr int kInWideGroupsPerTile = 512;
 uint32_t eval_in_wide_table_bytes(int bw);
 // out = postfix program over K device bitmaps (leaf.col = bitmap index), word by word
 int launch_bitmap_combine(fle_ctx* ctx, const uint64_t* const* leaf_bitmaps_dev, int nleaf,
