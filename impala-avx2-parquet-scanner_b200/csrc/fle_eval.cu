@@ -934,8 +934,9 @@ int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, 
     P1.planes[0] = P.planes[c];
     P1.bw[0] = P.bw[c];
     P1.passes[0].col = 0;
-    // bw <= 12: 16-bit table entries, one ALU instruction per lookup (fle_eval_in.cu)
-    if (ctx->in_wide != 0 && P.bw[c] <= 12) {
+    // one CTA per SM, producer warp + 16 consumer warps: 16-bit table entries (one ALU instruction per
+    // lookup) for bw <= 12, replicated bit table beyond (fle_eval_in.cu)
+    if (ctx->in_wide != 0) {
       const int rc = launch_program(ctx, P1, MODE_IN_WIDE, (int)P.bw[c]);
       if (rc != FLE_E_UNSUPPORTED) return rc;
     }

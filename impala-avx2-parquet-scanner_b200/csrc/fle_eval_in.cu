@@ -43,14 +43,22 @@ namespace fle {
 // umulhi(x, 2^(32-J))) to unload the ALU pipe -- IMAD.HI issues at a quarter of the LOP3 rate
 // (tools/micro/int_pipes.cu) and shows up as dispatch stalls, every mix was slower; 2 stages /
 // 3-4 CTAs per SM instead of 4 stages / 2 CTAs -- no change, the pipe is the limit.
-template <int BW>
+// REP (the one-CTA-per-SM kernel at the end of this file, bw 13..16): the table is replicated
+// 32 / 16 / 8 times for bw <= 14 / 15 / 16 (64 KB at most), copy c of word w at byte
+// (w * copies + c) * 4, and lane l reads copy l mod copies: conflict-free up to bw 14, two or four
+// lanes per copy beyond (1.5 / 2.1 wavefronts per lookup instead of ~3.5 with one shared copy).
+// The word index then sits at bits kShift.. of the half, which is where pos() puts the code bits.
+template <int BW, bool REP = false>
 struct InTable {
-  static constexpr bool kPerLane = BW <= 13;  // 2^13 bits x 32 lanes = 32 KB
+  static constexpr bool kPerLane = REP || BW <= 13;  // 2^13 bits x 32 lanes = 32 KB
   static constexpr int kWords = BW <= 5 ? 1 : (1 << (BW - 5));
-  static constexpr int kShift = kPerLane ? 7 : 2;  // log2 of the byte stride between consecutive table words
+  static constexpr int kCopies = !REP ? (BW <= 13 ? 32 : 1) : (BW <= 14 ? 32 : (BW == 15 ? 16 : 8));
+  // log2 of the byte stride between consecutive table words
+  static constexpr int kShift = kCopies == 32 ? 7 : (kCopies == 16 ? 6 : (kCopies == 8 ? 5 : 2));
   static constexpr uint32_t kAddrMask = (uint32_t)(kWords - 1) << kShift;
+  static constexpr uint32_t kTableBytes = (uint32_t)kWords * 4u * (uint32_t)kCopies;
   // bit position of code bit i inside its 16-bit half of a transposed word
-  FLE_HD static constexpr int pos(int i) { return (kPerLane && i >= 5) ? i + 2 : i; }
+  FLE_HD static constexpr int pos(int i) { return (kPerLane && i >= 5) ? i + (kShift - 5) : i; }
 };
 
 // (a & ~M) | (b & M) as ONE LOP3 (written in C the compiler spends a LOP3 per constant, M and ~M)
@@ -87,10 +95,15 @@ __device__ __forceinline__ void in_transpose(uint32_t (&S)[16]) {
   in_stage<1, 0x55555555u>(S);
 }
 
-template <int BW>
+template <int BW, bool REP = false>
 struct InDecode {
-  using IT = InTable<BW>;
+  using IT = InTable<BW, REP>;
   uint32_t table;  // shared address of this lane's table (of the shared one for bw > 13)
+
+  // the group's planes, in registers: bit planes of rows 0..31 / 32..63, plane i at word 15 - pos(i)
+  struct Planes {
+    uint32_t S0[16], S1[16];
+  };
 
   // membership of the code in bits 0..15 of h (higher bits ignored) -> bit 31 of the result
   __device__ __forceinline__ uint32_t probe(uint32_t h) const {
@@ -100,7 +113,15 @@ struct InDecode {
 
   template <class L>
   __device__ __forceinline__ uint64_t run(const L& ld) const {
-    uint32_t S0[16], S1[16];  // bit planes of rows 0..31 / 32..63, plane i at word 15 - pos(i)
+    Planes pl;
+    load(ld, pl);
+    return compute(pl);
+  }
+
+  template <class L>
+  __device__ __forceinline__ void load(const L& ld, Planes& pl) const {
+    uint32_t (&S0)[16] = pl.S0;
+    uint32_t (&S1)[16] = pl.S1;
 #pragma unroll
     for (int j = 0; j < 16; ++j) S0[j] = S1[j] = 0u;
 #pragma unroll
@@ -114,6 +135,11 @@ struct InDecode {
         S1[15 - IT::pos(i + 1 < BW ? i + 1 : i)] = (uint32_t)b;
       }
     }
+  }
+
+  __device__ __forceinline__ uint64_t compute(Planes& pl) const {
+    uint32_t (&S0)[16] = pl.S0;
+    uint32_t (&S1)[16] = pl.S1;
     in_transpose(S0);  // S0[k] = half(row k) << 16 | half(row 16 + k)
     in_transpose(S1);  // S1[k] = half(row 32 + k) << 16 | half(row 48 + k)
     uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;  // rows 0..15, 16..31, 32..47, 48..63 (bit k = row base + k)
@@ -384,25 +410,52 @@ struct InWideDecode {
 // threads at 64 registers (285 us).  ncu: issue slots 71 % busy, ALU pipe 64 %; a group costs 592
 // issued instructions (268 ALU, 195 FMA, 70 LSU), so the kernel is bound by instruction issue as
 // much as by the ALU pipe.
+// The two table forms behind one interface for the kernel below.
+template <int BW>
+struct WideEntryPolicy {  // bw <= 12: 16-bit entries, lane-private
+  using Decode = InWideDecode<BW>;
+  static constexpr uint32_t kTableBytes = InWide<BW>::kTableBytes;
+  static constexpr uint32_t kCopies = 32;
+  static constexpr uint32_t kItemsPerLit = 32;
+  // item i of the table build: literal i / 32, lane i % 32
+  __device__ static __forceinline__ void put(uint32_t* table, uint32_t c, uint32_t lane) {
+    using IW = InWide<BW>;
+    const uint32_t e = c & (uint32_t)(IW::kEntries - 1), x = c >> IW::kTB;
+    atomicOr(&table[(e >> 1) * 32u + lane], 1u << ((e & 1u) * 16u + x * 8u));
+  }
+};
+
+template <int BW>
+struct WideBitsPolicy {  // bw 13..16: bit table, 32 / 16 / 8 copies
+  using Decode = InDecode<BW, true>;
+  using IT = InTable<BW, true>;
+  static constexpr uint32_t kTableBytes = IT::kTableBytes;
+  static constexpr uint32_t kCopies = IT::kCopies;
+  static constexpr uint32_t kItemsPerLit = IT::kCopies;
+  __device__ static __forceinline__ void put(uint32_t* table, uint32_t c, uint32_t copy) {
+    atomicOr(&table[(c >> 5) * kCopies + copy], 0x80000000u >> (c & 31));  // bit-reversed words, see probe()
+  }
+};
+
 // 16 consumer warps + one producer warp.  There is no CTA-wide barrier in the tile loop: a consumer
 // warp waits for the stage's "full" mbarrier, copies its groups' planes into registers, arrives on
 // the stage's "empty" mbarrier and only then evaluates; the producer refills a stage as soon as all
 // 16 warps have released it.  Warps therefore drift apart by up to a tile, which keeps some of them
-// in the ALU-only transposes while others are in the FMA / LSU-heavy lookups.
+// in the ALU-only transposes while others are in the FMA / LSU-heavy lookups (bw 12, 600 M rows:
+// 229 -> 202 us; the same change made the two-CTA bit-table kernel above 7 % slower).
 constexpr int kInWideConsumers = 512;
 constexpr int kInWideThreads = kInWideConsumers + 32;
 
-template <int BW>
+template <int BW, class POL>
 __global__ void __launch_bounds__(kInWideThreads, 1) eval_in_wide_kernel(const __grid_constant__ EvalParams P) {
   constexpr int NT = kInWideThreads, NC = kInWideConsumers;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t full0 = smem_u32(smem + P.smem_bar_off);  // full[s] at + 8 s, empty[s] at + 32 + 8 s (nstages <= 4)
   const uint32_t empty0 = full0 + 32u;
   const uint32_t stage0 = smem_u32(smem + P.smem_stage_off);
-  using IW = InWide<BW>;
-  uint32_t* table_ptr = reinterpret_cast<uint32_t*>(smem + P.smem_masks_off);  // [entry pair][lane]
-  InWideDecode<BW> dec;
-  dec.table = smem_u32(table_ptr) + (threadIdx.x & 31u) * 4u;
+  uint32_t* table_ptr = reinterpret_cast<uint32_t*>(smem + P.smem_masks_off);
+  typename POL::Decode dec;
+  dec.table = smem_u32(table_ptr) + (threadIdx.x & (POL::kCopies - 1u)) * 4u;
   const int T = NC;  // one group per consumer thread per tile
   const int seg_groups = T >> 3;
   const int64_t ntiles = P.ngroups / T;
@@ -415,15 +468,12 @@ __global__ void __launch_bounds__(kInWideThreads, 1) eval_in_wide_kernel(const _
     }
     mbar_fence_init();
   }
-  for (int i = threadIdx.x; i < (int)(IW::kTableBytes / 4u); i += NT) table_ptr[i] = 0;
+  for (int i = threadIdx.x; i < (int)(POL::kTableBytes / 4u); i += NT) table_ptr[i] = 0;
   __syncthreads();
   const PassDesc& pd = P.passes[0];
   const int off = (int)pd.lit[0], cnt = (int)pd.lit[1];
-  for (int i = threadIdx.x; i < cnt * 32; i += NT) {
-    const uint32_t c = P.in_lits[off + (i >> 5)];  // already masked to BW bits by the host
-    const uint32_t e = c & (uint32_t)(IW::kEntries - 1), x = c >> IW::kTB;
-    atomicOr(&table_ptr[(e >> 1) * 32u + (uint32_t)(i & 31)], 1u << ((e & 1u) * 16u + x * 8u));
-  }
+  for (int i = threadIdx.x; i < cnt * (int)POL::kItemsPerLit; i += NT)  // literals already masked to BW bits by the host
+    POL::put(table_ptr, P.in_lits[off + i / (int)POL::kItemsPerLit], (uint32_t)i % POL::kItemsPerLit);
   __syncthreads();
   uint64_t cnt_bits = 0;
 
@@ -451,7 +501,7 @@ __global__ void __launch_bounds__(kInWideThreads, 1) eval_in_wide_kernel(const _
     uint32_t parity = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       mbar_wait(full0 + stage * 8, parity);
-      typename InWideDecode<BW>::Planes pl;
+      typename POL::Decode::Planes pl;
       dec.load(InSmemGroup{stage0 + stage * P.stage_bytes + thread_off}, pl);
       __syncwarp();
       if ((threadIdx.x & 31u) == 0) mbar_arrive(empty0 + stage * 8);  // this warp is done with the stage
@@ -476,14 +526,18 @@ __global__ void __launch_bounds__(kInWideThreads, 1) eval_in_wide_kernel(const _
 
 const void* eval_in_wide_kernel_for(int bw) {
   switch (bw) {
-#define X(B) case B: return (const void*)eval_in_wide_kernel<B>;
+#define X(B) case B: return (const void*)eval_in_wide_kernel<B, WideEntryPolicy<B> >;
     X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12)
+#undef X
+#define X(B) case B: return (const void*)eval_in_wide_kernel<B, WideBitsPolicy<B> >;
+    X(13) X(14) X(15) X(16)
 #undef X
   }
   return nullptr;
 }
 
 uint32_t eval_in_wide_table_bytes(int bw) {
+  if (bw > 12) return (4u << (bw - 5)) * (bw <= 14 ? 32u : (bw == 15 ? 16u : 8u));  // InTable<bw, true>::kTableBytes
   const int tb = bw < 11 ? bw : 11;
   return (uint32_t)std::max(2, 1 << tb) * 64u;
 }

@@ -113,8 +113,11 @@ int fle_ctx_sync(fle_ctx* ctx);
  * "eval_narrow_bw" (single-pass programs on columns up to this width -- default 2; 1, 2 or 4
  * exist -- read the planes with coalesced 128-bit loads instead of staging them),
  * "in_lookup_min" (IN lists of at least this many literals on columns of <= 16 bits use the
- * decode + membership-lookup kernel, shorter ones equality chains on the planes; default 9,
- * 2^30 disables the lookup kernel),
+ * decode + membership-lookup kernels, shorter ones equality chains on the planes; default 9,
+ * 2^30 disables the lookup kernels),
+ * "in_wide" (1 [default]: the lookup runs on the one-CTA-per-SM producer/consumer kernel --
+ * 16-bit table entries for bw <= 12, replicated bit table for bw 13..16; 0: the two-CTA bit-table
+ * kernel, kept as an on-device cross-check),
  * "codec_variant" (0 = direct loads/stores; 1 [default] = per-bit-width choice among the staged
  * unpack kernels; 2 = per-row bulk stores, 3 = warp-private copy-out, 4 = CTA-wide copy-out),
  * "codec_ctas_per_sm" (0 = auto), "h2d_chunk_rows". */

@@ -505,7 +505,7 @@ def test_in_list_lookup_kernel_vs_oracle(ctx, oracle, bw):
     for L in (1, 8, 64, 256, 1000):
         lits = rng.integers(0, 1 << bw, size=L, dtype=np.uint64)  # duplicates and absent codes included
         want, wcnt = oracle.pred(IN, words, bw, 0, n, lits)
-        # (lookup_min, in_wide): entry-table kernel (bw <= 12), bit-table kernel, plane form
+        # (lookup_min, in_wide): one-CTA producer/consumer kernel (entry table, replicated bit table), two-CTA bit-table kernel, plane form
         for lookup_min, wide in ((1, 1), (1, 0), (1 << 30, 1)):
             ctx.set_option("in_lookup_min", lookup_min)
             ctx.set_option("in_wide", wide)
@@ -517,7 +517,7 @@ def test_in_list_lookup_kernel_vs_oracle(ctx, oracle, bw):
                 ctx.set_option("in_wide", 1)
             assert (bm == want).all() and cnt == wcnt, (bw, L, lookup_min, wide)
             if lookup_min == 1 and bw <= 16:
-                assert mode == (6 if wide and bw <= 12 else 3), (bw, mode)
+                assert mode == (6 if wide else 3), (bw, mode)
 
 
 # ------------------------------------------------------------------------------------------

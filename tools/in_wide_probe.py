@@ -20,7 +20,7 @@ G = (n + 63) // 64
 cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
 gen = torch.Generator().manual_seed(7)
 ctx.set_option("in_lookup_min", 1)
-for bw, dom in ((12, 2526), (11, 2048), (10, 1000), (8, 256), (6, 50), (3, 7))[:int(os.environ.get("NBW", "6"))]:
+for bw, dom in ((16, 40000), (14, 16384), (13, 8192), (12, 2526), (11, 2048), (10, 1000), (8, 256), (6, 50), (3, 7))[:int(os.environ.get("NBW", "9"))]:
     v, w = make_col(ctx, n, bw, dom=dom, seed=bw)
     del v
     by = G * bw * 8 + G * 8
@@ -28,7 +28,7 @@ for bw, dom in ((12, 2526), (11, 2048), (10, 1000), (8, 256), (6, 50), (3, 7))[:
         lits = torch.randint(0, dom, (L,), generator=gen).tolist()
         prog = [(IN, 0, lits)]
         res = {}
-        for name, wide, nt, stages in (("bit", 0, 0, 0), ("wide", 1, 0, 0), ("bit2", 0, 0, 0), ("wide2", 1, 0, 0)):
+        for name, wide, nt, stages in (("bit", 0, 0, 0), ("wide", 1, 0, 0)):
             ctx.set_option("in_wide", wide)
             ctx.set_option("eval_stages", stages)
             bm = torch.empty(G, dtype=torch.int64, device="cuda")
