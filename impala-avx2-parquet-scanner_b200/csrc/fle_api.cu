@@ -367,6 +367,7 @@ int fle_ctx_destroy(fle_ctx* ctx) {
   if (ctx->d_in_lits) cudaFree(ctx->d_in_lits);
   if (ctx->h_in_lits) cudaFreeHost(ctx->h_in_lits);
   if (ctx->d_count) cudaFree(ctx->d_count);
+  if (ctx->d_split) cudaFree(ctx->d_split);
   if (ctx->h_count) cudaFreeHost(ctx->h_count);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -405,6 +406,7 @@ int fle_ctx_set_option(fle_ctx* ctx, const char* name, int64_t value) {
   else if (k == "eval_gpt") ctx->eval_gpt = (int)value;
   else if (k == "in_lookup_min") ctx->in_lookup_min = (int)value;
   else if (k == "in_wide") ctx->in_wide = (int)value;
+  else if (k == "in_split_min_rows") ctx->in_split_min_rows = value;
   else if (k == "eval_narrow_bw") ctx->eval_narrow_bw = (int)value;
   else if (k == "codec_variant") ctx->codec_variant = (int)value;
   else if (k == "codec_ctas_per_sm") ctx->codec_ctas_per_sm = (int)value;
@@ -425,6 +427,7 @@ int64_t fle_ctx_get_option(fle_ctx* ctx, const char* name) {
   if (k == "eval_gpt") return ctx->eval_gpt;
   if (k == "in_lookup_min") return ctx->in_lookup_min;
   if (k == "in_wide") return ctx->in_wide;
+  if (k == "in_split_min_rows") return ctx->in_split_min_rows;
   if (k == "eval_narrow_bw") return ctx->eval_narrow_bw;
   if (k == "codec_variant") return ctx->codec_variant;
   if (k == "codec_ctas_per_sm") return ctx->codec_ctas_per_sm;

@@ -21,9 +21,11 @@
 // Single-pass programs and single IN lists have their own kernels (fle_eval1.cu, fle_eval_in.cu).
 #include <algorithm>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <set>
 #include <utility>
+#include <vector>
 
 #include "fle_device.cuh"
 #include "fle_internal.h"
@@ -1017,9 +1019,155 @@ int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, 
   return launch_program(ctx, P, MODE_DIRECT, sum_bw);
 }
 
+// Long IN lists inside a larger program.  The fused kernels walk an IN leaf's literal pool per
+// group (O(L * bw) plane operations, like the reference, fle-encoding.h:8279-8290), so a program
+// with a 256-literal list runs an order of magnitude below the roofline although the lookup
+// kernels answer the same list at a cost independent of L.  AND / OR are associative and
+// commutative on bitmaps, so every maximal chain of one operator that contains such a leaf is
+// regrouped: each long list goes through the lookup kernel into a temporary bitmap, ALL other
+// operands of the chain are joined into ONE fused sub-program (each of its columns still read
+// once), and the bitmaps are combined word by word (n / 8 bytes each: 8 % of a bw-12 column).
+// FLE_E_UNSUPPORTED = nothing to regroup, the caller runs the program as a whole.
+constexpr int kInSplitMinLits = 16;
+
+static int launch_eval_in_split(fle_ctx* ctx, const fle_col_desc* cols, int ncols, const fle_pred_node* nodes,
+                                int nnodes, int64_t first_row, int64_t n, uint64_t* bitmap_dev,
+                                uint64_t* count_dev) {
+  if (nnodes < 2 || nnodes > FLE_MAX_NODES || !bitmap_dev) return FLE_E_UNSUPPORTED;
+  const int min_lits = std::max(kInSplitMinLits, ctx->in_lookup_min);
+  int lhs[FLE_MAX_NODES], rhs[FLE_MAX_NODES], start[FLE_MAX_NODES];
+  bool has_big[FLE_MAX_NODES];
+  {
+    int stack[FLE_MAX_NODES], sp = 0;
+    bool any = false;
+    for (int i = 0; i < nnodes; ++i) {
+      const fle_pred_node& nd = nodes[i];
+      if (nd.op == FLE_OP_AND || nd.op == FLE_OP_OR) {
+        if (sp < 2) return FLE_E_UNSUPPORTED;  // malformed: the normal path reports it
+        rhs[i] = stack[--sp];
+        lhs[i] = stack[--sp];
+        start[i] = start[lhs[i]];
+        has_big[i] = has_big[lhs[i]] || has_big[rhs[i]];
+      } else {
+        lhs[i] = rhs[i] = -1;
+        start[i] = i;
+        const bool leaf_col = nd.op != FLE_OP_ALL && nd.op != FLE_OP_NONE;
+        if (leaf_col && (nd.col < 0 || nd.col >= ncols || cols[nd.col].max_def_level != 0)) return FLE_E_UNSUPPORTED;
+        has_big[i] = nd.op == FLE_OP_IN && nd.ncodes >= min_lits && cols[nd.col].bit_width <= 16;
+        any = any || has_big[i];
+      }
+      stack[sp++] = i;
+    }
+    if (sp != 1 || !any) return FLE_E_UNSUPPORTED;
+  }
+  const int64_t nwords = (n + 63) / 64;
+  // temporary bitmaps: one per long list + at most one per operator chain, carved out of a grow-only
+  // buffer of the context (stream-ordered allocations would go back to the driver at every
+  // synchronisation: 75 MB bitmaps, several hundred microseconds per call)
+  int nbig = 0, nops = 0;
+  for (int i = 0; i < nnodes; ++i) {
+    if (nodes[i].op == FLE_OP_AND || nodes[i].op == FLE_OP_OR) nops += has_big[i] ? 1 : 0;
+    else nbig += has_big[i] ? 1 : 0;
+  }
+  const size_t bm_bytes = ((size_t)std::max<int64_t>(nwords, 1) * 8 + 255) / 256 * 256;
+  const size_t need = bm_bytes * (size_t)(nbig + nops);
+  if (need > ctx->split_cap) {
+    FLE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_split) cudaFree(ctx->d_split);
+    ctx->d_split = nullptr;
+    ctx->split_cap = 0;
+    FLE_CUDA_TRY(ctx, cudaMalloc(&ctx->d_split, need));
+    ctx->split_cap = need;
+  }
+  std::vector<const uint64_t*> leaf_bm;
+  int rc = FLE_OK;
+  // evaluates a column-space postfix fragment into a fresh bitmap, returns its index in leaf_bm
+  const auto materialise = [&](std::vector<fle_pred_node>& frag) -> int {
+    uint64_t* lb = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(ctx->d_split) + bm_bytes * leaf_bm.size());
+    std::vector<int> map(ncols, -1);
+    std::vector<fle_col_desc> dc;
+    for (auto& nd : frag) {
+      if (nd.op == FLE_OP_AND || nd.op == FLE_OP_OR || nd.op == FLE_OP_ALL || nd.op == FLE_OP_NONE) continue;
+      if (map[nd.col] < 0) { map[nd.col] = (int)dc.size(); dc.push_back(cols[nd.col]); }
+      nd.col = map[nd.col];
+    }
+    LoweredProgram lp;
+    rc = prepare_eval(ctx, dc.data(), (int)dc.size(), frag.data(), (int)frag.size(), &lp);
+    if (rc == FLE_OK) rc = launch_prepared(ctx, &lp, dc.data(), (int)dc.size(), first_row, n, lb, nullptr);
+    if (rc != FLE_OK) return -1;
+    leaf_bm.push_back(lb);
+    return (int)leaf_bm.size() - 1;
+  };
+  // node -> column-space fragment (no long list below) or bitmap-space postfix over leaf_bm
+  struct Res { bool comb; std::vector<fle_pred_node> prog; };
+  std::function<Res(int)> emit = [&](int i) -> Res {
+    Res r;
+    if (!has_big[i]) {
+      r.comb = false;
+      r.prog.assign(nodes + start[i], nodes + i + 1);
+      return r;
+    }
+    r.comb = true;
+    const int op = nodes[i].op;
+    if (op != FLE_OP_AND && op != FLE_OP_OR) {  // the long list itself
+      std::vector<fle_pred_node> leaf(1, nodes[i]);
+      const int b = materialise(leaf);
+      r.prog.push_back(fle_pred_node{FLE_OP_EQ, (int32_t)b, 0, nullptr, 0, 0});  // the combine kernel only looks at .col
+      return r;
+    }
+    // operands of the maximal chain of `op` through subtrees that hold a long list
+    std::vector<int> operands, todo(1, i);
+    while (!todo.empty()) {
+      const int k = todo.back();
+      todo.pop_back();
+      if (nodes[k].op == op && has_big[k]) {
+        todo.push_back(rhs[k]);
+        todo.push_back(lhs[k]);
+      } else {
+        operands.push_back(k);
+      }
+    }
+    std::vector<fle_pred_node> joined;  // all the other operands as ONE fused program
+    int njoined = 0, ncomb = 0;
+    for (int k : operands) {
+      if (rc != FLE_OK) break;
+      Res sub = emit(k);
+      if (!sub.comb) {  // constants only: straight into the combine program, there is no column to launch on
+        bool consts = true;
+        for (const auto& nd : sub.prog)
+          consts = consts && (nd.op == FLE_OP_ALL || nd.op == FLE_OP_NONE || nd.op == FLE_OP_AND || nd.op == FLE_OP_OR);
+        sub.comb = consts;
+      }
+      if (sub.comb) {
+        r.prog.insert(r.prog.end(), sub.prog.begin(), sub.prog.end());
+        if (++ncomb > 1) r.prog.push_back(fle_pred_node{op, 0, 0, nullptr, 0, 0});
+      } else {
+        joined.insert(joined.end(), sub.prog.begin(), sub.prog.end());
+        if (++njoined > 1) joined.push_back(fle_pred_node{op, 0, 0, nullptr, 0, 0});
+      }
+    }
+    if (rc == FLE_OK && njoined > 0) {
+      const int b = materialise(joined);
+      r.prog.push_back(fle_pred_node{FLE_OP_EQ, (int32_t)b, 0, nullptr, 0, 0});
+      if (ncomb > 0) r.prog.push_back(fle_pred_node{op, 0, 0, nullptr, 0, 0});
+    }
+    return r;
+  };
+  Res root = emit(nnodes - 1);
+  if (rc == FLE_OK)
+    rc = launch_bitmap_combine(ctx, leaf_bm.data(), (int)leaf_bm.size(), root.prog.data(), (int)root.prog.size(), n,
+                               bitmap_dev, count_dev);
+  return rc;
+}
+
 int launch_eval(fle_ctx* ctx, const fle_col_desc* cols, int ncols, const fle_pred_node* nodes,
                 int nnodes, int64_t first_row, int64_t n, uint64_t* bitmap_dev,
                 uint64_t* count_dev) {
+  if (nnodes > 1 && ctx->in_split_min_rows >= 0 && n >= ctx->in_split_min_rows && ctx->eval_variant != 0 &&
+      ctx->in_lookup_min < (1 << 30)) {
+    const int rc = launch_eval_in_split(ctx, cols, ncols, nodes, nnodes, first_row, n, bitmap_dev, count_dev);
+    if (rc != FLE_E_UNSUPPORTED) return rc;
+  }
   LoweredProgram lp;
   int rc = prepare_eval(ctx, cols, ncols, nodes, nnodes, &lp);
   if (rc != FLE_OK) return rc;

@@ -61,6 +61,7 @@ struct fle_ctx {
   int eval_narrow_bw = 2;    // single-pass programs on columns up to this width skip shared-memory staging (bw 1, 2, 4)
   int in_lookup_min = 9;     // IN lists at least this long use the decode+lookup kernel (bw <= 16); shorter ones the plane form
   int in_wide = 1;           // IN lookup on bw <= 12: 16-bit entry table (1) or the bit table (0)
+  int64_t in_split_min_rows = 1ll << 20;  // calls of at least this many rows evaluate long IN lists (>= 16 literals) inside larger programs with the lookup kernels; -1 = never
   int codec_variant = 1;
   int codec_ctas_per_sm = 0;  // 0 = as many as fit
   int eval_jit = 1;                      // 0 never, 1 when n >= eval_jit_min_rows or already compiled, 2 always
@@ -75,6 +76,8 @@ struct fle_ctx {
   int in_lits_cap = 0;
   uint32_t* h_in_lits = nullptr;  // pinned staging for IN literal pools
   uint64_t* d_count = nullptr;    // 8-byte result slot for host-facing calls
+  uint64_t* d_split = nullptr;    // temporary bitmaps of regrouped programs (long IN lists), grow-only
+  size_t split_cap = 0;           // bytes
   uint64_t* h_count = nullptr;    // pinned
 
   // host-facing pipelines: staging buffers

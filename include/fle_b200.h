@@ -115,6 +115,9 @@ int fle_ctx_sync(fle_ctx* ctx);
  * "in_lookup_min" (IN lists of at least this many literals on columns of <= 16 bits use the
  * decode + membership-lookup kernels, shorter ones equality chains on the planes; default 9,
  * 2^30 disables the lookup kernels),
+ * "in_split_min_rows" (device-resident evaluations of at least this many rows -- default 2^20 --
+ * evaluate IN lists of >= 16 literals that sit INSIDE a larger program with the lookup kernels and
+ * combine bitmaps, instead of walking the literal pool in the fused kernel; -1 = never),
  * "in_wide" (1 [default]: the lookup runs on the one-CTA-per-SM producer/consumer kernel --
  * 16-bit table entries for bw <= 12, replicated bit table for bw 13..16; 0: the two-CTA bit-table
  * kernel, kept as an on-device cross-check),

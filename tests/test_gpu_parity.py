@@ -520,6 +520,48 @@ def test_in_list_lookup_kernel_vs_oracle(ctx, oracle, bw):
                 assert mode == (6 if wide else 3), (bw, mode)
 
 
+def test_long_in_lists_inside_programs_vs_oracle(ctx, oracle):
+    """Long IN lists inside larger programs (device-resident calls): the list goes through the lookup kernel,
+    the other operands of its AND / OR chain run as one fused program, bitmaps are combined word by word
+    (in_split_min_rows).  Must equal the reference's leaf-by-leaf evaluation (simple-predicates.h:145-163,
+    fle-encoding.h:8236-8313) and the unsplit program."""
+    import torch
+    rng = np.random.default_rng(77)
+    n = 64 * 9000 + 29
+    bws = (12, 6, 16, 3)
+    doms = (2526, 50, 40000, 7)
+    vals = [rng.integers(0, d, size=n).astype(np.uint32) for d in doms]
+    cols = [(oracle.pack(v, bw), bw) for v, bw in zip(vals, bws)]
+    dev = [(torch.from_numpy(w.view(np.int64)).cuda(), bw) for w, bw in cols]
+    big0 = rng.choice(vals[0], size=256).astype(np.uint64)
+    big2 = rng.choice(vals[2], size=64).astype(np.uint64)
+    progs = {
+        "in_and": [(IN, 0, big0), (LT, 1, 30), (AND, None, None)],
+        "lt_and_in": [(LT, 1, 30), (IN, 0, big0), (AND, None, None)],
+        "chain": [(IN, 0, big0), (GE, 1, 5), (AND, None, None), (LT, 1, 40), (AND, None, None), (IN, 2, big2), (AND, None, None),
+                  (IN, 3, [1, 4]), (AND, None, None)],
+        "or_of_and": [(IN, 0, big0), (GE, 1, 5), (LT, 3, 4), (AND, None, None), (OR, None, None)],
+        "nested": [(IN, 0, big0), (LT, 1, 10), (AND, None, None), (GE, 3, 5), (OR, None, None), (LT, 2, 30000), (AND, None, None)],
+        "two_lists_or": [(IN, 0, big0), (IN, 2, big2), (OR, None, None)],
+        "same_col": [(IN, 0, big0), (LT, 0, 1500), (AND, None, None), (GE, 0, 100), (AND, None, None)],
+        "consts": [(ALL, None, None), (IN, 0, big0), (AND, None, None), (NONE, None, None), (OR, None, None)],
+    }
+    for name, prog in progs.items():
+        want, wcnt = oracle.eval_tree(cols, prog, n)
+        for split in (0, -1):
+            ctx.set_option("in_split_min_rows", split)
+            try:
+                launches = ctx.launch_count
+                bm, cnt = ctx.eval_dev(dev, prog, n)
+                torch.cuda.synchronize()
+                launches = ctx.launch_count - launches
+            finally:
+                ctx.set_option("in_split_min_rows", 1 << 20)
+            got = bm.cpu().numpy().view(np.uint64)
+            assert (got == want).all() and int(cnt.item()) == wcnt, (name, split)
+            assert (launches > 1) == (split == 0), (name, split, launches)
+
+
 # ------------------------------------------------------------------------------------------
 # "next" rows: page framing on the device, PLAIN-encoded predicates (SURVEY 8f-1, 8f-3)
 # ------------------------------------------------------------------------------------------

@@ -47,3 +47,28 @@ for bw, dom in ((16, 40000), (14, 16384), (13, 8192), (12, 2526), (11, 2048), (1
         print(line, flush=True)
     del w
     torch.cuda.empty_cache()
+
+# long IN lists inside larger programs: regrouped (lookup kernel + fused rest + combine) against the whole program on the
+# specialised kernel (in_split_min_rows = -1)
+from fle_b200 import AND, LT  # noqa: E402
+
+if os.environ.get("SPLIT", "1") == "1":
+    ctx.set_option("in_lookup_min", 9)
+    v, w12 = make_col(ctx, n, 12, dom=2526, seed=12)
+    del v
+    v, w6 = make_col(ctx, n, 6, dom=50, seed=6)
+    del v
+    by = G * 12 * 8 + G * 6 * 8 + G * 8
+    for L in (20, 64, 256):
+        prog = [(IN, 0, torch.randint(0, 2526, (L,), generator=gen).tolist()), (LT, 1, 23), (AND, None, None)]
+        res = {}
+        for name, split in (("whole", -1), ("regrouped", 0)):
+            ctx.set_option("in_split_min_rows", split)
+            bm = torch.empty(G, dtype=torch.int64, device="cuda")
+            mn, md = timeit(lambda: ctx.eval_dev([(w12, 12), (w6, 6)], prog, n, bitmap=bm, count=cnt))
+            res[name] = (mn, bm)
+        ctx.set_option("in_split_min_rows", 1 << 20)
+        same = bool(torch.equal(res["whole"][1], res["regrouped"][1]))
+        print(f"IN({L}) on bw12 AND bw6 < 23: whole {res['whole'][0]*1e3:7.1f} us frac {by/res['whole'][0]/1e6/PEAK:.3f} | "
+              f"regrouped {res['regrouped'][0]*1e3:7.1f} us frac {by/res['regrouped'][0]/1e6/PEAK:.3f} identical {same}", flush=True)
+        assert same
