@@ -30,8 +30,10 @@ EXPORTS = [
     "fle_unpack_u32_dev", "fle_eval", "fle_eval_dev", "fle_bitmap_count_dev", "fle_intersect_bitset",
     "fle_intersect_bitset_dev", "fle_bitmap_select_dev", "fle_gather_dev", "fle_sum_product_dev",
     "fle_page_parse", "fle_realign_dev", "fle_plain_eval_dev", "fle_dict_encode_dev", "fle_eval_codegen",
-    "fle_eval_sum_product_dev",
+    "fle_eval_sum_product_dev", "fle_group_create_local", "fle_group_export", "fle_group_open", "fle_group_close",
+    "fle_group_status", "fle_eval_group_dev", "fle_eval_sum_product_group_dev",
 ]
+GROUP_HANDLE_BYTES = 64
 
 
 class FleError(RuntimeError):
@@ -51,6 +53,15 @@ class PageLayout(C.Structure):
 
 
 T_INT32, T_INT64, T_FLOAT, T_DOUBLE = range(4)
+
+
+def group_create_local(ctxs: Sequence["FleContext"]):
+    """Contexts of ONE process (same or different devices) whose totals are summed in-kernel."""
+    lib = load_library()
+    arr = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    rc = lib.fle_group_create_local(arr, len(ctxs))
+    if rc != OK:
+        raise FleError(rc, lib.fle_strerror(rc).decode())
 
 
 class PredNode(C.Structure):
@@ -114,6 +125,13 @@ def load_library() -> C.CDLL:
                                            vp, vp, vp]
     L.fle_eval_codegen.argtypes = [C.POINTER(ColDesc), i32, C.POINTER(PredNode), i32, i32, C.c_char_p, C.c_size_t,
                                    C.POINTER(C.c_size_t)]
+    L.fle_group_create_local.argtypes = [C.POINTER(vp), i32]
+    L.fle_group_export.argtypes = [vp, vp]
+    L.fle_group_open.argtypes = [vp, i32, i32, vp]
+    L.fle_group_close.argtypes = [vp]
+    L.fle_group_status.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), u64p, u64p]
+    L.fle_eval_group_dev.argtypes = L.fle_eval_dev.argtypes
+    L.fle_eval_sum_product_group_dev.argtypes = L.fle_eval_sum_product_dev.argtypes
     _lib = L
     return L
 
@@ -364,6 +382,55 @@ class FleContext:
         if out is None:
             out = torch.zeros(2, dtype=torch.int64, device=plain_i64.device)
         self._check(self.lib.fle_eval_sum_product_dev(
+            self.h, descs, len(cols), nodes, len(nodes), first_row, n, plain_i64.data_ptr(), code_col, dict_i64.data_ptr(),
+            dict_i64.numel(), bitmap.data_ptr() if bitmap is not None else None, out.data_ptr(), out.data_ptr() + 8))
+        return out
+
+    # -- groups of GPUs (totals summed inside the scan kernel) --------------------------------
+    def group_export(self) -> bytes:
+        buf = C.create_string_buffer(GROUP_HANDLE_BYTES)
+        self._check(self.lib.fle_group_export(self.h, buf))
+        return buf.raw
+
+    def group_open(self, rank: int, world: int, handles: Sequence[bytes]):
+        blob = b"".join(handles)
+        assert len(blob) == world * GROUP_HANDLE_BYTES
+        self._check(self.lib.fle_group_open(self.h, rank, world, blob))
+
+    def group_close(self):
+        self._check(self.lib.fle_group_close(self.h))
+
+    def group_status(self):
+        r, w, d, t = C.c_int(0), C.c_int(0), C.c_uint64(0), C.c_uint64(0)
+        self._check(self.lib.fle_group_status(self.h, C.byref(r), C.byref(w), C.byref(d), C.byref(t)))
+        return {"rank": r.value, "world": w.value, "reductions_done": d.value, "peers_timed_out": t.value}
+
+    def eval_group_dev(self, cols: Sequence, program: Sequence[tuple], n: int, first_row: int = 0, bitmap=None, count=None,
+                       prepared=None):
+        """eval_dev over this GPU's rows; count = matches over all GPUs of the group."""
+        import torch
+        dev = cols[0][0].device
+        if bitmap is None:
+            bitmap = torch.empty(max(1, (n + 63) // 64), dtype=torch.int64, device=dev)
+        if count is None:
+            count = torch.zeros(1, dtype=torch.int64, device=dev)
+        if prepared is None:
+            prepared = (self.make_col_descs(cols),) + _build_program(program)
+        descs, nodes, _keep = prepared
+        self._check(self.lib.fle_eval_group_dev(self.h, descs, len(cols), nodes, len(nodes), first_row, n,
+                                                bitmap.data_ptr(), count.data_ptr()))
+        return bitmap, count
+
+    def eval_sum_product_group_dev(self, cols: Sequence, program: Sequence[tuple], n: int, plain_i64, code_col: int, dict_i64,
+                                   first_row: int = 0, bitmap=None, out=None, prepared=None):
+        """eval_sum_product_dev over this GPU's rows; out = (sum, count) over all GPUs of the group."""
+        import torch
+        if prepared is None:
+            prepared = (self.make_col_descs(cols),) + _build_program(program)
+        descs, nodes, _keep = prepared
+        if out is None:
+            out = torch.zeros(2, dtype=torch.int64, device=plain_i64.device)
+        self._check(self.lib.fle_eval_sum_product_group_dev(
             self.h, descs, len(cols), nodes, len(nodes), first_row, n, plain_i64.data_ptr(), code_col, dict_i64.data_ptr(),
             dict_i64.numel(), bitmap.data_ptr() if bitmap is not None else None, out.data_ptr(), out.data_ptr() + 8))
         return out

@@ -368,6 +368,7 @@ int fle_ctx_destroy(fle_ctx* ctx) {
   if (ctx->h_in_lits) cudaFreeHost(ctx->h_in_lits);
   if (ctx->d_count) cudaFree(ctx->d_count);
   if (ctx->d_split) cudaFree(ctx->d_split);
+  fle::group_release(ctx);
   if (ctx->h_count) cudaFreeHost(ctx->h_count);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -413,6 +414,7 @@ int fle_ctx_set_option(fle_ctx* ctx, const char* name, int64_t value) {
   else if (k == "eval_jit") ctx->eval_jit = (int)value;
   else if (k == "eval_jit_min_rows") ctx->eval_jit_min_rows = value;
   else if (k == "h2d_chunk_rows") ctx->h2d_chunk_rows = value;
+  else if (k == "group_timeout_ms") ctx->grp_timeout_ms = value;
   else return set_error(ctx, FLE_E_INVALID, "unknown option " + k);
   return FLE_OK;
 }
@@ -434,6 +436,7 @@ int64_t fle_ctx_get_option(fle_ctx* ctx, const char* name) {
   if (k == "eval_jit") return ctx->eval_jit;
   if (k == "eval_jit_min_rows") return ctx->eval_jit_min_rows;
   if (k == "h2d_chunk_rows") return ctx->h2d_chunk_rows;
+  if (k == "group_timeout_ms") return ctx->grp_timeout_ms;
   if (k == "jit_launches") return ctx->jit_launches;
   if (k == "last_mode") return ctx->last_mode;
   if (k == "num_sms") return ctx->num_sms;
@@ -838,6 +841,72 @@ int fle_eval_sum_product_dev(fle_ctx* ctx, const fle_col_desc* cols, int ncols, 
   const uint8_t* planes = reinterpret_cast<const uint8_t*>(cols[code_col].planes) + (uint64_t)(first_row / 64) * bw * 8u;
   return launch_sum_product(ctx, bitmap_dev, n, plain_i64_dev, reinterpret_cast<const uint64_t*>(planes), bw,
                             dict_i64_dev, ndict, sum_dev, count_dev);
+}
+
+// ---- groups of GPUs: totals summed inside the scan kernel ---------------------------------------
+// The fused exchange attaches to the ONE kernel that publishes the call's totals (group_fill looks at
+// grp_on and at the count pointer); paths that end in another kernel (nullable columns, long IN
+// lists regrouped around the lookup kernel, the two-kernel aggregate, empty inputs) are followed by
+// the one-warp reduce kernel instead.  Either way a call consumes exactly one sequence number.
+int fle_eval_group_dev(fle_ctx* ctx, const fle_col_desc* cols, int ncols, const fle_pred_node* nodes, int nnodes,
+                       int64_t first_row, int64_t n, uint64_t* bitmap_dev, uint64_t* total_count_dev) {
+  FLE_CHECK_CTX(ctx);
+  if (!total_count_dev) return set_error(ctx, FLE_E_INVALID, "group evaluation needs a count slot");
+  if (ctx->grp_world < 1) return set_error(ctx, FLE_E_INVALID, "context does not belong to a group");
+  if (!cols || !nodes || ncols < 1 || nnodes < 1) return set_error(ctx, FLE_E_INVALID, "empty program");
+  if (ncols > FLE_MAX_COLS) return set_error(ctx, FLE_E_UNSUPPORTED, "too many columns");
+  if (any_nullable(cols, ncols)) {
+    int rc = eval_dev_nullable(ctx, cols, ncols, nodes, nnodes, first_row, n, bitmap_dev, total_count_dev);
+    if (rc != FLE_OK) return rc;
+    return launch_group_reduce(ctx, total_count_dev, nullptr);
+  }
+  // single-kernel path: lower + launch with the exchange fused; everything else: trailing reduce
+  const int64_t launches0 = ctx->launches;
+  LoweredProgram lp;
+  int rc = FLE_E_UNSUPPORTED;
+  bool fused = false;
+  if (n > 0) {
+    // (long IN lists inside larger programs keep their regrouped multi-kernel form)
+    std::string err;
+    bool long_in = false;
+    for (int i = 0; i < nnodes && nnodes > 1; ++i)
+      long_in = long_in || (nodes[i].op == FLE_OP_IN && nodes[i].ncodes >= 16);
+    if (!long_in) {
+      rc = prepare_eval(ctx, cols, ncols, nodes, nnodes, &lp);
+      if (rc != FLE_OK) return rc;
+      ctx->grp_on = true;
+      rc = launch_prepared(ctx, &lp, cols, ncols, first_row, n, bitmap_dev, total_count_dev);
+      ctx->grp_on = false;
+      if (rc != FLE_OK) return rc;
+      fused = ctx->launches == launches0 + 1;
+    }
+  }
+  if (fused) return FLE_OK;
+  if (rc == FLE_E_UNSUPPORTED) {
+    rc = launch_eval(ctx, cols, ncols, nodes, nnodes, first_row, n, bitmap_dev, total_count_dev);
+    if (rc != FLE_OK) return rc;
+  }
+  return launch_group_reduce(ctx, total_count_dev, nullptr);
+}
+
+int fle_eval_sum_product_group_dev(fle_ctx* ctx, const fle_col_desc* cols, int ncols, const fle_pred_node* nodes,
+                                   int nnodes, int64_t first_row, int64_t n, const int64_t* plain_i64_dev, int code_col,
+                                   const int64_t* dict_i64_dev, int ndict, uint64_t* bitmap_dev, int64_t* total_sum_dev,
+                                   uint64_t* total_count_dev) {
+  FLE_CHECK_CTX(ctx);
+  if (!total_count_dev || !total_sum_dev) return set_error(ctx, FLE_E_INVALID, "group aggregate needs sum and count slots");
+  if (ctx->grp_world < 1) return set_error(ctx, FLE_E_INVALID, "context does not belong to a group");
+  const int64_t launches0 = ctx->launches;
+  ctx->grp_on = n > 0;
+  int rc = fle_eval_sum_product_dev(ctx, cols, ncols, nodes, nnodes, first_row, n, plain_i64_dev, code_col, dict_i64_dev,
+                                    ndict, bitmap_dev, total_sum_dev, total_count_dev);
+  const bool was_on = ctx->grp_on;
+  ctx->grp_on = false;
+  if (rc != FLE_OK) return rc;
+  // one launch with the group attached = the fused kernel did the exchange; the two-kernel fallback
+  // (predicate kernel with no count slot, then the aggregate kernel) did not
+  if (was_on && ctx->launches == launches0 + 1) return FLE_OK;
+  return launch_group_reduce(ctx, total_count_dev, reinterpret_cast<uint64_t*>(total_sum_dev));
 }
 
 // ---- page framing / PLAIN columns ------------------------------------------------------------

@@ -837,6 +837,7 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
   P.ticket = ctx->d_ticket;
   P.tile_counter = ctx->d_ticket + 1;
   P.in_lits = ctx->d_in_lits;
+  group_fill(ctx, &P);
   void* args[] = {(void*)&P, jit_args};
   cudaError_t e = cudaLaunchKernel(kern, dim3(grid), dim3(nt), args, smem_bytes, ctx->stream);
   if (e != cudaSuccess) {

@@ -15,9 +15,75 @@ __device__ __forceinline__ uint64_t finish_word(uint64_t planes_order, int64_t g
   return r;
 }
 
+// ------------------------------------------------------------------------------------------
+// Cross-GPU sum of the two totals, run by the first warp of the LAST CTA of a launch (the one that
+// owns the totals) -- the all-reduce the scan ends with, fused into the scan kernel:
+// lane r posts {a, b} into entry [seq % kGroupSlots][my rank] of rank r's mailbox with peer stores
+// (NVLink / NVSwitch; data, system-wide fence, then the sequence number as the release flag), then
+// waits for rank r's entry of the same sequence number in its OWN mailbox and the warp sums the
+// entries.  A rank posts launch seq+1 only after it has read every entry of launch seq (stream
+// order), and launch seq+2 only after every peer has posted seq+1, i.e. after every peer is done
+// reading seq: two slots would do, kGroupSlots = 4.  A peer that does not show up within
+// grp_timeout_ns is counted in grp_state[1] (the host checks it) and its entry taken as 0.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t group_ld_acquire(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void group_st_release(uint64_t* p, uint64_t v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t group_now_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ void group_allreduce_warp(uint64_t* const* mail, unsigned long long* state, int world,
+                                                     int rank, uint64_t timeout_ns, uint64_t& a, uint64_t& b) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t seq = *((volatile unsigned long long*)state) + 1ull;
+  const uint32_t slot = (uint32_t)(seq % (uint64_t)kGroupSlots);
+  uint64_t va = 0, vb = 0;
+  bool lost = false;
+  if (lane < world) {
+    uint64_t* dst = mail[lane] + ((size_t)slot * FLE_MAX_GROUP + rank) * kGroupEntryWords;
+    *((volatile uint64_t*)(dst + 1)) = a;
+    *((volatile uint64_t*)(dst + 2)) = b;
+    __threadfence_system();
+    group_st_release(dst, seq);
+    const uint64_t* src = mail[rank] + ((size_t)slot * FLE_MAX_GROUP + lane) * kGroupEntryWords;
+    const uint64_t t0 = group_now_ns();
+    while (group_ld_acquire(src) != seq) {
+      if (group_now_ns() - t0 > timeout_ns) {
+        lost = true;
+        break;
+      }
+    }
+    if (!lost) {
+      va = *((const volatile uint64_t*)(src + 1));
+      vb = *((const volatile uint64_t*)(src + 2));
+    }
+  }
+  const unsigned nlost = __popc(__ballot_sync(0xffffffffu, lost));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    va += __shfl_xor_sync(0xffffffffu, va, o);
+    vb += __shfl_xor_sync(0xffffffffu, vb, o);
+  }
+  a = va;
+  b = vb;
+  if (lane == 0) {
+    state[0] = seq;
+    if (nlost) state[1] += nlost;
+  }
+}
+
 // block-wide reduction of the popcounts (and, for fused aggregates, of a second 64-bit sum kept in
 // partial[gridDim.x ...]) + "last block sums", so the launch needs no memset/atomics on the
-// result slots.
+// result slots.  With a group attached (P.grp_world > 1) the last block also sums the totals over
+// the GPUs of the group before writing them.
 template <int NT, bool WITH_SUM>
 __device__ __forceinline__ void publish_totals(const EvalParams& P, uint64_t cnt, uint64_t sum) {
   __shared__ uint64_t warp_cnt[NT / 32];
@@ -65,17 +131,21 @@ __device__ __forceinline__ void publish_totals(const EvalParams& P, uint64_t cnt
       if (WITH_SUM) warp_sum[threadIdx.x >> 5] = u;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
       uint64_t tot = 0, tot2 = 0;
 #pragma unroll
       for (int w = 0; w < NT / 32; ++w) {
         tot += warp_cnt[w];
         if (WITH_SUM) tot2 += warp_sum[w];
       }
-      if (P.count_out) *P.count_out = tot;
-      if (WITH_SUM && P.agg_sum_out) *P.agg_sum_out = (int64_t)tot2;
-      *P.ticket = 0;  // self-reset for the next launch on this stream
-      if (P.tile_counter) *P.tile_counter = 0;
+      if (P.grp_world > 1)
+        group_allreduce_warp(P.grp_mail, P.grp_state, P.grp_world, P.grp_rank, P.grp_timeout_ns, tot, tot2);
+      if (threadIdx.x == 0) {
+        if (P.count_out) *P.count_out = tot;
+        if (WITH_SUM && P.agg_sum_out) *P.agg_sum_out = (int64_t)tot2;
+        *P.ticket = 0;  // self-reset for the next launch on this stream
+        if (P.tile_counter) *P.tile_counter = 0;
+      }
     }
   }
 }

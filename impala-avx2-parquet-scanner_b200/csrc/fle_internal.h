@@ -86,6 +86,15 @@ struct fle_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copy[2] = {nullptr, nullptr};
   cudaEvent_t ev_done[2] = {nullptr, nullptr};
+
+  // group of GPUs whose totals are summed inside the kernels (fle_group.cu)
+  int grp_world = 0, grp_rank = 0;
+  bool grp_on = false;                  // set for the duration of a fle_*_group_dev call
+  bool grp_ipc = false;                 // peers' mailboxes were opened from IPC handles
+  uint64_t* d_grp_mail = nullptr;       // own mailbox (cudaMalloc: exportable)
+  unsigned long long* d_grp_state = nullptr;
+  uint64_t* grp_peer_mail[FLE_MAX_GROUP] = {nullptr};
+  int64_t grp_timeout_ms = 10000;
 };
 
 namespace fle {
@@ -93,6 +102,12 @@ namespace fle {
 int set_cuda_error(fle_ctx* ctx, cudaError_t e, const char* what);
 int set_error(fle_ctx* ctx, int code, const std::string& msg);
 int ensure_scratch(fle_ctx* ctx, int nblocks, int n_in_lits);
+// fle_group.cu: fills the group fields of a kernel parameter block when a group call is in progress
+void group_fill(const fle_ctx* ctx, EvalParams* P);
+// sums {*a_dev, *b_dev (optional)} over the group in place with a one-warp kernel (paths that end in a
+// kernel without the fused exchange)
+int launch_group_reduce(fle_ctx* ctx, uint64_t* a_dev, uint64_t* b_dev);
+void group_release(fle_ctx* ctx);
 
 #define FLE_CUDA_TRY(ctx, expr)                                   \
   do {                                                            \

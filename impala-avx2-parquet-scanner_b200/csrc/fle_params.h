@@ -20,6 +20,9 @@ typedef long long int64_t;
 #ifndef FLE_MAX_COLS
 #define FLE_MAX_COLS 8 /* == include/fle_b200.h */
 #endif
+#ifndef FLE_MAX_GROUP
+#define FLE_MAX_GROUP 8 /* == include/fle_b200.h: GPUs of one box */
+#endif
 
 namespace fle {
 
@@ -47,6 +50,14 @@ enum PassType : uint8_t { PASS_LT = 0, PASS_EQ = 1, PASS_IN = 2, PASS_CONST = 3 
 enum FoldOp : uint8_t { FOLD_SET = 0, FOLD_AND = 1, FOLD_OR = 2 };
 
 constexpr int kMaxPasses = 40;
+// Cross-GPU reduction fused into the tail of an eval kernel (fle_group_*, fle_group.cu): every rank owns
+// a mailbox of kGroupSlots x FLE_MAX_GROUP entries of 4 x u64 {sequence flag, value 0, value 1, -};
+// launch number `seq` of a rank posts its totals into entry [seq % kGroupSlots][rank] of EVERY
+// rank's mailbox with peer stores over NVLink (release), then reads the entries of all ranks in
+// its own mailbox (acquire) and sums them.
+constexpr int kGroupSlots = 4;
+constexpr int kGroupEntryWords = 4;
+constexpr int kGroupMailWords = kGroupSlots * FLE_MAX_GROUP * kGroupEntryWords;
 constexpr int kMaxCombs = 64;
 constexpr int kMaxSlots = 32;
 
@@ -105,6 +116,12 @@ struct EvalParams {
   const int64_t* agg_plain;
   const int64_t* agg_dict;
   int64_t* agg_sum_out;
+  // optional: the totals (count, aggregate) are summed over the GPUs of a group before they are
+  // written (grp_world > 1); see kGroupSlots above
+  uint64_t* grp_mail[FLE_MAX_GROUP];  // mailbox of every rank, the own one included
+  unsigned long long* grp_state;      // [0] launches done (sequence number), [1] peers timed out so far
+  int32_t grp_world, grp_rank;
+  uint64_t grp_timeout_ns;
   PassDesc passes[kMaxPasses];
   CombDesc combs[kMaxCombs];
 };

@@ -63,6 +63,8 @@ enum {
 #define FLE_MAX_COLS 8      /* columns per fused evaluation */
 #define FLE_MAX_NODES 64    /* postfix nodes per fused evaluation */
 #define FLE_MAX_IN_CODES 4096
+#define FLE_MAX_GROUP 8     /* GPUs of one box whose totals one evaluation can sum */
+#define FLE_GROUP_HANDLE_BYTES 64
 
 /* One encoded column (chunk / page payload).  `planes` points at the first FLE group, i.e.
  * AFTER the 1-byte bit-width header DictDecoderBase::SetData strips (dict-encoding.h:185-192).
@@ -245,6 +247,41 @@ int fle_eval_sum_product_dev(fle_ctx* ctx, const fle_col_desc* cols_dev, int nco
                              const int64_t* plain_i64_dev, int code_col, const int64_t* dict_i64_dev,
                              int ndict, uint64_t* bitmap_out_dev, int64_t* sum_dev,
                              uint64_t* count_dev);
+
+/* ---- row groups partitioned across the GPUs of one box -------------------------- */
+/* The reference runs one HdfsParquetScanner per scanner thread over its own scan ranges
+ * (hdfs-parquet-scanner.cc:1040) and its row groups are independent (:1056-1060); here one
+ * context per GPU scans a contiguous range of row groups and the per-query totals (match count,
+ * one exact int64 partial aggregate) are summed over the GPUs INSIDE the scan kernel: its last
+ * thread block posts the GPU's totals into every peer's mailbox with peer stores over
+ * NVLink/NVSwitch and adds up the peers' entries -- no separate collective, no host in the loop.
+ * Every context of a group must issue the same sequence of fle_*_group_dev calls (like any
+ * collective); a peer that does not arrive within "group_timeout_ms" (context option, default
+ * 10000) is reported by fle_group_status and its contribution taken as 0.
+ *
+ * One process, several GPUs (or several contexts on one GPU): */
+int fle_group_create_local(fle_ctx* const* ctxs, int n);
+/* One process per GPU: every rank exports a 64-byte handle of its mailbox (CUDA IPC), the caller
+ * all-gathers the handles with its own transport (MPI, torch.distributed, a socket) and every rank
+ * opens the group with all of them (handles = world x FLE_GROUP_HANDLE_BYTES bytes, rank order). */
+int fle_group_export(fle_ctx* ctx, void* handle_out);
+int fle_group_open(fle_ctx* ctx, int rank, int world, const void* handles);
+int fle_group_close(fle_ctx* ctx);
+/* Synchronises the context's stream; any output may be NULL. */
+int fle_group_status(fle_ctx* ctx, int* rank, int* world, uint64_t* reductions_done, uint64_t* peers_timed_out);
+/* fle_eval_dev over this GPU's rows; *total_count_dev = matches of ALL GPUs of the group.
+ * The bitmap stays local (it covers this GPU's rows). */
+int fle_eval_group_dev(fle_ctx* ctx, const fle_col_desc* cols_dev, int ncols, const fle_pred_node* postfix,
+                       int nnodes, int64_t first_row, int64_t n, uint64_t* bitmap_out_dev,
+                       uint64_t* total_count_dev);
+/* fle_eval_sum_product_dev over this GPU's rows; *total_sum_dev / *total_count_dev = the exact
+ * int64 aggregate / match count over ALL GPUs of the group (TPC-H Q6 end to end in one kernel
+ * per GPU). */
+int fle_eval_sum_product_group_dev(fle_ctx* ctx, const fle_col_desc* cols_dev, int ncols,
+                                   const fle_pred_node* postfix, int nnodes, int64_t first_row, int64_t n,
+                                   const int64_t* plain_i64_dev, int code_col, const int64_t* dict_i64_dev,
+                                   int ndict, uint64_t* bitmap_out_dev, int64_t* total_sum_dev,
+                                   uint64_t* total_count_dev);
 
 /* ---- page framing and PLAIN-encoded columns ("next" rows) ------------- */
 /* Byte layout of one uncompressed data-page body (hdfs-parquet-table-writer.cc:567-575,
