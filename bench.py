@@ -126,7 +126,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
         return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(self.reasons), "samples": len(self.samples),
-                "sampled_over": "warm-up + timed steps of the headline loop (5 ms period)"}
+                "sampled_over": "warm-up + timed steps of the headline loop and of the Q6 loops (5 ms period)"}
 
 
 # --------------------------------------------------------------------------------------------
@@ -296,8 +296,11 @@ class Bench:
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if ok.item() > 0:
             self.group = True
+            self.ctx.set_option("group_deferred", 0 if self.args.reduce == "group-immediate" else 1)
             self.reduce_impl = ("in-kernel: last CTA of the scan posts {count, sum} to every peer's mailbox with peer "
-                                "stores over NVLink and sums the peers' entries (fle_eval_group_dev, CUDA-IPC mailboxes)")
+                                "stores over NVLink and sums the peers' entries (fle_eval_group_dev, CUDA-IPC mailboxes; "
+                                + ("collected inside the same kernel)" if self.args.reduce == "group-immediate" else
+                                   "collected by the next query's kernel, the last one by fle_group_flush inside the timed region)"))
         else:  # pragma: no cover
             try:
                 self.ctx.group_close()
@@ -352,11 +355,15 @@ class Bench:
         torch = self.torch
         for _ in range(warm):
             fn()
+        if self.group:
+            self.ctx.group_flush()
         self.barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(self.stream)
         for _ in range(steps):
             fn()
+        if self.group:
+            self.ctx.group_flush()  # deferred mode: the last query's totals are collected inside the timed region
         b.record(self.stream)
         self.barrier()
         return self.max_over_ranks(a.elapsed_time(b) / steps)[0]
@@ -416,7 +423,7 @@ class Bench:
             return t
 
         main_mode = "local" if world == 1 else ("group" if self.group else "nccl")
-        sampler = ClockSampler(self.local_rank)
+        sampler = self.sampler = ClockSampler(self.local_rank)
         sampler.start()
         # warm-up (+ correctness of every selectivity once, reductions included)
         nwarm = max(args.warmup, len(SELECTIVITIES))
@@ -425,6 +432,8 @@ class Bench:
         for w in pending:
             w.wait()
         pending.clear()
+        if main_mode == "group":
+            ctx.group_flush()
         torch.cuda.synchronize()
         assert torch.equal(count_ring[:nwarm], want_totals(nwarm)[:nwarm]), "warm-up counts differ from the torch compare"
 
@@ -440,6 +449,8 @@ class Bench:
             for w in pending:
                 w.wait()  # all reduced counts are complete before the clock stops
             pending.clear()
+            if mode == "group":
+                ctx.group_flush()  # ... in deferred mode too: the last query's totals are collected here
             t1.record(self.stream)
             self.barrier()
             return t0.elapsed_time(t1), [a.elapsed_time(b) for a, b in ev]
@@ -447,8 +458,6 @@ class Bench:
         launches0 = ctx.launch_count
         elapsed_ms, kern_ms = timed_loop(main_mode)
         launches = ctx.launch_count - launches0
-        sampler.stop()
-        self.clocks = sampler.summary()
         if world > 1:
             assert torch.equal(count_ring[:steps], want_totals(steps)), "reduced match counts differ from the torch compare"
             if self.group:
@@ -845,7 +854,7 @@ def main():
     ap.add_argument("--no-cfg4", action="store_true")
     ap.add_argument("--no-sub", action="store_true", help="skip the codec / in_lists / scanner sub-records")
     ap.add_argument("--no-nccl-compare", action="store_true")
-    ap.add_argument("--reduce", default="group", choices=["group", "nccl"], help="N > 1: how per-step totals are summed")
+    ap.add_argument("--reduce", default="group", choices=["group", "group-immediate", "nccl"], help="N > 1: how per-step totals are summed")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -860,6 +869,8 @@ def main():
     G = (n + 63) // 64
     b.run_headline()
     b.run_q6()
+    b.sampler.stop()
+    b.clocks = b.sampler.summary()
     e2e = None
     if not args.no_e2e:
         b.run_e2e()

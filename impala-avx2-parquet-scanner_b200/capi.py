@@ -31,7 +31,7 @@ EXPORTS = [
     "fle_intersect_bitset_dev", "fle_bitmap_select_dev", "fle_gather_dev", "fle_sum_product_dev",
     "fle_page_parse", "fle_realign_dev", "fle_plain_eval_dev", "fle_dict_encode_dev", "fle_eval_codegen",
     "fle_eval_sum_product_dev", "fle_group_create_local", "fle_group_export", "fle_group_open", "fle_group_close",
-    "fle_group_status", "fle_eval_group_dev", "fle_eval_sum_product_group_dev",
+    "fle_group_status", "fle_group_flush", "fle_eval_group_dev", "fle_eval_sum_product_group_dev",
 ]
 GROUP_HANDLE_BYTES = 64
 
@@ -129,6 +129,7 @@ def load_library() -> C.CDLL:
     L.fle_group_export.argtypes = [vp, vp]
     L.fle_group_open.argtypes = [vp, i32, i32, vp]
     L.fle_group_close.argtypes = [vp]
+    L.fle_group_flush.argtypes = [vp]
     L.fle_group_status.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), u64p, u64p]
     L.fle_eval_group_dev.argtypes = L.fle_eval_dev.argtypes
     L.fle_eval_sum_product_group_dev.argtypes = L.fle_eval_sum_product_dev.argtypes
@@ -396,6 +397,10 @@ class FleContext:
         blob = b"".join(handles)
         assert len(blob) == world * GROUP_HANDLE_BYTES
         self._check(self.lib.fle_group_open(self.h, rank, world, blob))
+
+    def group_flush(self):
+        """Deferred mode: enqueue the collection of the last group call's totals."""
+        self._check(self.lib.fle_group_flush(self.h))
 
     def group_close(self):
         self._check(self.lib.fle_group_close(self.h))

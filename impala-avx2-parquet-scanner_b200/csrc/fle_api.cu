@@ -415,6 +415,7 @@ int fle_ctx_set_option(fle_ctx* ctx, const char* name, int64_t value) {
   else if (k == "eval_jit_min_rows") ctx->eval_jit_min_rows = value;
   else if (k == "h2d_chunk_rows") ctx->h2d_chunk_rows = value;
   else if (k == "group_timeout_ms") ctx->grp_timeout_ms = value;
+  else if (k == "group_deferred") ctx->grp_deferred = value != 0;
   else return set_error(ctx, FLE_E_INVALID, "unknown option " + k);
   return FLE_OK;
 }
@@ -437,6 +438,7 @@ int64_t fle_ctx_get_option(fle_ctx* ctx, const char* name) {
   if (k == "eval_jit_min_rows") return ctx->eval_jit_min_rows;
   if (k == "h2d_chunk_rows") return ctx->h2d_chunk_rows;
   if (k == "group_timeout_ms") return ctx->grp_timeout_ms;
+  if (k == "group_deferred") return ctx->grp_deferred ? 1 : 0;
   if (k == "jit_launches") return ctx->jit_launches;
   if (k == "last_mode") return ctx->last_mode;
   if (k == "num_sms") return ctx->num_sms;

@@ -16,54 +16,77 @@ __device__ __forceinline__ uint64_t finish_word(uint64_t planes_order, int64_t g
 }
 
 // ------------------------------------------------------------------------------------------
-// Cross-GPU sum of the two totals, run by the first warp of the LAST CTA of a launch (the one that
-// owns the totals) -- the all-reduce the scan ends with, fused into the scan kernel:
-// lane r posts {a, b} into entry [seq % kGroupSlots][my rank] of rank r's mailbox with peer stores
-// (NVLink / NVSwitch; data, system-wide fence, then the sequence number as the release flag), then
-// waits for rank r's entry of the same sequence number in its OWN mailbox and the warp sums the
-// entries.  A rank posts launch seq+1 only after it has read every entry of launch seq (stream
-// order), and launch seq+2 only after every peer has posted seq+1, i.e. after every peer is done
-// reading seq: two slots would do, kGroupSlots = 4.  A peer that does not show up within
-// grp_timeout_ns is counted in grp_state[1] (the host checks it) and its entry taken as 0.
+// Cross-GPU sum of the two totals, run by the LAST CTA of a launch (the one that owns the totals) --
+// the all-reduce the scan ends with, fused into the scan kernel.
+//   post(seq):    lane r writes the entry [seq % kGroupSlots][my rank] of rank r's mailbox with peer stores
+//                 (NVLink / NVSwitch).  An entry is four 64-bit words {seq:32 | a.lo, seq:32 | a.hi,
+//                 seq:32 | b.lo, seq:32 | b.hi}: every word carries its own sequence tag and 64-bit stores
+//                 are single-copy atomic, so the words need no ordering among themselves -- no fence, no
+//                 separate flag, the stores are fire-and-forget;
+//   collect(seq): lane r polls rank r's entry in the OWN mailbox until all four tags read seq; the warp sums.
+// Immediate mode: post(seq), collect(seq), write the totals -- results are ordered on the stream like any
+// kernel output, at the price of one NVLink round trip and of running the GPUs in lockstep.
+// Deferred mode (context option "group_deferred"): post(seq) only; the NEXT exchange of the context (or
+// fle_group_flush) collects seq -- a second warp does it while the first one posts, and by then the peers'
+// entries have long arrived -- and writes the totals where call seq wanted them.  The exchange then adds
+// no dependent memory round trip to the kernel's tail and the GPUs may drift apart by one query.
+// Sequence numbers and the pending call's pointers are kept by the HOST (every member issues the same
+// sequence of group calls) and travel as kernel parameters: the tail reads no device-side state.
+// Slot reuse: a rank posts seq only after its previous launch has collected seq-2 (deferred) or seq-1
+// (immediate) from every peer, and a peer posts its seq-1 only after its launch seq-2 is complete, i.e.
+// after it has consumed everything up to seq-3: entries seq-3 .. seq can be live, kGroupSlots = 8 > 4.
+// A peer that does not show up within grp_timeout_ns is counted in *grp_lost (the host checks it) and its
+// entry taken as 0.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t group_ld_acquire(const uint64_t* p) {
-  uint64_t v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void group_st_release(uint64_t* p, uint64_t v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
+struct GroupView {
+  uint64_t* const* mail;
+  unsigned long long* lost;
+  int world, rank;
+  uint64_t timeout_ns;
+};
+
 __device__ __forceinline__ uint64_t group_now_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
 
-__device__ __forceinline__ void group_allreduce_warp(uint64_t* const* mail, unsigned long long* state, int world,
-                                                     int rank, uint64_t timeout_ns, uint64_t& a, uint64_t& b) {
+__device__ __forceinline__ void group_post(const GroupView& g, uint32_t seq, uint64_t a, uint64_t b) {
   const int lane = threadIdx.x & 31;
-  const uint64_t seq = *((volatile unsigned long long*)state) + 1ull;
-  const uint32_t slot = (uint32_t)(seq % (uint64_t)kGroupSlots);
+  if (lane < g.world) {
+    uint64_t* dst = g.mail[lane] + ((size_t)(seq % (uint32_t)kGroupSlots) * FLE_MAX_GROUP + g.rank) * kGroupEntryWords;
+    const uint64_t tag = (uint64_t)seq << 32;
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(tag | (a & 0xffffffffull)), "l"(tag | (a >> 32))
+                 : "memory");
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst + 2), "l"(tag | (b & 0xffffffffull)), "l"(tag | (b >> 32))
+                 : "memory");
+  }
+}
+
+__device__ __forceinline__ void group_collect(const GroupView& g, uint32_t seq, uint64_t& a, uint64_t& b) {
+  const int lane = threadIdx.x & 31;
   uint64_t va = 0, vb = 0;
   bool lost = false;
-  if (lane < world) {
-    uint64_t* dst = mail[lane] + ((size_t)slot * FLE_MAX_GROUP + rank) * kGroupEntryWords;
-    *((volatile uint64_t*)(dst + 1)) = a;
-    *((volatile uint64_t*)(dst + 2)) = b;
-    __threadfence_system();
-    group_st_release(dst, seq);
-    const uint64_t* src = mail[rank] + ((size_t)slot * FLE_MAX_GROUP + lane) * kGroupEntryWords;
-    const uint64_t t0 = group_now_ns();
-    while (group_ld_acquire(src) != seq) {
-      if (group_now_ns() - t0 > timeout_ns) {
-        lost = true;
-        break;
+  if (lane < g.world) {
+    const uint64_t* src = g.mail[g.rank] + ((size_t)(seq % (uint32_t)kGroupSlots) * FLE_MAX_GROUP + lane) * kGroupEntryWords;
+    uint64_t w0, w1, w2, w3;
+    uint64_t t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
+      asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+      asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w2), "=l"(w3) : "l"(src + 2) : "memory");
+      if ((uint32_t)(w0 >> 32) == seq && (uint32_t)(w1 >> 32) == seq && (uint32_t)(w2 >> 32) == seq && (uint32_t)(w3 >> 32) == seq) break;
+      if ((spin & 63u) == 63u) {
+        const uint64_t now = group_now_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > g.timeout_ns) {
+          lost = true;
+          break;
+        }
       }
     }
     if (!lost) {
-      va = *((const volatile uint64_t*)(src + 1));
-      vb = *((const volatile uint64_t*)(src + 2));
+      va = (w0 & 0xffffffffull) | (w1 << 32);
+      vb = (w2 & 0xffffffffull) | (w3 << 32);
     }
   }
   const unsigned nlost = __popc(__ballot_sync(0xffffffffu, lost));
@@ -74,9 +97,19 @@ __device__ __forceinline__ void group_allreduce_warp(uint64_t* const* mail, unsi
   }
   a = va;
   b = vb;
-  if (lane == 0) {
-    state[0] = seq;
-    if (nlost) state[1] += nlost;
+  if (lane == 0 && nlost) atomicAdd(g.lost, (unsigned long long)nlost);
+}
+
+// collects what an earlier deferred exchange left pending and writes it where that call wanted it
+// (warp-collective)
+__device__ __forceinline__ void group_collect_pending(const GroupView& g, uint32_t pend_seq, uint64_t* pend_count,
+                                                      uint64_t* pend_sum) {
+  if (pend_seq == 0) return;
+  uint64_t pa, pb;
+  group_collect(g, pend_seq, pa, pb);
+  if ((threadIdx.x & 31) == 0) {
+    if (pend_count) *pend_count = pa;
+    if (pend_sum) *pend_sum = pb;
   }
 }
 
@@ -131,6 +164,8 @@ __device__ __forceinline__ void publish_totals(const EvalParams& P, uint64_t cnt
       if (WITH_SUM) warp_sum[threadIdx.x >> 5] = u;
     }
     __syncthreads();
+    const bool grp = P.grp_world > 1;
+    const GroupView gv{P.grp_mail, P.grp_lost, P.grp_world, P.grp_rank, P.grp_timeout_ns};
     if (threadIdx.x < 32) {
       uint64_t tot = 0, tot2 = 0;
 #pragma unroll
@@ -138,14 +173,21 @@ __device__ __forceinline__ void publish_totals(const EvalParams& P, uint64_t cnt
         tot += warp_cnt[w];
         if (WITH_SUM) tot2 += warp_sum[w];
       }
-      if (P.grp_world > 1)
-        group_allreduce_warp(P.grp_mail, P.grp_state, P.grp_world, P.grp_rank, P.grp_timeout_ns, tot, tot2);
+      bool write_now = true;
+      if (grp) {
+        group_post(gv, P.grp_seq, tot, tot2);
+        if (P.grp_deferred) write_now = false;
+        else group_collect(gv, P.grp_seq, tot, tot2);
+      }
       if (threadIdx.x == 0) {
-        if (P.count_out) *P.count_out = tot;
-        if (WITH_SUM && P.agg_sum_out) *P.agg_sum_out = (int64_t)tot2;
+        if (write_now && P.count_out) *P.count_out = tot;
+        if (write_now && WITH_SUM && P.agg_sum_out) *P.agg_sum_out = (int64_t)tot2;
         *P.ticket = 0;  // self-reset for the next launch on this stream
         if (P.tile_counter) *P.tile_counter = 0;
       }
+    } else if (threadIdx.x < 64 && grp) {
+      // the totals an earlier deferred call left pending, while the first warp posts
+      group_collect_pending(gv, P.grp_pend_seq, P.grp_pend_count, P.grp_pend_sum);
     }
   }
 }

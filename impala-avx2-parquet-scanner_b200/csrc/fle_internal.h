@@ -90,9 +90,14 @@ struct fle_ctx {
   // group of GPUs whose totals are summed inside the kernels (fle_group.cu)
   int grp_world = 0, grp_rank = 0;
   bool grp_on = false;                  // set for the duration of a fle_*_group_dev call
+  bool grp_deferred = false;            // option "group_deferred"
   bool grp_ipc = false;                 // peers' mailboxes were opened from IPC handles
   uint64_t* d_grp_mail = nullptr;       // own mailbox (cudaMalloc: exportable)
-  unsigned long long* d_grp_state = nullptr;
+  unsigned long long* d_grp_state = nullptr;  // [0] peers lost to time-outs
+  uint32_t grp_seq = 0;                 // exchanges issued (host-side: every member issues the same sequence)
+  uint32_t grp_pend_seq = 0;            // deferred exchange not collected yet (0: none) and where its totals go
+  uint64_t* grp_pend_count = nullptr;
+  uint64_t* grp_pend_sum = nullptr;
   uint64_t* grp_peer_mail[FLE_MAX_GROUP] = {nullptr};
   int64_t grp_timeout_ms = 10000;
 };
@@ -103,7 +108,7 @@ int set_cuda_error(fle_ctx* ctx, cudaError_t e, const char* what);
 int set_error(fle_ctx* ctx, int code, const std::string& msg);
 int ensure_scratch(fle_ctx* ctx, int nblocks, int n_in_lits);
 // fle_group.cu: fills the group fields of a kernel parameter block when a group call is in progress
-void group_fill(const fle_ctx* ctx, EvalParams* P);
+void group_fill(fle_ctx* ctx, EvalParams* P);
 // sums {*a_dev, *b_dev (optional)} over the group in place with a one-warp kernel (paths that end in a
 // kernel without the fused exchange)
 int launch_group_reduce(fle_ctx* ctx, uint64_t* a_dev, uint64_t* b_dev);

@@ -52,10 +52,10 @@ enum FoldOp : uint8_t { FOLD_SET = 0, FOLD_AND = 1, FOLD_OR = 2 };
 constexpr int kMaxPasses = 40;
 // Cross-GPU reduction fused into the tail of an eval kernel (fle_group_*, fle_group.cu): every rank owns
 // a mailbox of kGroupSlots x FLE_MAX_GROUP entries of 4 x u64 {sequence flag, value 0, value 1, -};
-// launch number `seq` of a rank posts its totals into entry [seq % kGroupSlots][rank] of EVERY
-// rank's mailbox with peer stores over NVLink (release), then reads the entries of all ranks in
-// its own mailbox (acquire) and sums them.
-constexpr int kGroupSlots = 4;
+// exchange number `seq` of a rank posts its totals into entry [seq % kGroupSlots][rank] of EVERY
+// rank's mailbox with peer stores over NVLink (release) and reads the entries of all ranks in
+// its own mailbox (acquire) -- protocol in fle_eval_common.cuh.
+constexpr int kGroupSlots = 8;
 constexpr int kGroupEntryWords = 4;
 constexpr int kGroupMailWords = kGroupSlots * FLE_MAX_GROUP * kGroupEntryWords;
 constexpr int kMaxCombs = 64;
@@ -119,8 +119,13 @@ struct EvalParams {
   // optional: the totals (count, aggregate) are summed over the GPUs of a group before they are
   // written (grp_world > 1); see kGroupSlots above
   uint64_t* grp_mail[FLE_MAX_GROUP];  // mailbox of every rank, the own one included
-  unsigned long long* grp_state;      // [0] launches done (sequence number), [1] peers timed out so far
+  unsigned long long* grp_lost;       // peers that timed out so far
   int32_t grp_world, grp_rank;
+  int32_t grp_deferred;
+  uint32_t grp_seq;                   // this exchange's sequence number (host-side counter, never 0)
+  uint32_t grp_pend_seq, grp_pad;     // deferred exchange to collect first (0: none) and where its totals go
+  uint64_t* grp_pend_count;
+  uint64_t* grp_pend_sum;
   uint64_t grp_timeout_ns;
   PassDesc passes[kMaxPasses];
   CombDesc combs[kMaxCombs];

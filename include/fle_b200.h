@@ -267,6 +267,13 @@ int fle_group_create_local(fle_ctx* const* ctxs, int n);
 int fle_group_export(fle_ctx* ctx, void* handle_out);
 int fle_group_open(fle_ctx* ctx, int rank, int world, const void* handles);
 int fle_group_close(fle_ctx* ctx);
+/* Context option "group_deferred" (default 0).  0: a group call's totals are in place when its kernel
+ * ends (one NVLink round trip inside the kernel; the GPUs of the group run in lockstep).  1: the
+ * kernel posts its totals and returns; they are collected -- and written to the pointers the call was
+ * given -- by the context's NEXT group call or by fle_group_flush (enqueues a one-warp kernel), so a
+ * stream of queries pays nothing for the exchange and the GPUs may drift apart by one query.  Read
+ * the totals of call k only after call k+1 or fle_group_flush has been enqueued on the stream. */
+int fle_group_flush(fle_ctx* ctx);
 /* Synchronises the context's stream; any output may be NULL. */
 int fle_group_status(fle_ctx* ctx, int* rank, int* world, uint64_t* reductions_done, uint64_t* peers_timed_out);
 /* fle_eval_dev over this GPU's rows; *total_count_dev = matches of ALL GPUs of the group.

@@ -36,8 +36,9 @@ def _close(ctxs):
         c.close()
 
 
+@pytest.mark.parametrize("deferred", [0, 1])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_cfg4_q6_partitioned_reduced_scale(oracle, world):
+def test_cfg4_q6_partitioned_reduced_scale(oracle, world, deferred):
     """cfg4 at reduced scale: rows cut into row groups, contiguous row-group ranges per member
     (partition.rank_rows), fused Q6 + exact int64 revenue, totals identical on every member and equal to
     the oracle's evaluation of the whole table -- for any member count."""
@@ -53,6 +54,8 @@ def test_cfg4_q6_partitioned_reduced_scale(oracle, world):
     want_rev = int((price[sel] * vals[1][sel].astype(np.int64)).sum())
 
     streams, ctxs = _members(world)
+    for c in ctxs:
+        c.set_option("group_deferred", deferred)
     ddict = torch.arange(0, 11, dtype=torch.int64, device="cuda")
     shards, outs, bms = [], [], []
     for r in range(world):
@@ -68,20 +71,29 @@ def test_cfg4_q6_partitioned_reduced_scale(oracle, world):
         ctxs[0].set_option("eval_jit", jit)
         ctxs[0].eval_sum_product_dev(shards[0][2], Q6, shards[0][1], shards[0][3], 1, ddict)
     torch.cuda.synchronize()
-    for it in range(3):  # several queries back to back: the mailbox slots are reused
+    all_outs = []
+    for it in range(12):  # queries back to back, more than there are mailbox slots; deferred: no sync in between
         outs, bms = [], []
         for r, (first, n, dcols, dprice) in enumerate(shards):
-            ctxs[r].set_option("eval_jit", 2 if it < 2 else 0)  # fused single kernel, then the two-kernel fallback + reduce kernel
+            ctxs[r].set_option("eval_jit", 2 if it % 3 < 2 else 0)  # fused single kernel / the two-kernel fallback + reduce kernel
             with torch.cuda.stream(streams[r]):
                 bm = torch.zeros(max(1, (n + 63) // 64), dtype=torch.int64, device="cuda")
                 out = ctxs[r].eval_sum_product_group_dev(dcols, Q6, n, dprice, 1, ddict, bitmap=bm)
             outs.append(out)
             bms.append(bm)
-        torch.cuda.synchronize()
-        for r, (first, n, _, _) in enumerate(shards):
+        all_outs.append(outs)
+        if not deferred or it == 11:
+            if deferred:
+                for r in range(world):
+                    with torch.cuda.stream(streams[r]):
+                        ctxs[r].group_flush()
+            torch.cuda.synchronize()
+            for r, (first, n, _, _) in enumerate(shards):
+                got = bms[r].cpu().numpy().view(np.uint64)[: (n + 63) // 64]
+                assert (got == want_bm[first // 64: first // 64 + len(got)]).all(), "local bitmap differs from the oracle's slice"
+    for it, outs in enumerate(all_outs):
+        for r in range(world):
             assert int(outs[r][0].item()) == want_rev and int(outs[r][1].item()) == want_cnt, (world, it, r)
-            got = bms[r].cpu().numpy().view(np.uint64)[: (n + 63) // 64]
-            assert (got == want_bm[first // 64: first // 64 + len(got)]).all(), "local bitmap differs from the oracle's slice"
     _close(ctxs)
 
 
