@@ -31,7 +31,8 @@ EXPORTS = [
     "fle_intersect_bitset_dev", "fle_bitmap_select_dev", "fle_gather_dev", "fle_sum_product_dev",
     "fle_page_parse", "fle_realign_dev", "fle_plain_eval_dev", "fle_dict_encode_dev", "fle_eval_codegen",
     "fle_eval_sum_product_dev", "fle_group_create_local", "fle_group_export", "fle_group_open", "fle_group_close",
-    "fle_group_status", "fle_group_flush", "fle_eval_group_dev", "fle_eval_sum_product_group_dev",
+    "fle_h2d_prefetch", "fle_prefetch_fence", "fle_host_register", "fle_host_unregister", "fle_pages_gather_dev",
+    "fle_assemble_rows_dev", "fle_group_status", "fle_group_flush", "fle_eval_group_dev", "fle_eval_sum_product_group_dev",
 ]
 GROUP_HANDLE_BYTES = 64
 
@@ -62,6 +63,17 @@ def group_create_local(ctxs: Sequence["FleContext"]):
     rc = lib.fle_group_create_local(arr, len(ctxs))
     if rc != OK:
         raise FleError(rc, lib.fle_strerror(rc).decode())
+
+
+class PageRef(C.Structure):
+    _fields_ = [("src_dev", C.c_void_p), ("src_bytes", C.c_uint64), ("src_bit_width", C.c_int32), ("dst_bit_width", C.c_int32),
+                ("dst_dev", C.c_void_p), ("groups", C.c_int64), ("def_src_dev", C.c_void_p), ("def_bytes", C.c_uint64),
+                ("rows", C.c_int64)]
+
+
+class SlotDesc(C.Structure):
+    _fields_ = [("planes_dev", C.c_void_p), ("bytes", C.c_uint64), ("bit_width", C.c_int32), ("slot_size", C.c_int32),
+                ("dict_dev", C.c_void_p), ("ndict", C.c_int32), ("tuple_offset", C.c_int32)]
 
 
 class PredNode(C.Structure):
@@ -125,6 +137,12 @@ def load_library() -> C.CDLL:
                                            vp, vp, vp]
     L.fle_eval_codegen.argtypes = [C.POINTER(ColDesc), i32, C.POINTER(PredNode), i32, i32, C.c_char_p, C.c_size_t,
                                    C.POINTER(C.c_size_t)]
+    L.fle_h2d_prefetch.argtypes = [vp, vp, vp, C.c_size_t]
+    L.fle_prefetch_fence.argtypes = [vp]
+    L.fle_host_register.argtypes = [vp, C.c_size_t]
+    L.fle_host_unregister.argtypes = [vp]
+    L.fle_pages_gather_dev.argtypes = [vp, C.POINTER(PageRef), i32, vp]
+    L.fle_assemble_rows_dev.argtypes = [vp, vp, i64, C.POINTER(SlotDesc), i32, i32, vp, i64, vp, vp]
     L.fle_group_create_local.argtypes = [C.POINTER(vp), i32]
     L.fle_group_export.argtypes = [vp, vp]
     L.fle_group_open.argtypes = [vp, i32, i32, vp]
@@ -439,6 +457,32 @@ class FleContext:
             self.h, descs, len(cols), nodes, len(nodes), first_row, n, plain_i64.data_ptr(), code_col, dict_i64.data_ptr(),
             dict_i64.numel(), bitmap.data_ptr() if bitmap is not None else None, out.data_ptr(), out.data_ptr() + 8))
         return out
+
+    # -- row-group batches ---------------------------------------------------------------------
+    def pages_gather_dev(self, refs: Sequence[dict], null_rows=None):
+        """refs: dicts with the fields of fle_page_ref (device addresses as ints)."""
+        import torch
+        arr = (PageRef * len(refs))()
+        for i, r in enumerate(refs):
+            for k, v in r.items():
+                setattr(arr[i], k, v)
+        if null_rows is None:
+            null_rows = torch.zeros(1, dtype=torch.int64, device="cuda")
+        self._check(self.lib.fle_pages_gather_dev(self.h, arr, len(refs), null_rows.data_ptr()))
+        return null_rows
+
+    def assemble_rows_dev(self, bitmap, nrows: int, slots: Sequence[dict], tuple_size: int, cap_rows: int):
+        """slots: dicts with the fields of fle_slot_desc.  Returns (tuples uint8 [cap_rows, tuple_size], count, bad_codes)."""
+        import torch
+        arr = (SlotDesc * len(slots))()
+        for i, r in enumerate(slots):
+            for k, v in r.items():
+                setattr(arr[i], k, v)
+        tuples = torch.empty((max(1, cap_rows), tuple_size), dtype=torch.uint8, device=bitmap.device)
+        out = torch.zeros(2, dtype=torch.int64, device=bitmap.device)
+        self._check(self.lib.fle_assemble_rows_dev(self.h, bitmap.data_ptr(), nrows, arr, len(slots), tuple_size,
+                                                   tuples.data_ptr(), cap_rows, out.data_ptr(), out.data_ptr() + 8))
+        return tuples, out[0:1], out[1:2]
 
     def page_parse(self, page: np.ndarray, max_def_level: int) -> PageLayout:
         page = np.ascontiguousarray(page, dtype=np.uint8)

@@ -47,20 +47,46 @@ int ensure_scratch(fle_ctx* ctx, int nblocks, int n_in_lits) {
     ctx->d_partial = p;
     ctx->partial_cap = cap;
   }
-  if (n_in_lits > ctx->in_lits_cap) {
-    const int cap = std::max(n_in_lits, 4096);
-    uint32_t *d = nullptr, *h = nullptr;
-    FLE_CUDA_TRY(ctx, cudaMalloc(&d, (size_t)cap * 4));
-    FLE_CUDA_TRY(ctx, cudaMallocHost(&h, (size_t)cap * 4));
-    if (ctx->d_in_lits) {
-      FLE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-      cudaFree(ctx->d_in_lits);
-      cudaFreeHost(ctx->h_in_lits);
-    }
-    ctx->d_in_lits = d;
-    ctx->h_in_lits = h;
-    ctx->in_lits_cap = cap;
+  (void)n_in_lits;
+  return FLE_OK;
+}
+
+int upload_literals(fle_ctx* ctx, const void* words, int nwords, int* slot, uint64_t* gen, const uint32_t** dev) {
+  const int si = ctx->lit_next;
+  ctx->lit_next = (ctx->lit_next + 1) % fle_ctx::kLitSlots;
+  fle_ctx::LitSlot& S = ctx->lit_slots[si];
+  if (S.ev_pending) {  // the ring wrapped around: this slot's previous copy must have read the pinned side
+    FLE_CUDA_TRY(ctx, cudaEventSynchronize(S.ev));
+    S.ev_pending = false;
   }
+  if (nwords > S.cap) {
+    const int cap = std::max(nwords, 4096);
+    if (S.d) {
+      // the device side may still be read by kernels in flight: free it in stream order
+      FLE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      cudaFree(S.d);
+      cudaFreeHost(S.h);
+      S.d = nullptr;
+      S.h = nullptr;
+      S.cap = 0;
+    }
+    FLE_CUDA_TRY(ctx, cudaMalloc(&S.d, (size_t)cap * 4));
+    FLE_CUDA_TRY(ctx, cudaMallocHost(&S.h, (size_t)cap * 4));
+    S.cap = cap;
+  }
+  if (!S.ev) FLE_CUDA_TRY(ctx, cudaEventCreateWithFlags(&S.ev, cudaEventDisableTiming));
+  std::memcpy(S.h, words, (size_t)nwords * 4);
+  FLE_CUDA_TRY(ctx, cudaMemcpyAsync(S.d, S.h, (size_t)nwords * 4, cudaMemcpyHostToDevice, ctx->stream));
+  cudaStreamCaptureStatus cap_st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(ctx->stream, &cap_st) != cudaSuccess) cudaGetLastError();
+  if (cap_st == cudaStreamCaptureStatusNone) {  // (an event recorded during capture cannot be waited for by the host)
+    FLE_CUDA_TRY(ctx, cudaEventRecord(S.ev, ctx->stream));
+    S.ev_pending = true;
+  }
+  S.gen = ++ctx->lit_gen_counter;
+  if (slot) *slot = si;
+  if (gen) *gen = S.gen;
+  if (dev) *dev = S.d;
   return FLE_OK;
 }
 
@@ -364,10 +390,15 @@ int fle_ctx_destroy(fle_ctx* ctx) {
   }
   if (ctx->d_partial) cudaFree(ctx->d_partial);
   if (ctx->d_ticket) cudaFree(ctx->d_ticket);
-  if (ctx->d_in_lits) cudaFree(ctx->d_in_lits);
-  if (ctx->h_in_lits) cudaFreeHost(ctx->h_in_lits);
+  for (auto& S : ctx->lit_slots) {
+    if (S.d) cudaFree(S.d);
+    if (S.h) cudaFreeHost(S.h);
+    if (S.ev) cudaEventDestroy(S.ev);
+  }
   if (ctx->d_count) cudaFree(ctx->d_count);
   if (ctx->d_split) cudaFree(ctx->d_split);
+  if (ctx->d_tile_state) cudaFree(ctx->d_tile_state);
+  if (ctx->ev_prefetch) cudaEventDestroy(ctx->ev_prefetch);
   fle::group_release(ctx);
   if (ctx->h_count) cudaFreeHost(ctx->h_count);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -414,6 +445,7 @@ int fle_ctx_set_option(fle_ctx* ctx, const char* name, int64_t value) {
   else if (k == "eval_jit") ctx->eval_jit = (int)value;
   else if (k == "eval_jit_min_rows") ctx->eval_jit_min_rows = value;
   else if (k == "h2d_chunk_rows") ctx->h2d_chunk_rows = value;
+  else if (k == "reference_compat") ctx->reference_compat = value != 0;
   else if (k == "group_timeout_ms") ctx->grp_timeout_ms = value;
   else if (k == "group_deferred") ctx->grp_deferred = value != 0;
   else return set_error(ctx, FLE_E_INVALID, "unknown option " + k);
@@ -437,6 +469,7 @@ int64_t fle_ctx_get_option(fle_ctx* ctx, const char* name) {
   if (k == "eval_jit") return ctx->eval_jit;
   if (k == "eval_jit_min_rows") return ctx->eval_jit_min_rows;
   if (k == "h2d_chunk_rows") return ctx->h2d_chunk_rows;
+  if (k == "reference_compat") return ctx->reference_compat ? 1 : 0;
   if (k == "group_timeout_ms") return ctx->grp_timeout_ms;
   if (k == "group_deferred") return ctx->grp_deferred ? 1 : 0;
   if (k == "jit_launches") return ctx->jit_launches;
@@ -637,7 +670,7 @@ int fle_eval(fle_ctx* ctx, const fle_col_desc* cols, int ncols, const fle_pred_n
   if (n == 0) {
     LoweredProgram lp;
     std::string err;
-    int rc0 = lower_program(cols, ncols, nodes, nnodes, &lp, &err);  // still validate the program
+    int rc0 = lower_program(cols, ncols, nodes, nnodes, &lp, &err, ctx->reference_compat);  // still validate the program
     return rc0 == FLE_OK ? FLE_OK : set_error(ctx, rc0, err);
   }
   const int64_t G = (n + 63) / 64, g0 = first_row / 64;
@@ -843,6 +876,53 @@ int fle_eval_sum_product_dev(fle_ctx* ctx, const fle_col_desc* cols, int ncols, 
   const uint8_t* planes = reinterpret_cast<const uint8_t*>(cols[code_col].planes) + (uint64_t)(first_row / 64) * bw * 8u;
   return launch_sum_product(ctx, bitmap_dev, n, plain_i64_dev, reinterpret_cast<const uint64_t*>(planes), bw,
                             dict_i64_dev, ndict, sum_dev, count_dev);
+}
+
+// ---- row-group batches ---------------------------------------------------------------------------
+int fle_h2d_prefetch(fle_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+  FLE_CHECK_CTX(ctx);
+  if (bytes == 0) return FLE_OK;
+  if (!dst_dev || !src_host) return set_error(ctx, FLE_E_INVALID, "null pointer");
+  FLE_CUDA_TRY(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+  return FLE_OK;
+}
+
+int fle_prefetch_fence(fle_ctx* ctx) {
+  FLE_CHECK_CTX(ctx);
+  if (!ctx->ev_prefetch) FLE_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_prefetch, cudaEventDisableTiming));
+  FLE_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_prefetch, ctx->copy_stream));
+  FLE_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_prefetch, 0));
+  return FLE_OK;
+}
+
+int fle_host_register(void* p, size_t bytes) {
+  if (!p || bytes == 0) return FLE_E_INVALID;
+  cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? FLE_E_NOMEM : FLE_E_CUDA;
+  }
+  return FLE_OK;
+}
+
+int fle_host_unregister(void* p) {
+  if (p && cudaHostUnregister(p) != cudaSuccess) {
+    cudaGetLastError();
+    return FLE_E_CUDA;
+  }
+  return FLE_OK;
+}
+
+int fle_pages_gather_dev(fle_ctx* ctx, const fle_page_ref* refs, int nrefs, uint64_t* null_rows_dev) {
+  FLE_CHECK_CTX(ctx);
+  return launch_pages_gather(ctx, refs, nrefs, null_rows_dev);
+}
+
+int fle_assemble_rows_dev(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nrows, const fle_slot_desc* cols, int ncols,
+                          int tuple_size, uint8_t* tuples_dev, int64_t cap_rows, uint64_t* count_dev,
+                          uint64_t* bad_codes_dev) {
+  FLE_CHECK_CTX(ctx);
+  return launch_assemble(ctx, bitmap_dev, nrows, cols, ncols, tuple_size, tuples_dev, cap_rows, count_dev, bad_codes_dev);
 }
 
 // ---- groups of GPUs: totals summed inside the scan kernel ---------------------------------------

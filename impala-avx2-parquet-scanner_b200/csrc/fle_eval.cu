@@ -476,7 +476,7 @@ struct Chain {
 }  // namespace
 
 int lower_program(const fle_col_desc* cols, int ncols, const fle_pred_node* nodes, int nnodes,
-                  LoweredProgram* out, std::string* err) {
+                  LoweredProgram* out, std::string* err, bool mask_literals) {
   auto fail = [&](int code, const char* m) {
     if (err) *err = m;
     return code;
@@ -563,11 +563,28 @@ int lower_program(const fle_col_desc* cols, int ncols, const fle_pred_node* node
     const int bw = cols[nd.col].bit_width;
     const uint64_t mask = bw >= 32 ? 0xffffffffull : ((1ull << bw) - 1ull);
     ch.col = (uint8_t)nd.col;
+    // A literal that does not fit the column's bit width.  The reference's plane algebra simply ignores
+    // the high bits (fle-encoding.h:7965-7971; its precondition is value < 2^bw), which turns `x < 2^bw`
+    // into `x < 0`; that is kept under the "reference_compat" option.  By default the comparison is
+    // folded to what it means for codes below 2^bw: no row equals / exceeds it, every row is below it.
     if (nd.op == FLE_OP_IN) {
       ch.type = PASS_IN;
       ch.in_off = (uint32_t)lp.in_lits.size();
-      ch.in_cnt = (uint32_t)nd.ncodes;
-      for (int j = 0; j < nd.ncodes; ++j) lp.in_lits.push_back((uint32_t)(nd.codes[j] & mask));
+      for (int j = 0; j < nd.ncodes; ++j) {
+        if (!mask_literals && nd.codes[j] > mask) continue;
+        lp.in_lits.push_back((uint32_t)(nd.codes[j] & mask));
+      }
+      ch.in_cnt = (uint32_t)(lp.in_lits.size() - ch.in_off);
+      if (ch.in_cnt == 0) {  // every literal folded away: nothing matches
+        ch.type = PASS_CONST;
+        ch.init = 0;
+      }
+      chains.push_back(ch);
+      continue;
+    }
+    if (!mask_literals && nd.code > mask) {
+      ch.type = PASS_CONST;
+      ch.init = (nd.op == FLE_OP_LT || nd.op == FLE_OP_LE) ? 1 : 0;
       chains.push_back(ch);
       continue;
     }
@@ -836,7 +853,6 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
   P.partial = ctx->d_partial;
   P.ticket = ctx->d_ticket;
   P.tile_counter = ctx->d_ticket + 1;
-  P.in_lits = ctx->d_in_lits;
   group_fill(ctx, &P);
   void* args[] = {(void*)&P, jit_args};
   cudaError_t e = cudaLaunchKernel(kern, dim3(grid), dim3(nt), args, smem_bytes, ctx->stream);
@@ -858,20 +874,10 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
 int prepare_eval(fle_ctx* ctx, const fle_col_desc* cols, int ncols, const fle_pred_node* nodes,
                  int nnodes, LoweredProgram* lp) {
   std::string err;
-  int rc = lower_program(cols, ncols, nodes, nnodes, lp, &err);
+  int rc = lower_program(cols, ncols, nodes, nnodes, lp, &err, ctx->reference_compat);
   if (rc != FLE_OK) return set_error(ctx, rc, err);
-  lp->lits_uploaded = false;
-  const int nl = (int)lp->in_lits.size();
-  if (nl > 0) {
-    rc = ensure_scratch(ctx, 1, nl);
-    if (rc != FLE_OK) return rc;
-    // the pinned staging buffer is reused per program: let the previous copy drain first
-    FLE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    std::memcpy(ctx->h_in_lits, lp->in_lits.data(), (size_t)nl * 4);
-    FLE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_in_lits, ctx->h_in_lits, (size_t)nl * 4,
-                                      cudaMemcpyHostToDevice, ctx->stream));
-    lp->lits_uploaded = true;
-  }
+  lp->lit_slot = -1;
+  lp->lit_gen = 0;
   return FLE_OK;
 }
 
@@ -906,6 +912,15 @@ int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, 
   P.bitmap = bitmap_dev;
   P.count_out = count_dev;
   P.n_in_lits = (int)lp->in_lits.size();
+  P.in_lits = nullptr;
+  if (P.n_in_lits > 0) {
+    // the program's literal pool: uploaded once, again only if its slot has been reused since
+    if (lp->lit_slot < 0 || ctx->lit_slots[lp->lit_slot].gen != lp->lit_gen) {
+      const int rc = upload_literals(ctx, lp->in_lits.data(), P.n_in_lits, &lp->lit_slot, &lp->lit_gen, nullptr);
+      if (rc != FLE_OK) return rc;
+    }
+    P.in_lits = ctx->lit_slots[lp->lit_slot].d;
+  }
   if (agg) {
     P.agg_plain = agg->plain;
     P.agg_dict = agg->dict;

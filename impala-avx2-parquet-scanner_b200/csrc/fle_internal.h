@@ -19,7 +19,9 @@ namespace fle {
 struct LoweredProgram {
   EvalParams p;                  // passes / combs / nslots / slot0_init filled in
   std::vector<uint32_t> in_lits; // IN literal pool
-  bool lits_uploaded = false;    // pool already copied to ctx->d_in_lits
+  int lit_slot = -1;             // literal slot of the context holding the pool (fle_ctx::lit_slots) ...
+  uint64_t lit_gen = 0;          // ... and the slot's generation when it was written: a slot that has been
+                                 // handed to another program since is uploaded again before a launch
   // run-time specialisation (fle_jit.cu), filled in lazily by launch_prepared
   JitPlan jit_plan;
   uint32_t jit_bw[FLE_MAX_COLS] = {0};  // bit widths jit_plan was made for
@@ -30,8 +32,10 @@ struct LoweredProgram {
 };
 
 // Returns FLE_OK or FLE_E_*; err gets a human-readable reason.
+// mask_literals: keep only the low bit_width bits of a literal (the reference's plane algebra); otherwise
+// comparisons with literals >= 2^bit_width are folded to constants
 int lower_program(const fle_col_desc* cols, int ncols, const fle_pred_node* nodes, int nnodes,
-                  LoweredProgram* out, std::string* err);
+                  LoweredProgram* out, std::string* err, bool mask_literals = false);
 
 }  // namespace fle
 
@@ -67,14 +71,29 @@ struct fle_ctx {
   int eval_jit = 1;                      // 0 never, 1 when n >= eval_jit_min_rows or already compiled, 2 always
   int64_t eval_jit_min_rows = 1ll << 24;
   int64_t h2d_chunk_rows = 0;  // 0 = auto
+  bool reference_compat = false;  // reproduce the reference where this library deliberately differs (literal masking)
 
   // scratch owned by the context (device)
   uint64_t* d_partial = nullptr;  // per-CTA counts
   int partial_cap = 0;
   unsigned int* d_ticket = nullptr;
-  uint32_t* d_in_lits = nullptr;
-  int in_lits_cap = 0;
-  uint32_t* h_in_lits = nullptr;  // pinned staging for IN literal pools
+  // IN literal pools: a ring of {pinned host, device} slots, one per prepared program.  Uploads and
+  // kernels are ordered by the context's one stream, so a device slot can be rewritten as soon as the
+  // copy is enqueued; only the PINNED side needs care (the host must not overwrite it before the
+  // previous copy has read it): one event per slot, waited for only when the ring wraps around
+  // onto an upload that is still in flight.  No stream synchronisation on the enqueue path.
+  struct LitSlot {
+    uint32_t* h = nullptr;
+    uint32_t* d = nullptr;
+    int cap = 0;  // 32-bit words
+    cudaEvent_t ev = nullptr;
+    bool ev_pending = false;
+    uint64_t gen = 0;
+  };
+  static constexpr int kLitSlots = 16;
+  LitSlot lit_slots[kLitSlots];
+  int lit_next = 0;
+  uint64_t lit_gen_counter = 0;
   uint64_t* d_count = nullptr;    // 8-byte result slot for host-facing calls
   uint64_t* d_split = nullptr;    // temporary bitmaps of regrouped programs (long IN lists), grow-only
   size_t split_cap = 0;           // bytes
@@ -86,6 +105,12 @@ struct fle_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copy[2] = {nullptr, nullptr};
   cudaEvent_t ev_done[2] = {nullptr, nullptr};
+
+  // single-pass bitmap compaction (fle_rowgroup.cu): tile status words, tagged with a launch generation
+  uint64_t* d_tile_state = nullptr;
+  size_t tile_state_cap = 0;  // bytes
+  uint32_t tile_gen = 0;
+  cudaEvent_t ev_prefetch = nullptr;  // last fle_h2d_prefetch on the copy stream
 
   // group of GPUs whose totals are summed inside the kernels (fle_group.cu)
   int grp_world = 0, grp_rank = 0;
@@ -107,6 +132,9 @@ namespace fle {
 int set_cuda_error(fle_ctx* ctx, cudaError_t e, const char* what);
 int set_error(fle_ctx* ctx, int code, const std::string& msg);
 int ensure_scratch(fle_ctx* ctx, int nblocks, int n_in_lits);
+// copies nwords 32-bit words into the next literal slot (pinned -> device, async on the context's stream);
+// *slot / *gen identify it, *dev is the device address the kernels read
+int upload_literals(fle_ctx* ctx, const void* words, int nwords, int* slot, uint64_t* gen, const uint32_t** dev);
 // fle_group.cu: fills the group fields of a kernel parameter block when a group call is in progress
 void group_fill(fle_ctx* ctx, EvalParams* P);
 // sums {*a_dev, *b_dev (optional)} over the group in place with a one-warp kernel (paths that end in a
@@ -178,6 +206,10 @@ int launch_select(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nbits, uint3
 int launch_gather(fle_ctx* ctx, const uint64_t* planes_dev, int bw, const uint32_t* ids_dev,
                   const uint64_t* count_dev, int64_t cap, const void* dict_dev, int ndict, int elem_size,
                   void* out_dev);
+// fle_rowgroup.cu
+int launch_pages_gather(fle_ctx* ctx, const fle_page_ref* refs, int nrefs, uint64_t* null_rows_dev);
+int launch_assemble(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nrows, const fle_slot_desc* cols, int ncols,
+                    int tuple_size, uint8_t* tuples_dev, int64_t cap_rows, uint64_t* count_dev, uint64_t* bad_codes_dev);
 int launch_sum_product(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nrows, const int64_t* plain_dev,
                        const uint64_t* planes_dev, int bw, const int64_t* dict_dev, int ndict, int64_t* sum_dev,
                        uint64_t* count_dev);

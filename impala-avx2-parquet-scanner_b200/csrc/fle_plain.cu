@@ -235,6 +235,7 @@ int launch_plain_eval(fle_ctx* ctx, const void* values_dev, int elem_type, int64
   if (op < FLE_OP_EQ || op > FLE_OP_IN) return set_error(ctx, FLE_E_INVALID, "PLAIN predicates are EQ..IN leaves");
   if (n < 0 || nlits < (op == FLE_OP_IN ? 0 : 1) || nlits > kPlainMaxLits || (nlits > 0 && !lits_host))
     return set_error(ctx, FLE_E_INVALID, "bad literal list");
+  if (op != FLE_OP_IN && nlits != 1) return set_error(ctx, FLE_E_INVALID, "a comparison takes exactly one literal");
   if (n > 0 && (!values_dev || !bitmap_dev)) return set_error(ctx, FLE_E_INVALID, "null pointer");
   const int es = kElemSize[elem_type];
   if (reinterpret_cast<uintptr_t>(values_dev) & (es - 1))
@@ -244,6 +245,7 @@ int launch_plain_eval(fle_ctx* ctx, const void* values_dev, int elem_type, int64
     return FLE_OK;
   }
   PlainParams P;
+  std::memset(&P, 0, sizeof(P));
   P.values = values_dev;
   P.n = n;
   P.op = op;
@@ -260,12 +262,13 @@ int launch_plain_eval(fle_ctx* ctx, const void* values_dev, int elem_type, int64
   if (nlits <= kPlainInlineLits) {
     if (nlits > 0) std::memcpy(P.lit_inline, lits_host, (size_t)nlits * es);
   } else {
-    // longer lists travel through the context's pinned staging buffer (reused: drain first)
-    FLE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    std::memcpy(ctx->h_in_lits, lits_host, (size_t)nlits * es);
-    FLE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_in_lits, ctx->h_in_lits, (size_t)nlits * es, cudaMemcpyHostToDevice, ctx->stream));
+    // longer lists travel through one of the context's literal slots (no stream synchronisation)
+    std::memcpy(P.lit_inline, lits_host, es);  // literal 0 is always inline
+    const uint32_t* d = nullptr;
+    rc = upload_literals(ctx, lits_host, (int)(((size_t)nlits * es + 3) / 4), nullptr, nullptr, &d);
+    if (rc != FLE_OK) return rc;
+    P.lits = d;
   }
-  P.lits = ctx->d_in_lits;
   P.partial = ctx->d_partial;
   P.ticket = ctx->d_ticket;
   // `literal OP value` (the reference's generic template) is `value OP' literal` with OP' mirrored

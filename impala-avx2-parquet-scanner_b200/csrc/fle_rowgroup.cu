@@ -1,0 +1,398 @@
+// Row-group batches for the drop-in scanner (host/exec/hdfs-parquet-scanner.h): what AssembleRows
+// (/root/reference/hdfs-parquet-scanner.cc:1078-1275) does for ONE row group, as three device steps
+// that together need a handful of launches however many data pages the column chunks hold:
+//
+//   pages_gather_kernel  every data page's FLE section -- at whatever byte offset it sits inside the
+//                        uploaded column-chunk image (page headers, def levels and the width byte
+//                        precede it: dict-encoding.h:185-192, hdfs-parquet-scanner.cc:882-919) and
+//                        with whatever bit width the page was written with (the reference's writer
+//                        picks the width per page, dict-encoding.h:438-444) -- is funnel-shifted into
+//                        ONE aligned plane array per column at the column's widest width (missing high
+//                        planes are zero planes, which leaves every code unchanged); the pages'
+//                        definition levels are counted on the way (rows with def level 0 = NULLs).
+//   select1_kernel       bitmap -> ascending row ids in ONE launch: decoupled look-back over 65536-row
+//                        tiles (the skip-distance list of :1134-1148).
+//   assemble_kernel      the same scan, but instead of row ids the survivors' TUPLES are written:
+//                        code of every column (FleDecoder::Get(T*, skip), fle-encoding.h:344-379) ->
+//                        dictionary value (DictDecoder::GetValue, dict-encoding.h:321-330) -> slot at its
+//                        tuple offset (ReadSlot, hdfs-parquet-scanner.cc:515-531), column by column as
+//                        :1151-1168 does -- select + gather + lookup + tuple layout in one pass.
+#include "fle_device.cuh"
+#include "fle_internal.h"
+
+namespace fle {
+
+// ------------------------------------------------------------------------------------------
+// pages -> planes
+// ------------------------------------------------------------------------------------------
+struct PageRefDev {
+  const uint8_t* src;      // FLE groups of the page, any byte alignment
+  uint64_t* dst;           // 8-byte aligned
+  const uint8_t* def_src;  // 1-bit FLE definition levels of the page, or null
+  int64_t groups;
+  int64_t rows;            // rows of the page (def-level count)
+  int32_t src_bw, dst_bw;
+};
+
+constexpr int kGatherGroupsPerCta = 256;
+
+// 64 bits at byte address p (any alignment) out of the two aligned words around it (up to 7 bytes
+// after the value are touched: column-chunk images are uploaded with 16 bytes of slack)
+__device__ __forceinline__ uint64_t load_u64_unaligned(const uint8_t* p) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint64_t* q = reinterpret_cast<const uint64_t*>(a & ~(uintptr_t)7);
+  const uint32_t sh = (uint32_t)(a & 7) * 8u;
+  const uint64_t lo = __ldg(q);
+  if (sh == 0) return lo;
+  const uint64_t hi = __ldg(q + 1);
+  return (lo >> sh) | (hi << (64u - sh));
+}
+
+// grid = (tiles of the largest page, pages).  A CTA copies 256 groups of one page: the page's plane
+// words are consecutive in the source, so word w of the tile goes to thread w % 256 (coalesced 8-byte
+// reads); the destination word of source word (g, i) is g * dst_bw + i.
+__global__ void __launch_bounds__(256)
+pages_gather_kernel(const PageRefDev* __restrict__ refs, unsigned long long* __restrict__ null_rows) {
+  const PageRefDev R = refs[blockIdx.y];
+  const int64_t g0 = (int64_t)blockIdx.x * kGatherGroupsPerCta;
+  // CTAs of this page that have groups to copy (at least one: it also counts the definition levels)
+  const int64_t nalive = max((int64_t)1, (R.groups + kGatherGroupsPerCta - 1) / kGatherGroupsPerCta);
+  if ((int64_t)blockIdx.x >= nalive) return;
+  const int64_t ng = min((int64_t)kGatherGroupsPerCta, R.groups - g0);
+  if (ng > 0) {
+    const int sbw = R.src_bw, dbw = R.dst_bw;
+    const uint8_t* s = R.src + (uint64_t)g0 * sbw * 8u;
+    uint64_t* d = R.dst + (uint64_t)g0 * dbw;
+    const int64_t nw = ng * sbw;
+    for (int64_t w = threadIdx.x; w < nw; w += 256) {
+      const int64_t g = w / sbw;
+      const int i = (int)(w - g * sbw);
+      d[g * dbw + i] = load_u64_unaligned(s + w * 8);
+    }
+    if (dbw > sbw) {
+      const int pad = dbw - sbw;
+      for (int64_t w = threadIdx.x; w < ng * pad; w += 256) {
+        const int64_t g = w / pad;
+        d[g * dbw + sbw + (int)(w - g * pad)] = 0ull;
+      }
+    }
+  }
+  // definition levels (bit width 1: one word per 64 rows, row k at bit 63 - k): count the rows that are NOT defined
+  if (R.def_src && null_rows) {
+    const int64_t dgroups = (R.rows + 63) / 64;
+    unsigned long long nulls = 0;
+    for (int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x; g < dgroups; g += nalive * 256) {
+      const uint64_t w = load_u64_unaligned(R.def_src + g * 8);
+      const int64_t left = R.rows - g * 64;
+      const uint64_t want = left >= 64 ? ~0ull : (~0ull << (64 - left));
+      nulls += __popcll(~w & want);
+    }
+    if (__syncthreads_or(nulls != 0)) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) nulls += __shfl_xor_sync(0xffffffffu, nulls, o);
+      if ((threadIdx.x & 31) == 0 && nulls) atomicAdd(null_rows, nulls);
+    }
+  }
+}
+
+int launch_pages_gather(fle_ctx* ctx, const fle_page_ref* refs, int nrefs, uint64_t* null_rows_dev) {
+  if (nrefs < 0 || (nrefs > 0 && !refs)) return set_error(ctx, FLE_E_INVALID, "bad page list");
+  if (null_rows_dev) FLE_CUDA_TRY(ctx, cudaMemsetAsync(null_rows_dev, 0, 8, ctx->stream));
+  if (nrefs == 0) return FLE_OK;
+  std::vector<PageRefDev> h((size_t)nrefs);
+  int64_t max_groups = 1;
+  for (int i = 0; i < nrefs; ++i) {
+    const fle_page_ref& r = refs[i];
+    if (r.src_bit_width < 1 || r.src_bit_width > 32 || r.dst_bit_width < r.src_bit_width || r.dst_bit_width > 32)
+      return set_error(ctx, FLE_E_INVALID, "page bit widths outside 1..32 or destination narrower than the page");
+    if (r.groups < 0 || r.rows < 0 || (r.groups > 0 && (!r.src_dev || !r.dst_dev)))
+      return set_error(ctx, FLE_E_INVALID, "bad page reference");
+    if ((uint64_t)r.groups * (uint64_t)r.src_bit_width * 8u > r.src_bytes)
+      return set_error(ctx, FLE_E_BUFFER, "page shorter than its groups");
+    if (r.def_src_dev && (uint64_t)((r.rows + 63) / 64) * 8u > r.def_bytes)
+      return set_error(ctx, FLE_E_BUFFER, "definition levels shorter than the page's rows");
+    if (reinterpret_cast<uintptr_t>(r.dst_dev) & 7) return set_error(ctx, FLE_E_ALIGN, "plane destination must be 8-byte aligned");
+    h[i].src = static_cast<const uint8_t*>(r.src_dev);
+    h[i].dst = static_cast<uint64_t*>(r.dst_dev);
+    h[i].def_src = static_cast<const uint8_t*>(r.def_src_dev);
+    h[i].groups = r.groups;
+    h[i].rows = r.rows;
+    h[i].src_bw = r.src_bit_width;
+    h[i].dst_bw = r.dst_bit_width;
+    max_groups = std::max(max_groups, r.groups);
+  }
+  const uint32_t* d = nullptr;
+  int rc = upload_literals(ctx, h.data(), (int)(h.size() * sizeof(PageRefDev) / 4), nullptr, nullptr, &d);
+  if (rc != FLE_OK) return rc;
+  const dim3 grid((unsigned)((max_groups + kGatherGroupsPerCta - 1) / kGatherGroupsPerCta), (unsigned)nrefs);
+  pages_gather_kernel<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const PageRefDev*>(d),
+                                                    reinterpret_cast<unsigned long long*>(null_rows_dev));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(ctx, e, "pages_gather launch");
+  ctx->launches += 1;
+  return FLE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// single-pass ordered compaction of a bitmap (decoupled look-back)
+// ------------------------------------------------------------------------------------------
+constexpr int kTileThreads = 256;
+constexpr int kTileWordsPerThread = 4;
+constexpr int kTileWords = kTileThreads * kTileWordsPerThread;  // 65536 rows per tile
+
+// tile status words: [63:40] launch generation, [39:38] 1 = aggregate / 2 = inclusive prefix, [37:0] value.
+// The generation makes entries of earlier launches read as "not there yet": no reset between launches.
+constexpr uint64_t kTileAgg = 1ull << 38, kTilePrefix = 2ull << 38, kTileValMask = (1ull << 38) - 1ull;
+
+struct SlotDev {  // one materialised column
+  const uint64_t* planes;
+  const void* dict;
+  int32_t bw, ndict, slot_size, tuple_off;
+};
+
+struct TileScanParams {
+  const uint64_t* bm;
+  int64_t nbits, nwords;
+  int32_t ntiles;
+  uint32_t gen;           // 24 bits, never 0
+  uint64_t* tile_state;   // ntiles words
+  unsigned int* ticket;   // [0] completion ticket, [1] tile counter (both self-resetting)
+  uint64_t* count_out;
+  // select: row ids
+  uint32_t* ids;
+  int64_t cap;
+  // assemble: tuples
+  uint8_t* tuples;
+  int32_t tuple_size, ncols;
+  unsigned long long* bad_codes;
+  SlotDev cols[FLE_MAX_COLS];
+};
+
+__device__ __forceinline__ uint64_t tile_tail_mask(int64_t w, int64_t nbits) {
+  const int64_t left = nbits - w * 64;
+  if (left >= 64) return ~0ull;
+  if (left <= 0) return 0ull;
+  return (1ull << left) - 1ull;
+}
+
+__device__ __forceinline__ uint32_t code_of_row(const uint64_t* __restrict__ planes, int bw, uint32_t r) {
+  const uint64_t* g = planes + (uint64_t)(r >> 6) * bw;
+  const int sh = 63 - (int)(r & 63);
+  uint32_t v = 0;
+  for (int i = 0; i < bw; ++i) v |= (uint32_t)((ldg_gather64(g + i) >> sh) & 1ull) << i;
+  return v;
+}
+
+template <bool ASSEMBLE>
+__global__ void __launch_bounds__(kTileThreads) tile_scan_kernel(const __grid_constant__ TileScanParams P) {
+  __shared__ uint32_t warp_scan[kTileThreads / 32];
+  __shared__ int tile_s;
+  __shared__ uint64_t base_s;
+  __shared__ bool last_s;
+  const uint64_t gen = (uint64_t)P.gen << 40;
+  for (;;) {
+    // tiles are claimed in launch order, so every predecessor of a tile is running or done: the
+    // look-back below cannot wait for a CTA that has not been scheduled
+    if (threadIdx.x == 0) tile_s = (int)atomicAdd(P.ticket + 1, 1u);
+    __syncthreads();
+    const int tile = tile_s;
+    if (tile >= P.ntiles) break;
+    const int64_t w0 = (int64_t)tile * kTileWords + (int64_t)threadIdx.x * kTileWordsPerThread;
+    uint64_t m[kTileWordsPerThread];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < kTileWordsPerThread; ++k) {
+      const int64_t w = w0 + k;
+      m[k] = w < P.nwords ? (P.bm[w] & tile_tail_mask(w, P.nbits)) : 0ull;
+      mine += __popcll(m[k]);
+    }
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((threadIdx.x & 31) >= o) incl += y;
+    }
+    if ((threadIdx.x & 31) == 31) warp_scan[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t woff = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kTileThreads / 32; ++w) {
+      if (w < (int)(threadIdx.x >> 5)) woff += warp_scan[w];
+      total += warp_scan[w];
+    }
+    if (threadIdx.x < 32) {  // first warp: publish, look back, publish the inclusive prefix
+      const int lane = threadIdx.x;
+      volatile uint64_t* st = P.tile_state;
+      if (lane == 0) st[tile] = gen | (tile == 0 ? kTilePrefix : kTileAgg) | (uint64_t)total;
+      uint64_t excl = 0;
+      int idx = tile - 1;
+      while (idx >= 0) {
+        const int j = idx - lane;
+        uint64_t s = kTilePrefix;  // lanes past the front of the array: a prefix of 0
+        if (j >= 0) {
+          do {
+            s = st[j];
+          } while ((s >> 40) != (gen >> 40) || (s & (kTileAgg | kTilePrefix)) == 0);
+        }
+        const unsigned has_prefix = __ballot_sync(0xffffffffu, (s & kTilePrefix) != 0);
+        // the nearest predecessor that already knows its inclusive prefix closes the look-back; without
+        // one all 32 aggregates are added and the window moves on
+        const int first = has_prefix ? __ffs(has_prefix) - 1 : 31;
+        uint64_t v = lane <= first ? (s & kTileValMask) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        excl += v;
+        if (has_prefix) break;
+        idx -= 32;
+      }
+      if (lane == 0) {
+        if (tile != 0) st[tile] = gen | kTilePrefix | (excl + total);
+        base_s = excl;
+        if (tile == P.ntiles - 1 && P.count_out) *P.count_out = excl + total;
+      }
+    }
+    __syncthreads();
+    int64_t pos = (int64_t)base_s + woff + (incl - mine);
+#pragma unroll
+    for (int k = 0; k < kTileWordsPerThread; ++k) {
+      uint64_t x = m[k];
+      const uint32_t rbase = (uint32_t)((w0 + k) * 64);
+      while (x) {
+        const uint32_t r = rbase + (uint32_t)(__ffsll((long long)x) - 1);
+        x &= x - 1;
+        if (pos < P.cap) {
+          if (!ASSEMBLE) {
+            P.ids[pos] = r;
+          } else {
+            uint8_t* t = P.tuples + (uint64_t)pos * P.tuple_size;
+            for (int q = 0; q < P.tuple_size; q += 8) *reinterpret_cast<uint64_t*>(t + q) = 0ull;  // null indicators + padding
+            for (int c = 0; c < P.ncols; ++c) {
+              const SlotDev& S = P.cols[c];
+              const uint32_t code = code_of_row(S.planes, S.bw, r);
+              if (code >= (uint32_t)S.ndict) {  // DictDecoder::GetValue() == false (dict-encoding.h:325)
+                atomicAdd(P.bad_codes, 1ull);
+                continue;
+              }
+              uint8_t* slot = t + S.tuple_off;
+              switch (S.slot_size) {
+                case 1: *slot = static_cast<const uint8_t*>(S.dict)[code]; break;
+                case 2: *reinterpret_cast<uint16_t*>(slot) = static_cast<const uint16_t*>(S.dict)[code]; break;
+                case 4: *reinterpret_cast<uint32_t*>(slot) = static_cast<const uint32_t*>(S.dict)[code]; break;
+                default: *reinterpret_cast<uint64_t*>(slot) = static_cast<const uint64_t*>(S.dict)[code]; break;
+              }
+            }
+          }
+        }
+        ++pos;
+      }
+    }
+    __syncthreads();
+  }
+  // the last CTA to leave resets the two counters for the next launch on this stream
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last_s = atomicAdd(P.ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last_s && threadIdx.x == 0) {
+    P.ticket[0] = 0;
+    P.ticket[1] = 0;
+  }
+}
+
+static int launch_tile_scan(fle_ctx* ctx, TileScanParams& P, bool assemble) {
+  const int64_t nwords = (P.nbits + 63) / 64;
+  P.nwords = nwords;
+  P.ntiles = (int)((nwords + kTileWords - 1) / kTileWords);
+  if ((size_t)P.ntiles * 8 > ctx->tile_state_cap) {
+    const size_t cap = std::max<size_t>((size_t)P.ntiles * 8, 64 << 10);
+    if (ctx->d_tile_state) {
+      FLE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      cudaFree(ctx->d_tile_state);
+      ctx->d_tile_state = nullptr;
+      ctx->tile_state_cap = 0;
+    }
+    FLE_CUDA_TRY(ctx, cudaMalloc(&ctx->d_tile_state, cap));
+    FLE_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_tile_state, 0, cap, ctx->stream));
+    ctx->tile_state_cap = cap;
+  }
+  ctx->tile_gen = (ctx->tile_gen + 1) & 0xffffffu;
+  if (ctx->tile_gen == 0) {  // generation wrap: entries of 2^24 launches ago must not be taken for this launch's
+    FLE_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_tile_state, 0, ctx->tile_state_cap, ctx->stream));
+    ctx->tile_gen = 1;
+  }
+  P.gen = ctx->tile_gen;
+  P.tile_state = ctx->d_tile_state;
+  P.ticket = ctx->d_ticket;
+  const int grid = std::max(1, std::min(P.ntiles, ctx->num_sms * 8));
+  if (assemble) tile_scan_kernel<true><<<grid, kTileThreads, 0, ctx->stream>>>(P);
+  else tile_scan_kernel<false><<<grid, kTileThreads, 0, ctx->stream>>>(P);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(ctx, e, "tile_scan launch");
+  ctx->launches += 1;
+  return FLE_OK;
+}
+
+int launch_select(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nbits, uint32_t* ids_dev, int64_t cap,
+                  uint64_t* count_dev) {
+  if (nbits < 0 || cap < 0 || !count_dev || (nbits > 0 && !bitmap_dev) || (cap > 0 && !ids_dev))
+    return set_error(ctx, FLE_E_INVALID, "bad select arguments");
+  if (nbits > (int64_t)0xFFFFFFFFll) return set_error(ctx, FLE_E_UNSUPPORTED, "row ids are 32-bit: at most 2^32-1 rows per call");
+  if (nbits == 0) {
+    FLE_CUDA_TRY(ctx, cudaMemsetAsync(count_dev, 0, 8, ctx->stream));
+    return FLE_OK;
+  }
+  TileScanParams P;
+  std::memset(&P, 0, sizeof(P));
+  P.bm = bitmap_dev;
+  P.nbits = nbits;
+  P.count_out = count_dev;
+  P.ids = ids_dev;
+  P.cap = cap;
+  return launch_tile_scan(ctx, P, false);
+}
+
+int launch_assemble(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nrows, const fle_slot_desc* cols, int ncols,
+                    int tuple_size, uint8_t* tuples_dev, int64_t cap_rows, uint64_t* count_dev, uint64_t* bad_codes_dev) {
+  if (nrows < 0 || cap_rows < 0 || !count_dev || !bad_codes_dev || ncols < 1 || ncols > FLE_MAX_COLS || !cols ||
+      (nrows > 0 && !bitmap_dev) || (cap_rows > 0 && !tuples_dev))
+    return set_error(ctx, FLE_E_INVALID, "bad assemble arguments");
+  if (nrows > (int64_t)0xFFFFFFFFll) return set_error(ctx, FLE_E_UNSUPPORTED, "at most 2^32-1 rows per call");
+  if (tuple_size < 8 || (tuple_size & 7) || (reinterpret_cast<uintptr_t>(tuples_dev) & 7))
+    return set_error(ctx, FLE_E_ALIGN, "tuples are multiples of 8 bytes at an 8-byte aligned address");
+  TileScanParams P;
+  std::memset(&P, 0, sizeof(P));
+  for (int c = 0; c < ncols; ++c) {
+    const fle_slot_desc& s = cols[c];
+    if (s.bit_width < 1 || s.bit_width > 32) return set_error(ctx, FLE_E_INVALID, "bit width outside 1..32");
+    if (s.slot_size != 1 && s.slot_size != 2 && s.slot_size != 4 && s.slot_size != 8)
+      return set_error(ctx, FLE_E_INVALID, "slot sizes are 1, 2, 4 or 8 bytes");
+    if (s.tuple_offset < 0 || s.tuple_offset + s.slot_size > tuple_size || (s.tuple_offset % s.slot_size))
+      return set_error(ctx, FLE_E_INVALID, "slot outside the tuple or misaligned");
+    if (!s.planes_dev || !s.dict_dev || s.ndict < 0) return set_error(ctx, FLE_E_INVALID, "null column or dictionary");
+    if ((uint64_t)((nrows + 63) / 64) * s.bit_width * 8u > s.bytes) return set_error(ctx, FLE_E_BUFFER, "rows beyond the encoded buffer");
+    if (reinterpret_cast<uintptr_t>(s.planes_dev) & 7) return set_error(ctx, FLE_E_ALIGN, "planes must be 8-byte aligned");
+    P.cols[c].planes = static_cast<const uint64_t*>(s.planes_dev);
+    P.cols[c].dict = s.dict_dev;
+    P.cols[c].bw = s.bit_width;
+    P.cols[c].ndict = s.ndict;
+    P.cols[c].slot_size = s.slot_size;
+    P.cols[c].tuple_off = s.tuple_offset;
+  }
+  FLE_CUDA_TRY(ctx, cudaMemsetAsync(bad_codes_dev, 0, 8, ctx->stream));
+  if (nrows == 0) {
+    FLE_CUDA_TRY(ctx, cudaMemsetAsync(count_dev, 0, 8, ctx->stream));
+    return FLE_OK;
+  }
+  P.bm = bitmap_dev;
+  P.nbits = nrows;
+  P.count_out = count_dev;
+  P.cap = cap_rows;
+  P.tuples = tuples_dev;
+  P.tuple_size = tuple_size;
+  P.ncols = ncols;
+  P.bad_codes = reinterpret_cast<unsigned long long*>(bad_codes_dev);
+  return launch_tile_scan(ctx, P, true);
+}
+
+}  // namespace fle

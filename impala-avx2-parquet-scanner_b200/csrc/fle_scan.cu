@@ -3,7 +3,7 @@
 // distances and then calls ReadValue(skip) -> DictDecoder::GetValue(T*, skip) ->
 // FleDecoder::Get(T*, skip) (fle-encoding.h:344-379) once per survivor and column.
 // On the device that is
-//   select   : bitmap -> ascending row ids            (ordered stream compaction)
+//   select   : bitmap -> ascending row ids            (ordered stream compaction; fle_rowgroup.cu)
 //   gather   : row id -> code = bit (63 - r%64) of the bw plane words of group r/64
 //   lookup   : code -> dictionary value               (dense output column)
 // plus the fused aggregate a TPC-H Q6 scan needs downstream of the bitmap:
@@ -13,104 +13,11 @@
 
 namespace fle {
 
-constexpr int kSelThreads = 256;
-constexpr int kSelWordsPerThread = 4;
-constexpr int kSelWordsPerBlock = kSelThreads * kSelWordsPerThread;
-
 __device__ __forceinline__ uint64_t sel_tail_mask(int64_t w, int64_t nbits) {
   const int64_t left = nbits - w * 64;
   if (left >= 64) return ~0ull;
   if (left <= 0) return 0ull;
   return (1ull << left) - 1ull;
-}
-
-// pass 1: popcount per block of kSelWordsPerBlock words (thread t owns consecutive words)
-__global__ void __launch_bounds__(kSelThreads)
-select_count_kernel(const uint64_t* __restrict__ bm, int64_t nbits, int64_t nwords, uint64_t* __restrict__ block_sums) {
-  __shared__ uint32_t warp_sum[kSelThreads / 32];
-  const int64_t w0 = (int64_t)blockIdx.x * kSelWordsPerBlock + (int64_t)threadIdx.x * kSelWordsPerThread;
-  uint32_t c = 0;
-#pragma unroll
-  for (int k = 0; k < kSelWordsPerThread; ++k) {
-    const int64_t w = w0 + k;
-    if (w < nwords) c += __popcll(bm[w] & sel_tail_mask(w, nbits));
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-  if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = c;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint64_t t = 0;
-    for (int i = 0; i < kSelThreads / 32; ++i) t += warp_sum[i];
-    block_sums[blockIdx.x] = t;
-  }
-}
-
-// pass 2 (one block): exclusive scan of the block sums in place; total -> *count_out
-__global__ void __launch_bounds__(1024) select_scan_kernel(uint64_t* __restrict__ block_sums, int nblocks,
-                                                           uint64_t* __restrict__ count_out) {
-  __shared__ uint64_t warp_tot[32];
-  __shared__ uint64_t carry_s;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  for (int base = 0; base < nblocks; base += 1024) {
-    const int i = base + threadIdx.x;
-    const uint64_t v = i < nblocks ? block_sums[i] : 0;
-    uint64_t incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint64_t y = __shfl_up_sync(0xffffffffu, incl, o);
-      if ((threadIdx.x & 31) >= o) incl += y;
-    }
-    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    uint64_t woff = 0;
-    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += warp_tot[w];
-    const uint64_t carry = carry_s;
-    if (i < nblocks) block_sums[i] = carry + woff + incl - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_s = carry + woff + incl;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0 && count_out) *count_out = carry_s;
-}
-
-// pass 3: every block writes its survivors' row ids at its scanned offset, in row order
-__global__ void __launch_bounds__(kSelThreads)
-select_write_kernel(const uint64_t* __restrict__ bm, int64_t nbits, int64_t nwords,
-                    const uint64_t* __restrict__ block_offs, uint32_t* __restrict__ ids, int64_t cap) {
-  __shared__ uint32_t warp_scan[kSelThreads / 32];
-  const int64_t w0 = (int64_t)blockIdx.x * kSelWordsPerBlock + (int64_t)threadIdx.x * kSelWordsPerThread;
-  uint64_t m[kSelWordsPerThread];
-  uint32_t mine = 0;
-#pragma unroll
-  for (int k = 0; k < kSelWordsPerThread; ++k) {
-    const int64_t w = w0 + k;
-    m[k] = w < nwords ? (bm[w] & sel_tail_mask(w, nbits)) : 0ull;
-    mine += __popcll(m[k]);
-  }
-  uint32_t incl = mine;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-    if ((threadIdx.x & 31) >= o) incl += y;
-  }
-  if ((threadIdx.x & 31) == 31) warp_scan[threadIdx.x >> 5] = incl;
-  __syncthreads();
-  uint32_t woff = 0;
-  for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += warp_scan[w];
-  int64_t pos = (int64_t)block_offs[blockIdx.x] + woff + (incl - mine);
-#pragma unroll
-  for (int k = 0; k < kSelWordsPerThread; ++k) {
-    uint64_t x = m[k];
-    const uint32_t base = (uint32_t)((w0 + k) * 64);
-    while (x) {
-      const int b = __ffsll((long long)x) - 1;
-      if (pos < cap) ids[pos] = base + (uint32_t)b;
-      ++pos;
-      x &= x - 1;
-    }
-  }
 }
 
 // code of row r: bit (63 - r%64) of each of the bw plane words of group r/64
@@ -222,28 +129,6 @@ sum_product_kernel(const uint64_t* __restrict__ bm, int64_t nrows, const int64_t
       if (count_out) atomicAdd(count_out, tc);
     }
   }
-}
-
-int launch_select(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nbits, uint32_t* ids_dev, int64_t cap,
-                  uint64_t* count_dev) {
-  if (nbits < 0 || cap < 0 || !count_dev || (nbits > 0 && !bitmap_dev) || (cap > 0 && !ids_dev))
-    return set_error(ctx, FLE_E_INVALID, "bad select arguments");
-  if (nbits > (int64_t)0xFFFFFFFFll) return set_error(ctx, FLE_E_UNSUPPORTED, "row ids are 32-bit: at most 2^32-1 rows per call");
-  if (nbits == 0) {
-    FLE_CUDA_TRY(ctx, cudaMemsetAsync(count_dev, 0, 8, ctx->stream));
-    return FLE_OK;
-  }
-  const int64_t nwords = (nbits + 63) / 64;
-  const int nblocks = (int)((nwords + kSelWordsPerBlock - 1) / kSelWordsPerBlock);
-  int rc = ensure_scratch(ctx, nblocks, 0);
-  if (rc != FLE_OK) return rc;
-  select_count_kernel<<<nblocks, kSelThreads, 0, ctx->stream>>>(bitmap_dev, nbits, nwords, ctx->d_partial);
-  select_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_partial, nblocks, count_dev);
-  select_write_kernel<<<nblocks, kSelThreads, 0, ctx->stream>>>(bitmap_dev, nbits, nwords, ctx->d_partial, ids_dev, cap);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return set_cuda_error(ctx, e, "select launch");
-  ctx->launches += 3;
-  return FLE_OK;
 }
 
 int launch_gather(fle_ctx* ctx, const uint64_t* planes_dev, int bw, const uint32_t* ids_dev,

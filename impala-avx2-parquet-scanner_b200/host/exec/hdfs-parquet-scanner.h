@@ -21,7 +21,14 @@
 //     nullable column:  [int32 num_def_bytes][def levels: FLE, bit width 1][u8 bw][FLE groups]
 //     required column:  [u8 bw][FLE groups]
 //
-// Two evaluation paths, same results:
+// Three evaluation paths, same results:
+//   * row-group batch (default when it applies): ALL data pages of every column chunk are uploaded --
+//     one copy per column chunk when its pages lie back to back in (pinned) host memory, on the
+//     context's copy stream, so row group k+1 can cross PCIe while k is evaluated
+//     (StartRowGroupUpload) -- then fle_pages_gather_dev re-bases the pages' FLE sections onto one
+//     plane array per column (counting NULLs on the way), ONE fused fle_eval_dev covers the row group
+//     and fle_assemble_rows_dev writes the survivors' tuples; two host synchronisations per row group
+//     however many pages it holds.  Applies to fresh readers over dictionary pages without NULLs;
 //   * per leaf (the reference's structure): every leaf call goes through ColumnReader<T> ->
 //     DictDecoder<T> -> FleDecoder, which evaluates the WHOLE page on the GPU on first use and
 //     then serves the <=1024-row windows from the cached bitmap;
@@ -82,7 +89,8 @@ class HdfsParquetScanner {
   template<typename T> class ColumnReader;
 
   HdfsParquetScanner() : tuple_size_(0), fused_enabled_(true), fused_pos_(0), fused_rows_(0),
-      fused_evals_(0), leaf_windows_(0), device_materialise_(true), device_spans_(0) {}
+      fused_evals_(0), leaf_windows_(0), device_materialise_(true), device_spans_(0),
+      row_group_batch_(true), batch_state_(0), batch_bank_(0), batch_rows_(0), row_group_batches_(0) {}
   ~HdfsParquetScanner();
 
   // CreateColumnReaders/CreateReader (:1410-1451, :670-720) + InitColumns (:1453-1531) for
@@ -127,6 +135,14 @@ class HdfsParquetScanner {
   int64_t fused_evals() const { return fused_evals_; }
   int64_t leaf_windows() const { return leaf_windows_; }
   int64_t device_spans() const { return device_spans_; }
+  // false: never take the whole-row-group batch path.
+  void set_row_group_batch(bool on) { row_group_batch_ = on; }
+  int64_t row_group_batches() const { return row_group_batches_; }
+  // Extension: begins the upload of this row group's column chunks (asynchronously, on the calling
+  // thread's copy stream) so that it overlaps the AssembleRows of the previous row group.  Optional:
+  // AssembleRows calls it itself.  Call after the last AddColumn/AddSimplePredicate.  Returns false when the
+  // row group does not qualify for the batch path (nothing is uploaded then).
+  bool StartRowGroupUpload();
 
   BaseColumnReader* column_reader(int idx) { return column_readers_[idx]; }
 
@@ -140,6 +156,7 @@ class HdfsParquetScanner {
   // survivors' codes come back.  Returns false (nothing consumed) when the span does not qualify.
   bool DevicePageSpan(std::vector<uint8_t>* rows, int64_t* num_passed, int64_t* span_rows);
   void* DeviceBuffer(size_t slot, size_t bytes);
+  bool DeviceRowGroup(std::vector<uint8_t>* rows, int64_t* num_passed, int64_t* span_rows);
 
   std::vector<BaseColumnReader*> column_readers_;
   std::vector<SimplePredicate*> simple_predicates_;
@@ -155,6 +172,23 @@ class HdfsParquetScanner {
   int64_t device_spans_;
   std::vector<std::pair<void*, size_t> > dev_buffers_;  // grow-only device scratch, freed with the scanner
   std::vector<uint32_t> host_codes_;
+
+  // row-group batch: what StartRowGroupUpload prepared
+  struct BatchColumn {
+    void* image_dev;          // the uploaded column-chunk image(s)
+    void* planes_dev;         // groups * bit_width * 8 bytes, filled by fle_pages_gather_dev
+    void* dict_dev;
+    int bit_width;            // widest page
+    int ndict;
+  };
+  bool row_group_batch_;
+  int batch_state_;           // 0 not tried, 1 uploaded, -1 does not qualify
+  int batch_bank_;
+  int64_t batch_rows_;
+  int64_t row_group_batches_;
+  std::vector<BatchColumn> batch_cols_;
+  std::vector<fle_page_ref> batch_refs_;
+  FusedProgram batch_prog_;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -193,6 +227,11 @@ class HdfsParquetScanner::BaseColumnReader {
   int def_bytes() const { return def_bytes_; }
   bool page_is_dictionary() const { return page_encoding_ == parquet_encoding::FLE_DICTIONARY ||
                                            page_encoding_ == parquet_encoding::PLAIN_DICTIONARY; }
+  // row-group batch accessors
+  const std::vector<DataPage>& pages() const { return pages_; }
+  bool fresh() const { return next_page_ == 0 && num_buffered_values_ == 0; }
+  void ConsumeAllPages() { next_page_ = pages_.size(); num_buffered_values_ = 0; }
+  virtual const void* dict_values(int* n, int* elem_size) const = 0;
 
  protected:
   friend class HdfsParquetScanner;
@@ -246,9 +285,43 @@ class HdfsParquetScanner::ColumnReader : public HdfsParquetScanner::BaseColumnRe
     root_bitset.resize(n_root);
   }
 
+  // PLAIN data pages (columns that overflowed the dictionary, hdfs-parquet-table-writer.cc:276-279):
+  // ParquetPlainEncoder::Eq..In<T> (parquet-common.h:197-255) compare num_rows values from the read
+  // cursor on.  Here the page's values are uploaded once, the whole page is evaluated per (op, literal)
+  // by fle_plain_eval_dev and windows are bit slices of that result.  Default: `value OP literal`, In()
+  // implemented, NULLs handled like the dictionary path.  FleGpu::reference_compat(): `literal OP value`
+  // (the reference's generic templates), In() appends nothing (its empty stub), no NULL handling.
+  void PlainOp(int op, int64_t num_rows, boost::dynamic_bitset<>& skip_bitset, const T* lits, int nlits) {
+    const bool compat = FleGpu::reference_compat();
+    if (compat && op == FLE_OP_IN) return;
+    const int et = PlainElemType();
+    fle_ctx* ctx = FleGpu::ctx();
+    if (et < 0 || ctx == NULL) {
+      if (et < 0) parent_->parse_status_ = Status("PLAIN predicates: unsupported slot type");
+      skip_bitset.resize(skip_bitset.size() + num_rows, false);
+      return;
+    }
+    boost::dynamic_bitset<> data_bitset;
+    boost::dynamic_bitset<>* out = &skip_bitset;
+    int64_t data_rows = num_rows;
+    if (!compat && max_def_level() > 0) {
+      fle_def_levels_->Eq(num_rows, skip_bitset, max_def_level());
+      data_rows = static_cast<int64_t>(skip_bitset.count());
+      out = &data_bitset;
+    }
+    const std::vector<uint64_t>* bm = PlainBitmap(ctx, et, op, lits, nlits, compat);
+    // the read cursor: values of this page already consumed by ReadSlot/SkipSlot
+    int64_t pos = plain_pos_;
+    for (int64_t i = 0; i < data_rows; ++i, ++pos) {
+      const bool bit = bm != NULL && pos < plain_values_ && (((*bm)[pos >> 6] >> (pos & 63)) & 1);
+      out->push_back(bit);
+    }
+    if (out == &data_bitset) IntersectBitset(skip_bitset, data_bitset);
+  }
+
 #define FLE_COLUMN_READER_OP(Name, ArgT)                                                   \
   void Name(int64_t num_rows, boost::dynamic_bitset<>& skip_bitset, ArgT val) {            \
-    if (!page_is_dictionary()) { skip_bitset.resize(skip_bitset.size() + num_rows, false); return; } \
+    if (!page_is_dictionary()) { PlainCall##Name(num_rows, skip_bitset, val); return; }      \
     if (max_def_level() == 0) {                                                            \
       dict_decoder_->Name(num_rows, skip_bitset, val);                                     \
       return;                                                                              \
@@ -268,11 +341,26 @@ class HdfsParquetScanner::ColumnReader : public HdfsParquetScanner::BaseColumnRe
 
  protected:
   virtual Status InitDataPage(uint8_t* data, int size) {  // :453-472
+    if (!page_is_dictionary()) {  // PLAIN: values back to back
+      plain_data_ = data;
+      plain_values_ = size / static_cast<int>(sizeof(T));
+      plain_pos_ = 0;
+      plain_cache_.clear();
+      plain_dev_ = NULL;
+      return Status::OK();
+    }
     if (dict_decoder_.get() == NULL) return Status("File corrupt. Missing dictionary page.");
     dict_decoder_->SetData(data, size);
     return Status::OK();
   }
   virtual bool ReadSlot(void* slot, int skip_rows) {  // :515-531
+    if (!page_is_dictionary()) {  // ParquetPlainEncoder::Decode<T>(data_, ..., skip_rows)
+      plain_pos_ += skip_rows;
+      if (plain_pos_ >= plain_values_) return false;
+      memcpy(slot, plain_data_ + plain_pos_ * sizeof(T), sizeof(T));
+      ++plain_pos_;
+      return true;
+    }
     T val;
     bool result = dict_decoder_->GetValue(&val, skip_rows);
     memcpy(slot, &val, sizeof(T));
@@ -280,7 +368,16 @@ class HdfsParquetScanner::ColumnReader : public HdfsParquetScanner::BaseColumnRe
   }
   virtual bool SkipSlot(int skip_rows) {  // :533-547
     if (skip_rows <= 0) return true;
+    if (!page_is_dictionary()) {
+      plain_pos_ += skip_rows;
+      return true;
+    }
     return dict_decoder_->SkipValue(skip_rows);
+  }
+  virtual const void* dict_values(int* n, int* elem_size) const {
+    *n = dict_decoder_.get() ? static_cast<int>(dict_decoder_->dict().size()) : 0;
+    *elem_size = sizeof(T);
+    return *n > 0 ? static_cast<const void*>(&dict_decoder_->dict()[0]) : NULL;
   }
   virtual bool SlotFromCode(void* slot, uint32_t code) {  // what GetValue does after Get(&index), dict-encoding.h:321-330
     const std::vector<T>& d = dict_decoder_->dict();
@@ -290,10 +387,72 @@ class HdfsParquetScanner::ColumnReader : public HdfsParquetScanner::BaseColumnRe
   }
 
  private:
+  static int PlainElemType();
+#define FLE_PLAIN_CALL(Name, OP)                                                                       \
+  void PlainCall##Name(int64_t num_rows, boost::dynamic_bitset<>& bs, T& val) { PlainOp(OP, num_rows, bs, &val, 1); }
+  FLE_PLAIN_CALL(Eq, FLE_OP_EQ)
+  FLE_PLAIN_CALL(Lt, FLE_OP_LT)
+  FLE_PLAIN_CALL(Le, FLE_OP_LE)
+  FLE_PLAIN_CALL(Gt, FLE_OP_GT)
+  FLE_PLAIN_CALL(Ge, FLE_OP_GE)
+#undef FLE_PLAIN_CALL
+  void PlainCallIn(int64_t num_rows, boost::dynamic_bitset<>& bs, std::vector<T>& vals) {
+    PlainOp(FLE_OP_IN, num_rows, bs, vals.empty() ? NULL : &vals[0], static_cast<int>(vals.size()));
+  }
+  struct PlainCached {
+    int op;
+    bool swapped;
+    std::vector<T> lits;
+    std::vector<uint64_t> bitmap;
+  };
+  // whole-page bitmap for (op, literals): one upload per page, one kernel per distinct leaf
+  const std::vector<uint64_t>* PlainBitmap(fle_ctx* ctx, int et, int op, const T* lits, int nlits, bool swapped) {
+    for (size_t i = 0; i < plain_cache_.size(); ++i) {
+      const PlainCached& c = plain_cache_[i];
+      if (c.op == op && c.swapped == swapped && static_cast<int>(c.lits.size()) == nlits &&
+          (nlits == 0 || memcmp(&c.lits[0], lits, sizeof(T) * nlits) == 0)) return &c.bitmap;
+    }
+    if (plain_values_ <= 0) return NULL;
+    const size_t bytes = static_cast<size_t>(plain_values_) * sizeof(T);
+    const size_t words = (static_cast<size_t>(plain_values_) + 63) / 64;
+    if (plain_dev_ == NULL) {
+      plain_dev_ = FleGpu::DeviceScratch(0, 60, bytes + 16);
+      if (plain_dev_ == NULL) return NULL;
+      if (FleGpu::Check(fle_h2d(ctx, plain_dev_, plain_data_, bytes), "fle_h2d(PLAIN page)") != FLE_OK) return NULL;
+    }
+    void* bm_dev = FleGpu::DeviceScratch(0, 61, words * 8 + 16);
+    if (bm_dev == NULL) return NULL;
+    int rc = fle_plain_eval_dev(ctx, plain_dev_, et, plain_values_, op, lits, nlits, swapped ? 1 : 0,
+                                static_cast<uint64_t*>(bm_dev), NULL);
+    if (FleGpu::Check(rc, "fle_plain_eval_dev") != FLE_OK) return NULL;
+    plain_cache_.push_back(PlainCached());
+    PlainCached& c = plain_cache_.back();
+    c.op = op;
+    c.swapped = swapped;
+    c.lits.assign(lits, lits + nlits);
+    c.bitmap.assign(words, 0);
+    if (FleGpu::Check(fle_d2h(ctx, &c.bitmap[0], bm_dev, words * 8), "fle_d2h(PLAIN bitmap)") != FLE_OK ||
+        FleGpu::Check(fle_ctx_sync(ctx), "fle_ctx_sync") != FLE_OK) {
+      plain_cache_.pop_back();
+      return NULL;
+    }
+    return &plain_cache_.back().bitmap;
+  }
+
   std::unique_ptr<DictDecoder<T> > dict_decoder_;
   std::vector<uint8_t> dict_copy_;
+  const uint8_t* plain_data_ = NULL;
+  int64_t plain_values_ = 0, plain_pos_ = 0;
+  void* plain_dev_ = NULL;
+  std::vector<PlainCached> plain_cache_;
   friend class HdfsParquetScanner;
 };
+
+template<typename T> inline int HdfsParquetScanner::ColumnReader<T>::PlainElemType() { return -1; }
+template<> inline int HdfsParquetScanner::ColumnReader<int32_t>::PlainElemType() { return FLE_T_INT32; }
+template<> inline int HdfsParquetScanner::ColumnReader<int64_t>::PlainElemType() { return FLE_T_INT64; }
+template<> inline int HdfsParquetScanner::ColumnReader<float>::PlainElemType() { return FLE_T_FLOAT; }
+template<> inline int HdfsParquetScanner::ColumnReader<double>::PlainElemType() { return FLE_T_DOUBLE; }
 
 // ---------------------------------------------------------------------------------------
 inline HdfsParquetScanner::~HdfsParquetScanner() {
@@ -367,7 +526,8 @@ inline Status HdfsParquetScanner::BaseColumnReader::ReadDataPage() {
     data_ += num_definition_bytes;
     data_size_ -= num_definition_bytes;
   }
-  if (!page_is_dictionary()) return Status("only FLE_DICTIONARY data pages are on the hot path");
+  if (!page_is_dictionary() && page_encoding_ != parquet_encoding::PLAIN)
+    return Status("unsupported data page encoding");
   // Data can be empty if the column contains all NULLs (:921)
   if (data_size_ != 0) return InitDataPage(data_, data_size_);
   return Status::OK();
@@ -381,16 +541,19 @@ inline int HdfsParquetScanner::BaseColumnReader::ReadDefinitionLevel() {  // :92
 }
 
 inline bool HdfsParquetScanner::BaseColumnReader::ReadValue(uint8_t* tuple, int skip_rows) {  // :1006-1026
+  // (the reference compares the level with max_def_level() unconditionally; for a REQUIRED column
+  //  ReadDefinitionLevel() returns 1 != 0, so every value reads as NULL -- kept under reference_compat)
+  const bool compat = FleGpu::reference_compat();
   int tmp_skip_rows = 0;
   for (int i = 0; i < skip_rows; ++i) {
     int definition_level = ReadDefinitionLevel();
     if (definition_level < 0) return false;
-    if (max_def_level() > 0 && definition_level != max_def_level()) continue;
+    if ((max_def_level() > 0 || compat) && definition_level != max_def_level()) continue;
     ++tmp_skip_rows;
   }
   int definition_level = ReadDefinitionLevel();
   if (definition_level < 0) return false;
-  if (max_def_level() > 0 && definition_level != max_def_level()) {
+  if ((max_def_level() > 0 || compat) && definition_level != max_def_level()) {
     tuple[null_offset_] = 1;  // tuple->SetNull(...)
     if (!SkipSlot(tmp_skip_rows)) return false;
     return true;
@@ -399,11 +562,12 @@ inline bool HdfsParquetScanner::BaseColumnReader::ReadValue(uint8_t* tuple, int 
 }
 
 inline bool HdfsParquetScanner::BaseColumnReader::SkipValue(int skip_rows) {  // :1028-1037
+  const bool compat = FleGpu::reference_compat();
   int tmp_skip_rows = 0;
   for (int i = 0; i < skip_rows; ++i) {
     int definition_level = ReadDefinitionLevel();
     if (definition_level < 0) return false;
-    if (max_def_level() > 0 && definition_level != max_def_level()) continue;
+    if ((max_def_level() > 0 || compat) && definition_level != max_def_level()) continue;
     ++tmp_skip_rows;
   }
   return SkipSlot(tmp_skip_rows);
@@ -569,6 +733,192 @@ inline bool HdfsParquetScanner::DevicePageSpan(std::vector<uint8_t>* rows, int64
   return true;
 }
 
+// ---------------------------------------------------------------------------------------
+// Row-group batch (see the file comment).  Page body framing as in ReadDataPage above.
+// ---------------------------------------------------------------------------------------
+inline bool HdfsParquetScanner::StartRowGroupUpload() {
+  if (batch_state_ != 0) return batch_state_ > 0;
+  batch_state_ = -1;
+  const int ncols = static_cast<int>(column_readers_.size());
+  if (!row_group_batch_ || !fused_enabled_ || !device_materialise_ || FleGpu::reference_compat()) return false;
+  if (ncols == 0 || ncols > FLE_MAX_COLS || simple_predicates_.empty()) return false;
+  const size_t npages = column_readers_[0]->pages().size();
+  if (npages == 0) return false;
+  // every column: fresh reader, dictionary pages only, the same rows per page as column 0, every page but
+  // the last a whole number of 64-row groups (the pages of a column are concatenated into one plane array)
+  struct PageView { const uint8_t* fle; int64_t fle_bytes; int bw; const uint8_t* def; int64_t def_bytes; int64_t rows; };
+  std::vector<std::vector<PageView> > views(ncols, std::vector<PageView>(npages));
+  int64_t total_rows = 0;
+  for (int c = 0; c < ncols; ++c) {
+    BaseColumnReader* r = column_readers_[c];
+    if (!r->fresh() || r->pages().size() != npages || r->max_def_level() > 1) return false;
+    for (size_t p = 0; p < npages; ++p) {
+      const DataPage& pg = r->pages()[p];
+      if (pg.encoding != parquet_encoding::FLE_DICTIONARY && pg.encoding != parquet_encoding::PLAIN_DICTIONARY) return false;
+      if (pg.num_values != column_readers_[0]->pages()[p].num_values || pg.num_values <= 0) return false;
+      if (p + 1 < npages && (pg.num_values & 63)) return false;
+      PageView& v = views[c][p];
+      const uint8_t* d = pg.data;
+      int64_t left = pg.size;
+      v.def = NULL;
+      v.def_bytes = 0;
+      v.rows = pg.num_values;
+      if (r->max_def_level() > 0) {
+        if (left < 4) return false;
+        int32_t nd = 0;
+        memcpy(&nd, d, 4);
+        if (nd <= 0 || nd > left - 4 || nd < (v.rows + 63) / 64 * 8) return false;
+        v.def = d + 4;
+        v.def_bytes = nd;
+        d += 4 + nd;
+        left -= 4 + nd;
+      }
+      if (left < 1) return false;  // all-NULL page
+      v.bw = d[0];
+      v.fle = d + 1;
+      v.fle_bytes = left - 1;
+      if (v.bw < 1 || v.bw > 32 || v.fle_bytes < (v.rows + 63) / 64 * v.bw * 8) return false;  // (a shorter stream means NULLs)
+      if (c == 0) total_rows += v.rows;
+    }
+  }
+  if (total_rows >= (int64_t(1) << 31)) return false;
+  batch_prog_ = FusedProgram();
+  if (!LowerPredicates(&batch_prog_)) return false;
+  fle_ctx* ctx = FleGpu::ctx();
+  if (ctx == NULL) return false;
+  batch_bank_ = FleGpu::NextBank();
+  batch_cols_.assign(ncols, BatchColumn());
+  batch_refs_.clear();
+  const int64_t total_groups = (total_rows + 63) / 64;
+  for (int c = 0; c < ncols; ++c) {
+    BaseColumnReader* r = column_readers_[c];
+    BatchColumn& bc = batch_cols_[c];
+    bc.bit_width = 0;
+    for (size_t p = 0; p < npages; ++p) bc.bit_width = std::max(bc.bit_width, views[c][p].bw);
+    // one upload per column chunk when its pages lie back to back in host memory (as they do in the I/O buffer
+    // a column chunk was read into), one per page otherwise
+    const uint8_t* lo = r->pages()[0].data;
+    const uint8_t* hi = lo;
+    int64_t sum = 0;
+    bool ascending = true;
+    for (size_t p = 0; p < npages; ++p) {
+      const DataPage& pg = r->pages()[p];
+      if (pg.data < hi) ascending = false;
+      lo = std::min(lo, pg.data);
+      hi = std::max(hi, pg.data + pg.size);
+      sum += pg.size;
+    }
+    const bool one_copy = ascending && (hi - lo) <= sum + sum / 4 + 4096;
+    const size_t image_bytes = one_copy ? static_cast<size_t>(hi - lo) : static_cast<size_t>(sum + 16 * npages);
+    bc.image_dev = FleGpu::DeviceScratch(batch_bank_, 3 * c, image_bytes + 64);
+    bc.planes_dev = FleGpu::DeviceScratch(batch_bank_, 3 * c + 1, static_cast<size_t>(total_groups) * bc.bit_width * 8 + 64);
+    int nd = 0, es = 0;
+    const void* dv = r->dict_values(&nd, &es);
+    bc.ndict = nd;
+    bc.dict_dev = FleGpu::DeviceScratch(batch_bank_, 3 * c + 2, static_cast<size_t>(std::max(nd, 1)) * es);
+    if (!bc.image_dev || !bc.planes_dev || !bc.dict_dev) return false;
+    if (nd > 0 && FleGpu::Check(fle_h2d_prefetch(ctx, bc.dict_dev, dv, static_cast<size_t>(nd) * es), "fle_h2d_prefetch(dict)") != FLE_OK) return false;
+    if (one_copy && FleGpu::Check(fle_h2d_prefetch(ctx, bc.image_dev, lo, image_bytes), "fle_h2d_prefetch(chunk)") != FLE_OK) return false;
+    int64_t g0 = 0;
+    size_t off = 0;
+    for (size_t p = 0; p < npages; ++p) {
+      const DataPage& pg = r->pages()[p];
+      const PageView& v = views[c][p];
+      size_t base;  // offset of the page body inside the device image
+      if (one_copy) {
+        base = static_cast<size_t>(pg.data - lo);
+      } else {
+        base = off;
+        if (FleGpu::Check(fle_h2d_prefetch(ctx, static_cast<uint8_t*>(bc.image_dev) + off, pg.data, pg.size), "fle_h2d_prefetch(page)") != FLE_OK) return false;
+        off += (static_cast<size_t>(pg.size) + 15) / 16 * 16;
+      }
+      fle_page_ref ref;
+      memset(&ref, 0, sizeof(ref));
+      const uint8_t* img = static_cast<const uint8_t*>(bc.image_dev) + base;
+      ref.src_dev = img + (v.fle - pg.data);
+      ref.src_bytes = static_cast<uint64_t>(v.fle_bytes);
+      ref.src_bit_width = v.bw;
+      ref.dst_bit_width = bc.bit_width;
+      ref.dst_dev = static_cast<uint8_t*>(bc.planes_dev) + static_cast<size_t>(g0) * bc.bit_width * 8;
+      ref.groups = (v.rows + 63) / 64;
+      if (v.def != NULL) {
+        ref.def_src_dev = img + (v.def - pg.data);
+        ref.def_bytes = static_cast<uint64_t>(v.def_bytes);
+      }
+      ref.rows = v.rows;
+      batch_refs_.push_back(ref);
+      g0 += ref.groups;
+    }
+  }
+  batch_rows_ = total_rows;
+  batch_state_ = 1;
+  return true;
+}
+
+inline bool HdfsParquetScanner::DeviceRowGroup(std::vector<uint8_t>* rows, int64_t* num_passed, int64_t* span_rows) {
+  if (!StartRowGroupUpload()) return false;
+  batch_state_ = -1;  // one shot: whatever happens below, the batch is not retried
+  fle_ctx* ctx = FleGpu::ctx();
+  if (ctx == NULL) return false;
+  const int ncols = static_cast<int>(column_readers_.size());
+  const int64_t n = batch_rows_, groups = (n + 63) / 64;
+  const int bank = batch_bank_;
+  uint64_t* bitmap_dev = static_cast<uint64_t*>(FleGpu::DeviceScratch(bank, 40, static_cast<size_t>(groups) * 8 + 64));
+  uint64_t* hdr_dev = static_cast<uint64_t*>(FleGpu::DeviceScratch(bank, 41, 64));  // [0] NULL rows, [1] survivors, [2] bad codes
+  uint64_t* hdr = static_cast<uint64_t*>(FleGpu::PinnedScratch(bank, 0, 64));
+  if (!bitmap_dev || !hdr_dev || !hdr) return false;
+  if (FleGpu::Check(fle_prefetch_fence(ctx), "fle_prefetch_fence") != FLE_OK) return false;
+  if (FleGpu::Check(fle_pages_gather_dev(ctx, &batch_refs_[0], static_cast<int>(batch_refs_.size()), hdr_dev), "fle_pages_gather_dev") != FLE_OK) return false;
+  std::vector<fle_col_desc> cols(ncols);
+  std::vector<fle_slot_desc> slots(ncols);
+  for (int c = 0; c < ncols; ++c) {
+    BaseColumnReader* r = column_readers_[c];
+    memset(&cols[c], 0, sizeof(fle_col_desc));
+    cols[c].planes = batch_cols_[c].planes_dev;
+    cols[c].bytes = static_cast<uint64_t>(groups) * batch_cols_[c].bit_width * 8;
+    cols[c].bit_width = batch_cols_[c].bit_width;
+    memset(&slots[c], 0, sizeof(fle_slot_desc));
+    slots[c].planes_dev = batch_cols_[c].planes_dev;
+    slots[c].bytes = cols[c].bytes;
+    slots[c].bit_width = batch_cols_[c].bit_width;
+    slots[c].slot_size = r->slot_size_;
+    slots[c].dict_dev = batch_cols_[c].dict_dev;
+    slots[c].ndict = batch_cols_[c].ndict;
+    slots[c].tuple_offset = r->tuple_offset_;
+  }
+  int rc = fle_eval_dev(ctx, &cols[0], ncols, &batch_prog_.nodes[0], static_cast<int>(batch_prog_.nodes.size()), 0, n, bitmap_dev, NULL);
+  if (rc == FLE_E_UNSUPPORTED) return false;
+  if (FleGpu::Check(rc, "fle_eval_dev(row group)") != FLE_OK) return false;
+  // tuples: room for every row (grow-only scratch; only the survivors' bytes come back)
+  uint8_t* tuples_dev = static_cast<uint8_t*>(FleGpu::DeviceScratch(bank, 42, static_cast<size_t>(n) * tuple_size_ + 64));
+  if (!tuples_dev) return false;
+  rc = fle_assemble_rows_dev(ctx, bitmap_dev, n, &slots[0], ncols, tuple_size_, tuples_dev, n, hdr_dev + 1, hdr_dev + 2);
+  if (FleGpu::Check(rc, "fle_assemble_rows_dev") != FLE_OK) return false;
+  if (FleGpu::Check(fle_d2h(ctx, hdr, hdr_dev, 24), "fle_d2h(counts)") != FLE_OK) return false;
+  if (FleGpu::Check(fle_ctx_sync(ctx), "fle_ctx_sync") != FLE_OK) return false;
+  if (hdr[0] != 0) return false;  // NULLs in the row group: the page-span / window paths handle them (nothing was consumed)
+  if (hdr[2] != 0) {
+    parse_status_ = Status("dictionary index out of range");
+    return false;
+  }
+  const uint64_t passed = hdr[1];
+  if (passed > 0) {
+    const size_t bytes = static_cast<size_t>(passed) * tuple_size_;
+    uint8_t* stage = static_cast<uint8_t*>(FleGpu::PinnedScratch(bank, 1, bytes));
+    if (!stage) return false;
+    if (FleGpu::Check(fle_d2h(ctx, stage, tuples_dev, bytes), "fle_d2h(tuples)") != FLE_OK) return false;
+    if (FleGpu::Check(fle_ctx_sync(ctx), "fle_ctx_sync") != FLE_OK) return false;
+    rows->insert(rows->end(), stage, stage + bytes);
+  }
+  for (int c = 0; c < ncols; ++c) column_readers_[c]->ConsumeAllPages();
+  fused_rows_ = 0;
+  ++fused_evals_;
+  ++row_group_batches_;
+  *num_passed = static_cast<int64_t>(passed);
+  *span_rows = n;
+  return true;
+}
+
 inline bool HdfsParquetScanner::BuildFusedSpan(const std::vector<int64_t>& page_pos) {
   const int ncols = static_cast<int>(column_readers_.size());
   if (ncols > FLE_MAX_COLS) return false;
@@ -659,8 +1009,18 @@ inline Status HdfsParquetScanner::AssembleRows(int64_t expected_rows_in_group, s
   boost::dynamic_bitset<> skip_bitset;
   std::vector<int> skip_rows;
   *num_passed = 0;
+  const bool compat = FleGpu::reference_compat();
+  if (rows_read == 0) {  // the whole row group as one batch
+    int64_t passed = 0, span = 0;
+    if (DeviceRowGroup(rows, &passed, &span)) {
+      *num_passed += passed;
+      rows_read += span;
+    } else if (!parse_status_.ok() || !FleGpu::ok()) {
+      return FleGpu::ok() ? parse_status_ : Status(FleGpu::message());
+    }
+  }
   while (rows_read < expected_rows_in_group) {
-    if (fused_enabled_ && device_materialise_) {
+    if (fused_enabled_ && device_materialise_ && !compat) {
       int64_t passed = 0, span = 0;
       if (DevicePageSpan(rows, &passed, &span)) {
         *num_passed += passed;
@@ -673,9 +1033,9 @@ inline Status HdfsParquetScanner::AssembleRows(int64_t expected_rows_in_group, s
     if (!EvalSimplePredicates(skip_bitset)) return parse_status_;
     if (skip_bitset.size() == 0) break;
     const int bitset_size = static_cast<int>(skip_bitset.size());
-    if (skip_bitset.count() == 0) {  // :1125-1131
+    if (skip_bitset.count() == 0) {  // :1125-1131 (the reference does not look at the result here)
       for (int c = 0; c < num_column_readers; ++c) {
-        if (!column_readers_[c]->SkipValue(bitset_size)) return Status("SkipValue failed");
+        if (!column_readers_[c]->SkipValue(bitset_size) && !compat) return Status("SkipValue failed");
       }
       rows_read += bitset_size;
       continue;
@@ -699,8 +1059,13 @@ inline Status HdfsParquetScanner::AssembleRows(int64_t expected_rows_in_group, s
       }
     }
     if (last_skip_rows != 0) {  // :1107-1113
-      for (int c = 0; c < num_column_readers; ++c) {
-        if (!column_readers_[c]->SkipValue(last_skip_rows)) return Status("SkipValue failed");
+      bool result = true;
+      for (int c = 0; c < num_column_readers; ++c) result = column_readers_[c]->SkipValue(last_skip_rows);
+      if (!result) {
+        // the reference: `if (!result) return parse_status_;` -- a Skip() that lands on the end of a page
+        // reports false there and the rest of the row group is dropped without an error
+        *num_passed += static_cast<int64_t>(skip_rows.size());
+        return compat ? parse_status_ : Status("SkipValue failed");
       }
     }
     *num_passed += static_cast<int64_t>(skip_rows.size());

@@ -1,18 +1,29 @@
-// Throughput of the drop-in column-reader batch interface (exec/hdfs-parquet-scanner.h) on one
-// Impala-shaped row group: three OPTIONAL FLE_DICTIONARY columns (def levels present, no NULLs),
-// host-resident page bodies, the TPC-H Q6 conjuncts attached as a SimplePredicate forest,
-// AssembleRows = EvalSimplePredicates window by window + materialisation of the survivors
-// (hdfs-parquet-scanner.cc:1101-1181).  Reports rows/s for the fused path (one GPU evaluation per
-// page span; survivors materialised on the device, or by ReadValue(skip) on the host from windows
-// sliced out of the cached bitmap) and for the reference-shaped per-leaf path
-// (one call per leaf and 1024-row window, still on the GPU), and checks both against a
-// row-at-a-time evaluation.
-//   scanner-bench [rows (default 4194304)] [rows per page (default 65536)] [repetitions (default 5)]
+// Throughput of the drop-in column-reader batch interface (exec/hdfs-parquet-scanner.h) on
+// Impala-shaped row groups: three OPTIONAL FLE_DICTIONARY columns (def levels present, no NULLs), the
+// TPC-H Q6 conjuncts attached as a SimplePredicate forest, AssembleRows = predicate evaluation +
+// materialisation of the survivors as tuples (hdfs-parquet-scanner.cc:1078-1275).
+//
+// The page bodies of a column chunk lie back to back (each behind a pseudo page header, so the FLE
+// sections start at odd offsets, as in a file) in one PINNED buffer -- what an integration gets by
+// allocating its I/O buffers with fle_host_alloc or pinning them with fle_host_register.
+//
+//   scanner-bench [--json] [--rows N] [--rows-per-page P] [--row-groups R] [--threads a,b,c] [--reps K]
+//
+// Reports, per thread count T: T scanner threads (one library context each, as the reference runs one
+// scanner per thread, hdfs-parquet-scanner.cc:1040), each scanning R row groups, row group k+1's upload
+// started before AssembleRows(k) (StartRowGroupUpload) -- rows/s and page bytes/s of the whole job; next
+// to it the same bytes copied pinned -> device and nothing else (the PCIe roofline of that job on this
+// box).  Single-threaded per-path numbers (row-group batch / page spans / host materialisation / per
+// leaf) and a byte-for-byte comparison of the tuples of all paths come first.
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
+#include <atomic>
 #include <chrono>
 #include <cstdio>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "exec/hdfs-parquet-scanner.h"
@@ -24,9 +35,12 @@ using std::vector;
 
 struct ColumnChunk {
   vector<uint8_t> dict_page;
-  vector<vector<uint8_t> > page_bodies;
+  uint8_t* image = NULL;  // pinned: [pseudo header][page body] ...
+  size_t image_bytes = 0;
   vector<HdfsParquetScanner::DataPage> pages;
 };
+
+static const int kPseudoHeaderBytes = 23;  // a thrift PageHeader of a data page is 20-odd bytes
 
 static ColumnChunk WriteColumn(const vector<int32_t>& values, int rows_per_page) {
   ColumnChunk cc;
@@ -39,6 +53,8 @@ static ColumnChunk WriteColumn(const vector<int32_t>& values, int rows_per_page)
   }
   cc.dict_page.resize(dict.dict_encoded_size());
   dict.WriteDict(&cc.dict_page[0]);
+  vector<vector<uint8_t> > bodies;
+  size_t total = 0;
   for (size_t p = 0; p < page_indices.size(); ++p) {
     const size_t rows = page_indices[p].size();
     vector<uint8_t> defbuf((rows / 64 + 3) * 8);
@@ -53,68 +69,223 @@ static ColumnChunk WriteColumn(const vector<int32_t>& values, int rows_per_page)
     const int data_len = dict.WriteData(&data[0], data.size(), page_indices[p]);
     if (data_len <= 0) { std::fprintf(stderr, "WriteData failed\n"); exit(2); }
     body.insert(body.end(), data.begin(), data.begin() + data_len);
-    cc.page_bodies.push_back(body);
+    total += kPseudoHeaderBytes + body.size();
+    bodies.push_back(body);
   }
-  size_t r0 = 0;
-  for (size_t p = 0; p < cc.page_bodies.size(); ++p) {
-    cc.pages.push_back(HdfsParquetScanner::DataPage(&cc.page_bodies[p][0], cc.page_bodies[p].size(), page_indices[p].size()));
-    r0 += page_indices[p].size();
+  void* pinned = NULL;
+  if (fle_host_alloc(total + 64, &pinned) != FLE_OK) { std::fprintf(stderr, "fle_host_alloc failed\n"); exit(2); }
+  cc.image = static_cast<uint8_t*>(pinned);
+  cc.image_bytes = total;
+  size_t off = 0;
+  for (size_t p = 0; p < bodies.size(); ++p) {
+    memset(cc.image + off, 0x15, kPseudoHeaderBytes);
+    off += kPseudoHeaderBytes;
+    memcpy(cc.image + off, &bodies[p][0], bodies[p].size());
+    cc.pages.push_back(HdfsParquetScanner::DataPage(cc.image + off, bodies[p].size(), page_indices[p].size()));
+    off += bodies[p].size();
   }
   return cc;
 }
 
+struct Workload {
+  ColumnChunk c[3];
+  GeOperate<int32_t> ge0{0, 8730};
+  LeOperate<int32_t> le0{0, 9094};
+  AndOperate between0{&ge0, &le0};
+  GeOperate<int32_t> ge1{1, 5};
+  LeOperate<int32_t> le1{1, 7};
+  LtOperate<int32_t> lt2{2, 24};
+  int n = 0;
+  int64_t want = 0;
+  size_t bytes = 0;
+
+  void Attach(HdfsParquetScanner* s) {
+    for (int k = 0; k < 3; ++k) s->AddColumn<int32_t>(1, &c[k].dict_page[0], c[k].dict_page.size(), c[k].pages);
+    s->AddSimplePredicate(&between0);
+    s->AddSimplePredicate(&ge1);
+    s->AddSimplePredicate(&le1);
+    s->AddSimplePredicate(&lt2);
+  }
+};
+
+static double Now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// one scanner thread: R row groups, the next one's upload in flight while the current one is assembled
+static bool ScanRowGroups(Workload* w, int row_groups, int64_t* passed_total, int64_t* batches) {
+  std::unique_ptr<HdfsParquetScanner> cur(new HdfsParquetScanner()), next;
+  w->Attach(cur.get());
+  cur->StartRowGroupUpload();
+  vector<uint8_t> rows;
+  *passed_total = 0;
+  *batches = 0;
+  for (int k = 0; k < row_groups; ++k) {
+    if (k + 1 < row_groups) {
+      next.reset(new HdfsParquetScanner());
+      w->Attach(next.get());
+      next->StartRowGroupUpload();
+    }
+    rows.clear();
+    int64_t passed = 0;
+    Status st = cur->AssembleRows(w->n, &rows, &passed);
+    if (!st.ok() || passed != w->want) {
+      std::fprintf(stderr, "scan failed: %s passed %lld want %lld\n", st.GetErrorMsg().c_str(), (long long)passed, (long long)w->want);
+      return false;
+    }
+    *passed_total += passed;
+    *batches += cur->row_group_batches();
+    cur.swap(next);
+  }
+  return true;
+}
+
+// the same bytes, pinned -> device, nothing else
+static bool CopyRowGroups(Workload* w, int row_groups) {
+  fle_ctx* ctx = FleGpu::ctx();
+  if (!ctx) return false;
+  void* dev[3];
+  for (int k = 0; k < 3; ++k) dev[k] = FleGpu::DeviceScratch(0, 50 + k, w->c[k].image_bytes + 64);
+  for (int r = 0; r < row_groups; ++r) {
+    for (int k = 0; k < 3; ++k)
+      if (fle_h2d_prefetch(ctx, dev[k], w->c[k].image, w->c[k].image_bytes) != FLE_OK) return false;
+    if (fle_prefetch_fence(ctx) != FLE_OK || fle_ctx_sync(ctx) != FLE_OK) return false;
+  }
+  return true;
+}
+
+// fn(t, false) once per thread before the clock starts (context creation, scratch growth, kernel load),
+// then fn(t, true) timed
+template <typename Fn>
+static double RunThreads(int threads, Fn fn, bool* ok) {
+  std::atomic<int> ready(0), go(0);
+  std::atomic<bool> all_ok(true);
+  vector<std::thread> th;
+  vector<double> done_at(threads, 0.0);  // (thread exit frees the thread's context and scratch: not part of the job)
+  for (int t = 0; t < threads; ++t) {
+    th.emplace_back([&, t]() {
+      if (!fn(t, false)) all_ok.store(false);
+      ready.fetch_add(1);
+      while (!go.load()) std::this_thread::yield();
+      if (!fn(t, true)) all_ok.store(false);
+      done_at[t] = Now();
+    });
+  }
+  while (ready.load() < threads) std::this_thread::yield();
+  const double t0 = Now();
+  go.store(1);
+  for (auto& x : th) x.join();
+  double s = 0;
+  for (int t = 0; t < threads; ++t) s = std::max(s, done_at[t] - t0);
+  *ok = all_ok.load();
+  return s;
+}
+
 int main(int argc, char** argv) {
-  const int n = argc > 1 ? atoi(argv[1]) : 4194304;
-  const int rows_per_page = argc > 2 ? atoi(argv[2]) : 65536;
-  const int reps = argc > 3 ? atoi(argv[3]) : 5;
+  int n = 4194304, rows_per_page = 65536, reps = 5, row_groups = 8;
+  vector<int> thread_counts = {1, 2, 4};
+  bool json = false;
+  for (int i = 1; i < argc; ++i) {
+    const std::string a = argv[i];
+    if (a == "--json") json = true;
+    else if (a == "--rows" && i + 1 < argc) n = atoi(argv[++i]);
+    else if (a == "--rows-per-page" && i + 1 < argc) rows_per_page = atoi(argv[++i]);
+    else if (a == "--reps" && i + 1 < argc) reps = atoi(argv[++i]);
+    else if (a == "--row-groups" && i + 1 < argc) row_groups = atoi(argv[++i]);
+    else if (a == "--threads" && i + 1 < argc) {
+      thread_counts.clear();
+      for (char* tok = strtok(argv[++i], ","); tok; tok = strtok(NULL, ",")) thread_counts.push_back(atoi(tok));
+    } else if (i == 1 && atoi(argv[1]) > 0) {  // old positional form: rows [rows per page [reps]]
+      n = atoi(argv[1]);
+      if (argc > 2) rows_per_page = atoi(argv[2]);
+      if (argc > 3) reps = atoi(argv[3]);
+      break;
+    }
+  }
+  (void)json;
+  Workload w;
+  w.n = n;
   srand(7);
   vector<int32_t> shipdate(n), discount(n), quantity(n);
-  int64_t want = 0;
   for (int i = 0; i < n; ++i) {
     shipdate[i] = 8000 + rand() % 2526;
     discount[i] = rand() % 11;
     quantity[i] = 1 + rand() % 50;
-    want += shipdate[i] >= 8730 && shipdate[i] <= 9094 && discount[i] >= 5 && discount[i] <= 7 && quantity[i] < 24;
+    w.want += shipdate[i] >= 8730 && shipdate[i] <= 9094 && discount[i] >= 5 && discount[i] <= 7 && quantity[i] < 24;
   }
-  ColumnChunk c0 = WriteColumn(shipdate, rows_per_page), c1 = WriteColumn(discount, rows_per_page), c2 = WriteColumn(quantity, rows_per_page);
-  size_t bytes = 0;
-  for (const ColumnChunk* c : {&c0, &c1, &c2})
-    for (const auto& b : c->page_bodies) bytes += b.size();
-  std::printf("{\"rows\": %d, \"rows_per_page\": %d, \"page_bytes_total\": %zu, \"survivors\": %lld", n, rows_per_page, bytes, (long long)want);
-  for (int mode = 2; mode >= 0; --mode) {  // 2: fused + device-resident page spans, 1: fused + host materialisation, 0: per leaf
-    const int fused = mode >= 1;
+  w.c[0] = WriteColumn(shipdate, rows_per_page);
+  w.c[1] = WriteColumn(discount, rows_per_page);
+  w.c[2] = WriteColumn(quantity, rows_per_page);
+  for (int k = 0; k < 3; ++k) w.bytes += w.c[k].image_bytes;
+  std::printf("{\"rows\": %d, \"rows_per_page\": %d, \"pages_per_column\": %zu, \"page_bytes_total\": %zu, \"survivors\": %lld, "
+              "\"page_memory\": \"pinned (fle_host_alloc), pages of a column chunk back to back behind %d-byte pseudo headers\"",
+              n, rows_per_page, w.c[0].pages.size(), w.bytes, (long long)w.want, kPseudoHeaderBytes);
+
+  // ---- one thread, one row group, path by path; the tuples of every path must be identical ---------------
+  vector<uint8_t> reference_rows;
+  for (int mode = 3; mode >= 0; --mode) {  // 3 row-group batch, 2 page spans on the device, 1 fused + host materialisation, 0 per leaf
     double best = 1e30;
     int64_t passed = 0, evals = 0, windows = 0;
-    for (int r = 0; r < reps + 1; ++r) {  // first repetition = warm-up (context creation, kernel load)
+    const int mode_reps = mode == 0 ? 1 : reps;
+    for (int r = 0; r < mode_reps + 1; ++r) {  // first repetition = warm-up (context creation, kernel load)
       HdfsParquetScanner scanner;
-      int i0 = scanner.AddColumn<int32_t>(1, &c0.dict_page[0], c0.dict_page.size(), c0.pages);
-      int i1 = scanner.AddColumn<int32_t>(1, &c1.dict_page[0], c1.dict_page.size(), c1.pages);
-      int i2 = scanner.AddColumn<int32_t>(1, &c2.dict_page[0], c2.dict_page.size(), c2.pages);
-      GeOperate<int32_t> ge0(i0, 8730);
-      LeOperate<int32_t> le0(i0, 9094);
-      AndOperate between0(&ge0, &le0);
-      GeOperate<int32_t> ge1(i1, 5);
-      LeOperate<int32_t> le1(i1, 7);
-      LtOperate<int32_t> lt2(i2, 24);
-      scanner.AddSimplePredicate(&between0);
-      scanner.AddSimplePredicate(&ge1);
-      scanner.AddSimplePredicate(&le1);
-      scanner.AddSimplePredicate(&lt2);
-      scanner.set_fused(fused != 0);
-      scanner.set_device_materialise(mode == 2);
+      w.Attach(&scanner);
+      scanner.set_fused(mode >= 1);
+      scanner.set_device_materialise(mode >= 2);
+      scanner.set_row_group_batch(mode == 3);
       vector<uint8_t> rows;
-      const auto t0 = std::chrono::steady_clock::now();
+      const double t0 = Now();
       Status st = scanner.AssembleRows(n, &rows, &passed);
-      const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-      if (!st.ok() || passed != want) { std::fprintf(stderr, "scan failed: passed %lld want %lld\n", (long long)passed, (long long)want); return 1; }
+      const double s = Now() - t0;
+      if (!st.ok() || passed != w.want) { std::fprintf(stderr, "scan failed: passed %lld want %lld\n", (long long)passed, (long long)w.want); return 1; }
+      if (mode == 3 && scanner.row_group_batches() != 1) { std::fprintf(stderr, "row-group batch path did not run\n"); return 1; }
+      if (r == 0) {
+        if (reference_rows.empty()) reference_rows = rows;
+        else if (rows != reference_rows) { std::fprintf(stderr, "tuples of path %d differ from the row-group batch path\n", mode); return 1; }
+      }
       if (r > 0 && s < best) best = s;
       evals = scanner.fused_evals();
       windows = scanner.leaf_windows();
     }
-    std::printf(", \"%s\": {\"ms\": %.3f, \"rows_per_s\": %.4g, \"fused_evals\": %lld, \"leaf_windows\": %lld}",
-                mode == 2 ? "device_page_spans" : (mode == 1 ? "fused_host_materialise" : "per_leaf"),
-                best * 1e3, n / best, (long long)evals, (long long)windows);
+    std::printf(", \"%s\": {\"ms\": %.3f, \"rows_per_s\": %.4g, \"page_GBps\": %.3f, \"fused_evals\": %lld, \"leaf_windows\": %lld}",
+                mode == 3 ? "row_group_batch" : mode == 2 ? "device_page_spans" : (mode == 1 ? "fused_host_materialise" : "per_leaf"),
+                best * 1e3, n / best, w.bytes / best / 1e9, (long long)evals, (long long)windows);
   }
-  std::printf("}\n");
+  std::printf(", \"tuples_identical_across_paths\": true");
+
+  // ---- T scanner threads x R row groups ---------------------------------------------------------------------
+  std::printf(", \"row_groups_per_thread\": %d, \"threads\": [", row_groups);
+  double best_frac = 0, best_rows_per_s = 0, best_gbps = 0, best_peak = 0;
+  int best_threads = 0;
+  for (size_t ti = 0; ti < thread_counts.size(); ++ti) {
+    const int T = thread_counts[ti];
+    bool ok = true;
+    double scan_s = 1e30, copy_s = 1e30;
+    for (int r = 0; r < 3; ++r) {
+      bool ok1 = true;
+      const double s = RunThreads(T, [&](int, bool timed) {
+        int64_t p, b;
+        const int rg = timed ? row_groups : 2;
+        return ScanRowGroups(&w, rg, &p, &b) && b == rg;
+      }, &ok1);
+      ok = ok && ok1;
+      if (r > 0) scan_s = std::min(scan_s, s);
+      const double c = RunThreads(T, [&](int, bool timed) { return CopyRowGroups(&w, timed ? row_groups : 1); }, &ok1);
+      ok = ok && ok1;
+      if (r > 0) copy_s = std::min(copy_s, c);
+    }
+    if (!ok) { std::fprintf(stderr, "threaded scan failed\n"); return 1; }
+    const double total_rows = (double)n * row_groups * T, total_bytes = (double)w.bytes * row_groups * T;
+    std::printf("%s{\"threads\": %d, \"ms\": %.3f, \"rows_per_s\": %.4g, \"page_GBps\": %.3f, \"h2d_only_GBps\": %.3f, \"frac_of_h2d\": %.3f}",
+                ti ? ", " : "", T, scan_s * 1e3, total_rows / scan_s, total_bytes / scan_s / 1e9, total_bytes / copy_s / 1e9, copy_s / scan_s);
+    if (copy_s / scan_s > best_frac) {
+      best_frac = copy_s / scan_s;
+      best_rows_per_s = total_rows / scan_s;
+      best_gbps = total_bytes / scan_s / 1e9;
+      best_peak = total_bytes / copy_s / 1e9;
+      best_threads = T;
+    }
+  }
+  std::printf("], \"best\": {\"threads\": %d, \"rows_per_s\": %.4g, \"page_GBps\": %.3f, \"h2d_only_GBps\": %.3f, \"frac_of_h2d\": %.3f}}\n",
+              best_threads, best_rows_per_s, best_gbps, best_peak, best_frac);
+  for (int k = 0; k < 3; ++k) fle_host_free(w.c[k].image);
   return 0;
 }

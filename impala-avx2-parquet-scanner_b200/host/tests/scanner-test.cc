@@ -99,7 +99,7 @@ static bool RowPasses(const Table& t, int r) {
 
 static void RunScan(const Table& t, bool nullable, int pp0, int pp1, int pp2, bool fused, vector<uint8_t>* rows,
                     int64_t* passed, int64_t* fused_evals, int64_t* leaf_windows, int* tuple_size, int offs[3],
-                    bool device = true, int64_t* device_spans = NULL) {
+                    bool device = true, int64_t* device_spans = NULL, bool batch = true, int64_t* batches = NULL) {
   ColumnChunk c0 = WriteColumn(t.shipdate, t.nn_shipdate, pp0, nullable);
   ColumnChunk c1 = WriteColumn(t.discount, t.nn_discount, pp1, nullable);
   ColumnChunk c2 = WriteColumn(t.quantity, t.nn_quantity, pp2, nullable);
@@ -122,9 +122,11 @@ static void RunScan(const Table& t, bool nullable, int pp0, int pp1, int pp2, bo
   scanner.AddSimplePredicate(&lt2);
   scanner.set_fused(fused);
   scanner.set_device_materialise(device);
+  scanner.set_row_group_batch(batch);
   Status st = scanner.AssembleRows(t.n, rows, passed);
   EXPECT_TRUE(st.ok());
   if (device_spans) *device_spans = scanner.device_spans();
+  if (batches) *batches = scanner.row_group_batches();
   *fused_evals = scanner.fused_evals();
   *leaf_windows = scanner.leaf_windows();
   *tuple_size = scanner.tuple_size();
@@ -152,6 +154,15 @@ static void CheckScan(const Table& t, bool nullable, int pp0, int pp1, int pp2, 
     EXPECT_EQ(spans_h, 0);
     EXPECT_EQ(passed_h, passed_f);
     EXPECT_TRUE(rows_h == rows_f);
+  }
+  {  // ... and as the page-span path with the whole-row-group batch switched off
+    vector<uint8_t> rows_s;
+    int64_t passed_s = 0, fe4 = 0, lw4 = 0, spans_s = 0, batches_s = 0;
+    int ts4 = 0, offs4[3];
+    RunScan(tt, nullable, pp0, pp1, pp2, true, &rows_s, &passed_s, &fe4, &lw4, &ts4, offs4, true, &spans_s, false, &batches_s);
+    EXPECT_EQ(batches_s, 0);
+    EXPECT_EQ(passed_s, passed_f);
+    EXPECT_TRUE(rows_s == rows_f);
   }
   if (expect_fused) { EXPECT_TRUE(fe > 0); EXPECT_EQ(lw, 0); }
   EXPECT_EQ(passed_f, passed_l);
@@ -225,6 +236,147 @@ TEST(Scanner, OrAndInTree) {
     EXPECT_EQ(passed, want);
     if (fused) EXPECT_TRUE(scanner.fused_evals() > 0);
   }
+}
+
+// the whole row group as ONE batch: equal pages across the columns, no NULLs (def levels present or not)
+TEST(Scanner, RowGroupBatch) {
+  for (int nullable = 0; nullable < 2; ++nullable) {
+    Table t = MakeTable(64 * 5000 + 29, 0, 41 + nullable);
+    vector<uint8_t> rows;
+    int64_t passed = 0, fe = 0, lw = 0, spans = 0, batches = 0;
+    int ts = 0, offs[3];
+    RunScan(t, nullable != 0, 64 * 300, 64 * 300, 64 * 300, true, &rows, &passed, &fe, &lw, &ts, offs, true, &spans, true, &batches);
+    EXPECT_EQ(batches, 1);
+    EXPECT_EQ(spans, 0);
+    EXPECT_EQ(lw, 0);
+    int64_t want = 0;
+    for (int r = 0; r < t.n; ++r) want += RowPasses(t, r);
+    EXPECT_EQ(passed, want);
+  }
+  {  // NULLs present: the batch notices (definition levels are counted on the device) and hands over, nothing is lost
+    Table t = MakeTable(64 * 5000 + 29, 0.01, 43);
+    vector<uint8_t> rows;
+    int64_t passed = 0, fe = 0, lw = 0, spans = 0, batches = 0;
+    int ts = 0, offs[3];
+    RunScan(t, true, 64 * 300, 64 * 300, 64 * 300, true, &rows, &passed, &fe, &lw, &ts, offs, true, &spans, true, &batches);
+    EXPECT_EQ(batches, 0);
+    int64_t want = 0;
+    for (int r = 0; r < t.n; ++r) want += RowPasses(t, r);
+    EXPECT_EQ(passed, want);
+  }
+}
+
+// PLAIN data pages (a column that overflowed the dictionary, hdfs-parquet-table-writer.cc:276-279) next to a
+// dictionary column: ParquetPlainEncoder::Eq..In (parquet-common.h:197-255)
+TEST(Scanner, PlainPages) {
+  const int n = 64 * 900 + 11, per_page = 20000;
+  srand(77);
+  vector<int32_t> price(n), qty(n);
+  vector<bool> nn(n, true);
+  for (int i = 0; i < n; ++i) { price[i] = rand() % 1000000; qty[i] = 1 + rand() % 50; }
+  for (int compat = 0; compat < 2; ++compat) {
+    FleGpu::SetReferenceCompat(compat != 0);
+    ColumnChunk cq = WriteColumn(qty, nn, per_page, true);
+    ColumnChunk cp;  // PLAIN: [int32 num_def_bytes][def levels][values back to back], no dictionary page
+    for (int r0 = 0; r0 < n; r0 += per_page) {
+      const int m = std::min(per_page, n - r0);
+      vector<uint8_t> defbuf((m / 64 + 3) * 8);
+      FleEncoder def_levels(&defbuf[0], defbuf.size(), 1);
+      for (int i = 0; i < m; ++i) def_levels.Put(1);
+      def_levels.Flush();
+      int32_t nd = def_levels.len();
+      vector<uint8_t> body(4 + nd);
+      memcpy(&body[0], &nd, 4);
+      memcpy(&body[4], def_levels.buffer(), nd);
+      body.insert(body.end(), reinterpret_cast<const uint8_t*>(&price[r0]), reinterpret_cast<const uint8_t*>(&price[r0]) + 4 * m);
+      cp.page_bodies.push_back(body);
+    }
+    for (size_t p = 0; p < cp.page_bodies.size(); ++p) {
+      HdfsParquetScanner::DataPage pg(&cp.page_bodies[p][0], cp.page_bodies[p].size(),
+                                      std::min(per_page, n - (int)p * per_page));
+      pg.encoding = parquet_encoding::PLAIN;
+      cp.pages.push_back(pg);
+    }
+    HdfsParquetScanner scanner;
+    int ip = scanner.AddColumn<int32_t>(1, NULL, 0, cp.pages);
+    int iq = scanner.AddColumn<int32_t>(1, &cq.dict_page[0], cq.dict_page.size(), cq.pages);
+    LtOperate<int32_t> lt_price(ip, 30000);
+    LtOperate<int32_t> lt_qty(iq, 24);
+    scanner.AddSimplePredicate(&lt_price);
+    scanner.AddSimplePredicate(&lt_qty);
+    vector<uint8_t> rows;
+    int64_t passed = 0;
+    Status st = scanner.AssembleRows(n, &rows, &passed);
+    EXPECT_TRUE(st.ok());
+    // default: `price < 30000`; reference_compat: the reference's generic template evaluates `30000 < price`
+    // (parquet-common.h:214)
+    int64_t want = 0, bad = 0;
+    for (int r = 0; r < n; ++r) {
+      const bool pass = (compat ? 30000 < price[r] : price[r] < 30000) && qty[r] < 24;
+      if (!pass) continue;
+      if (want < passed) {
+        const uint8_t* tuple = &rows[want * scanner.tuple_size()];
+        int32_t a, b;
+        memcpy(&a, tuple + scanner.slot_offset(ip), 4);
+        memcpy(&b, tuple + scanner.slot_offset(iq), 4);
+        bad += !(a == price[r] && b == qty[r] && tuple[0] == 0 && tuple[1] == 0);
+      }
+      ++want;
+    }
+    EXPECT_EQ(passed, want);
+    EXPECT_EQ(bad, 0);
+    std::printf("    compat=%d plain pages: %lld survivors\n", compat, (long long)passed);
+  }
+  FleGpu::SetReferenceCompat(false);
+}
+
+// The deviations DESIGN.md lists, pinned in both modes (the reference lines are cited in util/fle-gpu-context.h)
+TEST(Scanner, ReferenceCompatSwitch) {
+  // 1. Skip() landing exactly on the end of the data (fle-encoding.h:381-402)
+  const int bw = 7, n = 64 * 5;
+  vector<uint8_t> buf((n / 64 + 2) * bw * 8);
+  FleEncoder enc(&buf[0], buf.size(), bw);
+  for (int i = 0; i < n; ++i) EXPECT_TRUE(enc.Put(i % 100));
+  enc.Flush();
+  for (int compat = 0; compat < 2; ++compat) {
+    FleGpu::SetReferenceCompat(compat != 0);
+    FleDecoder dec(&buf[0], (n / 64) * bw * 8, bw);
+    EXPECT_TRUE(dec.Skip(n - 64));
+    EXPECT_EQ((int)dec.Skip(64), compat ? 0 : 1);
+  }
+  // 2. a row group whose pages hold a multiple of 64 values: the reference's AssembleRows stops at the first page
+  //    whose trailing Skip lands on the page end (hdfs-parquet-scanner.cc:1107-1113) and reports success
+  Table t = MakeTable(64 * 64, 0, 5);
+  t.quantity.assign(t.n, 1);  // every row passes `quantity < 24` ...
+  for (int r = 0; r < t.n; ++r) if (r % 1024 >= 1000) t.quantity[r] = 40;  // ... except the tail of every window
+  vector<bool> all(t.n, true);
+  for (int compat = 0; compat < 2; ++compat) {
+    FleGpu::SetReferenceCompat(compat != 0);
+    ColumnChunk c = WriteColumn(t.quantity, all, 64 * 32, true);  // two pages of 2048 rows
+    HdfsParquetScanner scanner;
+    int i0 = scanner.AddColumn<int32_t>(1, &c.dict_page[0], c.dict_page.size(), c.pages);
+    LtOperate<int32_t> lt(i0, 24);
+    scanner.AddSimplePredicate(&lt);
+    vector<uint8_t> rows;
+    int64_t passed = 0;
+    EXPECT_TRUE(scanner.AssembleRows(t.n, &rows, &passed).ok());
+    int64_t want_all = 0, want_first_page = 0;
+    for (int r = 0; r < t.n; ++r) { want_all += t.quantity[r] < 24; if (r < 64 * 32) want_first_page += t.quantity[r] < 24; }
+    EXPECT_EQ(passed, compat ? want_first_page : want_all);
+  }
+  // 3. the data page's width byte (dict-encoding.h:438-444): Log2(max index + 1) vs the width the data is packed with
+  for (int compat = 0; compat < 2; ++compat) {
+    FleGpu::SetReferenceCompat(compat != 0);
+    DictEncoder<int32_t> dict(4);
+    vector<int> first_page, second_page;
+    for (int v = 0; v < 40; ++v) dict.Put(1000 - v, v < 3 ? first_page : second_page);  // page 1 sees 3 of 40 entries
+    vector<uint8_t> dpage(dict.dict_encoded_size());
+    dict.WriteDict(&dpage[0]);
+    vector<uint8_t> data(1 + 3 * dict.bit_width() * 8);
+    EXPECT_TRUE(dict.WriteData(&data[0], data.size(), first_page) > 0);
+    EXPECT_EQ((int)data[0], compat ? 2 : dict.bit_width());  // Log2(2 + 1) = 2; the data is packed with 6 bits either way
+  }
+  FleGpu::SetReferenceCompat(false);
 }
 
 int main() { return RunAllTests(); }

@@ -91,8 +91,11 @@ class DictEncoderBase {
     // (:438-444) although the data is packed with bit_width() (:432); a page that has not
     // seen the newest dictionary entries would then be decoded with the wrong width.  The
     // header written here is the width the data was actually packed with.
-    (void)max_indice;
-    *buffer = static_cast<uint8_t>(bit_width());
+    if (FleGpu::reference_compat()) {  // byte for byte what the reference writes (:438-444)
+      *buffer = max_indice == -1 ? 0 : (max_indice == 0 ? 1 : static_cast<uint8_t>(FleLog2Ceil(max_indice + 1)));
+    } else {
+      *buffer = static_cast<uint8_t>(bit_width());
+    }
     encoder.Flush();
     return 1 + encoder.len();
   }

@@ -24,7 +24,8 @@
 // written as 0 (the reference leaves stale staging bytes there, which are never decoded);
 // a group that does not fit entirely inside the buffer is treated as the end of data (the
 // reference would read past the buffer); predicate rows past the end of the buffer read
-// as "no match"; Skip() that lands exactly on the end of the data returns true.
+// as "no match"; Skip() that lands exactly on the end of the data returns true (FleGpu::SetReferenceCompat(true)
+// restores the reference's `false`).
 #ifndef IMPALA_FLE_ENCODING_H
 #define IMPALA_FLE_ENCODING_H
 
@@ -269,6 +270,7 @@ inline bool FleDecoder::Get(T* val, int skip_rows) {  // fle-encoding.h:344-379
 
 inline bool FleDecoder::Skip(int skip_rows) {  // :381-402
   if (Advance(skip_rows)) return true;
+  if (FleGpu::reference_compat()) return false;  // exactly the reference: false at the end of the data
   // Landing exactly on the end of the data is a successful skip here.  (The reference returns
   // false in that case, and its AssembleRows then silently drops the rest of the row group
   // whenever a page holds a multiple of 64 values, hdfs-parquet-scanner.cc:1107-1113.)
@@ -321,8 +323,12 @@ inline const std::vector<uint64_t>* FleDecoder::WholeBufferBitmap(int op, const 
   memset(&node, 0, sizeof(node));
   node.op = op;
   node.col = 0;
-  node.code = nlits > 0 ? lits[0] : 0;
-  node.codes = c.lits.empty() ? NULL : &c.lits[0];
+  // only the low bit_width bits of a literal take part in the plane algebra (fle-encoding.h:7965-7971)
+  const uint64_t lit_mask = bit_width_ >= 64 ? ~uint64_t(0) : ((uint64_t(1) << bit_width_) - 1);
+  std::vector<uint64_t> masked(c.lits);
+  for (size_t i = 0; i < masked.size(); ++i) masked[i] &= lit_mask;
+  node.code = nlits > 0 ? masked[0] : 0;
+  node.codes = masked.empty() ? NULL : &masked[0];
   node.ncodes = nlits;
   int rc = fle_eval(ctx, &col, 1, &node, 1, 0, num_groups_ * 64, &c.bitmap[0], NULL);
   if (FleGpu::Check(rc, "fle_eval") != FLE_OK) {

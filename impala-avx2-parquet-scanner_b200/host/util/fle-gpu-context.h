@@ -11,9 +11,11 @@
 #ifndef FLE_B200_HOST_GPU_CONTEXT_H
 #define FLE_B200_HOST_GPU_CONTEXT_H
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <vector>
 
 #include "fle_b200.h"
 
@@ -30,8 +32,43 @@ class FleGpu {
       int rc = fle_ctx_create(dev ? std::atoi(dev) : 0, NULL, &h.ctx);
       if (rc != FLE_OK) Fail(rc, "fle_ctx_create");
     }
+    const int want = reference_compat() ? 1 : 0;
+    if (h.ctx && h.compat_applied != want) {
+      fle_ctx_set_option(h.ctx, "reference_compat", want);
+      h.compat_applied = want;
+    }
     return h.ctx;
   }
+
+  // Process-wide switch (also FLE_B200_REFERENCE_COMPAT=1): reproduce the reference EXACTLY where the
+  // drop-ins deliberately differ from it --
+  //   FleDecoder::Skip() landing on the end of the data returns false (fle-encoding.h:381-402), and
+  //     AssembleRows then drops the rest of the row group (hdfs-parquet-scanner.cc:1107-1113);
+  //   DictEncoder::WriteData(buf, len, indices) stores Log2(max_indice + 1) in the page's width byte
+  //     (dict-encoding.h:438-444) although the data is packed with bit_width();
+  //   ReadValue()/SkipValue() compare the definition level with max_def_level() even for REQUIRED columns,
+  //     whose ReadDefinitionLevel() returns 1: every value becomes NULL (hdfs-parquet-scanner.cc:1006-1037);
+  //   PLAIN pages: `literal OP value` operand order, In() a no-op, no NULL handling (parquet-common.h:197-255,
+  //     hdfs-parquet-scanner.cc:346-349);
+  //   predicate literals >= 2^bit_width keep only their low bits (library option "reference_compat").
+  static bool reference_compat() {
+    std::atomic<int>& f = compat_flag();
+    int v = f.load(std::memory_order_relaxed);
+    if (v < 0) {
+      const char* e = std::getenv("FLE_B200_REFERENCE_COMPAT");
+      v = (e && std::atoi(e) != 0) ? 1 : 0;
+      f.store(v, std::memory_order_relaxed);
+    }
+    return v != 0;
+  }
+  static void SetReferenceCompat(bool on) { compat_flag().store(on ? 1 : 0, std::memory_order_relaxed); }
+
+  // Grow-only scratch of the calling thread, recycled between scanners (a scanner lives for one row
+  // group; allocating per scanner costs more than scanning).  Two banks, so that row group k+1 can be
+  // uploaded while row group k is still being evaluated.  Freed at thread exit.
+  static void* DeviceScratch(int bank, size_t slot, size_t bytes) { return holder().Scratch(bank, slot, bytes, false); }
+  static void* PinnedScratch(int bank, size_t slot, size_t bytes) { return holder().Scratch(bank, slot, bytes, true); }
+  static int NextBank() { return holder().next_bank++ & 1; }
 
   // Records and returns rc; rc != FLE_OK marks the thread's status as failed.
   static int Check(int rc, const char* what) {
@@ -48,15 +85,50 @@ class FleGpu {
   }
 
  private:
+  struct Buf {
+    void* p = NULL;
+    size_t bytes = 0;
+  };
   struct Holder {
     fle_ctx* ctx = NULL;
     bool tried = false;
     int status = FLE_OK;
+    int compat_applied = 0;
+    int next_bank = 0;
     std::string message;
+    std::vector<Buf> dev[2], pinned[2];
+    void* Scratch(int bank, size_t slot, size_t bytes, bool host) {
+      std::vector<Buf>& v = host ? pinned[bank & 1] : dev[bank & 1];
+      if (v.size() <= slot) v.resize(slot + 1);
+      Buf& b = v[slot];
+      if (b.p && b.bytes >= bytes) return b.p;
+      fle_ctx* c = FleGpu::ctx();
+      if (c == NULL) return NULL;
+      if (b.p) {
+        if (host) fle_host_free(b.p); else fle_dev_free(c, b.p);
+        b.p = NULL;
+        b.bytes = 0;
+      }
+      const size_t want = bytes + bytes / 4 + 4096;
+      const int rc = host ? fle_host_alloc(want, &b.p) : fle_dev_alloc(c, want, &b.p);
+      if (FleGpu::Check(rc, host ? "fle_host_alloc" : "fle_dev_alloc") != FLE_OK) return NULL;
+      b.bytes = want;
+      return b.p;
+    }
     ~Holder() {
+      for (int k = 0; k < 2; ++k) {
+        for (size_t i = 0; i < dev[k].size(); ++i)
+          if (dev[k][i].p && ctx) fle_dev_free(ctx, dev[k][i].p);
+        for (size_t i = 0; i < pinned[k].size(); ++i)
+          if (pinned[k][i].p) fle_host_free(pinned[k][i].p);
+      }
       if (ctx) fle_ctx_destroy(ctx);
     }
   };
+  static std::atomic<int>& compat_flag() {
+    static std::atomic<int> f(-1);
+    return f;
+  }
   static Holder& holder() {
     static thread_local Holder h;
     return h;

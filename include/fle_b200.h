@@ -81,8 +81,10 @@ typedef struct fle_col_desc {
 } fle_col_desc;
 
 /* One node of a postfix (reverse-Polish) predicate program.  Leaves name a column and carry
- * dictionary CODES pre-encoded on the host (DictDecoder<T>::Eq..In, dict-encoding.h:461-541);
- * only the low bit_width bits of a code are compared, as in the reference's plane algebra. */
+ * dictionary CODES pre-encoded on the host (DictDecoder<T>::Eq..In, dict-encoding.h:461-541).
+ * Codes are expected to fit the column's bit width (the reference's precondition); one that does
+ * not is folded to the constant the comparison means ("reference_compat" = 1: its high bits are
+ * ignored, as in the reference's plane algebra). */
 typedef struct fle_pred_node {
   int32_t op;            /* FLE_OP_* */
   int32_t col;           /* leaf: index into cols[] */
@@ -125,7 +127,11 @@ int fle_ctx_sync(fle_ctx* ctx);
  * kernel, kept as an on-device cross-check),
  * "codec_variant" (0 = direct loads/stores; 1 [default] = per-bit-width choice among the staged
  * unpack kernels; 2 = per-row bulk stores, 3 = warp-private copy-out, 4 = CTA-wide copy-out),
- * "codec_ctas_per_sm" (0 = auto), "h2d_chunk_rows". */
+ * "codec_ctas_per_sm" (0 = auto), "h2d_chunk_rows",
+ * "reference_compat" (default 0; 1 reproduces the reference where this library deliberately differs:
+ * a literal >= 2^bit_width keeps only its low bit_width bits, as in the reference's plane algebra,
+ * instead of being folded to the constant the comparison means -- `x < 2^bw` is true for every code;
+ * the host-side drop-ins have their own switch, FleGpu::SetReferenceCompat). */
 int fle_ctx_set_option(fle_ctx* ctx, const char* name, int64_t value);
 int64_t fle_ctx_get_option(fle_ctx* ctx, const char* name);
 /* Number of kernels of this library launched through ctx so far (bench `gpu_launches`). */
@@ -231,6 +237,59 @@ int fle_sum_product_dev(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nrows,
                         const int64_t* plain_i64_dev, const uint8_t* enc_dev, size_t enc_len,
                         int bit_width, const int64_t* dict_i64_dev, int ndict, int64_t* sum_dev,
                         uint64_t* count_dev);
+
+/* ---- one row group of the scanner as a batch (AssembleRows, hdfs-parquet-scanner.cc:1078-1275) -- */
+/* Uploads on the context's COPY stream (a second stream), so that the column chunks of row group
+ * k+1 cross PCIe while row group k is evaluated and materialised on the context's main stream;
+ * fle_prefetch_fence makes the main stream wait (on the device, not the host) for every upload
+ * enqueued so far.  src_host should be pinned (fle_host_alloc / fle_host_register): a pageable
+ * source is staged by the driver at a fraction of the PCIe rate. */
+int fle_h2d_prefetch(fle_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int fle_prefetch_fence(fle_ctx* ctx);
+/* Pins / unpins an existing host range (e.g. the I/O buffers the pages are read into) in place. */
+int fle_host_register(void* p, size_t bytes);
+int fle_host_unregister(void* p);
+
+/* One data page's FLE section inside a column-chunk image that already sits in device memory.
+ * The section starts at an arbitrary byte offset (after the page header, the definition levels and
+ * the 1-byte width header, dict-encoding.h:185-192) and was written with the page's own bit width
+ * (the reference's writer chooses it per page, dict-encoding.h:438-444). */
+typedef struct fle_page_ref {
+  const void* src_dev;      /* first FLE group of the page, any alignment */
+  uint64_t src_bytes;
+  int32_t src_bit_width;    /* width the page was packed with */
+  int32_t dst_bit_width;    /* width of the destination planes, >= src (missing high planes become zero planes) */
+  void* dst_dev;            /* 8-byte aligned; groups * dst_bit_width * 8 bytes */
+  int64_t groups;           /* 64-row groups of the page */
+  const void* def_src_dev;  /* optional: the page's definition levels (FLE, bit width 1), any alignment */
+  uint64_t def_bytes;
+  int64_t rows;             /* rows of the page (only used for the definition-level count) */
+} fle_page_ref;
+/* Re-bases the FLE sections of all pages (of all columns) of a row group onto aligned plane arrays
+ * in ONE launch -- consecutive pages of a column go to consecutive dst ranges, so the column becomes one
+ * plane array the fused kernels can scan -- and counts the rows whose definition level is 0 into
+ * *null_rows_dev (optional).  refs is a HOST array. */
+int fle_pages_gather_dev(fle_ctx* ctx, const fle_page_ref* refs, int nrefs, uint64_t* null_rows_dev);
+
+/* One materialised column of the survivors' tuples. */
+typedef struct fle_slot_desc {
+  const void* planes_dev;  /* FLE groups, 8-byte aligned, rows aligned with the bitmap */
+  uint64_t bytes;
+  int32_t bit_width;
+  int32_t slot_size;       /* 1, 2, 4 or 8 bytes: sizeof(T) of ColumnReader<T> */
+  const void* dict_dev;    /* ndict dictionary values of slot_size bytes (DictDecoder<T>::dict_) */
+  int32_t ndict;
+  int32_t tuple_offset;    /* byte offset of the slot inside a tuple */
+} fle_slot_desc;
+/* Replaces the materialisation loop of AssembleRows (hdfs-parquet-scanner.cc:1134-1180: skip-distance
+ * list, then ReadValue(skip) -> DictDecoder<T>::GetValue -> FleDecoder::Get(T*, skip) per survivor and
+ * column) for rows [0, nrows) of a bitmap: tuple j (tuple_size bytes, zero-filled, then one slot per
+ * column holding the dictionary value of the j-th selected row) is written to tuples_dev for
+ * j < min(selected, cap_rows), in ascending row order; *count_dev = selected rows; *bad_codes_dev =
+ * codes >= ndict met on the way (GetValue() == false; their slots stay zero).  One launch. */
+int fle_assemble_rows_dev(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nrows, const fle_slot_desc* cols,
+                          int ncols, int tuple_size, uint8_t* tuples_dev, int64_t cap_rows, uint64_t* count_dev,
+                          uint64_t* bad_codes_dev);
 
 /* fle_eval_dev + fle_sum_product_dev in ONE pass (the whole of TPC-H Q6 below the final
  * all-reduce): evaluates the program over rows [first_row, first_row + n) and accumulates

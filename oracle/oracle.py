@@ -234,6 +234,12 @@ class Ref:
         L.ref_scan_materialize.restype = C.c_int64
         L.ref_scan_materialize.argtypes = [C.c_int, _u8p, C.c_int64, C.c_int, C.c_int64, C.c_int, _u64p,
                                            C.c_int, _u32p]
+        L.ref_skip_seq.restype = C.c_int64
+        L.ref_skip_seq.argtypes = [_u8p, C.c_int64, C.c_int, _i32p, C.c_int64, _i32p, _i32p]
+        L.ref_set_compat.restype = None
+        L.ref_set_compat.argtypes = [C.c_int]
+        L.ref_scan_materialize_checked.restype = C.c_int64
+        L.ref_scan_materialize_checked.argtypes = L.ref_scan_materialize.argtypes
         L.ref_time_and_leaves.restype = C.c_double
         L.ref_time_and_leaves.argtypes = [C.POINTER(_u8p), _i32p, C.c_int, C.POINTER(_RefLeaf), C.c_int,
                                           C.c_int64, C.c_int, C.c_int, C.c_int, _u64p]
@@ -314,6 +320,26 @@ class Ref:
                                           len(l), _p(out, _u32p))
         if k < 0:
             raise RuntimeError("reference Get(val, skip) returned false")
+        return out[:k].copy()
+
+    def skip_seq(self, words, nbytes, bw, skips):
+        """[Skip(s) for s in skips] as 0/1, then whether a Get() still succeeds."""
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        s = np.ascontiguousarray(skips, dtype=np.int32)
+        res = np.zeros(len(s), dtype=np.int32)
+        fin = C.c_int32(0)
+        self.lib.ref_skip_seq(_p(words, _u8p), nbytes, bw, _p(s, _i32p), len(s), _p(res, _i32p), C.byref(fin))
+        return res.tolist(), int(fin.value)
+
+    def set_compat(self, on: bool):
+        self.lib.ref_set_compat(1 if on else 0)
+
+    def scan_materialize_checked(self, op, words, nbytes, bw, n, window, lits):
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        l = _lits(lits)
+        out = np.zeros(n, dtype=np.uint32)
+        k = self.lib.ref_scan_materialize_checked(op, _p(words, _u8p), nbytes, bw, n, window, _p(l, _u64p), len(l),
+                                                  _p(out, _u32p))
         return out[:k].copy()
 
     # -- timing (bench.py cpu_baseline) ------------------------------------------------

@@ -102,6 +102,28 @@ int64_t ref_get_skip(const uint8_t* enc, int64_t enc_len, int bw, const int32_t*
   return nskips;
 }
 
+// Sequence of Skip(skips[i]) calls (fle-encoding.h:381): results[i] = what each returned; *final_get =
+// what a Get() after the last one returns.  Pins the end-of-data behaviour of Skip().
+int64_t ref_skip_seq(const uint8_t* enc, int64_t enc_len, int bw, const int32_t* skips, int64_t nskips,
+                     int32_t* results, int32_t* final_get) {
+  PaddedCopy pc(enc, enc_len);
+  FleDecoder dec(pc.data(), (int)enc_len, bw);
+  for (int64_t i = 0; i < nskips; ++i) results[i] = dec.Skip(skips[i]) ? 1 : 0;
+  uint32_t v = 0;
+  *final_get = dec.Get(&v) ? 1 : 0;
+  return nskips;
+}
+
+// Built against the drop-in headers this switches them to reproduce the reference exactly
+// (FleGpu::SetReferenceCompat); built against the reference itself it is a no-op.
+void ref_set_compat(int on) {
+#ifdef FLE_B200_HOST_GPU_CONTEXT_H
+  impala::FleGpu::SetReferenceCompat(on != 0);
+#else
+  (void)on;
+#endif
+}
+
 // Advance the cursor with `pre_get` plain Get() calls, then run ONE predicate call for
 // num_rows rows.  Output: LSB-first 64-bit blocks; returns the bitset size.
 int64_t ref_pred(int op, const uint8_t* enc, int64_t enc_len, int bw, int64_t pre_get,
@@ -207,6 +229,44 @@ int64_t ref_scan_materialize(int op, const uint8_t* enc, int64_t enc_len, int bw
       out_vals[nout++] = v;
     }
     if (last_skip_rows != 0) dec.Skip(last_skip_rows);
+    done += w;
+  }
+  return nout;
+}
+
+// The same loop with the return values honoured the way AssembleRows honours them: when the trailing
+// Skip(last_skip_rows) reports false the scan RETURNS (`if (!result) return parse_status_;`,
+// hdfs-parquet-scanner.cc:1107-1113) -- which is what happens when a page holds a multiple of 64 values
+// and the skip lands exactly on its end.  Returns the number of codes written before that.
+int64_t ref_scan_materialize_checked(int op, const uint8_t* enc, int64_t enc_len, int bw, int64_t n,
+                                     int window, const uint64_t* lits, int nlits, uint32_t* out_vals) {
+  PaddedCopy pc(enc, enc_len);
+  FleDecoder dec(pc.data(), (int)enc_len, bw);
+  int64_t done = 0, nout = 0;
+  while (done < n) {
+    int64_t w = std::min<int64_t>(window, n - done);
+    Bitset bs;
+    RunPred(dec, op, w, bs, lits, nlits);
+    if (bs.count() == 0) {
+      dec.Skip((int)w);  // (result not looked at here, :1125-1131)
+      done += w;
+      continue;
+    }
+    int start = 0;
+    std::vector<int> skip_rows;
+    for (int i = 0; i < (int)w; ++i) {
+      if (bs[i]) {
+        skip_rows.push_back(i - start);
+        start = i + 1;
+      }
+    }
+    int last_skip_rows = (int)w - start;
+    for (int s : skip_rows) {
+      uint32_t v = 0;
+      if (!dec.Get(&v, s)) return nout;
+      out_vals[nout++] = v;
+    }
+    if (last_skip_rows != 0 && !dec.Skip(last_skip_rows)) return nout;
     done += w;
   }
   return nout;

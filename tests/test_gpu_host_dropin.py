@@ -116,3 +116,43 @@ def test_driver_vs_live_reference(hostdrv, ref, bw):
     a, ga = hostdrv.get_skip(words, bw, skips)
     b, gb = ref.get_skip(words, bw, skips)
     assert ga == gb and (a[:ga] == b[:gb]).all()
+
+
+@pytest.mark.parametrize("bw", [1, 7, 12, 16, 32])
+def test_deviations_pinned_against_live_reference(hostdrv, ref, bw):
+    """DESIGN.md's deliberate deviations, run on the reference itself and on the drop-in in BOTH modes: a buffer that
+    holds a multiple of 64 values, Skip() landing exactly on its end (fle-encoding.h:381-402) and the AssembleRows loop
+    that returns when that Skip reports false (hdfs-parquet-scanner.cc:1107-1113)."""
+    rng = np.random.default_rng(900 + bw)
+    n = 64 * 48
+    vals = rng.integers(0, 1 << bw, size=n, dtype=np.uint64).astype(np.uint32)
+    words = ref.pack(vals, bw)
+    nbytes = (n // 64) * bw * 8                     # exactly the groups that hold values (no Flush spare group)
+    lit = int(np.sort(vals)[n // 2])
+    try:
+        for skips in ([n], [64, n - 64], [n - 1, 1], [1000, 1000, n - 2000], [n + 64], [100, 200, 300]):
+            want, want_get = ref.skip_seq(words, nbytes, bw, skips)
+            hostdrv.set_compat(True)
+            got, got_get = hostdrv.skip_seq(words, nbytes, bw, skips)
+            assert got == want, ("reference_compat", skips)
+            # (after a Skip() that failed the reference's Get() hands out stale staging values and reports success;
+            #  the drop-in reports false -- compared only where every Skip succeeded)
+            if all(want):
+                assert got_get == want_get
+            hostdrv.set_compat(False)
+            got, got_get = hostdrv.skip_seq(words, nbytes, bw, skips)
+            if sum(skips) == n:                      # the ONE case the default mode answers differently
+                assert want[-1] == 0 and got[-1] == 1 and got[:-1] == want[:-1] and got_get == 0
+            else:
+                assert got == want, skips
+        for window in (1024, 64):
+            want = ref.scan_materialize_checked(LT, words, nbytes, bw, n, window, [lit])
+            full = ref.scan_materialize(LT, words, bw, n, window, [lit])   # the loop without the early return
+            hostdrv.set_compat(True)
+            assert (hostdrv.scan_materialize_checked(LT, words, nbytes, bw, n, window, [lit]) == want).all()
+            hostdrv.set_compat(False)
+            got = hostdrv.scan_materialize_checked(LT, words, nbytes, bw, n, window, [lit])
+            assert (got == full).all() and (full == vals[vals < lit]).all()
+            assert len(want) <= len(full)           # the reference may stop early; the default mode never does
+    finally:
+        hostdrv.set_compat(False)

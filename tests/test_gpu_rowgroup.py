@@ -1,0 +1,136 @@
+"""Row-group batch kernels behind the scanner's AssembleRows (fle_pages_gather_dev, the single-pass
+fle_bitmap_select_dev, fle_assemble_rows_dev) against numpy restatements of the reference loops
+(hdfs-parquet-scanner.cc:1134-1180, dict-encoding.h:185-192, :321-330, :438-444)."""
+import numpy as np
+import pytest
+
+from oracle.oracle import GE
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(words, n):
+    return np.unpackbits(np.ascontiguousarray(words).view(np.uint8), bitorder="little")[:n].astype(bool)
+
+
+@pytest.mark.parametrize("n", [1, 63, 64, 65536, 65537, 64 * 70000 + 17, 1 << 24])
+@pytest.mark.parametrize("density", [0.0, 0.018, 0.5, 1.0])
+def test_single_pass_select(ctx, n, density):
+    import torch
+    rng = np.random.default_rng(n % 1000 + int(density * 100))
+    sel = rng.random(n) < density if 0 < density < 1 else np.full(n, density == 1.0)
+    words = np.packbits(np.concatenate([sel, np.zeros((-n) % 64, dtype=bool)]), bitorder="little").view(np.uint64)
+    words = words.copy()
+    if n % 64:
+        words[-1] |= np.uint64(0xFFFFFFFFFFFFFFFF) << np.uint64(n % 64)  # garbage past the end must be ignored
+    bm = torch.from_numpy(words.view(np.int64)).cuda()
+    want = np.nonzero(sel)[0].astype(np.uint32)
+    for rep in range(3):  # launches back to back: the tile status words are reused, only the generation changes
+        ids, cnt = ctx.bitmap_select_dev(bm, n)
+    torch.cuda.synchronize()
+    k = int(cnt.item())
+    assert k == len(want)
+    assert (ids.cpu().numpy().view(np.uint32)[:k] == want).all()
+    # capacity smaller than the number of survivors: the count is still exact, the prefix is written
+    cap = max(1, k // 3)
+    ids2, cnt2 = ctx.bitmap_select_dev(bm, n, cap=cap)
+    torch.cuda.synchronize()
+    assert int(cnt2.item()) == k
+    assert (ids2.cpu().numpy().view(np.uint32)[:min(cap, k)] == want[:min(cap, k)]).all()
+
+
+def test_pages_gather_widths_offsets_and_nulls(ctx, oracle):
+    """Pages of one column chunk at odd offsets of the chunk image, written with growing bit widths
+    (the reference's writer picks the width per page), gathered into one plane array at the widest width."""
+    import torch
+    rng = np.random.default_rng(11)
+    page_rows = [64 * 300, 64 * 300, 64 * 300, 64 * 120 + 37]
+    page_bw = [3, 5, 5, 7]
+    dst_bw = 7
+    blob = bytearray()
+    refs, all_vals, nulls_want = [], [], 0
+    for rows, bw in zip(page_rows, page_bw):
+        vals = rng.integers(0, 1 << bw, size=rows).astype(np.uint32)
+        all_vals.append(vals)
+        words = oracle.pack(vals, bw)
+        defs = rng.random(rows) < 0.97
+        nulls_want += int((~defs).sum())
+        dwords = oracle.pack(defs.astype(np.uint32), 1)
+        blob += bytes(rng.integers(0, 255, size=int(rng.integers(17, 40)), dtype=np.uint8))  # "page header"
+        blob += np.int32(dwords.nbytes).tobytes()
+        def_off = len(blob)
+        blob += dwords.tobytes()
+        blob += bytes([bw])
+        data_off = len(blob)
+        blob += words.tobytes()
+        refs.append(dict(src_off=data_off, src_bytes=words.nbytes, src_bit_width=bw, groups=(rows + 63) // 64,
+                         def_off=def_off, def_bytes=dwords.nbytes, rows=rows))
+    blob += bytes(16)
+    dblob = torch.from_numpy(np.frombuffer(bytes(blob), dtype=np.uint8).copy()).cuda()
+    total_groups = sum(r["groups"] for r in refs)
+    planes = torch.full((total_groups * dst_bw,), -1, dtype=torch.int64, device="cuda")
+    g0, crefs = 0, []
+    for r in refs:
+        crefs.append(dict(src_dev=dblob.data_ptr() + r["src_off"], src_bytes=r["src_bytes"], src_bit_width=r["src_bit_width"],
+                          dst_bit_width=dst_bw, dst_dev=planes.data_ptr() + g0 * dst_bw * 8, groups=r["groups"],
+                          def_src_dev=dblob.data_ptr() + r["def_off"], def_bytes=r["def_bytes"], rows=r["rows"]))
+        g0 += r["groups"]
+    nulls = ctx.pages_gather_dev(crefs)
+    torch.cuda.synchronize()
+    assert int(nulls.item()) == nulls_want
+    got = planes.cpu().numpy().view(np.uint64)
+    g0 = 0
+    for r, vals in zip(refs, all_vals):
+        dec = oracle.unpack(got[g0 * dst_bw:(g0 + r["groups"]) * dst_bw], dst_bw, 0, len(vals))
+        assert (dec == vals).all()
+        g0 += r["groups"]
+    # ... and the fused kernel scans the gathered column as one plane array (ragged last page: rows are per page)
+    n_full = sum(page_rows[:3])
+    bm, cnt = ctx.eval_dev([(planes, dst_bw)], [(GE, 0, 3)], n_full)
+    torch.cuda.synchronize()
+    assert int(cnt.item()) == int((np.concatenate(all_vals[:3]) >= 3).sum())
+
+
+@pytest.mark.parametrize("slot_sizes", [(4, 4, 4), (8, 4, 2, 1), (1,), (8, 8)])
+def test_assemble_rows(ctx, oracle, slot_sizes):
+    import torch
+    rng = np.random.default_rng(len(slot_sizes))
+    n = 64 * 5000 + 21
+    dtypes = {1: np.int8, 2: np.int16, 4: np.int32, 8: np.int64}
+    sel = rng.random(n) < 0.03
+    words = np.packbits(np.concatenate([sel, np.zeros((-n) % 64, dtype=bool)]), bitorder="little").view(np.uint64)
+    bm = torch.from_numpy(words.view(np.int64).copy()).cuda()
+    ncols = len(slot_sizes)
+    off = ncols
+    slots, keep, cols = [], [], []
+    for c, ss in enumerate(slot_sizes):
+        bw = int(rng.integers(1, 14))
+        nd = (1 << bw) - (1 if c == 0 and bw > 2 else 0)  # one column with a code outside its dictionary
+        codes = rng.integers(0, 1 << bw, size=n).astype(np.uint32)
+        d = rng.integers(-100, 100, size=nd).astype(dtypes[ss])
+        off = (off + ss - 1) // ss * ss
+        planes = torch.from_numpy(oracle.pack(codes, bw).view(np.int64)).cuda()
+        dd = torch.from_numpy(d).cuda()
+        keep += [planes, dd]
+        slots.append(dict(planes_dev=planes.data_ptr(), bytes=planes.numel() * 8, bit_width=bw, slot_size=ss,
+                          dict_dev=dd.data_ptr(), ndict=nd, tuple_offset=off))
+        cols.append((codes, d, off, ss, nd))
+        off += ss
+    tuple_size = (off + 7) // 8 * 8
+    k = int(sel.sum())
+    tuples, cnt, bad = ctx.assemble_rows_dev(bm, n, slots, tuple_size, k + 5)
+    torch.cuda.synchronize()
+    assert int(cnt.item()) == k
+    got = tuples.cpu().numpy()[:k]
+    want = np.zeros((k, tuple_size), dtype=np.uint8)
+    rows = np.nonzero(sel)[0]
+    bad_want = 0
+    for codes, d, o, ss, nd in cols:
+        cs = codes[rows]
+        ok = cs < nd
+        bad_want += int((~ok).sum())
+        v = np.zeros(k, dtype=d.dtype)
+        v[ok] = d[cs[ok]]
+        want[:, o:o + ss] = v.view(np.uint8).reshape(k, ss)
+    assert int(bad.item()) == bad_want
+    assert (got == want).all()
