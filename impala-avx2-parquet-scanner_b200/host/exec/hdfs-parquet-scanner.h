@@ -817,7 +817,14 @@ inline bool HdfsParquetScanner::StartRowGroupUpload() {
     bc.ndict = nd;
     bc.dict_dev = FleGpu::DeviceScratch(batch_bank_, 3 * c + 2, static_cast<size_t>(std::max(nd, 1)) * es);
     if (!bc.image_dev || !bc.planes_dev || !bc.dict_dev) return false;
-    if (nd > 0 && FleGpu::Check(fle_h2d_prefetch(ctx, bc.dict_dev, dv, static_cast<size_t>(nd) * es), "fle_h2d_prefetch(dict)") != FLE_OK) return false;
+    if (nd > 0) {
+      // through pinned staging: an asynchronous copy from pageable memory makes the host wait for the copy
+      // stream, which is busy with the previous column chunk
+      void* stage = FleGpu::PinnedScratch(batch_bank_, 2 + c, static_cast<size_t>(nd) * es);
+      if (!stage) return false;
+      memcpy(stage, dv, static_cast<size_t>(nd) * es);
+      if (FleGpu::Check(fle_h2d_prefetch(ctx, bc.dict_dev, stage, static_cast<size_t>(nd) * es), "fle_h2d_prefetch(dict)") != FLE_OK) return false;
+    }
     if (one_copy && FleGpu::Check(fle_h2d_prefetch(ctx, bc.image_dev, lo, image_bytes), "fle_h2d_prefetch(chunk)") != FLE_OK) return false;
     int64_t g0 = 0;
     size_t off = 0;

@@ -178,9 +178,24 @@ def test_edge_sizes_and_errors(ctx, oracle):
     with pytest.raises(fle_b200.FleError) as ei:
         ctx.eval([(w, 9)], [(LT, 1, 1)], 100)
     assert ei.value.code == capi.E_INVALID
-    # literal wider than the column: only bw bits take part, as in the reference's plane algebra
-    bm, _ = ctx.eval([(w, 9)], [(EQ, 0, 512 + 5)], 640)
-    assert (bm == oracle.pred(EQ, w, 9, 0, 640, [5])[0]).all()
+    # literal wider than the column: folded to what the comparison means for 9-bit codes ...
+    bm, cnt = ctx.eval([(w, 9)], [(EQ, 0, 512 + 5)], 640)
+    assert cnt == 0 and not bm.any()
+    bm, cnt = ctx.eval([(w, 9)], [(LT, 0, 512)], 640)
+    assert cnt == 640
+    bm, cnt = ctx.eval([(w, 9)], [(GE, 0, 1 << 40)], 640)
+    assert cnt == 0
+    bm, cnt = ctx.eval([(w, 9)], [(IN, 0, [512 + 5, 7, 1 << 33])], 640)
+    assert (bm == oracle.pred(EQ, w, 9, 0, 640, [7])[0]).all()
+    # ... unless the reference's plane algebra is asked for: only the low bw bits take part (fle-encoding.h:7965-7971)
+    ctx.set_option("reference_compat", 1)
+    try:
+        bm, _ = ctx.eval([(w, 9)], [(EQ, 0, 512 + 5)], 640)
+        assert (bm == oracle.pred(EQ, w, 9, 0, 640, [5])[0]).all()
+        bm, cnt = ctx.eval([(w, 9)], [(LT, 0, 512)], 640)
+        assert cnt == 0
+    finally:
+        ctx.set_option("reference_compat", 0)
 
 
 def test_intersect_bitset_vs_oracle(ctx, oracle):
