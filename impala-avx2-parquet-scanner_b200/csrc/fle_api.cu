@@ -438,6 +438,7 @@ int fle_ctx_set_option(fle_ctx* ctx, const char* name, int64_t value) {
   else if (k == "eval_gpt") ctx->eval_gpt = (int)value;
   else if (k == "in_lookup_min") ctx->in_lookup_min = (int)value;
   else if (k == "in_wide") ctx->in_wide = (int)value;
+  else if (k == "in_mux_bw") ctx->in_mux_bw = (int)std::min<int64_t>(7, std::max<int64_t>(0, value));
   else if (k == "in_split_min_rows") ctx->in_split_min_rows = value;
   else if (k == "eval_narrow_bw") ctx->eval_narrow_bw = (int)value;
   else if (k == "codec_variant") ctx->codec_variant = (int)value;
@@ -462,6 +463,7 @@ int64_t fle_ctx_get_option(fle_ctx* ctx, const char* name) {
   if (k == "eval_gpt") return ctx->eval_gpt;
   if (k == "in_lookup_min") return ctx->in_lookup_min;
   if (k == "in_wide") return ctx->in_wide;
+  if (k == "in_mux_bw") return ctx->in_mux_bw;
   if (k == "in_split_min_rows") return ctx->in_split_min_rows;
   if (k == "eval_narrow_bw") return ctx->eval_narrow_bw;
   if (k == "codec_variant") return ctx->codec_variant;

@@ -658,7 +658,8 @@ namespace {
 inline uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 constexpr int kNT = 256;
-enum LaunchMode { MODE_DIRECT = 0, MODE_STAGED = 1, MODE_SINGLE_PASS = 2, MODE_IN_LOOKUP = 3, MODE_JIT = 4, MODE_NARROW = 5, MODE_IN_WIDE = 6 };
+enum LaunchMode { MODE_DIRECT = 0, MODE_STAGED = 1, MODE_SINGLE_PASS = 2, MODE_IN_LOOKUP = 3, MODE_JIT = 4, MODE_NARROW = 5, MODE_IN_WIDE = 6,
+                  MODE_IN_MUX = 7 };
 
 // cudaOccupancyMaxActiveBlocksPerMultiprocessor / cudaFuncSetAttribute are not free; remember
 // the answers per (kernel, dynamic smem)
@@ -711,6 +712,7 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
   const int64_t G = P.ngroups;
   const void* kern = nullptr;
   int nt = kNT;       // threads per CTA
+  int mode_reported = mode;
   if (mode == MODE_JIT) {
     kern = jit_kern;
   } else if (mode == MODE_SINGLE_PASS) {
@@ -726,6 +728,11 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
   } else if (mode == MODE_NARROW) {
     kern = eval1_narrow_kernel_for(P.passes[0].type, P.passes[0].k, (int)P.bw[0]);
     if (!kern) return FLE_E_UNSUPPORTED;
+  } else if (mode == MODE_IN_MUX) {
+    kern = eval_in_mux_kernel_for((int)P.bw[0]);
+    if (!kern) return FLE_E_UNSUPPORTED;
+    mode = MODE_SINGLE_PASS;  // same tile pipeline and launch shape as the single-pass compare kernels
+    mode_reported = MODE_IN_MUX;
   } else {
     kern = mode == MODE_STAGED ? (const void*)eval_tma_kernel<kNT> : (const void*)eval_direct_kernel<kNT>;
   }
@@ -755,7 +762,14 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
     gpt = std::min(gpt, 8);
     if (mode == MODE_IN_WIDE) gpt = 1;  // the table leaves room for 24-48 KB stages only
     if (mode == MODE_JIT && P.agg_plain) gpt = kJitAggGpt;  // compiled into the kernel (fle_eval_jit.cuh)
-    if (mode == MODE_SINGLE_PASS) {
+    if (mode_reported == MODE_IN_MUX) {
+      // compute-heavy (2^bw instructions per 32 rows): two CTAs per SM so that one computes while the other waits
+      // at its tile barrier, and tiles as large as two stages per CTA allow (bw 6, 600 M rows: 1 CTA x 3 stages x
+      // 2 groups per thread 0.64 of roofline, 2 CTAs x 2 stages x 4 groups 0.79)
+      if (ctx->eval_gpt <= 0) gpt = (int)std::max<uint32_t>(1, std::min<uint32_t>(8, (48u * 1024u) / bytes_per_gpt));
+      sp_ctas = 2;
+      sp_stages = 2;
+    } else if (mode == MODE_SINGLE_PASS) {
       const uint32_t stage = (uint32_t)gpt * bytes_per_gpt;
       if (sp_narrow) {
         sp_ctas = stage < 20u * 1024u ? 3 : 2;
@@ -864,7 +878,7 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
     return set_cuda_error(ctx, e, what);
   }
   ctx->launches += 1;
-  ctx->last_mode = mode;
+  ctx->last_mode = mode_reported;
   if (mode == MODE_JIT) ctx->jit_launches += 1;
   return FLE_OK;
 }
@@ -952,6 +966,16 @@ int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, 
     P1.planes[0] = P.planes[c];
     P1.bw[0] = P.bw[c];
     P1.passes[0].col = 0;
+    // narrow columns: the membership function as a multiplexer tree over the planes (fle_eval1.cu, InMuxRegs)
+    if ((int)P.bw[c] <= ctx->in_mux_bw) {
+      std::memset(P1.in_masks, 0, sizeof(P1.in_masks));
+      for (uint32_t j = 0; j < p0.lit[1]; ++j) {
+        const uint32_t code = lp->in_lits[p0.lit[0] + j] & 127u;
+        P1.in_masks[code] = in_mux_term_on_fma((int)P.bw[c], (int)(code & 7u)) ? 1u : ~0u;
+      }
+      const int rc = launch_program(ctx, P1, MODE_IN_MUX, (int)P.bw[c]);
+      if (rc != FLE_E_UNSUPPORTED) return rc;
+    }
     // one CTA per SM, producer warp + 16 consumer warps: 16-bit table entries (one ALU instruction per
     // lookup) for bw <= 12, replicated bit table beyond (fle_eval_in.cu)
     if (ctx->in_wide != 0) {

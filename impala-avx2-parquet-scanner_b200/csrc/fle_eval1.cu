@@ -61,6 +61,10 @@ struct PassRegs {
 
   // plane-order result word of one group (bit 63-r = row r)
   template <class L>
+  __device__ __forceinline__ uint64_t run(const EvalParams&, const L& ld) const {
+    return run(ld);
+  }
+  template <class L>
   __device__ __forceinline__ uint64_t run(const L& ld) const {
     uint32_t al[K], ah[K];
 #pragma unroll
@@ -108,8 +112,91 @@ struct PassRegs {
 // such a CTA only costs the tiles it did not get.  Claiming in batches of consecutive tiles was
 // slower (bw 12: 1.04 -> 1.00 of roofline): neighbouring CTAs on neighbouring tiles is what the
 // memory system likes.
-template <bool IS_LT, int K, int BW>
-__global__ void __launch_bounds__(256) eval1_kernel(const __grid_constant__ EvalParams P) {
+// ------------------------------------------------------------------------------------------
+// IN list on a narrow column, in the plane domain.  The reference ORs one equality chain per literal
+// (fle-encoding.h:8279-8290: L * bw operations per 64 rows); the lookup kernels of fle_eval_in.cu
+// transpose the planes into codes and look every row up (~9 instructions per ROW whatever the width).
+// For bw <= 7 the membership function itself is small: a truth table of 2^bw bits.  Shannon expansion
+// over the planes, per 32 rows:
+//   minterms of the low T = min(bw, 3) planes            2^T LOP3 (immediate truth tables)
+//   one leaf per value of the high planes:
+//       leaf = OR_j (minterm_j & member[leaf * 2^T + j])   2^bw LOP3, the member masks are kernel
+//                                                          parameters = constant-bank operands
+//   multiplexer tree over the high planes                 2^(bw - T) - 1 LOP3 (x ? b : a)
+// i.e. about 2^bw + 2^(bw-3) + 8 instructions per 32 rows, independent of the list length: bw 6 158 per
+// group against 463 for the lookup kernel, bw 3 16.  Bit-identical to the OR of equalities: the same
+// boolean function of the row's bits.
+// LOP3 issues at 64 lanes per clock per SM, half the scheduler rate, and with every term on that pipe bw 6 / 7
+// ran at 0.55 / 0.41 of the HBM roofline, ALU-bound.  The minterms of a leaf are DISJOINT bit sets, so their OR
+// is also their SUM, and `minterm & member` with member in {0, ~0} is `minterm * member` with member in {0, 1}:
+// every other term is therefore an IMAD on the FMA pipe (also 64 lanes per clock, independent of the ALU pipe;
+// tools/micro/int_pipes.cu: LOP3 + IMAD together 122 lanes per clock).
+// ------------------------------------------------------------------------------------------
+template <int BW>
+struct InMuxRegs {
+  static_assert(BW >= 1 && BW <= 7, "plane-domain IN lists: bw <= 7");
+  static constexpr int T = BW < 3 ? BW : 3;
+  uint32_t nm;
+  __device__ __forceinline__ void init(const PassDesc& pd) { nm = pd.neg[0] ? ~0u : 0u; }
+
+  __device__ __forceinline__ static uint32_t half(const EvalParams& P, const uint32_t (&x)[BW]) {
+    uint32_t m[1 << T];
+    if constexpr (T == 1) {
+      m[0] = ~x[0];
+      m[1] = x[0];
+    } else if constexpr (T == 2) {
+      m[0] = ~x[0] & ~x[1];
+      m[1] = x[0] & ~x[1];
+      m[2] = ~x[0] & x[1];
+      m[3] = x[0] & x[1];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t a = (j & 1) ? x[0] : ~x[0], b = (j & 2) ? x[1] : ~x[1], c = (j & 4) ? x[2] : ~x[2];
+        m[j] = a & b & c;  // one LOP3: the complements fold into its truth table
+      }
+    }
+    constexpr int kLeaves = 1 << (BW - T);
+    uint32_t node[kLeaves];
+#pragma unroll
+    for (int k = 0; k < kLeaves; ++k) {
+      uint32_t acc = m[0] & P.in_masks[k * (1 << T)];
+#pragma unroll
+      for (int j = 1; j < (1 << T); ++j) {
+        if (in_mux_term_on_fma(BW, j)) acc = m[j] * P.in_masks[k * (1 << T) + j] + acc;  // IMAD: disjoint bits, 0 / 1 factor
+        else acc |= m[j] & P.in_masks[k * (1 << T) + j];
+      }
+      node[k] = acc;
+    }
+#pragma unroll
+    for (int i = T; i < BW; ++i) {
+#pragma unroll
+      for (int k = 0; k < (kLeaves >> (i - T + 1)); ++k) node[k] = (node[2 * k] & ~x[i]) | (node[2 * k + 1] & x[i]);
+    }
+    return node[0];
+  }
+
+  template <class L>
+  __device__ __forceinline__ uint64_t run(const EvalParams& P, const L& ld) const {
+    uint32_t xl[BW], xh[BW];
+#pragma unroll
+    for (int i = 0; i < BW; i += 2) {
+      uint64_t w0, w1;
+      ld.template load_pair<BW>(i, w0, w1);
+      xl[i] = (uint32_t)w0;
+      xh[i] = (uint32_t)(w0 >> 32);
+      if (i + 1 < BW) {
+        xl[i + 1 < BW ? i + 1 : i] = (uint32_t)w1;
+        xh[i + 1 < BW ? i + 1 : i] = (uint32_t)(w1 >> 32);
+      }
+    }
+    const uint32_t rl = half(P, xl) ^ nm, rh = half(P, xh) ^ nm;
+    return ((uint64_t)rh << 32) | rl;
+  }
+};
+
+template <class PR, int BW>
+__device__ __forceinline__ void eval1_body(const EvalParams& P) {
   constexpr int NT = 256;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ int64_t stage_tile[8];  // tile held by each stage, -1 = no more tiles
@@ -144,7 +231,7 @@ __global__ void __launch_bounds__(256) eval1_kernel(const __grid_constant__ Eval
     next_claim = atomicAdd(P.tile_counter, 1u);
   }
 
-  PassRegs<IS_LT, K, BW> pr;
+  PR pr;
   pr.init(P.passes[0]);
 
   const uint32_t seg = threadIdx.x & 7, jrow = threadIdx.x >> 3;
@@ -174,7 +261,7 @@ __global__ void __launch_bounds__(256) eval1_kernel(const __grid_constant__ Eval
     // bw 4 0.91 -> 0.95, bw 12 1.02 -> 1.04)
 #pragma unroll 2
     for (int q = 0; q < gpt; ++q) {
-      const uint64_t r = finish_word(pr.run(SmemGroup{a}), g, P.nrows);
+      const uint64_t r = finish_word(pr.run(P, SmemGroup{a}), g, P.nrows);
       P.bitmap[g] = r;
       cnt += __popcll(r);
       a += kGroupStride;
@@ -188,11 +275,21 @@ __global__ void __launch_bounds__(256) eval1_kernel(const __grid_constant__ Eval
   // ragged remainder (< T groups), planes straight from global memory
   for (int64_t g = ntiles * T + (int64_t)blockIdx.x * NT + threadIdx.x; g < P.ngroups;
        g += (int64_t)gridDim.x * NT) {
-    const uint64_t r = finish_word(pr.run(GlobalGroup{P.planes[0] + g * BW}), g, P.nrows);
+    const uint64_t r = finish_word(pr.run(P, GlobalGroup{P.planes[0] + g * BW}), g, P.nrows);
     P.bitmap[g] = r;
     cnt += __popcll(r);
   }
   publish_count<NT>(P, cnt);
+}
+
+template <bool IS_LT, int K, int BW>
+__global__ void __launch_bounds__(256) eval1_kernel(const __grid_constant__ EvalParams P) {
+  eval1_body<PassRegs<IS_LT, K, BW>, BW>(P);
+}
+
+template <int BW>
+__global__ void __launch_bounds__(256) eval_in_mux_kernel(const __grid_constant__ EvalParams P) {
+  eval1_body<InMuxRegs<BW>, BW>(P);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -302,6 +399,15 @@ const void* eval1_narrow_kernel_for(int type, int k, int bw) {
   } else if (type == PASS_EQ) {
     if (k == 1) return eval1_narrow_for_bw<false, 1>(bw);
     if (k == 4) return eval1_narrow_for_bw<false, 4>(bw);
+  }
+  return nullptr;
+}
+
+const void* eval_in_mux_kernel_for(int bw) {
+  switch (bw) {
+#define X(B) case B: return (const void*)eval_in_mux_kernel<B>;
+    X(1) X(2) X(3) X(4) X(5) X(6) X(7)
+#undef X
   }
   return nullptr;
 }

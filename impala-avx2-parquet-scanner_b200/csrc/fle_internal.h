@@ -65,6 +65,7 @@ struct fle_ctx {
   int eval_narrow_bw = 2;    // single-pass programs on columns up to this width skip shared-memory staging (bw 1, 2, 4)
   int in_lookup_min = 9;     // IN lists at least this long use the decode+lookup kernel (bw <= 16); shorter ones the plane form
   int in_wide = 1;           // IN lookup on bw <= 12: 16-bit entry table (1) or the bit table (0)
+  int in_mux_bw = 7;         // IN lists of in_lookup_min+ literals on columns up to this width run in the plane domain (0 = never)
   int64_t in_split_min_rows = 1ll << 20;  // calls of at least this many rows evaluate long IN lists (>= 16 literals) inside larger programs with the lookup kernels; -1 = never
   int codec_variant = 1;
   int codec_ctas_per_sm = 0;  // 0 = as many as fit
@@ -174,6 +175,8 @@ const void* eval1_kernel_for(int type, int k, int bw);
 // fle_eval1.cu: unstaged kernels for bw 1, 2, 4 (coalesced 128-bit global loads), or nullptr
 const void* eval1_narrow_kernel_for(int type, int k, int bw);
 constexpr int kNarrowUnits = 8;  // 16/32-byte units per thread per tile of the narrow kernels
+// fle_eval1.cu: IN list on a narrow column as a multiplexer tree over the planes (bw <= 7), or nullptr
+const void* eval_in_mux_kernel_for(int bw);
 // fle_eval_in.cu: IN list by decode + membership-table lookup (bw <= 16), or nullptr
 const void* eval_in_kernel_for(int bw);
 // fle_eval_in.cu: IN list by decode + 16-bit entry table (bw <= 12, CTAs of 512 threads), or nullptr

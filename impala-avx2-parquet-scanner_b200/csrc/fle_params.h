@@ -129,6 +129,17 @@ struct EvalParams {
   uint64_t grp_timeout_ns;
   PassDesc passes[kMaxPasses];
   CombDesc combs[kMaxCombs];
+  // IN list on a narrow column (bw <= 7) evaluated in the plane domain (fle_eval1.cu, InMuxRegs):
+  // in_masks[c] says whether code c is a member of the list -- as ~0 / 0 where the term is ANDed in on the
+  // ALU pipe, as 1 / 0 where it is multiplied in on the FMA pipe (in_mux_term_on_fma)
+  uint32_t in_masks[128];
 };
+
+// which of the 2^min(bw, 3) minterm terms of a leaf go to the FMA pipe (IMAD) instead of the ALU pipe (LOP3)
+inline
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+constexpr bool in_mux_term_on_fma(int bw, int j) { return bw >= 3 && ((j & 1) != 0 || (bw == 7 && j == 6)); }
 
 }  // namespace fle

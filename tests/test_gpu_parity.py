@@ -520,19 +520,22 @@ def test_in_list_lookup_kernel_vs_oracle(ctx, oracle, bw):
     for L in (1, 8, 64, 256, 1000):
         lits = rng.integers(0, 1 << bw, size=L, dtype=np.uint64)  # duplicates and absent codes included
         want, wcnt = oracle.pred(IN, words, bw, 0, n, lits)
-        # (lookup_min, in_wide): one-CTA producer/consumer kernel (entry table, replicated bit table), two-CTA bit-table kernel, plane form
-        for lookup_min, wide in ((1, 1), (1, 0), (1 << 30, 1)):
+        # (lookup_min, in_wide, in_mux_bw): multiplexer tree over the planes (bw <= 7), one-CTA producer/consumer kernel
+        # (entry table, replicated bit table), two-CTA bit-table kernel, equality chains on the planes
+        for lookup_min, wide, mux in ((1, 1, 7), (1, 1, 0), (1, 0, 0), (1 << 30, 1, 7)):
             ctx.set_option("in_lookup_min", lookup_min)
             ctx.set_option("in_wide", wide)
+            ctx.set_option("in_mux_bw", mux)
             try:
                 bm, cnt = ctx.eval([(words, bw)], [(IN, 0, lits)], n)
                 mode = ctx.get_option("last_mode")
             finally:
                 ctx.set_option("in_lookup_min", 9)
                 ctx.set_option("in_wide", 1)
-            assert (bm == want).all() and cnt == wcnt, (bw, L, lookup_min, wide)
+                ctx.set_option("in_mux_bw", 7)
+            assert (bm == want).all() and cnt == wcnt, (bw, L, lookup_min, wide, mux)
             if lookup_min == 1 and bw <= 16:
-                assert mode == (6 if wide else 3), (bw, mode)
+                assert mode == (7 if bw <= mux else (6 if wide else 3)), (bw, mode)
 
 
 def test_long_in_lists_inside_programs_vs_oracle(ctx, oracle):
