@@ -988,6 +988,7 @@ int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, 
     const int rc = launch_in_lookup();
     if (rc != FLE_E_UNSUPPORTED) return rc;
   }
+  if (P.comb_op) return FLE_E_UNSUPPORTED;  // only the single-IN-list kernels combine on the way out
   // narrow columns: consecutive groups are already 128-bit coalesced in global memory
   if (staged_ok && single_pass && ctx->eval_variant == 1 && !agg && (int)P.bw[p0.col] <= ctx->eval_narrow_bw &&
       (reinterpret_cast<uintptr_t>(bitmap_dev) & 15) == 0) {
@@ -1099,6 +1100,81 @@ static int launch_eval_in_split(fle_ctx* ctx, const fle_col_desc* cols, int ncol
       stack[sp++] = i;
     }
     if (sp != 1 || !any) return FLE_E_UNSUPPORTED;
+  }
+  // The common shape -- ONE chain of AND (or OR) at the root whose operands are long lists and subtrees without
+  // one -- needs no temporary bitmap and no combine pass: the other operands run as one fused program straight
+  // into the caller's bitmap, then every long list goes through its lookup kernel, which folds the bitmap in on
+  // the way out (EvalParams::comb_*), in place; the last kernel also counts.
+  {
+    const int root = nnodes - 1, op = nodes[root].op;
+    if (op == FLE_OP_AND || op == FLE_OP_OR) {
+      std::vector<int> operands, todo(1, root), big;
+      std::vector<fle_pred_node> joined;
+      int njoined = 0;
+      bool flat_ok = true;
+      while (!todo.empty()) {
+        const int k = todo.back();
+        todo.pop_back();
+        if (nodes[k].op == op && has_big[k]) {
+          todo.push_back(rhs[k]);
+          todo.push_back(lhs[k]);
+        } else {
+          operands.push_back(k);
+        }
+      }
+      for (int k : operands) {
+        if (!has_big[k]) {
+          joined.insert(joined.end(), nodes + start[k], nodes + k + 1);
+          if (++njoined > 1) joined.push_back(fle_pred_node{op, 0, 0, nullptr, 0, 0});
+        } else if (nodes[k].op == FLE_OP_IN) {
+          big.push_back(k);
+        } else {
+          flat_ok = false;  // a long list below another operator: the general regrouping below
+        }
+      }
+      if (flat_ok && !big.empty()) {
+        int rc = FLE_OK;
+        bool have = false;
+        if (njoined > 0) {
+          std::vector<int> map(ncols, -1);
+          std::vector<fle_col_desc> dc;
+          bool consts_only = true;
+          for (auto& nd : joined) {
+            if (nd.op == FLE_OP_AND || nd.op == FLE_OP_OR || nd.op == FLE_OP_ALL || nd.op == FLE_OP_NONE) continue;
+            consts_only = false;
+            if (map[nd.col] < 0) { map[nd.col] = (int)dc.size(); dc.push_back(cols[nd.col]); }
+            nd.col = map[nd.col];
+          }
+          if (consts_only) dc.push_back(cols[0]);  // constants need a column to launch on
+          LoweredProgram lpj;
+          rc = prepare_eval(ctx, dc.data(), (int)dc.size(), joined.data(), (int)joined.size(), &lpj);
+          if (rc == FLE_OK) rc = launch_prepared(ctx, &lpj, dc.data(), (int)dc.size(), first_row, n, bitmap_dev, nullptr);
+          if (rc != FLE_OK) return rc;
+          have = true;
+        }
+        for (size_t b = 0; b < big.size() && rc == FLE_OK; ++b) {
+          fle_pred_node leaf = nodes[big[b]];
+          const fle_col_desc dc = cols[leaf.col];
+          leaf.col = 0;
+          LoweredProgram lpb;
+          rc = prepare_eval(ctx, &dc, 1, &leaf, 1, &lpb);
+          if (rc != FLE_OK) return rc;
+          if (have) {
+            lpb.p.comb_bm = bitmap_dev;
+            lpb.p.comb_op = op == FLE_OP_AND ? FOLD_AND : FOLD_OR;
+          }
+          rc = launch_prepared(ctx, &lpb, &dc, 1, first_row, n, bitmap_dev, b + 1 == big.size() ? count_dev : nullptr);
+          if (rc == FLE_E_UNSUPPORTED && have) {
+            // (no lookup kernel for this list, e.g. the lookup kernels are switched off: materialise and combine word by word)
+            flat_ok = false;
+            break;
+          }
+          if (rc != FLE_OK) return rc;
+          have = true;
+        }
+        if (flat_ok) return rc;
+      }
+    }
   }
   const int64_t nwords = (n + 63) / 64;
   // temporary bitmaps: one per long list + at most one per operator chain, carved out of a grow-only

@@ -261,7 +261,8 @@ __device__ __forceinline__ void eval1_body(const EvalParams& P) {
     // bw 4 0.91 -> 0.95, bw 12 1.02 -> 1.04)
 #pragma unroll 2
     for (int q = 0; q < gpt; ++q) {
-      const uint64_t r = finish_word(pr.run(P, SmemGroup{a}), g, P.nrows);
+      const uint64_t other = comb_load(P, g);
+      const uint64_t r = comb_apply(P, finish_word(pr.run(P, SmemGroup{a}), g, P.nrows), other);
       P.bitmap[g] = r;
       cnt += __popcll(r);
       a += kGroupStride;
@@ -275,7 +276,8 @@ __device__ __forceinline__ void eval1_body(const EvalParams& P) {
   // ragged remainder (< T groups), planes straight from global memory
   for (int64_t g = ntiles * T + (int64_t)blockIdx.x * NT + threadIdx.x; g < P.ngroups;
        g += (int64_t)gridDim.x * NT) {
-    const uint64_t r = finish_word(pr.run(P, GlobalGroup{P.planes[0] + g * BW}), g, P.nrows);
+    const uint64_t other = comb_load(P, g);
+    const uint64_t r = comb_apply(P, finish_word(pr.run(P, GlobalGroup{P.planes[0] + g * BW}), g, P.nrows), other);
     P.bitmap[g] = r;
     cnt += __popcll(r);
   }

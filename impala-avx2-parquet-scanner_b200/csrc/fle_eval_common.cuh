@@ -113,6 +113,16 @@ __device__ __forceinline__ void group_collect_pending(const GroupView& g, uint32
   }
 }
 
+// the optional second operand of the single-IN-list kernels (EvalParams::comb_*)
+__device__ __forceinline__ uint64_t comb_load(const EvalParams& P, int64_t g) {
+  return P.comb_op ? *((const volatile uint64_t*)(P.comb_bm + g)) : 0ull;
+}
+__device__ __forceinline__ uint64_t comb_apply(const EvalParams& P, uint64_t r, uint64_t other) {
+  if (P.comb_op == FOLD_AND) return r & other;
+  if (P.comb_op == FOLD_OR) return r | other;
+  return r;
+}
+
 // block-wide reduction of the popcounts (and, for fused aggregates, of a second 64-bit sum kept in
 // partial[gridDim.x ...]) + "last block sums", so the launch needs no memset/atomics on the
 // result slots.  With a group attached (P.grp_world > 1) the last block also sums the totals over

@@ -247,7 +247,8 @@ __global__ void __launch_bounds__(256) eval_in_kernel(const __grid_constant__ Ev
     uint32_t a = stage0 + stage * P.stage_bytes + thread_off;
     int64_t g = tile * T + thread_g;
     for (int q = 0; q < gpt; ++q) {
-      const uint64_t r = finish_row_order(dec.run(InSmemGroup{a}), negmask, g, P.nrows);
+      const uint64_t other = comb_load(P, g);
+      const uint64_t r = comb_apply(P, finish_row_order(dec.run(InSmemGroup{a}), negmask, g, P.nrows), other);
       P.bitmap[g] = r;
       cnt_bits += __popcll(r);
       a += kGroupStride;
@@ -260,7 +261,8 @@ __global__ void __launch_bounds__(256) eval_in_kernel(const __grid_constant__ Ev
   }
   for (int64_t g = ntiles * T + (int64_t)blockIdx.x * NT + threadIdx.x; g < P.ngroups;
        g += (int64_t)gridDim.x * NT) {
-    const uint64_t r = finish_row_order(dec.run(InGlobalGroup{P.planes[0] + g * BW}), negmask, g, P.nrows);
+    const uint64_t other = comb_load(P, g);
+    const uint64_t r = comb_apply(P, finish_row_order(dec.run(InGlobalGroup{P.planes[0] + g * BW}), negmask, g, P.nrows), other);
     P.bitmap[g] = r;
     cnt_bits += __popcll(r);
   }
@@ -506,7 +508,8 @@ __global__ void __launch_bounds__(kInWideThreads, 1) eval_in_wide_kernel(const _
       __syncwarp();
       if ((threadIdx.x & 31u) == 0) mbar_arrive(empty0 + stage * 8);  // this warp is done with the stage
       const int64_t g = tile * T + thread_g;
-      const uint64_t r = finish_row_order(dec.compute(pl), negmask, g, P.nrows);
+      const uint64_t other = comb_load(P, g);  // (issued before the lookups: its latency hides behind them)
+      const uint64_t r = comb_apply(P, finish_row_order(dec.compute(pl), negmask, g, P.nrows), other);
       P.bitmap[g] = r;
       cnt_bits += __popcll(r);
       if (++stage == nst) {
@@ -516,7 +519,8 @@ __global__ void __launch_bounds__(kInWideThreads, 1) eval_in_wide_kernel(const _
     }
     for (int64_t g = ntiles * T + (int64_t)blockIdx.x * NC + threadIdx.x; g < P.ngroups;
          g += (int64_t)gridDim.x * NC) {
-      const uint64_t r = finish_row_order(dec.run(InGlobalGroup{P.planes[0] + g * BW}), negmask, g, P.nrows);
+      const uint64_t other = comb_load(P, g);
+      const uint64_t r = comb_apply(P, finish_row_order(dec.run(InGlobalGroup{P.planes[0] + g * BW}), negmask, g, P.nrows), other);
       P.bitmap[g] = r;
       cnt_bits += __popcll(r);
     }

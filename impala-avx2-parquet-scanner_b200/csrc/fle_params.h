@@ -129,6 +129,10 @@ struct EvalParams {
   uint64_t grp_timeout_ns;
   PassDesc passes[kMaxPasses];
   CombDesc combs[kMaxCombs];
+  // single-IN-list kernels only: the list's bitmap is combined with an earlier bitmap on the way out,
+  // out[g] = IN(g) AND / OR comb_bm[g] (comb_op = FOLD_AND / FOLD_OR, 0 = none; comb_bm may be the output itself)
+  const uint64_t* comb_bm;
+  int32_t comb_op, comb_pad;
   // IN list on a narrow column (bw <= 7) evaluated in the plane domain (fle_eval1.cu, InMuxRegs):
   // in_masks[c] says whether code c is a member of the list -- as ~0 / 0 where the term is ANDed in on the
   // ALU pipe, as 1 / 0 where it is multiplied in on the FMA pipe (in_mux_term_on_fma)
