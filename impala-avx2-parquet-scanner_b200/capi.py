@@ -27,7 +27,7 @@ EXPORTS = [
     "fle_ctx_get_option", "fle_ctx_launch_count", "fle_last_error", "fle_strerror", "fle_version",
     "fle_device_count", "fle_host_alloc", "fle_host_free", "fle_dev_alloc", "fle_dev_free", "fle_h2d",
     "fle_d2h", "fle_encoded_bytes", "fle_pack_u32", "fle_pack_u32_dev", "fle_unpack_u32",
-    "fle_unpack_u32_dev", "fle_eval", "fle_eval_dev", "fle_bitmap_count_dev", "fle_intersect_bitset",
+    "fle_unpack_u32_dev", "fle_unpack_u8_dev", "fle_unpack_u16_dev", "fle_eval", "fle_eval_dev", "fle_bitmap_count_dev", "fle_intersect_bitset",
     "fle_intersect_bitset_dev", "fle_bitmap_select_dev", "fle_gather_dev", "fle_sum_product_dev",
     "fle_page_parse", "fle_realign_dev", "fle_plain_eval_dev", "fle_dict_encode_dev", "fle_eval_codegen",
     "fle_eval_sum_product_dev", "fle_group_create_local", "fle_group_export", "fle_group_open", "fle_group_close",
@@ -118,7 +118,7 @@ def load_library() -> C.CDLL:
     L.fle_encoded_bytes.restype = C.c_size_t
     for f in (L.fle_pack_u32, L.fle_pack_u32_dev):
         f.argtypes = [vp, vp, i64, i32, vp, C.c_size_t, C.POINTER(C.c_size_t)]
-    for f in (L.fle_unpack_u32, L.fle_unpack_u32_dev):
+    for f in (L.fle_unpack_u32, L.fle_unpack_u32_dev, L.fle_unpack_u8_dev, L.fle_unpack_u16_dev):
         f.argtypes = [vp, vp, C.c_size_t, i32, i64, i64, vp]
     for f in (L.fle_eval, L.fle_eval_dev):
         f.argtypes = [vp, C.POINTER(ColDesc), i32, C.POINTER(PredNode), i32, i64, i64, vp, vp]
@@ -314,6 +314,17 @@ class FleContext:
             out = torch.empty(n, dtype=torch.int32, device=words.device)
         self._check(self.lib.fle_unpack_u32_dev(self.h, words.data_ptr(), words.numel() * words.element_size(), bw,
                                                 first_row, n, out.data_ptr()))
+        return out
+
+    def unpack_narrow_dev(self, words, bw: int, first_row: int, n: int, out=None):
+        """1-byte values for bw <= 8, 2-byte values for bw <= 16 (FleDecoder::Get<T> for int8 / int16 columns)."""
+        import torch
+        es = 1 if bw <= 8 else 2
+        if out is None:
+            out = torch.empty(n, dtype=torch.uint8 if es == 1 else torch.int16, device=words.device)
+        es = out.element_size()
+        fn = self.lib.fle_unpack_u8_dev if es == 1 else self.lib.fle_unpack_u16_dev
+        self._check(fn(self.h, words.data_ptr(), words.numel() * words.element_size(), bw, first_row, n, out.data_ptr()))
         return out
 
     def make_col_descs(self, cols: Sequence):

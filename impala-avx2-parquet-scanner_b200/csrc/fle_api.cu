@@ -557,6 +557,31 @@ int fle_unpack_u32_dev(fle_ctx* ctx, const uint8_t* enc_dev, size_t enc_len, int
   return launch_unpack_u32(ctx, reinterpret_cast<const uint64_t*>(p), bw, n, out_dev);
 }
 
+static int unpack_narrow_dev(fle_ctx* ctx, const uint8_t* enc_dev, size_t enc_len, int bw, int64_t first_row, int64_t n,
+                             int elem_size, void* out_dev) {
+  if (n < 0 || first_row < 0 || !enc_dev || (n > 0 && !out_dev)) return set_error(ctx, FLE_E_INVALID, "bad unpack arguments");
+  if (bw < 1 || bw > 8 * elem_size) return set_error(ctx, FLE_E_INVALID, "bit width does not fit the output element");
+  if (first_row & 63) return set_error(ctx, FLE_E_ALIGN, "unpack_dev: first_row must be a multiple of 64");
+  const int64_t g0 = first_row / 64, G = (n + 63) / 64;
+  if ((uint64_t)(g0 + G) * bw * 8u > enc_len) return set_error(ctx, FLE_E_BUFFER, "rows beyond the encoded buffer");
+  const uint8_t* p = enc_dev + (uint64_t)g0 * bw * 8u;
+  if ((reinterpret_cast<uintptr_t>(p) & 15) || (reinterpret_cast<uintptr_t>(out_dev) & 15))
+    return set_error(ctx, FLE_E_ALIGN, "narrow unpack: enc and out must be 16-byte aligned");
+  return launch_unpack_narrow(ctx, reinterpret_cast<const uint64_t*>(p), bw, n, elem_size, out_dev);
+}
+
+int fle_unpack_u8_dev(fle_ctx* ctx, const uint8_t* enc_dev, size_t enc_len, int bw, int64_t first_row, int64_t n,
+                      uint8_t* out_dev) {
+  FLE_CHECK_CTX(ctx);
+  return unpack_narrow_dev(ctx, enc_dev, enc_len, bw, first_row, n, 1, out_dev);
+}
+
+int fle_unpack_u16_dev(fle_ctx* ctx, const uint8_t* enc_dev, size_t enc_len, int bw, int64_t first_row, int64_t n,
+                       uint16_t* out_dev) {
+  FLE_CHECK_CTX(ctx);
+  return unpack_narrow_dev(ctx, enc_dev, enc_len, bw, first_row, n, 2, out_dev);
+}
+
 // Host variants: values/planes cross PCIe in chunks through the context's two staging buffers.
 static const int64_t kCodecChunkValues = 32ll << 20;  // 32 Mi values (128 MiB of u32) per chunk
 

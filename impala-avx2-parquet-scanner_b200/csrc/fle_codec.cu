@@ -289,6 +289,130 @@ unpack_tma_kernel(const uint64_t* __restrict__ enc, int64_t ngroups, int64_t nva
   }
 }
 
+// Narrow decode targets.  FleDecoder::Get<T> serves int8 / int16 columns from u8 / u16 staging for
+// bw <= 8 / <= 16 (fle-encoding.h:236-238, :8354-8361; dict-test.cc:64-157): writing 4 bytes per value
+// where 1-2 do is 2.5-3.5x the necessary HBM write traffic at bw <= 8.  Same plane-side pipeline as
+// unpack_tma_kernel; the transposed words already hold two 16-bit values each (rows k and 32 + k),
+// byte permutes put neighbouring rows next to each other, and the value tile is 64 * ES bytes per
+// group (16-byte chunks rotated by the row, copied out with coalesced 128-bit stores).
+// Algorithmic bytes per group: bw * 8 + 64 * ES.
+template <int BW, int ES>
+__global__ void __launch_bounds__(kCodecThreads)
+unpack_narrow_kernel(const uint64_t* __restrict__ enc, int64_t ngroups, int64_t nvals, uint8_t* __restrict__ out) {
+  static_assert((ES == 1 && BW <= 8) || (ES == 2 && BW <= 16), "u8 for bw <= 8, u16 for bw <= 16");
+  using PT = PlaneTile<BW>;
+  constexpr int kStages = 2;
+  constexpr int kRowBytes = 64 * ES, kChunks = kRowBytes / 16;  // 4 or 8 chunks per group
+  constexpr int kTileBytes = kCodecThreads * kRowBytes;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t tile = smem_u32(smem);
+  const uint32_t stage0 = tile + kTileBytes;
+  constexpr uint32_t kStageStride = (PT::kBytes + 127) / 128 * 128;
+  const uint32_t bar0 = stage0 + kStages * kStageStride;
+  const int t = threadIdx.x;
+  const int64_t ntiles_full = ngroups / PT::kGroups;
+  if (t == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(bar0 + s * 8, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue = [&](int stage, int64_t tl) {
+    const uint32_t bar = bar0 + stage * 8;
+    mbar_arrive_expect_tx(bar, 8 * PT::kSegBytes);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(enc) + (uint64_t)tl * PT::kGroups * BW * 8;
+#pragma unroll
+    for (int s = 0; s < 8; ++s)
+      tma_load_1d(stage0 + stage * kStageStride + s * PT::kSegStride, src + (uint64_t)s * PT::kSegBytes, PT::kSegBytes, bar);
+  };
+  if (t == 0 && (int64_t)blockIdx.x < ntiles_full) issue(0, blockIdx.x);
+  auto chunk_addr = [&](int row, int chunk) { return tile + row * kRowBytes + (((chunk + row + (row >> 4)) & (kChunks - 1)) << 4); };
+
+  const int64_t ntiles = (ngroups + PT::kGroups - 1) / PT::kGroups;
+  int stage = 0;
+  uint32_t parity = 0;
+  for (int64_t tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+    const bool full = tl < ntiles_full;
+    const int row = full ? PT::thread_group(t) : t;
+    const int64_t g = tl * PT::kGroups + row;
+    uint64_t w[BW];
+    if (full) {
+      if (t == 0) {
+        const int64_t nxt = tl + gridDim.x;
+        if (nxt < ntiles_full) issue(stage ^ 1, nxt);
+      }
+      mbar_wait(bar0 + stage * 8, parity);
+      const uint32_t a = stage0 + stage * kStageStride + PT::thread_off(t);
+      if constexpr (BW % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < BW; i += 2) lds128(a + i * 8, w[i], w[i + 1 < BW ? i + 1 : i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < BW; ++i) w[i] = lds64(a + i * 8);
+      }
+      stage ^= 1;
+      if (stage == 0) parity ^= 1u;
+    } else if (g < ngroups) {
+      const uint64_t* src = enc + g * BW;
+#pragma unroll
+      for (int i = 0; i < BW; ++i) w[i] = __ldg(src + i);
+    }
+    if (g < ngroups) {
+      uint32_t A[32];  // after the transpose A[k] = value(row k) | value(row 32 + k) << 16
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        A[31 - i] = i < BW ? (uint32_t)(w[i < BW ? i : 0] >> 32) : 0u;
+        A[15 - i] = i < BW ? (uint32_t)(w[i < BW ? i : 0]) : 0u;
+      }
+      transpose32(A);
+      if constexpr (ES == 2) {
+        // chunk c (8 values): rows 8c..8c+7; rows 0..31 come from the low halves, rows 32..63 from the high halves
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = (c & 3) * 8 + 2 * j;
+            o[j] = __byte_perm(A[k], A[k + 1], c < 4 ? 0x5410 : 0x7632);
+          }
+          sts128u(chunk_addr(row, c), o[0], o[1], o[2], o[3]);
+        }
+      } else {
+        // chunk c (16 values): rows 16c..16c+15; a value is byte 0 (rows 0..31) or byte 2 (rows 32..63) of its word
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = (c & 1) * 16 + 4 * j;
+            const uint32_t sel = c < 2 ? 0x0040 : 0x0062;
+            const uint32_t lo = __byte_perm(A[k], A[k + 1], sel), hi = __byte_perm(A[k + 2], A[k + 3], sel);
+            o[j] = __byte_perm(lo, hi, 0x5410);
+          }
+          sts128u(chunk_addr(row, c), o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+    __syncthreads();
+    const int64_t b0 = tl * (int64_t)kTileBytes;  // first output byte of the tile
+    const int64_t nbytes = nvals * ES;
+#pragma unroll
+    for (int it = 0; it < kChunks; ++it) {
+      const int L = it * kCodecThreads + t;  // 16-byte chunk index inside the tile
+      const int64_t bi = b0 + (int64_t)L * 16;
+      if (bi >= nbytes) continue;
+      uint32_t a, b, c, d;
+      lds128u(chunk_addr(L / kChunks, L % kChunks), a, b, c, d);
+      if (bi + 16 <= nbytes) {
+        stg_stream128(out + bi, make_uint4(a, b, c, d));
+      } else {
+        const uint32_t wds[4] = {a, b, c, d};
+        for (int q = 0; q < (int)(nbytes - bi); ++q) out[bi + q] = (uint8_t)(wds[q >> 2] >> ((q & 3) * 8));
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // Unpack with warp-private copy-out (codec_variant = 3): same data path as unpack_tma_kernel, but a
 // warp copies out the 32 rows its own lanes wrote (two adjacent rows = 512 contiguous bytes per
 // store instruction), so the two CTA barriers around the copy-out become __syncwarp, and the plane
@@ -634,6 +758,17 @@ UnpackFn unpack_bulk_table_entry(int bw, Seq<I...>) {
   static const UnpackFn tab[] = {unpack_bulk_kernel<I>...};
   return tab[bw - 1];
 }
+typedef void (*UnpackNarrowFn)(const uint64_t*, int64_t, int64_t, uint8_t*);
+template <int... I>
+UnpackNarrowFn unpack_u8_table_entry(int bw, Seq<I...>) {
+  static const UnpackNarrowFn tab[] = {unpack_narrow_kernel<I, 1>...};
+  return tab[bw - 1];
+}
+template <int... I>
+UnpackNarrowFn unpack_u16_table_entry(int bw, Seq<I...>) {
+  static const UnpackNarrowFn tab[] = {unpack_narrow_kernel<I, 2>...};
+  return tab[bw - 1];
+}
 template <int... I>
 PackFn pack_tma_table_entry(int bw, Seq<I...>) {
   static const PackFn tab[] = {pack_tma_kernel<I>...};
@@ -731,6 +866,27 @@ int launch_unpack_u32(fle_ctx* ctx, const uint64_t* enc_dev, int bw, int64_t n, 
   fn<<<codec_grid(ctx, G), kCodecThreads, 0, ctx->stream>>>(enc_dev, G, n, out_dev);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(ctx, e, "unpack_kernel launch");
+  ctx->launches += 1;
+  return FLE_OK;
+}
+
+int launch_unpack_narrow(fle_ctx* ctx, const uint64_t* enc_dev, int bw, int64_t n, int elem_size, void* out_dev) {
+  if (elem_size != 1 && elem_size != 2) return set_error(ctx, FLE_E_INVALID, "narrow unpack writes 1- or 2-byte values");
+  if (bw < 1 || bw > 8 * elem_size) return set_error(ctx, FLE_E_INVALID, "bit width does not fit the output element");
+  if (n == 0) return FLE_OK;
+  const int64_t G = (n + 63) / 64;
+  UnpackNarrowFn fn = elem_size == 1 ? unpack_u8_table_entry(bw, MakeSeq<8>::type()) : unpack_u16_table_entry(bw, MakeSeq<16>::type());
+  const size_t stage = (plane_tile_bytes(bw, MakeSeq<32>::type()) + 127) / 128 * 128;
+  const size_t smem = (size_t)kCodecThreads * 64 * elem_size + 2 * stage + 64;
+  int rc = raise_smem_limit(ctx, (const void*)fn, smem);
+  if (rc != FLE_OK) return rc;
+  int per_sm = std::max<int>(1, std::min<int>(8, (int)((size_t)ctx->max_smem_per_sm / (smem + 1024))));
+  per_sm = std::min(per_sm, ctx->codec_ctas_per_sm > 0 ? ctx->codec_ctas_per_sm : 4);
+  const int64_t ntiles = (G + kCodecThreads - 1) / kCodecThreads;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)ctx->num_sms * per_sm));
+  fn<<<grid, kCodecThreads, smem, ctx->stream>>>(enc_dev, G, n, static_cast<uint8_t*>(out_dev));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(ctx, e, "unpack_narrow kernel launch");
   ctx->launches += 1;
   return FLE_OK;
 }

@@ -190,6 +190,7 @@ int launch_bitmap_combine(fle_ctx* ctx, const uint64_t* const* leaf_bitmaps_dev,
                           uint64_t* count_dev);
 int launch_pack_u32(fle_ctx* ctx, const uint32_t* vals_dev, int64_t n, int bw, uint64_t* enc_dev);
 int launch_unpack_u32(fle_ctx* ctx, const uint64_t* enc_dev, int bw, int64_t n, uint32_t* out_dev);
+int launch_unpack_narrow(fle_ctx* ctx, const uint64_t* enc_dev, int bw, int64_t n, int elem_size, void* out_dev);
 // fle_bitmap.cu: non-null rows per nullable column (counts_dev[c], 0 for required columns), one launch
 int launch_def_counts(fle_ctx* ctx, const fle_col_desc* cols, int ncols, int64_t n, uint64_t* counts_dev);
 int launch_bitmap_count(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nbits, uint64_t* count_dev);

@@ -174,6 +174,15 @@ int fle_unpack_u32(fle_ctx* ctx, const uint8_t* enc, size_t enc_len, int bit_wid
 int fle_unpack_u32_dev(fle_ctx* ctx, const uint8_t* enc_dev, size_t enc_len, int bit_width,
                        int64_t first_row, int64_t n, uint32_t* out_dev);
 
+/* Narrow decode targets: FleDecoder::Get<T> fills 1-byte values for bit_width <= 8 and 2-byte values for
+ * bit_width <= 16 (the u8 / u16 staging of fle-encoding.h:236-238, :8354-8361, used by int8 / int16 columns,
+ * dict-test.cc:64-157).  Same contract as fle_unpack_u32_dev with out_dev = n values of 1 / 2 bytes
+ * (16-byte aligned); FLE_E_INVALID when bit_width exceeds the element. */
+int fle_unpack_u8_dev(fle_ctx* ctx, const uint8_t* enc_dev, size_t enc_len, int bit_width,
+                      int64_t first_row, int64_t n, uint8_t* out_dev);
+int fle_unpack_u16_dev(fle_ctx* ctx, const uint8_t* enc_dev, size_t enc_len, int bit_width,
+                       int64_t first_row, int64_t n, uint16_t* out_dev);
+
 /* ---- fused predicate evaluation --------------------------------------------------------- */
 /* Replaces, in ONE pass that reads every encoded byte once:
  *   FleDecoder::Eq/Lt/Le/Gt/Ge/In            fle-encoding.h:7962-8313   (leaves)

@@ -680,3 +680,28 @@ def test_dict_build_on_device(ctx, oracle):
     with pytest.raises(fle_b200.FleError) as ei:
         ctx.dict_encode_dev(big)
     assert ei.value.code == fle_b200.capi.E_DICT_FULL
+
+
+@pytest.mark.parametrize("bw", list(range(1, 17)))
+def test_unpack_narrow_targets(ctx, oracle, bw):
+    """FleDecoder::Get<T> for int8 / int16 columns: 1-byte values for bw <= 8, 2-byte values for bw <= 16
+    (fle-encoding.h:236-238, :8354-8361), full tiles, ragged tails and group offsets."""
+    import torch
+    rng = np.random.default_rng(1600 + bw)
+    for n in (1, 63, 64 * 128, 64 * 128 * 3 + 64 * 17 + 9):
+        vals = rng.integers(0, 1 << bw, size=n, dtype=np.uint64).astype(np.uint32)
+        words = torch.from_numpy(oracle.pack(vals, bw).view(np.int64)).cuda()
+        for es in ((1, 2) if bw <= 8 else (2,)):
+            out = torch.full((n + 32,), -1, dtype=torch.uint8 if es == 1 else torch.int16, device="cuda")
+            ctx.unpack_narrow_dev(words, bw, 0, n, out=out[:n])
+            torch.cuda.synchronize()
+            got = out.cpu().numpy()
+            assert (got[:n].astype(np.uint16 if es == 2 else np.uint8) == vals).all(), (bw, n, es)
+            assert (got[n:] == -1 if es == 2 else got[n:] == 255).all(), "wrote past the end"
+        if n > 64 * 130:
+            first = 64 * 128
+            out = ctx.unpack_narrow_dev(words, bw, first, n - first)
+            torch.cuda.synchronize()
+            assert (out.cpu().numpy().astype(np.uint16 if bw > 8 else np.uint8) == vals[first:]).all()
+    with pytest.raises(Exception):
+        ctx.unpack_narrow_dev(words, 9, 0, 64, out=torch.empty(64, dtype=torch.uint8, device="cuda"))
