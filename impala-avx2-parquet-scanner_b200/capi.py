@@ -27,7 +27,7 @@ EXPORTS = [
     "fle_ctx_get_option", "fle_ctx_launch_count", "fle_last_error", "fle_strerror", "fle_version",
     "fle_device_count", "fle_host_alloc", "fle_host_free", "fle_dev_alloc", "fle_dev_free", "fle_h2d",
     "fle_d2h", "fle_encoded_bytes", "fle_pack_u32", "fle_pack_u32_dev", "fle_unpack_u32",
-    "fle_unpack_u32_dev", "fle_unpack_u8_dev", "fle_unpack_u16_dev", "fle_eval", "fle_eval_dev", "fle_bitmap_count_dev", "fle_intersect_bitset",
+    "fle_unpack_u32_dev", "fle_unpack_u8_dev", "fle_unpack_u16_dev", "fle_eval", "fle_eval_dev", "fle_eval_no_nulls_dev", "fle_bitmap_count_dev", "fle_intersect_bitset",
     "fle_intersect_bitset_dev", "fle_bitmap_select_dev", "fle_gather_dev", "fle_sum_product_dev",
     "fle_page_parse", "fle_realign_dev", "fle_plain_eval_dev", "fle_dict_encode_dev", "fle_eval_codegen",
     "fle_eval_sum_product_dev", "fle_group_create_local", "fle_group_export", "fle_group_open", "fle_group_close",
@@ -122,6 +122,7 @@ def load_library() -> C.CDLL:
         f.argtypes = [vp, vp, C.c_size_t, i32, i64, i64, vp]
     for f in (L.fle_eval, L.fle_eval_dev):
         f.argtypes = [vp, C.POINTER(ColDesc), i32, C.POINTER(PredNode), i32, i64, i64, vp, vp]
+    L.fle_eval_no_nulls_dev.argtypes = [vp, C.POINTER(ColDesc), i32, C.POINTER(PredNode), i32, i64, i64, vp, vp, vp]
     L.fle_bitmap_count_dev.argtypes = [vp, vp, i64, vp]
     for f in (L.fle_intersect_bitset, L.fle_intersect_bitset_dev):
         f.argtypes = [vp, vp, i64, vp, i64]
@@ -357,6 +358,22 @@ class FleContext:
         self._check(self.lib.fle_eval_dev(self.h, descs, len(cols), nodes, len(nodes), first_row, n,
                                           bitmap.data_ptr(), count.data_ptr()))
         return bitmap, count
+
+    def eval_no_nulls_dev(self, cols: Sequence, program: Sequence[tuple], n: int, bitmap=None, out=None, prepared=None):
+        """OPTIONAL columns, no host sync: returns (bitmap, out) with out = int64[2] CUDA tensor (count, NULL rows found);
+        the result is valid iff out[1] == 0."""
+        import torch
+        dev = cols[0][0].device
+        if bitmap is None:
+            bitmap = torch.empty(max(1, (n + 63) // 64), dtype=torch.int64, device=dev)
+        if out is None:
+            out = torch.zeros(2, dtype=torch.int64, device=dev)
+        if prepared is None:
+            prepared = (self.make_col_descs(cols),) + _build_program(program)
+        descs, nodes, _keep = prepared
+        self._check(self.lib.fle_eval_no_nulls_dev(self.h, descs, len(cols), nodes, len(nodes), 0, n, bitmap.data_ptr(),
+                                                   out.data_ptr(), out.data_ptr() + 8))
+        return bitmap, out
 
     def bitmap_count_dev(self, bitmap, nbits: int, count=None):
         import torch

@@ -397,6 +397,7 @@ int fle_ctx_destroy(fle_ctx* ctx) {
   }
   if (ctx->d_count) cudaFree(ctx->d_count);
   if (ctx->d_split) cudaFree(ctx->d_split);
+  if (ctx->d_realign) cudaFree(ctx->d_realign);
   if (ctx->d_tile_state) cudaFree(ctx->d_tile_state);
   if (ctx->ev_prefetch) cudaEventDestroy(ctx->ev_prefetch);
   fle::group_release(ctx);
@@ -651,6 +652,32 @@ int fle_eval_dev(fle_ctx* ctx, const fle_col_desc* cols, int ncols, const fle_pr
   if (any_nullable(cols, ncols))
     return eval_dev_nullable(ctx, cols, ncols, nodes, nnodes, first_row, n, bitmap_dev, count_dev);
   return launch_eval(ctx, cols, ncols, nodes, nnodes, first_row, n, bitmap_dev, count_dev);
+}
+
+// OPTIONAL columns without a host synchronisation: every Impala-written file marks its columns OPTIONAL
+// (hdfs-parquet-table-writer.cc:103-105) and TPC-H holds no NULL, so the def levels only have to be CHECKED.
+int fle_eval_no_nulls_dev(fle_ctx* ctx, const fle_col_desc* cols, int ncols, const fle_pred_node* nodes, int nnodes,
+                          int64_t first_row, int64_t n, uint64_t* bitmap_dev, uint64_t* count_dev, uint64_t* null_rows_dev) {
+  FLE_CHECK_CTX(ctx);
+  if (!cols || !nodes || ncols < 1 || nnodes < 1 || !null_rows_dev) return set_error(ctx, FLE_E_INVALID, "bad arguments");
+  if (ncols > FLE_MAX_COLS) return set_error(ctx, FLE_E_UNSUPPORTED, "too many columns");
+  if (first_row != 0 && any_nullable(cols, ncols))
+    return set_error(ctx, FLE_E_UNSUPPORTED, "nullable columns are evaluated from row 0 of the page");
+  std::vector<fle_col_desc> req(cols, cols + ncols);
+  for (auto& d : req) {
+    if (d.max_def_level > 1) return set_error(ctx, FLE_E_UNSUPPORTED, "max_def_level > 1 (nested types)");
+    d.max_def_level = 0;
+    d.def_planes = nullptr;
+    d.def_bytes = 0;
+  }
+  int rc = FLE_OK;
+  if (any_nullable(cols, ncols)) {
+    rc = launch_def_counts(ctx, cols, ncols, n, nullptr, null_rows_dev);
+  } else {
+    FLE_CUDA_TRY(ctx, cudaMemsetAsync(null_rows_dev, 0, 8, ctx->stream));
+  }
+  if (rc != FLE_OK) return rc;
+  return launch_eval(ctx, req.data(), ncols, nodes, nnodes, first_row, n, bitmap_dev, count_dev);
 }
 
 int fle_eval_codegen(const fle_col_desc* cols, int ncols, const fle_pred_node* nodes, int nnodes, int compile,

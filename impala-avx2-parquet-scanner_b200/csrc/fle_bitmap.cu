@@ -43,29 +43,38 @@ struct DefCountParams {
   const uint64_t* planes[FLE_MAX_COLS];
   int64_t ngroups, nrows;
   unsigned long long* counts;
+  unsigned long long* nulls_total;  // optional: rows whose level is 0, summed over all columns
 };
 
 __global__ void __launch_bounds__(kBmThreads) def_count_kernel(const __grid_constant__ DefCountParams P) {
   __shared__ uint64_t warp_buf[kBmThreads / 32];
   const uint64_t* pl = P.planes[blockIdx.y];
   if (!pl) return;
-  uint64_t c = 0;
+  uint64_t c = 0, rows = 0;
   for (int64_t g = (int64_t)blockIdx.x * kBmThreads + threadIdx.x; g < P.ngroups; g += (int64_t)gridDim.x * kBmThreads) {
     uint64_t w = ldg_stream64(pl + g);
     const int64_t left = P.nrows - g * 64;
     if (left < 64) w &= ~0ull << (64 - left);  // (left >= 1 for every g < ngroups)
     c += __popcll(w);
+    rows += left < 64 ? left : 64;
   }
   const uint64_t t = block_sum<kBmThreads>(c, warp_buf);
+  if (P.nulls_total) {
+    __syncthreads();
+    const uint64_t r = block_sum<kBmThreads>(rows, warp_buf);
+    if (threadIdx.x == 0 && r != t) atomicAdd(P.nulls_total, (unsigned long long)(r - t));
+    return;
+  }
   if (threadIdx.x == 0 && t) atomicAdd(&P.counts[blockIdx.y], (unsigned long long)t);
 }
 
-int launch_def_counts(fle_ctx* ctx, const fle_col_desc* cols, int ncols, int64_t n, uint64_t* counts_dev) {
+int launch_def_counts(fle_ctx* ctx, const fle_col_desc* cols, int ncols, int64_t n, uint64_t* counts_dev, uint64_t* nulls_total_dev) {
   if (ncols < 1 || ncols > FLE_MAX_COLS) return set_error(ctx, FLE_E_INVALID, "bad column count");
   DefCountParams P;
   P.ngroups = (n + 63) / 64;
   P.nrows = n;
   P.counts = reinterpret_cast<unsigned long long*>(counts_dev);
+  P.nulls_total = reinterpret_cast<unsigned long long*>(nulls_total_dev);
   for (int c = 0; c < FLE_MAX_COLS; ++c) P.planes[c] = nullptr;
   for (int c = 0; c < ncols; ++c) {
     if (cols[c].max_def_level == 0) continue;
@@ -74,7 +83,8 @@ int launch_def_counts(fle_ctx* ctx, const fle_col_desc* cols, int ncols, int64_t
     if (cols[c].def_bytes < (uint64_t)P.ngroups * 8u) return set_error(ctx, FLE_E_BUFFER, "def-level stream shorter than the rows requested");
     P.planes[c] = reinterpret_cast<const uint64_t*>(cols[c].def_planes);
   }
-  FLE_CUDA_TRY(ctx, cudaMemsetAsync(counts_dev, 0, (size_t)ncols * 8, ctx->stream));
+  if (nulls_total_dev) FLE_CUDA_TRY(ctx, cudaMemsetAsync(nulls_total_dev, 0, 8, ctx->stream));
+  else FLE_CUDA_TRY(ctx, cudaMemsetAsync(counts_dev, 0, (size_t)ncols * 8, ctx->stream));
   if (P.ngroups == 0) return FLE_OK;
   const int gx = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 4, (P.ngroups + kBmThreads - 1) / kBmThreads));
   def_count_kernel<<<dim3(gx, ncols), kBmThreads, 0, ctx->stream>>>(P);

@@ -716,7 +716,8 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
   if (mode == MODE_JIT) {
     kern = jit_kern;
   } else if (mode == MODE_SINGLE_PASS) {
-    kern = eval1_kernel_for(P.passes[0].type, P.passes[0].k, (int)P.bw[0]);
+    kern = P.plane_skew[0] ? eval1_skew_kernel_for(P.passes[0].type, P.passes[0].k, (int)P.bw[0])
+                           : eval1_kernel_for(P.passes[0].type, P.passes[0].k, (int)P.bw[0]);
     if (!kern) return FLE_E_UNSUPPORTED;
   } else if (mode == MODE_IN_LOOKUP) {
     kern = eval_in_kernel_for((int)P.bw[0]);
@@ -729,7 +730,7 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
     kern = eval1_narrow_kernel_for(P.passes[0].type, P.passes[0].k, (int)P.bw[0]);
     if (!kern) return FLE_E_UNSUPPORTED;
   } else if (mode == MODE_IN_MUX) {
-    kern = eval_in_mux_kernel_for((int)P.bw[0]);
+    kern = P.plane_skew[0] ? eval_in_mux_skew_kernel_for((int)P.bw[0]) : eval_in_mux_kernel_for((int)P.bw[0]);
     if (!kern) return FLE_E_UNSUPPORTED;
     mode = MODE_SINGLE_PASS;  // same tile pipeline and launch shape as the single-pass compare kernels
     mode_reported = MODE_IN_MUX;
@@ -806,7 +807,8 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
     uint32_t coff = 0;
     for (int c = 0; c < P.ncols; ++c) {
       P.col_off[c] = coff;
-      P.seg_stride[c] = (uint32_t)(T / 8) * P.bw[c] * 8u + 16u;
+      // (+ 16: the bank skew between segments; + 16 more for a skewed column, whose aligned superset is staged)
+      P.seg_stride[c] = (uint32_t)(T / 8) * P.bw[c] * 8u + 16u + (P.plane_skew[c] ? 16u : 0u);
       coff += 8u * P.seg_stride[c];
     }
     P.stage_bytes = round_up(coff, 128);
@@ -895,6 +897,109 @@ int prepare_eval(fle_ctx* ctx, const fle_col_desc* cols, int ncols, const fle_pr
   return FLE_OK;
 }
 
+// planes[c] rounded down to 16 bytes + plane_skew[c]; the staged range ends two groups early without slack
+static void apply_skew(EvalParams& P, int ncols, bool slack) {
+  for (int c = 0; c < ncols; ++c) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(P.planes[c]);
+    P.plane_skew[c] = (uint32_t)(a & 15);
+    P.planes[c] = reinterpret_cast<const uint64_t*>(a & ~(uintptr_t)15);
+  }
+  P.staged_groups = slack ? P.ngroups : std::max<int64_t>(0, P.ngroups - 2);
+}
+
+static int launch_prepared_skewed(fle_ctx* ctx, LoweredProgram* lp, const EvalParams& P0, const fle_col_desc* cols, int ncols,
+                                  int64_t first_row, int64_t n, uint64_t* bitmap_dev, uint64_t* count_dev, const AggSpec* agg,
+                                  int sum_bw, bool slack) {
+  (void)cols; (void)first_row; (void)n; (void)bitmap_dev; (void)count_dev;
+  if (agg) return FLE_E_UNSUPPORTED;
+  const PassDesc& p0 = P0.passes[0];
+  const bool single_pass = P0.npasses == 1 && P0.ncombs == 0 && (p0.type == PASS_LT || p0.type == PASS_EQ) &&
+                           (p0.k == 1 || p0.merge) && p0.slot[0] == 0;
+  const bool in_single = P0.npasses == 1 && P0.ncombs == 0 && p0.type == PASS_IN && p0.slot[0] == 0;
+  if (single_pass || (in_single && (int)P0.bw[p0.col] <= ctx->in_mux_bw && (int)p0.lit[1] >= ctx->in_lookup_min)) {
+    EvalParams P1 = P0;
+    const int c = p0.col;
+    P1.ncols = 1;
+    P1.planes[0] = P0.planes[c];
+    P1.bw[0] = P0.bw[c];
+    P1.passes[0].col = 0;
+    apply_skew(P1, 1, slack);
+    int mode = MODE_SINGLE_PASS;
+    if (in_single) {
+      mode = MODE_IN_MUX;
+      std::memset(P1.in_masks, 0, sizeof(P1.in_masks));
+      for (uint32_t j = 0; j < p0.lit[1]; ++j) {
+        const uint32_t code = lp->in_lits[p0.lit[0] + j] & 127u;
+        P1.in_masks[code] = in_mux_term_on_fma((int)P1.bw[0], (int)(code & 7u)) ? 1u : ~0u;
+      }
+    }
+    const int rc = launch_program(ctx, P1, mode, (int)P1.bw[0]);
+    if (rc != FLE_E_UNSUPPORTED) return rc;
+  }
+  if (P0.comb_op) return FLE_E_UNSUPPORTED;
+  if (ctx->eval_jit == 0) return FLE_E_UNSUPPORTED;
+  // specialised multi-column kernel over the images in place (the shape records that its columns are skewed)
+  bool same = lp->jit_state != 0 && lp->jit_agg_col == -2;
+  for (int c = 0; c < ncols && same; ++c) same = lp->jit_bw[c] == P0.bw[c];
+  if (!same) {
+    lp->jit_state = jit_plan(P0, lp->in_lits, &lp->jit_plan, -1, /*skew=*/true) ? 1 : -1;
+    lp->jit_agg_col = -2;  // (marks a skewed plan)
+    for (int c = 0; c < ncols; ++c) lp->jit_bw[c] = P0.bw[c];
+    lp->jit_entry.reset();
+  }
+  if (lp->jit_state != 1) return FLE_E_UNSUPPORTED;
+  if (!lp->jit_entry) lp->jit_entry = jit_lookup(lp->jit_plan.text, n, ctx->eval_jit_min_rows, ctx->eval_jit == 2);
+  if (!lp->jit_entry || lp->jit_entry->rc != FLE_OK) return FLE_E_UNSUPPORTED;
+  EvalParams P1 = P0;
+  apply_skew(P1, ncols, slack);
+  jit_fill_args(lp->jit_plan, P1, lp->in_lits, &lp->jit_args);
+  int rc = launch_program(ctx, P1, MODE_JIT, sum_bw, lp->jit_entry->kern, lp->jit_args.data(), true);
+  if (rc == FLE_E_UNSUPPORTED) rc = launch_program(ctx, P1, MODE_JIT, sum_bw, lp->jit_entry->kern, lp->jit_args.data(), false);
+  return rc;
+}
+
+int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, int ncols,
+                    int64_t first_row, int64_t n, uint64_t* bitmap_dev, uint64_t* count_dev, const AggSpec* agg);
+
+// last resort for columns that are not even 8-byte aligned: an aligned copy of every such column in the context's
+// scratch (funnel-shift kernel), then the ordinary paths
+static int launch_prepared_realigned(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, int ncols, int64_t first_row,
+                                     int64_t n, uint64_t* bitmap_dev, uint64_t* count_dev, const AggSpec* agg) {
+  const int64_t G = (n + 63) / 64, g0 = first_row / 64;
+  std::vector<fle_col_desc> dc(cols, cols + ncols);
+  size_t total = 0;
+  std::vector<size_t> off(ncols, 0);
+  for (int c = 0; c < ncols; ++c) {
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(cols[c].planes) + (uint64_t)g0 * cols[c].bit_width * 8u;
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) continue;
+    off[c] = total;
+    total += ((size_t)G * cols[c].bit_width * 8u + 255) / 256 * 256;
+  }
+  if (total > ctx->realign_cap) {
+    FLE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_realign) cudaFree(ctx->d_realign);
+    ctx->d_realign = nullptr;
+    ctx->realign_cap = 0;
+    FLE_CUDA_TRY(ctx, cudaMalloc(&ctx->d_realign, total));
+    ctx->realign_cap = total;
+  }
+  for (int c = 0; c < ncols; ++c) {
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(cols[c].planes) + (uint64_t)g0 * cols[c].bit_width * 8u;
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+      dc[c].planes = p;
+      dc[c].bytes = cols[c].bytes - (uint64_t)g0 * cols[c].bit_width * 8u;
+      continue;
+    }
+    const size_t nbytes = (size_t)G * cols[c].bit_width * 8u;
+    uint8_t* dst = static_cast<uint8_t*>(ctx->d_realign) + off[c];
+    const int rc = launch_realign(ctx, p, nbytes, dst);
+    if (rc != FLE_OK) return rc;
+    dc[c].planes = dst;
+    dc[c].bytes = (nbytes + 15) / 16 * 16;
+  }
+  return launch_prepared(ctx, lp, dc.data(), ncols, 0, n, bitmap_dev, count_dev, agg);
+}
+
 int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, int ncols,
                     int64_t first_row, int64_t n, uint64_t* bitmap_dev, uint64_t* count_dev, const AggSpec* agg) {
   if (n < 0 || first_row < 0 || (!bitmap_dev && !agg)) return set_error(ctx, FLE_E_INVALID, "bad row range or null bitmap");
@@ -903,7 +1008,7 @@ int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, 
   if (first_row & 63) return set_error(ctx, FLE_E_ALIGN, "first_row must be a multiple of 64");
   EvalParams P = lp->p;  // per-launch copy
   const int64_t G = (n + 63) / 64;
-  bool aligned = true;
+  bool aligned = true, byte_skewed = false, slack = true;
   int sum_bw = 0;
   P.ncols = ncols;
   for (int c = 0; c < ncols; ++c) {
@@ -913,12 +1018,14 @@ int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, 
     const int bw = cols[c].bit_width;
     const uint64_t need = (uint64_t)(first_row / 64 + G) * bw * 8u;
     if (cols[c].bytes < need) return set_error(ctx, FLE_E_BUFFER, "column shorter than the rows requested");
-    if (reinterpret_cast<uintptr_t>(cols[c].planes) & 7)
-      return set_error(ctx, FLE_E_ALIGN, "device plane pointers must be 8-byte aligned");
     const uint8_t* p = reinterpret_cast<const uint8_t*>(cols[c].planes) + (uint64_t)(first_row / 64) * bw * 8u;
     P.planes[c] = reinterpret_cast<const uint64_t*>(p);
     P.bw[c] = (uint32_t)bw;
     if (reinterpret_cast<uintptr_t>(p) & 15) aligned = false;
+    if (reinterpret_cast<uintptr_t>(p) & 7) byte_skewed = true;
+    // staged tiles of a skewed column read 16 bytes past their last group: keep the last groups out of the
+    // staged range unless the buffer is known to extend that far
+    if (cols[c].bytes < need + 16) slack = false;
     sum_bw += bw;
   }
   P.ngroups = G;
@@ -946,6 +1053,15 @@ int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, 
     if (agg) FLE_CUDA_TRY(ctx, cudaMemsetAsync(agg->sum_out, 0, 8, ctx->stream));
     return FLE_OK;
   }
+  P.staged_groups = G;
+  // Columns that are not 16-byte aligned (page payloads inside a file image): the skew-capable kernels read them
+  // in place -- single-pass programs (fle_eval1_skew.cu) and specialised multi-column programs (FLE_JIT_SKEW);
+  // everything else takes an aligned copy first (context scratch), so no caller ever has to realign.
+  if (!aligned && ctx->eval_variant != 0) {
+    const int rc = launch_prepared_skewed(ctx, lp, P, cols, ncols, first_row, n, bitmap_dev, count_dev, agg, sum_bw, slack);
+    if (rc != FLE_E_UNSUPPORTED) return rc;
+  }
+  if (byte_skewed) return launch_prepared_realigned(ctx, lp, cols, ncols, first_row, n, bitmap_dev, count_dev, agg);
   const bool staged_ok = ctx->eval_variant != 0 && aligned;
   // one pass of compare chains folding into one word: the per-bit-width kernels of fle_eval1.cu
   const PassDesc& p0 = P.passes[0];

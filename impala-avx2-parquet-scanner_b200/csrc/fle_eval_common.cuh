@@ -113,6 +113,32 @@ __device__ __forceinline__ void group_collect_pending(const GroupView& g, uint32
   }
 }
 
+// Two consecutive plane words at ANY byte address, from 32-bit loads and a funnel shift (skewed columns,
+// EvalParams::plane_skew).  Up to 3 bytes before the first and 4 after the last word are touched: inside the
+// staged superset for shared memory, inside the column buffer's slack for global memory.
+__device__ __forceinline__ void lds_pair_unaligned(uint32_t addr, bool second, uint64_t& w0, uint64_t& w1) {
+  const uint32_t b = addr & ~3u, sh = (addr & 3u) * 8u;
+  const uint32_t v0 = lds32(b), v1 = lds32(b + 4), v2 = lds32(b + 8);
+  w0 = ((uint64_t)__funnelshift_r(v1, v2, sh) << 32) | __funnelshift_r(v0, v1, sh);
+  w1 = 0;
+  if (second) {
+    const uint32_t v3 = lds32(b + 12), v4 = lds32(b + 16);
+    w1 = ((uint64_t)__funnelshift_r(v3, v4, sh) << 32) | __funnelshift_r(v2, v3, sh);
+  }
+}
+__device__ __forceinline__ void ldg_pair_unaligned(const void* p, bool second, uint64_t& w0, uint64_t& w1) {
+  const unsigned long long a = reinterpret_cast<unsigned long long>(p);
+  const uint32_t* b = reinterpret_cast<const uint32_t*>(a & ~3ull);
+  const uint32_t sh = (uint32_t)(a & 3ull) * 8u;
+  const uint32_t v0 = __ldg(b), v1 = __ldg(b + 1), v2 = __ldg(b + 2);
+  w0 = ((uint64_t)__funnelshift_r(v1, v2, sh) << 32) | __funnelshift_r(v0, v1, sh);
+  w1 = 0;
+  if (second) {
+    const uint32_t v3 = __ldg(b + 3), v4 = __ldg(b + 4);
+    w1 = ((uint64_t)__funnelshift_r(v3, v4, sh) << 32) | __funnelshift_r(v2, v3, sh);
+  }
+}
+
 // the optional second operand of the single-IN-list kernels (EvalParams::comb_*)
 __device__ __forceinline__ uint64_t comb_load(const EvalParams& P, int64_t g) {
   return P.comb_op ? *((const volatile uint64_t*)(P.comb_bm + g)) : 0ull;
@@ -219,15 +245,17 @@ __device__ __forceinline__ void issue_tile(const EvalParams& P, uint32_t bar0, u
                                            int64_t tile, int T) {
   const uint32_t bar = bar0 + stage * 8;
   uint32_t total = 0;
-  for (int c = 0; c < P.ncols; ++c) total += (uint32_t)T * P.bw[c] * 8u;
+  // (a skewed column stages 16 more bytes per segment: the aligned superset of the segment's byte range)
+  for (int c = 0; c < P.ncols; ++c) total += (uint32_t)T * P.bw[c] * 8u + (P.plane_skew[c] ? 128u : 0u);
   mbar_arrive_expect_tx(bar, total);
   for (int c = 0; c < P.ncols; ++c) {
     const uint32_t seg_bytes = (uint32_t)(T >> 3) * P.bw[c] * 8u;
+    const uint32_t copy_bytes = seg_bytes + (P.plane_skew[c] ? 16u : 0u);
     const uint8_t* src = reinterpret_cast<const uint8_t*>(P.planes[c]) + (uint64_t)tile * T * P.bw[c] * 8u;
     const uint32_t dst = stage0 + stage * P.stage_bytes + P.col_off[c];
 #pragma unroll
     for (int s = 0; s < 8; ++s)
-      tma_load_1d(dst + s * P.seg_stride[c], src + (uint64_t)s * seg_bytes, seg_bytes, bar);
+      tma_load_1d(dst + s * P.seg_stride[c], src + (uint64_t)s * seg_bytes, copy_bytes, bar);
   }
 }
 

@@ -39,12 +39,16 @@ struct JitSmemGroup {
   uint32_t a[NCOLS];
   template <int C, int BW>
   __device__ __forceinline__ void load_pair(int i, uint64_t& w0, uint64_t& w1) const {
+#ifdef FLE_JIT_SKEW
+    lds_pair_unaligned(a[C] + i * 8, i + 1 < BW, w0, w1);
+#else
     if constexpr (BW % 2 == 0) {
       lds128(a[C] + i * 8, w0, w1);
     } else {
       w0 = lds64(a[C] + i * 8);
       w1 = (i + 1 < BW) ? lds64(a[C] + (i + 1) * 8) : 0ull;
     }
+#endif
   }
 };
 // ... or in global memory (ragged remainder of the row range)
@@ -53,8 +57,12 @@ struct JitGlobalGroup {
   const uint64_t* p[NCOLS];
   template <int C, int BW>
   __device__ __forceinline__ void load_pair(int i, uint64_t& w0, uint64_t& w1) const {
+#ifdef FLE_JIT_SKEW
+    ldg_pair_unaligned(reinterpret_cast<const uint8_t*>(p[C]) + i * 8, i + 1 < BW, w0, w1);
+#else
     w0 = __ldg(p[C] + i);
     w1 = (i + 1 < BW) ? __ldg(p[C] + i + 1) : 0ull;
+#endif
   }
 };
 
@@ -210,7 +218,11 @@ fle_jit_kernel(const __grid_constant__ fle::EvalParams P, const __grid_constant_
   const int T = NT * gpt;
   const int seg_groups = T >> 3;
   const int nst = P.nstages;  // 0: unstaged launch, every group takes the global-memory loop below
+#ifdef FLE_JIT_SKEW
+  const int64_t ntiles = nst > 0 ? P.staged_groups / T : 0;
+#else
   const int64_t ntiles = nst > 0 ? P.ngroups / T : 0;
+#endif
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < nst; ++s) mbar_init(bar0 + s * 8, 1);

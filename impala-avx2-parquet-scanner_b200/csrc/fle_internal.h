@@ -96,6 +96,8 @@ struct fle_ctx {
   int lit_next = 0;
   uint64_t lit_gen_counter = 0;
   uint64_t* d_count = nullptr;    // 8-byte result slot for host-facing calls
+  void* d_realign = nullptr;      // aligned copies of columns no kernel can read in place, grow-only
+  size_t realign_cap = 0;
   uint64_t* d_split = nullptr;    // temporary bitmaps of regrouped programs (long IN lists), grow-only
   size_t split_cap = 0;           // bytes
   uint64_t* h_count = nullptr;    // pinned
@@ -175,6 +177,9 @@ const void* eval1_kernel_for(int type, int k, int bw);
 // fle_eval1.cu: unstaged kernels for bw 1, 2, 4 (coalesced 128-bit global loads), or nullptr
 const void* eval1_narrow_kernel_for(int type, int k, int bw);
 constexpr int kNarrowUnits = 8;  // 16/32-byte units per thread per tile of the narrow kernels
+// fle_eval1_skew.cu: the same kernels for a column at an arbitrary byte address (bw <= 16; LT chains 1-2, EQ 1), or nullptr
+const void* eval1_skew_kernel_for(int type, int k, int bw);
+const void* eval_in_mux_skew_kernel_for(int bw);
 // fle_eval1.cu: IN list on a narrow column as a multiplexer tree over the planes (bw <= 7), or nullptr
 const void* eval_in_mux_kernel_for(int bw);
 // fle_eval_in.cu: IN list by decode + membership-table lookup (bw <= 16), or nullptr
@@ -192,7 +197,8 @@ int launch_pack_u32(fle_ctx* ctx, const uint32_t* vals_dev, int64_t n, int bw, u
 int launch_unpack_u32(fle_ctx* ctx, const uint64_t* enc_dev, int bw, int64_t n, uint32_t* out_dev);
 int launch_unpack_narrow(fle_ctx* ctx, const uint64_t* enc_dev, int bw, int64_t n, int elem_size, void* out_dev);
 // fle_bitmap.cu: non-null rows per nullable column (counts_dev[c], 0 for required columns), one launch
-int launch_def_counts(fle_ctx* ctx, const fle_col_desc* cols, int ncols, int64_t n, uint64_t* counts_dev);
+int launch_def_counts(fle_ctx* ctx, const fle_col_desc* cols, int ncols, int64_t n, uint64_t* counts_dev,
+                      uint64_t* nulls_total_dev = nullptr);
 int launch_bitmap_count(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nbits, uint64_t* count_dev);
 int launch_intersect(fle_ctx* ctx, uint64_t* root_dev, int64_t n_root, const uint64_t* sub_dev,
                      int64_t n_sub);

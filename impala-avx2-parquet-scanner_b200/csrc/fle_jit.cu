@@ -35,7 +35,7 @@ void emit_fold(std::string& t, int slot, int fold, const std::string& v) {
 
 }  // namespace
 
-bool jit_plan(const EvalParams& P, const std::vector<uint32_t>& in_lits, JitPlan* plan, int agg_col) {
+bool jit_plan(const EvalParams& P, const std::vector<uint32_t>& in_lits, JitPlan* plan, int agg_col, bool skew) {
   JitPlan& J = *plan;
   J.text.clear();
   J.chains.clear();
@@ -153,7 +153,10 @@ bool jit_plan(const EvalParams& P, const std::vector<uint32_t>& in_lits, JitPlan
   if (J.chains.size() > 96 || J.nmask > 2048) return false;  // keep the parameter block < 10 KB
 
   std::string& t = J.text;
-  t = "// generated by fle_jit.cu -- one predicate-program shape\nnamespace fle {\n";
+  t = "// generated by fle_jit.cu -- one predicate-program shape\n";
+  // (the marker makes jit_compile_text define FLE_JIT_SKEW ahead of the kernel skeleton, whose loaders depend on it)
+  if (skew) t += "// FLE_JIT_SKEW: columns at arbitrary byte addresses (EvalParams::plane_skew)\n";
+  t += "namespace fle {\n";
   snprintf(b, sizeof(b), "constexpr int kJitNCols = %d;\n", P.ncols);
   t += b;
   snprintf(b, sizeof(b), "struct JitArgs {\n  uint32_t ini[%d];\n  uint32_t neg[%d];\n  uint32_t mask[%d];\n};\n",
@@ -162,7 +165,11 @@ bool jit_plan(const EvalParams& P, const std::vector<uint32_t>& in_lits, JitPlan
   t += "__device__ __forceinline__ void jit_stage_addr(const EvalParams& P, uint32_t base, uint32_t seg, uint32_t jrow,\n"
        "                                               uint32_t (&a)[kJitNCols]) {\n";
   for (int c = 0; c < P.ncols; ++c) {
-    snprintf(b, sizeof(b), "  a[%d] = base + P.col_off[%d] + seg * P.seg_stride[%d] + jrow * %uu;\n", c, c, c, P.bw[c] * 8u);
+    if (skew)
+      snprintf(b, sizeof(b), "  a[%d] = base + P.col_off[%d] + seg * P.seg_stride[%d] + jrow * %uu + P.plane_skew[%d];\n", c, c, c,
+               P.bw[c] * 8u, c);
+    else
+      snprintf(b, sizeof(b), "  a[%d] = base + P.col_off[%d] + seg * P.seg_stride[%d] + jrow * %uu;\n", c, c, c, P.bw[c] * 8u);
     t += b;
   }
   t += "}\n__device__ __forceinline__ void jit_advance(uint32_t (&a)[kJitNCols]) {\n";
@@ -172,7 +179,11 @@ bool jit_plan(const EvalParams& P, const std::vector<uint32_t>& in_lits, JitPlan
   }
   t += "}\n__device__ __forceinline__ void jit_global_addr(const EvalParams& P, int64_t g, const uint64_t* (&p)[kJitNCols]) {\n";
   for (int c = 0; c < P.ncols; ++c) {
-    snprintf(b, sizeof(b), "  p[%d] = P.planes[%d] + g * %u;\n", c, c, P.bw[c]);
+    if (skew)
+      snprintf(b, sizeof(b), "  p[%d] = reinterpret_cast<const uint64_t*>(reinterpret_cast<const uint8_t*>(P.planes[%d]) + P.plane_skew[%d] + g * %u);\n",
+               c, c, c, P.bw[c] * 8u);
+    else
+      snprintf(b, sizeof(b), "  p[%d] = P.planes[%d] + g * %u;\n", c, c, P.bw[c]);
     t += b;
   }
   t += "}\ntemplate <class L>\n"
@@ -199,7 +210,7 @@ bool jit_plan(const EvalParams& P, const std::vector<uint32_t>& in_lits, JitPlan
     t += b;
   }
   if (agg_col >= 0) {
-    if (agg_col >= P.ncols) return false;
+    if (agg_col >= P.ncols || skew) return false;
     const int bw = (int)P.bw[agg_col];
     snprintf(b, sizeof(b),
              "#define FLE_JIT_AGG 1\n#define FLE_JIT_GPT %d\nconstexpr int kJitAggCol = %d;\nconstexpr int kJitAggBw = %d;\n",
@@ -322,8 +333,9 @@ int jit_compile_text(const std::string& program_text, std::vector<char>* cubin, 
   names.push_back("fle_jit_program.h");
   texts.push_back(program_text.c_str());
   nvrtcProgram prog = nullptr;
-  nvrtcResult r = n->CreateProgram(&prog, "#include \"fle_eval_jit.cuh\"\n", "fle_jit_main.cu", (int)names.size(),
-                                   texts.data(), names.data());
+  const bool skew = program_text.find("// FLE_JIT_SKEW") != std::string::npos;
+  nvrtcResult r = n->CreateProgram(&prog, skew ? "#define FLE_JIT_SKEW 1\n#include \"fle_eval_jit.cuh\"\n" : "#include \"fle_eval_jit.cuh\"\n",
+                                   "fle_jit_main.cu", (int)names.size(), texts.data(), names.data());
   if (r != NVRTC_SUCCESS) {
     if (log) *log = std::string("nvrtcCreateProgram: ") + n->GetErrorString(r);
     return FLE_E_CUDA;

@@ -34,7 +34,7 @@ struct JitEntry {
 
 // P: lowered program with ncols / bw[] filled in.  agg_col >= 0: also generate the fused
 // SUM(plain * dict[code of column agg_col]) over the selected rows.  false: shape not supported
-bool jit_plan(const EvalParams& P, const std::vector<uint32_t>& in_lits, JitPlan* plan, int agg_col = -1);
+bool jit_plan(const EvalParams& P, const std::vector<uint32_t>& in_lits, JitPlan* plan, int agg_col = -1, bool skew = false);
 // the JitArgs parameter block for the current literals
 void jit_fill_args(const JitPlan& plan, const EvalParams& P, const std::vector<uint32_t>& in_lits,
                    std::vector<uint32_t>* args);

@@ -129,6 +129,15 @@ struct EvalParams {
   uint64_t grp_timeout_ns;
   PassDesc passes[kMaxPasses];
   CombDesc combs[kMaxCombs];
+  // Columns whose first group does not sit on a 16-byte boundary (page payloads inside a file image start one
+  // byte after the width header, dict-encoding.h:185-192): planes[c] is then rounded DOWN to 16 bytes and
+  // plane_skew[c] = the bytes to skip (1..15).  The TMA producer stages the 16-byte-aligned superset of every
+  // tile segment and the consumers rebuild the plane words from 32-bit loads with a funnel shift
+  // (lds_pair_unaligned, fle_eval_common.cuh) -- the column is read from HBM exactly once, no realigned copy.
+  // Only kernels built for it look at these fields (eval1_skew kernels, specialised kernels with FLE_JIT_SKEW).
+  uint32_t plane_skew[FLE_MAX_COLS];
+  int64_t staged_groups;  // groups that may go through staged tiles (the staged superset of the last groups must
+                          // not run past the end of the column buffer); == ngroups for aligned columns
   // single-IN-list kernels only: the list's bitmap is combined with an earlier bitmap on the way out,
   // out[g] = IN(g) AND / OR comb_bm[g] (comb_op = FOLD_AND / FOLD_OR, 0 = none; comb_bm may be the output itself)
   const uint64_t* comb_bm;

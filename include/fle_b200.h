@@ -201,6 +201,17 @@ int fle_eval_dev(fle_ctx* ctx, const fle_col_desc* cols_dev, int ncols,
                  const fle_pred_node* postfix, int nnodes, int64_t first_row, int64_t n,
                  uint64_t* bitmap_out_dev, uint64_t* match_count_dev);
 
+/* fle_eval_dev for OPTIONAL columns that are expected to hold no NULL (every column of an Impala-written file is
+ * OPTIONAL, hdfs-parquet-table-writer.cc:103-105; TPC-H data has no NULL): checks the definition levels and
+ * evaluates the program as if the columns were required, WITHOUT waiting for the check -- nothing is read back,
+ * the call only enqueues work.  *null_rows_dev = number of NULL rows found over all nullable columns; when it is 0
+ * bitmap and count are exactly those of fle_eval_dev, otherwise they are meaningless (the data streams are
+ * indexed by non-null ordinal) and the caller re-issues fle_eval_dev, which handles NULLs
+ * (hdfs-parquet-scanner.cc:326-345). */
+int fle_eval_no_nulls_dev(fle_ctx* ctx, const fle_col_desc* cols_dev, int ncols, const fle_pred_node* postfix,
+                          int nnodes, int64_t first_row, int64_t n, uint64_t* bitmap_out_dev,
+                          uint64_t* match_count_dev, uint64_t* null_rows_dev);
+
 /* The run-time specialisation behind "eval_jit", without a device: writes the CUDA C++ generated
  * for the program's shape (compile == 0) or compiles it for sm_100a with NVRTC and writes the
  * compiler log, empty on success (compile == 1), NUL-terminated, into out[0..cap); *len (optional)

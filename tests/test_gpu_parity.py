@@ -705,3 +705,99 @@ def test_unpack_narrow_targets(ctx, oracle, bw):
             assert (out.cpu().numpy().astype(np.uint16 if bw > 8 else np.uint8) == vals[first:]).all()
     with pytest.raises(Exception):
         ctx.unpack_narrow_dev(words, 9, 0, 64, out=torch.empty(64, dtype=torch.uint8, device="cuda"))
+
+
+def test_optional_columns_without_host_sync(ctx, oracle):
+    """fle_eval_no_nulls_dev: OPTIONAL columns checked and evaluated without reading anything back; the NULL count
+    says whether the optimistic result stands (hdfs-parquet-table-writer.cc:103-105, hdfs-parquet-scanner.cc:326-345)."""
+    import torch
+    rng = np.random.default_rng(31)
+    n = 64 * 3000 + 41
+    vals = [rng.integers(0, d, size=n).astype(np.uint32) for d in (2526, 11, 50)]
+    bws = (12, 4, 6)
+    cols = [(oracle.pack(v, bw), bw) for v, bw in zip(vals, bws)]
+    want, wcnt = oracle.eval_tree(cols, Q6, n)
+    ones = oracle.pack(np.ones(n, dtype=np.uint32), 1)
+    dcols = [(torch.from_numpy(w.view(np.int64)).cuda(), bw, torch.from_numpy(ones.view(np.int64)).cuda()) for w, bw in cols]
+    bm, out = ctx.eval_no_nulls_dev(dcols, Q6, n)
+    torch.cuda.synchronize()
+    assert int(out[1].item()) == 0 and int(out[0].item()) == wcnt
+    assert (bm.cpu().numpy().view(np.uint64)[: len(want)] == want).all()
+    # NULLs present: the call reports how many, the caller falls back to fle_eval_dev
+    defs = np.ones(n, dtype=np.uint32)
+    defs[rng.choice(n, size=77, replace=False)] = 0
+    dcols[1] = (dcols[1][0], 4, torch.from_numpy(oracle.pack(defs, 1).view(np.int64)).cuda())
+    _, out = ctx.eval_no_nulls_dev(dcols, Q6, n)
+    torch.cuda.synchronize()
+    assert int(out[1].item()) == 77
+    # required columns: nothing to check
+    _, out = ctx.eval_no_nulls_dev([(c[0], c[1]) for c in dcols], Q6, n)
+    torch.cuda.synchronize()
+    assert int(out[1].item()) == 0 and int(out[0].item()) == wcnt
+
+
+class _RawCol:
+    """A device 'tensor' that is a byte range of a larger uint8 tensor (what capi.make_col_descs needs)."""
+
+    def __init__(self, blob, off, nbytes):
+        self.blob, self.off, self.nbytes = blob, off, nbytes
+        self.device = blob.device
+
+    def data_ptr(self):
+        return self.blob.data_ptr() + self.off
+
+    def numel(self):
+        return self.nbytes
+
+    def element_size(self):
+        return 1
+
+
+@pytest.mark.parametrize("skew", [1, 2, 3, 4, 5, 7, 8, 9, 12, 15])
+def test_eval_directly_on_raw_page_image(ctx, oracle, skew):
+    """The FLE section of a page inside a file image starts at an ODD byte offset (dict-encoding.h:185-192): the
+    fused kernels evaluate it in place -- no realigned copy (fle_eval1_skew.cu, FLE_JIT_SKEW) -- for single-pass
+    programs, IN lists on narrow columns and multi-column programs; bit-identical to the oracle on the planes."""
+    import torch
+    rng = np.random.default_rng(50 + skew)
+    n = 64 * 4096 + 64 * 300 + 11   # full staged tiles + a ragged remainder
+    specs = ((2526, 12), (11, 4), (50, 6), (40000, 16), (7, 3))
+    blob = bytearray(b"\xee" * (256 + skew))
+    cols_np, offs = [], []
+    for d, bw in specs:
+        v = rng.integers(0, d, size=n).astype(np.uint32)
+        w = oracle.pack(v, bw)
+        pad = (-(len(blob) - skew)) % 16          # every column at the same misalignment
+        blob += b"\x33" * pad
+        offs.append(len(blob))
+        blob += w.tobytes()
+        cols_np.append((w, bw))
+    blob += b"\x44" * 64
+    dev = torch.from_numpy(np.frombuffer(bytes(blob), dtype=np.uint8).copy()).cuda()
+    assert all((dev.data_ptr() + o) % 16 == skew % 16 for o in offs)
+    raw = [(_RawCol(dev, o, w.nbytes), bw) for o, (w, bw) in zip(offs, cols_np)]
+    programs = [
+        ([0], [(GE, 0, 730), (LE, 0, 1094), (AND, None, None)]),                    # BETWEEN, single pass
+        ([3], [(EQ, 0, 12345)]),
+        ([4], [(IN, 0, [1, 4, 5, 6, 0, 2, 1, 4, 5, 6])]),                            # narrow IN list: multiplexer tree
+        ([0, 1, 2], Q6),                                                             # specialised multi-column kernel
+        ([4, 2], [(IN, 0, [1, 4]), (LT, 1, 23), (OR, None, None)]),
+    ]
+    for jit in (2, 0):
+        ctx.set_option("eval_jit", jit)
+        try:
+            for idx, prog in programs:
+                want, wcnt = oracle.eval_tree([cols_np[i] for i in idx], prog, n)
+                l0 = ctx.launch_count
+                bm, cnt = ctx.eval_dev([raw[i] for i in idx], prog, n)
+                torch.cuda.synchronize()
+                assert (bm.cpu().numpy().view(np.uint64)[: len(want)] == want).all() and int(cnt.item()) == wcnt, (skew, jit, idx)
+                if jit == 2 or len(idx) == 1:
+                    assert ctx.launch_count - l0 == 1, "the image must be evaluated in place, in one launch"
+            # a sub-range that starts further into the image (first_row on a group boundary)
+            want, wcnt = oracle.eval_tree([(cols_np[0][0][64 * 12:], 12)], [(LT, 0, 1000)], n - 64 * 64)
+            bm, cnt = ctx.eval_dev([raw[0]], [(LT, 0, 1000)], n - 64 * 64, first_row=64 * 64)
+            torch.cuda.synchronize()
+            assert (bm.cpu().numpy().view(np.uint64)[: len(want)] == want).all() and int(cnt.item()) == wcnt
+        finally:
+            ctx.set_option("eval_jit", 1)
