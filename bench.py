@@ -626,6 +626,44 @@ class Bench:
                     "frac_of_h2d_peak": h2d_s / e2e_s}
         del host_words, host_bm, dst
 
+    # -- the column as it sits inside a file image: FLE section at an odd byte offset, evaluated in place -------------
+    def run_page_image(self):
+        torch, ctx, dev = self.torch, self.ctx, self.dev
+        from fle_b200 import AND, GE, LE
+        n = self.args.rows
+        G = (n + 63) // 64
+        nbytes = self.col.numel() * 8
+        image = torch.empty(nbytes + 64, dtype=torch.uint8, device=dev)
+        off = 17  # one byte after a 16-byte boundary: the page's width byte precedes the groups (dict-encoding.h:185-192)
+        image[off:off + nbytes].copy_(self.col.view(torch.uint8))
+
+        class Raw:
+            device = dev
+            def data_ptr(self_): return image.data_ptr() + off
+            def numel(self_): return nbytes
+            def element_size(self_): return 1
+        lo, hi = between_bounds(30, 1 << BW)
+        prog = [(GE, 0, lo), (LE, 0, hi), (AND, None, None)]
+        cols = [(Raw(), BW)]
+        prep = (ctx.make_col_descs(cols),) + self.fle.capi._build_program(prog)
+        bm = torch.empty(G, dtype=torch.int64, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+        fn = lambda: ctx.eval_dev(cols, prog, n, bitmap=bm, count=cnt, prepared=prep)  # noqa: E731
+        l0 = ctx.launch_count
+        fn()
+        torch.cuda.synchronize()
+        per_call = ctx.launch_count - l0
+        ref_bm, ref_cnt = ctx.eval_dev([(self.col, BW)], prog, n)
+        torch.cuda.synchronize()
+        assert torch.equal(bm, ref_bm) and int(cnt.item()) == int(ref_cnt.item()) == self.want_counts[30]
+        med, mn = self.cold_ms(fn)
+        by = G * BW * 8 + G * 8
+        self.page_image = {"what": f"cfg1 BETWEEN on the same bw{BW} column placed at byte offset {off} of a device buffer (as the FLE section "
+                                   "of a page inside a file image), evaluated in place by the skew-capable kernel -- no realigned copy; "
+                                   "bitmap identical to the aligned column's", "ms": med, "ms_min": mn,
+                           "GBps": by / (med * 1e-3) / 1e9, "frac": by / (med * 1e-3) / 1e9 / self.peak, "launches_per_call": per_call}
+        del image, bm
+
     # -- cfg0 / cfg3 sub-records (one GPU) ----------------------------------------------------------------
     def run_codec(self):
         torch, ctx, dev = self.torch, self.ctx, self.dev
@@ -883,6 +921,10 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu_baseline = b.cpu_baseline()
+    page_image = None
+    if world == 1 and not args.no_sub:
+        b.run_page_image()
+        page_image = b.page_image
     del b.col
     torch.cuda.empty_cache()
     codec = in_lists = scanner = None
@@ -933,6 +975,7 @@ def main():
             "cfg4": cfg4,
             "codec": codec,
             "in_lists": in_lists,
+            "page_image": page_image,
             "e2e_scanner": scanner,
             "clocks": b.clocks,
             "gpu_launches": h["launches"],

@@ -176,7 +176,7 @@ def _build_program(program: Sequence[tuple]):
     return nodes, keep
 
 
-def eval_codegen(bit_widths: Sequence[int], program: Sequence[tuple], compile=False, agg_col: int = -1):
+def eval_codegen(bit_widths: Sequence[int], program: Sequence[tuple], compile=False, agg_col: int = -1, skew: bool = False):
     """The run-time specialisation of a program's shape, no device needed (fle_eval_codegen).
     Returns (rc, text): the generated CUDA C++ (compile=False), the NVRTC log, '' on success
     (compile=True), or the cubin as bytes (compile=2)."""
@@ -188,7 +188,7 @@ def eval_codegen(bit_widths: Sequence[int], program: Sequence[tuple], compile=Fa
     cap = 1 << 20
     buf = C.create_string_buffer(cap)
     n = C.c_size_t(0)
-    rc = lib.fle_eval_codegen(cols, len(bit_widths), nodes, len(nodes), int(compile) | ((agg_col + 1) << 8), buf, cap,
+    rc = lib.fle_eval_codegen(cols, len(bit_widths), nodes, len(nodes), int(compile) | ((agg_col + 1) << 8) | ((1 << 16) if skew else 0), buf, cap,
                               C.byref(n))
     if int(compile) == 2 and rc == OK:
         return rc, buf.raw[:n.value]

@@ -692,8 +692,9 @@ int fle_eval_codegen(const fle_col_desc* cols, int ncols, const fle_pred_node* n
     for (int c = 0; c < ncols; ++c) lp.p.bw[c] = (uint32_t)cols[c].bit_width;
     text.clear();
     const int agg_col = ((compile >> 8) & 0xff) - 1;
+    const bool skew = ((compile >> 16) & 1) != 0;
     compile &= 0xff;
-    if (!jit_plan(lp.p, lp.in_lits, &lp.jit_plan, agg_col)) {
+    if (!jit_plan(lp.p, lp.in_lits, &lp.jit_plan, agg_col, skew)) {
       rc = FLE_E_UNSUPPORTED;
       text = "program too large for a specialised kernel";
     } else if (compile) {

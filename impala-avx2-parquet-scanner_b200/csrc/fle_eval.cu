@@ -807,8 +807,9 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
     uint32_t coff = 0;
     for (int c = 0; c < P.ncols; ++c) {
       P.col_off[c] = coff;
-      // (+ 16: the bank skew between segments; + 16 more for a skewed column, whose aligned superset is staged)
-      P.seg_stride[c] = (uint32_t)(T / 8) * P.bw[c] * 8u + 16u + (P.plane_skew[c] ? 16u : 0u);
+      // (+ 16: the bank skew between segments.  A skewed column stages 16 bytes more per segment and is read in
+      //  whole 16-byte chunks: + 48 keeps the eight segments 3 chunks apart modulo 8, i.e. conflict-free)
+      P.seg_stride[c] = (uint32_t)(T / 8) * P.bw[c] * 8u + (P.plane_skew[c] ? 48u : 16u);
       coff += 8u * P.seg_stride[c];
     }
     P.stage_bytes = round_up(coff, 128);

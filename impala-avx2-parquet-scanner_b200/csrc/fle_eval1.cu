@@ -35,16 +35,6 @@ __global__ void __launch_bounds__(256) eval_in_mux_kernel(const __grid_constant_
 // owns `kGroups` adjacent groups of each of its U units, all U loads are issued before the
 // first use, and bw 1 stores its two result words with one 128-bit store.
 // ------------------------------------------------------------------------------------------
-template <int BW>
-struct RegGroup {
-  uint64_t w[BW];
-  template <int B>
-  __device__ __forceinline__ void load_pair(int i, uint64_t& w0, uint64_t& w1) const {
-    w0 = w[i];
-    w1 = (i + 1 < BW) ? w[i + 1 < BW ? i + 1 : i] : 0ull;
-  }
-};
-
 template <bool IS_LT, int K, int BW>
 __global__ void __launch_bounds__(256) eval1_narrow_kernel(const __grid_constant__ EvalParams P) {
   static_assert(BW == 1 || BW == 2 || BW == 4, "narrow kernel: one unit = 16 or 32 contiguous bytes");

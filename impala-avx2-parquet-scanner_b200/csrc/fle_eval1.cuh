@@ -30,15 +30,18 @@ struct GlobalGroup {
   }
 };
 
-// the same two loaders for a column at an arbitrary byte address (EvalParams::plane_skew)
-struct SmemGroupSkew {
-  uint32_t base;
-  template <int BW>
+// a group's planes already in registers
+template <int BW>
+struct RegGroup {
+  uint64_t w[BW];
+  template <int B>
   __device__ __forceinline__ void load_pair(int i, uint64_t& w0, uint64_t& w1) const {
-    lds_pair_unaligned(base + i * 8, i + 1 < BW, w0, w1);
+    w0 = w[i];
+    w1 = (i + 1 < BW) ? w[i + 1 < BW ? i + 1 : i] : 0ull;
   }
 };
 
+// the same loaders for a column at an arbitrary byte address (EvalParams::plane_skew)
 struct GlobalGroupSkew {
   const uint8_t* base;
   template <int BW>
@@ -49,6 +52,7 @@ struct GlobalGroupSkew {
 
 template <bool IS_LT, int K, int BW>
 struct PassRegs {
+  static constexpr bool kComb = false;  // (compare kernels never fold a second bitmap in: keep their inner loop bare)
   static constexpr bool kRegMasks = (K * BW <= 64);
   uint32_t m[kRegMasks ? K * BW : 1];
   uint32_t lit[K], nm[K], ini[K];
@@ -144,6 +148,7 @@ struct PassRegs {
 template <int BW>
 struct InMuxRegs {
   static_assert(BW >= 1 && BW <= 7, "plane-domain IN lists: bw <= 7");
+  static constexpr bool kComb = true;   // EvalParams::comb_*: long list AND / OR the other operands' bitmap
   static constexpr int T = BW < 3 ? BW : 3;
   uint32_t nm;
   __device__ __forceinline__ void init(const PassDesc& pd) { nm = pd.neg[0] ? ~0u : 0u; }
@@ -216,7 +221,6 @@ __device__ __forceinline__ void eval1_body(const EvalParams& P) {
   const int seg_groups = T >> 3;
   const int64_t ntiles = (SKEW ? P.staged_groups : P.ngroups) / T;
   const int nst = P.nstages;
-  using SmemLd = typename std::conditional<SKEW, SmemGroupSkew, SmemGroup>::type;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < nst; ++s) mbar_init(bar0 + s * 8, 1);
@@ -271,8 +275,17 @@ __device__ __forceinline__ void eval1_body(const EvalParams& P) {
     // bw 4 0.91 -> 0.95, bw 12 1.02 -> 1.04)
 #pragma unroll 2
     for (int q = 0; q < gpt; ++q) {
-      const uint64_t other = comb_load(P, g);
-      const uint64_t r = comb_apply(P, finish_word(pr.run(P, SmemLd{a}), g, P.nrows), other);
+      uint64_t other = 0;
+      if constexpr (PR::kComb) other = comb_load(P, g);
+      uint64_t r;
+      if constexpr (SKEW) {
+        RegGroup<BW> rg;
+        lds_planes_unaligned<BW>(a, rg.w);
+        r = finish_word(pr.run(P, rg), g, P.nrows);
+      } else {
+        r = finish_word(pr.run(P, SmemGroup{a}), g, P.nrows);
+      }
+      if constexpr (PR::kComb) r = comb_apply(P, r, other);
       P.bitmap[g] = r;
       cnt += __popcll(r);
       a += kGroupStride;
@@ -286,13 +299,14 @@ __device__ __forceinline__ void eval1_body(const EvalParams& P) {
   // ragged remainder (< T groups), planes straight from global memory
   for (int64_t g = ntiles * T + (int64_t)blockIdx.x * NT + threadIdx.x; g < P.ngroups;
        g += (int64_t)gridDim.x * NT) {
-    const uint64_t other = comb_load(P, g);
+    uint64_t other = 0;
+    if constexpr (PR::kComb) other = comb_load(P, g);
     uint64_t r;
     if constexpr (SKEW)
       r = finish_word(pr.run(P, GlobalGroupSkew{reinterpret_cast<const uint8_t*>(P.planes[0]) + P.plane_skew[0] + g * (BW * 8)}), g, P.nrows);
     else
       r = finish_word(pr.run(P, GlobalGroup{P.planes[0] + g * BW}), g, P.nrows);
-    r = comb_apply(P, r, other);
+    if constexpr (PR::kComb) r = comb_apply(P, r, other);
     P.bitmap[g] = r;
     cnt += __popcll(r);
   }

@@ -37,10 +37,15 @@ __device__ __forceinline__ uint64_t jit_res(uint32_t al, uint32_t ah, uint32_t n
 template <int NCOLS>
 struct JitSmemGroup {
   uint32_t a[NCOLS];
+  // every plane word of column C's group (skewed columns: whole-chunk loads + funnel shift)
+  template <int C, int BW>
+  __device__ __forceinline__ void load_all(uint64_t (&w)[BW]) const {
+    lds_planes_unaligned<BW>(a[C], w);
+  }
   template <int C, int BW>
   __device__ __forceinline__ void load_pair(int i, uint64_t& w0, uint64_t& w1) const {
 #ifdef FLE_JIT_SKEW
-    lds_pair_unaligned(a[C] + i * 8, i + 1 < BW, w0, w1);
+    lds_pair_unaligned(a[C] + i * 8, i + 1 < BW, w0, w1);  // (generated code for skewed columns uses load_all)
 #else
     if constexpr (BW % 2 == 0) {
       lds128(a[C] + i * 8, w0, w1);
@@ -55,6 +60,16 @@ struct JitSmemGroup {
 template <int NCOLS>
 struct JitGlobalGroup {
   const uint64_t* p[NCOLS];
+  template <int C, int BW>
+  __device__ __forceinline__ void load_all(uint64_t (&w)[BW]) const {
+#pragma unroll
+    for (int i = 0; i < BW; i += 2) {
+      uint64_t a_, b_;
+      ldg_pair_unaligned(reinterpret_cast<const uint8_t*>(p[C]) + i * 8, i + 1 < BW, a_, b_);
+      w[i] = a_;
+      if (i + 1 < BW) w[i + 1 < BW ? i + 1 : i] = b_;
+    }
+  }
   template <int C, int BW>
   __device__ __forceinline__ void load_pair(int i, uint64_t& w0, uint64_t& w1) const {
 #ifdef FLE_JIT_SKEW

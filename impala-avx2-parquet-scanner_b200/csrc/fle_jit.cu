@@ -113,8 +113,17 @@ bool jit_plan(const EvalParams& P, const std::vector<uint32_t>& in_lits, JitPlan
         body += b;
       }
       body += "    uint64_t w0, w1;\n";
+      if (skew) {  // a skewed column: all plane words at once (whole-chunk loads + funnel shift), then the sweep
+        snprintf(b, sizeof(b), "    uint64_t wq[%d];\n    ld.template load_all<%d, %d>(wq);\n", bw, col, bw);
+        body += b;
+      }
       for (int i = 0; i < bw; i += 2) {
-        snprintf(b, sizeof(b), "    ld.template load_pair<%d, %d>(%d, w0, w1);\n", col, bw, i);
+        if (skew) {
+          if (i + 1 < bw) snprintf(b, sizeof(b), "    w0 = wq[%d]; w1 = wq[%d];\n", i, i + 1);
+          else snprintf(b, sizeof(b), "    w0 = wq[%d]; w1 = 0;\n", i);
+        } else {
+          snprintf(b, sizeof(b), "    ld.template load_pair<%d, %d>(%d, w0, w1);\n", col, bw, i);
+        }
         body += b;
         for (int h = 0; h < 2 && i + h < bw; ++h) {
           for (const Sweep& s : sweep) {

@@ -217,7 +217,8 @@ int fle_eval_no_nulls_dev(fle_ctx* ctx, const fle_col_desc* cols_dev, int ncols,
  * compiler log, empty on success (compile == 1), NUL-terminated, into out[0..cap); *len (optional)
  * receives the untruncated length.  compile == 2 writes the sm_100a cubin instead (binary; for
  * cuobjdump -sass).  Bits 8..15 of `compile`: 1 + code_col to generate the fused aggregate of
- * fle_eval_sum_product_dev as well, 0 for none.  Only cols[i].bit_width is read.  FLE_E_UNSUPPORTED: the
+ * fle_eval_sum_product_dev as well, 0 for none; bit 16: the variant for columns at arbitrary byte addresses
+ * (page images evaluated in place).  Only cols[i].bit_width is read.  FLE_E_UNSUPPORTED: the
  * program has no specialised form (it is a single pass, or too large) or NVRTC is missing.
  * This is the step Impala's LLVM codegen performs for the expression trees the reference
  * interprets (simple-predicates.h:113-163). */

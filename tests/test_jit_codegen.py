@@ -100,3 +100,20 @@ def test_fused_aggregate_shape_compiles():
     assert rc == OK, log[:4000]
     rc, _ = eval_codegen([12, 4, 6], Q6, agg_col=5)
     assert rc != OK
+
+
+@pytest.mark.parametrize("name", ["q6", "odd_widths", "long_in", "in8_in_tree"])
+def test_skewed_shapes_compile_with_nvrtc(name):
+    """The variant for columns at arbitrary byte addresses (page images evaluated in place): another shape --
+    whole-chunk loads + funnel shift instead of the aligned plane loads -- that must compile and stay spill-free."""
+    ok, why = nvrtc_available()
+    if not ok:
+        pytest.skip("NVRTC unavailable here: " + why[:200])
+    bws, prog = SHAPES[name]
+    rc, text = eval_codegen(bws, prog, skew=True)
+    rc0, plain = eval_codegen(bws, prog)
+    assert rc == OK and rc0 == OK and text != plain and "FLE_JIT_SKEW" in text and "load_all<" in text
+    rc, log = eval_codegen(bws, prog, compile=True, skew=True)
+    assert rc == OK, log[:4000]
+    rc, _ = eval_codegen([12, 4, 6], Q6, agg_col=1, skew=True)
+    assert rc != OK  # the fused aggregate is not built for skewed columns (the caller gets the two-kernel form)
