@@ -398,6 +398,7 @@ int fle_ctx_destroy(fle_ctx* ctx) {
   if (ctx->d_count) cudaFree(ctx->d_count);
   if (ctx->d_split) cudaFree(ctx->d_split);
   if (ctx->d_realign) cudaFree(ctx->d_realign);
+  if (ctx->d_dict) cudaFree(ctx->d_dict);
   if (ctx->d_tile_state) cudaFree(ctx->d_tile_state);
   if (ctx->ev_prefetch) cudaEventDestroy(ctx->ev_prefetch);
   fle::group_release(ctx);

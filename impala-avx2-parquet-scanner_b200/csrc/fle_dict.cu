@@ -134,21 +134,29 @@ int launch_dict_encode(fle_ctx* ctx, const void* values_dev, int elem_type, int6
   if ((reinterpret_cast<uintptr_t>(values_dev) & (es - 1)) || (reinterpret_cast<uintptr_t>(enc_dev) & 15))
     return set_error(ctx, FLE_E_ALIGN, "values must be naturally aligned, enc_dev 16-byte aligned");
   cudaStream_t st = ctx->stream;
-  unsigned long long* keys = nullptr;
-  DictState* state = nullptr;
-  long long* list_keys = nullptr;
-  uint32_t *list_slots = nullptr, *slot_to_code = nullptr, *codes = nullptr;
-  auto cleanup = [&]() {
-    cudaFreeAsync(keys, st); cudaFreeAsync(state, st); cudaFreeAsync(list_keys, st);
-    cudaFreeAsync(list_slots, st); cudaFreeAsync(slot_to_code, st); cudaFreeAsync(codes, st);
-  };
+  // one grow-only scratch block per context (stream-ordered allocations go back to the driver at every
+  // synchronisation, and this call synchronises: allocating cost more than the kernels)
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t o_keys = 0, o_state = o_keys + up((size_t)kDictSlots * 8), o_lkeys = o_state + up(sizeof(DictState)),
+               o_lslots = o_lkeys + up((size_t)(max_entries + 2) * 8), o_s2c = o_lslots + up((size_t)(max_entries + 2) * 4),
+               o_codes = o_s2c + up((size_t)(kDictSlots + 1) * 4), total = o_codes + up((size_t)std::max<int64_t>(n, 1) * 4);
+  if (total > ctx->dict_cap) {
+    FLE_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    if (ctx->d_dict) cudaFree(ctx->d_dict);
+    ctx->d_dict = nullptr;
+    ctx->dict_cap = 0;
+    FLE_CUDA_TRY(ctx, cudaMalloc(&ctx->d_dict, total));
+    ctx->dict_cap = total;
+  }
+  uint8_t* base = static_cast<uint8_t*>(ctx->d_dict);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(base + o_keys);
+  DictState* state = reinterpret_cast<DictState*>(base + o_state);
+  long long* list_keys = reinterpret_cast<long long*>(base + o_lkeys);
+  uint32_t* list_slots = reinterpret_cast<uint32_t*>(base + o_lslots);
+  uint32_t* slot_to_code = reinterpret_cast<uint32_t*>(base + o_s2c);
+  uint32_t* codes = reinterpret_cast<uint32_t*>(base + o_codes);
+  auto cleanup = [&]() {};
 #define DICT_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return set_cuda_error(ctx, _e, #expr); } } while (0)
-  DICT_TRY(cudaMallocAsync(&keys, (size_t)kDictSlots * 8, st));
-  DICT_TRY(cudaMallocAsync(&state, sizeof(DictState), st));
-  DICT_TRY(cudaMallocAsync(&list_keys, (size_t)(max_entries + 2) * 8, st));
-  DICT_TRY(cudaMallocAsync(&list_slots, (size_t)(max_entries + 2) * 4, st));
-  DICT_TRY(cudaMallocAsync(&slot_to_code, (size_t)(kDictSlots + 1) * 4, st));
-  DICT_TRY(cudaMallocAsync(&codes, (size_t)std::max<int64_t>(n, 1) * 4, st));
   // (no byte pattern gives kEmptyKey, so cudaMemset cannot fill the table)
   dict_clear_kernel<<<kDictSlots / 256, 256, 0, st>>>(keys);
   DICT_TRY(cudaMemsetAsync(state, 0, sizeof(DictState), st));

@@ -96,6 +96,8 @@ struct fle_ctx {
   int lit_next = 0;
   uint64_t lit_gen_counter = 0;
   uint64_t* d_count = nullptr;    // 8-byte result slot for host-facing calls
+  void* d_dict = nullptr;         // dictionary build scratch (hash table, lists, codes), grow-only
+  size_t dict_cap = 0;
   void* d_realign = nullptr;      // aligned copies of columns no kernel can read in place, grow-only
   size_t realign_cap = 0;
   uint64_t* d_split = nullptr;    // temporary bitmaps of regrouped programs (long IN lists), grow-only
