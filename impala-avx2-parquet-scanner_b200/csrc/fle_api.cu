@@ -151,8 +151,11 @@ static int eval_dev_nullable(fle_ctx* ctx, const fle_col_desc* cols, int ncols,
     if (rc != FLE_OK) { cleanup(); return rc; }
   }
   std::vector<uint64_t> h_counts(ncols, 0);
-  FLE_CUDA_TRY(ctx, cudaMemcpyAsync(h_counts.data(), d_counts, (size_t)ncols * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  FLE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  {
+    cudaError_t e = cudaMemcpyAsync(h_counts.data(), d_counts, (size_t)ncols * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { cleanup(); return set_cuda_error(ctx, e, "def-level counts"); }
+  }
   bool any_null = false;
   for (int c = 0; c < ncols; ++c)
     if (cols[c].max_def_level != 0 && (int64_t)h_counts[c] != n) any_null = true;
@@ -397,6 +400,7 @@ int fle_ctx_destroy(fle_ctx* ctx) {
   }
   if (ctx->d_count) cudaFree(ctx->d_count);
   if (ctx->d_split) cudaFree(ctx->d_split);
+  if (ctx->d_chunk_counts) cudaFree(ctx->d_chunk_counts);
   if (ctx->d_realign) cudaFree(ctx->d_realign);
   if (ctx->d_dict) cudaFree(ctx->d_dict);
   if (ctx->d_tile_state) cudaFree(ctx->d_tile_state);
@@ -440,6 +444,8 @@ int fle_ctx_set_option(fle_ctx* ctx, const char* name, int64_t value) {
   else if (k == "eval_gpt") ctx->eval_gpt = (int)value;
   else if (k == "in_lookup_min") ctx->in_lookup_min = (int)value;
   else if (k == "in_wide") ctx->in_wide = (int)value;
+  else if (k == "in_wide_warps") ctx->in_wide_warps = (int)value;
+  else if (k == "in_wide_gpt") ctx->in_wide_gpt = (int)value;
   else if (k == "in_mux_bw") ctx->in_mux_bw = (int)std::min<int64_t>(7, std::max<int64_t>(0, value));
   else if (k == "in_split_min_rows") ctx->in_split_min_rows = value;
   else if (k == "eval_narrow_bw") ctx->eval_narrow_bw = (int)value;
@@ -465,6 +471,8 @@ int64_t fle_ctx_get_option(fle_ctx* ctx, const char* name) {
   if (k == "eval_gpt") return ctx->eval_gpt;
   if (k == "in_lookup_min") return ctx->in_lookup_min;
   if (k == "in_wide") return ctx->in_wide;
+  if (k == "in_wide_warps") return ctx->in_wide_warps;
+  if (k == "in_wide_gpt") return ctx->in_wide_gpt;
   if (k == "in_mux_bw") return ctx->in_mux_bw;
   if (k == "in_split_min_rows") return ctx->in_split_min_rows;
   if (k == "eval_narrow_bw") return ctx->eval_narrow_bw;
@@ -797,11 +805,23 @@ int fle_eval(fle_ctx* ctx, const fle_col_desc* cols, int ncols, const fle_pred_n
     rc = ensure_stage(ctx, b, total);
     if (rc != FLE_OK) return rc;
   }
-  uint64_t* d_counts = nullptr;
-  FLE_CUDA_TRY(ctx, cudaMalloc(&d_counts, (size_t)nchunks * 8));
+  // per-chunk counts: grow-only context scratch (no cudaMalloc / cudaFree -- a device-wide sync -- per call)
+  if (ctx->chunk_counts_cap < (size_t)nchunks) {
+    FLE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_chunk_counts) cudaFree(ctx->d_chunk_counts);
+    ctx->d_chunk_counts = nullptr;
+    ctx->chunk_counts_cap = 0;
+    const size_t cap = std::max<size_t>(256, (size_t)nchunks * 2);
+    FLE_CUDA_TRY(ctx, cudaMalloc(&ctx->d_chunk_counts, cap * 8));
+    ctx->chunk_counts_cap = cap;
+  }
+  uint64_t* d_counts = ctx->d_chunk_counts;
   std::vector<uint64_t> h_counts(nchunks, 0);
   rc = FLE_OK;
-  cudaError_t e = cudaSuccess;
+  // the staging buffers may still be read by work queued earlier on the context's stream (the aggregate
+  // fallback keeps its bitmap in d_stage[0]): the copy stream starts behind it
+  cudaError_t e = cudaEventRecord(ctx->ev_done[0], ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[0], 0);
   for (int64_t k = 0; k < nchunks && rc == FLE_OK && e == cudaSuccess; ++k) {
     const int b = (int)(k & 1);
     const int64_t cg0 = k * chunk_groups;
@@ -830,7 +850,6 @@ int fle_eval(fle_ctx* ctx, const fle_col_desc* cols, int ncols, const fle_pred_n
     e = cudaMemcpyAsync(h_counts.data(), d_counts, (size_t)nchunks * 8, cudaMemcpyDeviceToHost, ctx->stream);
   cudaError_t e2 = cudaStreamSynchronize(ctx->copy_stream);
   cudaError_t e3 = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_counts);
   if (rc != FLE_OK) return rc;
   if (e != cudaSuccess) return set_cuda_error(ctx, e, "fle_eval pipeline");
   if (e2 != cudaSuccess) return set_cuda_error(ctx, e2, "fle_eval copy stream");

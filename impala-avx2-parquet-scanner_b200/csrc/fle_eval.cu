@@ -712,6 +712,7 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
   const int64_t G = P.ngroups;
   const void* kern = nullptr;
   int nt = kNT;       // threads per CTA
+  int in_ncw = 16, in_gpt = 1;  // IN lookup kernel: consumer warps, groups per consumer thread per tile
   int mode_reported = mode;
   if (mode == MODE_JIT) {
     kern = jit_kern;
@@ -723,9 +724,19 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
     kern = eval_in_kernel_for((int)P.bw[0]);
     if (!kern) return FLE_E_UNSUPPORTED;
   } else if (mode == MODE_IN_WIDE) {
-    nt = kInWideThreadsPerCta;
-    kern = eval_in_wide_kernel_for((int)P.bw[0]);
+    int want_ncw = 16, want_gpt = 1;
+    if (ctx->in_wide >= 2) eval_in_wide_shape((int)P.bw[0], &want_ncw, &want_gpt);
+    if (ctx->in_wide_warps > 0) want_ncw = ctx->in_wide_warps;
+    if (ctx->in_wide_gpt > 0) want_gpt = ctx->in_wide_gpt;
+    kern = eval_in_wide_kernel_for((int)P.bw[0], ctx->in_wide, want_ncw, want_gpt);
+    if (kern) {
+      in_ncw = want_ncw;
+      in_gpt = want_gpt;
+    } else {
+      kern = eval_in_wide_kernel_for((int)P.bw[0], ctx->in_wide, 16, 1);
+    }
     if (!kern) return FLE_E_UNSUPPORTED;
+    nt = in_ncw * 32 + 32;
   } else if (mode == MODE_NARROW) {
     kern = eval1_narrow_kernel_for(P.passes[0].type, P.passes[0].k, (int)P.bw[0]);
     if (!kern) return FLE_E_UNSUPPORTED;
@@ -761,7 +772,7 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
       if (mode == MODE_SINGLE_PASS && gpt == 1 && bytes_per_gpt > 33u * 1024u && bytes_per_gpt < 44u * 1024u) gpt = 2;
     }
     gpt = std::min(gpt, 8);
-    if (mode == MODE_IN_WIDE) gpt = 1;  // the table leaves room for 24-48 KB stages only
+    if (mode == MODE_IN_WIDE) gpt = in_gpt;  // compiled into the kernel
     if (mode == MODE_JIT && P.agg_plain) gpt = kJitAggGpt;  // compiled into the kernel (fle_eval_jit.cuh)
     if (mode_reported == MODE_IN_MUX) {
       // compute-heavy (2^bw instructions per 32 rows): two CTAs per SM so that one computes while the other waits
@@ -793,7 +804,10 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
     const uint32_t tbytes = std::max(4u, (1u << P.bw[0]) / 8u);
     off += P.bw[0] <= 13 ? tbytes * 33u : tbytes;
   }
-  if (mode == MODE_IN_WIDE) off += eval_in_wide_table_bytes((int)P.bw[0]);  // 16-bit entries x 32 lanes
+  if (mode == MODE_IN_WIDE) {  // lane-private entries; the kernel addresses the table at a compile-time offset
+    if (off != 64u) return set_error(ctx, FLE_E_INVALID, "IN lookup table offset");
+    off += eval_in_wide_table_bytes((int)P.bw[0], ctx->in_wide);
+  }
   P.smem_slots_off = off;
   if (mode == MODE_DIRECT || mode == MODE_STAGED) off += (uint32_t)P.nslots * kNT * 8u;
   off = round_up(off, 128);
@@ -803,7 +817,7 @@ int launch_program(fle_ctx* ctx, EvalParams& P, int mode, int sum_bw, const void
   size_t smem_bytes = off;
   int rc;
   if (staged) {
-    const int T = (mode == MODE_IN_WIDE ? kInWideGroupsPerTile : nt) * gpt;
+    const int T = (mode == MODE_IN_WIDE ? in_ncw * 32 : nt) * gpt;
     uint32_t coff = 0;
     for (int c = 0; c < P.ncols; ++c) {
       P.col_off[c] = coff;

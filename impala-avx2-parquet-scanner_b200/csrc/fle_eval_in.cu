@@ -99,6 +99,7 @@ template <int BW, bool REP = false>
 struct InDecode {
   using IT = InTable<BW, REP>;
   uint32_t table;  // shared address of this lane's table (of the shared one for bw > 13)
+  __device__ __forceinline__ void init(uint32_t table_addr, uint32_t lane) { table = table_addr + (lane & (uint32_t)(IT::kCopies - 1)) * 4u; }
 
   // the group's planes, in registers: bit planes of rows 0..31 / 32..63, plane i at word 15 - pos(i)
   struct Planes {
@@ -309,6 +310,7 @@ template <int BW>
 struct InWideDecode {
   using IW = InWide<BW>;
   uint32_t table;  // shared address of this lane's column of the table
+  __device__ __forceinline__ void init(uint32_t table_addr, uint32_t lane) { table = table_addr + lane * 4u; }
 
   // (inline PTX: from C the compiler folds the * 2 into the half's extraction -- shift by 15, then
   //  a mask to clear bit 0 -- and spends a second ALU instruction per lookup)
@@ -406,6 +408,305 @@ struct InWideDecode {
   }
 };
 
+// ------------------------------------------------------------------------------------------
+// Third form (default, in_wide = 2): THREE instructions per lookup, and a transpose no larger than the code.
+//
+// ncu on the entry-table kernel above (profiles/r02_in_wide_entry_ncu.txt): 594 issued instructions per
+// group whatever the bit width (the butterflies are inline PTX, so zero planes do not fold away; bw 8 costs
+// what bw 12 costs), issue slots 82 % busy -- the kernel is bound by instruction issue, and every lookup pays
+// four of them: extract the half, IMAD the lane's table base onto it, load, IMAD-append.  Here the word that
+// comes out of the transpose IS the shared-memory offset of the row's table entry, lane bits included, so a
+// lookup is   ALU: extract (PRMT / LOP3 / SHF)   LSU: ld.shared [offset + constant table base]   FMA: IMAD
+// that drops the entry at the row's bit position of the result word (acc += entry * 2^row): the selection
+// word is assembled directly in row order, no epilogue.
+//
+//   bw <= 10  (InWordDecode): the low 8 planes go through 8 x 8 SWAR transposes (3 stages on 8 words per 32
+//             rows: 96 instructions per group instead of 224); a transposed byte is the row's low code byte,
+//             and ONE PRMT builds  offset = code << 8 | lane << 2  from it and the lane constant.  Entries are
+//             32-bit words; planes 8 and 9 stay bit-sliced: an entry carries the answers for all their values
+//             (2 x 16 bits or 4 x 8 bits apart), the IMADs sort them into per-case row words and the untouched
+//             planes select among those bitwise (1 / 3 LOP3 per 32 rows).
+//   bw 11, 12 (InByteDecode): the 16 x 16 butterflies above, with the five LANE bits fed in as constant planes
+//             (all-ones or all-zeros words per thread) at the positions the table layout wants them, so a
+//             transposed half is  code[10:2] << 7 | lane << 2 | code[1:0]  = the offset of a BYTE entry in a
+//             lane-private 64 KB table; bw 12 keeps plane 11 bit-sliced (answers in bits 0 and 4 of the byte,
+//             rows dropped four to a byte, nibble select).
+// Set membership of the same codes, so bit-identical to the OR of equalities by construction.
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kInTableOff = 64;  // the table's offset in dynamic shared memory (launch_program: right behind the mbarriers)
+
+__device__ __forceinline__ uint32_t bitsel_r(uint32_t a, uint32_t b, uint32_t m) {  // (a & ~m) | (b & m)
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(r) : "r"(a), "r"(b), "r"(m));
+  return r;
+}
+// acc + e * MUL as one IMAD (FMA pipe; written in C a power of two becomes a shift-add on the busier ALU pipe)
+template <uint32_t MUL>
+__device__ __forceinline__ uint32_t drop_at(uint32_t acc, uint32_t e) {
+  uint32_t r;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(e), "n"(MUL), "r"(acc));
+  return r;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+template <int J, uint32_t M>
+__device__ __forceinline__ void in_stage8(uint32_t (&S)[8]) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if ((k & J) == 0) {
+      const uint32_t a = S[k], b = S[k + J];
+      S[k] = bitsel<M>(a, b >> J);
+      S[k + J] = bitsel<M>(a << J, b);
+    }
+  }
+}
+// 8 x 8 bit transposes of the four byte lanes of S[0..7] at once:  S'[w] byte b, bit j == S[7 - j] byte b, bit 7 - w.
+// With plane i's 32-row half in S[7 - i]:  S'[w] byte b = low code byte of the half's row 24 - 8 b + w.
+__device__ __forceinline__ void in_transpose8(uint32_t (&S)[8]) {
+  in_stage8<4, 0x0F0F0F0Fu>(S);
+  in_stage8<2, 0x33333333u>(S);
+  in_stage8<1, 0x55555555u>(S);
+}
+
+template <int BW>
+struct InWord {
+  static constexpr int kTB = BW < 8 ? BW : 8;  // transposed code bits
+  static constexpr int kNX = BW - kTB;         // planes kept bit-sliced (0, 1 or 2)
+  static constexpr uint32_t kTableBytes = (1u << kTB) * 256u;  // entry of code e, lane l at e * 256 + l * 4
+  static constexpr int kCaseBits = kNX == 0 ? 32 : (kNX == 1 ? 16 : 8);  // distance between the answers inside an entry
+};
+
+template <int BW>
+struct InWordDecode {
+  using IW = InWord<BW>;
+  static_assert(IW::kNX <= 2, "bw <= 10");
+  uint32_t table;  // shared address of the table
+  uint32_t lane4;  // lane * 4: byte 0 of every entry offset
+
+  __device__ __forceinline__ void init(uint32_t table_addr, uint32_t lane) {
+    table = table_addr;
+    lane4 = lane * 4u;
+  }
+
+  struct Planes {
+    uint32_t S0[8], S1[8];
+    uint64_t X[IW::kNX > 0 ? IW::kNX : 1];
+  };
+
+  template <class L>
+  __device__ __forceinline__ uint64_t run(const L& ld) const {
+    Planes pl;
+    load(ld, pl);
+    return compute(pl);
+  }
+
+  template <class L>
+  __device__ __forceinline__ void load(const L& ld, Planes& pl) const {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pl.S0[j] = pl.S1[j] = 0u;
+#pragma unroll
+    for (int i = 0; i < BW; i += 2) {
+      uint64_t a, b;
+      ld.template load_pair<BW>(i, a, b);
+      if (i < IW::kTB) {
+        pl.S0[7 - (i < IW::kTB ? i : 0)] = (uint32_t)(a >> 32);
+        pl.S1[7 - (i < IW::kTB ? i : 0)] = (uint32_t)a;
+      } else {
+        pl.X[i >= IW::kTB ? i - IW::kTB : 0] = a;
+      }
+      if (i + 1 < BW) {
+        if (i + 1 < IW::kTB) {
+          pl.S0[7 - (i + 1 < IW::kTB ? i + 1 : 0)] = (uint32_t)(b >> 32);
+          pl.S1[7 - (i + 1 < IW::kTB ? i + 1 : 0)] = (uint32_t)b;
+        } else {
+          pl.X[i + 1 >= IW::kTB ? i + 1 - IW::kTB : 0] = b;
+        }
+      }
+    }
+  }
+
+  // entry of the half's row R (0..31): its code byte is byte 3 - R / 8 of word R % 8
+  template <int R>
+  __device__ __forceinline__ uint32_t entry(const uint32_t (&S)[8]) const {
+    constexpr uint32_t sel = 0x5504u | ((uint32_t)(3 - R / 8) << 4);  // [0][0][code byte][lane * 4]
+    return lds32(table + __byte_perm(S[R % 8], lane4, sel));
+  }
+
+  // rows R0 .. R0 + N - 1 of a half dropped at bits 0 .. N - 1 of an accumulator
+  // (two independent IMAD chains per accumulator: a single chain of 32 dependent IMADs shows up as 'wait' stalls)
+  template <int R0, int N>
+  __device__ __forceinline__ uint32_t rows(const uint32_t (&S)[8]) const {
+    uint32_t acc0 = 0, acc1 = 0;
+    rows_step<R0, N, 0>(S, acc0);
+    rows_step<R0, N, 1>(S, acc1);
+    return acc0 + acc1;
+  }
+  template <int R0, int N, int I>
+  __device__ __forceinline__ void rows_step(const uint32_t (&S)[8], uint32_t& acc) const {
+    if constexpr (I < N) {
+      acc = drop_at<(1u << I)>(acc, entry<R0 + I>(S));
+      rows_step<R0, N, I + 2>(S, acc);
+    }
+  }
+
+  // 32 rows of one half -> selection word in row order
+  __device__ __forceinline__ uint32_t half(const uint32_t (&S)[8], const uint32_t (&x)[2]) const {
+    if constexpr (IW::kNX == 0) {
+      return rows<0, 32>(S);
+    } else if constexpr (IW::kNX == 1) {
+      // an accumulator takes 16 rows: answers for plane 8 = 0 in its low half, for plane 8 = 1 in its high half
+      const uint32_t a = rows<0, 16>(S), b = rows<16, 16>(S);
+      return bitsel_r(__byte_perm(a, b, 0x5410), __byte_perm(a, b, 0x7632), x[0]);
+    } else {
+      // an accumulator takes 8 rows: byte c = answers for (plane 9, plane 8) = c
+      const uint32_t a0 = rows<0, 8>(S), a1 = rows<8, 8>(S), a2 = rows<16, 8>(S), a3 = rows<24, 8>(S);
+      uint32_t m[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t sel = ((uint32_t)(4 + c) << 4) | (uint32_t)c;  // [.][.][second.byte c][first.byte c]
+        m[c] = __byte_perm(__byte_perm(a0, a1, sel), __byte_perm(a2, a3, sel), 0x5410);
+      }
+      return bitsel_r(bitsel_r(m[0], m[1], x[0]), bitsel_r(m[2], m[3], x[0]), x[1]);
+    }
+  }
+
+  __device__ __forceinline__ uint64_t compute(Planes& pl) const {
+    in_transpose8(pl.S0);
+    in_transpose8(pl.S1);
+    uint32_t xlo[2] = {0u, 0u}, xhi[2] = {0u, 0u};
+#pragma unroll
+    for (int i = 0; i < IW::kNX; ++i) {
+      const uint64_t xr = __brevll(pl.X[i]);  // plane order (row k at bit 63 - k) -> row order
+      xlo[i] = (uint32_t)xr;
+      xhi[i] = (uint32_t)(xr >> 32);
+    }
+    const uint32_t lo = half(pl.S0, xlo), hi = half(pl.S1, xhi);
+    return ((uint64_t)hi << 32) | (uint64_t)lo;
+  }
+};
+
+template <int BW>
+struct InByte {
+  static constexpr int kTB = BW < 11 ? BW : 11;
+  static constexpr int kNX = BW - kTB;  // 0 or 1
+  static constexpr uint32_t kTableBytes = kTB <= 2 ? 128u : (1u << (kTB - 2)) * 128u;  // entry e, lane l at (e >> 2) * 128 + l * 4 + (e & 3)
+  // bit position of code bit i / of lane bit j inside a transposed 16-bit half (= the entry's byte offset)
+  FLE_HD static constexpr int pos(int i) { return i < 2 ? i : i + 5; }
+  FLE_HD static constexpr int lane_pos(int j) { return 2 + j; }
+};
+
+template <int BW>
+struct InByteDecode {
+  using IB = InByte<BW>;
+  static_assert(IB::kNX <= 1, "bw <= 12");
+  uint32_t table;
+  uint32_t lane_plane[5];  // lane bit j as a constant plane: all ones or all zeros
+
+  __device__ __forceinline__ void init(uint32_t table_addr, uint32_t lane) {
+    table = table_addr;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) lane_plane[j] = 0u - ((lane >> j) & 1u);
+  }
+
+  struct Planes {
+    uint32_t S0[16], S1[16];
+    uint64_t X;
+  };
+
+  template <class L>
+  __device__ __forceinline__ uint64_t run(const L& ld) const {
+    Planes pl;
+    load(ld, pl);
+    return compute(pl);
+  }
+
+  template <class L>
+  __device__ __forceinline__ void load(const L& ld, Planes& pl) const {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) pl.S0[j] = pl.S1[j] = 0u;
+    pl.X = 0;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) pl.S0[15 - IB::lane_pos(j)] = pl.S1[15 - IB::lane_pos(j)] = lane_plane[j];
+#pragma unroll
+    for (int i = 0; i < BW; i += 2) {
+      uint64_t a, b;
+      ld.template load_pair<BW>(i, a, b);
+      if (i < IB::kTB) {
+        pl.S0[15 - IB::pos(i < IB::kTB ? i : 0)] = (uint32_t)(a >> 32);
+        pl.S1[15 - IB::pos(i < IB::kTB ? i : 0)] = (uint32_t)a;
+      } else {
+        pl.X = a;
+      }
+      if (i + 1 < BW) {
+        if (i + 1 < IB::kTB) {
+          pl.S0[15 - IB::pos(i + 1 < IB::kTB ? i + 1 : 0)] = (uint32_t)(b >> 32);
+          pl.S1[15 - IB::pos(i + 1 < IB::kTB ? i + 1 : 0)] = (uint32_t)b;
+        } else {
+          pl.X = b;
+        }
+      }
+    }
+  }
+
+  // after in_transpose: S[k] = offset(row k) << 16 | offset(row 16 + k)
+  // (measured and dropped, tools/in_sweep.py: taking the halves apart on the idle FMA pipe -- hi = IMAD.HI(w, 2^16),
+  //  lo = IMAD(hi, -2^16, w) -- +1 %; the butterflies' right shifts as IMAD.HI: 3-9 % slower, as in round 1)
+  template <int R>
+  __device__ __forceinline__ uint32_t entry(const uint32_t (&S)[16]) const {
+    const uint32_t w = S[R % 16];
+    return lds_u8(table + (R < 16 ? (w >> 16) : (w & 0xFFFFu)));
+  }
+
+  // bit position of row I (0..15) of a nibble-packed accumulator: four rows to a byte, in its low nibble
+  FLE_HD static constexpr uint32_t nib_pos(int i) { return (uint32_t)(8 * (i / 4) + (i % 4)); }
+
+  template <int R0, int N, int I, bool NIB>
+  __device__ __forceinline__ void rows_step(const uint32_t (&S)[16], uint32_t& acc) const {
+    if constexpr (I < N) {
+      acc = drop_at<(1u << (NIB ? nib_pos(I) : (uint32_t)I))>(acc, entry<R0 + I>(S));
+      rows_step<R0, N, I + 2, NIB>(S, acc);
+    }
+  }
+  template <int R0, int N, bool NIB>
+  __device__ __forceinline__ uint32_t rows(const uint32_t (&S)[16]) const {  // two independent IMAD chains
+    uint32_t acc0 = 0, acc1 = 0;
+    rows_step<R0, N, 0, NIB>(S, acc0);
+    rows_step<R0, N, 1, NIB>(S, acc1);
+    return acc0 + acc1;
+  }
+
+  // 16 rows whose entries carry two answers (bit 0: plane 11 = 0, bit 4: plane 11 = 1), chosen by the 16 bits
+  // of that plane in byte pair BP (0: bytes 0, 1; 1: bytes 2, 3) of xr -> 16 result bits in bytes 0 and 2
+  template <int R0, int BP>
+  __device__ __forceinline__ uint32_t rows16_sel(const uint32_t (&S)[16], uint32_t xr) const {
+    const uint32_t acc = rows<R0, 16, true>(S);
+    const uint32_t y1 = __byte_perm(xr, 0u, BP == 0 ? 0x4140 : 0x4342);  // [0][x byte 1][0][x byte 0] of the pair
+    const uint32_t y = (y1 | (y1 << 4)) & 0x0F0F0F0Fu;                   // nibble n of the 16 bits -> low nibble of byte n
+    const uint32_t t = bitsel_r(acc, acc >> 4, y);                       // low nibbles: the selected answers (high: don't care)
+    return bitsel<0xF0F0F0F0u>(t, t >> 4);                               // bytes 0 and 2: [nibble 1 | nibble 0], [nibble 3 | nibble 2]
+  }
+
+  __device__ __forceinline__ uint32_t half(const uint32_t (&S)[16], uint32_t xr) const {
+    if constexpr (IB::kNX == 0) {
+      return rows<0, 32, false>(S);
+    } else {
+      return __byte_perm(rows16_sel<0, 0>(S, xr), rows16_sel<16, 1>(S, xr), 0x6420);
+    }
+  }
+
+  __device__ __forceinline__ uint64_t compute(Planes& pl) const {
+    in_transpose(pl.S0);
+    in_transpose(pl.S1);
+    const uint64_t xr = __brevll(pl.X);
+    const uint32_t lo = half(pl.S0, (uint32_t)xr), hi = half(pl.S1, (uint32_t)(xr >> 32));
+    return ((uint64_t)hi << 32) | (uint64_t)lo;
+  }
+};
+
 // One CTA of 512 threads per SM.  Tried and dropped (tools/in_wide_probe.py, 600 M rows, bw 12):
 // consumer groups of 128 / 256 threads with their own stage rings and named barriers, so that warps
 // drift apart (264 / 245 us against 228 us for one ring); half a group per thread in CTAs of 1024
@@ -439,27 +740,51 @@ struct WideBitsPolicy {  // bw 13..16: bit table, 32 / 16 / 8 copies
   }
 };
 
+template <int BW>
+struct WideWordPolicy {  // in_wide = 2, bw <= 10: 32-bit entries addressed by one PRMT
+  using Decode = InWordDecode<BW>;
+  using IW = InWord<BW>;
+  static constexpr uint32_t kTableBytes = IW::kTableBytes;
+  static constexpr uint32_t kCopies = 1;  // (the decoder adds the lane itself)
+  static constexpr uint32_t kItemsPerLit = 32;
+  __device__ static __forceinline__ void put(uint32_t* table, uint32_t c, uint32_t lane) {
+    const uint32_t e = c & ((1u << IW::kTB) - 1u), x = c >> IW::kTB;
+    atomicOr(&table[e * 64u + lane], 1u << (x * (uint32_t)(IW::kCaseBits & 31)));
+  }
+};
+
+template <int BW>
+struct WideBytePolicy {  // in_wide = 2, bw 11 / 12: byte entries, lane bits transposed in as constant planes
+  using Decode = InByteDecode<BW>;
+  using IB = InByte<BW>;
+  static constexpr uint32_t kTableBytes = IB::kTableBytes;
+  static constexpr uint32_t kCopies = 1;
+  static constexpr uint32_t kItemsPerLit = 32;
+  __device__ static __forceinline__ void put(uint32_t* table, uint32_t c, uint32_t lane) {
+    const uint32_t e = c & ((1u << IB::kTB) - 1u), x = c >> IB::kTB;
+    atomicOr(&table[(e >> 2) * 32u + lane], 1u << ((e & 3u) * 8u + x * 4u));
+  }
+};
+
 // 16 consumer warps + one producer warp.  There is no CTA-wide barrier in the tile loop: a consumer
 // warp waits for the stage's "full" mbarrier, copies its groups' planes into registers, arrives on
 // the stage's "empty" mbarrier and only then evaluates; the producer refills a stage as soon as all
 // 16 warps have released it.  Warps therefore drift apart by up to a tile, which keeps some of them
 // in the ALU-only transposes while others are in the FMA / LSU-heavy lookups (bw 12, 600 M rows:
 // 229 -> 202 us; the same change made the two-CTA bit-table kernel above 7 % slower).
-constexpr int kInWideConsumers = 512;
-constexpr int kInWideThreads = kInWideConsumers + 32;
-
-template <int BW, class POL>
-__global__ void __launch_bounds__(kInWideThreads, 1) eval_in_wide_kernel(const __grid_constant__ EvalParams P) {
-  constexpr int NT = kInWideThreads, NC = kInWideConsumers;
+// NCW consumer warps, GPT groups per consumer thread per tile (tile = NCW * 32 * GPT groups).
+template <int BW, class POL, int NCW = 16, int GPT = 1>
+__global__ void __launch_bounds__(NCW * 32 + 32, 1) eval_in_wide_kernel(const __grid_constant__ EvalParams P) {
+  constexpr int NC = NCW * 32, NT = NC + 32;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t full0 = smem_u32(smem + P.smem_bar_off);  // full[s] at + 8 s, empty[s] at + 32 + 8 s (nstages <= 4)
   const uint32_t empty0 = full0 + 32u;
   const uint32_t stage0 = smem_u32(smem + P.smem_stage_off);
-  uint32_t* table_ptr = reinterpret_cast<uint32_t*>(smem + P.smem_masks_off);
+  uint32_t* table_ptr = reinterpret_cast<uint32_t*>(smem + kInTableOff);  // (a compile-time address: the lookups' immediate)
   typename POL::Decode dec;
-  dec.table = smem_u32(table_ptr) + (threadIdx.x & (POL::kCopies - 1u)) * 4u;
-  const int T = NC;  // one group per consumer thread per tile
-  const int seg_groups = T >> 3;
+  dec.init(smem_u32(table_ptr), threadIdx.x & 31u);
+  constexpr int T = NC * GPT;
+  constexpr int seg_groups = T >> 3;
   const int64_t ntiles = P.ngroups / T;
   const int nst = P.nstages;
 
@@ -501,17 +826,26 @@ __global__ void __launch_bounds__(kInWideThreads, 1) eval_in_wide_kernel(const _
     const int64_t thread_g = (int64_t)seg * seg_groups + jrow;
     int stage = 0;
     uint32_t parity = 0;
+    constexpr uint32_t kGroupStride = (uint32_t)(NC / 8) * BW * 8u;  // between a thread's groups inside its segment
+    const int64_t last_g = P.ngroups - 1;
+    const uint64_t tail_mask = (P.nrows & 63) ? ((1ull << (P.nrows & 63)) - 1ull) : ~0ull;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       mbar_wait(full0 + stage * 8, parity);
-      typename POL::Decode::Planes pl;
-      dec.load(InSmemGroup{stage0 + stage * P.stage_bytes + thread_off}, pl);
+      typename POL::Decode::Planes pl[GPT];
+#pragma unroll
+      for (int q = 0; q < GPT; ++q) dec.load(InSmemGroup{stage0 + stage * P.stage_bytes + thread_off + (uint32_t)q * kGroupStride}, pl[q]);
       __syncwarp();
       if ((threadIdx.x & 31u) == 0) mbar_arrive(empty0 + stage * 8);  // this warp is done with the stage
-      const int64_t g = tile * T + thread_g;
-      const uint64_t other = comb_load(P, g);  // (issued before the lookups: its latency hides behind them)
-      const uint64_t r = comb_apply(P, finish_row_order(dec.compute(pl), negmask, g, P.nrows), other);
-      P.bitmap[g] = r;
-      cnt_bits += __popcll(r);
+#pragma unroll
+      for (int q = 0; q < GPT; ++q) {
+        const int64_t g = tile * T + thread_g + q * (NC / 8);
+        const uint64_t other = comb_load(P, g);  // (issued before the lookups: its latency hides behind them)
+        uint64_t r = dec.compute(pl[q]) ^ negmask;
+        if (g == last_g) r &= tail_mask;  // (only the table's last group can hold rows past the end)
+        r = comb_apply(P, r, other);
+        P.bitmap[g] = r;
+        cnt_bits += __popcll(r);
+      }
       if (++stage == nst) {
         stage = 0;
         parity ^= 1u;
@@ -528,7 +862,31 @@ __global__ void __launch_bounds__(kInWideThreads, 1) eval_in_wide_kernel(const _
   publish_count<NT>(P, cnt_bits);
 }
 
-const void* eval_in_wide_kernel_for(int bw) {
+// Launch shape of the form-2 kernels (consumer warps, groups per consumer thread per tile), measured at 600 M rows with
+// L = 64 / 256 (tools/in_sweep.py --opt in_wide_warps=.. --opt in_wide_gpt=..; profiles/r02_in_sweep_variants.txt):
+// two groups per thread amortise the tile loop's fixed instructions where the registers allow it (bw 8-10: +1-2 %),
+// 24 warps hide more latency where they do not (bw 7, 12); 31 warps: unstable between runs (+3 % / -8 %).
+void eval_in_wide_shape(int bw, int* ncw, int* gpt) {
+  *ncw = (bw == 7 || bw == 12) ? 24 : 16;
+  *gpt = (bw >= 8 && bw <= 10) ? 2 : 1;
+}
+
+const void* eval_in_wide_kernel_for(int bw, int form, int ncw, int gpt) {
+  if (form >= 2) {
+#define V(B, POL, W, Q) if (bw == B && ncw == W && gpt == Q) return (const void*)eval_in_wide_kernel<B, POL<B>, W, Q>;
+#define VS(B, POL) V(B, POL, 16, 1) V(B, POL, 16, 2) V(B, POL, 24, 1)
+    VS(7, WideWordPolicy) VS(8, WideWordPolicy) VS(9, WideWordPolicy) VS(10, WideWordPolicy)
+    VS(11, WideBytePolicy) VS(12, WideBytePolicy)
+#undef VS
+#undef V
+    if (ncw != 16 || gpt != 1) return nullptr;
+    switch (bw) {
+#define X(B) case B: return (const void*)eval_in_wide_kernel<B, WideWordPolicy<B> >;
+      X(1) X(2) X(3) X(4) X(5) X(6)
+#undef X
+    }
+  }
+  if (ncw != 16 || gpt != 1) return nullptr;
   switch (bw) {
 #define X(B) case B: return (const void*)eval_in_wide_kernel<B, WideEntryPolicy<B> >;
     X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12)
@@ -540,7 +898,9 @@ const void* eval_in_wide_kernel_for(int bw) {
   return nullptr;
 }
 
-uint32_t eval_in_wide_table_bytes(int bw) {
+uint32_t eval_in_wide_table_bytes(int bw, int form) {
+  if (form >= 2 && bw <= 10) return (1u << std::min(bw, 8)) * 256u;          // InWord<bw>::kTableBytes
+  if (form >= 2 && bw <= 12) return bw <= 2 ? 128u : (1u << (std::min(bw, 11) - 2)) * 128u;  // InByte<bw>::kTableBytes
   if (bw > 12) return (4u << (bw - 5)) * (bw <= 14 ? 32u : (bw == 15 ? 16u : 8u));  // InTable<bw, true>::kTableBytes
   const int tb = bw < 11 ? bw : 11;
   return (uint32_t)std::max(2, 1 << tb) * 64u;

@@ -64,8 +64,11 @@ struct fle_ctx {
   int eval_gpt = 0;          // 0 = auto
   int eval_narrow_bw = 2;    // single-pass programs on columns up to this width skip shared-memory staging (bw 1, 2, 4)
   int in_lookup_min = 9;     // IN lists at least this long use the decode+lookup kernel (bw <= 16); shorter ones the plane form
-  int in_wide = 1;           // IN lookup on bw <= 12: 16-bit entry table (1) or the bit table (0)
-  int in_mux_bw = 7;         // IN lists of in_lookup_min+ literals on columns up to this width run in the plane domain (0 = never)
+  int in_wide = 2;           // IN lookup kernel: two-CTA bit table (0), one-CTA producer/consumer kernel with 16-bit entries (1),
+                             // ... with word / byte entries addressed straight from the transposed word, bw <= 12 (2)
+  int in_wide_warps = 0;     // consumer warps per CTA of the one-CTA IN lookup kernel (form 2: 16 or 24; 0 = measured default)
+  int in_wide_gpt = 0;       // groups per consumer thread per tile (form 2: 1, or 2 with 16 warps; 0 = measured default)
+  int in_mux_bw = 6;         // IN lists of in_lookup_min+ literals on columns up to this width run in the plane domain (0 = never)
   int64_t in_split_min_rows = 1ll << 20;  // calls of at least this many rows evaluate long IN lists (>= 16 literals) inside larger programs with the lookup kernels; -1 = never
   int codec_variant = 1;
   int codec_ctas_per_sm = 0;  // 0 = as many as fit
@@ -103,6 +106,8 @@ struct fle_ctx {
   uint64_t* d_split = nullptr;    // temporary bitmaps of regrouped programs (long IN lists), grow-only
   size_t split_cap = 0;           // bytes
   uint64_t* h_count = nullptr;    // pinned
+  uint64_t* d_chunk_counts = nullptr;  // per-chunk counts of the host-buffer pipeline (fle_eval), grow-only
+  size_t chunk_counts_cap = 0;         // 64-bit words
 
   // host-facing pipelines: staging buffers
   void* d_stage[2] = {nullptr, nullptr};
@@ -187,10 +192,12 @@ const void* eval_in_mux_kernel_for(int bw);
 // fle_eval_in.cu: IN list by decode + membership-table lookup (bw <= 16), or nullptr
 const void* eval_in_kernel_for(int bw);
 // fle_eval_in.cu: IN list by decode + 16-bit entry table (bw <= 12, CTAs of 512 threads), or nullptr
-const void* eval_in_wide_kernel_for(int bw);
-constexpr int kInWideThreadsPerCta = 512 + 32;  // 16 consumer warps + the producer warp
-constexpr int kInWideGroupsPerTile = 512;
-uint32_t eval_in_wide_table_bytes(int bw);
+// form 1: 16-bit entries (bw <= 12) / replicated bit table (bw 13..16); form 2: word / byte entries addressed straight
+// from the transposed word (bw <= 12), same as form 1 beyond
+// ncw consumer warps (+ one producer warp) per CTA, gpt groups per consumer thread per tile
+const void* eval_in_wide_kernel_for(int bw, int form, int ncw, int gpt);
+void eval_in_wide_shape(int bw, int* ncw, int* gpt);  // the measured default of (ncw, gpt) per bit width
+uint32_t eval_in_wide_table_bytes(int bw, int form);
 // out = postfix program over K device bitmaps (leaf.col = bitmap index), word by word
 int launch_bitmap_combine(fle_ctx* ctx, const uint64_t* const* leaf_bitmaps_dev, int nleaf,
                           const fle_pred_node* nodes, int nnodes, int64_t nbits, uint64_t* out_dev,

@@ -122,9 +122,15 @@ int fle_ctx_sync(fle_ctx* ctx);
  * "in_split_min_rows" (device-resident evaluations of at least this many rows -- default 2^20 --
  * evaluate IN lists of >= 16 literals that sit INSIDE a larger program with the lookup kernels and
  * combine bitmaps, instead of walking the literal pool in the fused kernel; -1 = never),
- * "in_wide" (1 [default]: the lookup runs on the one-CTA-per-SM producer/consumer kernel --
- * 16-bit table entries for bw <= 12, replicated bit table for bw 13..16; 0: the two-CTA bit-table
- * kernel, kept as an on-device cross-check),
+ * "in_wide" (2 [default]: the lookup runs on the one-CTA-per-SM producer/consumer kernel with table
+ * entries addressed straight from the transposed word -- 32-bit entries for bw <= 10, byte entries
+ * for bw 11 / 12, three instructions per lookup -- and a replicated bit table for bw 13..16;
+ * 1: the same kernel with 16-bit entries for bw <= 12 (round 1's form); 0: the two-CTA bit-table
+ * kernel; the older forms stay as on-device cross-checks),
+ * "in_wide_warps", "in_wide_gpt" (0 = measured default: consumer warps per CTA and groups per
+ * consumer thread per tile of the form-2 lookup kernel),
+ * "in_mux_bw" (IN lists of in_lookup_min+ literals on columns up to this width -- default 6, at
+ * most 7 -- are evaluated in the plane domain as a multiplexer tree; 0 = never),
  * "codec_variant" (0 = direct loads/stores; 1 [default] = per-bit-width choice among the staged
  * unpack kernels; 2 = per-row bulk stores, 3 = warp-private copy-out, 4 = CTA-wide copy-out),
  * "codec_ctas_per_sm" (0 = auto), "h2d_chunk_rows",

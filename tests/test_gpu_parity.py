@@ -258,6 +258,21 @@ def test_nullable_columns_vs_oracle(ctx, oracle, null_frac):
 # ------------------------------------------------------------------------------------------
 # device-resident API at BASELINE.json sizes: size-independent properties
 # ------------------------------------------------------------------------------------------
+def _torch_pack_mask(mask):
+    """Boolean row mask -> selection bitmap packed by torch on the device (row r -> bit r & 63 of word
+    r >> 6, fle-encoding.h:7989-8008): an independent full-size image to compare EVERY word against."""
+    import torch
+    n = mask.numel()
+    G = (n + 63) // 64
+    if G * 64 != n:
+        mask = torch.cat([mask, torch.zeros(G * 64 - n, dtype=torch.bool, device=mask.device)])
+    m = mask.view(G, 64)
+    want = torch.zeros(G, dtype=torch.int64, device=mask.device)
+    for b in range(64):
+        want |= m[:, b].to(torch.int64) << b
+    return want
+
+
 def _torch_bits_to_count(bitmap):
     import torch
     b = bitmap.view(torch.uint8)
@@ -300,8 +315,9 @@ def test_cfg0_roundtrip_16M(ctx, bw):
 
 def test_cfg1_between_full_size(ctx):
     """config 1: N = 600,037,902 (SF100 lineitem rows), bw 12 BETWEEN; the count must equal a
-    plain torch compare on the values, both kernels must agree bit for bit, and the bitmap's
-    popcount must equal the reported count (checksum of checksums)."""
+    plain torch compare on the values, EVERY word of the bitmap must equal a bitmap packed by torch
+    from that compare, both kernels must agree bit for bit, and the bitmap's popcount must equal the
+    reported count (checksum of checksums)."""
     import torch
     n = 600_037_902
     bw = 12
@@ -309,11 +325,16 @@ def test_cfg1_between_full_size(ctx):
     vals = torch.randint(0, 4096, (n,), generator=g, device="cuda", dtype=torch.int32)
     words = ctx.pack_dev(vals, bw)
     lo, hi = 1000, 1409  # ~10 %
-    want = int(((vals >= lo) & (vals <= hi)).sum().item())
+    mask = (vals >= lo) & (vals <= hi)
+    want = int(mask.sum().item())
+    want_bm = _torch_pack_mask(mask)
+    del mask
     prog = [(GE, 0, lo), (LE, 0, hi), (AND, None, None)]
     bm1, c1 = ctx.eval_dev([(words, bw)], prog, n)
     torch.cuda.synchronize()
     assert int(c1.item()) == want
+    assert torch.equal(bm1, want_bm), "full 600 M-row bitmap differs from the torch-packed one"
+    del want_bm
     assert _torch_bits_to_count(bm1) == want
     ctx.set_option("eval_variant", 0)
     try:
@@ -352,6 +373,7 @@ def test_cfg2_q6_full_size(ctx):
             disc = v
     want_cnt = int(mask.sum().item())
     want_rev = int((price[mask] * dd[disc[mask].long()]).sum().item())
+    want_bm = _torch_pack_mask(mask)
     del mask, disc, v, m
     prog = [(GE, 0, 730), (LE, 0, 1094), (AND, None, None), (GE, 1, 5), (LE, 1, 7), (AND, None, None),
             (AND, None, None), (LT, 2, 23), (AND, None, None)]
@@ -359,6 +381,8 @@ def test_cfg2_q6_full_size(ctx):
     out = ctx.eval_sum_product_dev(cols, prog, n, price, 1, dd, bitmap=bm)
     torch.cuda.synchronize()
     assert int(out[0].item()) == want_rev and int(out[1].item()) == want_cnt
+    assert torch.equal(bm, want_bm), "full 600 M-row Q6 bitmap differs from the torch-packed one"
+    del want_bm
     assert _torch_bits_to_count(bm) == want_cnt
     bm1, c1 = ctx.eval_dev(cols, prog, n)
     two = ctx.sum_product_dev(bm1, n, price, cols[1][0], 4, dd)
@@ -388,10 +412,15 @@ def test_cfg3_in_lists_and_trees_full_size(ctx):
         w = ctx.pack_dev(v, bw)
         for L in (8, 64, 256):
             lits = torch.randint(0, d, (L,), generator=cpu)
-            want = int(torch.isin(v, lits.to("cuda", torch.int32)).sum().item())
+            member = torch.isin(v, lits.to("cuda", torch.int32))
+            want = int(member.sum().item())
+            want_bm = _torch_pack_mask(member)
+            del member
             bm, c = ctx.eval_dev([(w, bw)], [(IN, 0, lits.tolist())], n)
             torch.cuda.synchronize()
             assert int(c.item()) == want and _torch_bits_to_count(bm) == want, (bw, L)
+            assert torch.equal(bm, want_bm), ("full bitmap", bw, L)
+            del want_bm
             if L == 8:  # the other IN implementation (lookup kernel <-> unrolled equality chains)
                 ctx.set_option("in_lookup_min", 1)
                 try:
@@ -419,8 +448,7 @@ def test_cfg3_in_lists_and_trees_full_size(ctx):
         bm, c = ctx.eval_dev(cols, prog, n)
         torch.cuda.synchronize()
         assert int(c.item()) == want and _torch_bits_to_count(bm) == want, name
-        idx = torch.randint(0, n, (100000,), device="cuda")
-        assert torch.equal(((bm[idx >> 6] >> (idx & 63)) & 1).bool(), mask[idx]), name
+        assert torch.equal(bm, _torch_pack_mask(mask)), ("full bitmap", name)
 
 
 def test_two_contexts_two_threads(ctx, oracle):
@@ -522,7 +550,8 @@ def test_in_list_lookup_kernel_vs_oracle(ctx, oracle, bw):
         want, wcnt = oracle.pred(IN, words, bw, 0, n, lits)
         # (lookup_min, in_wide, in_mux_bw): multiplexer tree over the planes (bw <= 7), one-CTA producer/consumer kernel
         # (entry table, replicated bit table), two-CTA bit-table kernel, equality chains on the planes
-        for lookup_min, wide, mux in ((1, 1, 7), (1, 1, 0), (1, 0, 0), (1 << 30, 1, 7)):
+        # (wide 2: word / byte entries addressed straight from the transposed word; 1: 16-bit entries)
+        for lookup_min, wide, mux in ((1, 2, 7), (1, 2, 0), (1, 1, 0), (1, 0, 0), (1 << 30, 2, 7)):
             ctx.set_option("in_lookup_min", lookup_min)
             ctx.set_option("in_wide", wide)
             ctx.set_option("in_mux_bw", mux)
@@ -531,8 +560,8 @@ def test_in_list_lookup_kernel_vs_oracle(ctx, oracle, bw):
                 mode = ctx.get_option("last_mode")
             finally:
                 ctx.set_option("in_lookup_min", 9)
-                ctx.set_option("in_wide", 1)
-                ctx.set_option("in_mux_bw", 7)
+                ctx.set_option("in_wide", 2)
+                ctx.set_option("in_mux_bw", 6)
             assert (bm == want).all() and cnt == wcnt, (bw, L, lookup_min, wide, mux)
             if lookup_min == 1 and bw <= 16:
                 assert mode == (7 if bw <= mux else (6 if wide else 3)), (bw, mode)

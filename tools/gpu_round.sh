@@ -1,0 +1,22 @@
+#!/bin/bash
+# One GPU-box call: parity tests, the bench line, its ncu launch list, sweeps, ncu --set full captures.
+# Usage (from the repo root on the GPU box):  bash tools/gpu_round.sh [tag]
+tag=${1:-r02}
+out=gpurun_out
+mkdir -p $out
+( time timeout 1500 python -m pytest tests -m gpu -x -q ) > $out/${tag}_pytest_gpu.log 2>&1
+echo "pytest rc=$?" >> $out/${tag}_pytest_gpu.log
+timeout 900 python bench.py > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err
+echo "bench rc=$?"
+timeout 900 python bench.py --impl reference --steps 5 --warmup 1 > $out/${tag}_bench_reference_arm.json 2>> $out/${tag}_bench_n1.err
+timeout 600 python tools/in_sweep.py --out $out/${tag}_in_sweep.txt > /dev/null 2> $out/${tag}_in_sweep.err
+timeout 900 python tools/sweep.py programs --rows 600037902 --out $out/${tag}_sweep_programs_600M_rows.jsonl > /dev/null 2> $out/${tag}_sweep_programs.err
+timeout 600 python tools/sweep.py aux --rows 268435456 --out $out/${tag}_sweep_aux.jsonl > /dev/null 2> $out/${tag}_sweep_aux.err
+# launch list of the bench command (shares, not absolutes)
+timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/${tag}_bench_launches.csv \
+    python bench.py --steps 20 --warmup 3 --no-cpu > $out/${tag}_bench_under_ncu.log 2>&1
+for c in between12 q6agg in256; do
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:'eval|fle_jit' -c 2 -f -o $out/${tag}_${c} \
+      python tools/profile_one.py $c 600037902 3 > $out/${tag}_ncu_${c}.log 2>&1
+done
+ls -la $out

@@ -63,9 +63,12 @@ elif case.startswith("between"):
     for _ in range(reps):
         ctx.eval_dev(cols, prog, n, bitmap=bm, count=cnt)
 elif case.startswith("in"):
-    L = int(case[2:])
-    cols = [(col(2526, 12)[1], 12)]
-    prog = [(IN, 0, torch.randint(0, 2526, (L,)).tolist())]
+    # in<L> (bw 12, 2526 codes) or in<L>x<bw>
+    L, _, bwx = case[2:].partition("x")
+    L, bwx = int(L), int(bwx or 12)
+    dom = 2526 if bwx == 12 else min(1 << bwx, 40000)
+    cols = [(col(dom, bwx)[1], bwx)]
+    prog = [(IN, 0, torch.randint(0, dom, (L,)).tolist())]
     for _ in range(reps):
         ctx.eval_dev(cols, prog, n, bitmap=bm, count=cnt)
 elif case.startswith("unpack") or case.startswith("pack"):

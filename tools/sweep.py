@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Kernel sweeps on one B200 (device-resident inputs, CUDA events, min/median of `reps`).
+"""Kernel sweeps on one B200 (device-resident inputs, CUDA events, MEDIAN of `reps`; launches whose
+working set is below 2x the 126 MB L2 are timed one by one with an L2 flush -- a 384 MB overwrite --
+before each, so every fraction is a DRAM-bound number).
 
     python tools/sweep.py between|codec|programs|tune|all [--rows N] [--out gpurun_out/sweep.jsonl]
 
@@ -33,29 +35,52 @@ def peak():
 PEAK = peak()
 
 
-def timeit(fn, reps=10, warm=3, inner=8):
-    """Per-launch time with `inner` launches queued back to back between two events, so that the
-    host-side launch path overlaps the previous kernel (as in a real scan loop)."""
+L2_BYTES = 126 << 20
+_flush_buf = None
+
+
+def flush_l2():
+    global _flush_buf
+    if _flush_buf is None:
+        _flush_buf = torch.empty(384 << 20, dtype=torch.uint8, device="cuda")
+    _flush_buf.fill_(1)
+
+
+def timeit(fn, reps=10, warm=3, inner=8, working_set=None):
+    """Per-launch time.  Working sets above 2x L2: `inner` launches queued back to back between two
+    events, so that the host-side launch path overlaps the previous kernel (as in a real scan loop; the
+    inputs cannot stay in L2).  Smaller working sets (or unknown): one launch per event pair with the
+    L2 flushed before it."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
     ts = []
-    for _ in range(reps):
+    cold = working_set is None or working_set < 2 * L2_BYTES
+    for _ in range(reps if not cold else max(reps, 7)):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(inner):
+        if cold:
+            flush_l2()
+            a.record()
             fn()
-        b.record()
-        torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b) / inner)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        else:
+            a.record()
+            for _ in range(inner):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) / inner)
     return min(ts), statistics.median(ts)
 
 
 def rec(out, **kw):
     if "alg_bytes" in kw and "ms_min" in kw:
-        kw["GBps"] = kw["alg_bytes"] / (kw["ms_min"] * 1e-3) / 1e9
-        kw["GBps_med"] = kw["alg_bytes"] / (kw["ms_med"] * 1e-3) / 1e9
-        kw["frac"] = kw["GBps"] / PEAK
+        kw["GBps"] = kw["alg_bytes"] / (kw["ms_med"] * 1e-3) / 1e9
+        kw["GBps_best"] = kw["alg_bytes"] / (kw["ms_min"] * 1e-3) / 1e9
+        kw["frac"] = kw["GBps"] / PEAK          # of the MEDIAN launch
+        kw["cold_l2"] = kw["alg_bytes"] < 2 * L2_BYTES
     line = json.dumps(kw)
     print(line, flush=True)
     out.write(line + "\n")
@@ -87,7 +112,7 @@ def sweep_between(ctx, out, n, variants=(1, 2, 0), bws=range(1, 33)):
         prep = (ctx.make_col_descs(cols),) + fle_b200.capi._build_program(prog)
         for var in variants:
             ctx.set_option("eval_variant", var)
-            mn, md = timeit(lambda: ctx.eval_dev(cols, prog, n, bitmap=bm, count=cnt, prepared=prep))
+            mn, md = timeit(lambda: ctx.eval_dev(cols, prog, n, bitmap=bm, count=cnt, prepared=prep), working_set=G * bw * 8)
             rec(out, what="between", variant=var, bw=bw, rows=n, ms_min=mn, ms_med=md, alg_bytes=G * bw * 8 + G * 8,
                 rows_per_s=n / (mn * 1e-3), count=int(cnt.item()))
         ctx.set_option("eval_variant", 1)
@@ -108,7 +133,7 @@ def sweep_selectivity(ctx, out, n, bw=12):
         lo = (D - width) // 2
         prog = [(GE, 0, lo), (LE, 0, lo + width - 1), (AND, None, None)]
         prep = (ctx.make_col_descs(cols),) + fle_b200.capi._build_program(prog)
-        mn, md = timeit(lambda: ctx.eval_dev(cols, prog, n, bitmap=bm, count=cnt, prepared=prep))
+        mn, md = timeit(lambda: ctx.eval_dev(cols, prog, n, bitmap=bm, count=cnt, prepared=prep), working_set=G * bw * 8)
         rec(out, what="selectivity", sel_pct=sel, bw=bw, rows=n, ms_min=mn, ms_med=md, alg_bytes=G * bw * 8 + G * 8,
             rows_per_s=n / (mn * 1e-3), observed_sel=int(cnt.item()) / n)
 
@@ -118,12 +143,12 @@ def sweep_codec(ctx, out, n, bws=range(1, 33)):
     for bw in bws:
         v, w = make_col(ctx, n, bw, seed=100 + bw)
         o = torch.empty(n, dtype=torch.int32, device="cuda")
-        mn, md = timeit(lambda: ctx.unpack_dev(w, bw, 0, n, out=o))
+        mn, md = timeit(lambda: ctx.unpack_dev(w, bw, 0, n, out=o), working_set=n * 4)
         ok = bool(torch.equal(o, v))
         rec(out, what="unpack", bw=bw, values=n, ms_min=mn, ms_med=md, alg_bytes=G * bw * 8 + n * 4,
             values_per_s=n / (mn * 1e-3), ok=ok)
         w2 = torch.empty_like(w)
-        mn, md = timeit(lambda: ctx.pack_dev(v, bw, out=w2))
+        mn, md = timeit(lambda: ctx.pack_dev(v, bw, out=w2), working_set=n * 4)
         ok = bool(torch.equal(w2, w))
         rec(out, what="pack", bw=bw, values=n, ms_min=mn, ms_med=md, alg_bytes=G * bw * 8 + n * 4,
             values_per_s=n / (mn * 1e-3), ok=ok)
@@ -170,7 +195,8 @@ def sweep_programs(ctx, out, n):
         for label, var, jit in (("1j", 1, 2), (1, 1, 0), (2, 2, 0), (0, 0, 0)):
             ctx.set_option("eval_variant", var)
             ctx.set_option("eval_jit", jit)
-            mn, md = timeit(lambda: ctx.eval_dev(pc, prog, n, bitmap=bm, count=cnt, prepared=prep), reps=5 if "in256" in name else 10)
+            mn, md = timeit(lambda: ctx.eval_dev(pc, prog, n, bitmap=bm, count=cnt, prepared=prep), reps=5 if "in256" in name else 10,
+                            working_set=G * sum_bw * 8)
             rec(out, what="program", name=name, variant=label, rows=n, sum_bw=sum_bw, ms_min=mn, ms_med=md,
                 alg_bytes=G * sum_bw * 8 + G * 8, rows_per_s=n / (mn * 1e-3), count=int(cnt.item()))
         ctx.set_option("eval_variant", 1)
@@ -182,7 +208,7 @@ def sweep_programs(ctx, out, n):
     pc = [cols[c] + (ones,) for c in ("shipdate", "discount", "quantity")]
     prog = [tuple(p) + (None,) * (3 - len(p)) for p in programs["q6"][1]]
     prep = (ctx.make_col_descs(pc),) + fle_b200.capi._build_program(prog)
-    mn, md = timeit(lambda: ctx.eval_dev(pc, prog, n, bitmap=bm, count=cnt, prepared=prep))
+    mn, md = timeit(lambda: ctx.eval_dev(pc, prog, n, bitmap=bm, count=cnt, prepared=prep), working_set=G * 25 * 8)
     rec(out, what="program", name="q6_optional_cols_no_nulls", variant="1j", rows=n, sum_bw=25, ms_min=mn, ms_med=md,
         alg_bytes=G * 25 * 8 + G * 8, rows_per_s=n / (mn * 1e-3), count=int(cnt.item()))
 
@@ -226,7 +252,7 @@ def sweep_tune(ctx, out, n):
                         ctx.set_option("eval_gpt", gpt)
                         ctx.set_option("eval_ctas_per_sm", cps)
                         try:
-                            mn, md = timeit(lambda: ctx.eval_dev(pc, prog, n, bitmap=bm, count=cnt, prepared=prep), reps=4, warm=2)
+                            mn, md = timeit(lambda: ctx.eval_dev(pc, prog, n, bitmap=bm, count=cnt, prepared=prep), reps=4, warm=2, working_set=G * sum_bw * 8)
                         except fle_b200.FleError as e:
                             continue
                         rec(out, what="tune", case=cname, block=variant, stages=stages, gpt=gpt, ctas=cps, ms_min=mn,
@@ -267,13 +293,13 @@ def sweep_aux(ctx, out, n):
         m = min(n, 1 << 28)
         x = torch.randint(0, 1 << 20, (m,), generator=g, device="cuda", dtype=torch.int64).to(dt)
         pb = torch.empty((m + 63) // 64, dtype=torch.int64, device="cuda")
-        mn, md = timeit(lambda: ctx.plain_eval_dev(x, GE, [1 << 19], bitmap=pb, count=cnt))
+        mn, md = timeit(lambda: ctx.plain_eval_dev(x, GE, [1 << 19], bitmap=pb, count=cnt), working_set=m * nb)
         rec(out, what="aux", name=f"plain_eval {str(dt).split('.')[-1]}", rows=m, ms_min=mn, ms_med=md,
             alg_bytes=m * nb + (m + 63) // 64 * 8)
         del x, pb
     blob = torch.randint(0, 255, ((1 << 28) + 64,), generator=g, device="cuda", dtype=torch.int64).to(torch.uint8)
     dst = torch.empty((1 << 28) // 8 + 2, dtype=torch.int64, device="cuda")
-    mn, md = timeit(lambda: ctx.realign_dev(blob, 5, 1 << 28, out=dst))
+    mn, md = timeit(lambda: ctx.realign_dev(blob, 5, 1 << 28, out=dst), working_set=2 << 28)
     rec(out, what="aux", name="realign (funnel-shift copy, 256 MiB)", rows=1 << 28, ms_min=mn, ms_med=md, alg_bytes=2 << 28)
     del blob, dst
     m = 1 << 24
