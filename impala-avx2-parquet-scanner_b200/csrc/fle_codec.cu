@@ -413,6 +413,175 @@ unpack_narrow_kernel(const uint64_t* __restrict__ enc, int64_t ngroups, int64_t 
   }
 }
 
+// Narrow decode targets, second form (default): the pipeline of unpack_warp_kernel below -- three plane stages handed
+// back through "empty" mbarriers, warp-private copy-out, NO CTA barrier in the tile loop -- because a narrow tile is
+// short (bw 8 -> u8: 8 KB in, 8 KB out) and the two CTA barriers per tile of the first form left it at 0.40-0.59 of
+// its roofline (2^26 values).  u8 rows come out of two 8 x 8 SWAR transposes (fle_device.cuh: 96 instructions per
+// group instead of the 32 x 32 butterfly's 240) and 4 x 4 byte transposes (16 PRMT) that put neighbouring rows next
+// to each other; u16 rows out of the shared 32 x 32 butterfly as before.
+// Value tile: row = group (64 * ES bytes); 16-byte chunk c of row r sits at slot (c + r / 16) mod (4 ES) of the
+// row, and for u8 the two rows of a 128-byte line swap places in the upper half of the tile -- the eight lanes of
+// a store phase own rows 16 apart and the eight lanes of a copy-out phase read two neighbouring rows: both hit
+// eight distinct 16-byte slots.
+template <int ES>
+__device__ __forceinline__ uint32_t narrow_chunk_addr(uint32_t tile, int row, int chunk) {
+  constexpr int kChunks = 4 * ES;
+  const int prow = ES == 1 ? (row ^ ((row >> 6) & 1)) : row;
+  return tile + (uint32_t)prow * (64u * ES) + ((uint32_t)((chunk + (row >> 4)) & (kChunks - 1)) << 4);
+}
+
+// the 64 values of a group as 16 * ES words in row order
+template <int BW, int ES>
+__device__ __forceinline__ void transpose_planes_to_narrow(const uint64_t (&w)[BW], uint32_t (&o)[16 * ES]) {
+  if constexpr (ES == 1) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {  // rows 0..31 (bits 63..32 of the plane words), rows 32..63
+      uint32_t S[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) S[7 - i] = i < BW ? (uint32_t)(w[i < BW ? i : 0] >> (h == 0 ? 32 : 0)) : 0u;
+      swar8_transpose(S);  // S[x] byte b = value of the half's row 24 - 8 b + x
+#pragma unroll
+      for (int x0 = 0; x0 < 8; x0 += 4) {  // 4 x 4 byte transpose: Y[b] = rows 24 - 8 b + x0 .. + 3
+        const uint32_t t0 = __byte_perm(S[x0], S[x0 + 1], 0x5140), t1 = __byte_perm(S[x0], S[x0 + 1], 0x7362);
+        const uint32_t t2 = __byte_perm(S[x0 + 2], S[x0 + 3], 0x5140), t3 = __byte_perm(S[x0 + 2], S[x0 + 3], 0x7362);
+        // output word m of the half (rows 4 m .. 4 m + 3): b = 3 - m / 2, x0 = 4 (m % 2)
+        o[h * 8 + 6 + x0 / 4] = __byte_perm(t0, t2, 0x5410);  // b = 0: rows 24 + x0 ..
+        o[h * 8 + 4 + x0 / 4] = __byte_perm(t0, t2, 0x7632);  // b = 1: rows 16 + x0 ..
+        o[h * 8 + 2 + x0 / 4] = __byte_perm(t1, t3, 0x5410);  // b = 2: rows 8 + x0 ..
+        o[h * 8 + 0 + x0 / 4] = __byte_perm(t1, t3, 0x7632);  // b = 3: rows x0 ..
+      }
+    }
+  } else {
+    uint32_t A[32];  // after the transpose A[k] = value(row k) | value(row 32 + k) << 16
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      A[31 - i] = i < BW ? (uint32_t)(w[i < BW ? i : 0] >> 32) : 0u;
+      A[15 - i] = i < BW ? (uint32_t)(w[i < BW ? i : 0]) : 0u;
+    }
+    transpose32(A);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      o[j] = __byte_perm(A[2 * j], A[2 * j + 1], 0x5410);       // rows 2 j, 2 j + 1
+      o[16 + j] = __byte_perm(A[2 * j], A[2 * j + 1], 0x7632);  // rows 32 + 2 j, 33 + 2 j
+    }
+  }
+}
+
+template <int BW, int ES>
+__global__ void __launch_bounds__(kCodecThreads)
+unpack_narrow_warp_kernel(const uint64_t* __restrict__ enc, int64_t ngroups, int64_t nvals, uint8_t* __restrict__ out) {
+  static_assert((ES == 1 && BW <= 8) || (ES == 2 && BW <= 16), "u8 for bw <= 8, u16 for bw <= 16");
+  using PT = PlaneTile<BW>;
+  constexpr int kStages = 3;
+  constexpr int kRowBytes = 64 * ES, kChunks = 4 * ES;
+  constexpr int kTileBytes = kCodecThreads * kRowBytes;
+  constexpr uint32_t kStageStride = (PT::kBytes + 127) / 128 * 128;
+  extern __shared__ __align__(128) uint8_t smem[];
+  // [value tile][stages][full mbarriers][empty mbarriers]
+  const uint32_t tile = smem_u32(smem);
+  const uint32_t stage0 = tile + kTileBytes;
+  const uint32_t full0 = stage0 + kStages * kStageStride;
+  const uint32_t empty0 = full0 + kStages * 8;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int64_t ntiles_full = nvals / (PT::kGroups * 64);
+
+  if (t == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full0 + s * 8, 1);
+      mbar_init(empty0 + s * 8, kCodecThreads / 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue = [&](int stage, int64_t tl) {
+    const uint32_t bar = full0 + stage * 8;
+    mbar_arrive_expect_tx(bar, 8 * PT::kSegBytes);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(enc) + (uint64_t)tl * PT::kGroups * BW * 8;
+#pragma unroll
+    for (int s = 0; s < 8; ++s)
+      tma_load_1d(stage0 + stage * kStageStride + s * PT::kSegStride, src + (uint64_t)s * PT::kSegBytes, PT::kSegBytes, bar);
+  };
+  if (t == 0) {
+    for (int s = 0; s < kStages - 1; ++s) {
+      const int64_t tl = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
+      if (tl < ntiles_full) issue(s, tl);
+    }
+  }
+  const int row = PT::thread_group(t);  // (t & 7) * 16 + (t >> 3)
+  int stage = 0;
+  uint32_t use = 0;
+  for (int64_t tl = blockIdx.x; tl < ntiles_full; tl += gridDim.x) {
+    if (t == 0) {  // refill the stage consumed in the previous iteration, two tiles ahead (protocol: unpack_warp_kernel)
+      const int64_t nxt = tl + (int64_t)(kStages - 1) * gridDim.x;
+      int st2 = stage + kStages - 1;
+      uint32_t use2 = use;
+      if (st2 >= kStages) { st2 -= kStages; use2 += 1; }
+      if (nxt < ntiles_full) {
+        if (use2 >= 1) mbar_wait(empty0 + st2 * 8, (use2 - 1) & 1u);
+        issue(st2, nxt);
+      }
+    }
+    mbar_wait(full0 + stage * 8, use & 1u);
+    uint64_t w[BW];
+    const uint32_t a = stage0 + stage * kStageStride + PT::thread_off(t);
+    if constexpr (BW % 2 == 0) {
+#pragma unroll
+      for (int i = 0; i < BW; i += 2) lds128(a + i * 8, w[i], w[i + 1 < BW ? i + 1 : i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < BW; ++i) w[i] = lds64(a + i * 8);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty0 + stage * 8);
+    uint32_t o[16 * ES];
+    transpose_planes_to_narrow<BW, ES>(w, o);
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c)
+      sts128u(narrow_chunk_addr<ES>(tile, row, c), o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+    __syncwarp();
+    uint8_t* dst = out + tl * (int64_t)kTileBytes;
+#pragma unroll
+    for (int it = 0; it < kChunks; ++it) {
+      const int q = it * 32 + lane;   // 16-byte chunk among this warp's 32 rows
+      const int rr = q / kChunks;     // this warp's rr-th row: segment rr >> 2, row (rr & 3) of the warp's four
+      const int ch = q % kChunks;
+      const int r = (rr >> 2) * 16 + warp * 4 + (rr & 3);
+      uint32_t x, y, z, u;
+      lds128u(narrow_chunk_addr<ES>(tile, r, ch), x, y, z, u);
+      stg_stream128(dst + r * kRowBytes + ch * 16, make_uint4(x, y, z, u));
+    }
+    __syncwarp();
+    if (++stage == kStages) {
+      stage = 0;
+      use += 1;
+    }
+  }
+  // ragged remainder (< 128 * 64 values): plain loads and guarded stores
+  for (int64_t g = ntiles_full * PT::kGroups + (int64_t)blockIdx.x * kCodecThreads + t; g < ngroups;
+       g += (int64_t)gridDim.x * kCodecThreads) {
+    uint64_t w[BW];
+    const uint64_t* src = enc + g * BW;
+#pragma unroll
+    for (int i = 0; i < BW; ++i) w[i] = __ldg(src + i);
+    uint32_t o[16 * ES];
+    transpose_planes_to_narrow<BW, ES>(w, o);
+    const int64_t left = nvals - g * 64;
+    uint8_t* dst = out + g * kRowBytes;
+    if (left >= 64) {
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) stg_stream128(dst + 16 * c, make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 64; ++k) {
+        if (k < left) {
+          if constexpr (ES == 1) dst[k] = (uint8_t)(o[k >> 2] >> ((k & 3) * 8));
+          else reinterpret_cast<uint16_t*>(dst)[k] = (uint16_t)(o[k >> 1] >> ((k & 1) * 16));
+        }
+      }
+    }
+  }
+}
+
 // Unpack with warp-private copy-out (codec_variant = 3): same data path as unpack_tma_kernel, but a
 // warp copies out the 32 rows its own lanes wrote (two adjacent rows = 512 contiguous bytes per
 // store instruction), so the two CTA barriers around the copy-out become __syncwarp, and the plane
@@ -760,6 +929,16 @@ UnpackFn unpack_bulk_table_entry(int bw, Seq<I...>) {
 }
 typedef void (*UnpackNarrowFn)(const uint64_t*, int64_t, int64_t, uint8_t*);
 template <int... I>
+UnpackNarrowFn unpack_u8_warp_table_entry(int bw, Seq<I...>) {
+  static const UnpackNarrowFn tab[] = {unpack_narrow_warp_kernel<I, 1>...};
+  return tab[bw - 1];
+}
+template <int... I>
+UnpackNarrowFn unpack_u16_warp_table_entry(int bw, Seq<I...>) {
+  static const UnpackNarrowFn tab[] = {unpack_narrow_warp_kernel<I, 2>...};
+  return tab[bw - 1];
+}
+template <int... I>
 UnpackNarrowFn unpack_u8_table_entry(int bw, Seq<I...>) {
   static const UnpackNarrowFn tab[] = {unpack_narrow_kernel<I, 1>...};
   return tab[bw - 1];
@@ -875,13 +1054,20 @@ int launch_unpack_narrow(fle_ctx* ctx, const uint64_t* enc_dev, int bw, int64_t 
   if (bw < 1 || bw > 8 * elem_size) return set_error(ctx, FLE_E_INVALID, "bit width does not fit the output element");
   if (n == 0) return FLE_OK;
   const int64_t G = (n + 63) / 64;
-  UnpackNarrowFn fn = elem_size == 1 ? unpack_u8_table_entry(bw, MakeSeq<8>::type()) : unpack_u16_table_entry(bw, MakeSeq<16>::type());
+  // codec_variant 4: the first form (CTA-wide copy-out between two barriers); anything else: warp-private copy-out.
+  // Both want 16-byte aligned pointers (TMA source, 128-bit stores).
+  if (((reinterpret_cast<uintptr_t>(enc_dev) | reinterpret_cast<uintptr_t>(out_dev)) & 15) != 0)
+    return set_error(ctx, FLE_E_ALIGN, "narrow unpack wants 16-byte aligned buffers");
+  const bool warp_form = ctx->codec_variant != 4;
+  UnpackNarrowFn fn;
+  if (warp_form) fn = elem_size == 1 ? unpack_u8_warp_table_entry(bw, MakeSeq<8>::type()) : unpack_u16_warp_table_entry(bw, MakeSeq<16>::type());
+  else fn = elem_size == 1 ? unpack_u8_table_entry(bw, MakeSeq<8>::type()) : unpack_u16_table_entry(bw, MakeSeq<16>::type());
   const size_t stage = (plane_tile_bytes(bw, MakeSeq<32>::type()) + 127) / 128 * 128;
-  const size_t smem = (size_t)kCodecThreads * 64 * elem_size + 2 * stage + 64;
+  const size_t smem = (size_t)kCodecThreads * 64 * elem_size + (warp_form ? 3 : 2) * stage + 64;
   int rc = raise_smem_limit(ctx, (const void*)fn, smem);
   if (rc != FLE_OK) return rc;
   int per_sm = std::max<int>(1, std::min<int>(8, (int)((size_t)ctx->max_smem_per_sm / (smem + 1024))));
-  per_sm = std::min(per_sm, ctx->codec_ctas_per_sm > 0 ? ctx->codec_ctas_per_sm : 4);
+  per_sm = std::min(per_sm, ctx->codec_ctas_per_sm > 0 ? ctx->codec_ctas_per_sm : (warp_form ? 6 : 4));
   const int64_t ntiles = (G + kCodecThreads - 1) / kCodecThreads;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)ctx->num_sms * per_sm));
   fn<<<grid, kCodecThreads, smem, ctx->stream>>>(enc_dev, G, n, static_cast<uint8_t*>(out_dev));

@@ -201,6 +201,33 @@ __device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, u
                "r"(d)
                : "memory");
 }
+// (a & ~M) | (b & M) as ONE LOP3 (written in C the compiler spends a LOP3 per constant, M and ~M)
+template <uint32_t M>
+__device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(r) : "r"(a), "r"(b), "n"(M));
+  return r;
+}
+// 8 x 8 bit transposes of the four byte lanes of S[0..7] at once (three butterfly stages, 12 instructions per
+// stage):  S'[w] byte b, bit j == S[7 - j] byte b, bit 7 - w.  With plane i's 32-row half (row r at bit 31 - r)
+// in S[7 - i]:  S'[w] byte b = low 8 code bits of the half's row 24 - 8 b + w.
+template <int J, uint32_t M>
+__device__ __forceinline__ void swar8_stage(uint32_t (&S)[8]) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if ((k & J) == 0) {
+      const uint32_t a = S[k], b = S[k + J];
+      S[k] = bitsel<M>(a, b >> J);
+      S[k + J] = bitsel<M>(a << J, b);
+    }
+  }
+}
+__device__ __forceinline__ void swar8_transpose(uint32_t (&S)[8]) {
+  swar8_stage<4, 0x0F0F0F0Fu>(S);
+  swar8_stage<2, 0x33333333u>(S);
+  swar8_stage<1, 0x55555555u>(S);
+}
+
 // streaming (read-once) global loads/stores: keep L1 clean
 __device__ __forceinline__ uint64_t ldg_stream64(const uint64_t* p) {
   uint64_t v;

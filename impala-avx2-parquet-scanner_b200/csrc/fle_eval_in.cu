@@ -61,13 +61,6 @@ struct InTable {
   FLE_HD static constexpr int pos(int i) { return (kPerLane && i >= 5) ? i + (kShift - 5) : i; }
 };
 
-// (a & ~M) | (b & M) as ONE LOP3 (written in C the compiler spends a LOP3 per constant, M and ~M)
-template <uint32_t M>
-__device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b) {
-  uint32_t r;
-  asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(r) : "r"(a), "r"(b), "n"(M));
-  return r;
-}
 
 template <int J, uint32_t M>
 __device__ __forceinline__ void in_stage(uint32_t (&S)[16]) {
@@ -453,24 +446,8 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
   return v;
 }
 
-template <int J, uint32_t M>
-__device__ __forceinline__ void in_stage8(uint32_t (&S)[8]) {
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    if ((k & J) == 0) {
-      const uint32_t a = S[k], b = S[k + J];
-      S[k] = bitsel<M>(a, b >> J);
-      S[k + J] = bitsel<M>(a << J, b);
-    }
-  }
-}
-// 8 x 8 bit transposes of the four byte lanes of S[0..7] at once:  S'[w] byte b, bit j == S[7 - j] byte b, bit 7 - w.
-// With plane i's 32-row half in S[7 - i]:  S'[w] byte b = low code byte of the half's row 24 - 8 b + w.
-__device__ __forceinline__ void in_transpose8(uint32_t (&S)[8]) {
-  in_stage8<4, 0x0F0F0F0Fu>(S);
-  in_stage8<2, 0x33333333u>(S);
-  in_stage8<1, 0x55555555u>(S);
-}
+// (the 8 x 8 SWAR transpose, swar8_transpose, lives in fle_device.cuh: the narrow unpack kernels use it too)
+__device__ __forceinline__ void in_transpose8(uint32_t (&S)[8]) { swar8_transpose(S); }
 
 template <int BW>
 struct InWord {

@@ -721,12 +721,17 @@ def test_unpack_narrow_targets(ctx, oracle, bw):
         vals = rng.integers(0, 1 << bw, size=n, dtype=np.uint64).astype(np.uint32)
         words = torch.from_numpy(oracle.pack(vals, bw).view(np.int64)).cuda()
         for es in ((1, 2) if bw <= 8 else (2,)):
-            out = torch.full((n + 32,), -1, dtype=torch.uint8 if es == 1 else torch.int16, device="cuda")
-            ctx.unpack_narrow_dev(words, bw, 0, n, out=out[:n])
-            torch.cuda.synchronize()
-            got = out.cpu().numpy()
-            assert (got[:n].astype(np.uint16 if es == 2 else np.uint8) == vals).all(), (bw, n, es)
-            assert (got[n:] == -1 if es == 2 else got[n:] == 255).all(), "wrote past the end"
+            for variant in (1, 4):  # warp-private copy-out (default), CTA-wide copy-out
+                out = torch.full((n + 32,), -1, dtype=torch.uint8 if es == 1 else torch.int16, device="cuda")
+                ctx.set_option("codec_variant", variant)
+                try:
+                    ctx.unpack_narrow_dev(words, bw, 0, n, out=out[:n])
+                    torch.cuda.synchronize()
+                finally:
+                    ctx.set_option("codec_variant", 1)
+                got = out.cpu().numpy()
+                assert (got[:n].astype(np.uint16 if es == 2 else np.uint8) == vals).all(), (bw, n, es, variant)
+                assert (got[n:] == -1 if es == 2 else got[n:] == 255).all(), "wrote past the end"
         if n > 64 * 130:
             first = 64 * 128
             out = ctx.unpack_narrow_dev(words, bw, first, n - first)

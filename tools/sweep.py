@@ -211,6 +211,11 @@ def sweep_programs(ctx, out, n):
     mn, md = timeit(lambda: ctx.eval_dev(pc, prog, n, bitmap=bm, count=cnt, prepared=prep), working_set=G * 25 * 8)
     rec(out, what="program", name="q6_optional_cols_no_nulls", variant="1j", rows=n, sum_bw=25, ms_min=mn, ms_med=md,
         alg_bytes=G * 25 * 8 + G * 8, rows_per_s=n / (mn * 1e-3), count=int(cnt.item()))
+    # ... and through fle_eval_no_nulls_dev: the same two kernels, the NULL count stays on the device (no host sync)
+    o2 = torch.zeros(2, dtype=torch.int64, device="cuda")
+    mn, md = timeit(lambda: ctx.eval_no_nulls_dev(pc, prog, n, bitmap=bm, out=o2, prepared=prep), working_set=G * 25 * 8)
+    rec(out, what="program", name="q6_optional_cols_no_nulls_async", variant="1j", rows=n, sum_bw=25, ms_min=mn, ms_med=md,
+        alg_bytes=G * 25 * 8 + G * 8, rows_per_s=n / (mn * 1e-3), count=int(o2[0].item()), null_rows=int(o2[1].item()))
 
 
 def sweep_tune(ctx, out, n):
