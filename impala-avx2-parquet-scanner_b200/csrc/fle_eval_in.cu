@@ -413,17 +413,19 @@ struct InWideDecode {
 // that drops the entry at the row's bit position of the result word (acc += entry * 2^row): the selection
 // word is assembled directly in row order, no epilogue.
 //
-//   bw <= 10  (InWordDecode): the low 8 planes go through 8 x 8 SWAR transposes (3 stages on 8 words per 32
+//   bw <= 11  (InWordDecode): the low 8 planes go through 8 x 8 SWAR transposes (3 stages on 8 words per 32
 //             rows: 96 instructions per group instead of 224); a transposed byte is the row's low code byte,
 //             and ONE PRMT builds  offset = code << 8 | lane << 2  from it and the lane constant.  Entries are
-//             32-bit words; planes 8 and 9 stay bit-sliced: an entry carries the answers for all their values
-//             (2 x 16 bits or 4 x 8 bits apart), the IMADs sort them into per-case row words and the untouched
-//             planes select among those bitwise (1 / 3 LOP3 per 32 rows).
-//   bw 11, 12 (InByteDecode): the 16 x 16 butterflies above, with the five LANE bits fed in as constant planes
+//             32-bit words; planes 8, 9 and 10 stay bit-sliced: an entry carries the answers for all their values
+//             (2 x 16 bits or 4 x 8 bits apart, or 8 bits side by side), the IMADs sort them into per-case row
+//             words and the untouched planes select among those bitwise (1 / 3 LOP3 per 32 rows; for three planes
+//             a second 8 x 8 SWAR transpose sorts the answers, select8).
+//   bw 12     (InByteDecode): the 16 x 16 butterflies above, with the five LANE bits fed in as constant planes
 //             (all-ones or all-zeros words per thread) at the positions the table layout wants them, so a
 //             transposed half is  code[10:2] << 7 | lane << 2 | code[1:0]  = the offset of a BYTE entry in a
-//             lane-private 64 KB table; bw 12 keeps plane 11 bit-sliced (answers in bits 0 and 4 of the byte,
+//             lane-private 64 KB table; plane 11 stays bit-sliced (answers in bits 0 and 4 of the byte,
 //             rows dropped four to a byte, nibble select).
+//   bw 13..16 (InByte3Decode): the same, three planes bit-sliced (eight answers per entry byte, select8).
 // Set membership of the same codes, so bit-identical to the OR of equalities by construction.
 // ------------------------------------------------------------------------------------------
 constexpr uint32_t kInTableOff = 64;  // the table's offset in dynamic shared memory (launch_program: right behind the mbarriers)
@@ -449,18 +451,29 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
 // (the 8 x 8 SWAR transpose, swar8_transpose, lives in fle_device.cuh: the narrow unpack kernels use it too)
 __device__ __forceinline__ void in_transpose8(uint32_t (&S)[8]) { swar8_transpose(S); }
 
+// Eight answers per entry (three planes kept bit-sliced): bit c of a row's entry byte answers for value c of those
+// planes.  The entries of a 32-row half are dropped byte-wise into eight words, E[k] byte b = entry of row
+// 8 b + 7 - k, which is exactly the input the 8 x 8 SWAR transpose wants: afterwards E[7 - c] is the row-order
+// word of answers for value c, and the three untouched planes pick among the eight words bitwise (7 LOP3).
+__device__ __forceinline__ uint32_t select8(uint32_t (&E)[8], uint32_t x0, uint32_t x1, uint32_t x2) {
+  swar8_transpose(E);
+  const uint32_t a = bitsel_r(bitsel_r(E[7], E[6], x0), bitsel_r(E[5], E[4], x0), x1);
+  const uint32_t b = bitsel_r(bitsel_r(E[3], E[2], x0), bitsel_r(E[1], E[0], x0), x1);
+  return bitsel_r(a, b, x2);
+}
+
 template <int BW>
 struct InWord {
   static constexpr int kTB = BW < 8 ? BW : 8;  // transposed code bits
-  static constexpr int kNX = BW - kTB;         // planes kept bit-sliced (0, 1 or 2)
+  static constexpr int kNX = BW - kTB;         // planes kept bit-sliced (0 .. 3)
   static constexpr uint32_t kTableBytes = (1u << kTB) * 256u;  // entry of code e, lane l at e * 256 + l * 4
-  static constexpr int kCaseBits = kNX == 0 ? 32 : (kNX == 1 ? 16 : 8);  // distance between the answers inside an entry
+  static constexpr int kCaseBits = kNX == 0 ? 32 : (kNX == 1 ? 16 : (kNX == 2 ? 8 : 1));  // distance between the answers inside an entry
 };
 
 template <int BW>
 struct InWordDecode {
   using IW = InWord<BW>;
-  static_assert(IW::kNX <= 2, "bw <= 10");
+  static_assert(IW::kNX <= 3, "bw <= 11");
   uint32_t table;  // shared address of the table
   uint32_t lane4;  // lane * 4: byte 0 of every entry offset
 
@@ -531,8 +544,24 @@ struct InWordDecode {
   }
 
   // 32 rows of one half -> selection word in row order
-  __device__ __forceinline__ uint32_t half(const uint32_t (&S)[8], const uint32_t (&x)[2]) const {
-    if constexpr (IW::kNX == 0) {
+  // E[k] byte b = entry of row 8 b + 7 - k (select8)
+  template <int K>
+  __device__ __forceinline__ void drop_bytes(const uint32_t (&S)[8], uint32_t (&E)[8]) const {
+    if constexpr (K < 8) {
+      uint32_t acc = entry<7 - K>(S);
+      acc = drop_at<(1u << 8)>(acc, entry<8 + 7 - K>(S));
+      acc = drop_at<(1u << 16)>(acc, entry<16 + 7 - K>(S));
+      E[K] = drop_at<(1u << 24)>(acc, entry<24 + 7 - K>(S));
+      drop_bytes<K + 1>(S, E);
+    }
+  }
+
+  __device__ __forceinline__ uint32_t half(const uint32_t (&S)[8], const uint32_t (&x)[3]) const {
+    if constexpr (IW::kNX == 3) {
+      uint32_t E[8];
+      drop_bytes<0>(S, E);
+      return select8(E, x[0], x[1], x[2]);
+    } else if constexpr (IW::kNX == 0) {
       return rows<0, 32>(S);
     } else if constexpr (IW::kNX == 1) {
       // an accumulator takes 16 rows: answers for plane 8 = 0 in its low half, for plane 8 = 1 in its high half
@@ -554,7 +583,7 @@ struct InWordDecode {
   __device__ __forceinline__ uint64_t compute(Planes& pl) const {
     in_transpose8(pl.S0);
     in_transpose8(pl.S1);
-    uint32_t xlo[2] = {0u, 0u}, xhi[2] = {0u, 0u};
+    uint32_t xlo[3] = {0u, 0u, 0u}, xhi[3] = {0u, 0u, 0u};
 #pragma unroll
     for (int i = 0; i < IW::kNX; ++i) {
       const uint64_t xr = __brevll(pl.X[i]);  // plane order (row k at bit 63 - k) -> row order
@@ -717,6 +746,123 @@ struct WideBitsPolicy {  // bw 13..16: bit table, 32 / 16 / 8 copies
   }
 };
 
+// bw 13..16: byte entries with EIGHT answers (the top three planes stay bit-sliced, select8), the other bw - 3 code bits
+// and the copy number go through the 16 x 16 butterflies as in InByteDecode.  A half has room for 16 - (bw - 3) copy
+// bits: 32 lane-private copies up to bw 14, 16 / 8 copies for bw 15 / 16 (two / four lanes share a copy: 1.5 / 2.1
+// wavefronts per lookup); 64 KB at most.  Against the replicated bit table (InDecode<BW, true>: mask, add, load,
+// variable shift, funnel append = 5.5 instructions per row, 650 per group, ALU pipe 440) a row costs extract, load,
+// IMAD, plus 110 per group for the select: 575 per group, ALU pipe 365.
+template <int BW>
+struct InByte3 {
+  static constexpr int kTB = BW - 3;
+  static constexpr int kCB = (16 - kTB) < 5 ? (16 - kTB) : 5;  // copy bits
+  static constexpr uint32_t kCopies = 1u << kCB;
+  static constexpr uint32_t kTableBytes = (1u << kTB) * kCopies;  // entry e, copy c at ((e >> 2) * copies + c) * 4 + (e & 3)
+  FLE_HD static constexpr int pos(int i) { return i < 2 ? i : i + kCB; }
+  FLE_HD static constexpr int copy_pos(int j) { return 2 + j; }
+};
+
+template <int BW>
+struct InByte3Decode {
+  using IB = InByte3<BW>;
+  static_assert(BW >= 13 && BW <= 16, "bw 13..16");
+  uint32_t table;
+  uint32_t copy_plane[IB::kCB];  // copy-number bit j (= lane bit j) as a constant plane
+
+  __device__ __forceinline__ void init(uint32_t table_addr, uint32_t lane) {
+    table = table_addr;
+#pragma unroll
+    for (int j = 0; j < IB::kCB; ++j) copy_plane[j] = 0u - ((lane >> j) & 1u);
+  }
+
+  struct Planes {
+    uint32_t S0[16], S1[16];
+    uint64_t X[3];
+  };
+
+  template <class L>
+  __device__ __forceinline__ uint64_t run(const L& ld) const {
+    Planes pl;
+    load(ld, pl);
+    return compute(pl);
+  }
+
+  template <class L>
+  __device__ __forceinline__ void load(const L& ld, Planes& pl) const {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) pl.S0[j] = pl.S1[j] = 0u;
+#pragma unroll
+    for (int j = 0; j < IB::kCB; ++j) pl.S0[15 - IB::copy_pos(j)] = pl.S1[15 - IB::copy_pos(j)] = copy_plane[j];
+#pragma unroll
+    for (int i = 0; i < BW; i += 2) {
+      uint64_t a, b;
+      ld.template load_pair<BW>(i, a, b);
+      if (i < IB::kTB) {
+        pl.S0[15 - IB::pos(i < IB::kTB ? i : 0)] = (uint32_t)(a >> 32);
+        pl.S1[15 - IB::pos(i < IB::kTB ? i : 0)] = (uint32_t)a;
+      } else {
+        pl.X[i >= IB::kTB ? i - IB::kTB : 0] = a;
+      }
+      if (i + 1 < BW) {
+        if (i + 1 < IB::kTB) {
+          pl.S0[15 - IB::pos(i + 1 < IB::kTB ? i + 1 : 0)] = (uint32_t)(b >> 32);
+          pl.S1[15 - IB::pos(i + 1 < IB::kTB ? i + 1 : 0)] = (uint32_t)b;
+        } else {
+          pl.X[i + 1 >= IB::kTB ? i + 1 - IB::kTB : 0] = b;
+        }
+      }
+    }
+  }
+
+  // after in_transpose: S[k] = offset(row k) << 16 | offset(row 16 + k)
+  template <int R>
+  __device__ __forceinline__ uint32_t entry(const uint32_t (&S)[16]) const {
+    const uint32_t w = S[R % 16];
+    return lds_u8(table + (R < 16 ? (w >> 16) : (w & 0xFFFFu)));
+  }
+  template <int K>
+  __device__ __forceinline__ void drop_bytes(const uint32_t (&S)[16], uint32_t (&E)[8]) const {
+    if constexpr (K < 8) {
+      uint32_t acc = entry<7 - K>(S);
+      acc = drop_at<(1u << 8)>(acc, entry<8 + 7 - K>(S));
+      acc = drop_at<(1u << 16)>(acc, entry<16 + 7 - K>(S));
+      E[K] = drop_at<(1u << 24)>(acc, entry<24 + 7 - K>(S));
+      drop_bytes<K + 1>(S, E);
+    }
+  }
+
+  __device__ __forceinline__ uint64_t compute(Planes& pl) const {
+    in_transpose(pl.S0);
+    in_transpose(pl.S1);
+    uint32_t xlo[3], xhi[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const uint64_t xr = __brevll(pl.X[i]);  // plane order (row k at bit 63 - k) -> row order
+      xlo[i] = (uint32_t)xr;
+      xhi[i] = (uint32_t)(xr >> 32);
+    }
+    uint32_t E[8];
+    drop_bytes<0>(pl.S0, E);
+    const uint32_t lo = select8(E, xlo[0], xlo[1], xlo[2]);
+    drop_bytes<0>(pl.S1, E);
+    const uint32_t hi = select8(E, xhi[0], xhi[1], xhi[2]);
+    return ((uint64_t)hi << 32) | (uint64_t)lo;
+  }
+};
+
+template <int BW>
+struct WideByte3Policy {  // in_wide = 2, bw 13..16
+  using Decode = InByte3Decode<BW>;
+  using IB = InByte3<BW>;
+  static constexpr uint32_t kTableBytes = IB::kTableBytes;
+  static constexpr uint32_t kCopies = 1;  // (the decoder adds the copy number itself)
+  static constexpr uint32_t kItemsPerLit = IB::kCopies;
+  __device__ static __forceinline__ void put(uint32_t* table, uint32_t c, uint32_t copy) {
+    const uint32_t e = c & ((1u << IB::kTB) - 1u), x = c >> IB::kTB;
+    atomicOr(&table[(e >> 2) * IB::kCopies + copy], 1u << ((e & 3u) * 8u + x));
+  }
+};
+
 template <int BW>
 struct WideWordPolicy {  // in_wide = 2, bw <= 10: 32-bit entries addressed by one PRMT
   using Decode = InWordDecode<BW>;
@@ -844,7 +990,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, 1) eval_in_wide_kernel(const __
 // two groups per thread amortise the tile loop's fixed instructions where the registers allow it (bw 8-10: +1-2 %),
 // 24 warps hide more latency where they do not (bw 7, 12); 31 warps: unstable between runs (+3 % / -8 %).
 void eval_in_wide_shape(int bw, int* ncw, int* gpt) {
-  *ncw = (bw == 7 || bw == 12) ? 24 : 16;
+  *ncw = (bw == 7 || bw == 11 || bw == 12) ? 24 : 16;  // (bw 13..16: the 64 KB table leaves room for 16-warp tiles only)
   *gpt = (bw >= 8 && bw <= 10) ? 2 : 1;
 }
 
@@ -852,8 +998,9 @@ const void* eval_in_wide_kernel_for(int bw, int form, int ncw, int gpt) {
   if (form >= 2) {
 #define V(B, POL, W, Q) if (bw == B && ncw == W && gpt == Q) return (const void*)eval_in_wide_kernel<B, POL<B>, W, Q>;
 #define VS(B, POL) V(B, POL, 16, 1) V(B, POL, 16, 2) V(B, POL, 24, 1)
-    VS(7, WideWordPolicy) VS(8, WideWordPolicy) VS(9, WideWordPolicy) VS(10, WideWordPolicy)
-    VS(11, WideBytePolicy) VS(12, WideBytePolicy)
+    VS(7, WideWordPolicy) VS(8, WideWordPolicy) VS(9, WideWordPolicy) VS(10, WideWordPolicy) VS(11, WideWordPolicy)
+    VS(12, WideBytePolicy)
+    VS(13, WideByte3Policy) VS(14, WideByte3Policy) VS(15, WideByte3Policy) VS(16, WideByte3Policy)
 #undef VS
 #undef V
     if (ncw != 16 || gpt != 1) return nullptr;
@@ -876,8 +1023,9 @@ const void* eval_in_wide_kernel_for(int bw, int form, int ncw, int gpt) {
 }
 
 uint32_t eval_in_wide_table_bytes(int bw, int form) {
-  if (form >= 2 && bw <= 10) return (1u << std::min(bw, 8)) * 256u;          // InWord<bw>::kTableBytes
-  if (form >= 2 && bw <= 12) return bw <= 2 ? 128u : (1u << (std::min(bw, 11) - 2)) * 128u;  // InByte<bw>::kTableBytes
+  if (form >= 2 && bw <= 11) return (1u << std::min(bw, 8)) * 256u;          // InWord<bw>::kTableBytes
+  if (form >= 2 && bw == 12) return (1u << 9) * 128u;                         // InByte<12>::kTableBytes
+  if (form >= 2 && bw <= 16) return (1u << (bw - 3)) * (1u << std::min(16 - (bw - 3), 5));  // InByte3<bw>::kTableBytes
   if (bw > 12) return (4u << (bw - 5)) * (bw <= 14 ? 32u : (bw == 15 ? 16u : 8u));  // InTable<bw, true>::kTableBytes
   const int tb = bw < 11 ? bw : 11;
   return (uint32_t)std::max(2, 1 << tb) * 64u;
