@@ -113,6 +113,22 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 // When no column actually contains a NULL the deposit is the identity and the columns are
 // evaluated by the fused kernel as if they were required.
 // ------------------------------------------------------------------------------------------
+// grow-only scratch of the NULL path (no stream-ordered allocations per call); returns the base or nullptr
+static uint8_t* null_scratch(fle_ctx* ctx, size_t bytes) {
+  if (ctx->null_cap < bytes) {
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return nullptr;
+    if (ctx->d_null) cudaFree(ctx->d_null);
+    ctx->d_null = nullptr;
+    ctx->null_cap = 0;
+    if (cudaMalloc(&ctx->d_null, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    ctx->null_cap = bytes;
+  }
+  return static_cast<uint8_t*>(ctx->d_null);
+}
+
 static int eval_dev_nullable(fle_ctx* ctx, const fle_col_desc* cols, int ncols,
                              const fle_pred_node* nodes, int nnodes, int64_t first_row, int64_t n,
                              uint64_t* bitmap_dev, uint64_t* count_dev) {
@@ -123,20 +139,15 @@ static int eval_dev_nullable(fle_ctx* ctx, const fle_col_desc* cols, int ncols,
     if (count_dev) FLE_CUDA_TRY(ctx, cudaMemsetAsync(count_dev, 0, 8, ctx->stream));
     return FLE_OK;
   }
+  for (int c = 0; c < ncols; ++c)
+    if (cols[c].max_def_level > 1) return set_error(ctx, FLE_E_UNSUPPORTED, "max_def_level > 1 (nested types)");
   // 1. non-null rows per column (one launch, nothing written) ...
-  std::vector<uint64_t*> notnull(ncols, nullptr);
-  std::vector<uint64_t*> tmp;  // everything to free
-  uint64_t* d_counts = nullptr;
-  FLE_CUDA_TRY(ctx, cudaMallocAsync(&d_counts, (size_t)FLE_MAX_COLS * 8, ctx->stream));
-  tmp.push_back(d_counts);
-  auto cleanup = [&]() {
-    for (uint64_t* p : tmp) cudaFreeAsync(p, ctx->stream);
-  };
-  int rc = FLE_OK;
-  for (int c = 0; c < ncols && rc == FLE_OK; ++c)
-    if (cols[c].max_def_level > 1) rc = set_error(ctx, FLE_E_UNSUPPORTED, "max_def_level > 1 (nested types)");
-  if (rc == FLE_OK) rc = launch_def_counts(ctx, cols, ncols, n, d_counts);
-  if (rc != FLE_OK) { cleanup(); return rc; }
+  constexpr size_t kCountsBytes = 256;
+  uint8_t* scratch = null_scratch(ctx, kCountsBytes);
+  if (!scratch) return set_error(ctx, FLE_E_NOMEM, "scratch of the NULL path");
+  uint64_t* d_counts = reinterpret_cast<uint64_t*>(scratch);
+  int rc = launch_def_counts(ctx, cols, ncols, n, d_counts);
+  if (rc != FLE_OK) return rc;
   // 2a. ... and, without waiting for them, the fused kernel over the columns as if they were
   // required: with no NULL anywhere (TPC-H; Impala's writer marks every column OPTIONAL) the data
   // ordinal IS the row index and this is the answer.  (Skipped when a data stream is too short to
@@ -146,50 +157,40 @@ static int eval_dev_nullable(fle_ctx* ctx, const fle_col_desc* cols, int ncols,
   bool optimistic = true;
   for (int c = 0; c < ncols; ++c)
     if (cols[c].bytes < (uint64_t)nwords * (uint64_t)cols[c].bit_width * 8u) optimistic = false;
-  if (optimistic) {
+  // (a context whose previous nullable call DID find NULLs -- a file that has them usually has them in every row
+  //  group -- waits for the counts first instead of launching a scan it would throw away)
+  const bool launch_first = optimistic && !ctx->nulls_seen;
+  if (launch_first) {
     rc = launch_eval(ctx, req.data(), ncols, nodes, nnodes, 0, n, bitmap_dev, count_dev);
-    if (rc != FLE_OK) { cleanup(); return rc; }
+    if (rc != FLE_OK) return rc;
   }
   std::vector<uint64_t> h_counts(ncols, 0);
-  {
-    cudaError_t e = cudaMemcpyAsync(h_counts.data(), d_counts, (size_t)ncols * 8, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) { cleanup(); return set_cuda_error(ctx, e, "def-level counts"); }
-  }
+  FLE_CUDA_TRY(ctx, cudaMemcpyAsync(h_counts.data(), d_counts, (size_t)ncols * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  FLE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   bool any_null = false;
   for (int c = 0; c < ncols; ++c)
     if (cols[c].max_def_level != 0 && (int64_t)h_counts[c] != n) any_null = true;
+  ctx->nulls_seen = any_null;
   if (!any_null) {
-    if (!optimistic) rc = set_error(ctx, FLE_E_BUFFER, "column shorter than the rows requested");
-    cleanup();
-    return rc;
+    if (!optimistic) return set_error(ctx, FLE_E_BUFFER, "column shorter than the rows requested");
+    if (!launch_first) return launch_eval(ctx, req.data(), ncols, nodes, nnodes, 0, n, bitmap_dev, count_dev);
+    return FLE_OK;
   }
-  // NULLs present: not-null bitmaps of the nullable columns (def level == max_def_level)
-  for (int c = 0; c < ncols && rc == FLE_OK; ++c) {
-    if (cols[c].max_def_level == 0) continue;
-    cudaError_t e = cudaMallocAsync(&notnull[c], (size_t)nwords * 8, ctx->stream);
-    if (e != cudaSuccess) { rc = set_cuda_error(ctx, e, "cudaMallocAsync(notnull)"); break; }
-    tmp.push_back(notnull[c]);
-    fle_col_desc dc{cols[c].def_planes, cols[c].def_bytes, 1, 0, nullptr, 0};
-    fle_pred_node leaf{FLE_OP_EQ, 0, (uint64_t)cols[c].max_def_level, nullptr, 0, 0};
-    rc = launch_eval(ctx, &dc, 1, &leaf, 1, 0, n, notnull[c], nullptr);
-  }
-  if (rc != FLE_OK) { cleanup(); return rc; }
 
-  // 2b. general case.  A NULL row yields 0 in every leaf, and the deposit through the not-null
+  // 2b. NULLs present.  A NULL row yields 0 in every leaf, and the deposit through the not-null
   // bitmap (IntersectBitset) is a bit-wise injection, so it distributes over AND and OR:
   // deposit(a) op deposit(b) == deposit(a op b).  Every maximal subtree whose leaves sit on ONE
   // nullable column is therefore evaluated as one fused program in the data-ordinal domain and
-  // deposited once; every maximal subtree over required columns only is one fused program over
-  // the rows; the remaining (mixed) operators combine those bitmaps word by word.
+  // deposited once -- straight from the column's def-level planes (launch_deposit: no not-null bitmap is
+  // built); every maximal subtree over required columns only is one fused program over the rows.
   constexpr int kReq = -1, kMixed = -2;
   std::vector<int> node_start(nnodes, 0), node_cls(nnodes, kMixed);
   {
     std::vector<int> stack;  // node index of the subtree roots
-    for (int i = 0; i < nnodes && rc == FLE_OK; ++i) {
+    for (int i = 0; i < nnodes; ++i) {
       const fle_pred_node& nd = nodes[i];
       if (nd.op == FLE_OP_AND || nd.op == FLE_OP_OR) {
-        if (stack.size() < 2) { rc = set_error(ctx, FLE_E_INVALID, "malformed postfix program"); break; }
+        if (stack.size() < 2) return set_error(ctx, FLE_E_INVALID, "malformed postfix program");
         const int rb = stack.back(); stack.pop_back();
         const int ra = stack.back(); stack.pop_back();
         node_start[i] = node_start[ra];
@@ -197,16 +198,15 @@ static int eval_dev_nullable(fle_ctx* ctx, const fle_col_desc* cols, int ncols,
       } else {
         const bool is_const = nd.op == FLE_OP_ALL || nd.op == FLE_OP_NONE;
         const bool in_range = nd.col >= 0 && nd.col < ncols;
-        if (!is_const && !in_range) { rc = set_error(ctx, FLE_E_INVALID, "leaf column out of range"); break; }
+        if (!is_const && !in_range) return set_error(ctx, FLE_E_INVALID, "leaf column out of range");
         const bool nullable = in_range && cols[nd.col].max_def_level != 0;
         node_start[i] = i;
         node_cls[i] = nullable ? nd.col : (is_const ? kMixed : kReq);  // a constant without a nullable column stays a constant
       }
       stack.push_back(i);
     }
-    if (rc == FLE_OK && stack.size() != 1) rc = set_error(ctx, FLE_E_INVALID, "malformed postfix program");
+    if (stack.size() != 1) return set_error(ctx, FLE_E_INVALID, "malformed postfix program");
   }
-  if (rc != FLE_OK) { cleanup(); return rc; }
   // maximal single-class subtrees, found from the root downwards ([node_start, i] is contiguous in postfix)
   std::vector<std::pair<int, int> > subs;  // [start, end]
   for (int i = nnodes - 1; i >= 0;) {
@@ -218,16 +218,94 @@ static int eval_dev_nullable(fle_ctx* ctx, const fle_col_desc* cols, int ncols,
     }
   }
   std::sort(subs.begin(), subs.end());
+  // what joins the subtrees: ONE operator throughout (a conjunct chain: the usual case) lets every subtree fold
+  // into the output bitmap as it is produced; mixed operators (or constants) take leaf bitmaps + a combine pass
+  int join_op = 0, nreq = 0;
+  bool uniform = true;
+  {
+    size_t si = 0;
+    for (int i = 0; i < nnodes; ++i) {
+      if (si < subs.size() && i >= subs[si].first) {
+        if (node_cls[subs[si].second] == kReq) ++nreq;
+        i = subs[si].second;
+        ++si;
+        continue;
+      }
+      const int op = nodes[i].op;
+      if (op != FLE_OP_AND && op != FLE_OP_OR) { uniform = false; continue; }  // a constant leaf
+      if (join_op == 0) join_op = op;
+      else if (join_op != op) uniform = false;
+    }
+  }
+  const bool fold = uniform && nreq <= 1 && bitmap_dev != nullptr;
+  const size_t word_bytes = ((size_t)nwords * 8 + 255) / 256 * 256;
+  const size_t need = kCountsBytes + word_bytes * (fold ? 1 : subs.size() + 1);
+  scratch = null_scratch(ctx, need);
+  if (!scratch) return set_error(ctx, FLE_E_NOMEM, "scratch of the NULL path");
+  uint64_t* db = reinterpret_cast<uint64_t*>(scratch + kCountsBytes);  // data-domain bitmap of the subtree in flight (stream-ordered reuse)
+  size_t bump = kCountsBytes + word_bytes;
+
+  // the data-domain bitmap of a subtree on nullable column cls: false = the subtree is empty (no value, or NONE)
+  auto data_bitmap = [&](std::vector<fle_pred_node>& sub, int cls, int64_t* m_out) -> int {
+    const fle_col_desc& col = cols[cls];
+    const int64_t m = (int64_t)h_counts[cls];  // non-null values = rows of the data stream
+    *m_out = m;
+    const bool single = sub.size() == 1;
+    if (m == 0 || (single && sub[0].op == FLE_OP_NONE)) {
+      *m_out = 0;
+      return FLE_OK;
+    }
+    if (single && sub[0].op == FLE_OP_ALL) {
+      cudaError_t e = cudaMemsetAsync(db, 0xFF, (size_t)((m + 63) / 64) * 8, ctx->stream);
+      return e == cudaSuccess ? (int)FLE_OK : set_cuda_error(ctx, e, "cudaMemsetAsync(data bitmap)");
+    }
+    fle_col_desc dc{col.planes, col.bytes, col.bit_width, 0, nullptr, 0};
+    for (auto& nd : sub)
+      if (nd.op != FLE_OP_AND && nd.op != FLE_OP_OR) nd.col = 0;
+    return launch_eval(ctx, &dc, 1, sub.data(), (int)sub.size(), 0, m, db, nullptr);
+  };
+  auto eval_required = [&](std::vector<fle_pred_node>& sub, uint64_t* out, uint64_t* cnt) -> int {
+    std::vector<int> map(ncols, -1);  // remap the columns the subtree uses to 0..k-1
+    std::vector<fle_col_desc> dc;
+    for (auto& nd : sub) {
+      if (nd.op == FLE_OP_AND || nd.op == FLE_OP_OR) continue;
+      if (map[nd.col] < 0) { map[nd.col] = (int)dc.size(); dc.push_back(cols[nd.col]); }
+      nd.col = map[nd.col];
+    }
+    return launch_eval(ctx, dc.data(), (int)dc.size(), sub.data(), (int)sub.size(), 0, n, out, cnt);
+  };
+
+  if (fold) {
+    // the required subtree (if any) sets the output, every nullable subtree folds its deposit into it
+    std::vector<size_t> order;
+    for (size_t k = 0; k < subs.size(); ++k)
+      if (node_cls[subs[k].second] == kReq) order.push_back(k);
+    for (size_t k = 0; k < subs.size(); ++k)
+      if (node_cls[subs[k].second] != kReq) order.push_back(k);
+    for (size_t oi = 0; oi < order.size(); ++oi) {
+      const int s0 = subs[order[oi]].first, s1 = subs[order[oi]].second, cls = node_cls[s1];
+      const bool first = oi == 0, last = oi + 1 == order.size();
+      std::vector<fle_pred_node> sub(nodes + s0, nodes + s1 + 1);
+      if (cls == kReq) {
+        rc = eval_required(sub, bitmap_dev, last ? count_dev : nullptr);
+      } else {
+        int64_t m = 0;
+        rc = data_bitmap(sub, cls, &m);
+        if (rc != FLE_OK) return rc;
+        const int comb = first ? FOLD_SET : (join_op == FLE_OP_AND ? FOLD_AND : FOLD_OR);
+        // (an empty subtree deposits nothing: m = 0 makes every gathered bit 0)
+        rc = launch_deposit(ctx, reinterpret_cast<const uint64_t*>(cols[cls].def_planes), n, db, m, bitmap_dev, comb,
+                            last ? count_dev : nullptr);
+      }
+      if (rc != FLE_OK) return rc;
+    }
+    return FLE_OK;
+  }
+
   std::vector<const uint64_t*> leaf_bm;
   std::vector<fle_pred_node> prog;  // the combine program: mixed nodes + one leaf per subtree
   size_t si = 0;
-  auto alloc_words = [&](uint64_t** p, int64_t words) {
-    cudaError_t e = cudaMallocAsync(p, (size_t)std::max<int64_t>(words, 1) * 8, ctx->stream);
-    if (e != cudaSuccess) return set_cuda_error(ctx, e, "cudaMallocAsync(nullable path)");
-    tmp.push_back(*p);
-    return (int)FLE_OK;
-  };
-  for (int i = 0; i < nnodes && rc == FLE_OK; ++i) {
+  for (int i = 0; i < nnodes; ++i) {
     if (si >= subs.size() || i < subs[si].first) {  // mixed operator or plain constant: copied
       prog.push_back(nodes[i]);
       continue;
@@ -235,50 +313,23 @@ static int eval_dev_nullable(fle_ctx* ctx, const fle_col_desc* cols, int ncols,
     const int s0 = subs[si].first, s1 = subs[si].second, cls = node_cls[s1];
     ++si;
     i = s1;
-    uint64_t* lb = nullptr;
-    rc = alloc_words(&lb, nwords);
-    if (rc != FLE_OK) break;
+    uint64_t* lb = reinterpret_cast<uint64_t*>(scratch + bump);
+    bump += word_bytes;
     std::vector<fle_pred_node> sub(nodes + s0, nodes + s1 + 1);
     if (cls == kReq) {
-      // required columns only: remap the columns the subtree uses to 0..k-1
-      std::vector<int> map(ncols, -1);
-      std::vector<fle_col_desc> dc;
-      for (auto& nd : sub) {
-        if (nd.op == FLE_OP_AND || nd.op == FLE_OP_OR) continue;
-        if (map[nd.col] < 0) { map[nd.col] = (int)dc.size(); dc.push_back(cols[nd.col]); }
-        nd.col = map[nd.col];
-      }
-      rc = launch_eval(ctx, dc.data(), (int)dc.size(), sub.data(), (int)sub.size(), 0, n, lb, nullptr);
+      rc = eval_required(sub, lb, nullptr);
     } else {
-      const fle_col_desc& col = cols[cls];
-      const int64_t m = (int64_t)h_counts[cls];  // non-null values = rows of the data stream
-      const bool single = sub.size() == 1;
-      if (m == 0 || (single && sub[0].op == FLE_OP_NONE)) {
-        cudaError_t e = cudaMemsetAsync(lb, 0, (size_t)nwords * 8, ctx->stream);
-        if (e != cudaSuccess) rc = set_cuda_error(ctx, e, "cudaMemsetAsync(leaf)");
-      } else {
-        cudaError_t e = cudaMemcpyAsync(lb, notnull[cls], (size_t)nwords * 8, cudaMemcpyDeviceToDevice, ctx->stream);
-        if (e != cudaSuccess) rc = set_cuda_error(ctx, e, "cudaMemcpyAsync(notnull)");
-        if (rc == FLE_OK && !(single && sub[0].op == FLE_OP_ALL)) {
-          uint64_t* db = nullptr;
-          rc = alloc_words(&db, (m + 63) / 64);
-          if (rc != FLE_OK) break;
-          fle_col_desc dc{col.planes, col.bytes, col.bit_width, 0, nullptr, 0};
-          for (auto& nd : sub)
-            if (nd.op != FLE_OP_AND && nd.op != FLE_OP_OR) nd.col = 0;
-          rc = launch_eval(ctx, &dc, 1, sub.data(), (int)sub.size(), 0, m, db, nullptr);
-          if (rc == FLE_OK) rc = launch_intersect(ctx, lb, n, db, m);
-        }
-      }
+      int64_t m = 0;
+      rc = data_bitmap(sub, cls, &m);
+      if (rc == FLE_OK)
+        rc = launch_deposit(ctx, reinterpret_cast<const uint64_t*>(cols[cls].def_planes), n, db, m, lb, FOLD_SET, nullptr);
     }
+    if (rc != FLE_OK) return rc;
     fle_pred_node ref{FLE_OP_EQ, (int32_t)leaf_bm.size(), 0, nullptr, 0, 0};  // any leaf opcode: the combine kernel only looks at .col
     prog.push_back(ref);
     leaf_bm.push_back(lb);
   }
-  if (rc == FLE_OK)
-    rc = launch_bitmap_combine(ctx, leaf_bm.data(), (int)leaf_bm.size(), prog.data(), (int)prog.size(), n, bitmap_dev, count_dev);
-  cleanup();
-  return rc;
+  return launch_bitmap_combine(ctx, leaf_bm.data(), (int)leaf_bm.size(), prog.data(), (int)prog.size(), n, bitmap_dev, count_dev);
 }
 
 static bool any_nullable(const fle_col_desc* cols, int ncols) {
@@ -401,6 +452,7 @@ int fle_ctx_destroy(fle_ctx* ctx) {
   if (ctx->d_count) cudaFree(ctx->d_count);
   if (ctx->d_split) cudaFree(ctx->d_split);
   if (ctx->d_chunk_counts) cudaFree(ctx->d_chunk_counts);
+  if (ctx->d_null) cudaFree(ctx->d_null);
   if (ctx->d_realign) cudaFree(ctx->d_realign);
   if (ctx->d_dict) cudaFree(ctx->d_dict);
   if (ctx->d_tile_state) cudaFree(ctx->d_tile_state);

@@ -202,6 +202,93 @@ intersect_kernel(uint64_t* __restrict__ root, int64_t n_root, int64_t nwords,
   }
 }
 
+// Deposit straight from a column's definition levels (max_def_level == 1: the 1-bit FLE plane word of a group,
+// bit-reversed, IS the group's not-null word), out of place and combined with what the output already holds:
+//     out[w] = out[w] (op) deposit(not-null word w, the next popcount(not-null word) bits of sub)
+// -- one nullable column subtree of a conjunct chain per launch pair, with no not-null bitmap, no copy of it and no
+// separate combine pass (hdfs-parquet-scanner.cc:326-345 per leaf, :1857-1862 for the chain).
+__device__ __forceinline__ uint64_t def_word(const uint64_t* __restrict__ def_planes, int64_t w, int64_t nwords, int64_t n_root) {
+  return w < nwords ? (__brevll(def_planes[w]) & tail_mask_word(w, n_root)) : 0ull;
+}
+
+__global__ void __launch_bounds__(kBmThreads)
+def_block_counts_kernel(const uint64_t* __restrict__ def_planes, int64_t n_root, int64_t nwords, uint64_t* __restrict__ block_sums) {
+  __shared__ uint64_t warp_buf[kBmThreads / 32];
+  const int64_t w0 = (int64_t)blockIdx.x * kBmWordsPerBlock;
+  uint64_t c = 0;
+#pragma unroll
+  for (int k = 0; k < kBmWordsPerThread; ++k) c += __popcll(def_word(def_planes, w0 + k * kBmThreads + threadIdx.x, nwords, n_root));
+  const uint64_t t = block_sum<kBmThreads>(c, warp_buf);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(kBmThreads)
+deposit_kernel(const uint64_t* __restrict__ def_planes, int64_t n_root, int64_t nwords, const uint64_t* __restrict__ sub,
+               int64_t n_sub, const uint64_t* __restrict__ block_sums, uint64_t* __restrict__ out, int comb_op,
+               unsigned long long* __restrict__ count) {
+  __shared__ uint64_t warp_buf[kBmThreads / 32];
+  __shared__ uint32_t warp_scan[kBmThreads / 32];
+  uint64_t pre = 0;
+  for (int i = threadIdx.x; i < (int)blockIdx.x; i += kBmThreads) pre += block_sums[i];
+  const uint64_t block_off = block_sum<kBmThreads>(pre, warp_buf);
+  const int64_t w0 = (int64_t)blockIdx.x * kBmWordsPerBlock + (int64_t)threadIdx.x * kBmWordsPerThread;
+  uint64_t m[kBmWordsPerThread];
+  uint32_t mine = 0;
+#pragma unroll
+  for (int k = 0; k < kBmWordsPerThread; ++k) {
+    m[k] = def_word(def_planes, w0 + k, nwords, n_root);
+    mine += __popcll(m[k]);
+  }
+  uint32_t incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((threadIdx.x & 31) >= o) incl += y;
+  }
+  if ((threadIdx.x & 31) == 31) warp_scan[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  uint32_t warp_off = 0;
+  for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) warp_off += warp_scan[w];
+  int64_t rank = (int64_t)block_off + warp_off + (incl - mine);
+  uint64_t cnt = 0;
+#pragma unroll
+  for (int k = 0; k < kBmWordsPerThread; ++k) {
+    const int64_t w = w0 + k;
+    if (w < nwords) {
+      uint64_t r = deposit_bits(gather_bits(sub, n_sub, rank), m[k]);
+      if (comb_op == FOLD_AND) r &= out[w];
+      else if (comb_op == FOLD_OR) r |= out[w] & tail_mask_word(w, n_root);
+      out[w] = r;
+      cnt += __popcll(r);
+      rank += __popcll(m[k]);
+    }
+  }
+  if (count) {
+    __syncthreads();
+    const uint64_t t = block_sum<kBmThreads>(cnt, warp_buf);
+    if (threadIdx.x == 0 && t) atomicAdd(count, (unsigned long long)t);
+  }
+}
+
+int launch_deposit(fle_ctx* ctx, const uint64_t* def_planes_dev, int64_t n_root, const uint64_t* sub_dev, int64_t n_sub,
+                   uint64_t* out_dev, int comb_op, uint64_t* count_dev) {
+  if (n_root < 0 || n_sub < 0 || !def_planes_dev || !out_dev || (n_sub > 0 && !sub_dev))
+    return set_error(ctx, FLE_E_INVALID, "bad deposit arguments");
+  if (count_dev) FLE_CUDA_TRY(ctx, cudaMemsetAsync(count_dev, 0, 8, ctx->stream));
+  if (n_root == 0) return FLE_OK;
+  const int64_t nwords = (n_root + 63) / 64;
+  const int nblocks = (int)((nwords + kBmWordsPerBlock - 1) / kBmWordsPerBlock);
+  int rc = ensure_scratch(ctx, nblocks, 0);
+  if (rc != FLE_OK) return rc;
+  def_block_counts_kernel<<<nblocks, kBmThreads, 0, ctx->stream>>>(def_planes_dev, n_root, nwords, ctx->d_partial);
+  deposit_kernel<<<nblocks, kBmThreads, 0, ctx->stream>>>(def_planes_dev, n_root, nwords, sub_dev, n_sub, ctx->d_partial, out_dev,
+                                                         comb_op, reinterpret_cast<unsigned long long*>(count_dev));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(ctx, e, "deposit launch");
+  ctx->launches += 2;
+  return FLE_OK;
+}
+
 int launch_bitmap_count(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nbits, uint64_t* count_dev) {
   if (nbits < 0 || !count_dev) return set_error(ctx, FLE_E_INVALID, "bad bitmap_count arguments");
   if (nbits == 0) {

@@ -106,6 +106,9 @@ struct fle_ctx {
   uint64_t* d_split = nullptr;    // temporary bitmaps of regrouped programs (long IN lists), grow-only
   size_t split_cap = 0;           // bytes
   uint64_t* h_count = nullptr;    // pinned
+  bool nulls_seen = false;             // the previous nullable evaluation found NULLs (eval_dev_nullable)
+  void* d_null = nullptr;              // temporaries of the NULL path (data-domain bitmaps, leaf bitmaps), grow-only
+  size_t null_cap = 0;
   uint64_t* d_chunk_counts = nullptr;  // per-chunk counts of the host-buffer pipeline (fle_eval), grow-only
   size_t chunk_counts_cap = 0;         // 64-bit words
 
@@ -211,6 +214,10 @@ int launch_def_counts(fle_ctx* ctx, const fle_col_desc* cols, int ncols, int64_t
 int launch_bitmap_count(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nbits, uint64_t* count_dev);
 int launch_intersect(fle_ctx* ctx, uint64_t* root_dev, int64_t n_root, const uint64_t* sub_dev,
                      int64_t n_sub);
+// out = out (comb_op: FOLD_SET / FOLD_AND / FOLD_OR) deposit(not-null bitmap read straight from 1-bit def planes, sub);
+// count_dev (optional) receives popcount(out)
+int launch_deposit(fle_ctx* ctx, const uint64_t* def_planes_dev, int64_t n_root, const uint64_t* sub_dev, int64_t n_sub,
+                   uint64_t* out_dev, int comb_op, uint64_t* count_dev);
 // fle_plain.cu
 int launch_realign(fle_ctx* ctx, const uint8_t* src_dev, size_t nbytes, uint8_t* dst_dev);
 int launch_plain_eval(fle_ctx* ctx, const void* values_dev, int elem_type, int64_t n, int op, const void* lits_host,

@@ -16,7 +16,9 @@
 
 #include <map>
 #include <memory>
+#include <condition_variable>
 #include <mutex>
+#include <set>
 
 #include "fle_internal.h"
 #include "fle_jit.h"
@@ -323,8 +325,11 @@ Nvrtc* nvrtc() {
 }
 
 std::mutex g_mu;
+std::condition_variable g_compiled_cv;
 std::map<std::string, std::shared_ptr<JitEntry> > g_cache;
+std::set<std::string> g_compiling;  // shapes some thread is compiling right now
 std::map<std::string, int64_t> g_pending_rows;
+constexpr size_t kJitCacheMax = 1024;  // compiled shapes kept per process
 
 }  // namespace
 
@@ -373,16 +378,28 @@ int jit_compile_text(const std::string& program_text, std::vector<char>* cubin, 
 }
 
 std::shared_ptr<JitEntry> jit_lookup(const std::string& program_text, int64_t rows, int64_t min_rows, bool force) {
-  std::lock_guard<std::mutex> lock(g_mu);
-  auto it = g_cache.find(program_text);
-  if (it != g_cache.end()) return it->second;
+  // The lock covers the maps only, never a compilation: while one thread compiles a shape (0.3-0.8 s of NVRTC),
+  // cache hits of every other scanner thread go through, and callers that meet a shape IN compilation interpret
+  // meanwhile (force: they wait for that one entry).
+  std::unique_lock<std::mutex> lock(g_mu);
+  for (;;) {
+    auto it = g_cache.find(program_text);
+    if (it != g_cache.end()) return it->second;
+    if (g_compiling.find(program_text) == g_compiling.end()) break;
+    if (!force) return nullptr;
+    g_compiled_cv.wait(lock);
+  }
   // not compiled yet: the shape pays for its compilation once the rows evaluated with it (this
   // call included, all contexts of the process together) reach min_rows
   if (g_pending_rows.size() > 1024) g_pending_rows.clear();  // bounded bookkeeping for one-off shapes
   int64_t& seen = g_pending_rows[program_text];
   seen += rows;
   if (!force && seen < min_rows) return nullptr;
+  if (g_cache.size() >= kJitCacheMax) return nullptr;  // bounded cache: further shapes are interpreted
   g_pending_rows.erase(program_text);
+  g_compiling.insert(program_text);
+  lock.unlock();
+
   std::shared_ptr<JitEntry> e = std::make_shared<JitEntry>();
   std::vector<char> cubin;
   int rc = jit_compile_text(program_text, &cubin, &e->log);
@@ -404,7 +421,11 @@ std::shared_ptr<JitEntry> jit_lookup(const std::string& program_text, int64_t ro
     }
   }
   e->rc = rc;
+
+  lock.lock();
   g_cache[program_text] = e;
+  g_compiling.erase(program_text);
+  g_compiled_cv.notify_all();
   return e;
 }
 

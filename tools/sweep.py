@@ -218,6 +218,38 @@ def sweep_programs(ctx, out, n):
         alg_bytes=G * 25 * 8 + G * 8, rows_per_s=n / (mn * 1e-3), count=int(o2[0].item()), null_rows=int(o2[1].item()))
 
 
+def sweep_nulls(ctx, out, n):
+    """Q6 over three OPTIONAL columns that DO hold NULLs (2 %): per column one fused evaluation in the data-ordinal domain
+    and one deposit through the def-level planes, folded into the output bitmap (hdfs-parquet-scanner.cc:326-345);
+    the call includes the def-level count kernel, the optimistic launch and the host sync that picks the path."""
+    G = (n + 63) // 64
+    g = torch.Generator(device="cuda").manual_seed(77)
+    bm = torch.empty(G, dtype=torch.int64, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    pc, want, by = [], None, G * 8
+    for (d, bw), (lo, hi) in zip(((2526, 12), (11, 4), (50, 6)), ((730, 1094), (5, 7), (0, 22))):
+        nn = torch.rand(n, generator=g, device="cuda") >= 0.02
+        m = int(nn.sum().item())
+        data = torch.randint(0, d, (m,), generator=g, device="cuda", dtype=torch.int64).to(torch.int32)
+        leaf = torch.zeros(n, dtype=torch.bool, device="cuda")
+        leaf[nn] = (data >= lo) & (data <= hi)
+        want = leaf if want is None else (want & leaf)
+        pc.append((ctx.pack_dev(data, bw), bw, ctx.pack_dev(nn.to(torch.int32), 1)))
+        by += ((m + 63) // 64) * bw * 8 + G * 8
+        del nn, data, leaf
+    prog = [(GE, 0, 730), (LE, 0, 1094), (AND, None, None), (GE, 1, 5), (LE, 1, 7), (AND, None, None),
+            (AND, None, None), (LT, 2, 23), (AND, None, None)]
+    prep = (ctx.make_col_descs(pc),) + fle_b200.capi._build_program(prog)
+    l0 = ctx.launch_count
+    ctx.eval_dev(pc, prog, n, bitmap=bm, count=cnt, prepared=prep)
+    torch.cuda.synchronize()
+    per_call = ctx.launch_count - l0
+    assert int(cnt.item()) == int(want.sum().item()), "Q6 with NULLs: count differs from the torch compare"
+    mn, md = timeit(lambda: ctx.eval_dev(pc, prog, n, bitmap=bm, count=cnt, prepared=prep), working_set=by)
+    rec(out, what="program", name="q6_optional_cols_2pct_nulls", variant="1j", rows=n, sum_bw=25, ms_min=mn, ms_med=md,
+        alg_bytes=by, rows_per_s=n / (mn * 1e-3), count=int(cnt.item()), launches_per_call=per_call)
+
+
 def sweep_tune(ctx, out, n):
     G = (n + 63) // 64
     bm = torch.empty(G, dtype=torch.int64, device="cuda")
@@ -282,8 +314,8 @@ def sweep_aux(ctx, out, n):
     rec(out, what="aux", name="bitmap_count", rows=n, ms_min=mn, ms_med=md, alg_bytes=G * 8)
     ids = torch.empty(k + 64, dtype=torch.int32, device="cuda")
     mn, md = timeit(lambda: ctx.bitmap_select_dev(bm, n, cap=k + 64, ids=ids, count=cnt))
-    rec(out, what="aux", name=f"bitmap_select ({k} survivors, 3 launches)", rows=n, ms_min=mn, ms_med=md,
-        alg_bytes=2 * G * 8 + k * 4)
+    rec(out, what="aux", name=f"bitmap_select ({k} survivors, single pass with look-back)", rows=n, ms_min=mn, ms_med=md,
+        alg_bytes=G * 8 + k * 4)
     o = torch.empty(k + 64, dtype=torch.int32, device="cuda")
     mn, md = timeit(lambda: ctx.gather_dev(w, 12, ids, cnt, k + 64, out=o))
     rec(out, what="aux", name="gather codes of survivors (64 B fetched per survivor group)", rows=n, ms_min=mn, ms_med=md,
@@ -333,6 +365,8 @@ def main():
             sweep_codec(ctx, out, min(args.rows, 1 << 26))
         if what & {"programs", "all"}:
             sweep_programs(ctx, out, args.rows)
+        if what & {"nulls", "all"}:
+            sweep_nulls(ctx, out, args.rows)
         if what & {"tune"}:
             sweep_tune(ctx, out, args.rows)
         if what & {"aux", "all"}:
