@@ -329,11 +329,17 @@ class Bench:
         return [float(x.item()) for x in alls]
 
     def flush_l2(self):
-        """Between cold-timed launches: overwrite a buffer larger than twice the 126 MB L2."""
+        """Between cold-timed launches: overwrite a buffer larger than twice the 126 MB L2, then READ a second buffer of
+        twice the L2 that is clean in DRAM.  The overwrite alone leaves up to 126 MB of DIRTY lines behind, whose
+        write-back the next kernel pays for (~19 us at the HBM rate -- more than the whole roofline time of a 16 Mi-value
+        codec kernel); after the read pass the L2 holds clean lines of a buffer nobody uses."""
         torch = self.torch
         if self.flush_buf is None:
             self.flush_buf = torch.empty(384 << 20, dtype=torch.uint8, device=self.dev)
+            self.flush_clean = torch.zeros(256 << 17, dtype=torch.int64, device=self.dev)  # 256 MB
+            self.flush_sink = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self.flush_buf.zero_()
+        self.flush_clean.sum()
 
     def cold_ms(self, fn, reps=7, warm=2):
         """Median launch time with the L2 flushed before every timed launch (CUDA events on the stream)."""
@@ -557,6 +563,21 @@ class Bench:
             assert torch.equal(agg, want) and int(count.item()) == want_count
         scan_ms = self.loop_ms(lambda: ctx.eval_dev(q6_cols, q6_prog, n, bitmap=bitmap, count=count, prepared=prep), q6_steps)
         q6_bytes = G * (12 + 4 + 6) * 8 + G * 8
+        # the same scan as an Impala-written file presents it: every column OPTIONAL with a def-level stream (1-bit FLE,
+        # hdfs-parquet-table-writer.cc:103-105) that holds no NULL; checked and evaluated without a host sync
+        optional = None
+        if world == 1 and hasattr(ctx, "eval_no_nulls_dev"):
+            ones = torch.full((G,), -1, dtype=torch.int64, device=dev)
+            ocols = [c + (ones,) for c in q6_cols]
+            oprep = (ctx.make_col_descs(ocols),) + fle.capi._build_program(q6_prog)
+            o2 = torch.zeros(2, dtype=torch.int64, device=dev)
+            opt_ms = self.loop_ms(lambda: ctx.eval_no_nulls_dev(ocols, q6_prog, n, bitmap=bitmap, out=o2, prepared=oprep), q6_steps)
+            assert int(o2[0].item()) == want_count and int(o2[1].item()) == 0
+            obytes = q6_bytes + 3 * G * 8
+            optional = {"ms": opt_ms, "GBps": obytes / (opt_ms * 1e-3) / 1e9, "frac_of_peak": obytes / (opt_ms * 1e-3) / 1e9 / self.peak,
+                        "what": "scan_ms with three OPTIONAL columns through fle_eval_no_nulls_dev: def-level count kernel + fused scan, "
+                                "NULL count left on the device (no host sync); bytes = the scan's + 3 bits per row of def levels"}
+            del ones, ocols
         self.q6 = {
             "ms": q6_ms, "scan_ms": scan_ms, "two_kernel_ms": two_ms, "rows_per_s": n * world / (q6_ms * 1e-3),
             "jit_launches": ctx.get_option("jit_launches"),
@@ -567,7 +588,7 @@ class Bench:
             "revenue_exact_int64_1e-4_dollars": int(want[0].item()),
             "scan_achieved_GBps_per_gpu": q6_bytes / (scan_ms * 1e-3) / 1e9,
             "scan_frac_of_peak": q6_bytes / (scan_ms * 1e-3) / 1e9 / self.peak, "steps": q6_steps,
-            "full_bitmap_check": bm_check,
+            "full_bitmap_check": bm_check, "optional_columns_no_host_sync": optional,
         }
         del price, q6_cols, agg
         torch.cuda.empty_cache()
@@ -667,7 +688,7 @@ class Bench:
     # -- cfg0 / cfg3 sub-records (one GPU) ----------------------------------------------------------------
     def run_codec(self):
         torch, ctx, dev = self.torch, self.ctx, self.dev
-        out = {"what": "cfg0: FLE pack / unpack, uniform values, L2 flushed (384 MB overwrite) before every timed launch, median of 7; "
+        out = {"what": "cfg0: FLE pack / unpack, uniform values, L2 flushed (384 MB overwrite, then a 256 MB read of a clean buffer so that no dirty lines are left) before every timed launch, median of 7; "
                        "frac = (bw*8 + 64*sizeof(out)) bytes per group / time / measured HBM peak", "records": []}
         gen = torch.Generator(device=dev).manual_seed(0xF1E00000)
         for n in (1 << 24, 1 << 26):

@@ -1000,8 +1000,8 @@ static void unpack_choice(int bw, int* kind, int* ctas) {
   else if (bw <= 5) { *kind = UNPACK_STAGED; *ctas = 3; }
   else if (bw <= 8) { *kind = UNPACK_BULK; *ctas = 2; }
   else if (bw <= 21) { *kind = UNPACK_STAGED; *ctas = 2; }
-  else if (bw <= 28) { *kind = UNPACK_BULK; *ctas = 2; }
-  else { *kind = UNPACK_WARP; *ctas = 3; }
+  else { *kind = UNPACK_BULK; *ctas = 2; }  // (bw 29..32: warp-private copy-out measured equal warm, 9 % behind with a cold L2,
+                                            //  tools/codec_cold_probe.py: bw 32 0.889 vs 0.975)
 }
 
 int launch_unpack_u32(fle_ctx* ctx, const uint64_t* enc_dev, int bw, int64_t n, uint32_t* out_dev) {

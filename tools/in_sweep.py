@@ -44,6 +44,8 @@ def main():
              f"options {args.opt}", f"{'bw':>3} {'L':>4} {'ms':>8} {'GB/s':>8} {'frac':>6} {'mode':>5} {'launches':>8} | IN(L) AND qty<23: {'ms':>8} {'frac':>6} {'launches':>8}"]
 
     flush = torch.empty(384 << 20, dtype=torch.uint8, device="cuda")
+    clean = torch.zeros(256 << 17, dtype=torch.int64, device="cuda")
+    sink = torch.zeros(1, dtype=torch.int64, device="cuda")
 
     def timed(fn):
         for _ in range(2):
@@ -52,6 +54,7 @@ def main():
         for _ in range(7):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             flush.fill_(1)  # cold L2, and the GPU is busy while the host enqueues the timed launch
+            clean.sum()  # ... and no dirty lines left for the timed kernel to write back
             a.record()
             fn()
             b.record()

@@ -20,6 +20,8 @@ except Exception:
 torch.cuda.set_device(0)
 ctx = fle_b200.FleContext(0, torch.cuda.current_stream().cuda_stream)
 flush = torch.empty(384 << 20, dtype=torch.uint8, device="cuda")
+clean = torch.zeros(256 << 17, dtype=torch.int64, device="cuda")
+sink = torch.zeros(1, dtype=torch.int64, device="cuda")
 gen = torch.Generator(device="cuda").manual_seed(7)
 
 
@@ -29,6 +31,7 @@ def cold(fn, reps=9):
     ts = []
     for _ in range(reps):
         flush.fill_(1)
+        clean.sum()  # leave clean lines in the L2, not the overwrite's dirty ones
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         fn()

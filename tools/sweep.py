@@ -37,13 +37,20 @@ PEAK = peak()
 
 L2_BYTES = 126 << 20
 _flush_buf = None
+_flush_clean = None
+_flush_sink = None
 
 
 def flush_l2():
-    global _flush_buf
+    """384 MB overwrite, then a 256 MB READ of a buffer that is clean in DRAM: the overwrite alone leaves up to an L2 of
+    dirty lines whose write-back the timed kernel would pay for (~19 us)."""
+    global _flush_buf, _flush_clean, _flush_sink
     if _flush_buf is None:
         _flush_buf = torch.empty(384 << 20, dtype=torch.uint8, device="cuda")
+        _flush_clean = torch.zeros(256 << 17, dtype=torch.int64, device="cuda")
+        _flush_sink = torch.zeros(1, dtype=torch.int64, device="cuda")
     _flush_buf.fill_(1)
+    _flush_clean.sum()
 
 
 def timeit(fn, reps=10, warm=3, inner=8, working_set=None):
