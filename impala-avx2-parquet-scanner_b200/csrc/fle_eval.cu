@@ -963,7 +963,7 @@ static int launch_prepared_skewed(fle_ctx* ctx, LoweredProgram* lp, const EvalPa
     lp->jit_entry.reset();
   }
   if (lp->jit_state != 1) return FLE_E_UNSUPPORTED;
-  if (!lp->jit_entry) lp->jit_entry = jit_lookup(lp->jit_plan.text, n, ctx->eval_jit_min_rows, ctx->eval_jit == 2);
+  if (!lp->jit_entry) lp->jit_entry = jit_lookup(lp->jit_plan.text, n, ctx->eval_jit_min_rows, ctx->eval_jit == 2, ctx->eval_jit == 3, ctx->device);
   if (!lp->jit_entry || lp->jit_entry->rc != FLE_OK) return FLE_E_UNSUPPORTED;
   EvalParams P1 = P0;
   apply_skew(P1, ncols, slack);
@@ -1157,7 +1157,7 @@ int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, 
     }
     if (lp->jit_state == 1) {
       if (!lp->jit_entry)
-        lp->jit_entry = jit_lookup(lp->jit_plan.text, n, ctx->eval_jit_min_rows, ctx->eval_jit == 2 || agg);
+        lp->jit_entry = jit_lookup(lp->jit_plan.text, n, ctx->eval_jit_min_rows, ctx->eval_jit == 2 || agg, ctx->eval_jit == 3, ctx->device);
       if (lp->jit_entry && lp->jit_entry->rc == FLE_OK) {
         jit_fill_args(lp->jit_plan, P, lp->in_lits, &lp->jit_args);
         int rc = FLE_E_UNSUPPORTED;

@@ -19,6 +19,7 @@
 #include <condition_variable>
 #include <mutex>
 #include <set>
+#include <thread>
 
 #include "fle_internal.h"
 #include "fle_jit.h"
@@ -330,6 +331,14 @@ std::map<std::string, std::shared_ptr<JitEntry> > g_cache;
 std::set<std::string> g_compiling;  // shapes some thread is compiling right now
 std::map<std::string, int64_t> g_pending_rows;
 constexpr size_t kJitCacheMax = 1024;  // compiled shapes kept per process
+struct Compilers {  // background compilations (eval_jit = 3), joined before the cache is destroyed
+  std::vector<std::thread> threads;
+  ~Compilers() {
+    for (auto& t : threads)
+      if (t.joinable()) t.join();
+  }
+};
+Compilers g_compilers;  // (declared after the maps: destroyed before them)
 
 }  // namespace
 
@@ -377,7 +386,39 @@ int jit_compile_text(const std::string& program_text, std::vector<char>* cubin, 
   return FLE_OK;
 }
 
-std::shared_ptr<JitEntry> jit_lookup(const std::string& program_text, int64_t rows, int64_t min_rows, bool force) {
+// compile + load one shape (no lock held) and publish the entry
+static std::shared_ptr<JitEntry> compile_and_publish(const std::string& program_text, int device) {
+  std::shared_ptr<JitEntry> e = std::make_shared<JitEntry>();
+  std::vector<char> cubin;
+  int rc = jit_compile_text(program_text, &cubin, &e->log);
+  if (rc == FLE_OK) {
+    cudaLibrary_t lib = nullptr;
+    cudaError_t ce = device >= 0 ? cudaSetDevice(device) : cudaSuccess;  // (a background thread starts on device 0)
+    if (ce == cudaSuccess) ce = cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (ce == cudaSuccess) {
+      cudaKernel_t k = nullptr;
+      ce = cudaLibraryGetKernel(&k, lib, "fle_jit_kernel");
+      if (ce == cudaSuccess) {
+        e->lib = lib;
+        e->kern = reinterpret_cast<const void*>(k);
+      }
+    }
+    if (ce != cudaSuccess) {
+      cudaGetLastError();
+      e->log = std::string("loading the specialised kernel: ") + cudaGetErrorString(ce);
+      rc = FLE_E_CUDA;
+    }
+  }
+  e->rc = rc;
+  std::lock_guard<std::mutex> lock(g_mu);
+  g_cache[program_text] = e;
+  g_compiling.erase(program_text);
+  g_compiled_cv.notify_all();
+  return e;
+}
+
+std::shared_ptr<JitEntry> jit_lookup(const std::string& program_text, int64_t rows, int64_t min_rows, bool force,
+                                     bool background, int device) {
   // The lock covers the maps only, never a compilation: while one thread compiles a shape (0.3-0.8 s of NVRTC),
   // cache hits of every other scanner thread go through, and callers that meet a shape IN compilation interpret
   // meanwhile (force: they wait for that one entry).
@@ -398,35 +439,14 @@ std::shared_ptr<JitEntry> jit_lookup(const std::string& program_text, int64_t ro
   if (g_cache.size() >= kJitCacheMax) return nullptr;  // bounded cache: further shapes are interpreted
   g_pending_rows.erase(program_text);
   g_compiling.insert(program_text);
-  lock.unlock();
-
-  std::shared_ptr<JitEntry> e = std::make_shared<JitEntry>();
-  std::vector<char> cubin;
-  int rc = jit_compile_text(program_text, &cubin, &e->log);
-  if (rc == FLE_OK) {
-    cudaLibrary_t lib = nullptr;
-    cudaError_t ce = cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
-    if (ce == cudaSuccess) {
-      cudaKernel_t k = nullptr;
-      ce = cudaLibraryGetKernel(&k, lib, "fle_jit_kernel");
-      if (ce == cudaSuccess) {
-        e->lib = lib;
-        e->kern = reinterpret_cast<const void*>(k);
-      }
-    }
-    if (ce != cudaSuccess) {
-      cudaGetLastError();
-      e->log = std::string("loading the specialised kernel: ") + cudaGetErrorString(ce);
-      rc = FLE_E_CUDA;
-    }
+  if (background && !force) {
+    // eval_jit = 3: the compilation runs on its own thread and the caller interprets until the kernel is there
+    // (a scanner thread never stalls for NVRTC); the threads are joined when the library is unloaded
+    g_compilers.threads.emplace_back(compile_and_publish, program_text, device);
+    return nullptr;
   }
-  e->rc = rc;
-
-  lock.lock();
-  g_cache[program_text] = e;
-  g_compiling.erase(program_text);
-  g_compiled_cv.notify_all();
-  return e;
+  lock.unlock();
+  return compile_and_publish(program_text, device);
 }
 
 }  // namespace fle

@@ -43,6 +43,9 @@ int jit_compile_text(const std::string& program_text, std::vector<char>* cubin, 
 // process-wide kernel cache.  A shape that has no kernel yet is compiled (synchronously) once
 // `force` is set or the rows evaluated with it so far, `rows` included, reach min_rows; until then
 // the answer is null and the caller interprets.
-std::shared_ptr<JitEntry> jit_lookup(const std::string& program_text, int64_t rows, int64_t min_rows, bool force);
+// background: the compilation runs on its own thread (device: the CUDA device to load the kernel on), the answer
+// stays null until it is done.
+std::shared_ptr<JitEntry> jit_lookup(const std::string& program_text, int64_t rows, int64_t min_rows, bool force,
+                                     bool background = false, int device = -1);
 
 }  // namespace fle

@@ -111,7 +111,10 @@ int fle_ctx_sync(fle_ctx* ctx);
  * on a kernel specialised for the program's SHAPE at run time, compiled once per shape with
  * NVRTC and cached process-wide; literals are not part of the shape.  0 = never, 1 [default] =
  * once the rows evaluated with the shape in this process (this call included) reach
- * "eval_jit_min_rows" (default 2^24; the compilation happens inside that call), 2 = always; without a usable libnvrtc.so.12 modes 0/1 use the interpreting
+ * "eval_jit_min_rows" (default 2^24; the compilation happens inside that call), 2 = always, 3 = like 1 but the
+ * compilation runs on a thread of the library's own and the caller keeps to the interpreting kernels until the
+ * kernel is there -- no call ever waits for the compiler; while one thread compiles a shape, other threads'
+ * cache hits are not held up in any mode; without a usable libnvrtc.so.12 modes 0/1/3 use the interpreting
  * kernels and mode 2 fails with FLE_E_UNSUPPORTED),
  * "eval_stages", "eval_ctas_per_sm", "eval_gpt" (0 = auto: launch shape of the staged kernels),
  * "eval_narrow_bw" (single-pass programs on columns up to this width -- default 2; 1, 2 or 4

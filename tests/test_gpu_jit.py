@@ -123,6 +123,36 @@ def test_auto_mode_policy(ctx, oracle):
         ctx.set_option("eval_jit_min_rows", 1 << 24)
 
 
+def test_background_compilation(ctx, oracle):
+    """eval_jit = 3: the shape is compiled on a thread of the library's own; the calling thread never waits for NVRTC
+    -- it keeps to the interpreting kernels (same bits) until the kernel is there, then uses it."""
+    import time
+    rng = np.random.default_rng(14)
+    n = 64 * 3000
+    _, cols = make_cols(oracle, rng, n, (10, 5, 3), (700, 20, 6))  # a shape no other test uses
+    prog = [(LT, 0, 350), (GE, 1, 5), (OR,) + N_, (EQ, 2, 4), (AND,) + N_]
+    want, wcnt = oracle.eval_tree(cols, prog, n)
+    ctx.set_option("eval_variant", 1)
+    ctx.set_option("eval_jit", 3)
+    ctx.set_option("eval_jit_min_rows", 1)
+    try:
+        j0 = ctx.get_option("jit_launches")
+        t0 = time.time()
+        bm, cnt = ctx.eval(cols, prog, n)  # starts the compilation, runs interpreted
+        first_call_s = time.time() - t0
+        assert (bm == want).all() and cnt == wcnt and ctx.get_option("jit_launches") == j0
+        deadline = time.time() + 60
+        while ctx.get_option("jit_launches") == j0 and time.time() < deadline:
+            bm, cnt = ctx.eval(cols, prog, n)
+            assert (bm == want).all() and cnt == wcnt
+            time.sleep(0.02)
+        assert ctx.get_option("jit_launches") > j0, "the background compilation never delivered a kernel"
+        assert first_call_s < 0.25, f"the first call waited {first_call_s:.2f} s (for the compiler?)"
+    finally:
+        ctx.set_option("eval_jit", 1)
+        ctx.set_option("eval_jit_min_rows", 1 << 24)
+
+
 def test_device_resident_q6_matches_interpreting_kernel(ctx):
     """SF-10-sized Q6 on device-resident columns: auto mode picks the specialised kernel; its bitmap
     equals the interpreting kernel's word for word (which the other tests pin to the oracle)."""
