@@ -264,6 +264,22 @@ static int eval_dev_nullable(fle_ctx* ctx, const fle_col_desc* cols, int ncols,
       if (nd.op != FLE_OP_AND && nd.op != FLE_OP_OR) nd.col = 0;
     return launch_eval(ctx, &dc, 1, sub.data(), (int)sub.size(), 0, m, db, nullptr);
   };
+  // one nullable subtree -> out (comb: FOLD_SET / FOLD_AND / FOLD_OR with what out holds): evaluate + deposit in one
+  // kernel when the subtree is a single pass (fle_eval1_deposit.cu), else data-domain bitmap + deposit
+  auto deposit_subtree = [&](std::vector<fle_pred_node>& sub, int cls, uint64_t* out, int comb, uint64_t* cnt) -> int {
+    const uint64_t* def = reinterpret_cast<const uint64_t*>(cols[cls].def_planes);
+    if (ctx->null_fused) {
+      std::vector<fle_pred_node> s0(sub);
+      for (auto& nd : s0)
+        if (nd.op != FLE_OP_AND && nd.op != FLE_OP_OR) nd.col = 0;
+      const int r = launch_eval_deposit(ctx, cols[cls], s0.data(), (int)s0.size(), (int64_t)h_counts[cls], def, n, out, comb, cnt);
+      if (r != FLE_E_UNSUPPORTED) return r;
+    }
+    int64_t m = 0;
+    int r = data_bitmap(sub, cls, &m);
+    if (r != FLE_OK) return r;
+    return launch_deposit(ctx, def, n, db, m, out, comb, cnt);  // (an empty subtree deposits nothing: m = 0 makes every gathered bit 0)
+  };
   auto eval_required = [&](std::vector<fle_pred_node>& sub, uint64_t* out, uint64_t* cnt) -> int {
     std::vector<int> map(ncols, -1);  // remap the columns the subtree uses to 0..k-1
     std::vector<fle_col_desc> dc;
@@ -289,13 +305,8 @@ static int eval_dev_nullable(fle_ctx* ctx, const fle_col_desc* cols, int ncols,
       if (cls == kReq) {
         rc = eval_required(sub, bitmap_dev, last ? count_dev : nullptr);
       } else {
-        int64_t m = 0;
-        rc = data_bitmap(sub, cls, &m);
-        if (rc != FLE_OK) return rc;
         const int comb = first ? FOLD_SET : (join_op == FLE_OP_AND ? FOLD_AND : FOLD_OR);
-        // (an empty subtree deposits nothing: m = 0 makes every gathered bit 0)
-        rc = launch_deposit(ctx, reinterpret_cast<const uint64_t*>(cols[cls].def_planes), n, db, m, bitmap_dev, comb,
-                            last ? count_dev : nullptr);
+        rc = deposit_subtree(sub, cls, bitmap_dev, comb, last ? count_dev : nullptr);
       }
       if (rc != FLE_OK) return rc;
     }
@@ -319,10 +330,7 @@ static int eval_dev_nullable(fle_ctx* ctx, const fle_col_desc* cols, int ncols,
     if (cls == kReq) {
       rc = eval_required(sub, lb, nullptr);
     } else {
-      int64_t m = 0;
-      rc = data_bitmap(sub, cls, &m);
-      if (rc == FLE_OK)
-        rc = launch_deposit(ctx, reinterpret_cast<const uint64_t*>(cols[cls].def_planes), n, db, m, lb, FOLD_SET, nullptr);
+      rc = deposit_subtree(sub, cls, lb, FOLD_SET, nullptr);
     }
     if (rc != FLE_OK) return rc;
     fle_pred_node ref{FLE_OP_EQ, (int32_t)leaf_bm.size(), 0, nullptr, 0, 0};  // any leaf opcode: the combine kernel only looks at .col
@@ -495,6 +503,7 @@ int fle_ctx_set_option(fle_ctx* ctx, const char* name, int64_t value) {
   else if (k == "eval_ctas_per_sm") ctx->eval_ctas_per_sm = (int)value;
   else if (k == "eval_gpt") ctx->eval_gpt = (int)value;
   else if (k == "in_lookup_min") ctx->in_lookup_min = (int)value;
+  else if (k == "null_fused") ctx->null_fused = value != 0;
   else if (k == "in_wide") ctx->in_wide = (int)value;
   else if (k == "in_wide_warps") ctx->in_wide_warps = (int)value;
   else if (k == "in_wide_gpt") ctx->in_wide_gpt = (int)value;
@@ -522,6 +531,7 @@ int64_t fle_ctx_get_option(fle_ctx* ctx, const char* name) {
   if (k == "eval_ctas_per_sm") return ctx->eval_ctas_per_sm;
   if (k == "eval_gpt") return ctx->eval_gpt;
   if (k == "in_lookup_min") return ctx->in_lookup_min;
+  if (k == "null_fused") return ctx->null_fused ? 1 : 0;
   if (k == "in_wide") return ctx->in_wide;
   if (k == "in_wide_warps") return ctx->in_wide_warps;
   if (k == "in_wide_gpt") return ctx->in_wide_gpt;

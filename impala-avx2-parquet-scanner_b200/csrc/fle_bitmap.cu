@@ -6,34 +6,10 @@
 // the device that is a prefix popcount over root's words followed, per word, by a bit
 // gather from sub (64-bit funnel shift across two words) and a bit deposit into the set
 // positions of the root word.
-#include "fle_device.cuh"
+#include "fle_bitmap.cuh"
 #include "fle_internal.h"
 
 namespace fle {
-
-constexpr int kBmThreads = 256;
-constexpr int kBmWordsPerThread = 8;
-constexpr int kBmWordsPerBlock = kBmThreads * kBmWordsPerThread;
-
-__device__ __forceinline__ uint64_t tail_mask_word(int64_t w, int64_t nbits) {
-  const int64_t left = nbits - w * 64;
-  if (left >= 64) return ~0ull;
-  if (left <= 0) return 0ull;
-  return (1ull << left) - 1ull;
-}
-
-template <int NT>
-__device__ __forceinline__ uint64_t block_sum(uint64_t v, uint64_t* warp_buf) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if ((threadIdx.x & 31) == 0) warp_buf[threadIdx.x >> 5] = v;
-  __syncthreads();
-  uint64_t t = 0;
-#pragma unroll
-  for (int w = 0; w < NT / 32; ++w) t += warp_buf[w];
-  __syncthreads();
-  return t;
-}
 
 // Non-null rows per nullable column = set bits of its def-level stream (1-bit FLE planes: row k of a
 // group at bit 63 - k; def level 1 == present, hdfs-parquet-scanner.cc:890-899), all columns in one
@@ -119,33 +95,6 @@ sum_u64_kernel(const uint64_t* __restrict__ v, int n, uint64_t* __restrict__ out
   if (threadIdx.x == 0) *out = t;
 }
 
-// bit deposit: the i-th set bit of mask (from the LSB) receives bit i of src
-__device__ __forceinline__ uint64_t deposit_bits(uint64_t src, uint64_t mask) {
-  if (mask == ~0ull) return src;
-  const int ones = __popcll(mask);
-  if (ones >= 32) {
-    // few holes: open a zero gap at every clear position of mask, lowest first
-    uint64_t holes = ~mask;
-    uint64_t r = src;
-    while (holes) {
-      const int z = __ffsll((long long)holes) - 1;
-      const uint64_t low = (1ull << z) - 1ull;
-      r = (r & low) | ((r & ~low) << 1);
-      holes &= holes - 1;
-    }
-    return r & mask;
-  }
-  uint64_t r = 0, m = mask;
-  int i = 0;
-  while (m) {
-    const int p = __ffsll((long long)m) - 1;
-    r |= ((src >> i) & 1ull) << p;
-    m &= m - 1;
-    ++i;
-  }
-  return r;
-}
-
 // 64 bits of sub starting at bit offset `pos` (bits past n_sub read as 0)
 __device__ __forceinline__ uint64_t gather_bits(const uint64_t* __restrict__ sub, int64_t n_sub,
                                                 int64_t pos) {
@@ -207,10 +156,6 @@ intersect_kernel(uint64_t* __restrict__ root, int64_t n_root, int64_t nwords,
 //     out[w] = out[w] (op) deposit(not-null word w, the next popcount(not-null word) bits of sub)
 // -- one nullable column subtree of a conjunct chain per launch pair, with no not-null bitmap, no copy of it and no
 // separate combine pass (hdfs-parquet-scanner.cc:326-345 per leaf, :1857-1862 for the chain).
-__device__ __forceinline__ uint64_t def_word(const uint64_t* __restrict__ def_planes, int64_t w, int64_t nwords, int64_t n_root) {
-  return w < nwords ? (__brevll(def_planes[w]) & tail_mask_word(w, n_root)) : 0ull;
-}
-
 __global__ void __launch_bounds__(kBmThreads)
 def_block_counts_kernel(const uint64_t* __restrict__ def_planes, int64_t n_root, int64_t nwords, uint64_t* __restrict__ block_sums) {
   __shared__ uint64_t warp_buf[kBmThreads / 32];
@@ -268,6 +213,11 @@ deposit_kernel(const uint64_t* __restrict__ def_planes, int64_t n_root, int64_t 
     const uint64_t t = block_sum<kBmThreads>(cnt, warp_buf);
     if (threadIdx.x == 0 && t) atomicAdd(count, (unsigned long long)t);
   }
+}
+
+// (also the first launch of the fused evaluate + deposit kernels, fle_eval1_deposit.cu)
+void launch_def_block_counts(fle_ctx* ctx, const uint64_t* def_planes_dev, int64_t n_root, int64_t nwords, int nblocks) {
+  def_block_counts_kernel<<<nblocks, kBmThreads, 0, ctx->stream>>>(def_planes_dev, n_root, nwords, ctx->d_partial);
 }
 
 int launch_deposit(fle_ctx* ctx, const uint64_t* def_planes_dev, int64_t n_root, const uint64_t* sub_dev, int64_t n_sub,

@@ -106,6 +106,7 @@ struct fle_ctx {
   uint64_t* d_split = nullptr;    // temporary bitmaps of regrouped programs (long IN lists), grow-only
   size_t split_cap = 0;           // bytes
   uint64_t* h_count = nullptr;    // pinned
+  bool null_fused = true;              // NULL path: single-pass subtrees evaluate + deposit in one kernel (option "null_fused")
   bool nulls_seen = false;             // the previous nullable evaluation found NULLs (eval_dev_nullable)
   void* d_null = nullptr;              // temporaries of the NULL path (data-domain bitmaps, leaf bitmaps), grow-only
   size_t null_cap = 0;
@@ -218,6 +219,10 @@ int launch_intersect(fle_ctx* ctx, uint64_t* root_dev, int64_t n_root, const uin
 // count_dev (optional) receives popcount(out)
 int launch_deposit(fle_ctx* ctx, const uint64_t* def_planes_dev, int64_t n_root, const uint64_t* sub_dev, int64_t n_sub,
                    uint64_t* out_dev, int comb_op, uint64_t* count_dev);
+// fle_eval1_deposit.cu: the same with the sub-program (leaves on column 0 = col, n_sub values in its data stream)
+// evaluated inside the deposit kernel -- no data-domain bitmap.  FLE_E_UNSUPPORTED: not a single supported pass.
+int launch_eval_deposit(fle_ctx* ctx, const fle_col_desc& col, const fle_pred_node* nodes, int nnodes, int64_t n_sub,
+                        const uint64_t* def_planes_dev, int64_t n_root, uint64_t* out_dev, int comb_op, uint64_t* count_dev);
 // fle_plain.cu
 int launch_realign(fle_ctx* ctx, const uint8_t* src_dev, size_t nbytes, uint8_t* dst_dev);
 int launch_plain_eval(fle_ctx* ctx, const void* values_dev, int elem_type, int64_t n, int op, const void* lits_host,

@@ -251,8 +251,14 @@ def test_nullable_columns_vs_oracle(ctx, oracle, null_frac):
             else:
                 b = st.pop()
                 st[-1] = st[-1] & b if op == AND else st[-1] | b
-        bm, cnt = ctx.eval(cols, pr, n)
-        assert (bm == st[0]).all() and cnt == popcount(st[0]), pr
+        # single-pass subtrees evaluate + deposit in one kernel (default) / data-domain bitmap, then deposit
+        for fused in (1, 0):
+            ctx.set_option("null_fused", fused)
+            try:
+                bm, cnt = ctx.eval(cols, pr, n)
+            finally:
+                ctx.set_option("null_fused", 1)
+            assert (bm == st[0]).all() and cnt == popcount(st[0]), (pr, fused)
 
 
 # ------------------------------------------------------------------------------------------
