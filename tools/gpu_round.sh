@@ -10,13 +10,18 @@ timeout 900 python bench.py > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.
 echo "bench rc=$?"
 timeout 900 python bench.py --impl reference --steps 5 --warmup 1 > $out/${tag}_bench_reference_arm.json 2>> $out/${tag}_bench_n1.err
 timeout 600 python tools/in_sweep.py --out $out/${tag}_in_sweep.txt > /dev/null 2> $out/${tag}_in_sweep.err
-timeout 900 python tools/sweep.py programs --rows 600037902 --out $out/${tag}_sweep_programs_600M_rows.jsonl > /dev/null 2> $out/${tag}_sweep_programs.err
+timeout 900 python tools/sweep.py programs nulls --rows 600037902 --out $out/${tag}_sweep_programs_600M_rows.jsonl > /dev/null 2> $out/${tag}_sweep_programs.err
+timeout 300 python tools/narrow_unpack_probe.py > $out/${tag}_narrow_unpack.txt 2>&1
+timeout 300 python tools/codec_cold_probe.py > $out/${tag}_codec_cold.txt 2>&1
 timeout 600 python tools/sweep.py aux --rows 268435456 --out $out/${tag}_sweep_aux.jsonl > /dev/null 2> $out/${tag}_sweep_aux.err
 # launch list of the bench command (shares, not absolutes)
 timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/${tag}_bench_launches.csv \
     python bench.py --steps 20 --warmup 3 --no-cpu > $out/${tag}_bench_under_ncu.log 2>&1
-for c in between12 q6agg in256; do
+for c in between12 q6agg in256 in256x8; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:'eval|fle_jit' -c 2 -f -o $out/${tag}_${c} \
       python tools/profile_one.py $c 600037902 3 > $out/${tag}_ncu_${c}.log 2>&1
+  # only the summary travels back (gpurun_out/ is capped at 64 MiB; a report with sources is 10-40 MB)
+  python tools/ncu_brief.py $out/${tag}_${c}.ncu-rep > $out/${tag}_${c}_ncu_full_summary.txt 2>&1
+  rm -f $out/${tag}_${c}.ncu-rep
 done
 ls -la $out
