@@ -16,7 +16,12 @@ int set_error(fle_ctx* ctx, int code, const std::string& msg) {
 }
 
 int set_cuda_error(fle_ctx* ctx, cudaError_t e, const char* what) {
-  if (ctx) ctx->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  if (ctx) {
+    ctx->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    // a kernel that did not run to its end leaves the self-resetting ticket / tile counters non-zero: the next
+    // launch that uses them clears them first (reset_counters_if_dirty), or every later count would be wrong
+    ctx->counters_dirty = true;
+  }
   if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return FLE_E_NODEVICE;
   if (e == cudaErrorMemoryAllocation) return FLE_E_NOMEM;
   return FLE_E_CUDA;
@@ -36,6 +41,10 @@ struct DeviceGuard {
 };
 
 int ensure_scratch(fle_ctx* ctx, int nblocks, int n_in_lits) {
+  if (ctx->counters_dirty) {  // (every launcher that hands d_ticket to a kernel comes through here first)
+    ctx->counters_dirty = false;
+    FLE_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_ticket, 0, 8, ctx->stream));
+  }
   if (nblocks > ctx->partial_cap) {
     const int cap = std::max(nblocks, 4096);
     uint64_t* p = nullptr;

@@ -215,11 +215,6 @@ deposit_kernel(const uint64_t* __restrict__ def_planes, int64_t n_root, int64_t 
   }
 }
 
-// (also the first launch of the fused evaluate + deposit kernels, fle_eval1_deposit.cu)
-void launch_def_block_counts(fle_ctx* ctx, const uint64_t* def_planes_dev, int64_t n_root, int64_t nwords, int nblocks) {
-  def_block_counts_kernel<<<nblocks, kBmThreads, 0, ctx->stream>>>(def_planes_dev, n_root, nwords, ctx->d_partial);
-}
-
 int launch_deposit(fle_ctx* ctx, const uint64_t* def_planes_dev, int64_t n_root, const uint64_t* sub_dev, int64_t n_sub,
                    uint64_t* out_dev, int comb_op, uint64_t* count_dev) {
   if (n_root < 0 || n_sub < 0 || !def_planes_dev || !out_dev || (n_sub > 0 && !sub_dev))

@@ -81,6 +81,7 @@ struct fle_ctx {
   uint64_t* d_partial = nullptr;  // per-CTA counts
   int partial_cap = 0;
   unsigned int* d_ticket = nullptr;
+  bool counters_dirty = false;    // a CUDA error was reported: clear d_ticket before its next use
   // IN literal pools: a ring of {pinned host, device} slots, one per prepared program.  Uploads and
   // kernels are ordered by the context's one stream, so a device slot can be rewritten as soon as the
   // copy is enqueued; only the PINNED side needs care (the host must not overwrite it before the

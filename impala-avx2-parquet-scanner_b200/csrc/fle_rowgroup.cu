@@ -305,6 +305,8 @@ __global__ void __launch_bounds__(kTileThreads) tile_scan_kernel(const __grid_co
 }
 
 static int launch_tile_scan(fle_ctx* ctx, TileScanParams& P, bool assemble) {
+  const int rc0 = ensure_scratch(ctx, 1, 0);  // (clears the ticket / tile counters after a reported CUDA error)
+  if (rc0 != FLE_OK) return rc0;
   const int64_t nwords = (P.nbits + 63) / 64;
   P.nwords = nwords;
   P.ntiles = (int)((nwords + kTileWords - 1) / kTileWords);
