@@ -513,6 +513,7 @@ int fle_ctx_set_option(fle_ctx* ctx, const char* name, int64_t value) {
   else if (k == "eval_gpt") ctx->eval_gpt = (int)value;
   else if (k == "in_lookup_min") ctx->in_lookup_min = (int)value;
   else if (k == "null_fused") ctx->null_fused = value != 0;
+  else if (k == "in_mux_min") ctx->in_mux_min = (int)std::max<int64_t>(1, std::min<int64_t>(value, 1 << 30));
   else if (k == "in_wide") ctx->in_wide = (int)value;
   else if (k == "in_wide_warps") ctx->in_wide_warps = (int)value;
   else if (k == "in_wide_gpt") ctx->in_wide_gpt = (int)value;
@@ -541,6 +542,7 @@ int64_t fle_ctx_get_option(fle_ctx* ctx, const char* name) {
   if (k == "eval_gpt") return ctx->eval_gpt;
   if (k == "in_lookup_min") return ctx->in_lookup_min;
   if (k == "null_fused") return ctx->null_fused ? 1 : 0;
+  if (k == "in_mux_min") return ctx->in_mux_min;
   if (k == "in_wide") return ctx->in_wide;
   if (k == "in_wide_warps") return ctx->in_wide_warps;
   if (k == "in_wide_gpt") return ctx->in_wide_gpt;

@@ -931,7 +931,7 @@ static int launch_prepared_skewed(fle_ctx* ctx, LoweredProgram* lp, const EvalPa
   const bool single_pass = P0.npasses == 1 && P0.ncombs == 0 && (p0.type == PASS_LT || p0.type == PASS_EQ) &&
                            (p0.k == 1 || p0.merge) && p0.slot[0] == 0;
   const bool in_single = P0.npasses == 1 && P0.ncombs == 0 && p0.type == PASS_IN && p0.slot[0] == 0;
-  if (single_pass || (in_single && (int)P0.bw[p0.col] <= ctx->in_mux_bw && (int)p0.lit[1] >= ctx->in_lookup_min)) {
+  if (single_pass || (in_single && (int)P0.bw[p0.col] <= ctx->in_mux_bw && (int)p0.lit[1] >= std::min(ctx->in_lookup_min, ctx->in_mux_min))) {
     EvalParams P1 = P0;
     const int c = p0.col;
     P1.ncols = 1;
@@ -1115,7 +1115,10 @@ int launch_prepared(fle_ctx* ctx, LoweredProgram* lp, const fle_col_desc* cols, 
     }
     return launch_program(ctx, P1, MODE_IN_LOOKUP, (int)P.bw[c]);
   };
-  if (in_single && (int)p0.lit[1] >= ctx->in_lookup_min) {
+  // (the multiplexer tree of a narrow column costs 2^bw terms whatever the list holds: it beats unrolled equality
+  //  chains -- 2 * bw LOP3 per literal -- from a handful of literals on: bw 5, 8 literals 0.73 -> 0.88 of roofline)
+  const bool in_mux_short = in_single && (int)P.bw[p0.col] <= ctx->in_mux_bw && (int)p0.lit[1] >= ctx->in_mux_min;
+  if (in_single && ((int)p0.lit[1] >= ctx->in_lookup_min || in_mux_short)) {
     const int rc = launch_in_lookup();
     if (rc != FLE_E_UNSUPPORTED) return rc;
   }

@@ -68,6 +68,7 @@ struct fle_ctx {
                              // ... with word / byte entries addressed straight from the transposed word, bw <= 12 (2)
   int in_wide_warps = 0;     // consumer warps per CTA of the one-CTA IN lookup kernel (form 2: 16 or 24; 0 = measured default)
   int in_wide_gpt = 0;       // groups per consumer thread per tile (form 2: 1, or 2 with 16 warps; 0 = measured default)
+  int in_mux_min = 4;        // lists of at least this many literals on columns up to in_mux_bw use the multiplexer tree even below in_lookup_min
   int in_mux_bw = 6;         // IN lists of in_lookup_min+ literals on columns up to this width run in the plane domain (0 = never)
   int64_t in_split_min_rows = 1ll << 20;  // calls of at least this many rows evaluate long IN lists (>= 16 literals) inside larger programs with the lookup kernels; -1 = never
   int codec_variant = 1;

@@ -132,8 +132,8 @@ int fle_ctx_sync(fle_ctx* ctx);
  * kernel; the older forms stay as on-device cross-checks),
  * "in_wide_warps", "in_wide_gpt" (0 = measured default: consumer warps per CTA and groups per
  * consumer thread per tile of the form-2 lookup kernel),
- * "in_mux_bw" (IN lists of in_lookup_min+ literals on columns up to this width -- default 6, at
- * most 7 -- are evaluated in the plane domain as a multiplexer tree; 0 = never),
+ * "in_mux_bw", "in_mux_min" (IN lists on columns up to in_mux_bw bits -- default 6, at most 7; 0 = never --
+ * are evaluated in the plane domain as a multiplexer tree from in_mux_min literals on, default 4),
  * "codec_variant" (0 = direct loads/stores; 1 [default] = per-bit-width choice among the staged
  * unpack kernels; 2 = per-row bulk stores, 3 = warp-private copy-out, 4 = CTA-wide copy-out),
  * "codec_ctas_per_sm" (0 = auto), "h2d_chunk_rows",

@@ -561,6 +561,7 @@ def test_in_list_lookup_kernel_vs_oracle(ctx, oracle, bw):
             ctx.set_option("in_lookup_min", lookup_min)
             ctx.set_option("in_wide", wide)
             ctx.set_option("in_mux_bw", mux)
+            ctx.set_option("in_mux_min", 4 if lookup_min == 1 else 1 << 30)  # (last configuration: equality chains only)
             try:
                 bm, cnt = ctx.eval([(words, bw)], [(IN, 0, lits)], n)
                 mode = ctx.get_option("last_mode")
@@ -568,6 +569,7 @@ def test_in_list_lookup_kernel_vs_oracle(ctx, oracle, bw):
                 ctx.set_option("in_lookup_min", 9)
                 ctx.set_option("in_wide", 2)
                 ctx.set_option("in_mux_bw", 6)
+                ctx.set_option("in_mux_min", 4)
             assert (bm == want).all() and cnt == wcnt, (bw, L, lookup_min, wide, mux)
             if lookup_min == 1 and bw <= 16:
                 assert mode == (7 if bw <= mux else (6 if wide else 3)), (bw, mode)
