@@ -995,7 +995,11 @@ int codec_grid(fle_ctx* ctx, int64_t ngroups) {
 // and write streams for the memory system, nothing left to hide -- except for the narrowest
 // widths, whose tiles are nearly all output.
 enum UnpackKind { UNPACK_STAGED = 4, UNPACK_BULK = 2, UNPACK_WARP = 3 };
-static void unpack_choice(int bw, int* kind, int* ctas) {
+static void unpack_choice(int bw, int64_t ngroups, int* kind, int* ctas) {
+  // Short runs (the reference benchmark's own 16 Mi values: a 10-20 us kernel, 7 tiles per CTA) are about ramp-up
+  // and the tile loop's latency, not steady-state bandwidth: the warp-private pipeline -- three stages, no CTA
+  // barrier -- wins by 8-15 % from bw 4 to 28 (tools/codec_cold_probe.py 16777216: bw 8 0.63 -> 0.78, bw 16 0.75 -> 0.83)
+  if (ngroups <= (1 << 19) && bw >= 3 && bw <= 28) { *kind = UNPACK_WARP; *ctas = 3; return; }
   if (bw <= 3) { *kind = UNPACK_WARP; *ctas = 2; }
   else if (bw <= 5) { *kind = UNPACK_STAGED; *ctas = 3; }
   else if (bw <= 8) { *kind = UNPACK_BULK; *ctas = 2; }
@@ -1013,7 +1017,7 @@ int launch_unpack_u32(fle_ctx* ctx, const uint64_t* enc_dev, int bw, int64_t n, 
   if (ctx->codec_variant != 0 && enc_ok) {
     // codec_variant: 1 auto, 2 bulk stores, 3 warp-private copy-out, 4 staged copy-out (0: direct loads)
     int kind = ctx->codec_variant, ctas = 0;
-    if (kind == 1) unpack_choice(bw, &kind, &ctas);
+    if (kind == 1) unpack_choice(bw, G, &kind, &ctas);
     if (!out_ok || (kind != UNPACK_BULK && kind != UNPACK_WARP)) kind = UNPACK_STAGED;
     if (ctx->codec_ctas_per_sm > 0) ctas = ctx->codec_ctas_per_sm;
     const size_t stage = (plane_tile_bytes(bw, MakeSeq<32>::type()) + 127) / 128 * 128;
