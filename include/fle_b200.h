@@ -348,7 +348,10 @@ int fle_eval_sum_product_dev(fle_ctx* ctx, const fle_col_desc* cols_dev, int nco
  * collective); a peer that does not arrive within "group_timeout_ms" (context option, default
  * 10000) is reported by fle_group_status and its contribution taken as 0.
  *
- * One process, several GPUs (or several contexts on one GPU): */
+ * One process, several GPUs (or several contexts on one GPU -- then run every member's kernels once before the
+ * first group call: with "group_deferred" = 0 a member's kernel waits for its peers' kernels, and the CUDA runtime
+ * loads a kernel lazily at its first launch, which may need the device idle; members on different devices are not
+ * coupled that way): */
 int fle_group_create_local(fle_ctx* const* ctxs, int n);
 /* One process per GPU: every rank exports a 64-byte handle of its mailbox (CUDA IPC), the caller
  * all-gathers the handles with its own transport (MPI, torch.distributed, a socket) and every rank

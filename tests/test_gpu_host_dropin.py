@@ -31,7 +31,7 @@ def host_tests(lib_path):
     return os.path.join(HOST, "tests")
 
 
-@pytest.mark.parametrize("name", ["fle-test", "dict-test", "scanner-test"])
+@pytest.mark.parametrize("name", ["fle-test", "dict-test", "scanner-test", "group-test"])
 def test_cpp_suite(host_tests, name):
     p = subprocess.run([os.path.join(host_tests, name)], capture_output=True, text=True, timeout=900)
     print(p.stdout[-3000:], p.stderr[-3000:])
