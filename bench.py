@@ -981,9 +981,9 @@ def main():
             },
             "encoded_GBps": alg_bytes * world / (h["ms_per_step"] * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": b.peak, "unit": "GB/s", "frac": achieved / b.peak,
-                         "traffic": 971.3e6,
+                         "traffic": 972.2e6,
                          "traffic_source": "CITED, not measured in this run: ncu --set full dram__bytes_read.sum + dram__bytes_write.sum "
-                                           "per launch, profiles/r01_eval1_bw12_ncu_full_summary.txt (900.1 MB + 71.2 MB; algorithmic 975.1 MB)",
+                                           "per launch, profiles/r02_between12_ncu_full_summary.txt (900.1 MB + 72.0 MB; algorithmic 975.1 MB)",
                          "peak_source": b.peak_src,
                          "kernel": "fle::eval1_kernel<IS_LT=true, K=2, BW=12> (TMA-staged single-pass BETWEEN, 1 CTA per SM x 3 stages of 48 KB)",
                          "algorithmic_bytes_per_launch": alg_bytes, "mean_launch_ms": h["mean_kern_ms"],
