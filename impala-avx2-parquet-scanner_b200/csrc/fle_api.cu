@@ -150,47 +150,11 @@ static int eval_dev_nullable(fle_ctx* ctx, const fle_col_desc* cols, int ncols,
   }
   for (int c = 0; c < ncols; ++c)
     if (cols[c].max_def_level > 1) return set_error(ctx, FLE_E_UNSUPPORTED, "max_def_level > 1 (nested types)");
-  // 1. non-null rows per column (one launch, nothing written) ...
-  constexpr size_t kCountsBytes = 256;
-  uint8_t* scratch = null_scratch(ctx, kCountsBytes);
-  if (!scratch) return set_error(ctx, FLE_E_NOMEM, "scratch of the NULL path");
-  uint64_t* d_counts = reinterpret_cast<uint64_t*>(scratch);
-  int rc = launch_def_counts(ctx, cols, ncols, n, d_counts);
-  if (rc != FLE_OK) return rc;
-  // 2a. ... and, without waiting for them, the fused kernel over the columns as if they were
-  // required: with no NULL anywhere (TPC-H; Impala's writer marks every column OPTIONAL) the data
-  // ordinal IS the row index and this is the answer.  (Skipped when a data stream is too short to
-  // hold n values -- then there are NULLs for sure.)
-  std::vector<fle_col_desc> req(cols, cols + ncols);
-  for (auto& d : req) { d.max_def_level = 0; d.def_planes = nullptr; d.def_bytes = 0; }
-  bool optimistic = true;
-  for (int c = 0; c < ncols; ++c)
-    if (cols[c].bytes < (uint64_t)nwords * (uint64_t)cols[c].bit_width * 8u) optimistic = false;
-  // (a context whose previous nullable call DID find NULLs -- a file that has them usually has them in every row
-  //  group -- waits for the counts first instead of launching a scan it would throw away)
-  const bool launch_first = optimistic && !ctx->nulls_seen;
-  if (launch_first) {
-    rc = launch_eval(ctx, req.data(), ncols, nodes, nnodes, 0, n, bitmap_dev, count_dev);
-    if (rc != FLE_OK) return rc;
-  }
-  std::vector<uint64_t> h_counts(ncols, 0);
-  FLE_CUDA_TRY(ctx, cudaMemcpyAsync(h_counts.data(), d_counts, (size_t)ncols * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  FLE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  bool any_null = false;
-  for (int c = 0; c < ncols; ++c)
-    if (cols[c].max_def_level != 0 && (int64_t)h_counts[c] != n) any_null = true;
-  ctx->nulls_seen = any_null;
-  if (!any_null) {
-    if (!optimistic) return set_error(ctx, FLE_E_BUFFER, "column shorter than the rows requested");
-    if (!launch_first) return launch_eval(ctx, req.data(), ncols, nodes, nnodes, 0, n, bitmap_dev, count_dev);
-    return FLE_OK;
-  }
-
-  // 2b. NULLs present.  A NULL row yields 0 in every leaf, and the deposit through the not-null
+  // 0. (host only) A NULL row yields 0 in every leaf, and the deposit through the not-null
   // bitmap (IntersectBitset) is a bit-wise injection, so it distributes over AND and OR:
   // deposit(a) op deposit(b) == deposit(a op b).  Every maximal subtree whose leaves sit on ONE
   // nullable column is therefore evaluated as one fused program in the data-ordinal domain and
-  // deposited once -- straight from the column's def-level planes (launch_deposit: no not-null bitmap is
+  // deposited once -- straight from the column's def-level planes (no not-null bitmap is
   // built); every maximal subtree over required columns only is one fused program over the rows.
   constexpr int kReq = -1, kMixed = -2;
   std::vector<int> node_start(nnodes, 0), node_cls(nnodes, kMixed);
@@ -246,6 +210,89 @@ static int eval_dev_nullable(fle_ctx* ctx, const fle_col_desc* cols, int ncols,
       else if (join_op != op) uniform = false;
     }
   }
+  // the one-kernel NULL path (fle_null_chain.cu): one operator throughout, every subtree one pass on one column
+  NullChainPlan plan;
+  bool chain = false;
+  if (ctx->null_fused >= 2 && uniform && bitmap_dev && !subs.empty() && (int)subs.size() <= kNcMaxCols) {
+    chain = true;
+    plan.ncols = (int)subs.size();
+    plan.join_op = join_op == FLE_OP_OR ? FOLD_OR : FOLD_AND;
+    for (size_t k = 0; k < subs.size() && chain; ++k) {
+      const int s0 = subs[k].first, s1 = subs[k].second;
+      int col = node_cls[s1];
+      if (col == kReq) {  // a required subtree: exactly one column
+        for (int i = s0; i <= s1; ++i) {
+          if (nodes[i].op == FLE_OP_AND || nodes[i].op == FLE_OP_OR) continue;
+          if (col == kReq) col = nodes[i].col;
+          else if (col != nodes[i].col) chain = false;
+        }
+      }
+      if (!chain || col < 0) { chain = false; break; }
+      if ((reinterpret_cast<uintptr_t>(cols[col].planes) & 15) || cols[col].bit_width < 1) { chain = false; break; }
+      if (cols[col].max_def_level == 0 && cols[col].bytes < (uint64_t)nwords * (uint64_t)cols[col].bit_width * 8u) { chain = false; break; }
+      plan.col[k] = col;
+      if (null_chain_pass(ctx, cols[col], nodes + s0, s1 - s0 + 1, &plan.pd[k]) != FLE_OK) chain = false;
+    }
+  }
+  // 1. non-null rows per column (one launch, nothing written but the counts -- and, when the program is a chain the
+  // one-kernel NULL path can take, the per-tile counts that path starts from) ...
+  constexpr size_t kCountsBytes = 256;
+  const int64_t ntiles = null_chain_tiles(n);
+  const size_t sums_stride = ((size_t)ntiles + 1 + 31) / 32 * 32;  // entries per column
+  uint8_t* scratch = null_scratch(ctx, kCountsBytes + (chain ? (size_t)ncols * sums_stride * 12 : 0));
+  if (!scratch) return set_error(ctx, FLE_E_NOMEM, "scratch of the NULL path");
+  uint64_t* d_counts = reinterpret_cast<uint64_t*>(scratch);
+  uint64_t* d_pref = reinterpret_cast<uint64_t*>(scratch + kCountsBytes);  // [ncols][sums_stride] prefixes, then the counts
+  uint32_t* d_sums = reinterpret_cast<uint32_t*>(d_pref + (size_t)ncols * sums_stride);
+  int rc = chain ? launch_def_tile_counts(ctx, cols, ncols, n, d_counts, d_sums, sums_stride)
+                 : launch_def_counts(ctx, cols, ncols, n, d_counts);
+  if (rc != FLE_OK) return rc;
+  // 2a. ... and, without waiting for them, the fused kernel over the columns as if they were
+  // required: with no NULL anywhere (TPC-H; Impala's writer marks every column OPTIONAL) the data
+  // ordinal IS the row index and this is the answer.  (Skipped when a data stream is too short to
+  // hold n values -- then there are NULLs for sure.)
+  std::vector<fle_col_desc> req(cols, cols + ncols);
+  for (auto& d : req) { d.max_def_level = 0; d.def_planes = nullptr; d.def_bytes = 0; }
+  bool optimistic = true;
+  for (int c = 0; c < ncols; ++c)
+    if (cols[c].bytes < (uint64_t)nwords * (uint64_t)cols[c].bit_width * 8u) optimistic = false;
+  // (a context whose previous nullable call DID find NULLs -- a file that has them usually has them in every row
+  //  group -- launches the NULL path right away when it is the one-kernel chain, which is correct with or without
+  //  NULLs and needs nothing from the host; else it waits for the counts instead of launching a scan it would throw away)
+  const bool launch_first = optimistic && !ctx->nulls_seen;
+  const bool chain_first = chain && !launch_first;
+  if (launch_first) {
+    rc = launch_eval(ctx, req.data(), ncols, nodes, nnodes, 0, n, bitmap_dev, count_dev);
+    if (rc != FLE_OK) return rc;
+  } else if (chain_first) {
+    rc = launch_null_chain(ctx, plan, cols, n, d_sums, d_pref, sums_stride, bitmap_dev, count_dev);
+    if (rc != FLE_OK) return rc;
+  }
+  std::vector<uint64_t> h_counts(ncols, 0);
+  FLE_CUDA_TRY(ctx, cudaMemcpyAsync(h_counts.data(), d_counts, (size_t)ncols * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  FLE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  bool any_null = false;
+  for (int c = 0; c < ncols; ++c)
+    if (cols[c].max_def_level != 0 && (int64_t)h_counts[c] != n) any_null = true;
+  ctx->nulls_seen = any_null;
+  if (chain && (chain_first || any_null)) {
+    // (the kernel never reads past a column buffer; a stream too short for its non-null values is reported here)
+    for (int i = 0; i < plan.ncols; ++i) {
+      const fle_col_desc& col = cols[plan.col[i]];
+      const uint64_t vals = col.max_def_level != 0 ? h_counts[plan.col[i]] : (uint64_t)n;
+      if (col.bytes < (vals + 63) / 64 * (uint64_t)col.bit_width * 8u)
+        return set_error(ctx, FLE_E_BUFFER, "column shorter than its non-null values");
+    }
+    if (chain_first) return FLE_OK;
+    return launch_null_chain(ctx, plan, cols, n, d_sums, d_pref, sums_stride, bitmap_dev, count_dev);
+  }
+  if (!any_null) {
+    if (!optimistic) return set_error(ctx, FLE_E_BUFFER, "column shorter than the rows requested");
+    if (!launch_first) return launch_eval(ctx, req.data(), ncols, nodes, nnodes, 0, n, bitmap_dev, count_dev);
+    return FLE_OK;
+  }
+
+  // 2b. NULLs present, per column subtree (see the classification above)
   const bool fold = uniform && nreq <= 1 && bitmap_dev != nullptr;
   const size_t word_bytes = ((size_t)nwords * 8 + 255) / 256 * 256;
   const size_t need = kCountsBytes + word_bytes * (fold ? 1 : subs.size() + 1);
@@ -512,7 +559,8 @@ int fle_ctx_set_option(fle_ctx* ctx, const char* name, int64_t value) {
   else if (k == "eval_ctas_per_sm") ctx->eval_ctas_per_sm = (int)value;
   else if (k == "eval_gpt") ctx->eval_gpt = (int)value;
   else if (k == "in_lookup_min") ctx->in_lookup_min = (int)value;
-  else if (k == "null_fused") ctx->null_fused = value != 0;
+  else if (k == "null_fused") ctx->null_fused = (int)std::max<int64_t>(0, std::min<int64_t>(value, 2));
+  else if (k == "null_chain_ctas") ctx->null_chain_ctas = (int)std::max<int64_t>(0, value);
   else if (k == "in_mux_min") ctx->in_mux_min = (int)std::max<int64_t>(1, std::min<int64_t>(value, 1 << 30));
   else if (k == "in_wide") ctx->in_wide = (int)value;
   else if (k == "in_wide_warps") ctx->in_wide_warps = (int)value;
@@ -541,7 +589,8 @@ int64_t fle_ctx_get_option(fle_ctx* ctx, const char* name) {
   if (k == "eval_ctas_per_sm") return ctx->eval_ctas_per_sm;
   if (k == "eval_gpt") return ctx->eval_gpt;
   if (k == "in_lookup_min") return ctx->in_lookup_min;
-  if (k == "null_fused") return ctx->null_fused ? 1 : 0;
+  if (k == "null_fused") return ctx->null_fused;
+  if (k == "null_chain_ctas") return ctx->null_chain_ctas;
   if (k == "in_mux_min") return ctx->in_mux_min;
   if (k == "in_wide") return ctx->in_wide;
   if (k == "in_wide_warps") return ctx->in_wide_warps;

@@ -108,7 +108,9 @@ struct fle_ctx {
   uint64_t* d_split = nullptr;    // temporary bitmaps of regrouped programs (long IN lists), grow-only
   size_t split_cap = 0;           // bytes
   uint64_t* h_count = nullptr;    // pinned
-  bool null_fused = true;              // NULL path: single-pass subtrees evaluate + deposit in one kernel (option "null_fused")
+  int null_fused = 2;                  // NULL path (option "null_fused"): 0 data-domain bitmap, then deposit; 1 single-pass subtrees evaluate +
+                                       // deposit in one kernel per column; 2 a chain of such subtrees in ONE kernel (fle_null_chain.cu)
+  int null_chain_ctas = 0;             // CTAs of the chain kernel (0 = fill the device; tests pin 1-3 to walk the tile pipeline)
   bool nulls_seen = false;             // the previous nullable evaluation found NULLs (eval_dev_nullable)
   void* d_null = nullptr;              // temporaries of the NULL path (data-domain bitmaps, leaf bitmaps), grow-only
   size_t null_cap = 0;
@@ -225,6 +227,23 @@ int launch_deposit(fle_ctx* ctx, const uint64_t* def_planes_dev, int64_t n_root,
 // evaluated inside the deposit kernel -- no data-domain bitmap.  FLE_E_UNSUPPORTED: not a single supported pass.
 int launch_eval_deposit(fle_ctx* ctx, const fle_col_desc& col, const fle_pred_node* nodes, int nnodes, int64_t n_sub,
                         const uint64_t* def_planes_dev, int64_t n_root, uint64_t* out_dev, int comb_op, uint64_t* count_dev);
+// fle_null_chain.cu: a chain (one operator) of single-column single-pass subtrees over nullable / required columns
+// evaluated, deposited and folded in one kernel
+constexpr int kNcMaxCols = 4;
+struct NullChainPlan {
+  int ncols = 0;
+  int join_op = FOLD_AND;
+  int col[kNcMaxCols];      // index into the caller's column array
+  PassDesc pd[kNcMaxCols];  // the column's subtree as one pass
+};
+int64_t null_chain_tiles(int64_t n);
+int null_chain_pass(fle_ctx* ctx, const fle_col_desc& col, const fle_pred_node* nodes, int nnodes, PassDesc* out);
+// non-null rows per nullable column (counts_dev[c]) and per tile of 16384 rows (tile_sums_dev[c * stride + tile]), one launch
+int launch_def_tile_counts(fle_ctx* ctx, const fle_col_desc* cols, int ncols, int64_t n, uint64_t* counts_dev,
+                           uint32_t* tile_sums_dev, size_t sums_stride);
+// tile counts -> prefixes (pref_dev[c * stride + tile]), then the chain kernel
+int launch_null_chain(fle_ctx* ctx, const NullChainPlan& plan, const fle_col_desc* cols, int64_t n, const uint32_t* tile_sums_dev,
+                      uint64_t* pref_dev, size_t sums_stride, uint64_t* out_dev, uint64_t* count_dev);
 // fle_plain.cu
 int launch_realign(fle_ctx* ctx, const uint8_t* src_dev, size_t nbytes, uint8_t* dst_dev);
 int launch_plain_eval(fle_ctx* ctx, const void* values_dev, int elem_type, int64_t n, int op, const void* lits_host,

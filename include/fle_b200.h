@@ -137,6 +137,12 @@ int fle_ctx_sync(fle_ctx* ctx);
  * "codec_variant" (0 = direct loads/stores; 1 [default] = per-bit-width choice among the staged
  * unpack kernels; 2 = per-row bulk stores, 3 = warp-private copy-out, 4 = CTA-wide copy-out),
  * "codec_ctas_per_sm" (0 = auto), "h2d_chunk_rows",
+ * "null_fused" (nullable columns that DO hold NULLs, ColumnReader<T>::Eq..In + IntersectBitset,
+ * hdfs-parquet-scanner.cc:326-345: 2 [default] = a conjunct / disjunct chain of up to four column subtrees that
+ * are one pass each -- compares, BETWEENs, equalities; required columns may take part -- is evaluated, deposited
+ * through the def levels and folded in ONE kernel; 1 = one evaluate-and-deposit kernel per column subtree;
+ * 0 = data-domain bitmap, then deposit; programs a mode does not cover take the next one),
+ * "null_chain_ctas" (0 = fill the device; a test knob that pins the chain kernel's grid),
  * "reference_compat" (default 0; 1 reproduces the reference where this library deliberately differs:
  * a literal >= 2^bit_width keeps only its low bit_width bits, as in the reference's plane algebra,
  * instead of being folded to the constant the comparison means -- `x < 2^bw` is true for every code;

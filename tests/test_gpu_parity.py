@@ -243,7 +243,18 @@ def test_nullable_columns_vs_oracle(ctx, oracle, null_frac):
     prog2 = [(GE, 0, 730), (LE, 0, 1094), (AND, None, None), (EQ, 0, 5), (OR, None, None),
              (LT, 2, 10), (GT, 2, 40), (OR, None, None), (IN, 1, [3, 4, 20]), (AND, None, None), (AND, None, None)]
     prog3 = [(GE, 1, 3), (LE, 1, 9), (AND, None, None), (EQ, 1, 20), (OR, None, None)]
-    for pr in (prog, prog2, prog3):
+    # chains the one-kernel NULL path takes (null_fused = 2): two nullable BETWEENs AND a compare on the required
+    # column (the Q6 shape), an OR chain, a single leaf, the same nullable column twice, NOT BETWEEN, <= 4 compares
+    prog4 = [(GE, 0, 730), (LE, 0, 1094), (AND, None, None), (GE, 1, 3), (LE, 1, 9), (AND, None, None), (AND, None, None),
+             (LT, 2, 23), (AND, None, None)]
+    prog5 = [(EQ, 0, 5), (LT, 1, 7), (OR, None, None), (GT, 2, 40), (OR, None, None)]
+    prog6 = [(LT, 0, 100)]
+    prog7 = [(LT, 0, 2000), (GE, 1, 3), (AND, None, None), (GT, 0, 10), (AND, None, None)]
+    prog8 = [(LT, 0, 730), (GT, 0, 1094), (OR, None, None), (LE, 1, 20), (AND, None, None)]
+    prog9 = [(GT, 1, 2), (LT, 1, 20), (AND, None, None), (GE, 1, 4), (AND, None, None), (LE, 1, 18), (AND, None, None),
+             (GE, 2, 1), (AND, None, None)]
+    chains = (prog4, prog5, prog6, prog7, prog8, prog9)
+    for pr in (prog, prog2, prog3) + chains:
         st = []
         for op, ci, lits in pr:
             if op <= IN:
@@ -251,14 +262,22 @@ def test_nullable_columns_vs_oracle(ctx, oracle, null_frac):
             else:
                 b = st.pop()
                 st[-1] = st[-1] & b if op == AND else st[-1] | b
-        # single-pass subtrees evaluate + deposit in one kernel (default) / data-domain bitmap, then deposit
-        for fused in (1, 0):
+        # a chain of single-pass subtrees in one kernel (default; the grid pinned to 1 / 3 CTAs walks the tile pipeline) /
+        # single-pass subtrees evaluate + deposit in one kernel per column / data-domain bitmap, then deposit;
+        # twice each: the second call knows that the file holds NULLs and does not launch the optimistic scan
+        for fused, ctas in ((2, 0), (2, 1), (2, 3), (1, 0), (0, 0)):
             ctx.set_option("null_fused", fused)
+            ctx.set_option("null_chain_ctas", ctas)
             try:
-                bm, cnt = ctx.eval(cols, pr, n)
+                for rep in range(2):
+                    l0 = ctx.launch_count
+                    bm, cnt = ctx.eval(cols, pr, n)
+                    assert (bm == st[0]).all() and cnt == popcount(st[0]), (pr, fused, ctas)
+                    if fused == 2 and rep == 1 and null_frac > 0 and pr in chains:
+                        assert ctx.launch_count - l0 == 3, (pr, ctx.launch_count - l0)  # tile counts, prefixes, the chain
             finally:
-                ctx.set_option("null_fused", 1)
-            assert (bm == st[0]).all() and cnt == popcount(st[0]), (pr, fused)
+                ctx.set_option("null_fused", 2)
+                ctx.set_option("null_chain_ctas", 0)
 
 
 # ------------------------------------------------------------------------------------------

@@ -36,6 +36,18 @@ if case == "q6":
             (AND, None, None), (LT, 2, 23), (AND, None, None)]
     for _ in range(reps):
         ctx.eval_dev(cols, prog, n, bitmap=bm, count=cnt)
+elif case == "q6nulls":
+    # Q6 over three OPTIONAL columns with 2 % NULLs each (the NULL path: tile counts, prefixes, chain kernel)
+    cols = []
+    for d, bw in ((2526, 12), (11, 4), (50, 6)):
+        nn = torch.rand(n, generator=g, device="cuda") >= 0.02
+        data = torch.randint(0, d, (int(nn.sum().item()),), generator=g, device="cuda", dtype=torch.int64).to(torch.int32)
+        cols.append((ctx.pack_dev(data, bw), bw, ctx.pack_dev(nn.to(torch.int32), 1)))
+        del nn, data
+    prog = [(GE, 0, 730), (LE, 0, 1094), (AND, None, None), (GE, 1, 5), (LE, 1, 7), (AND, None, None),
+            (AND, None, None), (LT, 2, 23), (AND, None, None)]
+    for _ in range(reps):
+        ctx.eval_dev(cols, prog, n, bitmap=bm, count=cnt)
 elif case == "q6agg":
     cols = [(col(2526, 12)[1], 12), (col(11, 4)[1], 4), (col(50, 6)[1], 6)]
     prog = [(GE, 0, 730), (LE, 0, 1094), (AND, None, None), (GE, 1, 5), (LE, 1, 7), (AND, None, None),

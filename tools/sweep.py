@@ -247,14 +247,22 @@ def sweep_nulls(ctx, out, n):
     prog = [(GE, 0, 730), (LE, 0, 1094), (AND, None, None), (GE, 1, 5), (LE, 1, 7), (AND, None, None),
             (AND, None, None), (LT, 2, 23), (AND, None, None)]
     prep = (ctx.make_col_descs(pc),) + fle_b200.capi._build_program(prog)
-    l0 = ctx.launch_count
-    ctx.eval_dev(pc, prog, n, bitmap=bm, count=cnt, prepared=prep)
-    torch.cuda.synchronize()
-    per_call = ctx.launch_count - l0
-    assert int(cnt.item()) == int(want.sum().item()), "Q6 with NULLs: count differs from the torch compare"
-    mn, md = timeit(lambda: ctx.eval_dev(pc, prog, n, bitmap=bm, count=cnt, prepared=prep), working_set=by)
-    rec(out, what="program", name="q6_optional_cols_2pct_nulls", variant="1j", rows=n, sum_bw=25, ms_min=mn, ms_med=md,
-        alg_bytes=by, rows_per_s=n / (mn * 1e-3), count=int(cnt.item()), launches_per_call=per_call)
+    wantbm = None
+    for mode, label in ((2, "q6_optional_cols_2pct_nulls"), (1, "q6_optional_cols_2pct_nulls_per_column_kernels")):
+        ctx.set_option("null_fused", mode)
+        ctx.eval_dev(pc, prog, n, bitmap=bm, count=cnt, prepared=prep)  # (the first call learns that the file holds NULLs)
+        l0 = ctx.launch_count
+        ctx.eval_dev(pc, prog, n, bitmap=bm, count=cnt, prepared=prep)
+        torch.cuda.synchronize()
+        per_call = ctx.launch_count - l0
+        assert int(cnt.item()) == int(want.sum().item()), "Q6 with NULLs: count differs from the torch compare"
+        if wantbm is None:
+            wantbm = bm.clone()
+        assert bool((bm == wantbm).all()), "Q6 with NULLs: the two NULL paths disagree"
+        mn, md = timeit(lambda: ctx.eval_dev(pc, prog, n, bitmap=bm, count=cnt, prepared=prep), working_set=by)
+        rec(out, what="program", name=label, variant="1j", rows=n, sum_bw=25, ms_min=mn, ms_med=md,
+            alg_bytes=by, rows_per_s=n / (mn * 1e-3), count=int(cnt.item()), launches_per_call=per_call)
+    ctx.set_option("null_fused", 2)
 
 
 def sweep_tune(ctx, out, n):
