@@ -34,9 +34,9 @@ namespace fle {
 
 constexpr int kNcThreads = 256;  // one row word per thread and tile
 constexpr int kNcWords = 256;    // row words per tile (16384 rows)
-constexpr int kNcSeg = 34;       // staged groups per segment: 8 segments hold the <= 258 groups of a tile (even: every
-                                 // segment starts on a 16-byte boundary for odd bit widths as well)
-constexpr int kNcGroups = 8 * kNcSeg;
+constexpr int kNcSeg = 32;       // staged groups per segment: thread (seg, j) evaluates group seg * 32 + j; a tile whose rows are
+constexpr int kNcOver = 4;       // (nearly) all present spans up to 258 groups: the last ones go to a small overflow segment
+constexpr int kNcGroups = 8 * kNcSeg + kNcOver + 12;  // result words per column (+ slack for the funnel's second word)
 constexpr int kNcStages = 2;
 
 struct NcCol {
@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(kNcThreads + 32) null_chain_kernel(const __gri
       mbar_arrive_expect_tx(bar, (uint32_t)nb * gbytes);
       const uint8_t* src = reinterpret_cast<const uint8_t*>(C.planes) + (uint64_t)M.gfirst * gbytes;
       const uint32_t dst = smem0 + stage * P.stage_bytes + C.col_off;
-      for (int s = 0; s < 8; ++s) {
+      for (int s = 0; s < 9; ++s) {  // (segment 8 = the overflow segment, right behind the eighth)
         const int g0 = s * kNcSeg;
         if (g0 >= nb) break;
         const int cnt = min(kNcSeg, nb - g0);
@@ -421,6 +421,7 @@ __global__ void __launch_bounds__(kNcThreads + 32) null_chain_kernel(const __gri
 
   // ---- consumers ----
   const uint32_t seg = tid & 7, jrow = tid >> 3;
+  const uint32_t lm0 = smem_u32(&lit_masks[0][0]);
   auto load_raw = [&](int64_t tile, uint64_t (&raw)[NC]) {  // plane words of the def levels, as they lie in memory
     const int64_t w = tile * kNcWords + tid;
 #pragma unroll
@@ -454,7 +455,7 @@ __global__ void __launch_bounds__(kNcThreads + 32) null_chain_kernel(const __gri
           const NcMeta& M = meta[k & 3][c];
           const int q = M.ng - 1;
           if ((uint32_t)lane < C.bw)
-            sts64(smem0 + cur * P.stage_bytes + C.col_off + (q / kNcSeg) * C.seg_stride + (q % kNcSeg) * C.bw * 8u + lane * 8u,
+            sts64(smem0 + cur * P.stage_bytes + C.col_off + (q >> 5) * C.seg_stride + (q & 31) * C.bw * 8u + lane * 8u,
                   C.planes[(M.gfirst + q) * C.bw + lane]);
         }
       }
@@ -484,10 +485,25 @@ __global__ void __launch_bounds__(kNcThreads + 32) null_chain_kernel(const __gri
         const uint32_t gbytes = C.bw * 8u;
         const uint32_t base = smem0 + cur * P.stage_bytes + C.col_off + seg * C.seg_stride;
         const uint32_t res = smem0 + C.res_off;
-        const uint32_t maddr = smem_u32(&lit_masks[c][0]);
-        for (uint32_t j = jrow; j < (uint32_t)kNcSeg; j += kNcThreads / 8) {
-          const int q = (int)(seg * kNcSeg + j);
-          if (q < ng) sts64(res + q * 8u, __brevll(nc_run_pass(C.pd, C.bw, base + j * gbytes, maddr)));
+        const uint32_t maddr = lm0 + c * (32 * 4 * 4);
+        {
+          const int q = (int)(seg * kNcSeg + jrow);
+          if (q < ng) sts64(res + q * 8u, __brevll(nc_run_pass(C.pd, C.bw, base + jrow * gbytes, maddr)));
+        }
+        if (ng > 8 * kNcSeg && tid < ng - 8 * kNcSeg)  // overflow segment: a tile with (nearly) no NULL at all
+          sts64(res + (8 * kNcSeg + tid) * 8u,
+                __brevll(nc_run_pass(C.pd, C.bw, smem0 + cur * P.stage_bytes + C.col_off + 8 * C.seg_stride + tid * gbytes, maddr)));
+        // the warps' totals -> exclusive prefixes, in place (warp c for column c; phase D reads one word per thread)
+        if (warp == c) {
+          const uint32_t wa = smem_u32(&warp_tot[cur][c][0]) + (lane & 7) * 4u;
+          const uint32_t v = lds32(wa);
+          uint32_t incl = v;
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((lane & 7) >= o) incl += y;
+          }
+          if (lane < 8) asm volatile("st.shared.b32 [%0], %1;" ::"r"(wa), "r"(incl - v) : "memory");
         }
       }
     }
@@ -499,12 +515,7 @@ __global__ void __launch_bounds__(kNcThreads + 32) null_chain_kernel(const __gri
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         if (c < P.ncols) {
-          uint32_t t[8];
-          lds128u(smem_u32(&warp_tot[cur][c][0]), t[0], t[1], t[2], t[3]);
-          lds128u(smem_u32(&warp_tot[cur][c][4]), t[4], t[5], t[6], t[7]);
-          uint32_t lr = (uint32_t)meta[k & 3][c].lr0 + excl[c];
-#pragma unroll
-          for (int x = 0; x < 7; ++x) lr += x < warp ? t[x] : 0u;
+          const uint32_t lr = (uint32_t)meta[k & 3][c].lr0 + excl[c] + warp_tot[cur][c][warp];
           const uint32_t res = smem0 + P.col[c].res_off;
           const uint32_t m0 = (uint32_t)m[c], m1 = (uint32_t)(m[c] >> 32);
           const uint32_t lr1 = lr + __popc(m0);
@@ -632,7 +643,7 @@ int launch_null_chain(fle_ctx* ctx, const NullChainPlan& plan, const fle_col_des
     }
     C.col_off = off;
     C.seg_stride = ((uint32_t)kNcSeg * C.bw * 8u + 127u) / 128u * 128u + 16u;
-    off += (8u * C.seg_stride + 127u) / 128u * 128u;
+    off += (8u * C.seg_stride + (uint32_t)kNcOver * C.bw * 8u + 127u) / 128u * 128u;
   }
   P.stage_bytes = off;
   uint32_t roff = (uint32_t)kNcStages * P.stage_bytes;
