@@ -17,6 +17,7 @@
 //                        dictionary value (DictDecoder::GetValue, dict-encoding.h:321-330) -> slot at its
 //                        tuple offset (ReadSlot, hdfs-parquet-scanner.cc:515-531), column by column as
 //                        :1151-1168 does -- select + gather + lookup + tuple layout in one pass.
+#include "fle_bitmap.cuh"
 #include "fle_device.cuh"
 #include "fle_internal.h"
 
@@ -32,6 +33,8 @@ struct PageRefDev {
   int64_t groups;
   int64_t rows;            // rows of the page (def-level count)
   int32_t src_bw, dst_bw;
+  int64_t data_groups;     // expand: groups the page's data stream holds (non-null values only)
+  int32_t expand, pad;
 };
 
 constexpr int kGatherGroupsPerCta = 256;
@@ -59,7 +62,51 @@ pages_gather_kernel(const PageRefDev* __restrict__ refs, unsigned long long* __r
   const int64_t nalive = max((int64_t)1, (R.groups + kGatherGroupsPerCta - 1) / kGatherGroupsPerCta);
   if ((int64_t)blockIdx.x >= nalive) return;
   const int64_t ng = min((int64_t)kGatherGroupsPerCta, R.groups - g0);
-  if (ng > 0) {
+  if (R.expand) {
+    // The page's data stream is indexed by non-null ordinal: row word w of the page takes the popcount(def word)
+    // values that start at rank(w) = defined rows before it, spread over the word's defined rows; NULL rows read as
+    // code 0.  One thread per row word; the ranks come from the page's own definition levels (a CTA counts the words
+    // in front of its 256: pages are a few thousand words).
+    __shared__ uint64_t warp_buf[8];
+    __shared__ uint32_t warp_scan[8];
+    auto def_at = [&](int64_t w) -> uint64_t {  // plane order (row k of the word at bit 63 - k), rows past the page cleared
+      if (w >= R.groups) return 0ull;
+      const uint64_t d = load_u64_unaligned(R.def_src + w * 8);
+      const int64_t left = R.rows - w * 64;
+      return left >= 64 ? d : (left <= 0 ? 0ull : (d & (~0ull << (64 - left))));
+    };
+    uint64_t pre = 0;
+    for (int64_t j = threadIdx.x; j < g0; j += 256) pre += __popcll(def_at(j));
+    const uint64_t rank0 = block_sum<256>(pre, warp_buf);
+    const int64_t w = g0 + threadIdx.x;
+    const uint64_t d = def_at(w);
+    const uint32_t mine = __popcll(d);
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((threadIdx.x & 31) >= o) incl += y;
+    }
+    if ((threadIdx.x & 31) == 31) warp_scan[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int x = 0; x < (int)(threadIdx.x >> 5); ++x) woff += warp_scan[x];
+    if (w < R.groups) {
+      const int64_t rank = (int64_t)rank0 + woff + (incl - mine);
+      const int64_t dg = rank >> 6;
+      const int sh = (int)(rank & 63);
+      const uint64_t mask_r = __brevll(d);  // row order
+      const int sbw = R.src_bw, dbw = R.dst_bw;
+      uint64_t* out = R.dst + (uint64_t)w * dbw;
+      for (int i = 0; i < sbw; ++i) {
+        const uint64_t a = (mine && dg < R.data_groups) ? load_u64_unaligned(R.src + ((uint64_t)dg * sbw + i) * 8u) : 0ull;
+        const uint64_t b = (mine && sh && dg + 1 < R.data_groups) ? load_u64_unaligned(R.src + ((uint64_t)(dg + 1) * sbw + i) * 8u) : 0ull;
+        const uint64_t top = sh ? ((a << sh) | (b >> (64 - sh))) : a;  // ordinal rank + q at bit 63 - q
+        out[i] = __brevll(deposit_bits(__brevll(top), mask_r));
+      }
+      for (int i = sbw; i < dbw; ++i) out[i] = 0ull;
+    }
+  } else if (ng > 0) {
     const int sbw = R.src_bw, dbw = R.dst_bw;
     const uint8_t* s = R.src + (uint64_t)g0 * sbw * 8u;
     uint64_t* d = R.dst + (uint64_t)g0 * dbw;
@@ -105,9 +152,11 @@ int launch_pages_gather(fle_ctx* ctx, const fle_page_ref* refs, int nrefs, uint6
     const fle_page_ref& r = refs[i];
     if (r.src_bit_width < 1 || r.src_bit_width > 32 || r.dst_bit_width < r.src_bit_width || r.dst_bit_width > 32)
       return set_error(ctx, FLE_E_INVALID, "page bit widths outside 1..32 or destination narrower than the page");
-    if (r.groups < 0 || r.rows < 0 || (r.groups > 0 && (!r.src_dev || !r.dst_dev)))
+    if (r.groups < 0 || r.rows < 0 || (r.groups > 0 && ((!r.src_dev && !(r.expand && r.src_bytes == 0)) || !r.dst_dev)))
       return set_error(ctx, FLE_E_INVALID, "bad page reference");
-    if ((uint64_t)r.groups * (uint64_t)r.src_bit_width * 8u > r.src_bytes)
+    if (r.expand && !r.def_src_dev) return set_error(ctx, FLE_E_INVALID, "a page is expanded through its definition levels");
+    if (r.expand && r.groups != (r.rows + 63) / 64) return set_error(ctx, FLE_E_INVALID, "an expanded page has one group per 64 rows");
+    if (!r.expand && (uint64_t)r.groups * (uint64_t)r.src_bit_width * 8u > r.src_bytes)
       return set_error(ctx, FLE_E_BUFFER, "page shorter than its groups");
     if (r.def_src_dev && (uint64_t)((r.rows + 63) / 64) * 8u > r.def_bytes)
       return set_error(ctx, FLE_E_BUFFER, "definition levels shorter than the page's rows");
@@ -119,6 +168,9 @@ int launch_pages_gather(fle_ctx* ctx, const fle_page_ref* refs, int nrefs, uint6
     h[i].rows = r.rows;
     h[i].src_bw = r.src_bit_width;
     h[i].dst_bw = r.dst_bit_width;
+    h[i].expand = r.expand ? 1 : 0;
+    h[i].pad = 0;
+    h[i].data_groups = (int64_t)(r.src_bytes / ((uint64_t)r.src_bit_width * 8u));
     max_groups = std::max(max_groups, r.groups);
   }
   const uint32_t* d = nullptr;
@@ -148,6 +200,8 @@ struct SlotDev {  // one materialised column
   const uint64_t* planes;
   const void* dict;
   int32_t bw, ndict, slot_size, tuple_off;
+  const uint64_t* def;  // optional 1-bit definition levels, row-aligned
+  int32_t null_off, pad;
 };
 
 struct TileScanParams {
@@ -272,6 +326,10 @@ __global__ void __launch_bounds__(kTileThreads) tile_scan_kernel(const __grid_co
             for (int q = 0; q < P.tuple_size; q += 8) *reinterpret_cast<uint64_t*>(t + q) = 0ull;  // null indicators + padding
             for (int c = 0; c < P.ncols; ++c) {
               const SlotDev& S = P.cols[c];
+              if (S.def && !((ldg_gather64(S.def + (r >> 6)) >> (63 - (r & 63))) & 1ull)) {  // NULL: tuple->SetNull
+                t[S.null_off] = 1;
+                continue;
+              }
               const uint32_t code = code_of_row(S.planes, S.bw, r);
               if (code >= (uint32_t)S.ndict) {  // DictDecoder::GetValue() == false (dict-encoding.h:325)
                 atomicAdd(P.bad_codes, 1ull);
@@ -384,6 +442,12 @@ int launch_assemble(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nrows, con
     P.cols[c].ndict = s.ndict;
     P.cols[c].slot_size = s.slot_size;
     P.cols[c].tuple_off = s.tuple_offset;
+    if (s.def_planes_dev) {
+      if (reinterpret_cast<uintptr_t>(s.def_planes_dev) & 7) return set_error(ctx, FLE_E_ALIGN, "def_planes must be 8-byte aligned");
+      if (s.null_offset < 0 || s.null_offset >= tuple_size) return set_error(ctx, FLE_E_INVALID, "NULL indicator outside the tuple");
+      P.cols[c].def = static_cast<const uint64_t*>(s.def_planes_dev);
+      P.cols[c].null_off = s.null_offset;
+    }
   }
   FLE_CUDA_TRY(ctx, cudaMemsetAsync(bad_codes_dev, 0, 8, ctx->stream));
   if (nrows == 0) {

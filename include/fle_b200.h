@@ -299,7 +299,15 @@ typedef struct fle_page_ref {
   int64_t groups;           /* 64-row groups of the page */
   const void* def_src_dev;  /* optional: the page's definition levels (FLE, bit width 1), any alignment */
   uint64_t def_bytes;
-  int64_t rows;             /* rows of the page (only used for the definition-level count) */
+  int64_t rows;             /* rows of the page (definition-level count; expansion) */
+  int32_t expand;           /* 1 (needs def_src_dev): the page's FLE section holds only the NON-NULL values
+                             * (hdfs-parquet-scanner.cc:886-921: data values are indexed by non-null ordinal); dst
+                             * receives one group slot per 64 ROWS -- groups = ceil(rows / 64) -- with the value of every
+                             * defined row at the row's position and code 0 at NULL rows, so that the page joins a
+                             * row-aligned plane array the fused kernels scan like a required column (the definition
+                             * levels, gathered as a 1-bit column of their own, say which rows are NULL); src_bytes may
+                             * then be shorter than groups * src_bit_width * 8, even 0 for an all-NULL page */
+  int32_t reserved;
 } fle_page_ref;
 /* Re-bases the FLE sections of all pages (of all columns) of a row group onto aligned plane arrays
  * in ONE launch -- consecutive pages of a column go to consecutive dst ranges, so the column becomes one
@@ -316,6 +324,11 @@ typedef struct fle_slot_desc {
   const void* dict_dev;    /* ndict dictionary values of slot_size bytes (DictDecoder<T>::dict_) */
   int32_t ndict;
   int32_t tuple_offset;    /* byte offset of the slot inside a tuple */
+  const void* def_planes_dev; /* optional: the column's definition levels as 1-bit FLE planes aligned with the rows
+                               * (8-byte aligned); a selected row whose level is 0 gets tuple[null_offset] = 1 and its
+                               * slot stays zero (ReadSlot's tuple->SetNull, hdfs-parquet-scanner.cc:515-531) */
+  int32_t null_offset;     /* byte offset of the column's NULL indicator inside a tuple */
+  int32_t reserved;
 } fle_slot_desc;
 /* Replaces the materialisation loop of AssembleRows (hdfs-parquet-scanner.cc:1134-1180: skip-distance
  * list, then ReadValue(skip) -> DictDecoder<T>::GetValue -> FleDecoder::Get(T*, skip) per survivor and

@@ -134,3 +134,105 @@ def test_assemble_rows(ctx, oracle, slot_sizes):
         want[:, o:o + ss] = v.view(np.uint8).reshape(k, ss)
     assert int(bad.item()) == bad_want
     assert (got == want).all()
+
+
+@pytest.mark.parametrize("null_frac", [0.0, 0.03, 0.5, 1.0])
+def test_pages_gather_expands_null_pages(ctx, oracle, null_frac):
+    """Pages whose FLE section holds only the non-null values (hdfs-parquet-scanner.cc:886-921) are expanded into
+    row-aligned planes: the value at every defined row, code 0 at NULL rows; the definition levels travel as a 1-bit
+    column of their own.  Ragged last page, per-page widths, odd offsets, an all-NULL page without a data section."""
+    import torch
+    rng = np.random.default_rng(int(null_frac * 100) + 3)
+    page_rows = [64 * 300, 64 * 1100, 64 * 2, 64 * 120 + 37]
+    page_bw = [3, 5, 6, 7]
+    dst_bw = 7
+    blob = bytearray()
+    refs, want_rows, want_def = [], [], []
+    for pi, (rows, bw) in enumerate(zip(page_rows, page_bw)):
+        defs = rng.random(rows) >= null_frac if null_frac < 1.0 else np.zeros(rows, dtype=bool)
+        if pi == 2 and null_frac > 0:
+            defs[:] = False  # an all-NULL page: no width byte, no data (hdfs-parquet-scanner.cc:921)
+        vals = rng.integers(0, 1 << bw, size=int(defs.sum())).astype(np.uint32)
+        full = np.zeros(rows, dtype=np.uint32)
+        full[defs] = vals
+        want_rows.append(full)
+        want_def.append(defs)
+        dwords = oracle.pack(defs.astype(np.uint32), 1)
+        blob += bytes(rng.integers(0, 255, size=int(rng.integers(17, 40)), dtype=np.uint8))
+        blob += np.int32(dwords.nbytes).tobytes()
+        def_off = len(blob)
+        blob += dwords.tobytes()
+        data_off, data_bytes = len(blob), 0
+        if len(vals):
+            words = oracle.pack(vals, bw)
+            blob += bytes([bw])
+            data_off, data_bytes = len(blob), words.nbytes
+            blob += words.tobytes()
+        refs.append(dict(src_off=data_off, src_bytes=data_bytes, src_bit_width=bw, groups=(rows + 63) // 64,
+                         def_off=def_off, def_bytes=dwords.nbytes, rows=rows))
+    blob += bytes(16)
+    dblob = torch.from_numpy(np.frombuffer(bytes(blob), dtype=np.uint8).copy()).cuda()
+    total_groups = sum(r["groups"] for r in refs)
+    planes = torch.full((total_groups * dst_bw,), -1, dtype=torch.int64, device="cuda")
+    dplanes = torch.full((total_groups,), -1, dtype=torch.int64, device="cuda")
+    g0, crefs = 0, []
+    for r in refs:
+        crefs.append(dict(src_dev=dblob.data_ptr() + r["src_off"], src_bytes=r["src_bytes"], src_bit_width=r["src_bit_width"],
+                          dst_bit_width=dst_bw, dst_dev=planes.data_ptr() + g0 * dst_bw * 8, groups=r["groups"],
+                          def_src_dev=dblob.data_ptr() + r["def_off"], def_bytes=r["def_bytes"], rows=r["rows"], expand=1))
+        # the definition levels themselves: a 1-bit page copied as it is
+        crefs.append(dict(src_dev=dblob.data_ptr() + r["def_off"], src_bytes=r["def_bytes"], src_bit_width=1, dst_bit_width=1,
+                          dst_dev=dplanes.data_ptr() + g0 * 8, groups=r["groups"], rows=r["rows"]))
+        g0 += r["groups"]
+    nulls = ctx.pages_gather_dev(crefs)
+    torch.cuda.synchronize()
+    assert int(nulls.item()) == sum(int((~d).sum()) for d in want_def)
+    got = planes.cpu().numpy().view(np.uint64)
+    gotd = dplanes.cpu().numpy().view(np.uint64)
+    g0 = 0
+    for r, full, defs in zip(refs, want_rows, want_def):
+        dec = oracle.unpack(got[g0 * dst_bw:(g0 + r["groups"]) * dst_bw], dst_bw, 0, len(full))
+        assert (dec == full).all()
+        dd = oracle.unpack(gotd[g0:g0 + r["groups"]], 1, 0, len(full))
+        assert (dd == defs.astype(np.uint32)).all()
+        g0 += r["groups"]
+
+
+def test_assemble_rows_null_indicators(ctx, oracle):
+    """A selected row that is NULL in a materialised column gets its NULL indicator set and a zero slot
+    (ReadSlot -> tuple->SetNull, hdfs-parquet-scanner.cc:515-531)."""
+    import torch
+    rng = np.random.default_rng(5)
+    n = 64 * 3000 + 5
+    sel = rng.random(n) < 0.05
+    words = np.packbits(np.concatenate([sel, np.zeros((-n) % 64, dtype=bool)]), bitorder="little").view(np.uint64)
+    bm = torch.from_numpy(words.view(np.int64).copy()).cuda()
+    slots, keep, cols = [], [], []
+    tuple_size = 16  # [null byte x 2][pad][int32 at 4][int64 at 8]
+    for c, (ss, off, dt) in enumerate(((4, 4, np.int32), (8, 8, np.int64))):
+        bw = 9 + c
+        codes = rng.integers(0, 1 << bw, size=n).astype(np.uint32)
+        defs = rng.random(n) >= (0.3 if c == 0 else 0.0)
+        codes[~defs] = 0  # row-aligned planes as fle_pages_gather_dev (expand) leaves them
+        d = rng.integers(-1000, 1000, size=1 << bw).astype(dt)
+        planes = torch.from_numpy(oracle.pack(codes, bw).view(np.int64)).cuda()
+        dplanes = torch.from_numpy(oracle.pack(defs.astype(np.uint32), 1).view(np.int64)).cuda()
+        dd = torch.from_numpy(d).cuda()
+        keep += [planes, dplanes, dd]
+        slots.append(dict(planes_dev=planes.data_ptr(), bytes=planes.numel() * 8, bit_width=bw, slot_size=ss, dict_dev=dd.data_ptr(),
+                          ndict=1 << bw, tuple_offset=off, def_planes_dev=dplanes.data_ptr() if c == 0 else None, null_offset=c))
+        cols.append((codes, defs, d, off, ss))
+    k = int(sel.sum())
+    tuples, cnt, bad = ctx.assemble_rows_dev(bm, n, slots, tuple_size, k)
+    torch.cuda.synchronize()
+    assert int(cnt.item()) == k and int(bad.item()) == 0
+    got = tuples.cpu().numpy()[:k]
+    rows = np.nonzero(sel)[0]
+    want = np.zeros((k, tuple_size), dtype=np.uint8)
+    for c, (codes, defs, d, off, ss) in enumerate(cols):
+        v = d[codes[rows]].copy()
+        if c == 0:
+            v[~defs[rows]] = 0
+            want[:, c] = (~defs[rows]).astype(np.uint8)
+        want[:, off:off + ss] = v.view(np.uint8).reshape(k, ss)
+    assert (got == want).all()
