@@ -90,7 +90,8 @@ class HdfsParquetScanner {
 
   HdfsParquetScanner() : tuple_size_(0), fused_enabled_(true), fused_pos_(0), fused_rows_(0),
       fused_evals_(0), leaf_windows_(0), device_materialise_(true), device_spans_(0),
-      row_group_batch_(true), batch_state_(0), batch_bank_(0), batch_rows_(0), row_group_batches_(0) {}
+      row_group_batch_(true), batch_state_(0), batch_bank_(0), batch_rows_(0), row_group_batches_(0),
+      batch_ncols_nulls_(0), batch_nulls_seen_(false), row_group_null_batches_(0) {}
   ~HdfsParquetScanner();
 
   // CreateColumnReaders/CreateReader (:1410-1451, :670-720) + InitColumns (:1453-1531) for
@@ -178,6 +179,7 @@ class HdfsParquetScanner {
     void* image_dev;          // the uploaded column-chunk image(s)
     void* planes_dev;         // groups * bit_width * 8 bytes, filled by fle_pages_gather_dev
     void* dict_dev;
+    void* def_dev;            // nullable columns: the pages' definition levels as one row-aligned 1-bit plane array
     int bit_width;            // widest page
     int ndict;
   };
@@ -189,6 +191,16 @@ class HdfsParquetScanner {
   std::vector<BatchColumn> batch_cols_;
   std::vector<fle_page_ref> batch_refs_;
   FusedProgram batch_prog_;
+  // the same program for a row group that DOES hold NULLs: every leaf on a nullable column is ANDed with the
+  // column's definition levels (a 1-bit column of its own, index batch_def_col_[c]) -- NULL fails every leaf,
+  // simple-predicates.h / hdfs-parquet-scanner.cc:342-345
+  std::vector<fle_pred_node> batch_prog_nulls_;
+  std::vector<int> batch_def_col_;   // per column: index of its definition-level column in the NULL program, -1 = none
+  int batch_ncols_nulls_;            // columns of the NULL program (0: it does not fit, NULL row groups take the page paths)
+  bool batch_nulls_seen_;            // an earlier row group of this scanner held NULLs: start with the NULL program
+  int64_t row_group_null_batches_;
+ public:
+  int64_t row_group_null_batches() const { return row_group_null_batches_; }
 };
 
 // ---------------------------------------------------------------------------------------
@@ -773,11 +785,19 @@ inline bool HdfsParquetScanner::StartRowGroupUpload() {
         d += 4 + nd;
         left -= 4 + nd;
       }
-      if (left < 1) return false;  // all-NULL page
-      v.bw = d[0];
-      v.fle = d + 1;
-      v.fle_bytes = left - 1;
-      if (v.bw < 1 || v.bw > 32 || v.fle_bytes < (v.rows + 63) / 64 * v.bw * 8) return false;  // (a shorter stream means NULLs)
+      if (left < 1) {  // all-NULL page: no width byte, no data (:921)
+        if (v.def == NULL) return false;
+        v.bw = 1;
+        v.fle = d;
+        v.fle_bytes = 0;
+      } else {
+        v.bw = d[0];
+        v.fle = d + 1;
+        v.fle_bytes = left - 1;
+      }
+      if (v.bw < 1 || v.bw > 32) return false;
+      // (a nullable page's FLE section holds only the non-null values: it may be shorter than the rows)
+      if (v.def == NULL && v.fle_bytes < (v.rows + 63) / 64 * v.bw * 8) return false;
       if (c == 0) total_rows += v.rows;
     }
   }
@@ -812,6 +832,11 @@ inline bool HdfsParquetScanner::StartRowGroupUpload() {
     const size_t image_bytes = one_copy ? static_cast<size_t>(hi - lo) : static_cast<size_t>(sum + 16 * npages);
     bc.image_dev = FleGpu::DeviceScratch(batch_bank_, 3 * c, image_bytes + 64);
     bc.planes_dev = FleGpu::DeviceScratch(batch_bank_, 3 * c + 1, static_cast<size_t>(total_groups) * bc.bit_width * 8 + 64);
+    bc.def_dev = NULL;
+    if (r->max_def_level() > 0) {
+      bc.def_dev = FleGpu::DeviceScratch(batch_bank_, 24 + c, static_cast<size_t>(total_groups) * 8 + 64);
+      if (!bc.def_dev) return false;
+    }
     int nd = 0, es = 0;
     const void* dv = r->dict_values(&nd, &es);
     bc.ndict = nd;
@@ -848,14 +873,72 @@ inline bool HdfsParquetScanner::StartRowGroupUpload() {
       ref.dst_bit_width = bc.bit_width;
       ref.dst_dev = static_cast<uint8_t*>(bc.planes_dev) + static_cast<size_t>(g0) * bc.bit_width * 8;
       ref.groups = (v.rows + 63) / 64;
+      ref.rows = v.rows;
       if (v.def != NULL) {
+        // the page's values are indexed by non-null ordinal: expanded into row-aligned planes (code 0 at NULL rows;
+        // with no NULL in the page that is a plain copy), its definition levels counted on the way ...
         ref.def_src_dev = img + (v.def - pg.data);
         ref.def_bytes = static_cast<uint64_t>(v.def_bytes);
+        ref.expand = 1;
+        batch_refs_.push_back(ref);
+        // ... and gathered as a 1-bit column of their own
+        fle_page_ref dref;
+        memset(&dref, 0, sizeof(dref));
+        dref.src_dev = ref.def_src_dev;
+        dref.src_bytes = ref.def_bytes;
+        dref.src_bit_width = dref.dst_bit_width = 1;
+        dref.dst_dev = static_cast<uint8_t*>(bc.def_dev) + static_cast<size_t>(g0) * 8;
+        dref.groups = ref.groups;
+        dref.rows = v.rows;
+        batch_refs_.push_back(dref);
+      } else {
+        batch_refs_.push_back(ref);
       }
-      ref.rows = v.rows;
-      batch_refs_.push_back(ref);
       g0 += ref.groups;
     }
+  }
+  // the program for a row group with NULLs: leaves on nullable columns ANDed with the column's definition levels
+  // (once per column behind a pure AND tree, per leaf otherwise)
+  batch_prog_nulls_.clear();
+  batch_def_col_.assign(ncols, -1);
+  batch_ncols_nulls_ = ncols;
+  {
+    bool and_only = true;
+    for (size_t i = 0; i < batch_prog_.nodes.size(); ++i) and_only = and_only && batch_prog_.nodes[i].op != FLE_OP_OR;
+    std::vector<int> used;
+    for (size_t i = 0; i < batch_prog_.nodes.size(); ++i) {
+      const fle_pred_node& nd = batch_prog_.nodes[i];
+      batch_prog_nulls_.push_back(nd);
+      if (nd.op == FLE_OP_AND || nd.op == FLE_OP_OR) continue;
+      if (nd.col < 0 || nd.col >= ncols || column_readers_[nd.col]->max_def_level() == 0) continue;
+      if (batch_def_col_[nd.col] < 0) {
+        batch_def_col_[nd.col] = batch_ncols_nulls_++;
+        used.push_back(nd.col);
+      }
+      if (!and_only) {
+        fle_pred_node eq;
+        memset(&eq, 0, sizeof(eq));
+        eq.op = FLE_OP_EQ; eq.col = batch_def_col_[nd.col]; eq.code = 1;
+        batch_prog_nulls_.push_back(eq);
+        fle_pred_node an;
+        memset(&an, 0, sizeof(an));
+        an.op = FLE_OP_AND;
+        batch_prog_nulls_.push_back(an);
+      }
+    }
+    if (and_only) {
+      for (size_t k = 0; k < used.size(); ++k) {
+        fle_pred_node eq;
+        memset(&eq, 0, sizeof(eq));
+        eq.op = FLE_OP_EQ; eq.col = batch_def_col_[used[k]]; eq.code = 1;
+        batch_prog_nulls_.push_back(eq);
+        fle_pred_node an;
+        memset(&an, 0, sizeof(an));
+        an.op = FLE_OP_AND;
+        batch_prog_nulls_.push_back(an);
+      }
+    }
+    if (batch_ncols_nulls_ > FLE_MAX_COLS || batch_prog_nulls_.size() > FLE_MAX_NODES) batch_ncols_nulls_ = 0;
   }
   batch_rows_ = total_rows;
   batch_state_ = 1;
@@ -876,7 +959,7 @@ inline bool HdfsParquetScanner::DeviceRowGroup(std::vector<uint8_t>* rows, int64
   if (!bitmap_dev || !hdr_dev || !hdr) return false;
   if (FleGpu::Check(fle_prefetch_fence(ctx), "fle_prefetch_fence") != FLE_OK) return false;
   if (FleGpu::Check(fle_pages_gather_dev(ctx, &batch_refs_[0], static_cast<int>(batch_refs_.size()), hdr_dev), "fle_pages_gather_dev") != FLE_OK) return false;
-  std::vector<fle_col_desc> cols(ncols);
+  std::vector<fle_col_desc> cols(std::max(ncols, batch_ncols_nulls_));
   std::vector<fle_slot_desc> slots(ncols);
   for (int c = 0; c < ncols; ++c) {
     BaseColumnReader* r = column_readers_[c];
@@ -892,23 +975,46 @@ inline bool HdfsParquetScanner::DeviceRowGroup(std::vector<uint8_t>* rows, int64
     slots[c].dict_dev = batch_cols_[c].dict_dev;
     slots[c].ndict = batch_cols_[c].ndict;
     slots[c].tuple_offset = r->tuple_offset_;
+    slots[c].def_planes_dev = batch_cols_[c].def_dev;  // a survivor that is NULL here gets its indicator set (ReadSlot)
+    slots[c].null_offset = r->null_offset_;
+    if (batch_ncols_nulls_ > 0 && batch_def_col_[c] >= 0) {
+      fle_col_desc& d = cols[batch_def_col_[c]];
+      memset(&d, 0, sizeof(fle_col_desc));
+      d.planes = batch_cols_[c].def_dev;
+      d.bytes = static_cast<uint64_t>(groups) * 8;
+      d.bit_width = 1;
+    }
   }
-  int rc = fle_eval_dev(ctx, &cols[0], ncols, &batch_prog_.nodes[0], static_cast<int>(batch_prog_.nodes.size()), 0, n, bitmap_dev, NULL);
-  if (rc == FLE_E_UNSUPPORTED) return false;
-  if (FleGpu::Check(rc, "fle_eval_dev(row group)") != FLE_OK) return false;
   // tuples: room for every row (grow-only scratch; only the survivors' bytes come back)
   uint8_t* tuples_dev = static_cast<uint8_t*>(FleGpu::DeviceScratch(bank, 42, static_cast<size_t>(n) * tuple_size_ + 64));
   if (!tuples_dev) return false;
-  rc = fle_assemble_rows_dev(ctx, bitmap_dev, n, &slots[0], ncols, tuple_size_, tuples_dev, n, hdr_dev + 1, hdr_dev + 2);
-  if (FleGpu::Check(rc, "fle_assemble_rows_dev") != FLE_OK) return false;
-  if (FleGpu::Check(fle_d2h(ctx, hdr, hdr_dev, 24), "fle_d2h(counts)") != FLE_OK) return false;
-  if (FleGpu::Check(fle_ctx_sync(ctx), "fle_ctx_sync") != FLE_OK) return false;
-  if (hdr[0] != 0) return false;  // NULLs in the row group: the page-span / window paths handle them (nothing was consumed)
+  // A row group without NULLs (every Impala-written TPC-H file) is the plain program over the row-aligned planes.
+  // NULLs are only known once the counts are back: the evaluation is then repeated with the NULL program, and the
+  // scanner starts with that one from its next row group on.
+  bool with_nulls = batch_nulls_seen_ && batch_ncols_nulls_ > 0;
+  uint64_t passed = 0;
+  for (;;) {
+    int rc = with_nulls ? fle_eval_dev(ctx, &cols[0], batch_ncols_nulls_, &batch_prog_nulls_[0], static_cast<int>(batch_prog_nulls_.size()), 0, n, bitmap_dev, NULL)
+                        : fle_eval_dev(ctx, &cols[0], ncols, &batch_prog_.nodes[0], static_cast<int>(batch_prog_.nodes.size()), 0, n, bitmap_dev, NULL);
+    if (rc == FLE_E_UNSUPPORTED) return false;
+    if (FleGpu::Check(rc, "fle_eval_dev(row group)") != FLE_OK) return false;
+    rc = fle_assemble_rows_dev(ctx, bitmap_dev, n, &slots[0], ncols, tuple_size_, tuples_dev, n, hdr_dev + 1, hdr_dev + 2);
+    if (FleGpu::Check(rc, "fle_assemble_rows_dev") != FLE_OK) return false;
+    if (FleGpu::Check(fle_d2h(ctx, hdr, hdr_dev, 24), "fle_d2h(counts)") != FLE_OK) return false;
+    if (FleGpu::Check(fle_ctx_sync(ctx), "fle_ctx_sync") != FLE_OK) return false;
+    if (hdr[0] != 0 && !with_nulls) {
+      batch_nulls_seen_ = true;
+      if (batch_ncols_nulls_ == 0) return false;  // the NULL program does not fit: the page-span / window paths (nothing was consumed)
+      with_nulls = true;
+      continue;
+    }
+    break;
+  }
   if (hdr[2] != 0) {
     parse_status_ = Status("dictionary index out of range");
     return false;
   }
-  const uint64_t passed = hdr[1];
+  passed = hdr[1];
   if (passed > 0) {
     const size_t bytes = static_cast<size_t>(passed) * tuple_size_;
     uint8_t* stage = static_cast<uint8_t*>(FleGpu::PinnedScratch(bank, 1, bytes));
@@ -917,6 +1023,7 @@ inline bool HdfsParquetScanner::DeviceRowGroup(std::vector<uint8_t>* rows, int64
     if (FleGpu::Check(fle_ctx_sync(ctx), "fle_ctx_sync") != FLE_OK) return false;
     rows->insert(rows->end(), stage, stage + bytes);
   }
+  if (hdr[0] != 0) ++row_group_null_batches_;
   for (int c = 0; c < ncols; ++c) column_readers_[c]->ConsumeAllPages();
   fused_rows_ = 0;
   ++fused_evals_;

@@ -253,17 +253,92 @@ TEST(Scanner, RowGroupBatch) {
     for (int r = 0; r < t.n; ++r) want += RowPasses(t, r);
     EXPECT_EQ(passed, want);
   }
-  {  // NULLs present: the batch notices (definition levels are counted on the device) and hands over, nothing is lost
-    Table t = MakeTable(64 * 5000 + 29, 0.01, 43);
-    vector<uint8_t> rows;
-    int64_t passed = 0, fe = 0, lw = 0, spans = 0, batches = 0;
+  // NULLs present: the pages' values are expanded into row-aligned planes, the definition levels become 1-bit columns
+  // ANDed to the leaves, the row group stays ONE batch; tuples identical to the page paths and to the truth
+  for (int k = 0; k < 3; ++k) {
+    const double fracs[3] = {0.01, 0.4, 0.97};
+    Table t = MakeTable(64 * 5000 + 29, fracs[k], 43 + k);
+    vector<uint8_t> rows, rows_p;
+    int64_t passed = 0, passed_p = 0, fe = 0, lw = 0, spans = 0, batches = 0, b2 = 0;
     int ts = 0, offs[3];
     RunScan(t, true, 64 * 300, 64 * 300, 64 * 300, true, &rows, &passed, &fe, &lw, &ts, offs, true, &spans, true, &batches);
-    EXPECT_EQ(batches, 0);
-    int64_t want = 0;
-    for (int r = 0; r < t.n; ++r) want += RowPasses(t, r);
+    EXPECT_EQ(batches, 1);
+    EXPECT_EQ(spans, 0);
+    EXPECT_EQ(lw, 0);
+    RunScan(t, true, 64 * 300, 64 * 300, 64 * 300, true, &rows_p, &passed_p, &fe, &lw, &ts, offs, true, &spans, false, &b2);
+    EXPECT_EQ(b2, 0);
+    EXPECT_EQ(passed, passed_p);
+    EXPECT_TRUE(rows == rows_p);
+    int64_t want = 0, bad = 0;
+    for (int r = 0; r < t.n; ++r) {
+      if (!RowPasses(t, r)) continue;
+      if (want < passed) {
+        const uint8_t* tuple = &rows[want * ts];
+        int32_t a, b, c;
+        memcpy(&a, tuple + offs[0], 4); memcpy(&b, tuple + offs[1], 4); memcpy(&c, tuple + offs[2], 4);
+        bad += !(a == t.shipdate[r] && b == t.discount[r] && c == t.quantity[r]) || tuple[0] || tuple[1] || tuple[2];
+      }
+      ++want;
+    }
     EXPECT_EQ(passed, want);
+    EXPECT_EQ(bad, 0);
   }
+}
+
+// an OR tree over nullable columns as one batch: survivors that are NULL in a materialised column carry the column's
+// NULL indicator and a zero slot, exactly as the page paths (ReadValue -> ReadSlot) write them
+TEST(Scanner, RowGroupBatchOrTreeNullIndicators) {
+  Table t = MakeTable(64 * 1500, 0.2, 77);
+  vector<int32_t> shipmode, instruct;
+  for (int i = 0; i < t.n; ++i) { shipmode.push_back(100 + rand() % 7); instruct.push_back(rand() % 4); }
+  vector<uint8_t> rows[2];
+  int64_t passed[2] = {0, 0};
+  for (int batch = 0; batch < 2; ++batch) {
+    ColumnChunk c0 = WriteColumn(shipmode, t.nn_shipdate, 64 * 500, true);
+    ColumnChunk c1 = WriteColumn(instruct, t.nn_discount, 64 * 500, true);
+    ColumnChunk c2 = WriteColumn(t.quantity, t.nn_quantity, 64 * 500, true);
+    HdfsParquetScanner scanner;
+    int i0 = scanner.AddColumn<int32_t>(1, &c0.dict_page[0], c0.dict_page.size(), c0.pages);
+    int i1 = scanner.AddColumn<int32_t>(1, &c1.dict_page[0], c1.dict_page.size(), c1.pages);
+    int i2 = scanner.AddColumn<int32_t>(1, &c2.dict_page[0], c2.dict_page.size(), c2.pages);
+    vector<int32_t> modes;
+    modes.push_back(101); modes.push_back(104); modes.push_back(999);
+    InOperate<int32_t> in0(i0, modes);
+    EqOperate<int32_t> eq1(i1, 2);
+    OrOperate either(&in0, &eq1);
+    GtOperate<int32_t> gt_all(i2, -5);  // dictionary short-circuit: all non-NULL rows
+    OrOperate root(&either, &gt_all);
+    scanner.AddSimplePredicate(&root);
+    scanner.set_fused(true);
+    scanner.set_row_group_batch(batch != 0);
+    EXPECT_TRUE(scanner.AssembleRows(t.n, &rows[batch], &passed[batch]).ok());
+    EXPECT_EQ(scanner.row_group_batches(), batch);
+    EXPECT_EQ(scanner.row_group_null_batches(), batch);
+    if (batch) {
+      const int ts = scanner.tuple_size();
+      int64_t want = 0, bad = 0;
+      for (int r = 0; r < t.n; ++r) {
+        const bool a = t.nn_shipdate[r] && (shipmode[r] == 101 || shipmode[r] == 104);
+        const bool b = t.nn_discount[r] && instruct[r] == 2;
+        const bool c = t.nn_quantity[r];
+        if (!(a || b || c)) continue;
+        if (want < passed[1]) {
+          const uint8_t* tuple = &rows[1][want * ts];
+          int32_t v0, v1, v2;
+          memcpy(&v0, tuple + scanner.slot_offset(i0), 4); memcpy(&v1, tuple + scanner.slot_offset(i1), 4);
+          memcpy(&v2, tuple + scanner.slot_offset(i2), 4);
+          bad += tuple[0] != !t.nn_shipdate[r] || tuple[1] != !t.nn_discount[r] || tuple[2] != !t.nn_quantity[r];
+          bad += (t.nn_shipdate[r] ? v0 != shipmode[r] : v0 != 0) || (t.nn_discount[r] ? v1 != instruct[r] : v1 != 0) ||
+                 (t.nn_quantity[r] ? v2 != t.quantity[r] : v2 != 0);
+        }
+        ++want;
+      }
+      EXPECT_EQ(passed[1], want);
+      EXPECT_EQ(bad, 0);
+    }
+  }
+  EXPECT_EQ(passed[0], passed[1]);
+  EXPECT_TRUE(rows[0] == rows[1]);
 }
 
 // PLAIN data pages (a column that overflowed the dictionary, hdfs-parquet-table-writer.cc:276-279) next to a
