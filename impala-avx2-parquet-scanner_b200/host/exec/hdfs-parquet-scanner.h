@@ -201,6 +201,10 @@ class HdfsParquetScanner {
   int64_t row_group_null_batches_;
  public:
   int64_t row_group_null_batches() const { return row_group_null_batches_; }
+  // What one row group taught about the file travels to the scanner of the next one: a scanner that expects NULLs
+  // evaluates the NULL program at once instead of finding out from the counts of the plain one.
+  bool saw_nulls() const { return batch_nulls_seen_; }
+  void set_expect_nulls(bool v) { batch_nulls_seen_ = v; }
 };
 
 // ---------------------------------------------------------------------------------------

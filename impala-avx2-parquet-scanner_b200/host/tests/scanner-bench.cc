@@ -42,13 +42,16 @@ struct ColumnChunk {
 
 static const int kPseudoHeaderBytes = 23;  // a thrift PageHeader of a data page is 20-odd bytes
 
-static ColumnChunk WriteColumn(const vector<int32_t>& values, int rows_per_page) {
+// notnull (optional): values[i] is NULL where notnull[i] is false -- the page's FLE section then holds only the
+// non-null values (hdfs-parquet-scanner.cc:886-921)
+static ColumnChunk WriteColumn(const vector<int32_t>& values, int rows_per_page, const vector<bool>* notnull = NULL) {
   ColumnChunk cc;
   DictEncoder<int32_t> dict(4);
   const int n = values.size();
   vector<vector<int> > page_indices;
   for (int r = 0; r < n; ++r) {
     if (r % rows_per_page == 0) page_indices.push_back(vector<int>());
+    if (notnull && !(*notnull)[r]) continue;
     if (dict.Put(values[r], page_indices.back()) < 0) { std::fprintf(stderr, "dictionary full\n"); exit(2); }
   }
   cc.dict_page.resize(dict.dict_encoded_size());
@@ -56,10 +59,10 @@ static ColumnChunk WriteColumn(const vector<int32_t>& values, int rows_per_page)
   vector<vector<uint8_t> > bodies;
   size_t total = 0;
   for (size_t p = 0; p < page_indices.size(); ++p) {
-    const size_t rows = page_indices[p].size();
+    const size_t rows = std::min<size_t>(rows_per_page, n - p * (size_t)rows_per_page);
     vector<uint8_t> defbuf((rows / 64 + 3) * 8);
     FleEncoder def_levels(&defbuf[0], defbuf.size(), 1);
-    for (size_t i = 0; i < rows; ++i) def_levels.Put(1);
+    for (size_t i = 0; i < rows; ++i) def_levels.Put(notnull ? (*notnull)[p * (size_t)rows_per_page + i] : 1);
     def_levels.Flush();
     int32_t num_def_bytes = def_levels.len();
     vector<uint8_t> body(4 + num_def_bytes);
@@ -81,7 +84,8 @@ static ColumnChunk WriteColumn(const vector<int32_t>& values, int rows_per_page)
     memset(cc.image + off, 0x15, kPseudoHeaderBytes);
     off += kPseudoHeaderBytes;
     memcpy(cc.image + off, &bodies[p][0], bodies[p].size());
-    cc.pages.push_back(HdfsParquetScanner::DataPage(cc.image + off, bodies[p].size(), page_indices[p].size()));
+    cc.pages.push_back(HdfsParquetScanner::DataPage(cc.image + off, bodies[p].size(),
+                                                    std::min<size_t>(rows_per_page, n - p * (size_t)rows_per_page)));
     off += bodies[p].size();
   }
   return cc;
@@ -250,6 +254,54 @@ int main(int argc, char** argv) {
                 best * 1e3, n / best, w.bytes / best / 1e9, (long long)evals, (long long)windows);
   }
   std::printf(", \"tuples_identical_across_paths\": true");
+
+  // ---- the same row group with NULLs in every column (one thread): still ONE device batch -----------------------
+  {
+    const double null_frac = 0.02;
+    Workload wn;
+    wn.n = n;
+    vector<bool> nn[3];
+    for (int k = 0; k < 3; ++k) nn[k].resize(n);
+    for (int i = 0; i < n; ++i) {
+      for (int k = 0; k < 3; ++k) nn[k][i] = (rand() % 10000) >= null_frac * 10000;
+      wn.want += nn[0][i] && nn[1][i] && nn[2][i] && shipdate[i] >= 8730 && shipdate[i] <= 9094 && discount[i] >= 5 &&
+                 discount[i] <= 7 && quantity[i] < 24;
+    }
+    wn.c[0] = WriteColumn(shipdate, rows_per_page, &nn[0]);
+    wn.c[1] = WriteColumn(discount, rows_per_page, &nn[1]);
+    wn.c[2] = WriteColumn(quantity, rows_per_page, &nn[2]);
+    for (int k = 0; k < 3; ++k) wn.bytes += wn.c[k].image_bytes;
+    std::printf(", \"with_nulls\": {\"null_fraction\": %.2f, \"page_bytes_total\": %zu, \"survivors\": %lld", null_frac, wn.bytes, (long long)wn.want);
+    vector<uint8_t> ref_rows;
+    // 4: row-group batch by a scanner that was told to expect NULLs (set_expect_nulls: what the previous row group of
+    // the file taught), 3: row-group batch finding out by itself (plain program first), 2: page spans
+    for (int mode = 4; mode >= 2; --mode) {
+      double best = 1e30;
+      int64_t passed = 0;
+      for (int r = 0; r < reps + 1; ++r) {
+        HdfsParquetScanner scanner;
+        wn.Attach(&scanner);
+        scanner.set_row_group_batch(mode >= 3);
+        scanner.set_expect_nulls(mode == 4);
+        vector<uint8_t> rows;
+        const double t0 = Now();
+        Status st = scanner.AssembleRows(n, &rows, &passed);
+        const double s = Now() - t0;
+        if (!st.ok() || passed != wn.want) { std::fprintf(stderr, "NULL scan failed: passed %lld want %lld\n", (long long)passed, (long long)wn.want); return 1; }
+        if (mode >= 3 && scanner.row_group_null_batches() != 1) { std::fprintf(stderr, "NULL row-group batch did not run\n"); return 1; }
+        if (r == 0) {
+          if (ref_rows.empty()) ref_rows = rows;
+          else if (rows != ref_rows) { std::fprintf(stderr, "NULL tuples of path %d differ\n", mode); return 1; }
+        }
+        if (r > 0 && s < best) best = s;
+      }
+      std::printf(", \"%s\": {\"ms\": %.3f, \"rows_per_s\": %.4g, \"page_GBps\": %.3f}",
+                  mode == 4 ? "row_group_batch_expecting_nulls" : mode == 3 ? "row_group_batch" : "device_page_spans", best * 1e3, n / best,
+                  wn.bytes / best / 1e9);
+    }
+    std::printf(", \"tuples_identical_across_paths\": true}");
+    for (int k = 0; k < 3; ++k) fle_host_free(wn.c[k].image);
+  }
 
   // ---- T scanner threads x R row groups ---------------------------------------------------------------------
   std::printf(", \"row_groups_per_thread\": %d, \"threads\": [", row_groups);
