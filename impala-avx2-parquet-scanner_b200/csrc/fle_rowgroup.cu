@@ -28,12 +28,15 @@ namespace fle {
 // ------------------------------------------------------------------------------------------
 struct PageRefDev {
   const uint8_t* src;      // FLE groups of the page, any byte alignment
-  uint64_t* dst;           // 8-byte aligned
+  uint64_t* dst;           // 8-byte aligned: the destination group that receives the page's first row
   const uint8_t* def_src;  // 1-bit FLE definition levels of the page, or null
-  int64_t groups;
-  int64_t rows;            // rows of the page (def-level count)
+  int64_t groups;          // 64-row groups of the page
+  int64_t rows;            // rows of the page
   int32_t src_bw, dst_bw;
-  int64_t data_groups;     // expand: groups the page's data stream holds (non-null values only)
+  int64_t data_groups;     // groups the page's data stream holds (expand: the non-null values only)
+  int64_t dst_groups;      // destination groups the page touches: ceil((dst_bit + rows) / 64)
+  int32_t general;         // 0: aligned copy (no NULL expansion, first row on a group boundary, whole groups)
+  int32_t dst_bit;         // position of the page's first row inside its first destination group
   int32_t expand, pad;
 };
 
@@ -51,36 +54,74 @@ __device__ __forceinline__ uint64_t load_u64_unaligned(const uint8_t* p) {
   return (lo >> sh) | (hi << (64u - sh));
 }
 
-// grid = (tiles of the largest page, pages).  A CTA copies 256 groups of one page: the page's plane
-// words are consecutive in the source, so word w of the tile goes to thread w % 256 (coalesced 8-byte
-// reads); the destination word of source word (g, i) is g * dst_bw + i.
+// Destination groups that a page shares with its neighbours (its first group when the page starts inside a group,
+// its last one when it ends inside a group) are cleared first: the pages OR their rows into them.
+__global__ void __launch_bounds__(64) pages_edges_kernel(const PageRefDev* __restrict__ refs) {
+  const PageRefDev R = refs[blockIdx.x];
+  if (!R.general || R.dst_groups <= 0) return;
+  const int t = threadIdx.x & 31;
+  if (t >= R.dst_bw) return;
+  if (threadIdx.x < 32) {
+    if (R.dst_bit != 0) R.dst[t] = 0ull;
+  } else {
+    if (((int64_t)R.dst_bit + R.rows) & 63) R.dst[(uint64_t)(R.dst_groups - 1) * R.dst_bw + t] = 0ull;
+  }
+}
+
+// grid = (tiles of the largest page, pages).
+// Aligned pages (whole groups, first row on a group boundary, no NULL expansion): a CTA copies 256 groups of one
+// page; the page's plane words are consecutive in the source, so word w of the tile goes to thread w % 256
+// (coalesced 8-byte reads); the destination word of source word (g, i) is g * dst_bw + i.
+// Every other page is PLACED row by row: one thread per destination group.  The rows of the page that fall into
+// the group, their definition bits (all ones for a page without definition levels) and the rank of the first of
+// them among the page's defined rows (prefix popcount inside the CTA, the words in front of its 256 counted on the
+// way) say which values of the data stream -- indexed by non-null ordinal, hdfs-parquet-scanner.cc:886-921 -- go
+// where: per plane a funnel shift takes them out of the stream and a bit deposit spreads them over the defined
+// rows; NULL rows read as code 0.  Pages of any row count, starting at any row of the column, with or without
+// NULLs, thereby join ONE row-aligned plane array per column.
 __global__ void __launch_bounds__(256)
 pages_gather_kernel(const PageRefDev* __restrict__ refs, unsigned long long* __restrict__ null_rows) {
   const PageRefDev R = refs[blockIdx.y];
   const int64_t g0 = (int64_t)blockIdx.x * kGatherGroupsPerCta;
-  // CTAs of this page that have groups to copy (at least one: it also counts the definition levels)
-  const int64_t nalive = max((int64_t)1, (R.groups + kGatherGroupsPerCta - 1) / kGatherGroupsPerCta);
+  // CTAs of this page that have groups to write (at least one: it also counts the definition levels)
+  const int64_t span = R.general ? R.dst_groups : R.groups;
+  const int64_t nalive = max((int64_t)1, (span + kGatherGroupsPerCta - 1) / kGatherGroupsPerCta);
   if ((int64_t)blockIdx.x >= nalive) return;
   const int64_t ng = min((int64_t)kGatherGroupsPerCta, R.groups - g0);
-  if (R.expand) {
-    // The page's data stream is indexed by non-null ordinal: row word w of the page takes the popcount(def word)
-    // values that start at rank(w) = defined rows before it, spread over the word's defined rows; NULL rows read as
-    // code 0.  One thread per row word; the ranks come from the page's own definition levels (a CTA counts the words
-    // in front of its 256: pages are a few thousand words).
+  if (R.general) {
     __shared__ uint64_t warp_buf[8];
     __shared__ uint32_t warp_scan[8];
-    auto def_at = [&](int64_t w) -> uint64_t {  // plane order (row k of the word at bit 63 - k), rows past the page cleared
-      if (w >= R.groups) return 0ull;
-      const uint64_t d = load_u64_unaligned(R.def_src + w * 8);
-      const int64_t left = R.rows - w * 64;
-      return left >= 64 ? d : (left <= 0 ? 0ull : (d & (~0ull << (64 - left))));
+    const int s = R.dst_bit;
+    auto def_row_order = [&](int64_t j) -> uint64_t {  // definition bits of page rows [64 j, 64 j + 64), row r at bit r & 63
+      if (j < 0 || j >= R.groups) return 0ull;
+      uint64_t d = R.expand ? __brevll(load_u64_unaligned(R.def_src + j * 8)) : ~0ull;
+      const int64_t left = R.rows - j * 64;
+      if (left < 64) d &= (1ull << left) - 1ull;  // (left >= 1 for j < groups)
+      return d;
     };
-    uint64_t pre = 0;
-    for (int64_t j = threadIdx.x; j < g0; j += 256) pre += __popcll(def_at(j));
-    const uint64_t rank0 = block_sum<256>(pre, warp_buf);
-    const int64_t w = g0 + threadIdx.x;
-    const uint64_t d = def_at(w);
-    const uint32_t mine = __popcll(d);
+    auto def_bits = [&](int64_t r0) -> uint64_t {  // bit k = defined(page row r0 + k), 0 outside the page
+      if (r0 < 0) return def_row_order(0) << (int)(-r0);  // (only the page's first destination group: -r0 = dst_bit)
+      const int64_t j = r0 >> 6;
+      const int sh = (int)(r0 & 63);
+      uint64_t v = def_row_order(j) >> sh;
+      if (sh) v |= def_row_order(j + 1) << (64 - sh);
+      return v;
+    };
+    // defined rows of the page in front of this CTA's first destination group
+    const int64_t first_r = max((int64_t)0, g0 * 64 - s);
+    uint64_t rank0;
+    if (R.expand) {
+      uint64_t pre = 0;
+      for (int64_t j = threadIdx.x; j < (first_r >> 6); j += 256) pre += __popcll(def_row_order(j));
+      if (threadIdx.x == 0 && (first_r & 63)) pre += __popcll(def_row_order(first_r >> 6) & ((1ull << (first_r & 63)) - 1ull));
+      rank0 = block_sum<256>(pre, warp_buf);
+    } else {
+      rank0 = (uint64_t)first_r;
+    }
+    const int64_t wl = g0 + threadIdx.x;  // destination group of the page
+    const int64_t base_r = wl * 64 - s;   // page row of the group's first bit (negative: the group starts before the page)
+    const uint64_t mask_r = wl < R.dst_groups ? def_bits(base_r) : 0ull;
+    const uint32_t mine = __popcll(mask_r);
     uint32_t incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -91,20 +132,23 @@ pages_gather_kernel(const PageRefDev* __restrict__ refs, unsigned long long* __r
     __syncthreads();
     uint32_t woff = 0;
     for (int x = 0; x < (int)(threadIdx.x >> 5); ++x) woff += warp_scan[x];
-    if (w < R.groups) {
+    if (wl < R.dst_groups) {
       const int64_t rank = (int64_t)rank0 + woff + (incl - mine);
       const int64_t dg = rank >> 6;
       const int sh = (int)(rank & 63);
-      const uint64_t mask_r = __brevll(d);  // row order
       const int sbw = R.src_bw, dbw = R.dst_bw;
-      uint64_t* out = R.dst + (uint64_t)w * dbw;
+      const bool interior = base_r >= 0 && base_r + 64 <= R.rows;  // every row of the group belongs to this page
+      uint64_t* out = R.dst + (uint64_t)wl * dbw;
       for (int i = 0; i < sbw; ++i) {
         const uint64_t a = (mine && dg < R.data_groups) ? load_u64_unaligned(R.src + ((uint64_t)dg * sbw + i) * 8u) : 0ull;
         const uint64_t b = (mine && sh && dg + 1 < R.data_groups) ? load_u64_unaligned(R.src + ((uint64_t)(dg + 1) * sbw + i) * 8u) : 0ull;
         const uint64_t top = sh ? ((a << sh) | (b >> (64 - sh))) : a;  // ordinal rank + q at bit 63 - q
-        out[i] = __brevll(deposit_bits(__brevll(top), mask_r));
+        const uint64_t v = __brevll(deposit_bits(__brevll(top), mask_r));
+        if (interior) out[i] = v;
+        else if (v) atomicOr(reinterpret_cast<unsigned long long*>(out + i), (unsigned long long)v);  // (cleared by pages_edges_kernel)
       }
-      for (int i = sbw; i < dbw; ++i) out[i] = 0ull;
+      if (interior)
+        for (int i = sbw; i < dbw; ++i) out[i] = 0ull;
     }
   } else if (ng > 0) {
     const int sbw = R.src_bw, dbw = R.dst_bw;
@@ -148,34 +192,48 @@ int launch_pages_gather(fle_ctx* ctx, const fle_page_ref* refs, int nrefs, uint6
   if (nrefs == 0) return FLE_OK;
   std::vector<PageRefDev> h((size_t)nrefs);
   int64_t max_groups = 1;
+  bool any_general = false;
   for (int i = 0; i < nrefs; ++i) {
     const fle_page_ref& r = refs[i];
     if (r.src_bit_width < 1 || r.src_bit_width > 32 || r.dst_bit_width < r.src_bit_width || r.dst_bit_width > 32)
       return set_error(ctx, FLE_E_INVALID, "page bit widths outside 1..32 or destination narrower than the page");
     if (r.groups < 0 || r.rows < 0 || (r.groups > 0 && ((!r.src_dev && !(r.expand && r.src_bytes == 0)) || !r.dst_dev)))
       return set_error(ctx, FLE_E_INVALID, "bad page reference");
+    if (r.dst_bit < 0 || r.dst_bit > 63) return set_error(ctx, FLE_E_INVALID, "dst_bit outside 0..63");
     if (r.expand && !r.def_src_dev) return set_error(ctx, FLE_E_INVALID, "a page is expanded through its definition levels");
-    if (r.expand && r.groups != (r.rows + 63) / 64) return set_error(ctx, FLE_E_INVALID, "an expanded page has one group per 64 rows");
+    const int64_t rows = (r.rows == 0 && !r.expand && !r.def_src_dev) ? r.groups * 64 : r.rows;  // (callers that only copy groups)
+    if (r.groups != (rows + 63) / 64) return set_error(ctx, FLE_E_INVALID, "a page has one group per 64 rows");
     if (!r.expand && (uint64_t)r.groups * (uint64_t)r.src_bit_width * 8u > r.src_bytes)
       return set_error(ctx, FLE_E_BUFFER, "page shorter than its groups");
-    if (r.def_src_dev && (uint64_t)((r.rows + 63) / 64) * 8u > r.def_bytes)
+    if (r.def_src_dev && (uint64_t)((rows + 63) / 64) * 8u > r.def_bytes)
       return set_error(ctx, FLE_E_BUFFER, "definition levels shorter than the page's rows");
     if (reinterpret_cast<uintptr_t>(r.dst_dev) & 7) return set_error(ctx, FLE_E_ALIGN, "plane destination must be 8-byte aligned");
     h[i].src = static_cast<const uint8_t*>(r.src_dev);
     h[i].dst = static_cast<uint64_t*>(r.dst_dev);
     h[i].def_src = static_cast<const uint8_t*>(r.def_src_dev);
     h[i].groups = r.groups;
-    h[i].rows = r.rows;
+    h[i].rows = rows;
     h[i].src_bw = r.src_bit_width;
     h[i].dst_bw = r.dst_bit_width;
     h[i].expand = r.expand ? 1 : 0;
     h[i].pad = 0;
-    h[i].data_groups = (int64_t)(r.src_bytes / ((uint64_t)r.src_bit_width * 8u));
-    max_groups = std::max(max_groups, r.groups);
+    h[i].dst_bit = r.dst_bit;
+    h[i].dst_groups = (r.dst_bit + rows + 63) / 64;
+    // a page that ends inside a group is placed as well (the next page ORs its rows into that group) -- unless it is
+    // copied to a group boundary and nothing was said about rows at all
+    h[i].general = (r.expand || r.dst_bit != 0 || (rows & 63) != 0) ? 1 : 0;
+    // (without expansion the definition levels are only counted: the data stream then holds every row)
+    h[i].data_groups = r.expand ? (int64_t)(r.src_bytes / ((uint64_t)r.src_bit_width * 8u)) : r.groups;
+    any_general = any_general || h[i].general;
+    max_groups = std::max(max_groups, h[i].general ? h[i].dst_groups : r.groups);
   }
   const uint32_t* d = nullptr;
   int rc = upload_literals(ctx, h.data(), (int)(h.size() * sizeof(PageRefDev) / 4), nullptr, nullptr, &d);
   if (rc != FLE_OK) return rc;
+  if (any_general) {
+    pages_edges_kernel<<<nrefs, 64, 0, ctx->stream>>>(reinterpret_cast<const PageRefDev*>(d));
+    ctx->launches += 1;
+  }
   const dim3 grid((unsigned)((max_groups + kGatherGroupsPerCta - 1) / kGatherGroupsPerCta), (unsigned)nrefs);
   pages_gather_kernel<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const PageRefDev*>(d),
                                                     reinterpret_cast<unsigned long long*>(null_rows_dev));

@@ -296,23 +296,28 @@ typedef struct fle_page_ref {
   int32_t src_bit_width;    /* width the page was packed with */
   int32_t dst_bit_width;    /* width of the destination planes, >= src (missing high planes become zero planes) */
   void* dst_dev;            /* 8-byte aligned; groups * dst_bit_width * 8 bytes */
-  int64_t groups;           /* 64-row groups of the page */
+  int64_t groups;           /* 64-row groups of the page: ceil(rows / 64) */
   const void* def_src_dev;  /* optional: the page's definition levels (FLE, bit width 1), any alignment */
   uint64_t def_bytes;
-  int64_t rows;             /* rows of the page (definition-level count; expansion) */
+  int64_t rows;             /* rows of the page (0 with neither def levels nor expand: groups * 64) */
   int32_t expand;           /* 1 (needs def_src_dev): the page's FLE section holds only the NON-NULL values
-                             * (hdfs-parquet-scanner.cc:886-921: data values are indexed by non-null ordinal); dst
-                             * receives one group slot per 64 ROWS -- groups = ceil(rows / 64) -- with the value of every
-                             * defined row at the row's position and code 0 at NULL rows, so that the page joins a
-                             * row-aligned plane array the fused kernels scan like a required column (the definition
-                             * levels, gathered as a 1-bit column of their own, say which rows are NULL); src_bytes may
-                             * then be shorter than groups * src_bit_width * 8, even 0 for an all-NULL page */
-  int32_t reserved;
+                             * (hdfs-parquet-scanner.cc:886-921: data values are indexed by non-null ordinal); the
+                             * value of every defined row goes to the row's position, NULL rows get code 0, so that
+                             * the page joins a row-aligned plane array the fused kernels scan like a required column
+                             * (the definition levels, gathered as a 1-bit column of their own, say which rows are
+                             * NULL); src_bytes may then be shorter than groups * src_bit_width * 8, even 0 for an
+                             * all-NULL page */
+  int32_t dst_bit;          /* 0..63: position of the page's FIRST ROW inside the group at dst_dev.  Pages need not
+                             * hold whole groups (the reference's writer closes a dictionary page after 524225 rows,
+                             * hdfs-parquet-table-writer.cc:387): page k + 1 continues in the group page k ended in --
+                             * dst_dev = column base + (first row / 64) * dst_bit_width * 8, dst_bit = first row % 64;
+                             * the page then writes ceil((dst_bit + rows) / 64) groups, sharing the first / last one
+                             * with its neighbours (all pages of a launch are placed after those groups were cleared) */
 } fle_page_ref;
 /* Re-bases the FLE sections of all pages (of all columns) of a row group onto aligned plane arrays
- * in ONE launch -- consecutive pages of a column go to consecutive dst ranges, so the column becomes one
- * plane array the fused kernels can scan -- and counts the rows whose definition level is 0 into
- * *null_rows_dev (optional).  refs is a HOST array. */
+ * in ONE launch (two when a page starts or ends inside a group) -- consecutive pages of a column go to
+ * consecutive row ranges of dst, so the column becomes one plane array the fused kernels can scan -- and counts
+ * the rows whose definition level is 0 into *null_rows_dev (optional).  refs is a HOST array. */
 int fle_pages_gather_dev(fle_ctx* ctx, const fle_page_ref* refs, int nrefs, uint64_t* null_rows_dev);
 
 /* One materialised column of the survivors' tuples. */

@@ -236,3 +236,71 @@ def test_assemble_rows_null_indicators(ctx, oracle):
             want[:, c] = (~defs[rows]).astype(np.uint8)
         want[:, off:off + ss] = v.view(np.uint8).reshape(k, ss)
     assert (got == want).all()
+
+
+@pytest.mark.parametrize("null_frac", [None, 0.0, 0.05, 0.7])
+def test_pages_gather_places_ragged_pages(ctx, oracle, null_frac):
+    """Pages of ANY row count (the reference's writer closes a dictionary page after 524225 rows,
+    hdfs-parquet-table-writer.cc:387) are placed at their row offset of ONE row-aligned plane array: page k + 1
+    continues in the group page k ended in (fle_page_ref.dst_bit).  null_frac None: required column (no definition
+    levels); otherwise nullable pages, expanded through their definition levels, which travel as a 1-bit column."""
+    import torch
+    rng = np.random.default_rng(17 if null_frac is None else int(null_frac * 100) + 1)
+    page_rows = [64 * 30 + 1, 524225, 17, 3, 64 * 2, 5000, 63, 1]
+    page_bw = [3, 5, 6, 6, 7, 4, 2, 7]
+    dst_bw = 7
+    nullable = null_frac is not None
+    blob = bytearray()
+    refs, want_rows, want_def = [], [], []
+    for pi, (rows, bw) in enumerate(zip(page_rows, page_bw)):
+        defs = (rng.random(rows) >= null_frac) if nullable else np.ones(rows, dtype=bool)
+        if nullable and null_frac > 0 and pi == 3:
+            defs[:] = False
+        vals = rng.integers(0, 1 << bw, size=int(defs.sum())).astype(np.uint32)
+        full = np.zeros(rows, dtype=np.uint32)
+        full[defs] = vals
+        want_rows.append(full)
+        want_def.append(defs)
+        blob += bytes(rng.integers(0, 255, size=int(rng.integers(17, 40)), dtype=np.uint8))
+        def_off = def_bytes = 0
+        if nullable:
+            dwords = oracle.pack(defs.astype(np.uint32), 1)
+            blob += np.int32(dwords.nbytes).tobytes()
+            def_off, def_bytes = len(blob), dwords.nbytes
+            blob += dwords.tobytes()
+        data_off, data_bytes = len(blob), 0
+        if len(vals):
+            words = oracle.pack(vals, bw)
+            blob += bytes([bw])
+            data_off, data_bytes = len(blob), words.nbytes
+            blob += words.tobytes()
+        refs.append(dict(src_off=data_off, src_bytes=data_bytes, bw=bw, def_off=def_off, def_bytes=def_bytes, rows=rows))
+    blob += bytes(16)
+    dblob = torch.from_numpy(np.frombuffer(bytes(blob), dtype=np.uint8).copy()).cuda()
+    total = sum(page_rows)
+    G = (total + 63) // 64
+    planes = torch.full((G * dst_bw,), -1, dtype=torch.int64, device="cuda")
+    dplanes = torch.full((G,), -1, dtype=torch.int64, device="cuda")
+    row0, crefs = 0, []
+    for r in refs:
+        common = dict(groups=(r["rows"] + 63) // 64, rows=r["rows"], dst_bit=row0 % 64)
+        ref = dict(src_dev=dblob.data_ptr() + r["src_off"], src_bytes=r["src_bytes"], src_bit_width=r["bw"], dst_bit_width=dst_bw,
+                   dst_dev=planes.data_ptr() + (row0 // 64) * dst_bw * 8, **common)
+        if nullable:
+            ref.update(def_src_dev=dblob.data_ptr() + r["def_off"], def_bytes=r["def_bytes"], expand=1)
+            crefs.append(dict(src_dev=dblob.data_ptr() + r["def_off"], src_bytes=r["def_bytes"], src_bit_width=1, dst_bit_width=1,
+                              dst_dev=dplanes.data_ptr() + (row0 // 64) * 8, **common))
+        crefs.append(ref)
+        row0 += r["rows"]
+    for rep in range(2):  # (twice: the shared groups are cleared by the call itself)
+        nulls = ctx.pages_gather_dev(crefs)
+    torch.cuda.synchronize()
+    assert int(nulls.item()) == sum(int((~d).sum()) for d in want_def)
+    got = planes.cpu().numpy().view(np.uint64)
+    dec = oracle.unpack(got, dst_bw, 0, total)
+    assert (dec == np.concatenate(want_rows)).all()
+    if total % 64:  # rows past the end of the column read as 0
+        assert (oracle.unpack(got, dst_bw, 0, G * 64)[total:] == 0).all()
+    if nullable:
+        dd = oracle.unpack(dplanes.cpu().numpy().view(np.uint64), 1, 0, total)
+        assert (dd == np.concatenate(want_def).astype(np.uint32)).all()
