@@ -25,10 +25,14 @@
 //   * row-group batch (default when it applies): ALL data pages of every column chunk are uploaded --
 //     one copy per column chunk when its pages lie back to back in (pinned) host memory, on the
 //     context's copy stream, so row group k+1 can cross PCIe while k is evaluated
-//     (StartRowGroupUpload) -- then fle_pages_gather_dev re-bases the pages' FLE sections onto one
-//     plane array per column (counting NULLs on the way), ONE fused fle_eval_dev covers the row group
-//     and fle_assemble_rows_dev writes the survivors' tuples; two host synchronisations per row group
-//     however many pages it holds.  Applies to fresh readers over dictionary pages without NULLs;
+//     (StartRowGroupUpload) -- then fle_pages_gather_dev places the pages' FLE sections into one ROW-ALIGNED
+//     plane array per column: pages of any row count, cut differently per column, are placed at their row
+//     offset (dst_bit); pages of nullable columns hold only their non-null values and are expanded through
+//     their definition levels (code 0 at NULL rows), which become a 1-bit column of their own; NULLs are
+//     counted on the way.  ONE fused fle_eval_dev covers the row group -- the plain program, or, when the
+//     row group holds NULLs, the program with `AND def_c = 1` per nullable column / leaf -- and
+//     fle_assemble_rows_dev writes the survivors' tuples, NULL indicators included; two host synchronisations
+//     per row group however many pages it holds.  Applies to fresh readers over dictionary pages;
 //   * per leaf (the reference's structure): every leaf call goes through ColumnReader<T> ->
 //     DictDecoder<T> -> FleDecoder, which evaluates the WHOLE page on the GPU on first use and
 //     then serves the <=1024-row windows from the cached bitmap;
@@ -758,21 +762,25 @@ inline bool HdfsParquetScanner::StartRowGroupUpload() {
   const int ncols = static_cast<int>(column_readers_.size());
   if (!row_group_batch_ || !fused_enabled_ || !device_materialise_ || FleGpu::reference_compat()) return false;
   if (ncols == 0 || ncols > FLE_MAX_COLS || simple_predicates_.empty()) return false;
-  const size_t npages = column_readers_[0]->pages().size();
-  if (npages == 0) return false;
-  // every column: fresh reader, dictionary pages only, the same rows per page as column 0, every page but
-  // the last a whole number of 64-row groups (the pages of a column are concatenated into one plane array)
+  if (column_readers_[0]->pages().empty()) return false;
+  // every column: fresh reader, dictionary pages only, the same number of rows in the row group.  Pages may hold any
+  // number of rows (the reference's writer closes a dictionary page after 524225 rows,
+  // hdfs-parquet-table-writer.cc:387) and the columns may cut their pages differently: every page is placed at its
+  // row offset of the column's ONE row-aligned plane array (fle_page_ref.dst_bit).
   struct PageView { const uint8_t* fle; int64_t fle_bytes; int bw; const uint8_t* def; int64_t def_bytes; int64_t rows; };
-  std::vector<std::vector<PageView> > views(ncols, std::vector<PageView>(npages));
+  std::vector<std::vector<PageView> > views(ncols);
   int64_t total_rows = 0;
   for (int c = 0; c < ncols; ++c) {
     BaseColumnReader* r = column_readers_[c];
-    if (!r->fresh() || r->pages().size() != npages || r->max_def_level() > 1) return false;
+    const size_t npages = r->pages().size();
+    if (!r->fresh() || npages == 0 || r->max_def_level() > 1) return false;
+    views[c].resize(npages);
+    int64_t col_rows = 0;
     for (size_t p = 0; p < npages; ++p) {
       const DataPage& pg = r->pages()[p];
       if (pg.encoding != parquet_encoding::FLE_DICTIONARY && pg.encoding != parquet_encoding::PLAIN_DICTIONARY) return false;
-      if (pg.num_values != column_readers_[0]->pages()[p].num_values || pg.num_values <= 0) return false;
-      if (p + 1 < npages && (pg.num_values & 63)) return false;
+      if (pg.num_values <= 0) return false;
+      col_rows += pg.num_values;
       PageView& v = views[c][p];
       const uint8_t* d = pg.data;
       int64_t left = pg.size;
@@ -802,8 +810,9 @@ inline bool HdfsParquetScanner::StartRowGroupUpload() {
       if (v.bw < 1 || v.bw > 32) return false;
       // (a nullable page's FLE section holds only the non-null values: it may be shorter than the rows)
       if (v.def == NULL && v.fle_bytes < (v.rows + 63) / 64 * v.bw * 8) return false;
-      if (c == 0) total_rows += v.rows;
     }
+    if (c == 0) total_rows = col_rows;
+    else if (col_rows != total_rows) return false;
   }
   if (total_rows >= (int64_t(1) << 31)) return false;
   batch_prog_ = FusedProgram();
@@ -817,6 +826,7 @@ inline bool HdfsParquetScanner::StartRowGroupUpload() {
   for (int c = 0; c < ncols; ++c) {
     BaseColumnReader* r = column_readers_[c];
     BatchColumn& bc = batch_cols_[c];
+    const size_t npages = r->pages().size();
     bc.bit_width = 0;
     for (size_t p = 0; p < npages; ++p) bc.bit_width = std::max(bc.bit_width, views[c][p].bw);
     // one upload per column chunk when its pages lie back to back in host memory (as they do in the I/O buffer
@@ -855,7 +865,7 @@ inline bool HdfsParquetScanner::StartRowGroupUpload() {
       if (FleGpu::Check(fle_h2d_prefetch(ctx, bc.dict_dev, stage, static_cast<size_t>(nd) * es), "fle_h2d_prefetch(dict)") != FLE_OK) return false;
     }
     if (one_copy && FleGpu::Check(fle_h2d_prefetch(ctx, bc.image_dev, lo, image_bytes), "fle_h2d_prefetch(chunk)") != FLE_OK) return false;
-    int64_t g0 = 0;
+    int64_t row0 = 0;  // first row of the page inside the row group
     size_t off = 0;
     for (size_t p = 0; p < npages; ++p) {
       const DataPage& pg = r->pages()[p];
@@ -875,7 +885,9 @@ inline bool HdfsParquetScanner::StartRowGroupUpload() {
       ref.src_bytes = static_cast<uint64_t>(v.fle_bytes);
       ref.src_bit_width = v.bw;
       ref.dst_bit_width = bc.bit_width;
+      const int64_t g0 = row0 >> 6;
       ref.dst_dev = static_cast<uint8_t*>(bc.planes_dev) + static_cast<size_t>(g0) * bc.bit_width * 8;
+      ref.dst_bit = static_cast<int32_t>(row0 & 63);
       ref.groups = (v.rows + 63) / 64;
       ref.rows = v.rows;
       if (v.def != NULL) {
@@ -892,13 +904,14 @@ inline bool HdfsParquetScanner::StartRowGroupUpload() {
         dref.src_bytes = ref.def_bytes;
         dref.src_bit_width = dref.dst_bit_width = 1;
         dref.dst_dev = static_cast<uint8_t*>(bc.def_dev) + static_cast<size_t>(g0) * 8;
+        dref.dst_bit = ref.dst_bit;
         dref.groups = ref.groups;
         dref.rows = v.rows;
         batch_refs_.push_back(dref);
       } else {
         batch_refs_.push_back(ref);
       }
-      g0 += ref.groups;
+      row0 += v.rows;
     }
   }
   // the program for a row group with NULLs: leaves on nullable columns ANDed with the column's definition levels
