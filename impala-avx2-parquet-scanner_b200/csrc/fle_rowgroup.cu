@@ -139,11 +139,15 @@ pages_gather_kernel(const PageRefDev* __restrict__ refs, unsigned long long* __r
       const int sbw = R.src_bw, dbw = R.dst_bw;
       const bool interior = base_r >= 0 && base_r + 64 <= R.rows;  // every row of the group belongs to this page
       uint64_t* out = R.dst + (uint64_t)wl * dbw;
+      const bool whole = mask_r == ~0ull && sh == 0;  // 64 defined rows that are one group of the stream: a copy
       for (int i = 0; i < sbw; ++i) {
         const uint64_t a = (mine && dg < R.data_groups) ? load_u64_unaligned(R.src + ((uint64_t)dg * sbw + i) * 8u) : 0ull;
-        const uint64_t b = (mine && sh && dg + 1 < R.data_groups) ? load_u64_unaligned(R.src + ((uint64_t)(dg + 1) * sbw + i) * 8u) : 0ull;
-        const uint64_t top = sh ? ((a << sh) | (b >> (64 - sh))) : a;  // ordinal rank + q at bit 63 - q
-        const uint64_t v = __brevll(deposit_bits(__brevll(top), mask_r));
+        uint64_t v = a;
+        if (!whole) {
+          const uint64_t b = (mine && sh && dg + 1 < R.data_groups) ? load_u64_unaligned(R.src + ((uint64_t)(dg + 1) * sbw + i) * 8u) : 0ull;
+          const uint64_t top = sh ? ((a << sh) | (b >> (64 - sh))) : a;  // ordinal rank + q at bit 63 - q
+          v = __brevll(deposit_bits(__brevll(top), mask_r));
+        }
         if (interior) out[i] = v;
         else if (v) atomicOr(reinterpret_cast<unsigned long long*>(out + i), (unsigned long long)v);  // (cleared by pages_edges_kernel)
       }
@@ -224,7 +228,7 @@ int launch_pages_gather(fle_ctx* ctx, const fle_page_ref* refs, int nrefs, uint6
     h[i].general = (r.expand || r.dst_bit != 0 || (rows & 63) != 0) ? 1 : 0;
     // (without expansion the definition levels are only counted: the data stream then holds every row)
     h[i].data_groups = r.expand ? (int64_t)(r.src_bytes / ((uint64_t)r.src_bit_width * 8u)) : r.groups;
-    any_general = any_general || h[i].general;
+    any_general = any_general || (h[i].general && (r.dst_bit != 0 || ((r.dst_bit + rows) & 63) != 0));  // groups shared with a neighbour
     max_groups = std::max(max_groups, h[i].general ? h[i].dst_groups : r.groups);
   }
   const uint32_t* d = nullptr;

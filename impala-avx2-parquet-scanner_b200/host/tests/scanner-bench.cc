@@ -186,10 +186,11 @@ static double RunThreads(int threads, Fn fn, bool* ok) {
 int main(int argc, char** argv) {
   int n = 4194304, rows_per_page = 65536, reps = 5, row_groups = 8;
   vector<int> thread_counts = {1, 2, 4};
-  bool json = false;
+  bool json = false, extra = true;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     if (a == "--json") json = true;
+    else if (a == "--no-extra") extra = false;  // skip the NULL / writer-shaped row groups
     else if (a == "--rows" && i + 1 < argc) n = atoi(argv[++i]);
     else if (a == "--rows-per-page" && i + 1 < argc) rows_per_page = atoi(argv[++i]);
     else if (a == "--reps" && i + 1 < argc) reps = atoi(argv[++i]);
@@ -256,7 +257,7 @@ int main(int argc, char** argv) {
   std::printf(", \"tuples_identical_across_paths\": true");
 
   // ---- the same row group with NULLs in every column (one thread): still ONE device batch -----------------------
-  {
+  if (extra) {
     const double null_frac = 0.02;
     Workload wn;
     wn.n = n;
@@ -303,6 +304,45 @@ int main(int argc, char** argv) {
     for (int k = 0; k < 3; ++k) fle_host_free(wn.c[k].image);
   }
 
+  // ---- pages as the reference's writer cuts them: 524225 rows per dictionary page (hdfs-parquet-table-writer.cc:387),
+  //      i.e. no page boundary on a 64-row group, and another column cut differently ---------------------------------
+  if (extra) {
+    Workload wr;
+    wr.n = n;
+    wr.want = w.want;
+    wr.c[0] = WriteColumn(shipdate, 524225);
+    wr.c[1] = WriteColumn(discount, 524225);
+    wr.c[2] = WriteColumn(quantity, 300007);
+    for (int k = 0; k < 3; ++k) wr.bytes += wr.c[k].image_bytes;
+    std::printf(", \"writer_shaped_pages\": {\"rows_per_page\": [524225, 524225, 300007], \"page_bytes_total\": %zu", wr.bytes);
+    vector<uint8_t> ref_rows;
+    for (int mode = 3; mode >= 2; --mode) {
+      double best = 1e30;
+      int64_t passed = 0;
+      for (int r = 0; r < reps + 1; ++r) {
+        HdfsParquetScanner scanner;
+        wr.Attach(&scanner);
+        scanner.set_row_group_batch(mode == 3);
+        vector<uint8_t> rows;
+        const double t0 = Now();
+        Status st = scanner.AssembleRows(n, &rows, &passed);
+        const double s = Now() - t0;
+        if (!st.ok() || passed != wr.want) { std::fprintf(stderr, "ragged scan failed: passed %lld want %lld\n", (long long)passed, (long long)wr.want); return 1; }
+        if (mode == 3 && scanner.row_group_batches() != 1) { std::fprintf(stderr, "ragged row-group batch did not run\n"); return 1; }
+        if (r == 0) {
+          if (ref_rows.empty()) ref_rows = rows;
+          else if (rows != ref_rows) { std::fprintf(stderr, "ragged tuples of path %d differ\n", mode); return 1; }
+        }
+        if (r > 0 && s < best) best = s;
+      }
+      std::printf(", \"%s\": {\"ms\": %.3f, \"rows_per_s\": %.4g, \"page_GBps\": %.3f}", mode == 3 ? "row_group_batch" : "page_paths", best * 1e3,
+                  n / best, wr.bytes / best / 1e9);
+    }
+    if (ref_rows != reference_rows) { std::fprintf(stderr, "ragged tuples differ from the aligned pages' tuples\n"); return 1; }
+    std::printf(", \"tuples_identical_across_paths\": true}");
+    for (int k = 0; k < 3; ++k) fle_host_free(wr.c[k].image);
+  }
+
   // ---- T scanner threads x R row groups ---------------------------------------------------------------------
   std::printf(", \"row_groups_per_thread\": %d, \"threads\": [", row_groups);
   double best_frac = 0, best_rows_per_s = 0, best_gbps = 0, best_peak = 0;
@@ -311,7 +351,7 @@ int main(int argc, char** argv) {
     const int T = thread_counts[ti];
     bool ok = true;
     double scan_s = 1e30, copy_s = 1e30;
-    for (int r = 0; r < 3; ++r) {
+    for (int r = 0; r < 6; ++r) {  // (best of five: several host threads sharing one copy engine scatter by +-10 %)
       bool ok1 = true;
       const double s = RunThreads(T, [&](int, bool timed) {
         int64_t p, b;
