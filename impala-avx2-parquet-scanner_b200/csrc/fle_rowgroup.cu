@@ -37,7 +37,8 @@ struct PageRefDev {
   int64_t dst_groups;      // destination groups the page touches: ceil((dst_bit + rows) / 64)
   int32_t general;         // 0: aligned copy (no NULL expansion, first row on a group boundary, whole groups)
   int32_t dst_bit;         // position of the page's first row inside its first destination group
-  int32_t expand, pad;
+  int32_t expand;
+  int32_t plain;           // 0: FLE page; 1 / 2 / 4 / 8: PLAIN page of that many bytes per value (dst = value slots)
 };
 
 constexpr int kGatherGroupsPerCta = 256;
@@ -58,7 +59,7 @@ __device__ __forceinline__ uint64_t load_u64_unaligned(const uint8_t* p) {
 // its last one when it ends inside a group) are cleared first: the pages OR their rows into them.
 __global__ void __launch_bounds__(64) pages_edges_kernel(const PageRefDev* __restrict__ refs) {
   const PageRefDev R = refs[blockIdx.x];
-  if (!R.general || R.dst_groups <= 0) return;
+  if (!R.general || R.plain || R.dst_groups <= 0) return;
   const int t = threadIdx.x & 31;
   if (t >= R.dst_bw) return;
   if (threadIdx.x < 32) {
@@ -132,7 +133,30 @@ pages_gather_kernel(const PageRefDev* __restrict__ refs, unsigned long long* __r
     __syncthreads();
     uint32_t woff = 0;
     for (int x = 0; x < (int)(threadIdx.x >> 5); ++x) woff += warp_scan[x];
-    if (wl < R.dst_groups) {
+    if (R.plain) {
+      // a PLAIN page: the defined rows of the group take the next popcount(mask) values of the page (plain bytes
+      // each, at any byte address), NULL rows 0 -- into the column's row-aligned value array
+      if (wl < R.dst_groups) {
+        int64_t ord = (int64_t)rank0 + woff + (incl - mine);
+        const int size = R.plain;
+        uint8_t* out = reinterpret_cast<uint8_t*>(R.dst) + (uint64_t)wl * 64u * (uint32_t)size;
+        const int nrows = (int)min((int64_t)64, R.rows - wl * 64);
+        const int64_t nvals = (int64_t)(R.data_groups);  // (PLAIN: the number of VALUES the page holds)
+        for (int k = 0; k < nrows; ++k) {
+          uint64_t v = 0;
+          if ((mask_r >> k) & 1ull) {
+            if (ord < nvals) v = load_u64_unaligned(R.src + (uint64_t)ord * (uint32_t)size);
+            ++ord;
+          }
+          switch (size) {
+            case 1: out[k] = (uint8_t)v; break;
+            case 2: reinterpret_cast<uint16_t*>(out)[k] = (uint16_t)v; break;
+            case 4: reinterpret_cast<uint32_t*>(out)[k] = (uint32_t)v; break;
+            default: reinterpret_cast<uint64_t*>(out)[k] = v; break;
+          }
+        }
+      }
+    } else if (wl < R.dst_groups) {
       const int64_t rank = (int64_t)rank0 + woff + (incl - mine);
       const int64_t dg = rank >> 6;
       const int sh = (int)(rank & 63);
@@ -199,36 +223,43 @@ int launch_pages_gather(fle_ctx* ctx, const fle_page_ref* refs, int nrefs, uint6
   bool any_general = false;
   for (int i = 0; i < nrefs; ++i) {
     const fle_page_ref& r = refs[i];
-    if (r.src_bit_width < 1 || r.src_bit_width > 32 || r.dst_bit_width < r.src_bit_width || r.dst_bit_width > 32)
+    const bool plain = r.plain_size != 0;
+    if (plain && r.plain_size != 1 && r.plain_size != 2 && r.plain_size != 4 && r.plain_size != 8)
+      return set_error(ctx, FLE_E_INVALID, "PLAIN values are 1, 2, 4 or 8 bytes");
+    if (!plain && (r.src_bit_width < 1 || r.src_bit_width > 32 || r.dst_bit_width < r.src_bit_width || r.dst_bit_width > 32))
       return set_error(ctx, FLE_E_INVALID, "page bit widths outside 1..32 or destination narrower than the page");
     if (r.groups < 0 || r.rows < 0 || (r.groups > 0 && ((!r.src_dev && !(r.expand && r.src_bytes == 0)) || !r.dst_dev)))
       return set_error(ctx, FLE_E_INVALID, "bad page reference");
-    if (r.dst_bit < 0 || r.dst_bit > 63) return set_error(ctx, FLE_E_INVALID, "dst_bit outside 0..63");
+    if (!plain && (r.dst_bit < 0 || r.dst_bit > 63)) return set_error(ctx, FLE_E_INVALID, "dst_bit outside 0..63");
     if (r.expand && !r.def_src_dev) return set_error(ctx, FLE_E_INVALID, "a page is expanded through its definition levels");
     const int64_t rows = (r.rows == 0 && !r.expand && !r.def_src_dev) ? r.groups * 64 : r.rows;  // (callers that only copy groups)
     if (r.groups != (rows + 63) / 64) return set_error(ctx, FLE_E_INVALID, "a page has one group per 64 rows");
-    if (!r.expand && (uint64_t)r.groups * (uint64_t)r.src_bit_width * 8u > r.src_bytes)
+    if (!plain && !r.expand && (uint64_t)r.groups * (uint64_t)r.src_bit_width * 8u > r.src_bytes)
       return set_error(ctx, FLE_E_BUFFER, "page shorter than its groups");
+    if (plain && !r.expand && (uint64_t)rows * (uint64_t)r.plain_size > r.src_bytes)
+      return set_error(ctx, FLE_E_BUFFER, "page shorter than its values");
     if (r.def_src_dev && (uint64_t)((rows + 63) / 64) * 8u > r.def_bytes)
       return set_error(ctx, FLE_E_BUFFER, "definition levels shorter than the page's rows");
-    if (reinterpret_cast<uintptr_t>(r.dst_dev) & 7) return set_error(ctx, FLE_E_ALIGN, "plane destination must be 8-byte aligned");
+    if (reinterpret_cast<uintptr_t>(r.dst_dev) & (plain ? (uintptr_t)(r.plain_size - 1) : (uintptr_t)7))
+      return set_error(ctx, FLE_E_ALIGN, "plane destination must be 8-byte aligned (value slots: naturally aligned)");
     h[i].src = static_cast<const uint8_t*>(r.src_dev);
     h[i].dst = static_cast<uint64_t*>(r.dst_dev);
     h[i].def_src = static_cast<const uint8_t*>(r.def_src_dev);
     h[i].groups = r.groups;
     h[i].rows = rows;
-    h[i].src_bw = r.src_bit_width;
-    h[i].dst_bw = r.dst_bit_width;
+    h[i].src_bw = plain ? 1 : r.src_bit_width;
+    h[i].dst_bw = plain ? 1 : r.dst_bit_width;
     h[i].expand = r.expand ? 1 : 0;
-    h[i].pad = 0;
-    h[i].dst_bit = r.dst_bit;
-    h[i].dst_groups = (r.dst_bit + rows + 63) / 64;
+    h[i].plain = r.plain_size;
+    h[i].dst_bit = plain ? 0 : r.dst_bit;
+    h[i].dst_groups = (h[i].dst_bit + rows + 63) / 64;
     // a page that ends inside a group is placed as well (the next page ORs its rows into that group) -- unless it is
     // copied to a group boundary and nothing was said about rows at all
-    h[i].general = (r.expand || r.dst_bit != 0 || (rows & 63) != 0) ? 1 : 0;
+    h[i].general = (plain || r.expand || r.dst_bit != 0 || (rows & 63) != 0) ? 1 : 0;
     // (without expansion the definition levels are only counted: the data stream then holds every row)
-    h[i].data_groups = r.expand ? (int64_t)(r.src_bytes / ((uint64_t)r.src_bit_width * 8u)) : r.groups;
-    any_general = any_general || (h[i].general && (r.dst_bit != 0 || ((r.dst_bit + rows) & 63) != 0));  // groups shared with a neighbour
+    h[i].data_groups = plain ? (int64_t)(r.src_bytes / (uint64_t)r.plain_size)  // (values, not groups)
+                             : (r.expand ? (int64_t)(r.src_bytes / ((uint64_t)r.src_bit_width * 8u)) : r.groups);
+    any_general = any_general || (h[i].general && !plain && (r.dst_bit != 0 || ((r.dst_bit + rows) & 63) != 0));  // groups shared with a neighbour
     max_groups = std::max(max_groups, h[i].general ? h[i].dst_groups : r.groups);
   }
   const uint32_t* d = nullptr;
@@ -264,6 +295,7 @@ struct SlotDev {  // one materialised column
   int32_t bw, ndict, slot_size, tuple_off;
   const uint64_t* def;  // optional 1-bit definition levels, row-aligned
   int32_t null_off, pad;
+  const uint8_t* plain;  // optional: row-aligned PLAIN values (slot_size bytes each) instead of planes + dictionary
 };
 
 struct TileScanParams {
@@ -392,6 +424,16 @@ __global__ void __launch_bounds__(kTileThreads) tile_scan_kernel(const __grid_co
                 t[S.null_off] = 1;
                 continue;
               }
+              if (S.plain) {  // ParquetPlainEncoder::Decode: the value as it lies in the page
+                uint8_t* slot = t + S.tuple_off;
+                switch (S.slot_size) {
+                  case 1: *slot = S.plain[r]; break;
+                  case 2: *reinterpret_cast<uint16_t*>(slot) = reinterpret_cast<const uint16_t*>(S.plain)[r]; break;
+                  case 4: *reinterpret_cast<uint32_t*>(slot) = reinterpret_cast<const uint32_t*>(S.plain)[r]; break;
+                  default: *reinterpret_cast<uint64_t*>(slot) = reinterpret_cast<const uint64_t*>(S.plain)[r]; break;
+                }
+                continue;
+              }
               const uint32_t code = code_of_row(S.planes, S.bw, r);
               if (code >= (uint32_t)S.ndict) {  // DictDecoder::GetValue() == false (dict-encoding.h:325)
                 atomicAdd(P.bad_codes, 1ull);
@@ -490,14 +532,21 @@ int launch_assemble(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nrows, con
   std::memset(&P, 0, sizeof(P));
   for (int c = 0; c < ncols; ++c) {
     const fle_slot_desc& s = cols[c];
-    if (s.bit_width < 1 || s.bit_width > 32) return set_error(ctx, FLE_E_INVALID, "bit width outside 1..32");
+    const bool plain = s.plain_values_dev != nullptr;
+    if (!plain && (s.bit_width < 1 || s.bit_width > 32)) return set_error(ctx, FLE_E_INVALID, "bit width outside 1..32");
     if (s.slot_size != 1 && s.slot_size != 2 && s.slot_size != 4 && s.slot_size != 8)
       return set_error(ctx, FLE_E_INVALID, "slot sizes are 1, 2, 4 or 8 bytes");
     if (s.tuple_offset < 0 || s.tuple_offset + s.slot_size > tuple_size || (s.tuple_offset % s.slot_size))
       return set_error(ctx, FLE_E_INVALID, "slot outside the tuple or misaligned");
-    if (!s.planes_dev || !s.dict_dev || s.ndict < 0) return set_error(ctx, FLE_E_INVALID, "null column or dictionary");
-    if ((uint64_t)((nrows + 63) / 64) * s.bit_width * 8u > s.bytes) return set_error(ctx, FLE_E_BUFFER, "rows beyond the encoded buffer");
-    if (reinterpret_cast<uintptr_t>(s.planes_dev) & 7) return set_error(ctx, FLE_E_ALIGN, "planes must be 8-byte aligned");
+    if (plain) {
+      if (reinterpret_cast<uintptr_t>(s.plain_values_dev) & 7) return set_error(ctx, FLE_E_ALIGN, "value arrays must be 8-byte aligned");
+      if ((uint64_t)nrows * (uint64_t)s.slot_size > s.bytes) return set_error(ctx, FLE_E_BUFFER, "rows beyond the value array");
+      P.cols[c].plain = static_cast<const uint8_t*>(s.plain_values_dev);
+    } else {
+      if (!s.planes_dev || !s.dict_dev || s.ndict < 0) return set_error(ctx, FLE_E_INVALID, "null column or dictionary");
+      if ((uint64_t)((nrows + 63) / 64) * s.bit_width * 8u > s.bytes) return set_error(ctx, FLE_E_BUFFER, "rows beyond the encoded buffer");
+      if (reinterpret_cast<uintptr_t>(s.planes_dev) & 7) return set_error(ctx, FLE_E_ALIGN, "planes must be 8-byte aligned");
+    }
     P.cols[c].planes = static_cast<const uint64_t*>(s.planes_dev);
     P.cols[c].dict = s.dict_dev;
     P.cols[c].bw = s.bit_width;

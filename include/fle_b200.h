@@ -313,6 +313,12 @@ typedef struct fle_page_ref {
                              * dst_dev = column base + (first row / 64) * dst_bit_width * 8, dst_bit = first row % 64;
                              * the page then writes ceil((dst_bit + rows) / 64) groups, sharing the first / last one
                              * with its neighbours (all pages of a launch are placed after those groups were cleared) */
+  int32_t plain_size;       /* 0: an FLE page.  1 / 2 / 4 / 8: a PLAIN page (a column that overflowed its dictionary,
+                             * hdfs-parquet-table-writer.cc:276-279) -- src_dev = its values back to back, plain_size
+                             * bytes each, any alignment (the non-null ones only with expand = 1); dst_dev = the slot of
+                             * the page's first row in a row-aligned VALUE array (column base + first row * plain_size,
+                             * base 8-byte aligned); NULL rows get 0.  Bit widths and dst_bit are ignored. */
+  int32_t reserved;
 } fle_page_ref;
 /* Re-bases the FLE sections of all pages (of all columns) of a row group onto aligned plane arrays
  * in ONE launch (two when a page starts or ends inside a group) -- consecutive pages of a column go to
@@ -334,6 +340,9 @@ typedef struct fle_slot_desc {
                                * slot stays zero (ReadSlot's tuple->SetNull, hdfs-parquet-scanner.cc:515-531) */
   int32_t null_offset;     /* byte offset of the column's NULL indicator inside a tuple */
   int32_t reserved;
+  const void* plain_values_dev; /* optional: a PLAIN column -- row-aligned values of slot_size bytes (fle_pages_gather_dev,
+                                 * plain_size), copied into the slot as they are (ParquetPlainEncoder::Decode);
+                                 * planes_dev / dict_dev are not used then */
 } fle_slot_desc;
 /* Replaces the materialisation loop of AssembleRows (hdfs-parquet-scanner.cc:1134-1180: skip-distance
  * list, then ReadValue(skip) -> DictDecoder<T>::GetValue -> FleDecoder::Get(T*, skip) per survivor and

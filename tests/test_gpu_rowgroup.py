@@ -304,3 +304,74 @@ def test_pages_gather_places_ragged_pages(ctx, oracle, null_frac):
     if nullable:
         dd = oracle.unpack(dplanes.cpu().numpy().view(np.uint64), 1, 0, total)
         assert (dd == np.concatenate(want_def).astype(np.uint32)).all()
+
+
+@pytest.mark.parametrize("size", [1, 2, 4, 8])
+@pytest.mark.parametrize("null_frac", [None, 0.0, 0.1])
+def test_pages_gather_plain_pages_and_assemble(ctx, oracle, size, null_frac):
+    """PLAIN pages (a column that overflowed its dictionary, hdfs-parquet-table-writer.cc:276-279): values back to back at
+    any byte address, only the non-null ones for a nullable column, placed into a row-aligned value array; the assemble
+    kernel copies a survivor's value into its slot (ParquetPlainEncoder::Decode) or sets its NULL indicator."""
+    import torch
+    dt = {1: np.int8, 2: np.int16, 4: np.int32, 8: np.int64}[size]
+    rng = np.random.default_rng(size * 10 + (0 if null_frac is None else int(null_frac * 100) + 1))
+    page_rows = [64 * 30 + 1, 70001, 17, 64 * 2, 5000, 1]
+    nullable = null_frac is not None
+    blob = bytearray()
+    refs, want_vals, want_def = [], [], []
+    info = np.iinfo(dt)
+    for rows in page_rows:
+        defs = (rng.random(rows) >= null_frac) if nullable else np.ones(rows, dtype=bool)
+        vals = rng.integers(info.min, info.max, size=int(defs.sum()), dtype=dt)
+        full = np.zeros(rows, dtype=dt)
+        full[defs] = vals
+        want_vals.append(full)
+        want_def.append(defs)
+        blob += bytes(rng.integers(0, 255, size=int(rng.integers(17, 40)), dtype=np.uint8))
+        def_off = def_bytes = 0
+        if nullable:
+            dwords = oracle.pack(defs.astype(np.uint32), 1)
+            blob += np.int32(dwords.nbytes).tobytes()
+            def_off, def_bytes = len(blob), dwords.nbytes
+            blob += dwords.tobytes()
+        refs.append(dict(src_off=len(blob), src_bytes=vals.nbytes, def_off=def_off, def_bytes=def_bytes, rows=rows))
+        blob += vals.tobytes()
+    blob += bytes(16)
+    dblob = torch.from_numpy(np.frombuffer(bytes(blob), dtype=np.uint8).copy()).cuda()
+    total = sum(page_rows)
+    G = (total + 63) // 64
+    values = torch.full((G * 64 * size,), -1, dtype=torch.int8, device="cuda")
+    dplanes = torch.zeros(G, dtype=torch.int64, device="cuda")
+    row0, crefs = 0, []
+    for r in refs:
+        ref = dict(src_dev=dblob.data_ptr() + r["src_off"], src_bytes=r["src_bytes"], plain_size=size,
+                   dst_dev=values.data_ptr() + row0 * size, groups=(r["rows"] + 63) // 64, rows=r["rows"])
+        if nullable:
+            ref.update(def_src_dev=dblob.data_ptr() + r["def_off"], def_bytes=r["def_bytes"], expand=1)
+            crefs.append(dict(src_dev=dblob.data_ptr() + r["def_off"], src_bytes=r["def_bytes"], src_bit_width=1, dst_bit_width=1,
+                              dst_dev=dplanes.data_ptr() + (row0 // 64) * 8, groups=(r["rows"] + 63) // 64, rows=r["rows"], dst_bit=row0 % 64))
+        crefs.append(ref)
+        row0 += r["rows"]
+    nulls = ctx.pages_gather_dev(crefs)
+    torch.cuda.synchronize()
+    want = np.concatenate(want_vals)
+    defs = np.concatenate(want_def)
+    assert int(nulls.item()) == int((~defs).sum())
+    got = values.cpu().numpy().view(dt)[:total]
+    assert (got == want).all()
+    # survivors' tuples: [null byte][pad][slot]
+    sel = rng.random(total) < 0.1
+    words = np.packbits(np.concatenate([sel, np.zeros((-total) % 64, dtype=bool)]), bitorder="little").view(np.uint64)
+    bm = torch.from_numpy(words.view(np.int64).copy()).cuda()
+    tuple_size, off = 16, 8
+    slot = dict(slot_size=size, tuple_offset=off, plain_values_dev=values.data_ptr(), bytes=values.numel(), null_offset=0,
+                def_planes_dev=dplanes.data_ptr() if nullable else None)
+    k = int(sel.sum())
+    tuples, cnt, bad = ctx.assemble_rows_dev(bm, total, [slot], tuple_size, k)
+    torch.cuda.synchronize()
+    assert int(cnt.item()) == k and int(bad.item()) == 0
+    rows = np.nonzero(sel)[0]
+    wt = np.zeros((k, tuple_size), dtype=np.uint8)
+    wt[:, 0] = (~defs[rows]).astype(np.uint8)
+    wt[:, off:off + size] = want[rows].copy().view(np.uint8).reshape(k, size)
+    assert (tuples.cpu().numpy()[:k] == wt).all()
