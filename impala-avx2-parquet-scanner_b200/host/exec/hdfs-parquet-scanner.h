@@ -32,7 +32,9 @@
 //     counted on the way.  ONE fused fle_eval_dev covers the row group -- the plain program, or, when the
 //     row group holds NULLs, the program with `AND def_c = 1` per nullable column / leaf -- and
 //     fle_assemble_rows_dev writes the survivors' tuples, NULL indicators included; two host synchronisations
-//     per row group however many pages it holds.  Applies to fresh readers over dictionary pages;
+//     per row group however many pages it holds.  Applies to fresh readers whose predicate columns are
+//     dictionary-encoded; a column that is PLAIN throughout (it overflowed its dictionary) rides along when it is
+//     only materialised: its values are placed into a row-aligned value array the tuples are copied from;
 //   * per leaf (the reference's structure): every leaf call goes through ColumnReader<T> ->
 //     DictDecoder<T> -> FleDecoder, which evaluates the WHOLE page on the GPU on first use and
 //     then serves the <=1024-row windows from the cached bitmap;
@@ -95,7 +97,7 @@ class HdfsParquetScanner {
   HdfsParquetScanner() : tuple_size_(0), fused_enabled_(true), fused_pos_(0), fused_rows_(0),
       fused_evals_(0), leaf_windows_(0), device_materialise_(true), device_spans_(0),
       row_group_batch_(true), batch_state_(0), batch_bank_(0), batch_rows_(0), row_group_batches_(0),
-      batch_ncols_nulls_(0), batch_nulls_seen_(false), row_group_null_batches_(0) {}
+      batch_eval_cols_(0), batch_ncols_nulls_(0), batch_nulls_seen_(false), row_group_null_batches_(0) {}
   ~HdfsParquetScanner();
 
   // CreateColumnReaders/CreateReader (:1410-1451, :670-720) + InitColumns (:1453-1531) for
@@ -186,6 +188,8 @@ class HdfsParquetScanner {
     void* def_dev;            // nullable columns: the pages' definition levels as one row-aligned 1-bit plane array
     int bit_width;            // widest page
     int ndict;
+    bool plain;               // every page PLAIN (the column overflowed its dictionary): planes_dev is a row-aligned value array
+    int eval_col;             // the column's index among the columns the program is evaluated over (-1: a PLAIN column)
   };
   bool row_group_batch_;
   int batch_state_;           // 0 not tried, 1 uploaded, -1 does not qualify
@@ -200,6 +204,7 @@ class HdfsParquetScanner {
   // simple-predicates.h / hdfs-parquet-scanner.cc:342-345
   std::vector<fle_pred_node> batch_prog_nulls_;
   std::vector<int> batch_def_col_;   // per column: index of its definition-level column in the NULL program, -1 = none
+  int batch_eval_cols_;              // dictionary columns = columns of the plain program
   int batch_ncols_nulls_;            // columns of the NULL program (0: it does not fit, NULL row groups take the page paths)
   bool batch_nulls_seen_;            // an earlier row group of this scanner held NULLs: start with the NULL program
   int64_t row_group_null_batches_;
@@ -769,6 +774,7 @@ inline bool HdfsParquetScanner::StartRowGroupUpload() {
   // row offset of the column's ONE row-aligned plane array (fle_page_ref.dst_bit).
   struct PageView { const uint8_t* fle; int64_t fle_bytes; int bw; const uint8_t* def; int64_t def_bytes; int64_t rows; };
   std::vector<std::vector<PageView> > views(ncols);
+  std::vector<char> col_is_plain(ncols, 0);
   int64_t total_rows = 0;
   for (int c = 0; c < ncols; ++c) {
     BaseColumnReader* r = column_readers_[c];
@@ -776,9 +782,14 @@ inline bool HdfsParquetScanner::StartRowGroupUpload() {
     if (!r->fresh() || npages == 0 || r->max_def_level() > 1) return false;
     views[c].resize(npages);
     int64_t col_rows = 0;
+    // a column is dictionary-encoded throughout, or PLAIN throughout (it overflowed its dictionary in an earlier row
+    // group, hdfs-parquet-table-writer.cc:276-279) -- then it can be materialised but carries no predicate here
+    const bool col_plain = r->pages()[0].encoding == parquet_encoding::PLAIN;
+    col_is_plain[c] = col_plain;
     for (size_t p = 0; p < npages; ++p) {
       const DataPage& pg = r->pages()[p];
-      if (pg.encoding != parquet_encoding::FLE_DICTIONARY && pg.encoding != parquet_encoding::PLAIN_DICTIONARY) return false;
+      if (col_plain ? pg.encoding != parquet_encoding::PLAIN
+                    : (pg.encoding != parquet_encoding::FLE_DICTIONARY && pg.encoding != parquet_encoding::PLAIN_DICTIONARY)) return false;
       if (pg.num_values <= 0) return false;
       col_rows += pg.num_values;
       PageView& v = views[c][p];
@@ -797,7 +808,12 @@ inline bool HdfsParquetScanner::StartRowGroupUpload() {
         d += 4 + nd;
         left -= 4 + nd;
       }
-      if (left < 1) {  // all-NULL page: no width byte, no data (:921)
+      if (col_plain) {  // values back to back, r->slot_size_ bytes each (only the non-null ones)
+        v.bw = 1;
+        v.fle = d;
+        v.fle_bytes = left;
+        if (v.def == NULL && left < v.rows * r->slot_size_) return false;
+      } else if (left < 1) {  // all-NULL page: no width byte, no data (:921)
         if (v.def == NULL) return false;
         v.bw = 1;
         v.fle = d;
@@ -809,7 +825,7 @@ inline bool HdfsParquetScanner::StartRowGroupUpload() {
       }
       if (v.bw < 1 || v.bw > 32) return false;
       // (a nullable page's FLE section holds only the non-null values: it may be shorter than the rows)
-      if (v.def == NULL && v.fle_bytes < (v.rows + 63) / 64 * v.bw * 8) return false;
+      if (!col_plain && v.def == NULL && v.fle_bytes < (v.rows + 63) / 64 * v.bw * 8) return false;
     }
     if (c == 0) total_rows = col_rows;
     else if (col_rows != total_rows) return false;
@@ -817,10 +833,24 @@ inline bool HdfsParquetScanner::StartRowGroupUpload() {
   if (total_rows >= (int64_t(1) << 31)) return false;
   batch_prog_ = FusedProgram();
   if (!LowerPredicates(&batch_prog_)) return false;
+  batch_cols_.assign(ncols, BatchColumn());
+  batch_eval_cols_ = 0;
+  for (int c = 0; c < ncols; ++c) {
+    batch_cols_[c].plain = col_is_plain[c] != 0;
+    batch_cols_[c].eval_col = col_is_plain[c] ? -1 : batch_eval_cols_++;
+  }
+  std::vector<int> node_col(batch_prog_.nodes.size(), -1);  // the leaves' columns as the scanner numbers them
+  for (size_t i = 0; i < batch_prog_.nodes.size(); ++i) {
+    fle_pred_node& nd = batch_prog_.nodes[i];
+    if (nd.op == FLE_OP_AND || nd.op == FLE_OP_OR) continue;
+    if (nd.col < 0 || nd.col >= ncols || col_is_plain[nd.col]) return false;  // (a predicate on a PLAIN column: the page paths)
+    node_col[i] = nd.col;
+    nd.col = batch_cols_[nd.col].eval_col;
+  }
+  if (batch_eval_cols_ == 0) return false;
   fle_ctx* ctx = FleGpu::ctx();
   if (ctx == NULL) return false;
   batch_bank_ = FleGpu::NextBank();
-  batch_cols_.assign(ncols, BatchColumn());
   batch_refs_.clear();
   const int64_t total_groups = (total_rows + 63) / 64;
   for (int c = 0; c < ncols; ++c) {
@@ -845,7 +875,9 @@ inline bool HdfsParquetScanner::StartRowGroupUpload() {
     const bool one_copy = ascending && (hi - lo) <= sum + sum / 4 + 4096;
     const size_t image_bytes = one_copy ? static_cast<size_t>(hi - lo) : static_cast<size_t>(sum + 16 * npages);
     bc.image_dev = FleGpu::DeviceScratch(batch_bank_, 3 * c, image_bytes + 64);
-    bc.planes_dev = FleGpu::DeviceScratch(batch_bank_, 3 * c + 1, static_cast<size_t>(total_groups) * bc.bit_width * 8 + 64);
+    bc.planes_dev = FleGpu::DeviceScratch(batch_bank_, 3 * c + 1,
+                                          bc.plain ? static_cast<size_t>(total_groups) * 64 * r->slot_size_ + 64
+                                                   : static_cast<size_t>(total_groups) * bc.bit_width * 8 + 64);
     bc.def_dev = NULL;
     if (r->max_def_level() > 0) {
       bc.def_dev = FleGpu::DeviceScratch(batch_bank_, 24 + c, static_cast<size_t>(total_groups) * 8 + 64);
@@ -889,6 +921,11 @@ inline bool HdfsParquetScanner::StartRowGroupUpload() {
       ref.dst_dev = static_cast<uint8_t*>(bc.planes_dev) + static_cast<size_t>(g0) * bc.bit_width * 8;
       ref.dst_bit = static_cast<int32_t>(row0 & 63);
       ref.groups = (v.rows + 63) / 64;
+      if (bc.plain) {  // value slots instead of plane groups
+        ref.plain_size = r->slot_size_;
+        ref.dst_dev = static_cast<uint8_t*>(bc.planes_dev) + static_cast<size_t>(row0) * r->slot_size_;
+        ref.dst_bit = 0;
+      }
       ref.rows = v.rows;
       if (v.def != NULL) {
         // the page's values are indexed by non-null ordinal: expanded into row-aligned planes (code 0 at NULL rows;
@@ -904,7 +941,7 @@ inline bool HdfsParquetScanner::StartRowGroupUpload() {
         dref.src_bytes = ref.def_bytes;
         dref.src_bit_width = dref.dst_bit_width = 1;
         dref.dst_dev = static_cast<uint8_t*>(bc.def_dev) + static_cast<size_t>(g0) * 8;
-        dref.dst_bit = ref.dst_bit;
+        dref.dst_bit = static_cast<int32_t>(row0 & 63);
         dref.groups = ref.groups;
         dref.rows = v.rows;
         batch_refs_.push_back(dref);
@@ -918,7 +955,7 @@ inline bool HdfsParquetScanner::StartRowGroupUpload() {
   // (once per column behind a pure AND tree, per leaf otherwise)
   batch_prog_nulls_.clear();
   batch_def_col_.assign(ncols, -1);
-  batch_ncols_nulls_ = ncols;
+  batch_ncols_nulls_ = batch_eval_cols_;
   {
     bool and_only = true;
     for (size_t i = 0; i < batch_prog_.nodes.size(); ++i) and_only = and_only && batch_prog_.nodes[i].op != FLE_OP_OR;
@@ -927,15 +964,16 @@ inline bool HdfsParquetScanner::StartRowGroupUpload() {
       const fle_pred_node& nd = batch_prog_.nodes[i];
       batch_prog_nulls_.push_back(nd);
       if (nd.op == FLE_OP_AND || nd.op == FLE_OP_OR) continue;
-      if (nd.col < 0 || nd.col >= ncols || column_readers_[nd.col]->max_def_level() == 0) continue;
-      if (batch_def_col_[nd.col] < 0) {
-        batch_def_col_[nd.col] = batch_ncols_nulls_++;
-        used.push_back(nd.col);
+      const int oc = node_col[i];
+      if (oc < 0 || column_readers_[oc]->max_def_level() == 0) continue;
+      if (batch_def_col_[oc] < 0) {
+        batch_def_col_[oc] = batch_ncols_nulls_++;
+        used.push_back(oc);
       }
       if (!and_only) {
         fle_pred_node eq;
         memset(&eq, 0, sizeof(eq));
-        eq.op = FLE_OP_EQ; eq.col = batch_def_col_[nd.col]; eq.code = 1;
+        eq.op = FLE_OP_EQ; eq.col = batch_def_col_[oc]; eq.code = 1;
         batch_prog_nulls_.push_back(eq);
         fle_pred_node an;
         memset(&an, 0, sizeof(an));
@@ -976,17 +1014,23 @@ inline bool HdfsParquetScanner::DeviceRowGroup(std::vector<uint8_t>* rows, int64
   if (!bitmap_dev || !hdr_dev || !hdr) return false;
   if (FleGpu::Check(fle_prefetch_fence(ctx), "fle_prefetch_fence") != FLE_OK) return false;
   if (FleGpu::Check(fle_pages_gather_dev(ctx, &batch_refs_[0], static_cast<int>(batch_refs_.size()), hdr_dev), "fle_pages_gather_dev") != FLE_OK) return false;
-  std::vector<fle_col_desc> cols(std::max(ncols, batch_ncols_nulls_));
+  std::vector<fle_col_desc> cols(std::max(batch_eval_cols_, batch_ncols_nulls_));
   std::vector<fle_slot_desc> slots(ncols);
   for (int c = 0; c < ncols; ++c) {
     BaseColumnReader* r = column_readers_[c];
-    memset(&cols[c], 0, sizeof(fle_col_desc));
-    cols[c].planes = batch_cols_[c].planes_dev;
-    cols[c].bytes = static_cast<uint64_t>(groups) * batch_cols_[c].bit_width * 8;
-    cols[c].bit_width = batch_cols_[c].bit_width;
     memset(&slots[c], 0, sizeof(fle_slot_desc));
-    slots[c].planes_dev = batch_cols_[c].planes_dev;
-    slots[c].bytes = cols[c].bytes;
+    if (batch_cols_[c].plain) {
+      slots[c].plain_values_dev = batch_cols_[c].planes_dev;
+      slots[c].bytes = static_cast<uint64_t>(groups) * 64 * r->slot_size_;
+    } else {
+      fle_col_desc& e = cols[batch_cols_[c].eval_col];
+      memset(&e, 0, sizeof(fle_col_desc));
+      e.planes = batch_cols_[c].planes_dev;
+      e.bytes = static_cast<uint64_t>(groups) * batch_cols_[c].bit_width * 8;
+      e.bit_width = batch_cols_[c].bit_width;
+      slots[c].planes_dev = batch_cols_[c].planes_dev;
+      slots[c].bytes = e.bytes;
+    }
     slots[c].bit_width = batch_cols_[c].bit_width;
     slots[c].slot_size = r->slot_size_;
     slots[c].dict_dev = batch_cols_[c].dict_dev;
@@ -1012,7 +1056,7 @@ inline bool HdfsParquetScanner::DeviceRowGroup(std::vector<uint8_t>* rows, int64
   uint64_t passed = 0;
   for (;;) {
     int rc = with_nulls ? fle_eval_dev(ctx, &cols[0], batch_ncols_nulls_, &batch_prog_nulls_[0], static_cast<int>(batch_prog_nulls_.size()), 0, n, bitmap_dev, NULL)
-                        : fle_eval_dev(ctx, &cols[0], ncols, &batch_prog_.nodes[0], static_cast<int>(batch_prog_.nodes.size()), 0, n, bitmap_dev, NULL);
+                        : fle_eval_dev(ctx, &cols[0], batch_eval_cols_, &batch_prog_.nodes[0], static_cast<int>(batch_prog_.nodes.size()), 0, n, bitmap_dev, NULL);
     if (rc == FLE_E_UNSUPPORTED) return false;
     if (FleGpu::Check(rc, "fle_eval_dev(row group)") != FLE_OK) return false;
     rc = fle_assemble_rows_dev(ctx, bitmap_dev, n, &slots[0], ncols, tuple_size_, tuples_dev, n, hdr_dev + 1, hdr_dev + 2);
