@@ -493,6 +493,66 @@ TEST(Scanner, RowGroupBatchPlainMaterialisedColumn) {
   }
 }
 
+// Differential fuzz: random row counts, page cuts per column, nullability, NULL fractions and predicate shapes; the
+// row-group batch must return the page paths' tuples byte for byte (those are checked against the truth above).
+TEST(Scanner, RowGroupBatchFuzz) {
+  srand(2024);
+  int batches = 0;
+  for (int it = 0; it < 24; ++it) {
+    const int n = 1 + rand() % 90000;
+    const double nf = (it % 4 == 0) ? 0.0 : (rand() % 1000) / 1000.0 * ((it % 3) ? 0.1 : 1.0);
+    Table t = MakeTable(n, nf, 1000 + it);
+    bool nullable[3];
+    int pp[3];
+    for (int c = 0; c < 3; ++c) {
+      nullable[c] = rand() % 3 != 0;
+      pp[c] = (rand() % 4 == 0) ? (1 << 30) : 1 + rand() % (n + 10);
+      if (pp[c] < n / 40) pp[c] = n / 40 + 1;  // (at most ~40 pages per column)
+    }
+    const int shape = rand() % 3;
+    vector<uint8_t> rows[2];
+    int64_t passed[2] = {0, 0};
+    for (int batch = 1; batch >= 0; --batch) {
+      ColumnChunk c0 = WriteColumn(t.shipdate, t.nn_shipdate, pp[0], nullable[0]);
+      ColumnChunk c1 = WriteColumn(t.discount, t.nn_discount, pp[1], nullable[1]);
+      ColumnChunk c2 = WriteColumn(t.quantity, t.nn_quantity, pp[2], nullable[2]);
+      HdfsParquetScanner scanner;
+      int i0 = scanner.AddColumn<int32_t>(nullable[0], &c0.dict_page[0], c0.dict_page.size(), c0.pages);
+      int i1 = scanner.AddColumn<int32_t>(nullable[1], &c1.dict_page[0], c1.dict_page.size(), c1.pages);
+      int i2 = scanner.AddColumn<int32_t>(nullable[2], &c2.dict_page[0], c2.dict_page.size(), c2.pages);
+      GeOperate<int32_t> ge0(i0, 8730);
+      LeOperate<int32_t> le0(i0, 9094);
+      AndOperate between0(&ge0, &le0);
+      GeOperate<int32_t> ge1(i1, 5);
+      LtOperate<int32_t> lt2(i2, 24);
+      vector<int32_t> qs;
+      qs.push_back(3); qs.push_back(17); qs.push_back(49); qs.push_back(1000);
+      InOperate<int32_t> in2(i2, qs);
+      OrOperate or01(&between0, &ge1);
+      OrOperate or012(&or01, &in2);
+      if (shape == 0) {  // conjunct chain
+        scanner.AddSimplePredicate(&between0);
+        scanner.AddSimplePredicate(&ge1);
+        scanner.AddSimplePredicate(&lt2);
+      } else if (shape == 1) {  // (a OR b) AND c
+        scanner.AddSimplePredicate(&or01);
+        scanner.AddSimplePredicate(&lt2);
+      } else {  // a OR b OR c: survivors with NULLs in other columns
+        scanner.AddSimplePredicate(&or012);
+      }
+      scanner.set_row_group_batch(batch != 0);
+      EXPECT_TRUE(scanner.AssembleRows(t.n, &rows[batch], &passed[batch]).ok());
+      if (batch) batches += scanner.row_group_batches();
+    }
+    EXPECT_EQ(passed[0], passed[1]);
+    EXPECT_TRUE(rows[0] == rows[1]);
+    if (rows[0] != rows[1])
+      std::printf("    fuzz case %d differs: n=%d null_frac=%.3f pages=%d/%d/%d nullable=%d%d%d shape=%d\n", it, n, nf, pp[0], pp[1], pp[2],
+                  (int)nullable[0], (int)nullable[1], (int)nullable[2], shape);
+  }
+  EXPECT_EQ(batches, 24);
+}
+
 // The deviations DESIGN.md lists, pinned in both modes (the reference lines are cited in util/fle-gpu-context.h)
 TEST(Scanner, ReferenceCompatSwitch) {
   // 1. Skip() landing exactly on the end of the data (fle-encoding.h:381-402)
