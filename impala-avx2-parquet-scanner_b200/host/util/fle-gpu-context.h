@@ -31,6 +31,12 @@ class FleGpu {
       const char* dev = std::getenv("FLE_B200_DEVICE");
       int rc = fle_ctx_create(dev ? std::atoi(dev) : 0, NULL, &h.ctx);
       if (rc != FLE_OK) Fail(rc, "fle_ctx_create");
+      // a scanner thread never waits for the compiler: program shapes are specialised on a thread of the library's
+      // own and the interpreting kernels serve the row groups until the kernel is there (FLE_B200_EVAL_JIT overrides)
+      if (h.ctx) {
+        const char* jit = std::getenv("FLE_B200_EVAL_JIT");
+        fle_ctx_set_option(h.ctx, "eval_jit", jit ? std::atoi(jit) : 3);
+      }
     }
     const int want = reference_compat() ? 1 : 0;
     if (h.ctx && h.compat_applied != want) {
