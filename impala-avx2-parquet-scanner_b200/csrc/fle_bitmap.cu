@@ -86,15 +86,6 @@ bitmap_block_counts_kernel(const uint64_t* __restrict__ bm, int64_t nbits, int64
   if (threadIdx.x == 0) block_sums[blockIdx.x] = t;
 }
 
-__global__ void __launch_bounds__(kBmThreads)
-sum_u64_kernel(const uint64_t* __restrict__ v, int n, uint64_t* __restrict__ out) {
-  __shared__ uint64_t warp_buf[kBmThreads / 32];
-  uint64_t c = 0;
-  for (int i = threadIdx.x; i < n; i += kBmThreads) c += v[i];
-  const uint64_t t = block_sum<kBmThreads>(c, warp_buf);
-  if (threadIdx.x == 0) *out = t;
-}
-
 // 64 bits of sub starting at bit offset `pos` (bits past n_sub read as 0)
 __device__ __forceinline__ uint64_t gather_bits(const uint64_t* __restrict__ sub, int64_t n_sub,
                                                 int64_t pos) {
@@ -234,21 +225,38 @@ int launch_deposit(fle_ctx* ctx, const uint64_t* def_planes_dev, int64_t n_root,
   return FLE_OK;
 }
 
+// popcount of a bitmap in ONE launch: grid-stride, eight independent 8-byte loads in flight per thread, one atomic per CTA
+// (two launches -- block counts, then their sum -- cost 19.5 us for the 32 MB bitmap of 2^28 rows, most of it launch gaps)
+__global__ void __launch_bounds__(kBmThreads)
+bitmap_count_kernel(const uint64_t* __restrict__ bm, int64_t nbits, int64_t nwords, unsigned long long* __restrict__ count) {
+  __shared__ uint64_t warp_buf[kBmThreads / 32];
+  const int64_t stride = (int64_t)gridDim.x * kBmThreads;
+  uint64_t c = 0;
+  // every pass has its eight loads in flight at once, the ragged last pass included (a scalar remainder loop is a
+  // chain of dependent DRAM round trips: 5 us of a 16 us kernel)
+  for (int64_t w = (int64_t)blockIdx.x * kBmThreads + threadIdx.x; w < nwords; w += 8 * stride) {
+    uint64_t v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = ldg_stream64(bm + min(w + j * stride, nwords - 1));  // (unconditional: the loads batch)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c += (w + j * stride < nwords) ? __popcll(v[j]) : 0;
+  }
+  // bits past the end of the last word do not count
+  if (blockIdx.x == 0 && threadIdx.x == 0) c -= __popcll(bm[nwords - 1] & ~tail_mask_word(nwords - 1, nbits));
+  const uint64_t t = block_sum<kBmThreads>(c, warp_buf);
+  if (threadIdx.x == 0 && t) atomicAdd(count, (unsigned long long)t);
+}
+
 int launch_bitmap_count(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nbits, uint64_t* count_dev) {
   if (nbits < 0 || !count_dev) return set_error(ctx, FLE_E_INVALID, "bad bitmap_count arguments");
-  if (nbits == 0) {
-    FLE_CUDA_TRY(ctx, cudaMemsetAsync(count_dev, 0, 8, ctx->stream));
-    return FLE_OK;
-  }
+  FLE_CUDA_TRY(ctx, cudaMemsetAsync(count_dev, 0, 8, ctx->stream));
+  if (nbits == 0) return FLE_OK;
   const int64_t nwords = (nbits + 63) / 64;
-  const int nblocks = (int)((nwords + kBmWordsPerBlock - 1) / kBmWordsPerBlock);
-  int rc = ensure_scratch(ctx, nblocks, 0);
-  if (rc != FLE_OK) return rc;
-  bitmap_block_counts_kernel<<<nblocks, kBmThreads, 0, ctx->stream>>>(bitmap_dev, nbits, nwords, ctx->d_partial);
-  sum_u64_kernel<<<1, kBmThreads, 0, ctx->stream>>>(ctx->d_partial, nblocks, count_dev);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 8, (nwords + kBmThreads * 8 - 1) / (kBmThreads * 8)));
+  bitmap_count_kernel<<<grid, kBmThreads, 0, ctx->stream>>>(bitmap_dev, nbits, nwords, reinterpret_cast<unsigned long long*>(count_dev));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(ctx, e, "bitmap_count launch");
-  ctx->launches += 2;
+  ctx->launches += 1;
   return FLE_OK;
 }
 
