@@ -69,7 +69,7 @@ class PageRef(C.Structure):
     _fields_ = [("src_dev", C.c_void_p), ("src_bytes", C.c_uint64), ("src_bit_width", C.c_int32), ("dst_bit_width", C.c_int32),
                 ("dst_dev", C.c_void_p), ("groups", C.c_int64), ("def_src_dev", C.c_void_p), ("def_bytes", C.c_uint64),
                 ("rows", C.c_int64), ("expand", C.c_int32), ("dst_bit", C.c_int32),
-                ("plain_size", C.c_int32), ("reserved", C.c_int32)]
+                ("plain_size", C.c_int32), ("ndict", C.c_int32), ("dict_dev", C.c_void_p)]
 
 
 class SlotDesc(C.Structure):

@@ -39,6 +39,8 @@ struct PageRefDev {
   int32_t dst_bit;         // position of the page's first row inside its first destination group
   int32_t expand;
   int32_t plain;           // 0: FLE page; 1 / 2 / 4 / 8: PLAIN page of that many bytes per value (dst = value slots)
+  const uint8_t* dict;     // plain != 0 and set: the page is dictionary-encoded FLE after all, its codes are looked up here
+  int32_t ndict, pad2;
 };
 
 constexpr int kGatherGroupsPerCta = 256;
@@ -142,10 +144,35 @@ pages_gather_kernel(const PageRefDev* __restrict__ refs, unsigned long long* __r
         uint8_t* out = reinterpret_cast<uint8_t*>(R.dst) + (uint64_t)wl * 64u * (uint32_t)size;
         const int nrows = (int)min((int64_t)64, R.rows - wl * 64);
         const int64_t nvals = (int64_t)(R.data_groups);  // (PLAIN: the number of VALUES the page holds)
+        // a dictionary page of a column whose later pages are PLAIN (the column overflowed its dictionary inside this
+        // row group): the codes of the group's rows sit in at most two groups of the page's stream; value = dict[code]
+        uint64_t ga[32], gb[32];
+        const int sbw = R.src_bw;
+        if (R.dict) {
+          const int64_t dg = ord >> 6;
+          for (int i = 0; i < sbw; ++i) {
+            ga[i] = (mine && dg < R.data_groups) ? load_u64_unaligned(R.src + ((uint64_t)dg * sbw + i) * 8u) : 0ull;
+            gb[i] = (mine && dg + 1 < R.data_groups) ? load_u64_unaligned(R.src + ((uint64_t)(dg + 1) * sbw + i) * 8u) : 0ull;
+          }
+        }
+        const int64_t ord_group0 = ord >> 6;
         for (int k = 0; k < nrows; ++k) {
           uint64_t v = 0;
           if ((mask_r >> k) & 1ull) {
-            if (ord < nvals) v = load_u64_unaligned(R.src + (uint64_t)ord * (uint32_t)size);
+            if (R.dict) {
+              const uint64_t* g = (ord >> 6) == ord_group0 ? ga : gb;
+              const int sh = 63 - (int)(ord & 63);
+              uint32_t code = 0;
+              for (int i = 0; i < sbw; ++i) code |= (uint32_t)((g[i] >> sh) & 1ull) << i;
+              if (code < (uint32_t)R.ndict) {
+                const uint8_t* e = R.dict + (uint64_t)code * (uint32_t)size;
+                v = size == 8 ? *reinterpret_cast<const uint64_t*>(e)
+                              : (size == 4 ? *reinterpret_cast<const uint32_t*>(e)
+                                           : (size == 2 ? *reinterpret_cast<const uint16_t*>(e) : *e));
+              }
+            } else if (ord < nvals) {
+              v = load_u64_unaligned(R.src + (uint64_t)ord * (uint32_t)size);
+            }
             ++ord;
           }
           switch (size) {
@@ -226,6 +253,9 @@ int launch_pages_gather(fle_ctx* ctx, const fle_page_ref* refs, int nrefs, uint6
     const bool plain = r.plain_size != 0;
     if (plain && r.plain_size != 1 && r.plain_size != 2 && r.plain_size != 4 && r.plain_size != 8)
       return set_error(ctx, FLE_E_INVALID, "PLAIN values are 1, 2, 4 or 8 bytes");
+    const bool coded = plain && r.dict_dev != nullptr;  // a dictionary page decoded into a value array
+    if (coded && (r.src_bit_width < 1 || r.src_bit_width > 32 || r.ndict < 0 || (reinterpret_cast<uintptr_t>(r.dict_dev) & (uintptr_t)(r.plain_size - 1))))
+      return set_error(ctx, FLE_E_INVALID, "bad dictionary or bit width of a dictionary page that is decoded into values");
     if (!plain && (r.src_bit_width < 1 || r.src_bit_width > 32 || r.dst_bit_width < r.src_bit_width || r.dst_bit_width > 32))
       return set_error(ctx, FLE_E_INVALID, "page bit widths outside 1..32 or destination narrower than the page");
     if (r.groups < 0 || r.rows < 0 || (r.groups > 0 && ((!r.src_dev && !(r.expand && r.src_bytes == 0)) || !r.dst_dev)))
@@ -236,8 +266,10 @@ int launch_pages_gather(fle_ctx* ctx, const fle_page_ref* refs, int nrefs, uint6
     if (r.groups != (rows + 63) / 64) return set_error(ctx, FLE_E_INVALID, "a page has one group per 64 rows");
     if (!plain && !r.expand && (uint64_t)r.groups * (uint64_t)r.src_bit_width * 8u > r.src_bytes)
       return set_error(ctx, FLE_E_BUFFER, "page shorter than its groups");
-    if (plain && !r.expand && (uint64_t)rows * (uint64_t)r.plain_size > r.src_bytes)
+    if (plain && !coded && !r.expand && (uint64_t)rows * (uint64_t)r.plain_size > r.src_bytes)
       return set_error(ctx, FLE_E_BUFFER, "page shorter than its values");
+    if (coded && !r.expand && (uint64_t)r.groups * (uint64_t)r.src_bit_width * 8u > r.src_bytes)
+      return set_error(ctx, FLE_E_BUFFER, "page shorter than its groups");
     if (r.def_src_dev && (uint64_t)((rows + 63) / 64) * 8u > r.def_bytes)
       return set_error(ctx, FLE_E_BUFFER, "definition levels shorter than the page's rows");
     if (reinterpret_cast<uintptr_t>(r.dst_dev) & (plain ? (uintptr_t)(r.plain_size - 1) : (uintptr_t)7))
@@ -247,7 +279,10 @@ int launch_pages_gather(fle_ctx* ctx, const fle_page_ref* refs, int nrefs, uint6
     h[i].def_src = static_cast<const uint8_t*>(r.def_src_dev);
     h[i].groups = r.groups;
     h[i].rows = rows;
-    h[i].src_bw = plain ? 1 : r.src_bit_width;
+    h[i].dict = coded ? static_cast<const uint8_t*>(r.dict_dev) : nullptr;
+    h[i].ndict = coded ? r.ndict : 0;
+    h[i].pad2 = 0;
+    h[i].src_bw = (plain && !coded) ? 1 : r.src_bit_width;
     h[i].dst_bw = plain ? 1 : r.dst_bit_width;
     h[i].expand = r.expand ? 1 : 0;
     h[i].plain = r.plain_size;
@@ -257,7 +292,7 @@ int launch_pages_gather(fle_ctx* ctx, const fle_page_ref* refs, int nrefs, uint6
     // copied to a group boundary and nothing was said about rows at all
     h[i].general = (plain || r.expand || r.dst_bit != 0 || (rows & 63) != 0) ? 1 : 0;
     // (without expansion the definition levels are only counted: the data stream then holds every row)
-    h[i].data_groups = plain ? (int64_t)(r.src_bytes / (uint64_t)r.plain_size)  // (values, not groups)
+    h[i].data_groups = (plain && !coded) ? (int64_t)(r.src_bytes / (uint64_t)r.plain_size)  // (values, not groups)
                              : (r.expand ? (int64_t)(r.src_bytes / ((uint64_t)r.src_bit_width * 8u)) : r.groups);
     any_general = any_general || (h[i].general && !plain && (r.dst_bit != 0 || ((r.dst_bit + rows) & 63) != 0));  // groups shared with a neighbour
     max_groups = std::max(max_groups, h[i].general ? h[i].dst_groups : r.groups);

@@ -33,8 +33,9 @@
 //     row group holds NULLs, the program with `AND def_c = 1` per nullable column / leaf -- and
 //     fle_assemble_rows_dev writes the survivors' tuples, NULL indicators included; two host synchronisations
 //     per row group however many pages it holds.  Applies to fresh readers whose predicate columns are
-//     dictionary-encoded; a column that is PLAIN throughout (it overflowed its dictionary) rides along when it is
-//     only materialised: its values are placed into a row-aligned value array the tuples are copied from;
+//     dictionary-encoded; a column with PLAIN pages (it overflowed its dictionary: dictionary pages first, PLAIN
+//     pages from there on) rides along when it is only materialised: its values -- decoded through the dictionary
+//     or copied -- are placed into a row-aligned value array the tuples are copied from;
 //   * per leaf (the reference's structure): every leaf call goes through ColumnReader<T> ->
 //     DictDecoder<T> -> FleDecoder, which evaluates the WHOLE page on the GPU on first use and
 //     then serves the <=1024-row windows from the cached bitmap;
@@ -772,7 +773,7 @@ inline bool HdfsParquetScanner::StartRowGroupUpload() {
   // number of rows (the reference's writer closes a dictionary page after 524225 rows,
   // hdfs-parquet-table-writer.cc:387) and the columns may cut their pages differently: every page is placed at its
   // row offset of the column's ONE row-aligned plane array (fle_page_ref.dst_bit).
-  struct PageView { const uint8_t* fle; int64_t fle_bytes; int bw; const uint8_t* def; int64_t def_bytes; int64_t rows; };
+  struct PageView { const uint8_t* fle; int64_t fle_bytes; int bw; const uint8_t* def; int64_t def_bytes; int64_t rows; bool plain; };
   std::vector<std::vector<PageView> > views(ncols);
   std::vector<char> col_is_plain(ncols, 0);
   int64_t total_rows = 0;
@@ -782,14 +783,17 @@ inline bool HdfsParquetScanner::StartRowGroupUpload() {
     if (!r->fresh() || npages == 0 || r->max_def_level() > 1) return false;
     views[c].resize(npages);
     int64_t col_rows = 0;
-    // a column is dictionary-encoded throughout, or PLAIN throughout (it overflowed its dictionary in an earlier row
-    // group, hdfs-parquet-table-writer.cc:276-279) -- then it can be materialised but carries no predicate here
-    const bool col_plain = r->pages()[0].encoding == parquet_encoding::PLAIN;
-    col_is_plain[c] = col_plain;
+    // a column is dictionary-encoded throughout, or it overflowed its dictionary and continues PLAIN (the writer
+    // starts every row group with a dictionary and gives up after 40000 distinct values,
+    // hdfs-parquet-table-writer.cc:276-279): such a column can be materialised -- dictionary pages decoded, PLAIN pages
+    // copied into one row-aligned value array -- but carries no predicate here
+    bool any_plain = false;
+    for (size_t p = 0; p < npages; ++p) any_plain = any_plain || r->pages()[p].encoding == parquet_encoding::PLAIN;
+    col_is_plain[c] = any_plain;
     for (size_t p = 0; p < npages; ++p) {
       const DataPage& pg = r->pages()[p];
-      if (col_plain ? pg.encoding != parquet_encoding::PLAIN
-                    : (pg.encoding != parquet_encoding::FLE_DICTIONARY && pg.encoding != parquet_encoding::PLAIN_DICTIONARY)) return false;
+      const bool col_plain = pg.encoding == parquet_encoding::PLAIN;  // (this page)
+      if (!col_plain && pg.encoding != parquet_encoding::FLE_DICTIONARY && pg.encoding != parquet_encoding::PLAIN_DICTIONARY) return false;
       if (pg.num_values <= 0) return false;
       col_rows += pg.num_values;
       PageView& v = views[c][p];
@@ -808,6 +812,7 @@ inline bool HdfsParquetScanner::StartRowGroupUpload() {
         d += 4 + nd;
         left -= 4 + nd;
       }
+      v.plain = col_plain;
       if (col_plain) {  // values back to back, r->slot_size_ bytes each (only the non-null ones)
         v.bw = 1;
         v.fle = d;
@@ -925,6 +930,10 @@ inline bool HdfsParquetScanner::StartRowGroupUpload() {
         ref.plain_size = r->slot_size_;
         ref.dst_dev = static_cast<uint8_t*>(bc.planes_dev) + static_cast<size_t>(row0) * r->slot_size_;
         ref.dst_bit = 0;
+        if (!v.plain) {  // a dictionary page in front of the PLAIN ones: decoded through the dictionary
+          ref.dict_dev = bc.dict_dev;
+          ref.ndict = bc.ndict;
+        }
       }
       ref.rows = v.rows;
       if (v.def != NULL) {

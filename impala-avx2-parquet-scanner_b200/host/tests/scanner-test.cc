@@ -436,12 +436,57 @@ static ColumnChunk WritePlainColumn(const vector<int64_t>& values, const vector<
   return cp;
 }
 
+// the chunk as the writer leaves it: dictionary pages until the dictionary is full, PLAIN pages from there on
+static ColumnChunk WriteMixedColumn(const vector<int64_t>& values, const vector<bool>& notnull, int rows_per_page, int dict_pages) {
+  ColumnChunk cc;
+  DictEncoder<int64_t> dict(8);
+  const int n = values.size();
+  vector<vector<int> > page_indices;
+  for (int p = 0; p < dict_pages && p * rows_per_page < n; ++p) {
+    page_indices.push_back(vector<int>());
+    for (int r = p * rows_per_page; r < std::min(n, (p + 1) * rows_per_page); ++r)
+      if (notnull[r]) EXPECT_TRUE(dict.Put(values[r], page_indices.back()) >= 0);
+  }
+  cc.dict_page.resize(dict.dict_encoded_size());
+  dict.WriteDict(&cc.dict_page[0]);
+  for (int p = 0; p * rows_per_page < n; ++p) {
+    const int r0 = p * rows_per_page, m = std::min(rows_per_page, n - r0);
+    vector<uint8_t> defbuf((m / 64 + 3) * 8);
+    FleEncoder def_levels(&defbuf[0], defbuf.size(), 1);
+    for (int i = 0; i < m; ++i) def_levels.Put(notnull[r0 + i]);
+    def_levels.Flush();
+    int32_t nd = def_levels.len();
+    vector<uint8_t> body(4 + nd);
+    memcpy(&body[0], &nd, 4);
+    memcpy(&body[4], def_levels.buffer(), nd);
+    if (p < dict_pages) {
+      vector<uint8_t> data(1 + (page_indices[p].size() / 64 + 3) * dict.bit_width() * 8);
+      const int data_len = dict.WriteData(&data[0], data.size(), page_indices[p]);
+      EXPECT_TRUE(data_len > 0);
+      body.insert(body.end(), data.begin(), data.begin() + data_len);
+    } else {
+      for (int i = 0; i < m; ++i) {
+        if (!notnull[r0 + i]) continue;
+        const uint8_t* v = reinterpret_cast<const uint8_t*>(&values[r0 + i]);
+        body.insert(body.end(), v, v + 8);
+      }
+    }
+    cc.page_bodies.push_back(body);
+  }
+  for (size_t p = 0; p < cc.page_bodies.size(); ++p) {
+    HdfsParquetScanner::DataPage pg(&cc.page_bodies[p][0], cc.page_bodies[p].size(), std::min(rows_per_page, n - (int)p * rows_per_page));
+    if ((int)p >= dict_pages) pg.encoding = parquet_encoding::PLAIN;
+    cc.pages.push_back(pg);
+  }
+  return cc;
+}
+
 TEST(Scanner, RowGroupBatchPlainMaterialisedColumn) {
-  for (int k = 0; k < 2; ++k) {
-    Table t = MakeTable(64 * 3000 + 41, k ? 0.05 : 0.0, 61 + k);
+  for (int k = 0; k < 4; ++k) {  // k & 1: NULLs; k & 2: the chunk starts with dictionary pages
+    Table t = MakeTable(64 * 3000 + 41, (k & 1) ? 0.05 : 0.0, 61 + k);
     vector<int64_t> price(t.n);
     vector<bool> nn_price(t.n);
-    for (int i = 0; i < t.n; ++i) { price[i] = 90000 + (int64_t)rand() * 5 % 10400000; nn_price[i] = k == 0 || rand() % 10 != 0; }
+    for (int i = 0; i < t.n; ++i) { price[i] = 90000 + (int64_t)rand() * 5 % 10400000; nn_price[i] = (k & 1) == 0 || rand() % 10 != 0; }
     vector<uint8_t> rows[2];
     int64_t passed[2] = {0, 0};
     int ts = 0, off_p = 0, off_d = 0, ip = 0;
@@ -449,11 +494,11 @@ TEST(Scanner, RowGroupBatchPlainMaterialisedColumn) {
       ColumnChunk c0 = WriteColumn(t.shipdate, t.nn_shipdate, 50001, true);
       ColumnChunk c1 = WriteColumn(t.discount, t.nn_discount, 64 * 700, true);
       ColumnChunk c2 = WriteColumn(t.quantity, t.nn_quantity, 33333, true);
-      ColumnChunk cp = WritePlainColumn(price, nn_price, 20011);
+      ColumnChunk cp = (k & 2) ? WriteMixedColumn(price, nn_price, 20011, 2) : WritePlainColumn(price, nn_price, 20011);
       HdfsParquetScanner scanner;
       int i0 = scanner.AddColumn<int32_t>(1, &c0.dict_page[0], c0.dict_page.size(), c0.pages);
       int i1 = scanner.AddColumn<int32_t>(1, &c1.dict_page[0], c1.dict_page.size(), c1.pages);
-      ip = scanner.AddColumn<int64_t>(1, NULL, 0, cp.pages);
+      ip = (k & 2) ? scanner.AddColumn<int64_t>(1, &cp.dict_page[0], cp.dict_page.size(), cp.pages) : scanner.AddColumn<int64_t>(1, NULL, 0, cp.pages);
       int i2 = scanner.AddColumn<int32_t>(1, &c2.dict_page[0], c2.dict_page.size(), c2.pages);
       GeOperate<int32_t> ge0(i0, 8730);
       LeOperate<int32_t> le0(i0, 9094);
@@ -489,7 +534,7 @@ TEST(Scanner, RowGroupBatchPlainMaterialisedColumn) {
     }
     EXPECT_EQ(passed[1], want);
     EXPECT_EQ(bad, 0);
-    std::printf("    plain materialised column, nulls=%d: %lld survivors\n", k, (long long)passed[1]);
+    std::printf("    plain materialised column, nulls=%d dictionary pages first=%d: %lld survivors\n", k & 1, (k >> 1) & 1, (long long)passed[1]);
   }
 }
 

@@ -318,7 +318,12 @@ typedef struct fle_page_ref {
                              * bytes each, any alignment (the non-null ones only with expand = 1); dst_dev = the slot of
                              * the page's first row in a row-aligned VALUE array (column base + first row * plain_size,
                              * base 8-byte aligned); NULL rows get 0.  Bit widths and dst_bit are ignored. */
-  int32_t reserved;
+  int32_t ndict;
+  const void* dict_dev;     /* with plain_size != 0: the page IS a dictionary page (src_bit_width, FLE groups) of a
+                             * column whose later pages are PLAIN -- the writer starts every row group with a
+                             * dictionary and falls back to PLAIN after 40000 distinct values
+                             * (hdfs-parquet-table-writer.cc:276-279) -- and its rows are decoded into the same value
+                             * array: value = dict_dev[code] (ndict entries of plain_size bytes; a code >= ndict gives 0) */
 } fle_page_ref;
 /* Re-bases the FLE sections of all pages (of all columns) of a row group onto aligned plane arrays
  * in ONE launch (two when a page starts or ends inside a group) -- consecutive pages of a column go to

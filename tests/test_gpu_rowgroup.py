@@ -375,3 +375,68 @@ def test_pages_gather_plain_pages_and_assemble(ctx, oracle, size, null_frac):
     wt[:, 0] = (~defs[rows]).astype(np.uint8)
     wt[:, off:off + size] = want[rows].copy().view(np.uint8).reshape(k, size)
     assert (tuples.cpu().numpy()[:k] == wt).all()
+
+
+@pytest.mark.parametrize("size", [4, 8])
+@pytest.mark.parametrize("null_frac", [None, 0.2])
+def test_pages_gather_mixed_dictionary_and_plain_chunk(ctx, oracle, size, null_frac):
+    """A column chunk that starts dictionary-encoded and falls back to PLAIN after 40000 distinct values
+    (hdfs-parquet-table-writer.cc:276-279): its dictionary pages are decoded through the dictionary into the same
+    row-aligned value array the PLAIN pages are copied into."""
+    import torch
+    dt = {4: np.int32, 8: np.int64}[size]
+    rng = np.random.default_rng(size + (0 if null_frac is None else 7))
+    nullable = null_frac is not None
+    d = rng.integers(-10**6, 10**6, size=1000).astype(dt)
+    bw = 10
+    page_rows = [64 * 40 + 3, 9000, 70001, 29]
+    page_coded = [True, True, False, False]
+    blob = bytearray()
+    refs, want_vals, want_def = [], [], []
+    for rows, coded in zip(page_rows, page_coded):
+        defs = (rng.random(rows) >= null_frac) if nullable else np.ones(rows, dtype=bool)
+        m = int(defs.sum())
+        if coded:
+            codes = rng.integers(0, len(d), size=m).astype(np.uint32)
+            vals = d[codes]
+        else:
+            vals = rng.integers(-10**9, 10**9, size=m).astype(dt)
+        full = np.zeros(rows, dtype=dt)
+        full[defs] = vals
+        want_vals.append(full)
+        want_def.append(defs)
+        blob += bytes(rng.integers(0, 255, size=int(rng.integers(17, 40)), dtype=np.uint8))
+        def_off = def_bytes = 0
+        if nullable:
+            dwords = oracle.pack(defs.astype(np.uint32), 1)
+            blob += np.int32(dwords.nbytes).tobytes()
+            def_off, def_bytes = len(blob), dwords.nbytes
+            blob += dwords.tobytes()
+        if coded:
+            words = oracle.pack(codes, bw) if m else np.zeros(0, dtype=np.uint64)
+            blob += bytes([bw])
+            refs.append(dict(src_off=len(blob), src_bytes=words.nbytes, def_off=def_off, def_bytes=def_bytes, rows=rows, coded=True))
+            blob += words.tobytes()
+        else:
+            refs.append(dict(src_off=len(blob), src_bytes=vals.nbytes, def_off=def_off, def_bytes=def_bytes, rows=rows, coded=False))
+            blob += vals.tobytes()
+    blob += bytes(16)
+    dblob = torch.from_numpy(np.frombuffer(bytes(blob), dtype=np.uint8).copy()).cuda()
+    ddict = torch.from_numpy(d).cuda()
+    total = sum(page_rows)
+    G = (total + 63) // 64
+    values = torch.full((G * 64 * size,), -1, dtype=torch.int8, device="cuda")
+    row0, crefs = 0, []
+    for r in refs:
+        ref = dict(src_dev=dblob.data_ptr() + r["src_off"], src_bytes=r["src_bytes"], plain_size=size,
+                   dst_dev=values.data_ptr() + row0 * size, groups=(r["rows"] + 63) // 64, rows=r["rows"])
+        if r["coded"]:
+            ref.update(src_bit_width=bw, dict_dev=ddict.data_ptr(), ndict=len(d))
+        if nullable:
+            ref.update(def_src_dev=dblob.data_ptr() + r["def_off"], def_bytes=r["def_bytes"], expand=1)
+        crefs.append(ref)
+        row0 += r["rows"]
+    ctx.pages_gather_dev(crefs)
+    torch.cuda.synchronize()
+    got = values.cpu().numpy().view(dt)[:total]
+    assert (got == np.concatenate(want_vals)).all()
