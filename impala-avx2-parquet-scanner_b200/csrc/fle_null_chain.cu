@@ -252,7 +252,14 @@ __device__ __forceinline__ uint64_t nc_chains(const PassDesc& pd, uint32_t bw, u
   return ((uint64_t)rh << 32) | rl;
 }
 
+// COMPARES: every pass of the chain is one or two compare chains (a compare, BETWEEN / NOT BETWEEN) -- the kernel then
+// carries two of the six variants per column (a third of the code: the instruction cache holds the tile loop)
+template <bool COMPARES>
 __device__ __forceinline__ uint64_t nc_run_pass(const PassDesc& pd, uint32_t bw, uint32_t addr, uint32_t maddr) {
+  if constexpr (COMPARES) {
+    if (pd.k == 1) return nc_chains<true, 1>(pd, bw, addr, maddr);
+    return nc_chains<true, 2>(pd, bw, addr, maddr);
+  }
   if (pd.type == PASS_LT) {
     if (pd.k == 1) return nc_chains<true, 1>(pd, bw, addr, maddr);
     if (pd.k == 2) return nc_chains<true, 2>(pd, bw, addr, maddr);
@@ -318,7 +325,7 @@ struct NcMeta {
 
 // 8 consumer warps (one row word per thread and tile) + 1 producer warp (lane c owns column c: tile prefixes -> what
 // the tile stages -> bulk copies, two tiles ahead of the consumers, so that no consumer ever waits for a prefix)
-template <int NC>
+template <int NC, bool COMPARES>
 __global__ void __launch_bounds__(kNcThreads + 32) null_chain_kernel(const __grid_constant__ NcParams P) {
   extern __shared__ __align__(128) uint8_t nc_smem[];
   __shared__ NcMeta meta[4][NC];
@@ -493,11 +500,11 @@ __global__ void __launch_bounds__(kNcThreads + 32) null_chain_kernel(const __gri
         const uint32_t maddr = lm0 + c * (32 * 4 * 4);
         {
           const int q = (int)(seg * kNcSeg + jrow);
-          if (q < ng) sts64(res + q * 8u, __brevll(nc_run_pass(C.pd, C.bw, base + jrow * gbytes, maddr)));
+          if (q < ng) sts64(res + q * 8u, __brevll(nc_run_pass<COMPARES>(C.pd, C.bw, base + jrow * gbytes, maddr)));
         }
         if (ng > 8 * kNcSeg && tid < ng - 8 * kNcSeg)  // overflow segment: a tile with (nearly) no NULL at all
           sts64(res + (8 * kNcSeg + tid) * 8u,
-                __brevll(nc_run_pass(C.pd, C.bw, smem0 + cur * P.stage_bytes + C.col_off + 8 * C.seg_stride + tid * gbytes, maddr)));
+                __brevll(nc_run_pass<COMPARES>(C.pd, C.bw, smem0 + cur * P.stage_bytes + C.col_off + 8 * C.seg_stride + tid * gbytes, maddr)));
         // the warps' totals -> exclusive prefixes, in place (warp c for column c; phase D reads one word per thread)
         if (warp == c) {
           const uint32_t wa = smem_u32(&warp_tot[cur][c][0]) + (lane & 7) * 4u;
@@ -553,12 +560,12 @@ __global__ void __launch_bounds__(kNcThreads + 32) null_chain_kernel(const __gri
   }
 }
 
-static const void* null_chain_kernel_for(int nc) {
+static const void* null_chain_kernel_for(int nc, bool compares) {
   switch (nc) {
-    case 1: return (const void*)null_chain_kernel<1>;
-    case 2: return (const void*)null_chain_kernel<2>;
-    case 3: return (const void*)null_chain_kernel<3>;
-    case 4: return (const void*)null_chain_kernel<4>;
+    case 1: return compares ? (const void*)null_chain_kernel<1, true> : (const void*)null_chain_kernel<1, false>;
+    case 2: return compares ? (const void*)null_chain_kernel<2, true> : (const void*)null_chain_kernel<2, false>;
+    case 3: return compares ? (const void*)null_chain_kernel<3, true> : (const void*)null_chain_kernel<3, false>;
+    case 4: return compares ? (const void*)null_chain_kernel<4, true> : (const void*)null_chain_kernel<4, false>;
   }
   return nullptr;
 }
@@ -616,7 +623,9 @@ int launch_def_tile_counts(fle_ctx* ctx, const fle_col_desc* cols, int ncols, in
 // prefix + chain kernel; tile_sums_dev as written by launch_def_tile_counts (indexed by the column's position in cols)
 int launch_null_chain(fle_ctx* ctx, const NullChainPlan& plan, const fle_col_desc* cols, int64_t n, const uint32_t* tile_sums_dev,
                       uint64_t* pref_dev, size_t sums_stride, uint64_t* out_dev, uint64_t* count_dev) {
-  const void* kern = null_chain_kernel_for(plan.ncols);
+  bool compares = true;
+  for (int i = 0; i < plan.ncols; ++i) compares = compares && plan.pd[i].type == PASS_LT && (plan.pd[i].k == 1 || plan.pd[i].k == 2);
+  const void* kern = null_chain_kernel_for(plan.ncols, compares);
   if (!kern || n <= 0) return FLE_E_UNSUPPORTED;
   NcParams P;
   memset(&P, 0, sizeof(P));
