@@ -233,6 +233,11 @@ static int eval_dev_nullable(fle_ctx* ctx, const fle_col_desc* cols, int ncols,
       plan.col[k] = col;
       if (null_chain_pass(ctx, cols[col], nodes + s0, s1 - s0 + 1, &plan.pd[k]) != FLE_OK) chain = false;
     }
+    if (chain) {  // (columns too wide for the kernel's two stages: the per-column kernels)
+      int bws[kNcMaxCols];
+      for (int k = 0; k < plan.ncols; ++k) bws[k] = cols[plan.col[k]].bit_width;
+      chain = null_chain_fits(ctx, bws, plan.ncols);
+    }
   }
   // 1. non-null rows per column (one launch, nothing written but the counts -- and, when the program is a chain the
   // one-kernel NULL path can take, the per-tile counts that path starts from) ...

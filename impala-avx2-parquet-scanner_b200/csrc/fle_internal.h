@@ -237,6 +237,7 @@ struct NullChainPlan {
   PassDesc pd[kNcMaxCols];  // the column's subtree as one pass
 };
 int64_t null_chain_tiles(int64_t n);
+bool null_chain_fits(fle_ctx* ctx, const int* bw, int ncols);
 int null_chain_pass(fle_ctx* ctx, const fle_col_desc& col, const fle_pred_node* nodes, int nnodes, PassDesc* out);
 // non-null rows per nullable column (counts_dev[c]) and per tile of 16384 rows (tile_sums_dev[c * stride + tile]), one launch
 int launch_def_tile_counts(fle_ctx* ctx, const fle_col_desc* cols, int ncols, int64_t n, uint64_t* counts_dev,

@@ -572,6 +572,21 @@ static const void* null_chain_kernel_for(int nc, bool compares) {
 
 int64_t null_chain_tiles(int64_t n) { return ((n + 63) / 64 + kNcWords - 1) / kNcWords; }
 
+// dynamic shared memory of the chain kernel for these bit widths (two stages of every column + the result words)
+static size_t null_chain_smem(const int* bw, int ncols) {
+  size_t stage = 0;
+  for (int i = 0; i < ncols; ++i) {
+    const size_t seg_stride = ((size_t)kNcSeg * bw[i] * 8 + 127) / 128 * 128 + 16;
+    stage += (8 * seg_stride + (size_t)kNcOver * bw[i] * 8 + 127) / 128 * 128;
+  }
+  return (size_t)kNcStages * stage + (size_t)ncols * kNcGroups * 8;
+}
+
+// false: the columns are too wide for the kernel's two stages (the caller keeps to the per-column kernels)
+bool null_chain_fits(fle_ctx* ctx, const int* bw, int ncols) {
+  return ncols >= 1 && ncols <= kNcMaxCols && null_chain_smem(bw, ncols) + 4096 <= (size_t)ctx->max_smem_optin;
+}
+
 // the sub-program [nodes, nodes + nnodes) on column `col` as ONE pass, or FLE_E_UNSUPPORTED
 int null_chain_pass(fle_ctx* ctx, const fle_col_desc& col, const fle_pred_node* nodes, int nnodes, PassDesc* out) {
   if (col.bit_width < 1 || col.bit_width > 32) return FLE_E_UNSUPPORTED;

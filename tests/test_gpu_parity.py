@@ -280,6 +280,31 @@ def test_nullable_columns_vs_oracle(ctx, oracle, null_frac):
                 ctx.set_option("null_chain_ctas", 0)
 
 
+@pytest.mark.parametrize("bws", [(20, 20), (32, 32), (32,), (17, 3, 25, 9)])
+def test_nullable_wide_columns_chain_or_fallback(ctx, oracle, bws):
+    """The one-kernel NULL chain stages two tiles of every column in shared memory: wide columns that do not fit fall
+    back to the per-column kernels -- same answer either way (ColumnReader<T>::Eq..In + IntersectBitset)."""
+    rng = np.random.default_rng(sum(bws))
+    n = 64 * 1500 + 7
+    cols, want = [], None
+    prog = []
+    for c, bw in enumerate(bws):
+        nn = rng.random(n) >= 0.05
+        dom = min(1 << bw, 1 << 31)
+        data = rng.integers(0, dom, size=int(nn.sum())).astype(np.uint32)
+        dw, defw = oracle.pack(data, bw), oracle.pack(nn.astype(np.uint32), 1)
+        cols.append((dw, bw, defw))
+        lo, hi = dom // 8, dom // 8 + dom // 2
+        root = oracle.pred(EQ, defw, 1, 0, n, [1])[0]
+        sub = oracle.pred(GE, dw, bw, 0, len(data), [lo])[0] & oracle.pred(LE, dw, bw, 0, len(data), [hi])[0]
+        leaf = oracle.intersect_bitset(root, n, sub)[0]
+        want = leaf if want is None else (want & leaf)
+        prog += [(GE, c, lo), (LE, c, hi), (AND, None, None)] + ([(AND, None, None)] if c else [])
+    for _ in range(2):
+        bm, cnt = ctx.eval(cols, prog, n)
+        assert (bm == want).all() and cnt == popcount(want), bws
+
+
 # ------------------------------------------------------------------------------------------
 # device-resident API at BASELINE.json sizes: size-independent properties
 # ------------------------------------------------------------------------------------------
