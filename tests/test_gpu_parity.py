@@ -280,6 +280,38 @@ def test_nullable_columns_vs_oracle(ctx, oracle, null_frac):
                 ctx.set_option("null_chain_ctas", 0)
 
 
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 16383, 16384, 16385, 3 * 16384, 5 * 16384 + 1, 64 * 777 + 13])
+@pytest.mark.parametrize("null_frac", [0.0, 0.3, 1.0])
+def test_nullable_chain_sizes(ctx, oracle, n, null_frac):
+    """The NULL chain at tile edges (16384 rows per tile), tiny inputs, an all-NULL column and a column without NULLs
+    beside one that has them; grid pinned to one CTA as well, so that one CTA walks every tile."""
+    rng = np.random.default_rng(n % 997 + int(null_frac * 10))
+    nn = [rng.random(n) >= null_frac if null_frac < 1.0 else np.zeros(n, dtype=bool), rng.random(n) >= 0.1]
+    bws, doms = (11, 6), (2000, 50)
+    cols, want = [], None
+    for k in range(2):
+        data = rng.integers(0, doms[k], size=int(nn[k].sum())).astype(np.uint32)
+        dw = oracle.pack(data, bws[k]) if len(data) else np.zeros(bws[k], dtype=np.uint64)
+        defw = oracle.pack(nn[k].astype(np.uint32), 1)
+        cols.append((dw, bws[k], defw))
+        root = oracle.pred(EQ, defw, 1, 0, n, [1])[0]
+        if len(data):
+            sub = oracle.pred(LT, dw, bws[k], 0, len(data), [doms[k] // 2])[0]
+            leaf = oracle.intersect_bitset(root, n, sub)[0]
+        else:
+            leaf = np.zeros_like(root)
+        want = leaf if want is None else (want & leaf)
+    prog = [(LT, 0, doms[0] // 2), (LT, 1, doms[1] // 2), (AND, None, None)]
+    for ctas in (0, 1):
+        ctx.set_option("null_chain_ctas", ctas)
+        try:
+            for _ in range(2):
+                bm, cnt = ctx.eval(cols, prog, n)
+                assert (bm == want).all() and cnt == popcount(want), (n, null_frac, ctas)
+        finally:
+            ctx.set_option("null_chain_ctas", 0)
+
+
 @pytest.mark.parametrize("bws", [(20, 20), (32, 32), (32,), (17, 3, 25, 9)])
 def test_nullable_wide_columns_chain_or_fallback(ctx, oracle, bws):
     """The one-kernel NULL chain stages two tiles of every column in shared memory: wide columns that do not fit fall
