@@ -526,6 +526,8 @@ int fle_ctx_destroy(fle_ctx* ctx) {
   if (ctx->d_dict) cudaFree(ctx->d_dict);
   if (ctx->d_tile_state) cudaFree(ctx->d_tile_state);
   if (ctx->ev_prefetch) cudaEventDestroy(ctx->ev_prefetch);
+  for (int i = 0; i < fle_ctx::kPrefetchMarks; ++i)
+    if (ctx->ev_mark[i]) cudaEventDestroy(ctx->ev_mark[i]);
   fle::group_release(ctx);
   if (ctx->h_count) cudaFreeHost(ctx->h_count);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1094,6 +1096,22 @@ int fle_prefetch_fence(fle_ctx* ctx) {
   if (!ctx->ev_prefetch) FLE_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_prefetch, cudaEventDisableTiming));
   FLE_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_prefetch, ctx->copy_stream));
   FLE_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_prefetch, 0));
+  return FLE_OK;
+}
+
+int fle_prefetch_mark(fle_ctx* ctx, int slot) {
+  FLE_CHECK_CTX(ctx);
+  if (slot < 0 || slot >= fle_ctx::kPrefetchMarks) return set_error(ctx, FLE_E_INVALID, "prefetch mark outside 0..7");
+  if (!ctx->ev_mark[slot]) FLE_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_mark[slot], cudaEventDisableTiming));
+  FLE_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_mark[slot], ctx->copy_stream));
+  return FLE_OK;
+}
+
+int fle_prefetch_wait(fle_ctx* ctx, int slot) {
+  FLE_CHECK_CTX(ctx);
+  if (slot < 0 || slot >= fle_ctx::kPrefetchMarks) return set_error(ctx, FLE_E_INVALID, "prefetch mark outside 0..7");
+  if (!ctx->ev_mark[slot]) return set_error(ctx, FLE_E_INVALID, "fle_prefetch_wait before fle_prefetch_mark");
+  FLE_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_mark[slot], 0));
   return FLE_OK;
 }
 

@@ -129,6 +129,8 @@ struct fle_ctx {
   size_t tile_state_cap = 0;  // bytes
   uint32_t tile_gen = 0;
   cudaEvent_t ev_prefetch = nullptr;  // last fle_h2d_prefetch on the copy stream
+  static constexpr int kPrefetchMarks = 8;
+  cudaEvent_t ev_mark[kPrefetchMarks] = {nullptr};  // fle_prefetch_mark / fle_prefetch_wait
 
   // group of GPUs whose totals are summed inside the kernels (fle_group.cu)
   int grp_world = 0, grp_rank = 0;

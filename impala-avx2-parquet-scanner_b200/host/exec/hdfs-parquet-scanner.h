@@ -1004,6 +1004,7 @@ inline bool HdfsParquetScanner::StartRowGroupUpload() {
     }
     if (batch_ncols_nulls_ > FLE_MAX_COLS || batch_prog_nulls_.size() > FLE_MAX_NODES) batch_ncols_nulls_ = 0;
   }
+  if (FleGpu::Check(fle_prefetch_mark(ctx, batch_bank_), "fle_prefetch_mark") != FLE_OK) return false;
   batch_rows_ = total_rows;
   batch_state_ = 1;
   return true;
@@ -1021,7 +1022,8 @@ inline bool HdfsParquetScanner::DeviceRowGroup(std::vector<uint8_t>* rows, int64
   uint64_t* hdr_dev = static_cast<uint64_t*>(FleGpu::DeviceScratch(bank, 41, 64));  // [0] NULL rows, [1] survivors, [2] bad codes
   uint64_t* hdr = static_cast<uint64_t*>(FleGpu::PinnedScratch(bank, 0, 64));
   if (!bitmap_dev || !hdr_dev || !hdr) return false;
-  if (FleGpu::Check(fle_prefetch_fence(ctx), "fle_prefetch_fence") != FLE_OK) return false;
+  // (this row group's uploads only: the next row group's, enqueued before these kernels, keep crossing PCIe meanwhile)
+  if (FleGpu::Check(fle_prefetch_wait(ctx, bank), "fle_prefetch_wait") != FLE_OK) return false;
   if (FleGpu::Check(fle_pages_gather_dev(ctx, &batch_refs_[0], static_cast<int>(batch_refs_.size()), hdr_dev), "fle_pages_gather_dev") != FLE_OK) return false;
   std::vector<fle_col_desc> cols(std::max(batch_eval_cols_, batch_ncols_nulls_));
   std::vector<fle_slot_desc> slots(ncols);

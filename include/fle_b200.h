@@ -282,6 +282,13 @@ int fle_sum_product_dev(fle_ctx* ctx, const uint64_t* bitmap_dev, int64_t nrows,
  * source is staged by the driver at a fraction of the PCIe rate. */
 int fle_h2d_prefetch(fle_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 int fle_prefetch_fence(fle_ctx* ctx);
+/* The same, per row group: fle_prefetch_mark records a point (slot 0..7) on the copy stream behind the uploads
+ * enqueued so far, fle_prefetch_wait makes the main stream wait for THAT point only.  With row group k + 1's upload
+ * enqueued before row group k's kernels -- as a scanner does to keep PCIe busy -- the fence above would make k's
+ * kernels wait for k + 1's bytes as well; a mark per row group lets them start as soon as k's own column chunks
+ * have arrived (hdfs-parquet-scanner.cc:1078-1275 reads one row group at a time; this is the overlap around it). */
+int fle_prefetch_mark(fle_ctx* ctx, int slot);
+int fle_prefetch_wait(fle_ctx* ctx, int slot);
 /* Pins / unpins an existing host range (e.g. the I/O buffers the pages are read into) in place. */
 int fle_host_register(void* p, size_t bytes);
 int fle_host_unregister(void* p);
