@@ -181,15 +181,26 @@ static bool ScanRowGroups(Workload* w, int row_groups, int64_t* passed_total, in
   vector<uint8_t> rows;
   *passed_total = 0;
   *batches = 0;
+  const bool trace = getenv("FLE_BENCH_TRACE") != NULL;
+  double t_start = 0, t_asm = 0, t_new = 0;
   for (int k = 0; k < row_groups; ++k) {
     if (k + 1 < row_groups) {
+      const double a = Now();
       next.reset(new HdfsParquetScanner());
       w->Attach(next.get());
+      const double b = Now();
       next->StartRowGroupUpload();
+      t_new += b - a;
+      t_start += Now() - b;
     }
     rows.clear();
     int64_t passed = 0;
+    const double a2 = Now();
     Status st = cur->AssembleRows(w->n, &rows, &passed);
+    t_asm += Now() - a2;
+    if (trace && k + 1 == row_groups)
+      std::fprintf(stderr, "trace: %d row groups: new+attach %.3f ms, StartRowGroupUpload %.3f ms, AssembleRows %.3f ms\n", row_groups,
+                   t_new * 1e3, t_start * 1e3, t_asm * 1e3);
     if (!st.ok() || passed != w->want) {
       std::fprintf(stderr, "scan failed: %s passed %lld want %lld\n", st.GetErrorMsg().c_str(), (long long)passed, (long long)w->want);
       return false;
