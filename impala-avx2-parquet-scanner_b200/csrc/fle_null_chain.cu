@@ -178,7 +178,6 @@ __global__ void __launch_bounds__(1024) nc_prefix_kernel(const __grid_constant__
 // ------------------------------------------------------------------------------------------
 // launch 3
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t lds32s(uint32_t addr) { return lds32(addr); }
 __device__ __forceinline__ void lds64u(uint32_t addr, uint32_t& a, uint32_t& b) {
   asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr));
 }
