@@ -598,6 +598,71 @@ TEST(Scanner, RowGroupBatchFuzz) {
   EXPECT_EQ(batches, 24);
 }
 
+// Four scanner threads at once (one library context each, hdfs-parquet-scanner.cc:1040), every one scanning its own
+// tables with NULLs, ragged pages and a PLAIN column as one batch per row group; results against the truth.
+#include <atomic>
+#include <thread>
+TEST(Scanner, ConcurrentScannersWithNullsAndRaggedPages) {
+  std::atomic<int> bad(0), scans(0);
+  vector<std::thread> th;
+  for (int tix = 0; tix < 4; ++tix) {
+    th.emplace_back([&, tix]() {
+      for (int it = 0; it < 6; ++it) {
+        Table t = MakeTable(20000 + 7919 * ((tix * 6 + it) % 11), (it % 3) * 0.04, 500 + tix * 17 + it);
+        vector<int64_t> price(t.n);
+        vector<bool> nn_price(t.n);
+        unsigned st = 99 + tix * 31 + it;
+        for (int i = 0; i < t.n; ++i) {
+          st = st * 1664525u + 1013904223u;
+          price[i] = 90000 + (st >> 8) % 10400000;
+          nn_price[i] = (it % 2 == 0) || ((st >> 3) % 9 != 0);
+        }
+        ColumnChunk c0 = WriteColumn(t.shipdate, t.nn_shipdate, 5000 + 777 * tix, true);
+        ColumnChunk c1 = WriteColumn(t.discount, t.nn_discount, 64 * 100, true);
+        ColumnChunk c2 = WriteColumn(t.quantity, t.nn_quantity, 1 << 30, true);
+        ColumnChunk cp = WriteMixedColumn(price, nn_price, 3001, 2);
+        HdfsParquetScanner scanner;
+        int i0 = scanner.AddColumn<int32_t>(1, &c0.dict_page[0], c0.dict_page.size(), c0.pages);
+        int i1 = scanner.AddColumn<int32_t>(1, &c1.dict_page[0], c1.dict_page.size(), c1.pages);
+        int ip = scanner.AddColumn<int64_t>(1, &cp.dict_page[0], cp.dict_page.size(), cp.pages);
+        int i2 = scanner.AddColumn<int32_t>(1, &c2.dict_page[0], c2.dict_page.size(), c2.pages);
+        GeOperate<int32_t> ge0(i0, 8730);
+        LeOperate<int32_t> le0(i0, 9094);
+        AndOperate between0(&ge0, &le0);
+        GeOperate<int32_t> ge1(i1, 5);
+        LeOperate<int32_t> le1(i1, 7);
+        LtOperate<int32_t> lt2(i2, 24);
+        scanner.AddSimplePredicate(&between0);
+        scanner.AddSimplePredicate(&ge1);
+        scanner.AddSimplePredicate(&le1);
+        scanner.AddSimplePredicate(&lt2);
+        vector<uint8_t> rows;
+        int64_t passed = 0;
+        if (!scanner.AssembleRows(t.n, &rows, &passed).ok() || scanner.row_group_batches() != 1) { ++bad; continue; }
+        const int ts = scanner.tuple_size(), off_p = scanner.slot_offset(ip), off_s = scanner.slot_offset(i0);
+        int64_t want = 0;
+        for (int r = 0; r < t.n; ++r) {
+          if (!RowPasses(t, r)) continue;
+          if (want < passed) {
+            const uint8_t* tuple = &rows[want * ts];
+            int64_t pv;
+            int32_t sv;
+            memcpy(&pv, tuple + off_p, 8);
+            memcpy(&sv, tuple + off_s, 4);
+            if (tuple[ip] != !nn_price[r] || (nn_price[r] ? pv != price[r] : pv != 0) || sv != t.shipdate[r]) ++bad;
+          }
+          ++want;
+        }
+        if (want != passed) ++bad;
+        ++scans;
+      }
+    });
+  }
+  for (auto& x : th) x.join();
+  EXPECT_EQ(bad.load(), 0);
+  EXPECT_EQ(scans.load(), 24);
+}
+
 // The deviations DESIGN.md lists, pinned in both modes (the reference lines are cited in util/fle-gpu-context.h)
 TEST(Scanner, ReferenceCompatSwitch) {
   // 1. Skip() landing exactly on the end of the data (fle-encoding.h:381-402)
