@@ -15,6 +15,9 @@
 //                 exact because the keys are distinct) -> sorted dictionary + slot -> code map
 //   4. encode   : value -> slot (probe) -> code (u32)
 //   5. pack     : pack_kernel<bw> with bw = DictEncoderBase::bit_width() (dict-encoding.h:76-80)
+#include <mutex>
+#include <set>
+
 #include "fle_device.cuh"
 #include "fle_internal.h"
 
@@ -67,6 +70,116 @@ dict_insert_kernel(const T* __restrict__ vals, int64_t n, unsigned long long* __
         if (old == k) break;
       }
       h = (h + 1) & (kDictSlots - 1);
+    }
+  }
+}
+
+// The same insert behind a per-CTA front cache.  A column chunk has few distinct values (that is why it is dictionary-
+// encoded), so nearly every probe of the global table finds a key that is already there -- 2^28 random 8-byte reads of
+// a 1 MB table are 8.6 GB of L2 sector traffic, which is what the kernel above spends its time on.  Each persistent
+// CTA keeps the keys it has met in a shared-memory set (2^14 slots, multiply-shift hash, at most kFrontMax keys: a
+// crowded set only costs probes); only a value the CTA has not met before goes to the global table.
+constexpr int kFrontBits = 14, kFrontSlots = 1 << kFrontBits, kFrontMax = kFrontSlots * 3 / 4, kFrontProbes = 8;
+
+__device__ __forceinline__ uint32_t front_hash(unsigned long long k) {
+  return (uint32_t)((k * 0x9E3779B97F4A7C15ull) >> (64 - kFrontBits));
+}
+
+__device__ __forceinline__ void dict_insert_global(unsigned long long k, unsigned long long* __restrict__ keys, DictState* st,
+                                                   unsigned int max_entries) {
+  uint32_t h = dict_hash(k);
+  for (int probe = 0; probe < kDictSlots; ++probe) {
+    const unsigned long long cur = keys[h];
+    if (cur == k) return;
+    if (cur == kEmptyKey) {
+      const unsigned long long old = atomicCAS(&keys[h], kEmptyKey, k);
+      if (old == kEmptyKey) {
+        if (atomicAdd(&st->count, 1u) + 1u > max_entries) st->overflow = 1;
+        return;
+      }
+      if (old == k) return;
+    }
+    h = (h + 1) & (kDictSlots - 1);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024)
+dict_insert_front_kernel(const T* __restrict__ vals, int64_t n, unsigned long long* __restrict__ keys, DictState* st,
+                         unsigned int max_entries) {
+  extern __shared__ unsigned long long front[];  // kFrontSlots keys
+  __shared__ unsigned int front_count;
+  for (int i = threadIdx.x; i < kFrontSlots; i += 1024) front[i] = kEmptyKey;
+  if (threadIdx.x == 0) front_count = 0;
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * 1024;
+  for (int64_t i0 = (int64_t)blockIdx.x * 1024 + threadIdx.x; i0 < n; i0 += 4 * stride) {
+    if (*((volatile unsigned int*)&st->overflow)) return;
+    unsigned long long k4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) k4[j] = widen(vals[min(i0 + j * stride, n - 1)]);  // (unconditional: four loads in flight)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (i0 + j * stride >= n) break;
+      const unsigned long long k = k4[j];
+      if (k == kEmptyKey) { st->has_min = 1; continue; }
+      uint32_t h = front_hash(k);
+      bool known = false, placed = false;
+      for (int probe = 0; probe < kFrontProbes; ++probe) {
+        const unsigned long long cur = front[h];
+        if (cur == k) { known = true; break; }
+        if (cur == kEmptyKey) {
+          if (*((volatile unsigned int*)&front_count) >= (unsigned)kFrontMax) break;
+          const unsigned long long old = atomicCAS(&front[h], kEmptyKey, k);
+          if (old == kEmptyKey) { placed = true; atomicAdd(&front_count, 1u); break; }
+          if (old == k) { known = true; break; }
+        }
+        h = (h + 1) & (kFrontSlots - 1);
+      }
+      (void)placed;
+      if (!known) dict_insert_global(k, keys, st, max_entries);
+    }
+  }
+}
+
+// value -> code through a shared-memory map built from the sorted dictionary (nd <= kFrontMax): no global probe at all
+template <typename T>
+__global__ void __launch_bounds__(1024)
+dict_encode_front_kernel(const T* __restrict__ vals, int64_t n, const long long* __restrict__ dict_sorted, int nd,
+                         uint32_t* __restrict__ codes) {
+  extern __shared__ unsigned long long front[];  // kFrontSlots keys, then kFrontSlots 16-bit codes
+  unsigned short* fcode = reinterpret_cast<unsigned short*>(front + kFrontSlots);
+  __shared__ unsigned int min_code;
+  for (int i = threadIdx.x; i < kFrontSlots; i += 1024) front[i] = kEmptyKey;
+  if (threadIdx.x == 0) min_code = 0xFFFFFFFFu;
+  __syncthreads();
+  for (int c = threadIdx.x; c < nd; c += 1024) {
+    const unsigned long long k = (unsigned long long)dict_sorted[c];
+    if (k == kEmptyKey) { min_code = (unsigned)c; continue; }  // INT64_MIN (at most one entry): out of band
+    uint32_t h = front_hash(k);
+    for (;;) {  // (distinct keys, load <= 3/4: terminates)
+      if (atomicCAS(&front[h], kEmptyKey, k) == kEmptyKey) { fcode[h] = (unsigned short)c; break; }
+      h = (h + 1) & (kFrontSlots - 1);
+    }
+  }
+  __syncthreads();
+  const unsigned int mc = min_code;
+  const int64_t stride = (int64_t)gridDim.x * 1024;
+  for (int64_t i0 = (int64_t)blockIdx.x * 1024 + threadIdx.x; i0 < n; i0 += 4 * stride) {
+    unsigned long long k4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) k4[j] = widen(vals[min(i0 + j * stride, n - 1)]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (i0 + j * stride >= n) break;
+      const unsigned long long k = k4[j];
+      uint32_t code = mc;
+      if (k != kEmptyKey) {
+        uint32_t h = front_hash(k);
+        while (front[h] != k) h = (h + 1) & (kFrontSlots - 1);  // (every value of the column is in the dictionary)
+        code = fcode[h];
+      }
+      codes[i0 + j * stride] = code;
     }
   }
 }
@@ -161,14 +274,56 @@ int launch_dict_encode(fle_ctx* ctx, const void* values_dev, int elem_type, int6
   dict_clear_kernel<<<kDictSlots / 256, 256, 0, st>>>(keys);
   DICT_TRY(cudaMemsetAsync(state, 0, sizeof(DictState), st));
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 8, (n + 255) / 256));
+  // the kernels with a shared-memory front cache: one CTA of 1024 threads per SM; worth it from a few CTAs' worth of values on
+  const size_t front_smem = (size_t)kFrontSlots * 8, front_map_smem = (size_t)kFrontSlots * 10;
+  const bool front = n >= (1 << 20) && (size_t)ctx->max_smem_optin >= front_map_smem + 1024;
+  const int front_grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms, (n + 4095) / 4096));
+  if (front) {
+    static std::mutex mu;
+    static std::set<int> raised;
+    std::lock_guard<std::mutex> lock(mu);
+    if (raised.find(ctx->device) == raised.end()) {
+      DICT_TRY(cudaFuncSetAttribute(dict_insert_front_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)front_smem));
+      DICT_TRY(cudaFuncSetAttribute(dict_insert_front_kernel<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)front_smem));
+      DICT_TRY(cudaFuncSetAttribute(dict_encode_front_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)front_map_smem));
+      DICT_TRY(cudaFuncSetAttribute(dict_encode_front_kernel<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)front_map_smem));
+      raised.insert(ctx->device);
+    }
+  }
   if (n > 0) {
-    if (es == 4) dict_insert_kernel<int32_t><<<grid, 256, 0, st>>>((const int32_t*)values_dev, n, keys, state, (unsigned)max_entries);
-    else dict_insert_kernel<int64_t><<<grid, 256, 0, st>>>((const int64_t*)values_dev, n, keys, state, (unsigned)max_entries);
+    // The front cache pays while a CTA's set holds (nearly) every key of the column; a column with tens of thousands
+    // of distinct values overflows it and is better off with twice the warps probing the global table.  The first
+    // 4 Mi values tell: their distinct count picks the kernel for the rest.
+    auto insert_range = [&](int64_t first, int64_t count, bool use_front) {
+      const uint8_t* base = static_cast<const uint8_t*>(values_dev) + (size_t)first * es;
+      const int fg = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms, (count + 4095) / 4096));
+      const int gg = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 8, (count + 255) / 256));
+      if (use_front) {
+        if (es == 4) dict_insert_front_kernel<int32_t><<<fg, 1024, front_smem, st>>>((const int32_t*)base, count, keys, state, (unsigned)max_entries);
+        else dict_insert_front_kernel<int64_t><<<fg, 1024, front_smem, st>>>((const int64_t*)base, count, keys, state, (unsigned)max_entries);
+      } else if (es == 4) {
+        dict_insert_kernel<int32_t><<<gg, 256, 0, st>>>((const int32_t*)base, count, keys, state, (unsigned)max_entries);
+      } else {
+        dict_insert_kernel<int64_t><<<gg, 256, 0, st>>>((const int64_t*)base, count, keys, state, (unsigned)max_entries);
+      }
+      ctx->launches += 1;
+    };
+    constexpr int64_t kSample = 1 << 22;
+    if (!front) {
+      insert_range(0, n, false);
+    } else if (n <= 2 * kSample) {
+      insert_range(0, n, true);
+    } else {
+      insert_range(0, kSample, true);
+      DictState hs;
+      DICT_TRY(cudaMemcpyAsync(&hs, state, sizeof(hs), cudaMemcpyDeviceToHost, st));
+      DICT_TRY(cudaStreamSynchronize(st));
+      insert_range(kSample, n - kSample, !hs.overflow && hs.count <= (unsigned)kFrontMax / 2);
+    }
   }
   DictState h;
   DICT_TRY(cudaMemcpyAsync(&h, state, sizeof(h), cudaMemcpyDeviceToHost, st));
   DICT_TRY(cudaStreamSynchronize(st));
-  ctx->launches += n > 0 ? 1 : 0;
   const int nd = (int)h.count + (h.has_min ? 1 : 0);
   if (h.overflow || nd > max_entries) {
     cleanup();
@@ -186,8 +341,14 @@ int launch_dict_encode(fle_ctx* ctx, const void* values_dev, int elem_type, int6
   if (nd > 0) {
     dict_compact_kernel<<<kDictSlots / 256, 256, 0, st>>>(keys, state, list_keys, list_slots);
     dict_rank_kernel<<<(nd + 255) / 256, 256, 0, st>>>(list_keys, list_slots, nd, (long long*)dict_out_dev, slot_to_code);
-    if (es == 4) dict_encode_kernel<int32_t><<<grid, 256, 0, st>>>((const int32_t*)values_dev, n, keys, slot_to_code, codes);
-    else dict_encode_kernel<int64_t><<<grid, 256, 0, st>>>((const int64_t*)values_dev, n, keys, slot_to_code, codes);
+    if (front && nd <= kFrontMax) {
+      if (es == 4) dict_encode_front_kernel<int32_t><<<front_grid, 1024, front_map_smem, st>>>((const int32_t*)values_dev, n, (const long long*)dict_out_dev, nd, codes);
+      else dict_encode_front_kernel<int64_t><<<front_grid, 1024, front_map_smem, st>>>((const int64_t*)values_dev, n, (const long long*)dict_out_dev, nd, codes);
+    } else if (es == 4) {
+      dict_encode_kernel<int32_t><<<grid, 256, 0, st>>>((const int32_t*)values_dev, n, keys, slot_to_code, codes);
+    } else {
+      dict_encode_kernel<int64_t><<<grid, 256, 0, st>>>((const int64_t*)values_dev, n, keys, slot_to_code, codes);
+    }
     ctx->launches += 3;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { cleanup(); return set_cuda_error(ctx, e, "dict kernels"); }

@@ -789,7 +789,31 @@ def test_dict_build_on_device(ctx, oracle):
         assert bw == oracle.dict_bit_width(len(want_dict))
         codes = np.searchsorted(want_dict, vals).astype(np.uint32)
         assert (enc.cpu().numpy().view(np.uint64) == oracle.pack(codes, bw)).all()
+    # large chunks go through the shared-memory front caches (insert: the keys a CTA has met; encode: value -> code map
+    # built from the sorted dictionary when it has at most 12288 entries): few / many distinct values, INT64_MIN, int32,
+    # and a chunk long enough for the sampled choice between the two insert kernels
+    for dt, nd_want, with_min, n2 in ((torch.int64, 3000, True, (1 << 21) + 77), (torch.int64, 12288, False, (1 << 21) + 1),
+                                      (torch.int64, 30000, False, (1 << 23) + 5), (torch.int32, 777, False, (1 << 23) + 64 * 3),
+                                      (torch.int64, 9000, False, (1 << 23) + 9)):
+        codes_t = torch.randint(0, nd_want, (n2,), generator=torch.Generator().manual_seed(nd_want))
+        codes_t[-nd_want:] = torch.arange(nd_want)  # every entry occurs (the last ones only behind the sample)
+        table = torch.arange(nd_want, dtype=torch.int64) * 1000003 - 5 * 10**8
+        if dt == torch.int32:
+            table = torch.arange(nd_want, dtype=torch.int64) * 2711 - 10**6
+        if with_min:
+            table[0] = torch.iinfo(torch.int64).min
+        vals2 = table[codes_t].to(dt)
+        d2, bw2, enc2 = ctx.dict_encode_dev(vals2.cuda())
+        torch.cuda.synchronize()
+        assert torch.equal(d2.cpu(), table), (dt, nd_want)
+        assert bw2 == max(1, int(nd_want - 1).bit_length())
+        got2 = oracle.unpack(enc2.cpu().numpy().view(np.uint64), bw2, 0, n2)
+        assert (got2.astype(np.int64) == codes_t.numpy()).all(), (dt, nd_want)
     big = torch.arange(0, 50000, device="cuda", dtype=torch.int64)
+    with pytest.raises(fle_b200.FleError) as ei:
+        ctx.dict_encode_dev(big)
+    assert ei.value.code == fle_b200.capi.E_DICT_FULL
+    big = torch.arange(0, 1 << 23, device="cuda", dtype=torch.int64) % 50000  # ... and through the sampled path
     with pytest.raises(fle_b200.FleError) as ei:
         ctx.dict_encode_dev(big)
     assert ei.value.code == fle_b200.capi.E_DICT_FULL
