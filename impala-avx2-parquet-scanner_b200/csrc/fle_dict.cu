@@ -79,6 +79,7 @@ dict_insert_kernel(const T* __restrict__ vals, int64_t n, unsigned long long* __
 // a 1 MB table are 8.6 GB of L2 sector traffic, which is what the kernel above spends its time on.  Each persistent
 // CTA keeps the keys it has met in a shared-memory set (2^14 slots, multiply-shift hash, at most kFrontMax keys: a
 // crowded set only costs probes); only a value the CTA has not met before goes to the global table.
+constexpr int kFrontUnroll = 8;  // independent 8-byte loads per thread: 64 KB in flight per SM
 constexpr int kFrontBits = 14, kFrontSlots = 1 << kFrontBits, kFrontMax = kFrontSlots * 3 / 4, kFrontProbes = 8;
 
 __device__ __forceinline__ uint32_t front_hash(unsigned long long k) {
@@ -113,13 +114,13 @@ dict_insert_front_kernel(const T* __restrict__ vals, int64_t n, unsigned long lo
   if (threadIdx.x == 0) front_count = 0;
   __syncthreads();
   const int64_t stride = (int64_t)gridDim.x * 1024;
-  for (int64_t i0 = (int64_t)blockIdx.x * 1024 + threadIdx.x; i0 < n; i0 += 4 * stride) {
+  for (int64_t i0 = (int64_t)blockIdx.x * 1024 + threadIdx.x; i0 < n; i0 += kFrontUnroll * stride) {
     if (*((volatile unsigned int*)&st->overflow)) return;
-    unsigned long long k4[4];
+    unsigned long long k4[kFrontUnroll];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) k4[j] = widen(vals[min(i0 + j * stride, n - 1)]);  // (unconditional: four loads in flight)
+    for (int j = 0; j < kFrontUnroll; ++j) k4[j] = widen(vals[min(i0 + j * stride, n - 1)]);  // (unconditional: all loads in flight)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < kFrontUnroll; ++j) {
       if (i0 + j * stride >= n) break;
       const unsigned long long k = k4[j];
       if (k == kEmptyKey) { st->has_min = 1; continue; }
@@ -165,12 +166,12 @@ dict_encode_front_kernel(const T* __restrict__ vals, int64_t n, const long long*
   __syncthreads();
   const unsigned int mc = min_code;
   const int64_t stride = (int64_t)gridDim.x * 1024;
-  for (int64_t i0 = (int64_t)blockIdx.x * 1024 + threadIdx.x; i0 < n; i0 += 4 * stride) {
-    unsigned long long k4[4];
+  for (int64_t i0 = (int64_t)blockIdx.x * 1024 + threadIdx.x; i0 < n; i0 += kFrontUnroll * stride) {
+    unsigned long long k4[kFrontUnroll];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) k4[j] = widen(vals[min(i0 + j * stride, n - 1)]);
+    for (int j = 0; j < kFrontUnroll; ++j) k4[j] = widen(vals[min(i0 + j * stride, n - 1)]);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < kFrontUnroll; ++j) {
       if (i0 + j * stride >= n) break;
       const unsigned long long k = k4[j];
       uint32_t code = mc;
