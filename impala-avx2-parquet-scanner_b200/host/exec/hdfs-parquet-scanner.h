@@ -128,6 +128,12 @@ class HdfsParquetScanner {
   // appended to `rows` (tuple_size() bytes each: one null-indicator byte per column, then the
   // slots in AddColumn order).  Returns the number of rows that passed.
   Status AssembleRows(int64_t expected_rows_in_group, std::vector<uint8_t>* rows, int64_t* num_passed);
+  // The same into a tuple buffer of the caller's (the reference materialises into the row batch's tuple memory,
+  // hdfs-parquet-scanner.cc:1151-1168): when that buffer is pinned (fle_host_alloc / fle_host_register) the
+  // survivors' tuples of a row-group batch are copied device -> buffer directly -- no staging copy, which is the
+  // largest single item of a scanner thread's time per row group.  *bytes = tuple bytes written (num_passed *
+  // tuple_size()); a buffer that is too small makes the call fail.
+  Status AssembleRowsInto(int64_t expected_rows_in_group, uint8_t* tuple_buf, size_t capacity, int64_t* num_passed, size_t* bytes);
 
   int tuple_size() const { return tuple_size_; }
   int slot_offset(int idx) const;
@@ -207,6 +213,8 @@ class HdfsParquetScanner {
   std::vector<int> batch_def_col_;   // per column: index of its definition-level column in the NULL program, -1 = none
   int batch_eval_cols_;              // dictionary columns = columns of the plain program
   int batch_ncols_nulls_;            // columns of the NULL program (0: it does not fit, NULL row groups take the page paths)
+  uint8_t* direct_out_ = NULL;       // AssembleRowsInto: the caller's tuple buffer
+  size_t direct_cap_ = 0, direct_used_ = 0;
   bool batch_nulls_seen_;            // an earlier row group of this scanner held NULLs: start with the NULL program
   int64_t row_group_null_batches_;
  public:
@@ -1089,11 +1097,18 @@ inline bool HdfsParquetScanner::DeviceRowGroup(std::vector<uint8_t>* rows, int64
   passed = hdr[1];
   if (passed > 0) {
     const size_t bytes = static_cast<size_t>(passed) * tuple_size_;
-    uint8_t* stage = static_cast<uint8_t*>(FleGpu::PinnedScratch(bank, 1, bytes));
-    if (!stage) return false;
-    if (FleGpu::Check(fle_d2h(ctx, stage, tuples_dev, bytes), "fle_d2h(tuples)") != FLE_OK) return false;
-    if (FleGpu::Check(fle_ctx_sync(ctx), "fle_ctx_sync") != FLE_OK) return false;
-    rows->insert(rows->end(), stage, stage + bytes);
+    if (direct_out_ != NULL && direct_used_ + bytes <= direct_cap_) {
+      // AssembleRowsInto: the tuples land in the caller's (pinned) tuple buffer, no staging copy
+      if (FleGpu::Check(fle_d2h(ctx, direct_out_ + direct_used_, tuples_dev, bytes), "fle_d2h(tuples)") != FLE_OK) return false;
+      if (FleGpu::Check(fle_ctx_sync(ctx), "fle_ctx_sync") != FLE_OK) return false;
+      direct_used_ += bytes;
+    } else {
+      uint8_t* stage = static_cast<uint8_t*>(FleGpu::PinnedScratch(bank, 1, bytes));
+      if (!stage) return false;
+      if (FleGpu::Check(fle_d2h(ctx, stage, tuples_dev, bytes), "fle_d2h(tuples)") != FLE_OK) return false;
+      if (FleGpu::Check(fle_ctx_sync(ctx), "fle_ctx_sync") != FLE_OK) return false;
+      rows->insert(rows->end(), stage, stage + bytes);
+    }
   }
   if (hdr[0] != 0) ++row_group_null_batches_;
   for (int c = 0; c < ncols; ++c) column_readers_[c]->ConsumeAllPages();
@@ -1186,6 +1201,22 @@ inline bool HdfsParquetScanner::FusedWindow(int64_t limit_rows, const std::vecto
   }
   fused_pos_ = pos;
   return true;
+}
+
+inline Status HdfsParquetScanner::AssembleRowsInto(int64_t expected_rows_in_group, uint8_t* tuple_buf, size_t capacity,
+                                                   int64_t* num_passed, size_t* bytes) {
+  direct_out_ = tuple_buf;
+  direct_cap_ = capacity;
+  direct_used_ = 0;
+  std::vector<uint8_t> rest;  // what the page / window paths produce (they append to a vector)
+  Status st = AssembleRows(expected_rows_in_group, &rest, num_passed);
+  direct_out_ = NULL;
+  if (!st.ok()) return st;
+  // (the row-group batch comes first and covers the whole row group when it applies, so `rest` follows the direct bytes)
+  if (direct_used_ + rest.size() > capacity) return Status("AssembleRowsInto: tuple buffer too small");
+  if (!rest.empty()) memcpy(tuple_buf + direct_used_, &rest[0], rest.size());
+  *bytes = direct_used_ + rest.size();
+  return st;
 }
 
 inline Status HdfsParquetScanner::AssembleRows(int64_t expected_rows_in_group, std::vector<uint8_t>* rows,

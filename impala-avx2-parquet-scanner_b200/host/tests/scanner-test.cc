@@ -663,6 +663,43 @@ TEST(Scanner, ConcurrentScannersWithNullsAndRaggedPages) {
   EXPECT_EQ(scans.load(), 24);
 }
 
+// AssembleRowsInto: the same tuples, delivered into the caller's tuple buffer (batch path: device -> buffer directly;
+// page paths: through the vector)
+TEST(Scanner, AssembleRowsIntoCallerBuffer) {
+  for (int batch = 0; batch < 2; ++batch) {
+    Table t = MakeTable(64 * 900 + 5, 0.03, 321 + batch);
+    vector<uint8_t> rows;
+    vector<uint8_t> buf(size_t(t.n) * 32);
+    int64_t passed = 0, passed2 = 0;
+    size_t bytes = 0;
+    for (int into = 0; into < 2; ++into) {
+      ColumnChunk c0 = WriteColumn(t.shipdate, t.nn_shipdate, 20001, true);
+      ColumnChunk c1 = WriteColumn(t.discount, t.nn_discount, 64 * 50, true);
+      ColumnChunk c2 = WriteColumn(t.quantity, t.nn_quantity, 1 << 30, true);
+      HdfsParquetScanner scanner;
+      int i0 = scanner.AddColumn<int32_t>(1, &c0.dict_page[0], c0.dict_page.size(), c0.pages);
+      int i1 = scanner.AddColumn<int32_t>(1, &c1.dict_page[0], c1.dict_page.size(), c1.pages);
+      int i2 = scanner.AddColumn<int32_t>(1, &c2.dict_page[0], c2.dict_page.size(), c2.pages);
+      GeOperate<int32_t> ge0(i0, 8730);
+      LeOperate<int32_t> le1(i1, 7);
+      LtOperate<int32_t> lt2(i2, 24);
+      scanner.AddSimplePredicate(&ge0);
+      scanner.AddSimplePredicate(&le1);
+      scanner.AddSimplePredicate(&lt2);
+      scanner.set_row_group_batch(batch != 0);
+      if (into) {
+        EXPECT_TRUE(scanner.AssembleRowsInto(t.n, &buf[0], buf.size(), &passed2, &bytes).ok());
+        EXPECT_EQ((int64_t)bytes, passed2 * scanner.tuple_size());
+      } else {
+        EXPECT_TRUE(scanner.AssembleRows(t.n, &rows, &passed).ok());
+      }
+      EXPECT_EQ(scanner.row_group_batches(), batch);
+    }
+    EXPECT_EQ((int64_t)bytes, (int64_t)rows.size());
+    EXPECT_TRUE(bytes == rows.size() && memcmp(&buf[0], &rows[0], bytes) == 0);
+  }
+}
+
 // The deviations DESIGN.md lists, pinned in both modes (the reference lines are cited in util/fle-gpu-context.h)
 TEST(Scanner, ReferenceCompatSwitch) {
   // 1. Skip() landing exactly on the end of the data (fle-encoding.h:381-402)
