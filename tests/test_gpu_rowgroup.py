@@ -440,3 +440,29 @@ def test_pages_gather_mixed_dictionary_and_plain_chunk(ctx, oracle, size, null_f
     torch.cuda.synchronize()
     got = values.cpu().numpy().view(dt)[:total]
     assert (got == np.concatenate(want_vals)).all()
+
+
+def test_prefetch_marks(ctx, oracle):
+    """fle_h2d_prefetch + fle_prefetch_mark / fle_prefetch_wait: two uploads on the copy stream, each evaluated behind its
+    own mark (the second upload is enqueued BEFORE the first evaluation, as a scanner does); fence and error cases."""
+    import torch
+    import fle_b200
+    from oracle.oracle import LT
+    lib, h = ctx.lib, ctx.h
+    rng = np.random.default_rng(21)
+    n, bw = 64 * 3000 + 5, 9
+    vals = [rng.integers(0, 1 << bw, size=n).astype(np.uint32) for _ in range(2)]
+    words = [oracle.pack(v, bw) for v in vals]
+    host = [torch.from_numpy(w.view(np.int64)).pin_memory() for w in words]
+    dev = [torch.empty_like(hh, device="cuda") for hh in host]
+    for k in range(2):
+        assert lib.fle_h2d_prefetch(h, dev[k].data_ptr(), host[k].data_ptr(), host[k].numel() * 8) == 0
+        assert lib.fle_prefetch_mark(h, k) == 0
+    for k in range(2):
+        assert lib.fle_prefetch_wait(h, k) == 0
+        bm, cnt = ctx.eval_dev([(dev[k], bw)], [(LT, 0, 100)], n)
+        torch.cuda.synchronize()
+        assert int(cnt.item()) == int((vals[k] < 100).sum())
+    assert lib.fle_prefetch_fence(h) == 0
+    assert lib.fle_prefetch_wait(h, 7) == fle_b200.capi.E_INVALID   # never marked
+    assert lib.fle_prefetch_mark(h, 8) == fle_b200.capi.E_INVALID   # slots 0..7
