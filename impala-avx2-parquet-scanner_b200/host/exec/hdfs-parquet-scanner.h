@@ -213,6 +213,18 @@ class HdfsParquetScanner {
   std::vector<int> batch_def_col_;   // per column: index of its definition-level column in the NULL program, -1 = none
   int batch_eval_cols_;              // dictionary columns = columns of the plain program
   int batch_ncols_nulls_;            // columns of the NULL program (0: it does not fit, NULL row groups take the page paths)
+  // what EnqueueRowGroup set up: the row group's kernels are enqueued by StartRowGroupUpload already (on the bank's own
+  // context), so that they run as soon as its column chunks have arrived -- while the host still fetches the previous
+  // row group's tuples
+  std::vector<fle_col_desc> batch_eval_desc_;
+  std::vector<fle_slot_desc> batch_slots_;
+  uint64_t* batch_bitmap_dev_ = NULL;
+  uint64_t* batch_hdr_dev_ = NULL;   // [0] NULL rows, [1] survivors, [2] bad codes
+  uint64_t* batch_hdr_ = NULL;       // pinned copy
+  uint8_t* batch_tuples_dev_ = NULL;
+  bool batch_enqueued_ = false, batch_enqueued_nulls_ = false;
+  bool batch_placed_ = false;        // the pages were placed and the descriptors built (a later evaluation reuses them)
+  bool EnqueueRowGroup(bool with_nulls, bool first);
   uint8_t* direct_out_ = NULL;       // AssembleRowsInto: the caller's tuple buffer
   size_t direct_cap_ = 0, direct_used_ = 0;
   bool batch_nulls_seen_;            // an earlier row group of this scanner held NULLs: start with the NULL program
@@ -861,9 +873,10 @@ inline bool HdfsParquetScanner::StartRowGroupUpload() {
     nd.col = batch_cols_[nd.col].eval_col;
   }
   if (batch_eval_cols_ == 0) return false;
-  fle_ctx* ctx = FleGpu::ctx();
-  if (ctx == NULL) return false;
+  if (FleGpu::ctx() == NULL) return false;
   batch_bank_ = FleGpu::NextBank();
+  fle_ctx* ctx = FleGpu::bank_ctx(batch_bank_);
+  if (ctx == NULL) return false;
   batch_refs_.clear();
   const int64_t total_groups = (total_rows + 63) / 64;
   for (int c = 0; c < ncols; ++c) {
@@ -1015,77 +1028,102 @@ inline bool HdfsParquetScanner::StartRowGroupUpload() {
   if (FleGpu::Check(fle_prefetch_mark(ctx, batch_bank_), "fle_prefetch_mark") != FLE_OK) return false;
   batch_rows_ = total_rows;
   batch_state_ = 1;
+  // the row group's kernels right behind its upload (nothing here waits; a failure is looked at by DeviceRowGroup)
+  batch_enqueued_nulls_ = batch_nulls_seen_ && batch_ncols_nulls_ > 0;
+  batch_enqueued_ = EnqueueRowGroup(batch_enqueued_nulls_, true);
+  return true;
+}
+
+// gather + evaluation + tuple assembly + the counts on their way back, all enqueued on the bank's context; first: also
+// the wait for the row group's upload and the page placement (a second evaluation, with the NULL program, reuses them)
+inline bool HdfsParquetScanner::EnqueueRowGroup(bool with_nulls, bool first) {
+  fle_ctx* ctx = FleGpu::bank_ctx(batch_bank_);
+  if (ctx == NULL) return false;
+  const int ncols = static_cast<int>(column_readers_.size());
+  const int64_t n = batch_rows_, groups = (n + 63) / 64;
+  const int bank = batch_bank_;
+  if (first) {
+    batch_bitmap_dev_ = static_cast<uint64_t*>(FleGpu::DeviceScratch(bank, 40, static_cast<size_t>(groups) * 8 + 64));
+    batch_hdr_dev_ = static_cast<uint64_t*>(FleGpu::DeviceScratch(bank, 41, 64));
+    batch_hdr_ = static_cast<uint64_t*>(FleGpu::PinnedScratch(bank, 0, 64));
+    // tuples: room for every row (grow-only scratch; only the survivors' bytes come back)
+    batch_tuples_dev_ = static_cast<uint8_t*>(FleGpu::DeviceScratch(bank, 42, static_cast<size_t>(n) * tuple_size_ + 64));
+    if (!batch_bitmap_dev_ || !batch_hdr_dev_ || !batch_hdr_ || !batch_tuples_dev_) return false;
+    // (this row group's uploads only: the next row group's keep crossing PCIe meanwhile)
+    if (FleGpu::Check(fle_prefetch_wait(ctx, bank), "fle_prefetch_wait") != FLE_OK) return false;
+    if (FleGpu::Check(fle_pages_gather_dev(ctx, &batch_refs_[0], static_cast<int>(batch_refs_.size()), batch_hdr_dev_), "fle_pages_gather_dev") != FLE_OK) return false;
+    std::vector<fle_col_desc>& cols = batch_eval_desc_;
+    std::vector<fle_slot_desc>& slots = batch_slots_;
+    cols.assign(std::max(batch_eval_cols_, batch_ncols_nulls_), fle_col_desc());
+    slots.assign(ncols, fle_slot_desc());
+    for (int c = 0; c < ncols; ++c) {
+      BaseColumnReader* r = column_readers_[c];
+      memset(&slots[c], 0, sizeof(fle_slot_desc));
+      if (batch_cols_[c].plain) {
+        slots[c].plain_values_dev = batch_cols_[c].planes_dev;
+        slots[c].bytes = static_cast<uint64_t>(groups) * 64 * r->slot_size_;
+      } else {
+        fle_col_desc& e = cols[batch_cols_[c].eval_col];
+        memset(&e, 0, sizeof(fle_col_desc));
+        e.planes = batch_cols_[c].planes_dev;
+        e.bytes = static_cast<uint64_t>(groups) * batch_cols_[c].bit_width * 8;
+        e.bit_width = batch_cols_[c].bit_width;
+        slots[c].planes_dev = batch_cols_[c].planes_dev;
+        slots[c].bytes = e.bytes;
+      }
+      slots[c].bit_width = batch_cols_[c].bit_width;
+      slots[c].slot_size = r->slot_size_;
+      slots[c].dict_dev = batch_cols_[c].dict_dev;
+      slots[c].ndict = batch_cols_[c].ndict;
+      slots[c].tuple_offset = r->tuple_offset_;
+      slots[c].def_planes_dev = batch_cols_[c].def_dev;  // a survivor that is NULL here gets its indicator set (ReadSlot)
+      slots[c].null_offset = r->null_offset_;
+      if (batch_ncols_nulls_ > 0 && batch_def_col_[c] >= 0) {
+        fle_col_desc& d = cols[batch_def_col_[c]];
+        memset(&d, 0, sizeof(fle_col_desc));
+        d.planes = batch_cols_[c].def_dev;
+        d.bytes = static_cast<uint64_t>(groups) * 8;
+        d.bit_width = 1;
+      }
+    }
+    batch_placed_ = true;
+  }
+  int rc = with_nulls ? fle_eval_dev(ctx, &batch_eval_desc_[0], batch_ncols_nulls_, &batch_prog_nulls_[0], static_cast<int>(batch_prog_nulls_.size()), 0, n, batch_bitmap_dev_, NULL)
+                      : fle_eval_dev(ctx, &batch_eval_desc_[0], batch_eval_cols_, &batch_prog_.nodes[0], static_cast<int>(batch_prog_.nodes.size()), 0, n, batch_bitmap_dev_, NULL);
+  if (rc == FLE_E_UNSUPPORTED) return false;
+  if (FleGpu::Check(rc, "fle_eval_dev(row group)") != FLE_OK) return false;
+  rc = fle_assemble_rows_dev(ctx, batch_bitmap_dev_, n, &batch_slots_[0], ncols, tuple_size_, batch_tuples_dev_, n, batch_hdr_dev_ + 1, batch_hdr_dev_ + 2);
+  if (FleGpu::Check(rc, "fle_assemble_rows_dev") != FLE_OK) return false;
+  if (FleGpu::Check(fle_d2h(ctx, batch_hdr_, batch_hdr_dev_, 24), "fle_d2h(counts)") != FLE_OK) return false;
   return true;
 }
 
 inline bool HdfsParquetScanner::DeviceRowGroup(std::vector<uint8_t>* rows, int64_t* num_passed, int64_t* span_rows) {
   if (!StartRowGroupUpload()) return false;
   batch_state_ = -1;  // one shot: whatever happens below, the batch is not retried
-  fle_ctx* ctx = FleGpu::ctx();
+  const int bank = batch_bank_;
+  fle_ctx* ctx = FleGpu::bank_ctx(bank);
   if (ctx == NULL) return false;
   const int ncols = static_cast<int>(column_readers_.size());
-  const int64_t n = batch_rows_, groups = (n + 63) / 64;
-  const int bank = batch_bank_;
-  uint64_t* bitmap_dev = static_cast<uint64_t*>(FleGpu::DeviceScratch(bank, 40, static_cast<size_t>(groups) * 8 + 64));
-  uint64_t* hdr_dev = static_cast<uint64_t*>(FleGpu::DeviceScratch(bank, 41, 64));  // [0] NULL rows, [1] survivors, [2] bad codes
-  uint64_t* hdr = static_cast<uint64_t*>(FleGpu::PinnedScratch(bank, 0, 64));
-  if (!bitmap_dev || !hdr_dev || !hdr) return false;
-  // (this row group's uploads only: the next row group's, enqueued before these kernels, keep crossing PCIe meanwhile)
-  if (FleGpu::Check(fle_prefetch_wait(ctx, bank), "fle_prefetch_wait") != FLE_OK) return false;
-  if (FleGpu::Check(fle_pages_gather_dev(ctx, &batch_refs_[0], static_cast<int>(batch_refs_.size()), hdr_dev), "fle_pages_gather_dev") != FLE_OK) return false;
-  std::vector<fle_col_desc> cols(std::max(batch_eval_cols_, batch_ncols_nulls_));
-  std::vector<fle_slot_desc> slots(ncols);
-  for (int c = 0; c < ncols; ++c) {
-    BaseColumnReader* r = column_readers_[c];
-    memset(&slots[c], 0, sizeof(fle_slot_desc));
-    if (batch_cols_[c].plain) {
-      slots[c].plain_values_dev = batch_cols_[c].planes_dev;
-      slots[c].bytes = static_cast<uint64_t>(groups) * 64 * r->slot_size_;
-    } else {
-      fle_col_desc& e = cols[batch_cols_[c].eval_col];
-      memset(&e, 0, sizeof(fle_col_desc));
-      e.planes = batch_cols_[c].planes_dev;
-      e.bytes = static_cast<uint64_t>(groups) * batch_cols_[c].bit_width * 8;
-      e.bit_width = batch_cols_[c].bit_width;
-      slots[c].planes_dev = batch_cols_[c].planes_dev;
-      slots[c].bytes = e.bytes;
-    }
-    slots[c].bit_width = batch_cols_[c].bit_width;
-    slots[c].slot_size = r->slot_size_;
-    slots[c].dict_dev = batch_cols_[c].dict_dev;
-    slots[c].ndict = batch_cols_[c].ndict;
-    slots[c].tuple_offset = r->tuple_offset_;
-    slots[c].def_planes_dev = batch_cols_[c].def_dev;  // a survivor that is NULL here gets its indicator set (ReadSlot)
-    slots[c].null_offset = r->null_offset_;
-    if (batch_ncols_nulls_ > 0 && batch_def_col_[c] >= 0) {
-      fle_col_desc& d = cols[batch_def_col_[c]];
-      memset(&d, 0, sizeof(fle_col_desc));
-      d.planes = batch_cols_[c].def_dev;
-      d.bytes = static_cast<uint64_t>(groups) * 8;
-      d.bit_width = 1;
-    }
-  }
-  // tuples: room for every row (grow-only scratch; only the survivors' bytes come back)
-  uint8_t* tuples_dev = static_cast<uint8_t*>(FleGpu::DeviceScratch(bank, 42, static_cast<size_t>(n) * tuple_size_ + 64));
-  if (!tuples_dev) return false;
+  const int64_t n = batch_rows_;
   // A row group without NULLs (every Impala-written TPC-H file) is the plain program over the row-aligned planes.
   // NULLs are only known once the counts are back: the evaluation is then repeated with the NULL program, and the
   // scanner starts with that one from its next row group on.
-  bool with_nulls = batch_nulls_seen_ && batch_ncols_nulls_ > 0;
+  bool with_nulls = batch_enqueued_nulls_;
+  if (!batch_enqueued_) {
+    with_nulls = batch_nulls_seen_ && batch_ncols_nulls_ > 0;
+    if (!EnqueueRowGroup(with_nulls, !batch_placed_)) return false;
+  }
+  uint64_t* hdr = batch_hdr_;
+  uint8_t* tuples_dev = batch_tuples_dev_;
   uint64_t passed = 0;
   for (;;) {
-    int rc = with_nulls ? fle_eval_dev(ctx, &cols[0], batch_ncols_nulls_, &batch_prog_nulls_[0], static_cast<int>(batch_prog_nulls_.size()), 0, n, bitmap_dev, NULL)
-                        : fle_eval_dev(ctx, &cols[0], batch_eval_cols_, &batch_prog_.nodes[0], static_cast<int>(batch_prog_.nodes.size()), 0, n, bitmap_dev, NULL);
-    if (rc == FLE_E_UNSUPPORTED) return false;
-    if (FleGpu::Check(rc, "fle_eval_dev(row group)") != FLE_OK) return false;
-    rc = fle_assemble_rows_dev(ctx, bitmap_dev, n, &slots[0], ncols, tuple_size_, tuples_dev, n, hdr_dev + 1, hdr_dev + 2);
-    if (FleGpu::Check(rc, "fle_assemble_rows_dev") != FLE_OK) return false;
-    if (FleGpu::Check(fle_d2h(ctx, hdr, hdr_dev, 24), "fle_d2h(counts)") != FLE_OK) return false;
     if (FleGpu::Check(fle_ctx_sync(ctx), "fle_ctx_sync") != FLE_OK) return false;
     if (hdr[0] != 0 && !with_nulls) {
       batch_nulls_seen_ = true;
       if (batch_ncols_nulls_ == 0) return false;  // the NULL program does not fit: the page-span / window paths (nothing was consumed)
       with_nulls = true;
+      if (!EnqueueRowGroup(true, false)) return false;
       continue;
     }
     break;

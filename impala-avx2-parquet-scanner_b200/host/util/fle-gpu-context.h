@@ -46,6 +46,26 @@ class FleGpu {
     return h.ctx;
   }
 
+  // A scanner thread keeps two row groups in flight (one uploading and being evaluated while the other one's tuples
+  // are fetched): each of the two scratch banks has a context -- a stream pair -- of its own, so that the work of
+  // one row group never queues behind the other's.  Bank 0 is the thread's main context.
+  static fle_ctx* bank_ctx(int bank) {
+    if ((bank & 1) == 0) return ctx();
+    Holder& h = holder();
+    if (ctx() == NULL) return NULL;
+    if (!h.tried2) {
+      h.tried2 = true;
+      const char* dev = std::getenv("FLE_B200_DEVICE");
+      int rc = fle_ctx_create(dev ? std::atoi(dev) : 0, NULL, &h.ctx2);
+      if (rc != FLE_OK) { h.ctx2 = NULL; Fail(rc, "fle_ctx_create (second bank)"); }
+      if (h.ctx2) {
+        const char* jit = std::getenv("FLE_B200_EVAL_JIT");
+        fle_ctx_set_option(h.ctx2, "eval_jit", jit ? std::atoi(jit) : 3);
+      }
+    }
+    return h.ctx2;
+  }
+
   // Process-wide switch (also FLE_B200_REFERENCE_COMPAT=1): reproduce the reference EXACTLY where the
   // drop-ins deliberately differ from it --
   //   FleDecoder::Skip() landing on the end of the data returns false (fle-encoding.h:381-402), and
@@ -97,7 +117,8 @@ class FleGpu {
   };
   struct Holder {
     fle_ctx* ctx = NULL;
-    bool tried = false;
+    fle_ctx* ctx2 = NULL;  // the second scratch bank's context (bank_ctx)
+    bool tried = false, tried2 = false;
     int status = FLE_OK;
     int compat_applied = 0;
     int next_bank = 0;
@@ -128,6 +149,7 @@ class FleGpu {
         for (size_t i = 0; i < pinned[k].size(); ++i)
           if (pinned[k][i].p) fle_host_free(pinned[k][i].p);
       }
+      if (ctx2) fle_ctx_destroy(ctx2);
       if (ctx) fle_ctx_destroy(ctx);
     }
   };
