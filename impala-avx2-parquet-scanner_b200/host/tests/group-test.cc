@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <thread>
 #include <vector>
 
@@ -242,4 +243,11 @@ TEST(Group, EightMembersDeferredSomeEmpty) {  // more members than row groups' w
   RunGroup(8, true, small);
 }
 
-int main() { return RunAllTests(); }
+int main() {
+  // Several members share ONE device here.  A kernel that meets the driver for the first time is loaded lazily, which
+  // can wait for the device to drain -- while the other members' kernels sit in the exchange waiting for this very
+  // member: they would only get on by timing out (and count a lost peer).  One GPU per member, the library's real
+  // deployment, has no such coupling; on a shared device load everything up front.
+  setenv("CUDA_MODULE_LOADING", "EAGER", 1);
+  return RunAllTests();
+}
