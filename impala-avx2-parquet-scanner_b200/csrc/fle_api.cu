@@ -60,6 +60,25 @@ int ensure_scratch(fle_ctx* ctx, int nblocks, int n_in_lits) {
   return FLE_OK;
 }
 
+// Everything a first launch would allocate lazily -- the per-CTA partials, the literal slots with their pinned twins and
+// events -- allocated now.  cudaMalloc / cudaMallocHost may wait for the device to drain: inside a group call that is
+// a wait for the peers' kernels, which sit in the exchange waiting for THIS member's kernel (they only get on by timing
+// out and count a lost peer).  A member that joins a group therefore allocates up front (fle_group.cu).
+int prime_context(fle_ctx* ctx) {
+  int rc = ensure_scratch(ctx, 4096, 0);
+  if (rc != FLE_OK) return rc;
+  for (int i = 0; i < fle_ctx::kLitSlots; ++i) {
+    fle_ctx::LitSlot& S = ctx->lit_slots[i];
+    if (S.cap == 0) {
+      FLE_CUDA_TRY(ctx, cudaMalloc(&S.d, (size_t)4096 * 4));
+      FLE_CUDA_TRY(ctx, cudaMallocHost(&S.h, (size_t)4096 * 4));
+      S.cap = 4096;
+    }
+    if (!S.ev) FLE_CUDA_TRY(ctx, cudaEventCreateWithFlags(&S.ev, cudaEventDisableTiming));
+  }
+  return FLE_OK;
+}
+
 int upload_literals(fle_ctx* ctx, const void* words, int nwords, int* slot, uint64_t* gen, const uint32_t** dev) {
   const int si = ctx->lit_next;
   ctx->lit_next = (ctx->lit_next + 1) % fle_ctx::kLitSlots;

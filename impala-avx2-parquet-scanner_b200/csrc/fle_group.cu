@@ -128,7 +128,9 @@ static int group_alloc_own(fle_ctx* ctx) {
   // running kernels, and a member's kernel that is waiting for its peers must never be waited for
   cudaFuncAttributes fa;
   FLE_CUDA_TRY(ctx, cudaFuncGetAttributes(&fa, group_reduce_kernel));
-  return FLE_OK;
+  // ... and allocate now what the first launches would allocate lazily: an allocation can wait for the device as well
+  // (a member with an empty row-group range has launched nothing before its first group call)
+  return prime_context(ctx);
 }
 
 void group_release(fle_ctx* ctx) {

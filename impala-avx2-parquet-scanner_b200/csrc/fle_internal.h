@@ -152,6 +152,8 @@ namespace fle {
 int set_cuda_error(fle_ctx* ctx, cudaError_t e, const char* what);
 int set_error(fle_ctx* ctx, int code, const std::string& msg);
 int ensure_scratch(fle_ctx* ctx, int nblocks, int n_in_lits);
+// allocates what a context's first launches would allocate lazily (members of a group must not allocate inside a group call)
+int prime_context(fle_ctx* ctx);
 // copies nwords 32-bit words into the next literal slot (pinned -> device, async on the context's stream);
 // *slot / *gen identify it, *dev is the device address the kernels read
 int upload_literals(fle_ctx* ctx, const void* words, int nwords, int* slot, uint64_t* gen, const uint32_t** dev);

@@ -248,6 +248,6 @@ int main() {
   // can wait for the device to drain -- while the other members' kernels sit in the exchange waiting for this very
   // member: they would only get on by timing out (and count a lost peer).  One GPU per member, the library's real
   // deployment, has no such coupling; on a shared device load everything up front.
-  setenv("CUDA_MODULE_LOADING", "EAGER", 1);
+  setenv("CUDA_MODULE_LOADING", "EAGER", 0);  // (an explicit setting of the caller's wins)
   return RunAllTests();
 }
