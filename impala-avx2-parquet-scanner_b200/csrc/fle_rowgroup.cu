@@ -317,8 +317,9 @@ int launch_pages_gather(fle_ctx* ctx, const fle_page_ref* refs, int nrefs, uint6
 // single-pass ordered compaction of a bitmap (decoupled look-back)
 // ------------------------------------------------------------------------------------------
 constexpr int kTileThreads = 256;
-constexpr int kTileWordsPerThread = 4;
-constexpr int kTileWords = kTileThreads * kTileWordsPerThread;  // 65536 rows per tile
+// words per thread: 4 (65536 rows per tile) for long bitmaps; 1 (16384 rows per tile) where that would leave most SMs
+// without a tile -- a 4 Mi-row row group is 64 tiles of 65536 rows on 148 SMs, and a thread then walks ~5 survivors with
+// a dozen dependent gathers each (assemble: 80 us); with 256 tiles the same work is spread four times wider
 
 // tile status words: [63:40] launch generation, [39:38] 1 = aggregate / 2 = inclusive prefix, [37:0] value.
 // The generation makes entries of earlier launches read as "not there yet": no reset between launches.
@@ -366,8 +367,9 @@ __device__ __forceinline__ uint32_t code_of_row(const uint64_t* __restrict__ pla
   return v;
 }
 
-template <bool ASSEMBLE>
+template <bool ASSEMBLE, int kTileWordsPerThread>
 __global__ void __launch_bounds__(kTileThreads) tile_scan_kernel(const __grid_constant__ TileScanParams P) {
+  constexpr int kTileWords = kTileThreads * kTileWordsPerThread;
   __shared__ uint32_t warp_scan[kTileThreads / 32];
   __shared__ int tile_s;
   __shared__ uint64_t base_s;
@@ -506,6 +508,9 @@ static int launch_tile_scan(fle_ctx* ctx, TileScanParams& P, bool assemble) {
   if (rc0 != FLE_OK) return rc0;
   const int64_t nwords = (P.nbits + 63) / 64;
   P.nwords = nwords;
+  int wpt = 4;
+  if ((nwords + kTileThreads * 4 - 1) / (kTileThreads * 4) < 2 * (int64_t)ctx->num_sms) wpt = 1;
+  const int kTileWords = kTileThreads * wpt;
   P.ntiles = (int)((nwords + kTileWords - 1) / kTileWords);
   if ((size_t)P.ntiles * 8 > ctx->tile_state_cap) {
     const size_t cap = std::max<size_t>((size_t)P.ntiles * 8, 64 << 10);
@@ -528,8 +533,13 @@ static int launch_tile_scan(fle_ctx* ctx, TileScanParams& P, bool assemble) {
   P.tile_state = ctx->d_tile_state;
   P.ticket = ctx->d_ticket;
   const int grid = std::max(1, std::min(P.ntiles, ctx->num_sms * 8));
-  if (assemble) tile_scan_kernel<true><<<grid, kTileThreads, 0, ctx->stream>>>(P);
-  else tile_scan_kernel<false><<<grid, kTileThreads, 0, ctx->stream>>>(P);
+  if (assemble) {
+    if (wpt == 4) tile_scan_kernel<true, 4><<<grid, kTileThreads, 0, ctx->stream>>>(P);
+    else tile_scan_kernel<true, 1><<<grid, kTileThreads, 0, ctx->stream>>>(P);
+  } else {
+    if (wpt == 4) tile_scan_kernel<false, 4><<<grid, kTileThreads, 0, ctx->stream>>>(P);
+    else tile_scan_kernel<false, 1><<<grid, kTileThreads, 0, ctx->stream>>>(P);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(ctx, e, "tile_scan launch");
   ctx->launches += 1;
