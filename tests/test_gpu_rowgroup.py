@@ -39,6 +39,25 @@ def test_single_pass_select(ctx, n, density):
     assert (ids2.cpu().numpy().view(np.uint32)[:min(cap, k)] == want[:min(cap, k)]).all()
 
 
+def test_single_pass_select_long_bitmap(ctx):
+    """Bitmaps long enough for the 65536-row tiles (shorter ones take 16384-row tiles so that every SM gets work)."""
+    import torch
+    n = (1 << 25) + 3
+    g = torch.Generator(device="cuda").manual_seed(9)
+    sel = torch.rand(n, generator=g, device="cuda") < 0.018
+    G = (n + 63) // 64
+    pad = torch.cat([sel, torch.zeros(G * 64 - n, dtype=torch.bool, device="cuda")]).view(G, 64)
+    bm = torch.zeros(G, dtype=torch.int64, device="cuda")
+    for b in range(64):
+        bm |= pad[:, b].to(torch.int64) << b
+    want = torch.nonzero(sel).flatten().to(torch.int32)
+    ids, cnt = ctx.bitmap_select_dev(bm, n)
+    torch.cuda.synchronize()
+    k = int(cnt.item())
+    assert k == want.numel()
+    assert torch.equal(ids[:k].to(torch.int32), want)
+
+
 def test_pages_gather_widths_offsets_and_nulls(ctx, oracle):
     """Pages of one column chunk at odd offsets of the chunk image, written with growing bit widths
     (the reference's writer picks the width per page), gathered into one plane array at the widest width."""
