@@ -31,7 +31,7 @@ EXPORTS = [
     "fle_intersect_bitset_dev", "fle_bitmap_select_dev", "fle_gather_dev", "fle_sum_product_dev",
     "fle_page_parse", "fle_realign_dev", "fle_plain_eval_dev", "fle_dict_encode_dev", "fle_eval_codegen",
     "fle_eval_sum_product_dev", "fle_group_create_local", "fle_group_export", "fle_group_open", "fle_group_close",
-    "fle_h2d_prefetch", "fle_prefetch_fence", "fle_prefetch_mark", "fle_prefetch_wait", "fle_host_register", "fle_host_unregister", "fle_pages_gather_dev",
+    "fle_h2d_prefetch", "fle_prefetch_fence", "fle_prefetch_mark", "fle_prefetch_wait", "fle_ctx_share_copy_stream", "fle_host_register", "fle_host_unregister", "fle_pages_gather_dev",
     "fle_assemble_rows_dev", "fle_group_status", "fle_group_flush", "fle_eval_group_dev", "fle_eval_sum_product_group_dev",
 ]
 GROUP_HANDLE_BYTES = 64
@@ -145,6 +145,7 @@ def load_library() -> C.CDLL:
     L.fle_prefetch_fence.argtypes = [vp]
     L.fle_prefetch_mark.argtypes = [vp, i32]
     L.fle_prefetch_wait.argtypes = [vp, i32]
+    L.fle_ctx_share_copy_stream.argtypes = [vp, vp]
     L.fle_host_register.argtypes = [vp, C.c_size_t]
     L.fle_host_unregister.argtypes = [vp]
     L.fle_pages_gather_dev.argtypes = [vp, C.POINTER(PageRef), i32, vp]

@@ -1106,14 +1106,23 @@ int fle_h2d_prefetch(fle_ctx* ctx, void* dst_dev, const void* src_host, size_t b
   FLE_CHECK_CTX(ctx);
   if (bytes == 0) return FLE_OK;
   if (!dst_dev || !src_host) return set_error(ctx, FLE_E_INVALID, "null pointer");
-  FLE_CUDA_TRY(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+  fle_ctx* c = ctx->copy_owner ? ctx->copy_owner : ctx;
+  FLE_CUDA_TRY(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+  return FLE_OK;
+}
+
+int fle_ctx_share_copy_stream(fle_ctx* ctx, fle_ctx* owner) {
+  FLE_CHECK_CTX(ctx);
+  if (owner == ctx) owner = nullptr;
+  if (owner && (owner->device != ctx->device || owner->copy_owner)) return set_error(ctx, FLE_E_INVALID, "the copy stream's owner must be a context of the same device with a copy stream of its own");
+  ctx->copy_owner = owner;
   return FLE_OK;
 }
 
 int fle_prefetch_fence(fle_ctx* ctx) {
   FLE_CHECK_CTX(ctx);
   if (!ctx->ev_prefetch) FLE_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_prefetch, cudaEventDisableTiming));
-  FLE_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_prefetch, ctx->copy_stream));
+  FLE_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_prefetch, (ctx->copy_owner ? ctx->copy_owner : ctx)->copy_stream));
   FLE_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_prefetch, 0));
   return FLE_OK;
 }
@@ -1121,16 +1130,18 @@ int fle_prefetch_fence(fle_ctx* ctx) {
 int fle_prefetch_mark(fle_ctx* ctx, int slot) {
   FLE_CHECK_CTX(ctx);
   if (slot < 0 || slot >= fle_ctx::kPrefetchMarks) return set_error(ctx, FLE_E_INVALID, "prefetch mark outside 0..7");
-  if (!ctx->ev_mark[slot]) FLE_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_mark[slot], cudaEventDisableTiming));
-  FLE_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_mark[slot], ctx->copy_stream));
+  fle_ctx* c = ctx->copy_owner ? ctx->copy_owner : ctx;
+  if (!c->ev_mark[slot]) FLE_CUDA_TRY(ctx, cudaEventCreateWithFlags(&c->ev_mark[slot], cudaEventDisableTiming));
+  FLE_CUDA_TRY(ctx, cudaEventRecord(c->ev_mark[slot], c->copy_stream));
   return FLE_OK;
 }
 
 int fle_prefetch_wait(fle_ctx* ctx, int slot) {
   FLE_CHECK_CTX(ctx);
   if (slot < 0 || slot >= fle_ctx::kPrefetchMarks) return set_error(ctx, FLE_E_INVALID, "prefetch mark outside 0..7");
-  if (!ctx->ev_mark[slot]) return set_error(ctx, FLE_E_INVALID, "fle_prefetch_wait before fle_prefetch_mark");
-  FLE_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_mark[slot], 0));
+  fle_ctx* c = ctx->copy_owner ? ctx->copy_owner : ctx;
+  if (!c->ev_mark[slot]) return set_error(ctx, FLE_E_INVALID, "fle_prefetch_wait before fle_prefetch_mark");
+  FLE_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, c->ev_mark[slot], 0));
   return FLE_OK;
 }
 

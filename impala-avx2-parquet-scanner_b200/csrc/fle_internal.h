@@ -129,6 +129,7 @@ struct fle_ctx {
   size_t tile_state_cap = 0;  // bytes
   uint32_t tile_gen = 0;
   cudaEvent_t ev_prefetch = nullptr;  // last fle_h2d_prefetch on the copy stream
+  fle_ctx* copy_owner = nullptr;      // fle_ctx_share_copy_stream: prefetches and marks go through this context's copy stream
   static constexpr int kPrefetchMarks = 8;
   cudaEvent_t ev_mark[kPrefetchMarks] = {nullptr};  // fle_prefetch_mark / fle_prefetch_wait
 

@@ -53,6 +53,9 @@
 #include <algorithm>
 #include <memory>
 #include <string>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include <boost/dynamic_bitset.hpp>
@@ -1098,6 +1101,8 @@ inline bool HdfsParquetScanner::EnqueueRowGroup(bool with_nulls, bool first) {
   return true;
 }
 
+inline double TraceNow() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 inline bool HdfsParquetScanner::DeviceRowGroup(std::vector<uint8_t>* rows, int64_t* num_passed, int64_t* span_rows) {
   if (!StartRowGroupUpload()) return false;
   batch_state_ = -1;  // one shot: whatever happens below, the batch is not retried
@@ -1117,6 +1122,8 @@ inline bool HdfsParquetScanner::DeviceRowGroup(std::vector<uint8_t>* rows, int64
   uint64_t* hdr = batch_hdr_;
   uint8_t* tuples_dev = batch_tuples_dev_;
   uint64_t passed = 0;
+  static const bool trace = std::getenv("FLE_SCANNER_TRACE") != NULL;
+  const double t_sync0 = trace ? TraceNow() : 0;
   for (;;) {
     if (FleGpu::Check(fle_ctx_sync(ctx), "fle_ctx_sync") != FLE_OK) return false;
     if (hdr[0] != 0 && !with_nulls) {
@@ -1128,6 +1135,7 @@ inline bool HdfsParquetScanner::DeviceRowGroup(std::vector<uint8_t>* rows, int64
     }
     break;
   }
+  const double t_sync1 = trace ? TraceNow() : 0;
   if (hdr[2] != 0) {
     parse_status_ = Status("dictionary index out of range");
     return false;
@@ -1147,6 +1155,11 @@ inline bool HdfsParquetScanner::DeviceRowGroup(std::vector<uint8_t>* rows, int64
       if (FleGpu::Check(fle_ctx_sync(ctx), "fle_ctx_sync") != FLE_OK) return false;
       rows->insert(rows->end(), stage, stage + bytes);
     }
+  }
+  if (trace) {
+    const double t_end = TraceNow();
+    std::fprintf(stderr, "scanner trace: wait for the row group %.1f us, tuples back %.1f us (%llu survivors)\n", (t_sync1 - t_sync0) * 1e6,
+                 (t_end - t_sync1) * 1e6, (unsigned long long)passed);
   }
   if (hdr[0] != 0) ++row_group_null_batches_;
   for (int c = 0; c < ncols; ++c) column_readers_[c]->ConsumeAllPages();

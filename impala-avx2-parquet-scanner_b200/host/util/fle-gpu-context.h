@@ -61,6 +61,8 @@ class FleGpu {
       if (h.ctx2) {
         const char* jit = std::getenv("FLE_B200_EVAL_JIT");
         fle_ctx_set_option(h.ctx2, "eval_jit", jit ? std::atoi(jit) : 3);
+        // one copy stream for both banks: the uploads cross PCIe one after the other, in the order they are needed
+        fle_ctx_share_copy_stream(h.ctx2, h.ctx);
       }
     }
     return h.ctx2;

@@ -289,6 +289,12 @@ int fle_prefetch_fence(fle_ctx* ctx);
  * have arrived (hdfs-parquet-scanner.cc:1078-1275 reads one row group at a time; this is the overlap around it). */
 int fle_prefetch_mark(fle_ctx* ctx, int slot);
 int fle_prefetch_wait(fle_ctx* ctx, int slot);
+/* Makes ctx upload through owner's copy stream (and use owner's marks): a scanner thread that keeps two row groups in
+ * flight on two contexts -- so that neither's kernels queue behind the other's (hdfs-parquet-scanner.cc:1078-1275
+ * handles one row group at a time; this is the overlap around it) -- still wants its uploads to cross PCIe ONE AFTER
+ * THE OTHER: two copy streams share the link, and the row group that is needed first arrives last.  owner = NULL (or
+ * ctx itself) undoes it.  owner must outlive ctx's use of it; same device. */
+int fle_ctx_share_copy_stream(fle_ctx* ctx, fle_ctx* owner);
 /* Pins / unpins an existing host range (e.g. the I/O buffers the pages are read into) in place. */
 int fle_host_register(void* p, size_t bytes);
 int fle_host_unregister(void* p);
