@@ -13,6 +13,7 @@ timeout 600 python tools/in_sweep.py --out $out/${tag}_in_sweep.txt > /dev/null 
 timeout 900 python tools/sweep.py programs nulls --rows 600037902 --out $out/${tag}_sweep_programs_600M_rows.jsonl > /dev/null 2> $out/${tag}_sweep_programs.err
 timeout 300 python tools/narrow_unpack_probe.py > $out/${tag}_narrow_unpack.txt 2>&1
 timeout 300 python tools/codec_cold_probe.py > $out/${tag}_codec_cold.txt 2>&1
+timeout 300 python tools/dict_probe.py > $out/${tag}_dict_probe.txt 2>&1
 timeout 600 python tools/sweep.py aux --rows 268435456 --out $out/${tag}_sweep_aux.jsonl > /dev/null 2> $out/${tag}_sweep_aux.err
 # launch list of the bench command (shares, not absolutes)
 timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/${tag}_bench_launches.csv \
